@@ -1,0 +1,145 @@
+/*
+ * mepp_b200.h -- C ABI of the B200-native MEPP profiling hot path.
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  Every entry point
+ * replaces one piece of the reference's (npdeloss/mepp) per-task profiling path;
+ * the reference interface each one stands in for is cited as file:line into the
+ * reference tree.  All "dev" pointers are CUDA device pointers on the current
+ * device; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *
+ * Return value: 0 on success, non-zero on error; mepp_last_error() returns a
+ * thread-local message.  Nothing here falls back to the CPU: device entry points
+ * fail when no CUDA device / sm_100a is present.
+ *
+ * Data layouts (all little-endian):
+ *   N        number of sequences, L sequence length (all equal, utils.py:85-88)
+ *   n_pad    N rounded up to a multiple of 32 (one "k-block" = 32 sequences)
+ *   codes_T  uint32 [Wc][n_pad], Wc = ceil(L/16)+2 : base i of sequence n is the
+ *            2-bit field (i%16) of word [i/16][n]; A=0 C=1 G=2 T=3 (onehot_dna.py:3)
+ *   nmask_T  uint32 [Wm][n_pad], Wm = ceil(L/32)+2 : bit (i%32) of word [i/32][n]
+ *            is 1 when base i is not an upper-case ACGT (onehot_dna.py:23-30 "N" rule)
+ *   X planes the match matrix as GEMM operand A, fp16 hi/lo split, tiled:
+ *            [m_tile][k_block][plane 2][kc 4][row 128][8 seq] halves, row = task*L + position
+ *   Y planes the (1+P) score columns as GEMM operand B, same tiling with BN columns:
+ *            [n_tile][k_block][plane 2][kc 4][col BN][8 seq] halves
+ */
+#ifndef MEPP_B200_H
+#define MEPP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MEPP_B200_ABI_VERSION 1
+#define MEPP_MAX_MOTIF_LEN 32   /* taps held in a 64-bit code window */
+#define MEPP_MAX_MARGIN 16
+#define MEPP_X_SCALE 256.0f     /* X is stored as 256*x in the fp16 planes (exact) */
+
+int         mepp_abi_version(void);
+const char* mepp_last_error(void);
+/* 1 when a CUDA device with compute capability 10.x is present. */
+int         mepp_device_ok(void);
+
+/* ------------------------------------------------------------------ host side
+ * MOODS.tools.log_odds / threshold_from_p as called at motif_layers.py:37-48.
+ * pwm, W: row-major 4 x m (rows A,C,G,T).  bg: 4 doubles.  Pure host code. */
+int mepp_log_odds(const double* pwm, int m, const double* bg, double pseudocount, double* W);
+int mepp_threshold_from_p(const double* W, int m, const double* bg, double pvalue,
+                          double dp_precision, double* thr);
+
+/* Per-task scan table from a 4 x m PWM and an orientation ('+', '-', anything else =
+ * dual), replacing motif_matrix_to_conv1d_layer (motif_layers.py:12-78):
+ *   lut   float [MEPP_MAX_MOTIF_LEN][4][2]  (tap, base, filter) float32 weights, zero padded
+ *   bias  float32(-thr)  ; n_filters 1 or 2 ; thr double (for reporting)
+ * use_flags: 0 = reproduce the reference (pseudocount/pvalue/bg never reach MOODS,
+ * core.py:513-534, so 1e-4 / 1e-4 / flat are used); 1 = honour the arguments. */
+int mepp_motif_table(const double* pwm, int m, int orientation_char,
+                     double pseudocount, double pvalue, const double* bg, int use_flags,
+                     double dp_precision,
+                     float* lut, float* bias, int* n_filters, double* thr);
+
+/* ------------------------------------------------------------------ layout sizes */
+int64_t mepp_codes_words(int L);            /* Wc */
+int64_t mepp_nmask_words(int L);            /* Wm */
+int64_t mepp_pad32(int64_t n);              /* n_pad */
+int64_t mepp_x_planes_bytes(int64_t m_rows, int64_t n_pad);
+int     mepp_choose_bn(int C, int* n_tiles_n);  /* column tile width (multiple of 32, <=256) */
+int64_t mepp_y_planes_bytes(int C, int64_t n_pad);
+
+/* ------------------------------------------------------------------ K0: pack
+ * Replaces seq_to_mat / scored_fasta_df_to_dataset one-hot (onehot_dna.py:61-70,
+ * utils.py:141-194) and append_gc_ratios_to_dataset('global') (utils.py:275-308).
+ * ascii_dev: uint8 [N][L].  gc_dev: float [n_pad] (z, 0 for padding). */
+int mepp_pack_dna(const uint8_t* ascii_dev, int64_t N, int L,
+                  uint32_t* codes_T_dev, uint32_t* nmask_T_dev, float* gc_dev, void* stream);
+
+/* ------------------------------------------------------------------ Y operand
+ * Replaces add_permuted_scores_to_dataset (permutations.py:5-58).
+ * yhat_dev: float [N] centred+scaled scores (host does the float64 centring);
+ * perm_dev: int32 [P][N] permutation indices (explicit: the reference's shuffle is
+ * unseeded); zhat_dev: float [n_pad] centred GC covariate or NULL.
+ * Outputs: y_planes (tiled fp16 hi/lo, zero padded), col_syz double [C] = sum_n y_c z,
+ * ysum double[2] = {sum y, sum y^2} of the split-rounded values (same for every column). */
+int mepp_build_y(const float* yhat_dev, const int32_t* perm_dev, const float* zhat_dev,
+                 int64_t N, int P, void* y_planes_dev, double* col_syz_dev, double* ysum_dev,
+                 void* stream);
+
+/* ------------------------------------------------------------------ K1: scan
+ * Replaces the conv model + ReLU + margin blur + counts/density
+ * (motif_layers.py:80-165, core.py:25-145, core.py:415-470) for a group of T tasks.
+ *   lut_dev   float [T][MEPP_MAX_MOTIF_LEN][4][2]   bias_dev float [T]
+ *   mlen_dev  int32 [T]   nfilt_dev int32 [T]
+ *   x_planes_dev  A operand (rows t*L+l), written densely
+ *   rowstats_dev  double [T*L][3]: sum_n x, sum_n x^2, sum_n x*zhat  (x = blurred score); zeroed by the call
+ *   count_dev     int32 [T*L]  : #sequences with an unsmoothed match at each position; zeroed by the call
+ *   density_dev   int32 [T][n_pad]: #matches per sequence
+ *   hits_dev      optional: {int32 task, int32 seq, int32 pos, float x0} records, capacity hits_cap,
+ *                 hit_count_dev int64[1] total number of matches (may exceed cap); NULL to skip */
+int mepp_scan(const uint32_t* codes_T_dev, const uint32_t* nmask_T_dev, const float* zhat_dev,
+              int64_t N, int L, int T, int margin,
+              const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev, const int32_t* nfilt_dev,
+              void* x_planes_dev, double* rowstats_dev, int32_t* count_dev, int32_t* density_dev,
+              void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev, void* stream);
+
+/* ------------------------------------------------------------------ K2: profile GEMM
+ * S[r][c] = sum_n X[r][n] * Y[n][c] on tcgen05 tensor cores (fp16 hi/lo split, 3 products,
+ * fp32 TMEM accumulators); replaces the (B,L,1+P) x*y reduce_sum of core.py:250.
+ * S_dev: float [m_rows][ldS], ldS = n_tiles_n*BN. */
+int mepp_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float* S_dev,
+                      int64_t m_rows, int C, int64_t n_pad, void* stream);
+/* CUDA-core cross-check of the same contraction from the same planes (float64 accumulate). */
+int mepp_profile_gemm_check(const void* x_planes_dev, const void* y_planes_dev, double* S_dev,
+                            int64_t m_rows, int C, int64_t n_pad,
+                            const int32_t* rows_dev, int n_rows_sel, void* stream);
+
+/* ------------------------------------------------------------------ correlation epilogue
+ * core.py:182-267 (Pearson / partial correlation) + np.nan_to_num (core.py:602).
+ * r_dev: float [m_rows][C].  use_z: 1 = partial correlation controlling z. */
+int mepp_correlation(const float* S_dev, int64_t ldS, const double* rowstats_dev,
+                     const double* col_syz_dev, const double* ysum_dev, const double* zsum_host2,
+                     int64_t N, int64_t m_rows, int C, int use_z, float* r_dev, void* stream);
+
+/* ------------------------------------------------------------------ K3: permutation statistics
+ * core.py:269-376 for T tasks of L positions and C = 1+P columns.
+ *   k_lo, k_hi: floor of the numpy "linear" virtual index for the two percentiles over P values
+ *   ks_lo, ks_hi: same over L*P values (the pooled "semi" null)
+ * Outputs (per task):
+ *   full_os   float [T][L][4]: order statistics a[k_lo], a[k_lo+1], a[k_hi], a[k_hi+1] of r[l,1:]
+ *   full_cnt  int32 [T][L]   : #{p : |r[l,p]| >= |r[l,0]|}
+ *   semi_os   float [T][4]   : pooled order statistics
+ *   semi_cnt  int64 [T][L]   : #{(l',p) : |r[l',p]| >= |r[l,0]|}
+ *   integral  double [T][C]  : trapezoid over positions of |r[:,c]|
+ * work_dev: scratch of mepp_perm_stats_work_bytes(T, L, C) bytes. */
+int64_t mepp_perm_stats_work_bytes(int T, int L, int C);
+int mepp_perm_stats(const float* r_dev, int T, int L, int C,
+                    int k_lo, int k_hi, int64_t ks_lo, int64_t ks_hi,
+                    float* full_os_dev, int32_t* full_cnt_dev, float* semi_os_dev,
+                    long long* semi_cnt_dev, double* integral_dev, void* work_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEPP_B200_H */

@@ -1,0 +1,76 @@
+"""ctypes binding of the C ABI declared in include/mepp_b200.h.
+
+The product path has no CPU fallback: if the shared library is missing this
+module raises at import, and every device entry point fails when no sm_100
+CUDA device is present.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmepp_b200.so")
+
+MAX_MOTIF_LEN = 32
+MAX_MARGIN = 16
+X_SCALE = 256.0
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `python -m mepp_b200.build` "
+        "(nvcc, sm_100a). mepp_b200 has no CPU fallback."
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+_i64, _i32, _f64, _vp = C.c_int64, C.c_int, C.c_double, C.c_void_p
+_pd, _pf, _pi = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); must list every symbol of include/mepp_b200.h
+SIGNATURES = {
+    "mepp_abi_version": (_i32, []),
+    "mepp_last_error": (C.c_char_p, []),
+    "mepp_device_ok": (_i32, []),
+    "mepp_log_odds": (_i32, [_pd, _i32, _pd, _f64, _pd]),
+    "mepp_threshold_from_p": (_i32, [_pd, _i32, _pd, _f64, _f64, _pd]),
+    "mepp_motif_table": (_i32, [_pd, _i32, _i32, _f64, _f64, _pd, _i32, _f64, _pf, _pf, _pi, _pd]),
+    "mepp_codes_words": (_i64, [_i32]),
+    "mepp_nmask_words": (_i64, [_i32]),
+    "mepp_pad32": (_i64, [_i64]),
+    "mepp_x_planes_bytes": (_i64, [_i64, _i64]),
+    "mepp_choose_bn": (_i32, [_i32, _pi]),
+    "mepp_y_planes_bytes": (_i64, [_i32, _i64]),
+    "mepp_pack_dna": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "mepp_build_y": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "mepp_scan": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
+                         _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "mepp_profile_gemm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp]),
+    "mepp_profile_gemm_check": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp]),
+    "mepp_correlation": (_i32, [_vp, _i64, _vp, _vp, _vp, _pd, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "mepp_perm_stats_work_bytes": (_i64, [_i32, _i32, _i32]),
+    "mepp_perm_stats": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error():
+    return lib.mepp_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError(f"mepp_b200 {what}: {last_error()}")
+
+
+def device_ok():
+    return bool(lib.mepp_device_ok())
+
+
+def choose_bn(C_cols):
+    nt = C.c_int(0)
+    bn = lib.mepp_choose_bn(int(C_cols), C.byref(nt))
+    return bn, nt.value

@@ -1,0 +1,313 @@
+// K2: the positional profile contraction S[r][c] = sum_n X[r][n] * Y[n][c]
+// (rows r = task*L + position, columns c = true score + P permuted scores,
+// reduction over the N sequences) on the 5th-generation tensor cores.
+//
+// Replaces the reference's reduce_sum(x*y, 0) over a materialised (B, L, 1+P)
+// product, mepp/core.py:250 (npdeloss/mepp), which is this GEMM computed without
+// one.
+//
+// Numerics: both operands are fp16 hi+lo splits (hi + lo carries ~22 mantissa
+// bits); three tcgen05.mma products hi*hi + hi*lo + lo*hi accumulate in fp32 in
+// TMEM (the dropped lo*lo term is < 2^-22 relative).
+//
+// Structure: persistent CTAs, one 128 x BN output tile at a time.
+//   warp 0   : producer -- one elected lane issues cp.async.bulk (TMA engine, 1-D
+//              bulk copies of pre-tiled operand blocks) into a 4-stage smem ring,
+//              completion on mbarriers
+//   warp 1   : TMEM allocator + MMA issuer -- one lane issues tcgen05.mma
+//              (cta_group::1, kind::f16, M=128, N=BN, K=16), tcgen05.commit frees
+//              smem stages and publishes finished accumulators
+//   warps 2-5: epilogue -- tcgen05.ld the fp32 accumulator (double buffered in
+//              TMEM: 2 x 256 columns) and store S
+// Operand tiles use the no-swizzle K-major canonical layout (8x16-byte core
+// matrices, LBO = stride between the two 16-byte K chunks of one MMA, SBO = stride
+// between 8-row groups), produced directly in that layout by scan.cu / pack.cu.
+#include "common.cuh"
+#include <cstdlib>
+
+namespace mepp {
+
+constexpr int kStages = 4;
+constexpr int kGemmThreads = 192;
+constexpr int kAccCols = 256;  // TMEM columns per accumulator buffer
+
+struct GemmArgs {
+  const uint8_t* A; const uint8_t* B; float* S;
+  int64_t m_rows, ldS, KB;
+  int BN, n_tiles_m, n_tiles_n, variant;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = g.BN;
+  const uint32_t a_bytes = kATileBytes;
+  const uint32_t b_bytes = (uint32_t)b_tile_bytes(BN);
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* bar_area = smem + (size_t)kStages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_area);       // [kStages]
+  uint64_t* empty_bar = full_bar + kStages;                         // [kStages]
+  uint64_t* tfull_bar = empty_bar + kStages;                        // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(2u * kAccCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int64_t n_items = (int64_t)g.n_tiles_m * g.n_tiles_n;
+  const int64_t KB = g.KB;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int64_t mt = item / g.n_tiles_n, nt = item % g.n_tiles_n;
+        const uint8_t* a_src = g.A + a_tile_offset(mt, 0, KB);
+        const uint8_t* b_src = g.B + b_tile_offset(nt, 0, KB, BN);
+        for (int64_t kb = 0; kb < KB; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          bulk_g2s(sa, a_src + kb * (int64_t)a_bytes, a_bytes, fb);
+          bulk_g2s(sa + a_bytes, b_src + kb * (int64_t)b_bytes, b_bytes, fb);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+      const uint32_t a_lbo = g.variant == 1 ? 128u : (uint32_t)kBlockM * 16u;
+      const uint32_t a_sbo = g.variant == 1 ? (uint32_t)kBlockM * 16u : 128u;
+      const uint32_t b_lbo = g.variant == 1 ? 128u : (uint32_t)BN * 16u;
+      const uint32_t b_sbo = g.variant == 1 ? (uint32_t)BN * 16u : 128u;
+      const uint32_t a_plane = kChunks * kBlockM * 16, b_plane = (uint32_t)kChunks * BN * 16;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccCols;
+        for (int64_t kb = 0; kb < KB; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int s = 0; s < kBlockK / 16; ++s) {
+            const uint32_t a_off = (uint32_t)s * 2u * kBlockM * 16u, b_off = (uint32_t)s * 2u * BN * 16u;
+            const uint64_t a_hi = make_desc(sa + a_off, a_lbo, a_sbo);
+            const uint64_t a_lo = make_desc(sa + a_plane + a_off, a_lbo, a_sbo);
+            const uint64_t b_hi = make_desc(sb + b_off, b_lbo, b_sbo);
+            const uint64_t b_lo = make_desc(sb + b_plane + b_off, b_lbo, b_sbo);
+            tc_mma_f16(d_tmem, a_hi, b_hi, idesc, (kb > 0 || s > 0) ? 1u : 0u);
+            tc_mma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+            tc_mma_f16(d_tmem, a_lo, b_hi, idesc, 1u);
+          }
+          tc_commit(smem_u32(&empty_bar[stage]));   // smem stage reusable once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(smem_u32(&tfull_bar[acc]));       // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t acc = 0, acc_phase = 0;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int64_t mt = item / g.n_tiles_n, nt = item % g.n_tiles_n;
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      const int64_t row = mt * kBlockM + q * 32 + lane;
+      float* dst = g.S + row * g.ldS + nt * (int64_t)BN;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + (uint32_t)c0, v);
+        if (row < g.m_rows) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
+            o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+            *reinterpret_cast<float4*>(dst + c0 + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kAccCols) : "memory");
+  }
+}
+
+// Cross-check: the same contraction from the same fp16 planes on CUDA cores with
+// float64 accumulation (all four hi/lo products), for selected rows.
+__global__ void gemm_check_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B,
+                                  double* __restrict__ S, int64_t m_rows, int C, int64_t KB, int BN,
+                                  const int32_t* __restrict__ rows, int n_rows_sel) {
+  const int ri = blockIdx.y;
+  const int64_t r = rows ? rows[ri] : ri;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m_rows || c >= C || ri >= n_rows_sel) return;
+  const int64_t mt = r >> 7; const int row = (int)(r & 127);
+  const int nt = c / BN, col = c % BN;
+  double acc = 0.0;
+  for (int64_t kb = 0; kb < KB; ++kb) {
+    const uint8_t* at = A + a_tile_offset(mt, kb, KB);
+    const uint8_t* bt = B + b_tile_offset(nt, kb, KB, BN);
+    for (int kc = 0; kc < kChunks; ++kc) {
+      const __half* ah = reinterpret_cast<const __half*>(at + a_chunk_offset(0, kc, row));
+      const __half* al = reinterpret_cast<const __half*>(at + a_chunk_offset(1, kc, row));
+      const __half* bh = reinterpret_cast<const __half*>(bt + b_chunk_offset(0, kc, col, BN));
+      const __half* bl = reinterpret_cast<const __half*>(bt + b_chunk_offset(1, kc, col, BN));
+      for (int e = 0; e < 8; ++e) {
+        const double x = (double)__half2float(ah[e]) + (double)__half2float(al[e]);
+        if (x != 0.0) acc += x * ((double)__half2float(bh[e]) + (double)__half2float(bl[e]));
+      }
+    }
+  }
+  S[(int64_t)ri * C + c] = acc;
+}
+
+}  // namespace mepp
+
+extern "C" {
+
+int mepp_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float* S_dev, int64_t m_rows,
+                      int C, int64_t n_pad, void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(x_planes_dev && y_planes_dev && S_dev, "profile_gemm: null pointer");
+  MEPP_REQUIRE(m_rows > 0 && C > 0 && n_pad > 0 && n_pad % kBlockK == 0, "profile_gemm: bad shape");
+  MEPP_REQUIRE(mepp_device_ok(), "profile_gemm: no sm_100 CUDA device (no CPU fallback)");
+  GemmArgs g;
+  g.A = reinterpret_cast<const uint8_t*>(x_planes_dev);
+  g.B = reinterpret_cast<const uint8_t*>(y_planes_dev);
+  g.S = S_dev;
+  g.m_rows = m_rows;
+  g.KB = n_pad / kBlockK;
+  g.BN = mepp_choose_bn(C, &g.n_tiles_n);
+  g.ldS = (int64_t)g.n_tiles_n * g.BN;
+  g.n_tiles_m = (int)((m_rows + kBlockM - 1) / kBlockM);
+  const char* var = getenv("MEPP_GEMM_DESC_VARIANT");
+  g.variant = var ? atoi(var) : 0;
+  size_t smem = (size_t)kStages * (kATileBytes + b_tile_bytes(g.BN)) + 256;
+  MEPP_CUDA_CHECK(cudaFuncSetAttribute(profile_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0;
+  MEPP_CUDA_CHECK(cudaGetDevice(&dev));
+  MEPP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int64_t n_items = (int64_t)g.n_tiles_m * g.n_tiles_n;
+  unsigned grid = (unsigned)(n_items < sms ? n_items : sms);
+  profile_gemm_kernel<<<grid, kGemmThreads, smem, as_stream(stream)>>>(g);
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mepp_profile_gemm_check(const void* x_planes_dev, const void* y_planes_dev, double* S_dev, int64_t m_rows,
+                            int C, int64_t n_pad, const int32_t* rows_dev, int n_rows_sel, void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(x_planes_dev && y_planes_dev && S_dev && n_rows_sel > 0, "profile_gemm_check: bad arguments");
+  MEPP_REQUIRE(mepp_device_ok(), "profile_gemm_check: no sm_100 CUDA device (no CPU fallback)");
+  int nt = 0;
+  int BN = mepp_choose_bn(C, &nt);
+  dim3 grid((unsigned)((C + 127) / 128), (unsigned)n_rows_sel);
+  gemm_check_kernel<<<grid, 128, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint8_t*>(x_planes_dev), reinterpret_cast<const uint8_t*>(y_planes_dev), S_dev,
+      m_rows, C, n_pad / kBlockK, BN, rows_dev, n_rows_sel);
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

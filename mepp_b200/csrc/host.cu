@@ -1,0 +1,152 @@
+// Host-side pieces of the C ABI: error state, layout sizes, and the MOODS
+// log-odds / p-value threshold DP that the reference runs on the host
+// (mepp/motif_layers.py:36-48 -> MOODS.tools.log_odds / threshold_from_p).
+#include "common.cuh"
+#include <cmath>
+#include <vector>
+#include <algorithm>
+#include <limits>
+
+namespace mepp {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(const std::string& msg) { g_err = msg; return 1; }
+}  // namespace mepp
+
+extern "C" {
+
+int mepp_abi_version(void) { return MEPP_B200_ABI_VERSION; }
+const char* mepp_last_error(void) { return mepp::g_err.c_str(); }
+
+int mepp_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return 0; }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int64_t mepp_codes_words(int L) { return (L + 15) / 16 + 2; }
+int64_t mepp_nmask_words(int L) { return (L + 31) / 32 + 2; }
+int64_t mepp_pad32(int64_t n) { return (n + 31) / 32 * 32; }
+
+int64_t mepp_x_planes_bytes(int64_t m_rows, int64_t n_pad) {
+  int64_t mt = (m_rows + mepp::kBlockM - 1) / mepp::kBlockM;
+  return mt * (n_pad / mepp::kBlockK) * (int64_t)mepp::kATileBytes;
+}
+
+int mepp_choose_bn(int C, int* n_tiles_n) {
+  int nt = (C + 255) / 256;
+  if (nt < 1) nt = 1;
+  int bn = ((C + nt - 1) / nt + 31) / 32 * 32;
+  if (n_tiles_n) *n_tiles_n = nt;
+  return bn;
+}
+
+int64_t mepp_y_planes_bytes(int C, int64_t n_pad) {
+  int nt = 0;
+  int bn = mepp_choose_bn(C, &nt);
+  return (int64_t)nt * (n_pad / mepp::kBlockK) * (int64_t)mepp::b_tile_bytes(bn);
+}
+
+// MOODS.tools.log_odds: W[j][i] = ln((mat[j][i] + ps*bg[j]) / col_i) - ln(bg[j]).
+int mepp_log_odds(const double* pwm, int m, const double* bg, double ps, double* W) {
+  MEPP_REQUIRE(pwm && bg && W && m > 0, "log_odds: bad arguments");
+  for (int i = 0; i < m; ++i) {
+    double col = 0.0;
+    for (int j = 0; j < 4; ++j) col += pwm[j * m + i] + ps * bg[j];
+    for (int j = 0; j < 4; ++j)
+      W[j * m + i] = std::log((pwm[j * m + i] + ps * bg[j]) / col) - std::log(bg[j]);
+  }
+  return 0;
+}
+
+// MOODS.tools.threshold_from_p: distribution of the integer-rounded score under
+// bg by dynamic programming, then the smallest grid score whose upper tail <= p.
+int mepp_threshold_from_p(const double* W, int m, const double* bg, double p,
+                          double precision, double* thr) {
+  MEPP_REQUIRE(W && bg && thr && m > 0 && precision > 0, "threshold_from_p: bad arguments");
+  std::vector<long> mat(4 * (size_t)m);
+  for (int k = 0; k < 4 * m; ++k) {
+    double v = W[k];
+    mat[k] = v > 0.0 ? (long)(precision * v + 0.5) : (long)(precision * v - 0.5);
+  }
+  long maxT = 0, minV = std::numeric_limits<long>::max();
+  for (int i = 0; i < m; ++i) {
+    long mx = mat[i], mn = mat[i];
+    for (int j = 1; j < 4; ++j) {
+      mx = std::max(mx, mat[j * m + i]);
+      mn = std::min(mn, mat[j * m + i]);
+    }
+    maxT += mx;
+    minV = std::min(minV, mn);
+  }
+  long R = maxT - (long)m * minV;
+  MEPP_REQUIRE(R >= 0 && R < (1L << 28), "threshold_from_p: score range too large");
+  std::vector<double> t0((size_t)R + 1, 0.0), t1((size_t)R + 1, 0.0);
+  for (int j = 0; j < 4; ++j) t0[(size_t)(mat[j * m] - minV)] += bg[j];
+  long hi = 0;  // highest reachable index so far (keeps the DP sparse in early columns)
+  for (int j = 0; j < 4; ++j) hi = std::max(hi, mat[j * m] - minV);
+  for (int i = 1; i < m; ++i) {
+    long new_hi = 0;
+    for (int j = 0; j < 4; ++j) {
+      long s = mat[j * m + i] - minV;
+      double b = bg[j];
+      const double* src = t0.data();
+      double* dst = t1.data() + s;
+      for (long r = 0; r <= hi; ++r) dst[r] += b * src[r];
+      new_hi = std::max(new_hi, hi + s);
+    }
+    std::fill(t0.begin(), t0.begin() + hi + 1, 0.0);
+    t0.swap(t1);
+    hi = new_hi;
+  }
+  double sum = 0.0;
+  for (long r = R; r >= 0; --r) {
+    sum += t0[(size_t)r];
+    if (sum > p) { *thr = (double)(r + (long)m * minV + 1) / precision; return 0; }
+  }
+  *thr = (double)((long)m * minV) / precision;
+  return 0;
+}
+
+int mepp_motif_table(const double* pwm, int m, int orientation_char,
+                     double pseudocount, double pvalue, const double* bg_in, int use_flags,
+                     double dp_precision, float* lut, float* bias, int* n_filters, double* thr_out) {
+  MEPP_REQUIRE(pwm && lut && bias && n_filters, "motif_table: null argument");
+  MEPP_REQUIRE(m >= 1 && m <= MEPP_MAX_MOTIF_LEN, "motif_table: motif length must be in [1, 32]");
+  double bg[4] = {0.25, 0.25, 0.25, 0.25};
+  double ps = 1e-4, pv = 1e-4;  // core.py:513-534 never forwards the user's values
+  if (use_flags) {
+    ps = pseudocount; pv = pvalue;
+    if (bg_in) for (int j = 0; j < 4; ++j) bg[j] = bg_in[j];
+  }
+  std::vector<double> W(4 * (size_t)m), Wr(4 * (size_t)m);
+  if (mepp_log_odds(pwm, m, bg, ps, W.data())) return 1;
+  for (int c = 0; c < 4; ++c)
+    for (int j = 0; j < m; ++j) Wr[c * m + j] = W[(3 - c) * m + (m - 1 - j)];  // W[::-1, ::-1]
+  const double* f0 = W.data();
+  const double* f1 = nullptr;
+  if (orientation_char == '+') {
+  } else if (orientation_char == '-') {
+    f0 = Wr.data();  // motif_layers.py:36-42; threshold from the reversed matrix (:44-48)
+  } else {
+    f1 = Wr.data();  // dual: filter 1 = W[::-1,::-1], shared bias -thr(W) (:66-74)
+  }
+  double thr = 0.0;
+  if (mepp_threshold_from_p(f0, m, bg, pv, dp_precision, &thr)) return 1;
+  for (int k = 0; k < MEPP_MAX_MOTIF_LEN * 8; ++k) lut[k] = 0.0f;
+  for (int j = 0; j < m; ++j)
+    for (int c = 0; c < 4; ++c) {
+      lut[(j * 4 + c) * 2 + 0] = (float)f0[c * m + j];
+      lut[(j * 4 + c) * 2 + 1] = f1 ? (float)f1[c * m + j] : 0.0f;
+    }
+  *bias = (float)(-thr);
+  *n_filters = f1 ? 2 : 1;
+  if (thr_out) *thr_out = thr;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// K0: ASCII -> 2-bit codes + N mask + global GC ratio, and the Y (score / permuted
+// score) GEMM operand.  Replaces mepp/onehot_dna.py:61-70, mepp/utils.py:141-194,
+// mepp/utils.py:275-308 and mepp/permutations.py:5-58 of the reference.
+#include "common.cuh"
+
+namespace mepp {
+
+// One thread per (word w, sequence n); consecutive threads = consecutive n so the
+// transposed stores are coalesced.  The ASCII reads are strided 16-byte segments.
+__global__ void pack_codes_kernel(const uint8_t* __restrict__ ascii, int64_t N, int L,
+                                  int64_t n_pad, int Wc, uint32_t* __restrict__ codes_T) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int w = blockIdx.y;
+  if (n >= n_pad) return;
+  uint32_t word = 0;
+  if (n < N) {
+    int base = w * 16;
+    const uint8_t* s = ascii + n * (int64_t)L;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int p = base + i;
+      uint32_t c = 0;
+      if (p < L) {
+        uint8_t ch = s[p];
+        c = ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 0u;
+      }
+      word |= c << (2 * i);
+    }
+  }
+  codes_T[(int64_t)w * n_pad + n] = word;
+}
+
+// Mask words (32 bases each) and the GC covariate z[n] = (sum_l gc_l) / L with
+// gc_l = 1 for C/G, 0.5 for N (= every non upper-case-ACGT char), 0 otherwise.
+__global__ void pack_mask_gc_kernel(const uint8_t* __restrict__ ascii, int64_t N, int L,
+                                    int64_t n_pad, int Wm, uint32_t* __restrict__ nmask_T,
+                                    float* __restrict__ gc) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_pad) return;
+  int twice = 0;  // 2 * sum of gc_l, an exact integer
+  const uint8_t* s = ascii + n * (int64_t)L;
+  for (int w = 0; w < Wm; ++w) {
+    uint32_t word = 0;
+    if (n < N) {
+      for (int i = 0; i < 32; ++i) {
+        int p = w * 32 + i;
+        if (p < L) {
+          uint8_t ch = s[p];
+          bool acgt = (ch == 'A') | (ch == 'C') | (ch == 'G') | (ch == 'T');
+          if (!acgt) { word |= 1u << i; twice += 1; }
+          else if (ch == 'C' || ch == 'G') twice += 2;
+        }
+      }
+    }
+    nmask_T[(int64_t)w * n_pad + n] = word;
+  }
+  // float32 sum of {0, .5, 1} is exact; one rounding in the division (utils.py:262-266)
+  gc[n] = n < N ? (0.5f * (float)twice) / (float)L : 0.0f;
+}
+
+// ysplit[n] = fp16 hi | lo<<16 of yhat[n]; also accumulates sum and sum of squares
+// of the split-rounded values in float64 (identical for every permuted column).
+__global__ void y_split_kernel(const float* __restrict__ yhat, int64_t N, uint32_t* __restrict__ ysplit,
+                               double* __restrict__ ysum) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (n < N) {
+    __half h, l;
+    split_half(yhat[n], h, l);
+    ysplit[n] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+    v = (double)__half2float(h) + (double)__half2float(l);
+  }
+  double s = v, ss = v * v;
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (s != 0.0 || ss != 0.0)) {
+    atomicAdd(&ysum[0], s);
+    atomicAdd(&ysum[1], ss);
+  }
+}
+
+// One thread per (column c, 8 consecutive sequences): gathers the packed hi/lo pair
+// and writes one 16-byte chunk to each plane of the tiled B operand.
+__global__ void y_build_kernel(const uint32_t* __restrict__ ysplit, const int32_t* __restrict__ perm,
+                               int64_t N, int64_t n_pad, int C, int BN, int n_tiles_n,
+                               uint8_t* __restrict__ planes) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 8 sequences
+  int c = blockIdx.y;                                          // padded column index
+  int64_t n_groups = n_pad / 8;
+  if (g >= n_groups) return;
+  int64_t n0 = g * 8;
+  uint32_t v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int64_t n = n0 + i;
+    uint32_t x = 0;
+    if (c < C && n < N) {
+      int64_t src = c == 0 ? n : (int64_t)perm[(int64_t)(c - 1) * N + n];
+      x = ysplit[src];
+    }
+    v[i] = x;
+  }
+  uint4 hi, lo;
+  hi.x = (v[0] & 0xffffu) | (v[1] << 16);
+  hi.y = (v[2] & 0xffffu) | (v[3] << 16);
+  hi.z = (v[4] & 0xffffu) | (v[5] << 16);
+  hi.w = (v[6] & 0xffffu) | (v[7] << 16);
+  lo.x = (v[0] >> 16) | (v[1] & 0xffff0000u);
+  lo.y = (v[2] >> 16) | (v[3] & 0xffff0000u);
+  lo.z = (v[4] >> 16) | (v[5] & 0xffff0000u);
+  lo.w = (v[6] >> 16) | (v[7] & 0xffff0000u);
+  int64_t KB = n_pad / kBlockK;
+  int64_t kb = n0 / kBlockK;
+  int kc = (int)((n0 % kBlockK) / 8);
+  int nt = c / BN, col = c % BN;
+  uint8_t* tile = planes + b_tile_offset(nt, kb, KB, BN);
+  *reinterpret_cast<uint4*>(tile + b_chunk_offset(0, kc, col, BN)) = hi;
+  *reinterpret_cast<uint4*>(tile + b_chunk_offset(1, kc, col, BN)) = lo;
+}
+
+// col_syz[c] = sum_n y_c[n] * zhat[n] in float64; one block per column.
+__global__ void y_colstats_kernel(const uint32_t* __restrict__ ysplit, const int32_t* __restrict__ perm,
+                                  const float* __restrict__ zhat, int64_t N, int C,
+                                  double* __restrict__ col_syz) {
+  int c = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t n = threadIdx.x; n < N; n += blockDim.x) {
+    int64_t src = c == 0 ? n : (int64_t)perm[(int64_t)(c - 1) * N + n];
+    uint32_t x = ysplit[src];
+    double y = (double)__half2float(__ushort_as_half((unsigned short)(x & 0xffffu))) +
+               (double)__half2float(__ushort_as_half((unsigned short)(x >> 16)));
+    acc += y * (double)zhat[n];
+  }
+  __shared__ double red[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) col_syz[c] = v;
+  }
+}
+
+}  // namespace mepp
+
+extern "C" {
+
+int mepp_pack_dna(const uint8_t* ascii_dev, int64_t N, int L, uint32_t* codes_T_dev,
+                  uint32_t* nmask_T_dev, float* gc_dev, void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(ascii_dev && codes_T_dev && nmask_T_dev && gc_dev, "pack_dna: null pointer");
+  MEPP_REQUIRE(N > 0 && L > 0, "pack_dna: empty input");
+  MEPP_REQUIRE(mepp_device_ok(), "pack_dna: no sm_100 CUDA device (no CPU fallback)");
+  int64_t n_pad = mepp_pad32(N);
+  int Wc = (int)mepp_codes_words(L), Wm = (int)mepp_nmask_words(L);
+  cudaStream_t st = as_stream(stream);
+  dim3 grid((unsigned)((n_pad + 255) / 256), (unsigned)Wc);
+  pack_codes_kernel<<<grid, 256, 0, st>>>(ascii_dev, N, L, n_pad, Wc, codes_T_dev);
+  pack_mask_gc_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(ascii_dev, N, L, n_pad, Wm,
+                                                                      nmask_T_dev, gc_dev);
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mepp_build_y(const float* yhat_dev, const int32_t* perm_dev, const float* zhat_dev, int64_t N,
+                 int P, void* y_planes_dev, double* col_syz_dev, double* ysum_dev, void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(yhat_dev && y_planes_dev && col_syz_dev && ysum_dev, "build_y: null pointer");
+  MEPP_REQUIRE(N > 0 && P >= 0 && (P == 0 || perm_dev), "build_y: bad arguments");
+  MEPP_REQUIRE(mepp_device_ok(), "build_y: no sm_100 CUDA device (no CPU fallback)");
+  cudaStream_t st = as_stream(stream);
+  int C = 1 + P;
+  int n_tiles_n = 0;
+  int BN = mepp_choose_bn(C, &n_tiles_n);
+  int64_t n_pad = mepp_pad32(N);
+  uint32_t* ysplit = nullptr;
+  MEPP_CUDA_CHECK(cudaMallocAsync(&ysplit, sizeof(uint32_t) * (size_t)N, st));
+  MEPP_CUDA_CHECK(cudaMemsetAsync(ysum_dev, 0, 2 * sizeof(double), st));
+  y_split_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(yhat_dev, N, ysplit, ysum_dev);
+  dim3 grid((unsigned)((n_pad / 8 + 127) / 128), (unsigned)(n_tiles_n * BN));
+  y_build_kernel<<<grid, 128, 0, st>>>(ysplit, perm_dev, N, n_pad, C, BN, n_tiles_n,
+                                       reinterpret_cast<uint8_t*>(y_planes_dev));
+  if (zhat_dev) {
+    y_colstats_kernel<<<(unsigned)C, 256, 0, st>>>(ysplit, perm_dev, zhat_dev, N, C, col_syz_dev);
+  } else {
+    MEPP_CUDA_CHECK(cudaMemsetAsync(col_syz_dev, 0, sizeof(double) * (size_t)C, st));
+  }
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  MEPP_CUDA_CHECK(cudaFreeAsync(ysplit, st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,317 @@
+"""Per-process profiling engine: owns the staged device buffers of one scored-FASTA
+dataset and runs groups of (motif, orientation) tasks through the CUDA kernels.
+
+Boundary: this replaces what, in the reference, is spread over
+run_batch's save_dataset (mepp/batch.py:66-70), every run_single's load_dataset
+(mepp/single.py:177) and dataset_and_motif_matrix_to_profile_data
+(mepp/core.py:490-632): sequences are packed once into HBM, the score / permuted-score
+operand Y is built once, and each task group is scan -> tcgen05 GEMM -> correlation
+epilogue -> permutation statistics, with only L-length vectors returning to the host.
+
+PyTorch is used for device memory, streams and (in parallel.py) torch.distributed only.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from . import motif_layers
+from . import stats_host
+
+HIT_DTYPE = np.dtype([('task', np.int32), ('seq', np.int32), ('pos', np.int32), ('x0', np.float32)])
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class ProfileBatch:
+    """Results of a group of tasks: {column: (T, L)} positions, (T, N) density, thresholds, optional hits / r."""
+
+    def __init__(self, task_ids, positions, density, scores, thr, hit_counts=None, hits=None, r=None, n_seq=0):
+        self.task_ids = task_ids
+        self.positions = positions
+        self.density = density
+        self.scores = scores
+        self.thr = thr
+        self.hit_counts = hit_counts
+        self.hits = hits
+        self.r = r
+        self.n_seq = n_seq
+
+    def __len__(self):
+        return len(self.task_ids)
+
+    def positions_df(self, i):
+        import pandas as pd
+        return pd.DataFrame({k: np.array(v[i]) for k, v in self.positions.items()})
+
+    def ranks_df(self, i):
+        """core.py:576-579,596-624: rank = arange (sort=False), score, density."""
+        import pandas as pd
+        return pd.DataFrame(dict(rank=np.arange(self.n_seq), score=self.scores,
+                                 density=self.density[i].astype(np.float64)))
+
+    def motif_score_matrix(self, i, L):
+        """Dense (N, L) float32 unsmoothed score matrix of task i rebuilt from the match list
+        (what core.py:568-573 returns as motif_score_matrix)."""
+        if self.hits is None:
+            raise RuntimeError("profile() was called without return_hits=True")
+        h = self.hits[self.hits['task'] == i]
+        X0 = np.zeros((self.n_seq, L), dtype=np.float32)
+        X0[h['seq'], h['pos']] = h['x0']
+        return X0
+
+
+class Engine:
+    def __init__(self, device=None, mem_budget_bytes=32 << 30, max_group=512):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("mepp_b200: no CUDA device visible; the engine has no CPU fallback")
+        self.torch = torch
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        with torch.cuda.device(self.device):
+            if not _lib.device_ok():
+                raise RuntimeError("mepp_b200: device is not sm_100 (B200); kernels are built for sm_100a only")
+        self.mem_budget = int(mem_budget_bytes)
+        self.max_group = int(max_group)
+        self.staged = False
+        self._bufs = {}
+        self.launches = 0   # kernels launched by this engine (bench.py reports it)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _to_dev(self, a, dtype=None):
+        torch = self.torch
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True)
+
+    def _buf(self, name, nbytes_or_shape, dtype, zero=False):
+        """Grow-only named scratch buffer."""
+        torch = self.torch
+        shape = (int(nbytes_or_shape),) if np.isscalar(nbytes_or_shape) else tuple(int(s) for s in nbytes_or_shape)
+        need = int(np.prod(shape))
+        cur = self._bufs.get(name)
+        if cur is None or cur.numel() < need or cur.dtype != dtype:
+            cur = (torch.zeros if zero else torch.empty)(need, dtype=dtype, device=self.device)
+            self._bufs[name] = cur
+        return cur[:need].view(shape)
+
+    # ------------------------------------------------------------------ staging
+    def stage(self, ascii_u8, scores, perm_idx=None, use_gc=True):
+        """Stage one dataset: ascii (N, L) uint8, scores (N,) float32 (rows already ordered as the
+        reference's order_scored_fasta_df leaves them), perm_idx (P, N) int32 or None."""
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            N, L = int(ascii_u8.shape[0]), int(ascii_u8.shape[1])
+            if N < 4:
+                raise ValueError("need at least 4 sequences")
+            self.N, self.L = N, L
+            self.n_pad = int(_lib.lib.mepp_pad32(N))
+            Wc, Wm = int(_lib.lib.mepp_codes_words(L)), int(_lib.lib.mepp_nmask_words(L))
+            st = self._stream()
+            ascii_d = self._to_dev(ascii_u8, torch.uint8).contiguous()
+            self.codes_T = torch.empty((Wc, self.n_pad), dtype=torch.int32, device=self.device)
+            self.nmask_T = torch.empty((Wm, self.n_pad), dtype=torch.int32, device=self.device)
+            self.gc = torch.empty(self.n_pad, dtype=torch.float32, device=self.device)
+            _lib.check(_lib.lib.mepp_pack_dna(_ptr(ascii_d), N, L, _ptr(self.codes_T), _ptr(self.nmask_T),
+                                              _ptr(self.gc), st), "pack_dna")
+            self.launches += 2
+            self.use_gc = bool(use_gc)
+            if self.use_gc:
+                # centre the covariate in float64 (Pearson r is shift invariant); plumbing, not a hot op
+                z64 = self.gc[:N].double()
+                zhat = torch.zeros(self.n_pad, dtype=torch.float32, device=self.device)
+                zhat[:N] = (z64 - z64.mean()).float()
+                self.zhat = zhat
+                zh64 = zhat[:N].double()
+                self._zsum_dev = torch.stack([zh64.sum(), (zh64 * zh64).sum()])
+            else:
+                self.zhat = None
+                self._zsum_dev = None
+            # scores: float32 like the reference's dataset (utils.py:188-192); centred + scaled on host in float64
+            s32 = (scores.numpy() if isinstance(scores, torch.Tensor) else np.asarray(scores)).astype(np.float32)
+            self.scores = s32
+            y = s32.astype(np.float64)
+            yc = y - y.mean()
+            amax = float(np.abs(yc).max())
+            scale = 1.0 if amax == 0.0 or not math.isfinite(amax) else 2.0 ** (13 - math.floor(math.log2(amax)))
+            yhat = (yc * scale).astype(np.float32)
+            yhat_d = self._to_dev(yhat)
+            if perm_idx is not None and int(perm_idx.shape[0]) > 0:
+                P = int(perm_idx.shape[0])
+                if tuple(perm_idx.shape) != (P, N):
+                    raise ValueError("perm_idx must have shape (P, N)")
+                perm_d = self._to_dev(perm_idx, torch.int32).contiguous()
+            else:
+                P, perm_d = 0, None
+            self.P, self.C = P, 1 + P
+            self.BN, self.n_tiles_n = _lib.choose_bn(self.C)
+            self.ldS = self.BN * self.n_tiles_n
+            self.y_planes = torch.empty(int(_lib.lib.mepp_y_planes_bytes(self.C, self.n_pad)), dtype=torch.uint8,
+                                        device=self.device)
+            self.col_syz = torch.empty(self.C, dtype=torch.float64, device=self.device)
+            self.ysum = torch.empty(2, dtype=torch.float64, device=self.device)
+            _lib.check(_lib.lib.mepp_build_y(_ptr(yhat_d), _ptr(perm_d), _ptr(self.zhat), N, P, _ptr(self.y_planes),
+                                             _ptr(self.col_syz), _ptr(self.ysum), st), "build_y")
+            self.launches += 3 if self.use_gc else 2
+            self._zsum_host = None
+            self.staged = True
+        return self
+
+    def _zsum(self):
+        if self._zsum_host is None:
+            if self._zsum_dev is not None:
+                self._zsum_host = self._zsum_dev.cpu().numpy().astype(np.float64)
+            else:
+                self._zsum_host = np.zeros(2, dtype=np.float64)
+        return self._zsum_host
+
+    # ------------------------------------------------------------------ sizing
+    def group_size(self):
+        per_task = (self.L * self.n_pad * 4            # X planes (fp16 hi + lo)
+                    + self.L * self.ldS * 4            # S
+                    + self.L * self.C * 4              # r
+                    + self.L * max(self.P, 1) * 4      # sorted keys
+                    + self.n_pad * 4 + self.L * 64)
+        g = max(1, min(self.max_group, self.mem_budget // max(per_task, 1)))
+        return int(g)
+
+    # ------------------------------------------------------------------ tasks
+    def profile(self, tasks, margin=0, confidence_interval_pct=95, center=None, return_hits=False,
+                return_r=False, hits_cap=None, tables=None, honour_flags=False, pseudocount=1e-4, pvalue=1e-4,
+                bg=None):
+        """Run (motif_matrix (4, m), orientation) tasks.  Returns a ProfileBatch."""
+        if not self.staged:
+            raise RuntimeError("Engine.stage() must be called first")
+        if not 0 <= int(margin) <= _lib.MAX_MARGIN:
+            raise ValueError(f"margin must be in [0, {_lib.MAX_MARGIN}]")
+        torch = self.torch
+        T_all = len(tasks)
+        L, N = self.L, self.N
+        if center is None:
+            center = L // 2
+        if center < 0:
+            center = 0
+        if center > L:
+            center = L - 1          # core.py:503-509
+        if tables is None:
+            tables = motif_layers.scan_tables(list(tasks), honour_flags=honour_flags, pseudocount=pseudocount,
+                                              pvalue=pvalue, bg=bg)
+        for tb in tables:
+            if tb['m'] > L:
+                raise ValueError("motif longer than the sequences")
+        G = self.group_size()
+        outs = []
+        with torch.cuda.device(self.device):
+            for g0 in range(0, T_all, G):
+                outs.append(self._run_group(tables[g0:g0 + G], margin, return_hits, return_r, hits_cap,
+                                            confidence_interval_pct))
+            torch.cuda.current_stream(self.device).synchronize()
+        # ---- host finalisation, vectorised over tasks
+        cat = lambda k: np.concatenate([o[k] for o in outs], axis=0)
+        r0, count, density = cat('r0'), cat('count'), cat('density')
+        if self.P > 0:
+            full_os, full_cnt, semi_os, semi_cnt, integral = (cat('full_os'), cat('full_cnt'), cat('semi_os'),
+                                                              cat('semi_cnt'), cat('integral'))
+        else:
+            full_os = full_cnt = semi_os = semi_cnt = integral = None
+        positions = stats_host.finalize_positions(r0, full_os, full_cnt, semi_os, semi_cnt, integral, count, N,
+                                                  self.P, margin, confidence_interval_pct, center)
+        hits = None
+        if return_hits:
+            parts = []
+            off = 0
+            for o in outs:
+                h = o['hits'].copy()
+                h['task'] += off
+                off += o['r0'].shape[0]
+                parts.append(h)
+            hits = np.concatenate(parts) if parts else np.zeros(0, dtype=HIT_DTYPE)
+            order = np.lexsort((hits['pos'], hits['seq'], hits['task']))
+            hits = hits[order]
+        r = np.concatenate([o['r'] for o in outs], axis=0) if return_r else None
+        thr = np.array([tb['thr'] for tb in tables])
+        return ProfileBatch(list(range(T_all)), positions, density[:, :N], self.scores, thr,
+                            hit_counts=cat('hit_count'), hits=hits, r=r, n_seq=N)
+
+    def _run_group(self, tables, margin, return_hits, return_r, hits_cap, ci):
+        torch = self.torch
+        T = len(tables)
+        L, N, C_, P = self.L, self.N, self.C, self.P
+        st = self._stream()
+        m_rows = T * L
+        lut = np.stack([tb['lut'] for tb in tables]).astype(np.float32)
+        bias = np.array([tb['bias'] for tb in tables], dtype=np.float32)
+        mlen = np.array([tb['m'] for tb in tables], dtype=np.int32)
+        nfilt = np.array([tb['n_filters'] for tb in tables], dtype=np.int32)
+        lut_d, bias_d, mlen_d, nfilt_d = (self._to_dev(lut), self._to_dev(bias), self._to_dev(mlen),
+                                          self._to_dev(nfilt))
+        x_bytes = int(_lib.lib.mepp_x_planes_bytes(m_rows, self.n_pad))
+        x_planes = self._buf('x_planes', x_bytes, torch.uint8, zero=True)
+        rowstats = self._buf('rowstats', (m_rows, 3), torch.float64)
+        count = self._buf('count', (T, L), torch.int32)
+        density = self._buf('density', (T, self.n_pad), torch.int32)
+        hit_count = self._buf('hit_count', (1,), torch.int64)
+        hits_d = None
+        cap = 0
+        if return_hits:
+            cap = int(hits_cap) if hits_cap else max(1 << 20, int(T * N * L * 2e-3))
+            hits_d = self._buf('hits', cap * 16, torch.uint8)
+        _lib.check(_lib.lib.mepp_scan(_ptr(self.codes_T), _ptr(self.nmask_T), _ptr(self.zhat), N, L, T, int(margin),
+                                      _ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), _ptr(x_planes),
+                                      _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap,
+                                      _ptr(hit_count), st), "scan")
+        S = self._buf('S', (m_rows, self.ldS), torch.float32)
+        _lib.check(_lib.lib.mepp_profile_gemm(_ptr(x_planes), _ptr(self.y_planes), _ptr(S), m_rows, C_, self.n_pad,
+                                              st), "profile_gemm")
+        r = self._buf('r', (m_rows, C_), torch.float32)
+        zsum = self._zsum()
+        _lib.check(_lib.lib.mepp_correlation(_ptr(S), self.ldS, _ptr(rowstats), _ptr(self.col_syz), _ptr(self.ysum),
+                                             zsum.ctypes.data_as(C.POINTER(C.c_double)), N, m_rows, C_,
+                                             1 if self.use_gc else 0, _ptr(r), st), "correlation")
+        self.launches += 3 + (m_rows + 65534) // 65535 - 1
+        out = {}
+        if P > 0:
+            q = stats_host.percentile_q(ci)
+            k_lo, _ = stats_host.virtual_index(P, q[0])
+            k_hi, _ = stats_host.virtual_index(P, q[1])
+            ks_lo, _ = stats_host.virtual_index(L * P, q[0])
+            ks_hi, _ = stats_host.virtual_index(L * P, q[1])
+            full_os = self._buf('full_os', (T, L, 4), torch.float32)
+            full_cnt = self._buf('full_cnt', (T, L), torch.int32)
+            semi_os = self._buf('semi_os', (T, 4), torch.float32)
+            semi_cnt = self._buf('semi_cnt', (T, L), torch.int64)
+            integral = self._buf('integral', (T, C_), torch.float64)
+            work = self._buf('stats_work', int(_lib.lib.mepp_perm_stats_work_bytes(T, L, C_)), torch.uint8)
+            _lib.check(_lib.lib.mepp_perm_stats(_ptr(r), T, L, C_, k_lo, k_hi, ks_lo, ks_hi, _ptr(full_os),
+                                                _ptr(full_cnt), _ptr(semi_os), _ptr(semi_cnt), _ptr(integral),
+                                                _ptr(work), st), "perm_stats")
+            self.launches += 6
+            out.update(full_os=full_os.cpu().numpy(), full_cnt=full_cnt.cpu().numpy(),
+                       semi_os=semi_os.cpu().numpy(), semi_cnt=semi_cnt.cpu().numpy(),
+                       integral=integral.cpu().numpy())
+        out['r0'] = r.view(T, L, C_)[:, :, 0].contiguous().cpu().numpy()
+        out['count'] = count.cpu().numpy()
+        out['density'] = density.cpu().numpy()
+        nh = int(hit_count.cpu().numpy()[0])
+        out['hit_count'] = np.array([nh], dtype=np.int64)
+        if return_hits:
+            if nh > cap:
+                raise RuntimeError(f"match list overflow: {nh} matches > capacity {cap}; pass hits_cap")
+            raw = hits_d[:nh * 16].cpu().numpy()
+            out['hits'] = raw.view(HIT_DTYPE).copy()
+        if return_r:
+            out['r'] = r.view(T, L, C_).cpu().numpy().copy()
+        return out
+

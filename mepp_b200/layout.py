@@ -1,0 +1,24 @@
+"""Host-side decoders of the tiled fp16 hi/lo operand layouts (include/mepp_b200.h) -- used by
+tests and debugging only; the kernels produce and consume the tiled form directly."""
+import numpy as np
+
+
+def decode_x_planes(raw_u8, m_rows, n_pad):
+    """[m_tile][k_block][plane 2][kc 4][row 128][8] fp16 -> (hi, lo) float32 arrays (m_rows, n_pad)."""
+    MT = (m_rows + 127) // 128
+    KB = n_pad // 32
+    a = np.frombuffer(np.ascontiguousarray(raw_u8).tobytes(), dtype=np.float16)[:MT * KB * 2 * 4 * 128 * 8]
+    a = a.reshape(MT, KB, 2, 4, 128, 8).astype(np.float32)
+    # -> (plane, MT, row, KB, kc, e)
+    a = a.transpose(2, 0, 4, 1, 3, 5).reshape(2, MT * 128, KB * 32)
+    return a[0][:m_rows], a[1][:m_rows]
+
+
+def decode_y_planes(raw_u8, C, n_pad, BN, n_tiles_n):
+    """[n_tile][k_block][plane 2][kc 4][col BN][8] fp16 -> (hi, lo) float32 arrays (n_pad, C)."""
+    KB = n_pad // 32
+    a = np.frombuffer(np.ascontiguousarray(raw_u8).tobytes(), dtype=np.float16)[:n_tiles_n * KB * 2 * 4 * BN * 8]
+    a = a.reshape(n_tiles_n, KB, 2, 4, BN, 8).astype(np.float32)
+    # -> (plane, KB, kc, e, NT, col)
+    a = a.transpose(2, 1, 3, 5, 0, 4).reshape(2, KB * 32, n_tiles_n * BN)
+    return a[0][:, :C], a[1][:, :C]

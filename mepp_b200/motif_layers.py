@@ -1,0 +1,92 @@
+"""Host side of the PWM scan: log-odds weights and the MOODS-derived threshold.
+
+Mirrors mepp/motif_layers.py:12-78 of the reference (motif_matrix_to_conv1d_layer):
+instead of a Keras Conv1D layer it returns the scan table consumed by the CUDA scan
+kernel -- the same float32 filter weights (one or two filters) and the same bias
+-threshold.  The arithmetic runs in the C++ host code of libmepp_b200.so
+(mepp_log_odds / mepp_threshold_from_p / mepp_motif_table), as the reference runs
+MOODS' C++ on the host.
+"""
+import ctypes as C
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import _lib
+
+# MOODS' integer grid for the p-value DP (SURVEY.md section 8c fixes 1000.0).
+DP_PRECISION = 1000.0
+
+
+def flat_bg(alphabet_size=4):
+    """MOODS.tools.flat_bg (motif_layers.py:23)."""
+    return [1.0 / alphabet_size] * alphabet_size
+
+
+def _pd(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def log_odds(motif_matrix, bg=None, pseudocount=0.0001):
+    """MOODS.tools.log_odds as called at motif_layers.py:36-41.  Returns (4, m) float64."""
+    pwm = np.ascontiguousarray(motif_matrix, dtype=np.float64)
+    if pwm.ndim != 2 or pwm.shape[0] != 4:
+        raise ValueError("motif_matrix must have shape (4, m)")
+    bg = np.asarray(flat_bg(4) if bg is None else bg, dtype=np.float64)
+    W = np.empty_like(pwm)
+    _lib.check(_lib.lib.mepp_log_odds(_pd(pwm), pwm.shape[1], _pd(bg), float(pseudocount), _pd(W)), "log_odds")
+    return W
+
+
+def threshold_from_p(weights, bg=None, pvalue=0.0001, dp_precision=DP_PRECISION):
+    """MOODS.tools.threshold_from_p as called at motif_layers.py:44-48."""
+    W = np.ascontiguousarray(weights, dtype=np.float64)
+    bg = np.asarray(flat_bg(4) if bg is None else bg, dtype=np.float64)
+    thr = C.c_double(0.0)
+    _lib.check(_lib.lib.mepp_threshold_from_p(_pd(W), W.shape[1], _pd(bg), float(pvalue), float(dp_precision),
+                                              C.byref(thr)), "threshold_from_p")
+    return thr.value
+
+
+def motif_matrix_to_scan_table(motif_matrix, orientation='+', pseudocount=0.0001, pvalue=0.0001, bg=None,
+                               honour_flags=False, dp_precision=DP_PRECISION):
+    """Scan table for one (motif, orientation) task.
+
+    orientation '+' -> one filter W; '-' -> one filter W[::-1, ::-1] with the threshold of the
+    reversed matrix; anything else -> two filters sharing the forward threshold
+    (motif_layers.py:36-76, core.py:511-534).  With honour_flags=False the reference's
+    behaviour is reproduced: pseudocount / pvalue / bg never reach MOODS (core.py:513-534).
+    """
+    pwm = np.ascontiguousarray(motif_matrix, dtype=np.float64)
+    if pwm.ndim != 2 or pwm.shape[0] != 4:
+        raise ValueError("motif_matrix must have shape (4, m)")
+    m = pwm.shape[1]
+    if not 1 <= m <= _lib.MAX_MOTIF_LEN:
+        raise ValueError(f"motif length {m} outside [1, {_lib.MAX_MOTIF_LEN}]")
+    och = ord('+') if orientation == '+' else ord('-') if orientation == '-' else ord('d')
+    lut = np.zeros((_lib.MAX_MOTIF_LEN, 4, 2), dtype=np.float32)
+    bias = C.c_float(0.0)
+    nf = C.c_int(0)
+    thr = C.c_double(0.0)
+    bgp = None if bg is None else _pd(np.asarray(bg, dtype=np.float64))
+    _lib.check(_lib.lib.mepp_motif_table(
+        _pd(pwm), m, och, float(pseudocount), float(pvalue), bgp, 1 if honour_flags else 0, float(dp_precision),
+        lut.ctypes.data_as(C.POINTER(C.c_float)), C.byref(bias), C.byref(nf), C.byref(thr)), "motif_table")
+    return dict(lut=lut, bias=np.float32(bias.value), n_filters=nf.value, thr=thr.value, m=m)
+
+
+def scan_tables(tasks, n_threads=None, **kw):
+    """Scan tables for a list of (motif_matrix, orientation); the DP runs threaded (ctypes drops the GIL).
+    '+' and dual tasks of the same motif share one threshold computation through a small cache."""
+    cache = {}
+    keys = []
+    for pwm, orient in tasks:
+        o = orient if orient in ('+', '-') else 'd'
+        key = (np.ascontiguousarray(pwm, dtype=np.float64).tobytes(), np.shape(pwm), o)
+        keys.append(key)
+        cache.setdefault(key, (pwm, orient))
+    uniq = list(cache.items())
+    with ThreadPoolExecutor(max_workers=n_threads) as ex:
+        res = list(ex.map(lambda kv: motif_matrix_to_scan_table(kv[1][0], kv[1][1], **kw), uniq))
+    table = {kv[0]: r for kv, r in zip(uniq, res)}
+    return [table[k] for k in keys]

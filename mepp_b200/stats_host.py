@@ -1,0 +1,125 @@
+"""Host-side finalisation of the per-task statistics (L-length vectors only).
+
+Turns the order statistics / counts produced by the K3 CUDA kernels into the columns of
+the reference's positions_df, following mepp/core.py:269-413 and :438-454:
+numpy's "linear" percentile interpolation, permutation p-values = count / n, the
+parametric Fisher-z confidence interval and t-test, and the rolling-mean count smoothing.
+Everything here is O(T * L) numpy on vectors the GPU already reduced.
+"""
+import numpy as np
+from scipy import stats as _st
+
+POSITIONS_COLUMNS = [
+    'positional_r', 'position',
+    'permutation_full_positional_r_lower', 'permutation_full_positional_r_upper', 'permutation_full_positional_r_pval',
+    'permutation_semi_positional_r_lower', 'permutation_semi_positional_r_upper', 'permutation_semi_positional_r_pval',
+    'permutation_positional_r_lower', 'permutation_positional_r_upper', 'permutation_positional_r_pval',
+    'integral_r', 'permutation_integral_r_lower', 'permutation_integral_r_upper', 'permutation_integral_r_pval',
+    'positional_r_lower', 'positional_r_upper', 'positional_r_pval',
+    'count', 'smoothed_count',
+]
+POSITIONS_COLUMNS_NO_PERM = ['positional_r', 'position', 'positional_r_lower', 'positional_r_upper',
+                             'positional_r_pval', 'count', 'smoothed_count']
+
+
+def percentile_q(confidence_interval_pct):
+    """core.py:297-300."""
+    alpha = 1.0 - (confidence_interval_pct / 100.0)
+    return (100.0 * alpha / 2, 100.0 - 100.0 * alpha / 2)
+
+
+def virtual_index(n, q_pct):
+    """numpy 'linear' method on a float32 array: h = (n-1) * (q / float32(100)); returns (floor, gamma)."""
+    quant = np.true_divide(np.float64(q_pct), np.float32(100))
+    h = (n - 1) * quant
+    k = int(np.floor(h))
+    k = min(max(k, 0), n - 1)
+    return k, float(h - k)
+
+
+def lerp_f32(a, b, gamma):
+    """numpy's _lerp for float32 neighbours a, b and float64 gamma (difference taken in float32)."""
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    diff = np.subtract(b, a)  # float32, like numpy
+    out = a.astype(np.float64) + diff.astype(np.float64) * gamma
+    if gamma >= 0.5:
+        out = b.astype(np.float64) - diff.astype(np.float64) * (1 - gamma)
+    return out
+
+
+def parametric_ci(r32, num_samples, confidence_interval_pct=95):
+    """core.py:380-413 with the float32 arithmetic of the reference's numpy (value-based casting)."""
+    f = np.float32
+    r = np.asarray(r32, dtype=f)
+    n = num_samples
+    alpha = 1.0 - (confidence_interval_pct / 100.0)
+    z_margin = f(_st.norm.ppf(1.0 - alpha / 2.0) * np.sqrt(1.0 / (n - 3)))
+    eps = np.finfo(f).eps
+    with np.errstate(invalid='ignore', divide='ignore', over='ignore'):
+        z_r = f(0.5) * np.log((f(1) + r + eps) / (f(1) - r + eps))
+        lower = (np.exp(f(2) * (z_r - z_margin) + eps) - f(1)) / (np.exp(f(2) * (z_r - z_margin) + eps) + f(1))
+        upper = (np.exp(f(2) * (z_r + z_margin) + eps) - f(1)) / (np.exp(f(2) * (z_r + z_margin) + eps) + f(1))
+        t = r / np.sqrt((f(1) - (r * r)) / f(n - 2))
+        pval = _st.t.sf(np.abs(t), n - 1) * 2
+    return lower, upper, pval
+
+
+def smooth_counts(count, window):
+    """core.py:438-454 along the last axis: centred rolling mean, NaN edges ffill/bfill-ed."""
+    count = np.asarray(count, dtype=np.float64)
+    L = count.shape[-1]
+    out = np.full(count.shape, np.nan)
+    h = window // 2
+    if L >= window:
+        c = np.concatenate([np.zeros(count.shape[:-1] + (1,)), np.cumsum(count, axis=-1)], axis=-1)
+        out[..., h:L - h] = (c[..., window:] - c[..., :L - window + 1]) / window
+        out[..., :h] = out[..., h:h + 1]
+        out[..., L - h:] = out[..., L - h - 1:L - h]
+    return out
+
+
+def finalize_positions(r0, full_os, full_cnt, semi_os, semi_cnt, integral, count, n_seq, P, margin,
+                       confidence_interval_pct=95, center=None, permutation_mode='semi'):
+    """Assemble the positions_df columns for T tasks.
+
+    r0 (T, L) f32; full_os (T, L, 4) f32; full_cnt (T, L); semi_os (T, 4) f32; semi_cnt (T, L);
+    integral (T, 1+P) f64; count (T, L).  Returns {column: (T, L) array} in reference order.
+    """
+    T, L = r0.shape
+    if center is None:
+        center = L // 2
+    cols = {}
+    cols['positional_r'] = r0.astype(np.float32)
+    cols['position'] = np.broadcast_to(np.arange(L) - center, (T, L))
+    if P > 0:
+        q = percentile_q(confidence_interval_pct)
+        (_, g_lo), (_, g_hi) = virtual_index(P, q[0]), virtual_index(P, q[1])
+        cols['permutation_full_positional_r_lower'] = lerp_f32(full_os[..., 0], full_os[..., 1], g_lo)
+        cols['permutation_full_positional_r_upper'] = lerp_f32(full_os[..., 2], full_os[..., 3], g_hi)
+        cols['permutation_full_positional_r_pval'] = full_cnt.astype(np.float64) / float(P)
+        (_, gs_lo), (_, gs_hi) = virtual_index(L * P, q[0]), virtual_index(L * P, q[1])
+        s_lo = lerp_f32(semi_os[:, 0], semi_os[:, 1], gs_lo)
+        s_hi = lerp_f32(semi_os[:, 2], semi_os[:, 3], gs_hi)
+        cols['permutation_semi_positional_r_lower'] = np.broadcast_to(s_lo[:, None], (T, L))
+        cols['permutation_semi_positional_r_upper'] = np.broadcast_to(s_hi[:, None], (T, L))
+        cols['permutation_semi_positional_r_pval'] = semi_cnt.astype(np.float64) / float(L * P)
+        for suf in ('positional_r_lower', 'positional_r_upper', 'positional_r_pval'):
+            cols[f'permutation_{suf}'] = cols[f'permutation_{permutation_mode}_{suf}']
+        # np.trapz on the float32 r array yields float32 (core.py:352); percentiles over the P permuted integrals
+        integ32 = integral.astype(np.float32)
+        ipct = np.percentile(integ32[:, 1:], q, axis=-1)
+        ipval = np.mean((integ32[:, 1:] >= integ32[:, 0:1]).astype(float), axis=-1)
+        cols['integral_r'] = np.broadcast_to(integ32[:, 0:1], (T, L))
+        cols['permutation_integral_r_lower'] = np.broadcast_to(ipct[0][:, None], (T, L))
+        cols['permutation_integral_r_upper'] = np.broadcast_to(ipct[1][:, None], (T, L))
+        cols['permutation_integral_r_pval'] = np.broadcast_to(ipval[:, None], (T, L))
+    lo, up, pv = parametric_ci(cols['positional_r'], n_seq, confidence_interval_pct)
+    cols['positional_r_lower'] = lo
+    cols['positional_r_upper'] = up
+    cols['positional_r_pval'] = pv
+    cnt = count.astype(np.float64)
+    cols['count'] = cnt
+    cols['smoothed_count'] = smooth_counts(cnt, 1 + 2 * margin) if margin > 0 else cnt
+    order = POSITIONS_COLUMNS if P > 0 else POSITIONS_COLUMNS_NO_PERM
+    return {k: cols[k] for k in order}
