@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MEPP profiling hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2]
+
+Metric (BASELINE.json): Gbp*motifs/s scanned + profiled = N_seq * L * tasks / seconds, tasks =
+motifs x orientations.  A "step" is one pass of the whole hot path (scan -> tcgen05 profile GEMM ->
+correlation -> permutation statistics) over every task of the workload on synthetic scored FASTA
+of the named shape.  `value` times steps whose inputs are already staged in HBM; `e2e` times the
+same step through the public API from pinned HOST buffers: H2D of sequences / scores /
+permutation indices, 2-bit pack, score-operand build, host MOODS thresholds, all tasks, and D2H of
+every result table.  With --gpus N the tasks are sharded over N ranks (weak scaling: N copies of
+the task list, one per GPU; every rank stages its own replica) and the per-task tables are
+gathered to rank 0 with one NCCL collective.
+
+--impl reference times the CPU baseline (oracle/baseline.py: the reference's algorithm on the
+host cores; the reference's own TensorFlow/MOODS code cannot run in this image) on a bounded
+sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Gbp*motifs/s scanned+profiled"
+UNIT = "Gbp*motifs/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p.get("bf16_tflops_sustained",
+                    p["bf16_tflops"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.lines:
+            if not (t0 <= t <= t1 + 0.2):
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
+
+
+def build_workload(workload, world):
+    from mepp_b200 import synth
+    cfg = synth.make_config(workload)
+    base = [(pwm, o) for _, pwm, o in cfg["tasks"]]
+    tasks = base * world                       # weak scaling: per-GPU work fixed
+    return cfg, tasks
+
+
+def run_reference(args, rank, world):
+    """CPU baseline arm: rank 0 only; other ranks exit 0 without work."""
+    if rank != 0:
+        return
+    from oracle import baseline, staging
+    cfg, tasks = build_workload(args.workload, 1)
+    codes = staging.ascii_to_codes(cfg["ascii"])
+    Y = staging.permuted_scores(cfg["scores"], cfg["perm_idx"])
+    z = staging.gc_ratio_global(codes)
+    cores = os.cpu_count() or 1
+    per_step_budget = max(2.0, min(20.0, 100.0 / max(1, args.steps + args.warmup)))
+    n_done = 0
+    for _ in range(args.warmup):
+        baseline.time_sample(codes, Y, z, tasks, cfg["margin"], threads=cores, budget_s=per_step_budget / 2)
+    total_t, total_tasks = 0.0, 0
+    for _ in range(args.steps):
+        t, n_done = baseline.time_sample(codes, Y, z, tasks, cfg["margin"], threads=cores, budget_s=per_step_budget)
+        total_t += t
+        total_tasks += n_done
+    value = cfg["N"] * cfg["L"] * total_tasks / total_t / 1e9
+    sample = (f"{total_tasks} whole tasks of {args.workload} (first {n_done} motif x orientation tasks per step, "
+              f"N={cfg['N']} L={cfg['L']} P={cfg['P']}), float32 scan in C + BLAS sgemm profile + numpy stats")
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * total_t / max(1, args.steps), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=args.workload, N=cfg["N"], L=cfg["L"], P=cfg["P"], margin=cfg["margin"],
+                            tasks=len(tasks)),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    from mepp_b200 import parallel, motif_layers, build
+    build.build()
+    rank, world, local = parallel.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; mepp_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    from mepp_b200.engine import Engine
+    import torch.distributed as dist
+
+    cfg, tasks = build_workload(args.workload, world)
+    N, L, P, margin = cfg["N"], cfg["L"], cfg["P"], cfg["margin"]
+    T_total = len(tasks)
+    costs = [parallel.task_cost(pwm.shape[1], 1 if o in ('+', '-') else 2) for pwm, o in tasks]
+    my_ids = parallel.shard_tasks(costs, world)[rank]
+    my_tasks = [tasks[i] for i in my_ids]
+
+    # pinned host inputs (the e2e path copies them every step)
+    h_ascii = torch.from_numpy(cfg["ascii"]).pin_memory()
+    h_scores = torch.from_numpy(cfg["scores"]).pin_memory()
+    h_perm = torch.from_numpy(cfg["perm_idx"]).pin_memory()
+    h2d_bytes = h_ascii.numel() + 4 * h_scores.numel() + 4 * h_perm.numel() + len(my_tasks) * (32 * 4 * 2 * 4 + 12)
+
+    eng = Engine(device=local)
+    ncols = None
+
+    def e2e_step():
+        """Public-API step from host buffers: stage + thresholds + all tasks + gather."""
+        nonlocal ncols
+        eng.stage(h_ascii, h_scores, h_perm, use_gc=True)
+        tables = motif_layers.scan_tables(my_tasks)
+        batch = eng.profile(my_tasks, margin=margin, tables=tables)
+        block = np.stack([np.asarray(batch.positions[k], dtype=np.float64) for k in batch.positions], axis=-1)
+        ncols = block.shape[-1]
+        full = parallel.gather_blocks(block, my_ids, T_total, device=dev if world > 1 else None)
+        return batch, full
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    # ---- warm-up (e2e style so that every buffer exists), then the two timed regions
+    for _ in range(max(args.warmup, 1)):
+        batch, full = e2e_step()
+    tables = motif_layers.scan_tables(my_tasks)
+    d2h_bytes = int(sum(np.asarray(v).nbytes for v in batch.positions.values()) + batch.density.nbytes)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+
+    # (1) device-resident: inputs staged in HBM before the timed region
+    eng.stage(h_ascii, h_scores, h_perm, use_gc=True)
+    sync_all()
+    eng.timing = {}
+    launches0 = eng.launches
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.profile(my_tasks, margin=margin, tables=tables)
+    sync_all()
+    t1 = time.perf_counter()
+    launches = eng.launches - launches0
+    stage_ms = eng.collect_timing()
+    eng.timing = None
+    dt_value = parallel.barrier_and_max(t1 - t0, device=dev if world > 1 else None)
+
+    # (2) end to end from pinned host buffers
+    sync_all()
+    t2 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    sync_all()
+    t3 = time.perf_counter()
+    dt_e2e = parallel.barrier_and_max(t3 - t2, device=dev if world > 1 else None)
+    clocks = sampler.stop(t0, t3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    work_step = float(N) * L * T_total                      # bp x tasks per step, all ranks
+    value = work_step * args.steps / dt_value / 1e9
+    e2e_value = work_step * args.steps / dt_e2e / 1e9
+    n_local = len(my_tasks)
+    groups = -(-n_local // eng.group_size())
+    # per-kernel rooflines from the CUDA-event stage times of the timed value region (rank 0's share)
+    C_ = 1 + P
+    scan_bytes = 4.0 * N * L * n_local * args.steps          # fp16 hi+lo planes written once (4 B / bp*task)
+    gemm_alg = 2.0 * L * N * C_ * n_local * args.steps
+    kernels = {}
+    if stage_ms.get("scan"):
+        a = scan_bytes / (stage_ms["scan"] * 1e-3) / 1e9
+        kernels["scan"] = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"],
+                               ms_per_step=stage_ms["scan"] / args.steps, launches_per_step=groups)
+    if stage_ms.get("gemm"):
+        a = 3.0 * gemm_alg / (stage_ms["gemm"] * 1e-3) / 1e12
+        kernels["profile_gemm"] = dict(bound="tensor", achieved=a, peak=peaks["tf_sustained"], unit="TFLOP/s",
+                                       frac=a / peaks["tf_sustained"], frac_of_burst=a / peaks["tf_burst"],
+                                       algorithmic_tflops=a / 3.0, split_products=3,
+                                       ms_per_step=stage_ms["gemm"] / args.steps, launches_per_step=groups)
+    for k in ("correlation", "perm_stats"):
+        if stage_ms.get(k):
+            kernels[k] = dict(ms_per_step=stage_ms[k] / args.steps)
+    dominant = max(("scan", "profile_gemm"), key=lambda k: kernels.get(k, {}).get("ms_per_step", 0.0))
+    dk = kernels.get(dominant, {})
+    roofline = dict(kernel=dominant, bound=dk.get("bound"), achieved=dk.get("achieved"), peak=dk.get("peak"),
+                    unit=dk.get("unit"), frac=dk.get("frac"), traffic=None, peak_source=peaks["source"],
+                    note=("achieved = executed tensor FLOPs (3 fp16 products per algorithmic FLOP) / CUDA-event "
+                          "time; peak = sustained cuBLAS bf16" if dominant == "profile_gemm" else
+                          "achieved = 4 B per bp*task (fp16 hi+lo X planes written once) / CUDA-event time"))
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import baseline, staging
+        codes = staging.ascii_to_codes(cfg["ascii"])
+        Y = staging.permuted_scores(cfg["scores"], cfg["perm_idx"])
+        z = staging.gc_ratio_global(codes)
+        cores = os.cpu_count() or 1
+        t, n_done = baseline.time_sample(codes, Y, z, tasks, margin, threads=cores, budget_s=15.0)
+        cpu_baseline = dict(value=N * L * n_done / t / 1e9, unit=UNIT, cores=cores, kind="port",
+                            sample=f"first {n_done} tasks of {args.workload} (N={N}, L={L}, P={P}) in {t:.1f} s; "
+                                   f"float32 scan in C + BLAS sgemm profile + numpy statistics")
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 1),
+                ms_per_step=1e3 * dt_value / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload=args.workload, N=N, L=L, P=P, margin=margin, tasks_total=T_total,
+                            tasks_per_gpu=n_local, orientations="+,+/-", parallelism=f"tasks sharded over {world} GPU(s)",
+                            l2="inputs larger than L2 (X planes %.1f GB per group)" % (4.0 * N * L * min(n_local, eng.group_size()) / 1e9),
+                            gemm="fp16 hi/lo split, 3 tcgen05 products, fp32 TMEM accumulate"),
+                e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=1e3 * dt_e2e / args.steps,
+                         h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
+                gpu_launches=int(launches), roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline, clocks=clocks)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

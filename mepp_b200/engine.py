@@ -84,6 +84,7 @@ class Engine:
         self.staged = False
         self._bufs = {}
         self.launches = 0   # kernels launched by this engine (bench.py reports it)
+        self.timing = None  # set to {} to collect per-stage CUDA-event times (ms) in _run_group
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -245,6 +246,23 @@ class Engine:
         return ProfileBatch(list(range(T_all)), positions, density[:, :N], self.scores, thr,
                             hit_counts=cat('hit_count'), hits=hits, r=r, n_seq=N)
 
+    def _mark(self, prev, name):
+        """CUDA-event stage timer on the launching stream (only when self.timing is a dict)."""
+        if self.timing is None:
+            return None
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record(self.torch.cuda.current_stream(self.device))
+        if prev is not None:
+            self.timing.setdefault('_pairs', []).append((name, prev, e))
+        return e
+
+    def collect_timing(self):
+        """Sum the recorded stage times (ms) per stage name; call after a synchronize."""
+        out = {}
+        for name, a, b in (self.timing or {}).get('_pairs', []):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
     def _run_group(self, tables, margin, return_hits, return_r, hits_cap, ci):
         torch = self.torch
         T = len(tables)
@@ -268,19 +286,23 @@ class Engine:
         if return_hits:
             cap = int(hits_cap) if hits_cap else max(1 << 20, int(T * N * L * 2e-3))
             hits_d = self._buf('hits', cap * 16, torch.uint8)
+        ev = self._mark(None, None)
         _lib.check(_lib.lib.mepp_scan(_ptr(self.codes_T), _ptr(self.nmask_T), _ptr(self.zhat), N, L, T, int(margin),
                                       _ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), _ptr(x_planes),
                                       _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap,
                                       _ptr(hit_count), st), "scan")
         S = self._buf('S', (m_rows, self.ldS), torch.float32)
+        ev = self._mark(ev, 'scan')
         _lib.check(_lib.lib.mepp_profile_gemm(_ptr(x_planes), _ptr(self.y_planes), _ptr(S), m_rows, C_, self.n_pad,
                                               st), "profile_gemm")
+        ev = self._mark(ev, 'gemm')
         r = self._buf('r', (m_rows, C_), torch.float32)
         zsum = self._zsum()
         _lib.check(_lib.lib.mepp_correlation(_ptr(S), self.ldS, _ptr(rowstats), _ptr(self.col_syz), _ptr(self.ysum),
                                              zsum.ctypes.data_as(C.POINTER(C.c_double)), N, m_rows, C_,
                                              1 if self.use_gc else 0, _ptr(r), st), "correlation")
         self.launches += 3 + (m_rows + 65534) // 65535 - 1
+        ev = self._mark(ev, 'correlation')
         out = {}
         if P > 0:
             q = stats_host.percentile_q(ci)
@@ -298,6 +320,7 @@ class Engine:
                                                 _ptr(full_cnt), _ptr(semi_os), _ptr(semi_cnt), _ptr(integral),
                                                 _ptr(work), st), "perm_stats")
             self.launches += 6
+            ev = self._mark(ev, 'perm_stats')
             out.update(full_os=full_os.cpu().numpy(), full_cnt=full_cnt.cpu().numpy(),
                        semi_os=semi_os.cpu().numpy(), semi_cnt=semi_cnt.cpu().numpy(),
                        integral=integral.cpu().numpy())

@@ -1,0 +1,175 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  Bit-exact for match positions / scores / counts; profiles,
+confidence intervals within 1e-5 relative (with a floor tied to the row scale); p-values
+reported with their discrete flips."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import profile, staging  # noqa: E402
+
+
+def _engine():
+    if not torch.cuda.is_available():
+        pytest.fail("pytest -m gpu needs a CUDA device")
+    from mepp_b200.engine import Engine
+    return Engine()
+
+
+def _r_close(r_gpu, r_orc, rel=1e-5, floor_frac=1e-5):
+    """|dr| <= rel*|r| + floor_frac * (row scale), row scale = max_c |r[l, c]|."""
+    d = np.abs(r_gpu.astype(np.float64) - r_orc.astype(np.float64))
+    scale = np.abs(r_orc).max(axis=-1, keepdims=True)
+    return d <= rel * np.abs(r_orc) + floor_frac * scale + 1e-12
+
+
+def _oracle_inputs(cfg):
+    codes = staging.ascii_to_codes(cfg["ascii"])
+    Y = staging.permuted_scores(cfg["scores"], cfg["perm_idx"]) if cfg["perm_idx"] is not None and len(cfg["perm_idx"]) \
+        else cfg["scores"][:, None]
+    return codes, Y, staging.gc_ratio_global(codes)
+
+
+@pytest.fixture(scope="module")
+def cfg1():
+    from mepp_b200 import synth
+    return synth.make_config("cfg1")
+
+
+def test_pack_matches_oracle(cfg1):
+    eng = _engine().stage(cfg1["ascii"], cfg1["scores"], cfg1["perm_idx"])
+    N, L = cfg1["N"], cfg1["L"]
+    codes = staging.ascii_to_codes(cfg1["ascii"])
+    cT = eng.codes_T.cpu().numpy().view(np.uint32)
+    mT = eng.nmask_T.cpu().numpy().view(np.uint32)
+    dec = np.zeros((N, L), dtype=np.int8)
+    for i in range(L):
+        c = (cT[i // 16, :N] >> (2 * (i % 16))) & 3
+        dec[:, i] = np.where(((mT[i // 32, :N] >> (i % 32)) & 1) == 1, 4, c)
+    assert np.array_equal(dec, codes)
+    assert np.array_equal(eng.gc[:N].cpu().numpy(), staging.gc_ratio_global(codes))   # bit-exact float32
+    assert (eng.gc[N:].cpu().numpy() == 0).all()
+
+
+def test_config1_full_parity(cfg1):
+    """BASELINE.json configs[0]: 1000 x 201 bp, ohler motifs, '+' and '+/-', 100 permutations, margin 2."""
+    eng = _engine().stage(cfg1["ascii"], cfg1["scores"], cfg1["perm_idx"])
+    tasks = [(pwm, o) for _, pwm, o in cfg1["tasks"]]
+    batch = eng.profile(tasks, margin=cfg1["margin"], return_hits=True, return_r=True)
+    codes, Y, z = _oracle_inputs(cfg1)
+    flips = 0
+    for t, (pwm, o) in enumerate(tasks):
+        orc = profile.profile_task(codes, Y, z, pwm, o, margin=cfg1["margin"])
+        X0 = batch.motif_score_matrix(t, cfg1["L"])
+        assert np.array_equal(X0.view(np.uint32), orc["X0"].view(np.uint32)), f"task {t}: match scores not bit-exact"
+        assert batch.thr[t] == orc["thr"]
+        assert np.array_equal(batch.density[t], orc["ranks"]["density"])
+        assert _r_close(batch.r[t], orc["r"]).all(), f"task {t}: r outside tolerance"
+        pos = batch.positions
+        assert list(pos.keys()) == profile.POSITIONS_COLUMNS
+        for col in profile.POSITIONS_COLUMNS:
+            a = np.asarray(pos[col][t], dtype=np.float64)
+            b = np.asarray(orc["positions"][col], dtype=np.float64)
+            if col.endswith("_pval") and col.startswith("permutation"):
+                flips += int((np.abs(a - b) > 1e-12).sum())
+                assert np.abs(a - b).max() <= 0.05
+            elif col in ("position", "count", "smoothed_count"):
+                assert np.array_equal(a, b), col
+            elif col == "positional_r_pval":
+                assert np.allclose(a, b, rtol=1e-3, atol=1e-9), col
+            else:
+                scale = max(np.abs(b).max(), 1e-30)
+                assert np.abs(a - b).max() <= 1e-5 * scale + 2e-7, (col, np.abs(a - b).max(), scale)
+    # p-values are discrete (k/P): a 1-ulp difference in r can flip a '>='; report, allow a handful
+    print("permutation p-value flips over all tasks:", flips)
+    assert flips <= 20
+
+
+@pytest.mark.parametrize("orientation", ['+', '-', '+/-'])
+@pytest.mark.parametrize("margin", [0, 1, 5])
+def test_orientations_and_margins(orientation, margin):
+    from mepp_b200 import synth
+    rng = np.random.default_rng(5)
+    ascii_u8, scores = synth.synth_sequences(333, 77, seed=99, n_rate=0.02, lower_rate=0.02)   # ragged N (not % 32)
+    perm = synth.synth_permutations(333, 17, seed=99)
+    motifs = synth.synth_motifs(5, seed=3, m_lo=4, m_hi=32)
+    eng = _engine().stage(ascii_u8, scores, perm)
+    tasks = [(m, orientation) for m in motifs]
+    batch = eng.profile(tasks, margin=margin, return_hits=True, return_r=True)
+    codes = staging.ascii_to_codes(ascii_u8)
+    Y = staging.permuted_scores(scores, perm)
+    z = staging.gc_ratio_global(codes)
+    for t, (pwm, o) in enumerate(tasks):
+        orc = profile.profile_task(codes, Y, z, pwm, o, margin=margin)
+        X0 = batch.motif_score_matrix(t, 77)
+        assert np.array_equal(X0.view(np.uint32), orc["X0"].view(np.uint32))
+        assert _r_close(batch.r[t], orc["r"]).all()
+        assert np.array_equal(np.asarray(batch.positions["count"][t]), orc["positions"]["count"])
+        assert np.array_equal(np.asarray(batch.positions["smoothed_count"][t]), orc["positions"]["smoothed_count"])
+
+
+def test_edge_cases_all_n_no_hits_and_no_permutations():
+    from mepp_b200 import synth
+    L, N = 64, 40
+    ascii_u8 = np.full((N, L), ord('N'), dtype=np.uint8)
+    ascii_u8[::2] = np.frombuffer(b"ACGT" * 16, dtype=np.uint8)
+    scores = np.linspace(-1, 1, N).astype(np.float32)
+    cons = np.zeros((4, 8)); cons[[0, 1, 2, 3, 0, 1, 2, 3], np.arange(8)] = 1.0
+    uniform = np.full((4, 6), 0.25)
+    eng = _engine().stage(ascii_u8, scores, None)            # P = 0: no permutation columns
+    batch = eng.profile([(cons, '+'), (uniform, '+/-')], margin=2, return_hits=True, return_r=True)
+    assert list(batch.positions.keys()) == ['positional_r', 'position', 'positional_r_lower', 'positional_r_upper',
+                                            'positional_r_pval', 'count', 'smoothed_count']
+    codes = staging.ascii_to_codes(ascii_u8)
+    z = staging.gc_ratio_global(codes)
+    for t, (pwm, o) in enumerate([(cons, '+'), (uniform, '+/-')]):
+        orc = profile.profile_task(codes, scores[:, None], z, pwm, o, margin=2)
+        assert np.array_equal(batch.motif_score_matrix(t, L).view(np.uint32), orc["X0"].view(np.uint32))
+        assert _r_close(batch.r[t], orc["r"]).all()
+    assert (batch.density[1] == 0).all() and (np.asarray(batch.positions['positional_r'][1]) == 0).all()   # NaN -> 0
+    # all-N sequences never match; ACGT-repeat sequences match the consensus at every 4th position
+    assert (batch.density[0][1::2] == 0).all() and (batch.density[0][::2] > 0).all()
+
+
+def test_gemm_matches_float64_check_kernel():
+    """tcgen05 GEMM vs the CUDA-core float64 contraction of the same fp16 planes, K = 4096 sequences."""
+    from mepp_b200 import _lib, synth
+    from mepp_b200.engine import _ptr
+    ascii_u8, scores = synth.synth_sequences(4096 + 5, 130, seed=4, motifs=synth.synth_motifs(2, seed=8))
+    perm = synth.synth_permutations(4101, 300, seed=4)
+    eng = _engine().stage(ascii_u8, scores, perm)
+    motifs = synth.synth_motifs(3, seed=8)
+    eng.profile([(m, '+/-') for m in motifs], margin=2)
+    m_rows = 3 * 130
+    Sd = torch.empty((m_rows, eng.C), dtype=torch.float64, device='cuda')
+    _lib.check(_lib.lib.mepp_profile_gemm_check(_ptr(eng._bufs['x_planes']), _ptr(eng.y_planes), _ptr(Sd), m_rows,
+                                                eng.C, eng.n_pad, None, m_rows, None))
+    torch.cuda.synchronize()
+    S = eng._bufs['S'][:m_rows * eng.ldS].view(m_rows, eng.ldS)[:, :eng.C].double()
+    rowmax = Sd.abs().amax(dim=1, keepdim=True)
+    ok = (S - Sd).abs() <= 1e-5 * rowmax + 1e-3
+    assert bool(ok.all()), f"max err/rowmax {(((S - Sd).abs()) / rowmax.clamp_min(1e-30)).max().item():.3e}"
+
+
+def test_reference_entry_point_returns_the_reference_tuple(cfg1):
+    """dataset_and_motif_matrix_to_profile_data keeps core.py:490-632's signature and 5-tuple."""
+    from mepp_b200 import core, utils, permutations
+    from mepp_b200.dataset import ScoredDataset
+    ds = ScoredDataset(cfg1["ascii"], cfg1["scores"])
+    ds = permutations.add_permuted_scores_to_dataset(utils.append_gc_ratios_to_dataset(ds), num_permutations=100,
+                                                    perm_indices=cfg1["perm_idx"])
+    pwm = cfg1["tasks"][0][1]
+    msm, positions_df, ranks_df, processed, smoothed = core.dataset_and_motif_matrix_to_profile_data(
+        ds, pwm, orientation='+/-', motif_margin=2)
+    codes, Y, z = _oracle_inputs(cfg1)
+    orc = profile.profile_task(codes, Y, z, pwm, '+/-', margin=2)
+    assert msm.shape == (cfg1["N"], cfg1["L"]) and np.array_equal(msm.view(np.uint32), orc["X0"].view(np.uint32))
+    assert list(positions_df.columns) == profile.POSITIONS_COLUMNS
+    assert list(ranks_df.columns) == ['rank', 'score', 'density']
+    assert np.array_equal(ranks_df['density'].to_numpy(), orc["ranks"]["density"])
+    assert np.array_equal(ranks_df['score'].to_numpy(), cfg1["scores"])
+    sm = smoothed.motif_scores()
+    assert np.allclose(sm, profile.blur(orc["X0"], 2, dtype=np.float32), atol=1e-6)

@@ -1,0 +1,193 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the host-side
+threshold code agrees with the oracle, host statistics agree with numpy / the oracle, and the
+staging layer keeps the reference's semantics.  No GPU compute is called here."""
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import moods, profile, staging
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "mepp_b200.h")).read()
+    declared = set(re.findall(r"\b(mepp_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib.lib, name), f"{name} declared in include/mepp_b200.h but not exported"
+    assert declared == set(lib.SIGNATURES), "ctypes signatures out of sync with the header"
+    assert lib.lib.mepp_abi_version() == 1
+
+
+def test_device_entry_points_fail_loudly_without_gpu(lib):
+    import ctypes as C
+    if lib.device_ok():
+        pytest.skip("a GPU is present")
+    rc = lib.lib.mepp_pack_dna(C.c_void_p(16), 4, 8, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), None)
+    assert rc != 0 and "no sm_100 CUDA device" in lib.last_error()
+    from mepp_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine()
+    from mepp_b200 import utils
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        utils.force_cpu_only()
+
+
+def test_host_threshold_matches_oracle_on_shipped_libraries(lib):
+    from mepp_b200 import motif_layers, synth
+    for libname in ("ohler", "homer_clustered"):
+        for key, pwm in synth.load_motif_library(libname).items():
+            for o in ('+', '-', '+/-'):
+                tab = motif_layers.motif_matrix_to_scan_table(pwm, o)
+                Wf, Wr, thr = profile.motif_weights(pwm, o)
+                m = pwm.shape[1]
+                assert tab['thr'] == thr, (key, o)
+                assert tab['bias'] == np.float32(-thr)
+                assert np.array_equal(tab['lut'][:m, :, 0], Wf.T)
+                assert tab['n_filters'] == (2 if Wr is not None else 1)
+                if Wr is not None:
+                    assert np.array_equal(tab['lut'][:m, :, 1], Wr.T)
+                assert (tab['lut'][m:] == 0).all()
+
+
+def test_host_threshold_honours_flags_only_when_asked(lib):
+    from mepp_b200 import motif_layers, synth
+    pwm = list(synth.load_motif_library("ohler").values())[0]
+    a = motif_layers.motif_matrix_to_scan_table(pwm, '+', pseudocount=0.01, pvalue=0.001)
+    b = motif_layers.motif_matrix_to_scan_table(pwm, '+')
+    assert a['thr'] == b['thr']                       # reference quirk: flags never reach MOODS (core.py:513-534)
+    c = motif_layers.motif_matrix_to_scan_table(pwm, '+', pseudocount=0.01, pvalue=0.001, honour_flags=True)
+    W = moods.log_odds(pwm, moods.flat_bg(), 0.01)
+    assert c['thr'] == moods.threshold_from_p(W, moods.flat_bg(), 0.001) and c['thr'] < b['thr']
+    with pytest.raises(ValueError):
+        motif_layers.motif_matrix_to_scan_table(np.full((4, 40), 0.25), '+')
+
+
+def test_log_odds_and_threshold_wrappers(lib):
+    from mepp_b200 import motif_layers
+    rng = np.random.default_rng(1)
+    pwm = rng.dirichlet(np.ones(4), size=9).T
+    W = motif_layers.log_odds(pwm)
+    assert np.allclose(W, moods.log_odds(pwm, moods.flat_bg(), 1e-4), rtol=0, atol=1e-15)
+    for p in (1e-4, 1e-3):
+        assert motif_layers.threshold_from_p(W, pvalue=p) == moods.threshold_bruteforce(W, moods.flat_bg(), p)
+
+
+def test_lerp_matches_numpy_percentile():
+    from mepp_b200 import stats_host
+    rng = np.random.default_rng(2)
+    for P in (4, 100, 1000, 777):
+        r = rng.normal(scale=0.01, size=(13, P)).astype(np.float32)
+        for ci in (95, 90, 50):
+            q = stats_host.percentile_q(ci)
+            want = np.percentile(r, q, axis=-1)
+            s = np.sort(r, axis=-1)
+            for i, qq in enumerate(q):
+                k, g = stats_host.virtual_index(P, qq)
+                got = stats_host.lerp_f32(s[:, k], s[:, min(k + 1, P - 1)], g)
+                assert np.array_equal(got, want[i]), (P, ci, i)
+
+
+def test_finalize_positions_matches_oracle_columns():
+    """Feed finalize_positions exact order statistics / counts computed on the host from a random r."""
+    from mepp_b200 import stats_host
+    rng = np.random.default_rng(3)
+    T, L, P, N = 3, 41, 60, 500
+    r = rng.normal(scale=0.05, size=(T, L, 1 + P)).astype(np.float32)
+    r[0, 5, :] = 0.0
+    count = rng.integers(0, 9, size=(T, L))
+    q = stats_host.percentile_q(95)
+    k_lo, _ = stats_host.virtual_index(P, q[0]); k_hi, _ = stats_host.virtual_index(P, q[1])
+    ks_lo, _ = stats_host.virtual_index(L * P, q[0]); ks_hi, _ = stats_host.virtual_index(L * P, q[1])
+    s = np.sort(r[:, :, 1:], axis=-1)
+    full_os = np.stack([s[..., k_lo], s[..., k_lo + 1], s[..., k_hi], s[..., min(k_hi + 1, P - 1)]], axis=-1)
+    full_cnt = (np.abs(r[:, :, 1:]) >= np.abs(r[:, :, 0:1])).sum(-1)
+    flat = np.sort(r[:, :, 1:].reshape(T, -1), axis=-1)
+    semi_os = np.stack([flat[:, ks_lo], flat[:, ks_lo + 1], flat[:, ks_hi], flat[:, min(ks_hi + 1, L * P - 1)]], axis=-1)
+    semi_cnt = (np.abs(r[:, :, 1:]).reshape(T, 1, -1) >= np.abs(r[:, :, 0])[:, :, None]).sum(-1)
+    a = np.abs(r).astype(np.float64)
+    integral = (0.5 * (a[:, 1:] + a[:, :-1])).sum(axis=1)
+    cols = stats_host.finalize_positions(r[:, :, 0], full_os, full_cnt, semi_os, semi_cnt, integral, count, N, P, 2)
+    for t in range(T):
+        want = profile.positional_r_columns(r[t])
+        lo, up, pv = profile.parametric_ci(want['positional_r'], N)
+        want.update(positional_r_lower=lo, positional_r_upper=up, positional_r_pval=pv,
+                    count=count[t].astype(float), smoothed_count=profile.smooth_counts(count[t].astype(float), 5))
+        assert list(cols.keys()) == profile.POSITIONS_COLUMNS
+        for k in profile.POSITIONS_COLUMNS:
+            a_, b_ = np.asarray(cols[k][t], dtype=np.float64), np.asarray(want[k], dtype=np.float64)
+            if 'integral' in k:
+                assert np.allclose(a_, b_, rtol=1e-6, atol=1e-7), k     # float32 trapz summation order
+            else:
+                assert np.array_equal(a_, b_), k
+
+
+def test_smooth_counts_matches_pandas_rolling():
+    import pandas as pd
+    from mepp_b200 import stats_host
+    c = np.random.default_rng(4).integers(0, 50, size=37).astype(float)
+    for w in (3, 5, 11):
+        want = (pd.DataFrame(dict(position=np.arange(37), count=c)).set_index('position')
+                .rolling(w, center=True).mean().reset_index().ffill().bfill())['count'].to_numpy()
+        assert np.allclose(stats_host.smooth_counts(c, w), want, rtol=0, atol=1e-12)
+        assert np.allclose(profile.smooth_counts(c, w), want, rtol=0, atol=1e-12)
+
+
+def test_io_parsers_match_oracle_and_reference_rules():
+    from mepp_b200 import io as mio
+    txt = ">m1 NAME\n1 2 3\n1 1 1\n2 1 0\n0 0 0\n>m2\n1 0\n0 1\n0 0\n0 0\n>m1 NAME\n4 0 0\n0 4 0\n0 0 4\n0 0 0\n"
+    d, cons = mio.motif_matrix_file_to_dicts(io.StringIO(txt))
+    o = staging.parse_motifs(txt)
+    assert list(d.keys()) == list(o.keys()) == ["m1 NAME", "m2"]
+    for k in d:
+        assert np.array_equal(d[k], o[k])
+    assert cons["m1 NAME"] == "ACG" and cons["m2 m2"] == "AC"
+    fa = ">s1 2.5 extra\nACGT\nAC\n>s2 1.0\nACGTNN\n>s3 7\nACG\n>s4\nACGTAC\n"
+    assert mio.scored_fasta_file_to_dicts(io.StringIO(fa)) == staging.parse_scored_fasta(fa)
+
+
+def test_filter_order_dataset_roundtrip(tmp_path):
+    from mepp_b200 import io as mio, utils, permutations
+    fa = "".join(f">s{i} {s}\n{seq}\n" for i, (s, seq) in enumerate(
+        [(3.0, "ACGTAC"), (1.0, "ACGTNN"), (2.0, "acgtAC"), (0.5, "ACG"), (2.5, "TTTTTT")]))
+    dicts = mio.scored_fasta_file_to_dicts(io.StringIO(fa))
+    df = utils.order_scored_fasta_df(utils.filter_scored_fasta_df(utils.scored_fasta_dicts_to_df(*dicts), 50),
+                                     random_state=0)
+    assert list(df['sequence_id']) == ['s1', 's4', 's0']       # s3 short, s2 66 % degenerate (lowercase), sorted by score
+    assert list(df.columns) == ['sequence_id', 'sequence', 'score', 'description', 'length', 'degenerate_pct', 'rank']
+    ds = utils.append_gc_ratios_to_dataset(utils.scored_fasta_df_to_dataset(df))
+    ds = permutations.add_permuted_scores_to_dataset(ds, num_permutations=7, seed=1)
+    assert ds.num_permutations == 7 and ds.has_gc and ds.sequence_length == 6 and len(ds.element_spec) == 3
+    assert sorted(ds.perm_idx[3]) == [0, 1, 2]
+    assert permutations.add_permuted_scores_to_dataset(ds, num_permutations=0) is ds
+    path = str(tmp_path / "dataset")
+    mio.save_dataset(ds, path, delete_existing=True)
+    assert os.path.exists(path + ".element_spec.p")
+    ds2 = mio.load_dataset(path)
+    assert np.array_equal(ds2.ascii, ds.ascii) and np.array_equal(ds2.perm_idx, ds.perm_idx) and ds2.has_gc
+
+
+def test_synthetic_generator_is_deterministic_and_shaped():
+    from mepp_b200 import synth
+    a = synth.make_config("cfg1", n_motifs=2)
+    b = synth.make_config("cfg1", n_motifs=2)
+    assert np.array_equal(a["ascii"], b["ascii"]) and np.array_equal(a["perm_idx"], b["perm_idx"])
+    assert a["ascii"].shape == (1000, 201) and a["perm_idx"].shape == (100, 1000) and len(a["tasks"]) == 4
+    assert (np.diff(a["scores"]) >= 0).all()
+    frac_n = (a["ascii"] == ord('N')).mean()
+    assert 0.0005 < frac_n < 0.005
+    assert len(synth.load_motif_library("homer_clustered")) == 162       # 164 headers, 2 duplicate keys
+
+
+def test_layout_decoders_roundtrip():
+    from mepp_b200 import layout
+    rng = np.random.default_rng(0)
+    m_rows, n_pad = 200, 64
+    MT, KB = 2, 2
+    raw = rng.integers(0, 1000, size=(MT, KB, 2, 4, 128, 8)).astype(np.float16)
+    hi, lo = layout.decode_x_planes(raw.view(np.uint8).ravel(), m_rows, n_pad)
+    assert hi[130, 41] == np.float32(raw[1, 1, 0, 1, 2, 1]) and lo[5, 7] == np.float32(raw[0, 0, 1, 0, 5, 7])
