@@ -54,12 +54,15 @@ int mepp_threshold_from_p(const double* W, int m, const double* bg, double pvalu
  * dual), replacing motif_matrix_to_conv1d_layer (motif_layers.py:12-78):
  *   lut   float [MEPP_MAX_MOTIF_LEN][4][2]  (tap, base, filter) float32 weights, zero padded
  *   bias  float32(-thr)  ; n_filters 1 or 2 ; thr double (for reporting)
+ *   qtab  uint32 [16][16], qthr uint32 [2]: conservative 16-bit integer pre-filter of the scan
+ *         kernel (pairs of taps, both filters packed low/high); may be NULL
  * use_flags: 0 = reproduce the reference (pseudocount/pvalue/bg never reach MOODS,
  * core.py:513-534, so 1e-4 / 1e-4 / flat are used); 1 = honour the arguments. */
 int mepp_motif_table(const double* pwm, int m, int orientation_char,
                      double pseudocount, double pvalue, const double* bg, int use_flags,
                      double dp_precision,
-                     float* lut, float* bias, int* n_filters, double* thr);
+                     float* lut, float* bias, int* n_filters, double* thr,
+                     uint32_t* qtab, uint32_t* qthr);
 
 /* ------------------------------------------------------------------ layout sizes */
 int64_t mepp_codes_words(int L);            /* Wc */
@@ -91,7 +94,7 @@ int mepp_build_y(const float* yhat_dev, const int32_t* perm_dev, const float* zh
  * Replaces the conv model + ReLU + margin blur + counts/density
  * (motif_layers.py:80-165, core.py:25-145, core.py:415-470) for a group of T tasks.
  *   lut_dev   float [T][MEPP_MAX_MOTIF_LEN][4][2]   bias_dev float [T]
- *   mlen_dev  int32 [T]   nfilt_dev int32 [T]
+ *   mlen_dev  int32 [T]   nfilt_dev int32 [T]   qtab_dev uint32 [T][256]   qthr_dev uint32 [T][2]
  *   x_planes_dev  A operand (rows t*L+l), written densely
  *   rowstats_dev  double [T*L][3]: sum_n x, sum_n x^2, sum_n x*zhat  (x = blurred score); zeroed by the call
  *   count_dev     int32 [T*L]  : #sequences with an unsmoothed match at each position; zeroed by the call
@@ -101,6 +104,7 @@ int mepp_build_y(const float* yhat_dev, const int32_t* perm_dev, const float* zh
 int mepp_scan(const uint32_t* codes_T_dev, const uint32_t* nmask_T_dev, const float* zhat_dev,
               int64_t N, int L, int T, int margin,
               const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev, const int32_t* nfilt_dev,
+              const uint32_t* qtab_dev, const uint32_t* qthr_dev,
               void* x_planes_dev, double* rowstats_dev, int32_t* count_dev, int32_t* density_dev,
               void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev, void* stream);
 

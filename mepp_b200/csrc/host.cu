@@ -13,6 +13,55 @@ void set_error(const std::string& msg) { g_err = msg; }
 int fail(const std::string& msg) { g_err = msg; return 1; }
 }  // namespace mepp
 
+
+namespace mepp {
+// Conservative integer pre-filter for the scan kernel (csrc/scan.cu): per filter f and tap j the
+// float32 weights are shifted to be >= 0 and quantised DOWN to a common grid, q = floor((W - min_c W) * scale),
+// scale chosen so that the largest possible sum fits 16 bits.  For the real-valued score S of a window,
+//   sum_q <= scale * (S - lo) < sum_q + m,        lo = sum_j min_c W[c][j],
+// and the float32 sequentially rounded score differs from S by less than delta, so a window can only
+// pass the threshold if sum_q >= qthr.  Both filters are packed into one 32-bit entry (low / high half),
+// and two adjacent taps share one 16-entry table indexed by the 4-bit pair of 2-bit codes.
+static void build_filter_table(const float* lut, int m, int n_filters, float bias, uint32_t* qtab, uint32_t* qthr) {
+  double rsum[2] = {0.0, 0.0}, lo[2] = {0.0, 0.0}, absmax = 0.0;
+  double mn[2][MEPP_MAX_MOTIF_LEN];
+  for (int f = 0; f < n_filters; ++f)
+    for (int j = 0; j < m; ++j) {
+      double a = lut[(j * 4 + 0) * 2 + f], b = a, am = std::fabs(a);
+      for (int c = 1; c < 4; ++c) {
+        double w = lut[(j * 4 + c) * 2 + f];
+        a = std::min(a, w); b = std::max(b, w); am = std::max(am, std::fabs(w));
+      }
+      mn[f][j] = a; lo[f] += a; rsum[f] += b - a; absmax += am;
+    }
+  const double rmax = std::max(rsum[0], rsum[1]);
+  const double scale = rmax > 0.0 ? 65535.0 / rmax * (1.0 - 1e-9) : 1.0;
+  // |float32 sequential sum - real sum| <= m roundings of at most ulp(absmax)/2 each; doubled for safety
+  const double delta = 2.0 * m * absmax * 5.97e-8 + 1e-6;
+  const double thr32 = -(double)bias;
+  for (int t = 0; t < 16; ++t)
+    for (int e = 0; e < 16; ++e) {
+      uint32_t packed = 0;
+      for (int f = 0; f < n_filters; ++f) {
+        uint32_t q = 0;
+        for (int h = 0; h < 2; ++h) {
+          const int j = 2 * t + h, c = (e >> (2 * h)) & 3;
+          if (j < m) q += (uint32_t)std::floor(((double)lut[(j * 4 + c) * 2 + f] - mn[f][j]) * scale);
+        }
+        packed |= (q & 0xffffu) << (16 * f);
+      }
+      qtab[t * 16 + e] = packed;
+    }
+  for (int f = 0; f < 2; ++f) {
+    if (f >= n_filters) { qthr[f] = 0x10000u; continue; }           // unreachable for a 16-bit sum
+    const double need = scale * (thr32 - delta - lo[f]) - (double)m;  // candidates have sum_q > need
+    long long qq = need < 0.0 ? 0 : (long long)std::floor(need) + 1;
+    if (qq > 0x10000) qq = 0x10000;
+    qthr[f] = (uint32_t)qq;
+  }
+}
+}  // namespace mepp
+
 extern "C" {
 
 int mepp_abi_version(void) { return MEPP_B200_ABI_VERSION; }
@@ -114,7 +163,8 @@ int mepp_threshold_from_p(const double* W, int m, const double* bg, double p,
 
 int mepp_motif_table(const double* pwm, int m, int orientation_char,
                      double pseudocount, double pvalue, const double* bg_in, int use_flags,
-                     double dp_precision, float* lut, float* bias, int* n_filters, double* thr_out) {
+                     double dp_precision, float* lut, float* bias, int* n_filters, double* thr_out,
+                     uint32_t* qtab, uint32_t* qthr) {
   MEPP_REQUIRE(pwm && lut && bias && n_filters, "motif_table: null argument");
   MEPP_REQUIRE(m >= 1 && m <= MEPP_MAX_MOTIF_LEN, "motif_table: motif length must be in [1, 32]");
   double bg[4] = {0.25, 0.25, 0.25, 0.25};
@@ -146,6 +196,7 @@ int mepp_motif_table(const double* pwm, int m, int orientation_char,
   *bias = (float)(-thr);
   *n_filters = f1 ? 2 : 1;
   if (thr_out) *thr_out = thr;
+  if (qtab && qthr) mepp::build_filter_table(lut, m, *n_filters, *bias, qtab, qthr);
   return 0;
 }
 

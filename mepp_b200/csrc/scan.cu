@@ -8,14 +8,21 @@
 // mepp/core.py:59-145, the raw-moment sums over x of mepp/core.py:238-253 and the
 // count / density reductions of mepp/core.py:415-470.
 //
-// Float32 summation order (declared canonical order, identical to oracle/profile.py):
+// Float32 summation order of a score (declared canonical order, identical to oracle/profile.py):
 //   acc = 0; for tap j ascending: acc = fl32(acc + W[base_j][j]);  an N base adds the four
 //   quarter weights .25*W[A..T][j] one after the other;  s = fl32(acc + fl32(-thr)).
 //
+// Two-level evaluation.  Matches are rare (p = 1e-4 per strand), so every window first goes
+// through a conservative 16-bit integer pre-filter (host.cu: build_filter_table): pairs of
+// taps index a 16-entry table whose entries hold BOTH filters' quantised partial sums in
+// one 32-bit word, so one conflict-free LDS + one IADD advance two taps of two strands.
+// Only windows whose integer sum reaches the per-filter bound -- or that contain an N --
+// are queued and evaluated exactly in the canonical float32 order, warp-compacted so that
+// all 32 lanes work on candidates.  The filter has no false negatives by construction, so
+// every reported score comes from the exact path and is bit-identical to the oracle.
+//
 // Work decomposition: one CTA = one k-block (32 sequences) x 4 tasks; one warp = one
-// task; one lane = one sequence, walking the positions left to right.  Lanes of a
-// warp always look up the same tap, so a LUT read touches at most 4 distinct
-// addresses in 4 distinct banks (conflict free).
+// task; in the filter pass one lane = one sequence walking the positions left to right.
 #include "common.cuh"
 
 namespace mepp {
@@ -24,139 +31,114 @@ struct HitRec { int32_t task, seq, pos; float x0; };
 
 constexpr int kScanWarps = 4;
 constexpr int kRowStride = 36;  // floats per position row of the x0 staging buffer (32 + 4 pad)
+constexpr int kQueue = 64;      // candidate ring (flushed whenever 32 are pending)
 
 struct ScanArgs {
   const uint32_t* codes_T; const uint32_t* nmask_T; const float* zhat;
   int64_t N, n_pad, KB;
   int L, T, margin, Wc, Wm, strideC, strideM;
   const float* lut; const float* bias; const int32_t* mlen; const int32_t* nfilt;
+  const uint32_t* qtab; const uint32_t* qthr;
   uint8_t* x_planes; double* rowstats; int32_t* count; int32_t* density;
   HitRec* hits; int64_t hits_cap; unsigned long long* hit_count;
 };
 
-template <bool DUAL>
-__device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const int kb,
-                                          const uint32_t* __restrict__ my_codes,
-                                          const uint32_t* __restrict__ my_mask,
-                                          float2* __restrict__ s_lut, float* __restrict__ s_buf,
-                                          const float* __restrict__ s_z, const int lane) {
-  const unsigned full = 0xffffffffu;
-  const int L = a.L, mg = a.margin;
-  const int m = a.mlen[t];
-  const int padl = (m - 1) / 2;          // motif_layers.py:99-101
-  const int n_valid = L - m + 1;         // 'valid' convolution outputs
-  const float bias = a.bias[t];
-  const int64_t n = (int64_t)kb * 32 + lane;
-  const bool real = n < a.N;
+// Per-warp (= per task) state shared by the helper routines below.  The helpers are
+// deliberately NOT inlined and NOT templated: one small instruction stream for every task keeps
+// the kernel inside the instruction cache (an earlier variant specialised on motif length and
+// strand count, 26k SASS instructions, and spent most of its time on instruction fetch).
+struct TaskCtx {
+  const float2* s_lut; const uint32_t* s_codes; const uint32_t* s_mask; float* s_buf; const float* s_z;
+  uint16_t* s_queue;
+  int t, kb, m, padl, mg, L, strideC, strideM, dual;
+  uint32_t mbits; float bias;
+};
 
-  const float2* g_lut = reinterpret_cast<const float2*>(a.lut) + (size_t)t * (MEPP_MAX_MOTIF_LEN * 4);
-  for (int i = lane; i < MEPP_MAX_MOTIF_LEN * 4; i += 32) s_lut[i] = g_lut[i];
-  __syncwarp();
-
-  const int m4 = (m + 3) & ~3;           // taps padded with zero weights (adding +0 is exact)
-  const uint32_t mbits = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
-  const int k = 1 + 2 * mg;
-  const float kf = (float)k;
-  const int nbuf = 32 + 2 * mg;
-  const int kc = lane & 3, rsub = lane >> 2;
-
-  int dens = 0;
-  int loaded_cw = -1, loaded_mw = -1;
-  uint32_t w0 = 0, w1 = 0, w2 = 0, mw0 = 0, mw1 = 0;
-
-  for (int base = 0; base < L; base += 32) {
-    int b_start = 0;
-    if (base != 0) {
-      // carry the last 2*margin rows of the previous chunk to the front
-      for (int b = 0; b < 2 * mg; ++b) s_buf[b * kRowStride + lane] = s_buf[(32 + b) * kRowStride + lane];
-      b_start = 2 * mg;
+// Exact canonical-order score of the window starting at base i of one sequence.
+__device__ __forceinline__ float exact_x0(const TaskCtx& c, const uint32_t* __restrict__ codes,
+                                          const uint32_t* __restrict__ mask, int i) {
+  const int cw = i >> 4, mw = i >> 5;
+  const uint32_t w0 = codes[cw], w1 = codes[cw + 1], w2 = codes[cw + 2];
+  const uint32_t lo = __funnelshift_r(w0, w1, 2 * (i & 15));
+  const uint32_t hi = __funnelshift_r(w1, w2, 2 * (i & 15));
+  const uint32_t nwin = __funnelshift_r(mask[mw], mask[mw + 1], i & 31) & c.mbits;
+  float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll 1
+  for (int j = 0; j < c.m; ++j) {
+    const uint32_t code = (j < 16 ? (lo >> (2 * j)) : (hi >> (2 * (j - 16)))) & 3u;
+    const float2* l4 = c.s_lut + j * 4;
+    if ((nwin >> j) & 1u) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const float2 w = l4[cc];
+        a0 = __fadd_rn(a0, __fmul_rn(0.25f, w.x));
+        a1 = __fadd_rn(a1, __fmul_rn(0.25f, w.y));
+      }
+    } else {
+      const float2 w = l4[code];
+      a0 = __fadd_rn(a0, w.x);
+      a1 = __fadd_rn(a1, w.y);
     }
-    // ---- phase A: unsmoothed thresholded scores x0 for positions base-mg+b ----
-    for (int b = b_start; b < nbuf; ++b) {
-      const int p = base - mg + b;
-      const int i = p - padl;            // window start
-      float x0 = 0.0f;
-      if (i >= 0 && i < n_valid) {       // warp uniform
-        const int cw = i >> 4, mw = i >> 5;
-        if (cw != loaded_cw) { w0 = my_codes[cw]; w1 = my_codes[cw + 1]; w2 = my_codes[cw + 2]; loaded_cw = cw; }
-        if (mw != loaded_mw) { mw0 = my_mask[mw]; mw1 = my_mask[mw + 1]; loaded_mw = mw; }
-        const uint32_t lo = __funnelshift_r(w0, w1, 2 * (i & 15));   // bases i .. i+15
-        const uint32_t hi = __funnelshift_r(w1, w2, 2 * (i & 15));   // bases i+16 .. i+31
-        const uint32_t nwin = __funnelshift_r(mw0, mw1, i & 31) & mbits;
-        float a0 = 0.0f, a1 = 0.0f;
-        for (int j0 = 0; j0 < m4; j0 += 4) {
-          const uint32_t v = j0 < 16 ? (lo >> (2 * j0)) : (hi >> (2 * (j0 - 16)));
-          const float2* l4 = s_lut + j0 * 4;
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const uint32_t c = (v >> (2 * jj)) & 3u;
-            const float2 w = l4[jj * 4 + c];
-            a0 = __fadd_rn(a0, w.x);
-            if (DUAL) a1 = __fadd_rn(a1, w.y);
-          }
-        }
-        if (nwin != 0u) {
-          // window contains N: redo in the canonical order with four quarter-weight adds per N tap
-          a0 = 0.0f; a1 = 0.0f;
-          for (int j = 0; j < m; ++j) {
-            const uint32_t c = (j < 16 ? (lo >> (2 * j)) : (hi >> (2 * (j - 16)))) & 3u;
-            const float2* l4 = s_lut + j * 4;
-            if ((nwin >> j) & 1u) {
-#pragma unroll
-              for (int cc = 0; cc < 4; ++cc) {
-                a0 = __fadd_rn(a0, __fmul_rn(0.25f, l4[cc].x));
-                if (DUAL) a1 = __fadd_rn(a1, __fmul_rn(0.25f, l4[cc].y));
-              }
-            } else {
-              a0 = __fadd_rn(a0, l4[c].x);
-              if (DUAL) a1 = __fadd_rn(a1, l4[c].y);
-            }
-          }
-        }
-        float s = __fadd_rn(a0, bias);
-        if (DUAL) s = fmaxf(s, __fadd_rn(a1, bias));
-        x0 = real ? fmaxf(s, 0.0f) : 0.0f;
-        const bool hit = x0 > 0.0f;
-        const unsigned bal = __ballot_sync(full, hit);
-        if (bal != 0u) {
-          const int nh = __popc(bal);
-          unsigned long long slot0 = 0;
-          if (lane == 0) {
-            atomicAdd(&a.count[(int64_t)t * L + p], nh);
-            if (a.hit_count) slot0 = atomicAdd(a.hit_count, (unsigned long long)nh);
-          }
-          if (a.hits) {
-            slot0 = __shfl_sync(full, slot0, 0);
-            if (hit) {
-              const unsigned long long slot = slot0 + (unsigned)__popc(bal & ((1u << lane) - 1u));
-              if ((int64_t)slot < a.hits_cap) {
-                HitRec rec; rec.task = t; rec.seq = (int32_t)n; rec.pos = p; rec.x0 = x0;
-                a.hits[slot] = rec;
-              }
-            }
-          }
-          dens += hit ? 1 : 0;
+  }
+  float s = __fadd_rn(a0, c.bias);
+  if (c.dual) s = fmaxf(s, __fadd_rn(a1, c.bias));
+  return fmaxf(s, 0.0f);
+}
+
+// Evaluate up to 32 queued candidates (one per lane) exactly; publish matches.  Returns (warp
+// uniform) whether any candidate was a match.
+__device__ __noinline__ bool flush_candidates(const ScanArgs& a, const TaskCtx& c, int q_head, int count, int base,
+                                              int lane) {
+  __syncwarp();
+  bool any_hit = false;
+  if (lane < count) {
+    const uint32_t e = c.s_queue[(q_head + lane) & (kQueue - 1)];
+    const int s = (int)(e >> 8), b = (int)(e & 0xffu);
+    const int p = base - c.mg + b;
+    const float x0 = exact_x0(c, c.s_codes + s * c.strideC, c.s_mask + s * c.strideM, p - c.padl);
+    if (x0 > 0.0f) {
+      any_hit = true;
+      c.s_buf[b * kRowStride + s] = x0;
+      const int64_t ns = (int64_t)c.kb * 32 + s;
+      atomicAdd(&a.count[(int64_t)c.t * c.L + p], 1);
+      atomicAdd(&a.density[(int64_t)c.t * a.n_pad + ns], 1);
+      if (a.hit_count) {
+        const unsigned long long slot = atomicAdd(a.hit_count, 1ull);
+        if (a.hits && (int64_t)slot < a.hits_cap) {
+          HitRec rec; rec.task = c.t; rec.seq = (int32_t)ns; rec.pos = p; rec.x0 = x0;
+          a.hits[slot] = rec;
         }
       }
-      s_buf[b * kRowStride + lane] = x0;
     }
-    __syncwarp();
-    // ---- phase B: blur, row sums, fp16 split, tiled store; lane = (kc, rsub) ----
+  }
+  return __any_sync(0xffffffffu, any_hit);
+}
+
+// Phase B of one 32-position chunk: blur, row sums, fp16 split, tiled store; lane = (kc, rsub).
+__device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, int base, bool chunk_nz, int lane) {
+  const unsigned full = 0xffffffffu;
+  const int kc = lane & 3, rsub = lane >> 2;
+  const int mg = c.mg, L = c.L;
+  const int k = 1 + 2 * mg;
+  const float kf = (float)k;
 #pragma unroll 1
-    for (int it = 0; it < 4; ++it) {
-      const int rl = rsub + 8 * it;
-      const int p = base + rl;
-      const bool valid = p < L;
+  for (int it = 0; it < 4; ++it) {
+    const int rl = rsub + 8 * it;
+    const int p = base + rl;
+    const bool valid = p < L;
+    uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+    if (chunk_nz) {                    // warp uniform; most chunks hold no match at all
       const bool interior = valid && p >= mg && p <= L - 1 - mg;   // core.py:79-91 zero edges
       float xb[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) xb[q] = 0.0f;
       if (interior) {
-        const float* row = s_buf + rl * kRowStride + kc * 8;  // buffer row rl+d <-> position p-mg+d
+        const float* row = c.s_buf + rl * kRowStride + kc * 8;  // buffer row rl+d <-> position p-mg+d
         float4 u0 = *reinterpret_cast<const float4*>(row);
         float4 u1 = *reinterpret_cast<const float4*>(row + 4);
         xb[0] = u0.x; xb[1] = u0.y; xb[2] = u0.z; xb[3] = u0.w;
         xb[4] = u1.x; xb[5] = u1.y; xb[6] = u1.z; xb[7] = u1.w;
+#pragma unroll 1
         for (int d = 1; d < k; ++d) {
           u0 = *reinterpret_cast<const float4*>(row + d * kRowStride);
           u1 = *reinterpret_cast<const float4*>(row + d * kRowStride + 4);
@@ -179,7 +161,7 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const double v = (double)xb[q];
-          sx += v; sxx += v * v; sxz += v * (double)s_z[kc * 8 + q];
+          sx += v; sxx += v * v; sxz += v * (double)c.s_z[kc * 8 + q];
         }
       }
       if (__any_sync(full, nz)) {
@@ -187,11 +169,11 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
         sxx += __shfl_xor_sync(full, sxx, 1); sxx += __shfl_xor_sync(full, sxx, 2);
         sxz += __shfl_xor_sync(full, sxz, 1); sxz += __shfl_xor_sync(full, sxz, 2);
         if (kc == 0 && valid && sxx != 0.0) {
-          double* rs = a.rowstats + ((int64_t)t * L + p) * 3;
+          double* rs = a.rowstats + ((int64_t)c.t * L + p) * 3;
           atomicAdd(rs + 0, sx); atomicAdd(rs + 1, sxx); atomicAdd(rs + 2, sxz);
         }
       }
-      if (valid) {
+      if (nz) {
         uint32_t h[4], l[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -201,16 +183,109 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
           h[q] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
           l[q] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
         }
-        const int64_t r = (int64_t)t * L + p;
-        uint8_t* tile = a.x_planes + a_tile_offset(r >> 7, kb, a.KB);
-        const int row = (int)(r & 127);
-        *reinterpret_cast<uint4*>(tile + a_chunk_offset(0, kc, row)) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(tile + a_chunk_offset(1, kc, row)) = make_uint4(l[0], l[1], l[2], l[3]);
+        vh = make_uint4(h[0], h[1], h[2], h[3]);
+        vl = make_uint4(l[0], l[1], l[2], l[3]);
       }
     }
+    if (valid) {
+      const int64_t r = (int64_t)c.t * L + p;
+      uint8_t* tile = a.x_planes + a_tile_offset(r >> 7, c.kb, a.KB);
+      const int row = (int)(r & 127);
+      *reinterpret_cast<uint4*>(tile + a_chunk_offset(0, kc, row)) = vh;
+      *reinterpret_cast<uint4*>(tile + a_chunk_offset(1, kc, row)) = vl;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pair_sum(const char* qt, int g, uint32_t v) {
+  return *reinterpret_cast<const uint32_t*>(qt + (2 * g) * 64 + ((v << 2) & 0x3Cu)) +
+         *reinterpret_cast<const uint32_t*>(qt + (2 * g + 1) * 64 + ((v >> 2) & 0x3Cu));
+}
+
+__device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const int kb,
+                                          const uint32_t* __restrict__ s_codes, const uint32_t* __restrict__ s_mask,
+                                          float2* __restrict__ s_lut, uint32_t* __restrict__ s_qtab,
+                                          float* __restrict__ s_buf, uint16_t* __restrict__ s_queue,
+                                          const float* __restrict__ s_z, const int lane) {
+  const unsigned full = 0xffffffffu;
+  const int L = a.L, mg = a.margin;
+  const int m = a.mlen[t];
+  const int g2 = (m + 3) >> 2;           // 4-tap groups (two 16-entry pair tables each)
+  const int padl = (m - 1) / 2;          // motif_layers.py:99-101
+  const int n_valid = L - m + 1;         // 'valid' convolution outputs
+  const bool real = (int64_t)kb * 32 + lane < a.N;
+
+  const float2* g_lut = reinterpret_cast<const float2*>(a.lut) + (size_t)t * (MEPP_MAX_MOTIF_LEN * 4);
+  for (int i = lane; i < MEPP_MAX_MOTIF_LEN * 4; i += 32) s_lut[i] = g_lut[i];
+  for (int i = lane; i < 256; i += 32) s_qtab[i] = a.qtab[(size_t)t * 256 + i];
+  const uint32_t q0 = a.qthr[t * 2 + 0], q1 = a.qthr[t * 2 + 1];
+  __syncwarp();
+
+  TaskCtx c;
+  c.s_lut = s_lut; c.s_codes = s_codes; c.s_mask = s_mask; c.s_buf = s_buf; c.s_z = s_z; c.s_queue = s_queue;
+  c.t = t; c.kb = kb; c.m = m; c.padl = padl; c.mg = mg; c.L = L; c.strideC = a.strideC; c.strideM = a.strideM;
+  c.dual = a.nfilt[t] == 2;
+  c.mbits = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
+  c.bias = a.bias[t];
+
+  const int nbuf = 32 + 2 * mg;
+  const uint32_t* my_codes = s_codes + lane * a.strideC;
+  const uint32_t* my_mask = s_mask + lane * a.strideM;
+  const char* qt = reinterpret_cast<const char*>(s_qtab);
+
+  int loaded_cw = -1, loaded_mw = -1;
+  uint32_t w0 = 0, w1 = 0, w2 = 0, mw0 = 0, mw1 = 0;
+  int q_head = 0, q_tail = 0;            // warp-uniform ring indices
+  bool carry_nz = false;                 // previous chunk left non-zero x0 in the carried rows
+
+  for (int base = 0; base < L; base += 32) {
+    int b_start = 0;
+    if (base != 0) {
+      // carry the last 2*margin rows of the previous chunk to the front
+      for (int b = 0; b < 2 * mg; ++b) s_buf[b * kRowStride + lane] = s_buf[(32 + b) * kRowStride + lane];
+      b_start = 2 * mg;
+    }
+    bool new_nz = false;
+    // ---- phase A: integer pre-filter over positions base-mg+b, candidates queued ----
+#pragma unroll 1
+    for (int b = b_start; b < nbuf; ++b) {
+      const int i = base - mg + b - padl;  // window start
+      s_buf[b * kRowStride + lane] = 0.0f;
+      if (i >= 0 && i < n_valid) {         // warp uniform
+        const int cw = i >> 4, mw = i >> 5;
+        if (cw != loaded_cw) { w0 = my_codes[cw]; w1 = my_codes[cw + 1]; w2 = my_codes[cw + 2]; loaded_cw = cw; }
+        if (mw != loaded_mw) { mw0 = my_mask[mw]; mw1 = my_mask[mw + 1]; loaded_mw = mw; }
+        const uint32_t lo = __funnelshift_r(w0, w1, 2 * (i & 15));   // bases i .. i+15
+        const uint32_t nwin = __funnelshift_r(mw0, mw1, i & 31) & c.mbits;
+        uint32_t sum = pair_sum(qt, 0, lo);
+        if (g2 > 1) sum += pair_sum(qt, 1, lo >> 8);
+        if (g2 > 2) sum += pair_sum(qt, 2, lo >> 16);
+        if (g2 > 3) sum += pair_sum(qt, 3, lo >> 24);
+        if (g2 > 4) {
+          const uint32_t hi = __funnelshift_r(w1, w2, 2 * (i & 15)); // bases i+16 .. i+31
+          sum += pair_sum(qt, 4, hi);
+          if (g2 > 5) sum += pair_sum(qt, 5, hi >> 8);
+          if (g2 > 6) sum += pair_sum(qt, 6, hi >> 16);
+          if (g2 > 7) sum += pair_sum(qt, 7, hi >> 24);
+        }
+        const bool cand = real && (((sum & 0xffffu) >= q0) | ((sum >> 16) >= q1) | (nwin != 0u));
+        const unsigned bal = __ballot_sync(full, cand);
+        if (bal != 0u) {
+          if (cand) {
+            const int slot = q_tail + __popc(bal & ((1u << lane) - 1u));
+            s_queue[slot & (kQueue - 1)] = (uint16_t)((lane << 8) | b);
+          }
+          q_tail += __popc(bal);
+          if (q_tail - q_head >= 32) { new_nz |= flush_candidates(a, c, q_head, 32, base, lane); q_head += 32; }
+        }
+      }
+    }
+    if (q_tail != q_head) { new_nz |= flush_candidates(a, c, q_head, q_tail - q_head, base, lane); q_head = q_tail; }
+    __syncwarp();
+    store_chunk(a, c, base, carry_nz | new_nz, lane);
+    carry_nz = new_nz;
     __syncwarp();
   }
-  a.density[(int64_t)t * a.n_pad + n] = real ? dens : 0;
 }
 
 __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const ScanArgs a) {
@@ -221,9 +296,11 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const ScanArgs a)
   // carve shared memory
   float* s_bufs = reinterpret_cast<float*>(smem_raw);                                   // [warps][nbuf][36]
   float2* s_luts = reinterpret_cast<float2*>(s_bufs + kScanWarps * nbuf * kRowStride);  // [warps][128]
-  uint32_t* s_codes = reinterpret_cast<uint32_t*>(s_luts + kScanWarps * MEPP_MAX_MOTIF_LEN * 4);
+  uint32_t* s_qtabs = reinterpret_cast<uint32_t*>(s_luts + kScanWarps * MEPP_MAX_MOTIF_LEN * 4);  // [warps][256]
+  uint32_t* s_codes = s_qtabs + kScanWarps * 256;
   uint32_t* s_mask = s_codes + 32 * a.strideC;
   float* s_z = reinterpret_cast<float*>(s_mask + 32 * a.strideM);                       // [32]
+  uint16_t* s_queues = reinterpret_cast<uint16_t*>(s_z + 32);                           // [warps][kQueue]
 
   for (int idx = threadIdx.x; idx < a.Wc * 32; idx += blockDim.x) {
     const int s = idx & 31, w = idx >> 5;
@@ -243,21 +320,21 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const ScanArgs a)
   if (t >= a.T) return;
   float* s_buf = s_bufs + warp * nbuf * kRowStride;
   float2* s_lut = s_luts + warp * MEPP_MAX_MOTIF_LEN * 4;
-  const uint32_t* my_codes = s_codes + lane * a.strideC;
-  const uint32_t* my_mask = s_mask + lane * a.strideM;
-  if (a.nfilt[t] == 2) scan_task<true>(a, t, kb, my_codes, my_mask, s_lut, s_buf, s_z, lane);
-  else                 scan_task<false>(a, t, kb, my_codes, my_mask, s_lut, s_buf, s_z, lane);
+  uint32_t* s_qtab = s_qtabs + warp * 256;
+  uint16_t* s_queue = s_queues + warp * kQueue;
+  scan_task(a, t, kb, s_codes, s_mask, s_lut, s_qtab, s_buf, s_queue, s_z, lane);
 }
 
 }  // namespace mepp
 
 extern "C" int mepp_scan(const uint32_t* codes_T_dev, const uint32_t* nmask_T_dev, const float* zhat_dev,
                          int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
-                         const int32_t* mlen_dev, const int32_t* nfilt_dev, void* x_planes_dev,
-                         double* rowstats_dev, int32_t* count_dev, int32_t* density_dev, void* hits_dev,
-                         int64_t hits_cap, unsigned long long* hit_count_dev, void* stream) {
+                         const int32_t* mlen_dev, const int32_t* nfilt_dev, const uint32_t* qtab_dev,
+                         const uint32_t* qthr_dev, void* x_planes_dev, double* rowstats_dev, int32_t* count_dev,
+                         int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
+                         void* stream) {
   using namespace mepp;
-  MEPP_REQUIRE(codes_T_dev && nmask_T_dev && lut_dev && bias_dev && mlen_dev && nfilt_dev &&
+  MEPP_REQUIRE(codes_T_dev && nmask_T_dev && lut_dev && bias_dev && mlen_dev && nfilt_dev && qtab_dev && qthr_dev &&
                x_planes_dev && rowstats_dev && count_dev && density_dev, "scan: null pointer");
   MEPP_REQUIRE(N > 0 && L > 0 && T > 0, "scan: empty input");
   MEPP_REQUIRE(margin >= 0 && margin <= MEPP_MAX_MARGIN, "scan: margin must be in [0, 16]");
@@ -271,20 +348,23 @@ extern "C" int mepp_scan(const uint32_t* codes_T_dev, const uint32_t* nmask_T_de
   a.Wc = (int)mepp_codes_words(L); a.Wm = (int)mepp_nmask_words(L);
   a.strideC = a.Wc | 1; a.strideM = a.Wm | 1;
   a.lut = lut_dev; a.bias = bias_dev; a.mlen = mlen_dev; a.nfilt = nfilt_dev;
+  a.qtab = qtab_dev; a.qthr = qthr_dev;
   a.x_planes = reinterpret_cast<uint8_t*>(x_planes_dev); a.rowstats = rowstats_dev;
   a.count = count_dev; a.density = density_dev;
   a.hits = reinterpret_cast<HitRec*>(hits_dev); a.hits_cap = hits_cap; a.hit_count = hit_count_dev;
   const int nbuf = 32 + 2 * margin;
   size_t smem = sizeof(float) * kScanWarps * nbuf * kRowStride + sizeof(float2) * kScanWarps * MEPP_MAX_MOTIF_LEN * 4 +
-                sizeof(uint32_t) * 32 * (a.strideC + a.strideM) + sizeof(float) * 32;
+                sizeof(uint32_t) * kScanWarps * 256 + sizeof(uint32_t) * 32 * (a.strideC + a.strideM) +
+                sizeof(float) * 32 + sizeof(uint16_t) * kScanWarps * kQueue;
   MEPP_REQUIRE(smem <= 200 * 1024, "scan: sequence too long for the shared-memory staging (L too large)");
   MEPP_CUDA_CHECK(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MEPP_CUDA_CHECK(cudaMemsetAsync(rowstats_dev, 0, sizeof(double) * 3 * (size_t)T * L, st));
   MEPP_CUDA_CHECK(cudaMemsetAsync(count_dev, 0, sizeof(int32_t) * (size_t)T * L, st));
+  MEPP_CUDA_CHECK(cudaMemsetAsync(density_dev, 0, sizeof(int32_t) * (size_t)T * a.n_pad, st));
   if (hit_count_dev) MEPP_CUDA_CHECK(cudaMemsetAsync(hit_count_dev, 0, sizeof(unsigned long long), st));
   dim3 grid((unsigned)a.KB, (unsigned)((T + kScanWarps - 1) / kScanWarps));
   MEPP_REQUIRE(grid.y <= 65535, "scan: too many tasks in one call");
-  scan_kernel<<<grid, kScanWarps * 32, 0 + smem, st>>>(a);
+  scan_kernel<<<grid, kScanWarps * 32, smem, st>>>(a);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -273,8 +273,10 @@ class Engine:
         bias = np.array([tb['bias'] for tb in tables], dtype=np.float32)
         mlen = np.array([tb['m'] for tb in tables], dtype=np.int32)
         nfilt = np.array([tb['n_filters'] for tb in tables], dtype=np.int32)
-        lut_d, bias_d, mlen_d, nfilt_d = (self._to_dev(lut), self._to_dev(bias), self._to_dev(mlen),
-                                          self._to_dev(nfilt))
+        qtab = np.stack([tb['qtab'] for tb in tables]).view(np.int32)
+        qthr = np.stack([tb['qthr'] for tb in tables]).view(np.int32)
+        lut_d, bias_d, mlen_d, nfilt_d, qtab_d, qthr_d = (self._to_dev(lut), self._to_dev(bias), self._to_dev(mlen),
+                                                          self._to_dev(nfilt), self._to_dev(qtab), self._to_dev(qthr))
         x_bytes = int(_lib.lib.mepp_x_planes_bytes(m_rows, self.n_pad))
         x_planes = self._buf('x_planes', x_bytes, torch.uint8, zero=True)
         rowstats = self._buf('rowstats', (m_rows, 3), torch.float64)
@@ -288,7 +290,8 @@ class Engine:
             hits_d = self._buf('hits', cap * 16, torch.uint8)
         ev = self._mark(None, None)
         _lib.check(_lib.lib.mepp_scan(_ptr(self.codes_T), _ptr(self.nmask_T), _ptr(self.zhat), N, L, T, int(margin),
-                                      _ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), _ptr(x_planes),
+                                      _ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), _ptr(qtab_d), _ptr(qthr_d),
+                                      _ptr(x_planes),
                                       _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap,
                                       _ptr(hit_count), st), "scan")
         S = self._buf('S', (m_rows, self.ldS), torch.float32)

@@ -69,10 +69,13 @@ def motif_matrix_to_scan_table(motif_matrix, orientation='+', pseudocount=0.0001
     nf = C.c_int(0)
     thr = C.c_double(0.0)
     bgp = None if bg is None else _pd(np.asarray(bg, dtype=np.float64))
+    qtab = np.zeros(256, dtype=np.uint32)
+    qthr = np.zeros(2, dtype=np.uint32)
     _lib.check(_lib.lib.mepp_motif_table(
         _pd(pwm), m, och, float(pseudocount), float(pvalue), bgp, 1 if honour_flags else 0, float(dp_precision),
-        lut.ctypes.data_as(C.POINTER(C.c_float)), C.byref(bias), C.byref(nf), C.byref(thr)), "motif_table")
-    return dict(lut=lut, bias=np.float32(bias.value), n_filters=nf.value, thr=thr.value, m=m)
+        lut.ctypes.data_as(C.POINTER(C.c_float)), C.byref(bias), C.byref(nf), C.byref(thr),
+        qtab.ctypes.data, qthr.ctypes.data), "motif_table")
+    return dict(lut=lut, bias=np.float32(bias.value), n_filters=nf.value, thr=thr.value, m=m, qtab=qtab, qthr=qthr)
 
 
 def scan_tables(tasks, n_threads=None, **kw):
