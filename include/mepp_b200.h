@@ -14,7 +14,7 @@
  * Data layouts (all little-endian):
  *   N        number of sequences, L sequence length (all equal, utils.py:85-88)
  *   n_pad    N rounded up to a multiple of 32 (one "k-block" = 32 sequences)
- *   codes_T  uint32 [Wc][n_pad], Wc = ceil(L/16)+2 : base i of sequence n is the
+ *   codes_T  uint32 [Wc][n_pad], Wc = ceil(L/16)+3 : base i of sequence n is the
  *            2-bit field (i%16) of word [i/16][n]; A=0 C=1 G=2 T=3 (onehot_dna.py:3)
  *   nmask_T  uint32 [Wm][n_pad], Wm = ceil(L/32)+2 : bit (i%32) of word [i/32][n]
  *            is 1 when base i is not an upper-case ACGT (onehot_dna.py:23-30 "N" rule)

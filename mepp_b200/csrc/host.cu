@@ -17,7 +17,7 @@ int fail(const std::string& msg) { g_err = msg; return 1; }
 namespace mepp {
 // Conservative integer pre-filter for the scan kernel (csrc/scan.cu): per filter f and tap j the
 // float32 weights are shifted to be >= 0 and quantised DOWN to a common grid, q = floor((W - min_c W) * scale),
-// scale chosen so that the largest possible sum fits 16 bits.  For the real-valued score S of a window,
+// scale chosen so that the largest possible sum fits 15 bits.  For the real-valued score S of a window,
 //   sum_q <= scale * (S - lo) < sum_q + m,        lo = sum_j min_c W[c][j],
 // and the float32 sequentially rounded score differs from S by less than delta, so a window can only
 // pass the threshold if sum_q >= qthr.  Both filters are packed into one 32-bit entry (low / high half),
@@ -35,7 +35,7 @@ static void build_filter_table(const float* lut, int m, int n_filters, float bia
       mn[f][j] = a; lo[f] += a; rsum[f] += b - a; absmax += am;
     }
   const double rmax = std::max(rsum[0], rsum[1]);
-  const double scale = rmax > 0.0 ? 65535.0 / rmax * (1.0 - 1e-9) : 1.0;
+  const double scale = rmax > 0.0 ? 32767.0 / rmax * (1.0 - 1e-9) : 1.0;   // sums stay below 2^15
   // |float32 sequential sum - real sum| <= m roundings of at most ulp(absmax)/2 each; doubled for safety
   const double delta = 2.0 * m * absmax * 5.97e-8 + 1e-6;
   const double thr32 = -(double)bias;
@@ -52,13 +52,19 @@ static void build_filter_table(const float* lut, int m, int n_filters, float bia
       }
       qtab[t * 16 + e] = packed;
     }
-  for (int f = 0; f < 2; ++f) {
-    if (f >= n_filters) { qthr[f] = 0x10000u; continue; }           // unreachable for a 16-bit sum
+  // qthr[0] = qinit: per 16-bit half (0x8000 - pass bound), added to the packed sum so that "the half reaches
+  // its bound" shows up as bit 15 of the half; 0 = can never pass, 0x8000 = always passes.  qthr[1] keeps the
+  // two pass bounds (low 16 / high 16 bits) for inspection.
+  uint32_t qinit = 0, bounds = 0;
+  for (int f = 0; f < n_filters; ++f) {
     const double need = scale * (thr32 - delta - lo[f]) - (double)m;  // candidates have sum_q > need
-    long long qq = need < 0.0 ? 0 : (long long)std::floor(need) + 1;
-    if (qq > 0x10000) qq = 0x10000;
-    qthr[f] = (uint32_t)qq;
+    long long qq = need < 0.0 ? 0 : (long long)std::floor(need) + 1;  // pass bound: sum_q >= qq
+    uint32_t half = qq > 0x7fff ? 0u : (uint32_t)(0x8000 - qq);
+    qinit |= half << (16 * f);
+    bounds |= (uint32_t)(qq > 0xffff ? 0xffff : qq) << (16 * f);
   }
+  qthr[0] = qinit;
+  qthr[1] = bounds;
 }
 }  // namespace mepp
 
@@ -77,7 +83,7 @@ int mepp_device_ok(void) {
   return major == 10 ? 1 : 0;
 }
 
-int64_t mepp_codes_words(int L) { return (L + 15) / 16 + 2; }
+int64_t mepp_codes_words(int L) { return (L + 15) / 16 + 3; }
 int64_t mepp_nmask_words(int L) { return (L + 31) / 32 + 2; }
 int64_t mepp_pad32(int64_t n) { return (n + 31) / 32 * 32; }
 

@@ -197,9 +197,17 @@ __device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, in
   }
 }
 
-__device__ __forceinline__ uint32_t pair_sum(const char* qt, int g, uint32_t v) {
-  return *reinterpret_cast<const uint32_t*>(qt + (2 * g) * 64 + ((v << 2) & 0x3Cu)) +
-         *reinterpret_cast<const uint32_t*>(qt + (2 * g + 1) * 64 + ((v >> 2) & 0x3Cu));
+// Two adjacent pair tables (4 taps) from the byte of 2-bit codes in bits [2, 10) of `v4`
+// (v4 = window << 2).  `qbase` is the 1024-byte aligned shared address of the task's tables, so the
+// table offset is OR-ed in by the same LOP3 that masks the nibble.
+template <int G>
+__device__ __forceinline__ uint32_t group_sum(uint32_t qbase, uint32_t v4) {
+  uint32_t x0, x1;
+  const uint32_t a0 = (v4 & 0x3Cu) | qbase;
+  const uint32_t a1 = ((v4 >> 4) & 0x3Cu) | qbase;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(x0) : "r"(a0), "n"((2 * G) * 64));
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(x1) : "r"(a1), "n"((2 * G + 1) * 64));
+  return x0 + x1;
 }
 
 __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const int kb,
@@ -218,7 +226,9 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
   const float2* g_lut = reinterpret_cast<const float2*>(a.lut) + (size_t)t * (MEPP_MAX_MOTIF_LEN * 4);
   for (int i = lane; i < MEPP_MAX_MOTIF_LEN * 4; i += 32) s_lut[i] = g_lut[i];
   for (int i = lane; i < 256; i += 32) s_qtab[i] = a.qtab[(size_t)t * 256 + i];
-  const uint32_t q0 = a.qthr[t * 2 + 0], q1 = a.qthr[t * 2 + 1];
+  // qinit: per 16-bit half (0x8000 - pass bound), so "sum reaches the bound" <=> bit 15 of the half is set.
+  // Padding sequences never produce candidates.
+  const uint32_t qinit = real ? a.qthr[t * 2 + 0] : 0u;
   __syncwarp();
 
   TaskCtx c;
@@ -231,10 +241,13 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
   const int nbuf = 32 + 2 * mg;
   const uint32_t* my_codes = s_codes + lane * a.strideC;
   const uint32_t* my_mask = s_mask + lane * a.strideM;
-  const char* qt = reinterpret_cast<const char*>(s_qtab);
+  const uint32_t qbase = (uint32_t)__cvta_generic_to_shared(s_qtab);
+  const uint32_t nmask_keep = real ? c.mbits : 0u;
 
-  int loaded_cw = -1, loaded_mw = -1;
-  uint32_t w0 = 0, w1 = 0, w2 = 0, mw0 = 0, mw1 = 0;
+  // 96-bit shift register of 2-bit codes (bases i.., 16 per word) and 64-bit register of N bits,
+  // advanced by one base per position; refilled from shared memory every 16 / 32 positions.
+  uint32_t r0 = my_codes[0], r1 = my_codes[1], r2 = my_codes[2], n0 = my_mask[0], n1 = my_mask[1];
+  int next_cw = 3, next_mw = 2, left_c = 16, left_m = 32;
   int q_head = 0, q_tail = 0;            // warp-uniform ring indices
   bool carry_nz = false;                 // previous chunk left non-zero x0 in the carried rows
 
@@ -245,39 +258,42 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
       for (int b = 0; b < 2 * mg; ++b) s_buf[b * kRowStride + lane] = s_buf[(32 + b) * kRowStride + lane];
       b_start = 2 * mg;
     }
+    for (int b = b_start; b < nbuf; ++b) s_buf[b * kRowStride + lane] = 0.0f;
     bool new_nz = false;
     // ---- phase A: integer pre-filter over positions base-mg+b, candidates queued ----
+    // window starts i = base - mg + b - padl; only 0 <= i < n_valid are real windows
+    const int i_first = base - mg + b_start - padl;
+    int b_lo = b_start + (i_first < 0 ? -i_first : 0);
+    int b_hi = nbuf;
+    {
+      const int i_end = base - mg + nbuf - padl;      // exclusive
+      if (i_end > n_valid) b_hi -= i_end - n_valid;
+    }
 #pragma unroll 1
-    for (int b = b_start; b < nbuf; ++b) {
-      const int i = base - mg + b - padl;  // window start
-      s_buf[b * kRowStride + lane] = 0.0f;
-      if (i >= 0 && i < n_valid) {         // warp uniform
-        const int cw = i >> 4, mw = i >> 5;
-        if (cw != loaded_cw) { w0 = my_codes[cw]; w1 = my_codes[cw + 1]; w2 = my_codes[cw + 2]; loaded_cw = cw; }
-        if (mw != loaded_mw) { mw0 = my_mask[mw]; mw1 = my_mask[mw + 1]; loaded_mw = mw; }
-        const uint32_t lo = __funnelshift_r(w0, w1, 2 * (i & 15));   // bases i .. i+15
-        const uint32_t nwin = __funnelshift_r(mw0, mw1, i & 31) & c.mbits;
-        uint32_t sum = pair_sum(qt, 0, lo);
-        if (g2 > 1) sum += pair_sum(qt, 1, lo >> 8);
-        if (g2 > 2) sum += pair_sum(qt, 2, lo >> 16);
-        if (g2 > 3) sum += pair_sum(qt, 3, lo >> 24);
+    for (int b = b_lo; b < b_hi; ++b) {
+      const uint32_t v4 = r0 << 2;
+      uint32_t sum = qinit + group_sum<0>(qbase, v4) + group_sum<1>(qbase, r0 >> 6);
+      if (g2 > 2) {
+        sum += group_sum<2>(qbase, r0 >> 14) + group_sum<3>(qbase, r0 >> 22);
         if (g2 > 4) {
-          const uint32_t hi = __funnelshift_r(w1, w2, 2 * (i & 15)); // bases i+16 .. i+31
-          sum += pair_sum(qt, 4, hi);
-          if (g2 > 5) sum += pair_sum(qt, 5, hi >> 8);
-          if (g2 > 6) sum += pair_sum(qt, 6, hi >> 16);
-          if (g2 > 7) sum += pair_sum(qt, 7, hi >> 24);
+          sum += group_sum<4>(qbase, r1 << 2) + group_sum<5>(qbase, r1 >> 6);
+          if (g2 > 6) sum += group_sum<6>(qbase, r1 >> 14) + group_sum<7>(qbase, r1 >> 22);
         }
-        const bool cand = real && (((sum & 0xffffu) >= q0) | ((sum >> 16) >= q1) | (nwin != 0u));
-        const unsigned bal = __ballot_sync(full, cand);
-        if (bal != 0u) {
-          if (cand) {
-            const int slot = q_tail + __popc(bal & ((1u << lane) - 1u));
-            s_queue[slot & (kQueue - 1)] = (uint16_t)((lane << 8) | b);
-          }
-          q_tail += __popc(bal);
-          if (q_tail - q_head >= 32) { new_nz |= flush_candidates(a, c, q_head, 32, base, lane); q_head += 32; }
+      }
+      const bool cand = ((sum & 0x80008000u) | (n0 & nmask_keep)) != 0u;
+      // advance the window by one base
+      r0 = __funnelshift_r(r0, r1, 2); r1 = __funnelshift_r(r1, r2, 2); r2 >>= 2;
+      n0 = __funnelshift_r(n0, n1, 1); n1 >>= 1;
+      if (--left_c == 0) { r2 = my_codes[next_cw++]; left_c = 16; }
+      if (--left_m == 0) { n1 = my_mask[next_mw++]; left_m = 32; }
+      const unsigned bal = __ballot_sync(full, cand);
+      if (bal != 0u) {
+        if (cand) {
+          const int slot = q_tail + __popc(bal & ((1u << lane) - 1u));
+          s_queue[slot & (kQueue - 1)] = (uint16_t)((lane << 8) | b);
         }
+        q_tail += __popc(bal);
+        if (q_tail - q_head >= 32) { new_nz |= flush_candidates(a, c, q_head, 32, base, lane); q_head += 32; }
       }
     }
     if (q_tail != q_head) { new_nz |= flush_candidates(a, c, q_head, q_tail - q_head, base, lane); q_head = q_tail; }
@@ -289,18 +305,19 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
 }
 
 __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const ScanArgs a) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = blockIdx.x;
   const int nbuf = 32 + 2 * a.margin;
-  // carve shared memory
-  float* s_bufs = reinterpret_cast<float*>(smem_raw);                                   // [warps][nbuf][36]
+  // carve shared memory (the 1 KB filter tables come first: they must be 1024-byte aligned)
+  uint32_t* s_qtabs = reinterpret_cast<uint32_t*>(smem_raw);                            // [warps][256]
+  float* s_bufs = reinterpret_cast<float*>(s_qtabs + kScanWarps * 256);                 // [warps][nbuf][36]
   float2* s_luts = reinterpret_cast<float2*>(s_bufs + kScanWarps * nbuf * kRowStride);  // [warps][128]
-  uint32_t* s_qtabs = reinterpret_cast<uint32_t*>(s_luts + kScanWarps * MEPP_MAX_MOTIF_LEN * 4);  // [warps][256]
-  uint32_t* s_codes = s_qtabs + kScanWarps * 256;
+  uint32_t* s_codes = reinterpret_cast<uint32_t*>(s_luts + kScanWarps * MEPP_MAX_MOTIF_LEN * 4);
   uint32_t* s_mask = s_codes + 32 * a.strideC;
   float* s_z = reinterpret_cast<float*>(s_mask + 32 * a.strideM);                       // [32]
   uint16_t* s_queues = reinterpret_cast<uint16_t*>(s_z + 32);                           // [warps][kQueue]
+  if ((__cvta_generic_to_shared(smem_raw) & 1023) != 0) __trap();
 
   for (int idx = threadIdx.x; idx < a.Wc * 32; idx += blockDim.x) {
     const int s = idx & 31, w = idx >> 5;
