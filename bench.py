@@ -174,17 +174,19 @@ def main():
     h2d_bytes = h_ascii.numel() + 4 * h_scores.numel() + 4 * h_perm.numel() + len(my_tasks) * (32 * 4 * 2 * 4 + 12)
 
     eng = Engine(device=local)
-    ncols = None
 
     def e2e_step():
-        """Public-API step from host buffers: stage + thresholds + all tasks + gather."""
-        nonlocal ncols
+        """Public-API step from host buffers: stage + thresholds + all tasks (+ gather to rank 0 when sharded)."""
         eng.stage(h_ascii, h_scores, h_perm, use_gc=True)
         tables = motif_layers.scan_tables(my_tasks)
         batch = eng.profile(my_tasks, margin=margin, tables=tables)
-        block = np.stack([np.asarray(batch.positions[k], dtype=np.float64) for k in batch.positions], axis=-1)
-        ncols = block.shape[-1]
-        full = parallel.gather_blocks(block, my_ids, T_total, device=dev if world > 1 else None)
+        full = None
+        if world > 1:
+            cols = list(batch.positions)
+            block = np.empty((len(my_tasks), len(cols), L), dtype=np.float64)     # task-major, one row per column
+            for j, k in enumerate(cols):
+                block[:, j, :] = batch.positions[k]
+            full = parallel.gather_blocks(block, my_ids, T_total, device=dev)
         return batch, full
 
     def sync_all():

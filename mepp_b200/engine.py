@@ -83,6 +83,7 @@ class Engine:
         self.max_group = int(max_group)
         self.staged = False
         self._bufs = {}
+        self._pins = {}
         self.launches = 0   # kernels launched by this engine (bench.py reports it)
         self.timing = None  # set to {} to collect per-stage CUDA-event times (ms) in _run_group
 
@@ -213,22 +214,28 @@ class Engine:
             if tb['m'] > L:
                 raise ValueError("motif longer than the sequences")
         G = self.group_size()
+        if T_all > 96:
+            # at least three groups so that the host finalisation of one group overlaps the kernels of the next
+            G = min(G, max(32, -(-T_all // 3)))
+        groups = [(g0, min(g0 + G, T_all)) for g0 in range(0, T_all, G)]
         outs = []
         with torch.cuda.device(self.device):
-            for g0 in range(0, T_all, G):
-                outs.append(self._run_group(tables[g0:g0 + G], margin, return_hits, return_r, hits_cap,
-                                            confidence_interval_pct))
-            torch.cuda.current_stream(self.device).synchronize()
-        # ---- host finalisation, vectorised over tasks
+            pending = None
+            for gi, (g0, g1) in enumerate(groups):
+                nxt = self._launch_group(tables[g0:g1], margin, return_hits, return_r, hits_cap,
+                                         confidence_interval_pct, gi % 2)
+                if pending is not None:
+                    outs.append(self._collect_group(pending, margin, confidence_interval_pct, center))
+                pending = nxt
+                if return_hits or return_r:
+                    # the match list / r buffers are reused by the next group: no overlap in this mode
+                    outs.append(self._collect_group(pending, margin, confidence_interval_pct, center))
+                    pending = None
+            if pending is not None:
+                outs.append(self._collect_group(pending, margin, confidence_interval_pct, center))
         cat = lambda k: np.concatenate([o[k] for o in outs], axis=0)
-        r0, count, density = cat('r0'), cat('count'), cat('density')
-        if self.P > 0:
-            full_os, full_cnt, semi_os, semi_cnt, integral = (cat('full_os'), cat('full_cnt'), cat('semi_os'),
-                                                              cat('semi_cnt'), cat('integral'))
-        else:
-            full_os = full_cnt = semi_os = semi_cnt = integral = None
-        positions = stats_host.finalize_positions(r0, full_os, full_cnt, semi_os, semi_cnt, integral, count, N,
-                                                  self.P, margin, confidence_interval_pct, center)
+        density = cat('density')
+        positions = {k: np.concatenate([o['positions'][k] for o in outs], axis=0) for k in outs[0]['positions']}
         hits = None
         if return_hits:
             parts = []
@@ -236,7 +243,7 @@ class Engine:
             for o in outs:
                 h = o['hits'].copy()
                 h['task'] += off
-                off += o['r0'].shape[0]
+                off += o['density'].shape[0]
                 parts.append(h)
             hits = np.concatenate(parts) if parts else np.zeros(0, dtype=HIT_DTYPE)
             order = np.lexsort((hits['pos'], hits['seq'], hits['task']))
@@ -263,7 +270,19 @@ class Engine:
             out[name] = out.get(name, 0.0) + a.elapsed_time(b)
         return out
 
-    def _run_group(self, tables, margin, return_hits, return_r, hits_cap, ci):
+    def _pinned(self, name, slot, shape, dtype):
+        """Grow-only pinned host buffer (two slots: one group in flight, one being finalised)."""
+        torch = self.torch
+        key = (name, slot)
+        need = int(np.prod(shape))
+        cur = self._pins.get(key)
+        if cur is None or cur.numel() < need or cur.dtype != dtype:
+            cur = torch.empty(max(need, 1), dtype=dtype, pin_memory=True)
+            self._pins[key] = cur
+        return cur[:need].view(tuple(int(x) for x in shape))
+
+    def _launch_group(self, tables, margin, return_hits, return_r, hits_cap, ci, slot):
+        """Enqueue every kernel of one task group plus the D2H copies of its results (no host sync)."""
         torch = self.torch
         T = len(tables)
         L, N, C_, P = self.L, self.N, self.C, self.P
@@ -291,8 +310,7 @@ class Engine:
         ev = self._mark(None, None)
         _lib.check(_lib.lib.mepp_scan(_ptr(self.codes_T), _ptr(self.nmask_T), _ptr(self.zhat), N, L, T, int(margin),
                                       _ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), _ptr(qtab_d), _ptr(qthr_d),
-                                      _ptr(x_planes),
-                                      _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap,
+                                      _ptr(x_planes), _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap,
                                       _ptr(hit_count), st), "scan")
         S = self._buf('S', (m_rows, self.ldS), torch.float32)
         ev = self._mark(ev, 'scan')
@@ -306,38 +324,57 @@ class Engine:
                                              1 if self.use_gc else 0, _ptr(r), st), "correlation")
         self.launches += 3 + (m_rows + 65534) // 65535 - 1
         ev = self._mark(ev, 'correlation')
-        out = {}
+        dev = {}
         if P > 0:
             q = stats_host.percentile_q(ci)
             k_lo, _ = stats_host.virtual_index(P, q[0])
             k_hi, _ = stats_host.virtual_index(P, q[1])
             ks_lo, _ = stats_host.virtual_index(L * P, q[0])
             ks_hi, _ = stats_host.virtual_index(L * P, q[1])
-            full_os = self._buf('full_os', (T, L, 4), torch.float32)
-            full_cnt = self._buf('full_cnt', (T, L), torch.int32)
-            semi_os = self._buf('semi_os', (T, 4), torch.float32)
-            semi_cnt = self._buf('semi_cnt', (T, L), torch.int64)
-            integral = self._buf('integral', (T, C_), torch.float64)
+            dev['full_os'] = self._buf('full_os', (T, L, 4), torch.float32)
+            dev['full_cnt'] = self._buf('full_cnt', (T, L), torch.int32)
+            dev['semi_os'] = self._buf('semi_os', (T, 4), torch.float32)
+            dev['semi_cnt'] = self._buf('semi_cnt', (T, L), torch.int64)
+            dev['integral'] = self._buf('integral', (T, C_), torch.float64)
             work = self._buf('stats_work', int(_lib.lib.mepp_perm_stats_work_bytes(T, L, C_)), torch.uint8)
-            _lib.check(_lib.lib.mepp_perm_stats(_ptr(r), T, L, C_, k_lo, k_hi, ks_lo, ks_hi, _ptr(full_os),
-                                                _ptr(full_cnt), _ptr(semi_os), _ptr(semi_cnt), _ptr(integral),
-                                                _ptr(work), st), "perm_stats")
+            _lib.check(_lib.lib.mepp_perm_stats(_ptr(r), T, L, C_, k_lo, k_hi, ks_lo, ks_hi, _ptr(dev['full_os']),
+                                                _ptr(dev['full_cnt']), _ptr(dev['semi_os']), _ptr(dev['semi_cnt']),
+                                                _ptr(dev['integral']), _ptr(work), st), "perm_stats")
             self.launches += 6
             ev = self._mark(ev, 'perm_stats')
-            out.update(full_os=full_os.cpu().numpy(), full_cnt=full_cnt.cpu().numpy(),
-                       semi_os=semi_os.cpu().numpy(), semi_cnt=semi_cnt.cpu().numpy(),
-                       integral=integral.cpu().numpy())
-        out['r0'] = r.view(T, L, C_)[:, :, 0].contiguous().cpu().numpy()
-        out['count'] = count.cpu().numpy()
-        out['density'] = density.cpu().numpy()
-        nh = int(hit_count.cpu().numpy()[0])
-        out['hit_count'] = np.array([nh], dtype=np.int64)
-        if return_hits:
-            if nh > cap:
-                raise RuntimeError(f"match list overflow: {nh} matches > capacity {cap}; pass hits_cap")
-            raw = hits_d[:nh * 16].cpu().numpy()
-            out['hits'] = raw.view(HIT_DTYPE).copy()
+        dev['r0'] = self._buf('r0', (T, L), torch.float32)
+        dev['r0'].copy_(r.view(T, L, C_)[:, :, 0])
+        dev['count'] = count
+        dev['density'] = density
+        dev['hit_count'] = hit_count
         if return_r:
-            out['r'] = r.view(T, L, C_).cpu().numpy().copy()
-        return out
+            dev['r'] = r.view(T, L, C_)
+        host = {}
+        for k, t in dev.items():
+            h = self._pinned(k, slot, t.shape, t.dtype)
+            h.copy_(t, non_blocking=True)
+            host[k] = h
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        return dict(host=host, done=done, T=T, hits_d=hits_d, cap=cap, return_hits=return_hits)
 
+    def _collect_group(self, pend, margin, ci, center):
+        """Wait for one group's D2H copies and finalise its statistics on the host."""
+        pend['done'].synchronize()
+        h = {k: v.numpy() for k, v in pend['host'].items()}
+        out = {}
+        if self.P > 0:
+            args = (h['full_os'], h['full_cnt'], h['semi_os'], h['semi_cnt'], h['integral'])
+        else:
+            args = (None, None, None, None, None)
+        out['positions'] = stats_host.finalize_positions(h['r0'], *args, h['count'], self.N, self.P, margin, ci, center)
+        out['density'] = h['density'].copy()
+        nh = int(h['hit_count'][0])
+        out['hit_count'] = np.array([nh], dtype=np.int64)
+        if pend['return_hits']:
+            if nh > pend['cap']:
+                raise RuntimeError(f"match list overflow: {nh} matches > capacity {pend['cap']}; pass hits_cap")
+            out['hits'] = pend['hits_d'][:nh * 16].cpu().numpy().view(HIT_DTYPE).copy()
+        if 'r' in h:
+            out['r'] = h['r'].copy()
+        return out

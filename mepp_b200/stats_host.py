@@ -6,8 +6,33 @@ numpy's "linear" percentile interpolation, permutation p-values = count / n, the
 parametric Fisher-z confidence interval and t-test, and the rolling-mean count smoothing.
 Everything here is O(T * L) numpy on vectors the GPU already reduced.
 """
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
+from scipy import special as _sp
 from scipy import stats as _st
+
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1))
+    return _POOL
+
+
+def _t_sf2(abs_t, df):
+    """2 * scipy.stats.t.sf(|t|, df) (core.py:410), chunked over host threads for large inputs
+    (scipy.special.stdtr is the function t.sf evaluates; it releases the GIL)."""
+    x = -np.asarray(abs_t, dtype=np.float64)
+    if x.size < 32768:
+        return _sp.stdtr(df, x) * 2
+    flat = x.reshape(-1)
+    n = min(32, os.cpu_count() or 1)
+    parts = list(_pool().map(lambda c: _sp.stdtr(df, c), np.array_split(flat, n)))
+    return (np.concatenate(parts) * 2).reshape(x.shape)
 
 POSITIONS_COLUMNS = [
     'positional_r', 'position',
@@ -61,7 +86,7 @@ def parametric_ci(r32, num_samples, confidence_interval_pct=95):
         lower = (np.exp(f(2) * (z_r - z_margin) + eps) - f(1)) / (np.exp(f(2) * (z_r - z_margin) + eps) + f(1))
         upper = (np.exp(f(2) * (z_r + z_margin) + eps) - f(1)) / (np.exp(f(2) * (z_r + z_margin) + eps) + f(1))
         t = r / np.sqrt((f(1) - (r * r)) / f(n - 2))
-        pval = _st.t.sf(np.abs(t), n - 1) * 2
+        pval = _t_sf2(np.abs(t), n - 1)
     return lower, upper, pval
 
 

@@ -46,7 +46,7 @@ def main():
     # ---- scan
     tables = motif_layers.scan_tables(tasks)
     T = len(tasks)
-    out = eng._run_group(tables, margin, True, True, None, 95)
+    out = eng._collect_group(eng._launch_group(tables, margin, True, True, None, 95, 0), margin, 95, None)
     torch.cuda.synchronize()
     hits = out['hits']
     m_rows = T * L
@@ -72,7 +72,7 @@ def main():
         sx, sxx, sxz = Xb.sum(0), (Xb * Xb).sum(0), (Xb * zhat[:, None]).sum(0)
         print(f"   rowstats err: {np.abs(rs[t*L:(t+1)*L,0]-sx).max():.2e} {np.abs(rs[t*L:(t+1)*L,1]-sxx).max():.2e} "
               f"{np.abs(rs[t*L:(t+1)*L,2]-sxz).max():.2e}", flush=True)
-        print(f"   count equal {np.array_equal(out['count'][t], (X0>0).sum(0))} density equal "
+        print(f"   count equal {np.array_equal(out['positions']['count'][t], (X0>0).sum(0))} density equal "
               f"{np.array_equal(out['density'][t,:N], (X0>0).sum(1))}", flush=True)
     # ---- GEMM vs float64 check kernel and vs host
     S = eng._bufs['S'][:m_rows * eng.ldS].view(m_rows, eng.ldS).cpu().numpy()[:, :eng.C].astype(np.float64)
