@@ -14,10 +14,11 @@
  * Data layouts (all little-endian):
  *   N        number of sequences, L sequence length (all equal, utils.py:85-88)
  *   n_pad    N rounded up to a multiple of 32 (one "k-block" = 32 sequences)
- *   codes_T  uint32 [Wc][n_pad], Wc = ceil(L/16)+3 : base i of sequence n is the
- *            2-bit field (i%16) of word [i/16][n]; A=0 C=1 G=2 T=3 (onehot_dna.py:3)
- *   nmask_T  uint32 [Wm][n_pad], Wm = ceil(L/32)+2 : bit (i%32) of word [i/32][n]
- *            is 1 when base i is not an upper-case ACGT (onehot_dna.py:23-30 "N" rule)
+ *   sym_T    uint32 [W3][n_pad], W3 = ceil(3L/32)+8 : per sequence a continuous bit stream with
+ *            3 bits per base -- the 2-bit code A=0 C=1 G=2 T=3 (onehot_dna.py:3) plus an N flag
+ *            (symbol 4 = not an upper-case ACGT, onehot_dna.py:23-30); base i sits at bits
+ *            [3i, 3i+3) of the stream, word w of sequence n is sym_T[w][n] (transposed so that
+ *            lanes = sequences read coalesced)
  *   X planes the match matrix as GEMM operand A, fp16 hi/lo split, tiled:
  *            [m_tile][k_block][plane 2][kc 4][row 128][8 seq] halves, row = task*L + position
  *   Y planes the (1+P) score columns as GEMM operand B, same tiling with BN columns:
@@ -54,7 +55,7 @@ int mepp_threshold_from_p(const double* W, int m, const double* bg, double pvalu
  * dual), replacing motif_matrix_to_conv1d_layer (motif_layers.py:12-78):
  *   lut   float [MEPP_MAX_MOTIF_LEN][4][2]  (tap, base, filter) float32 weights, zero padded
  *   bias  float32(-thr)  ; n_filters 1 or 2 ; thr double (for reporting)
- *   qtab  uint32 [16][16], qthr uint32 [2]: conservative 16-bit integer pre-filter of the scan
+ *   qtab  uint32 [16][64], qthr uint32 [2]: conservative 16-bit integer pre-filter of the scan
  *         kernel (pairs of taps, both filters packed low/high); may be NULL
  * use_flags: 0 = reproduce the reference (pseudocount/pvalue/bg never reach MOODS,
  * core.py:513-534, so 1e-4 / 1e-4 / flat are used); 1 = honour the arguments. */
@@ -65,8 +66,7 @@ int mepp_motif_table(const double* pwm, int m, int orientation_char,
                      uint32_t* qtab, uint32_t* qthr);
 
 /* ------------------------------------------------------------------ layout sizes */
-int64_t mepp_codes_words(int L);            /* Wc */
-int64_t mepp_nmask_words(int L);            /* Wm */
+int64_t mepp_sym_words(int L);              /* W3 */
 int64_t mepp_pad32(int64_t n);              /* n_pad */
 int64_t mepp_x_planes_bytes(int64_t m_rows, int64_t n_pad);
 int     mepp_choose_bn(int C, int* n_tiles_n);  /* column tile width (multiple of 32, <=256) */
@@ -77,7 +77,7 @@ int64_t mepp_y_planes_bytes(int C, int64_t n_pad);
  * utils.py:141-194) and append_gc_ratios_to_dataset('global') (utils.py:275-308).
  * ascii_dev: uint8 [N][L].  gc_dev: float [n_pad] (z, 0 for padding). */
 int mepp_pack_dna(const uint8_t* ascii_dev, int64_t N, int L,
-                  uint32_t* codes_T_dev, uint32_t* nmask_T_dev, float* gc_dev, void* stream);
+                  uint32_t* sym_T_dev, float* gc_dev, void* stream);
 
 /* ------------------------------------------------------------------ Y operand
  * Replaces add_permuted_scores_to_dataset (permutations.py:5-58).
@@ -94,14 +94,14 @@ int mepp_build_y(const float* yhat_dev, const int32_t* perm_dev, const float* zh
  * Replaces the conv model + ReLU + margin blur + counts/density
  * (motif_layers.py:80-165, core.py:25-145, core.py:415-470) for a group of T tasks.
  *   lut_dev   float [T][MEPP_MAX_MOTIF_LEN][4][2]   bias_dev float [T]
- *   mlen_dev  int32 [T]   nfilt_dev int32 [T]   qtab_dev uint32 [T][256]   qthr_dev uint32 [T][2]
+ *   mlen_dev  int32 [T]   nfilt_dev int32 [T]   qtab_dev uint32 [T][1024]   qthr_dev uint32 [T][2]
  *   x_planes_dev  A operand (rows t*L+l), written densely
  *   rowstats_dev  double [T*L][3]: sum_n x, sum_n x^2, sum_n x*zhat  (x = blurred score); zeroed by the call
  *   count_dev     int32 [T*L]  : #sequences with an unsmoothed match at each position; zeroed by the call
  *   density_dev   int32 [T][n_pad]: #matches per sequence
  *   hits_dev      optional: {int32 task, int32 seq, int32 pos, float x0} records, capacity hits_cap,
  *                 hit_count_dev int64[1] total number of matches (may exceed cap); NULL to skip */
-int mepp_scan(const uint32_t* codes_T_dev, const uint32_t* nmask_T_dev, const float* zhat_dev,
+int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
               int64_t N, int L, int T, int margin,
               const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev, const int32_t* nfilt_dev,
               const uint32_t* qtab_dev, const uint32_t* qthr_dev,

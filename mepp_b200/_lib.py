@@ -33,15 +33,14 @@ SIGNATURES = {
     "mepp_log_odds": (_i32, [_pd, _i32, _pd, _f64, _pd]),
     "mepp_threshold_from_p": (_i32, [_pd, _i32, _pd, _f64, _f64, _pd]),
     "mepp_motif_table": (_i32, [_pd, _i32, _i32, _f64, _f64, _pd, _i32, _f64, _pf, _pf, _pi, _pd, _vp, _vp]),
-    "mepp_codes_words": (_i64, [_i32]),
-    "mepp_nmask_words": (_i64, [_i32]),
+    "mepp_sym_words": (_i64, [_i32]),
     "mepp_pad32": (_i64, [_i64]),
     "mepp_x_planes_bytes": (_i64, [_i64, _i64]),
     "mepp_choose_bn": (_i32, [_i32, _pi]),
     "mepp_y_planes_bytes": (_i64, [_i32, _i64]),
-    "mepp_pack_dna": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "mepp_pack_dna": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "mepp_build_y": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
-    "mepp_scan": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+    "mepp_scan": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                          _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "mepp_profile_gemm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp]),
     "mepp_profile_gemm_check": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp]),

@@ -21,7 +21,7 @@ namespace mepp {
 //   sum_q <= scale * (S - lo) < sum_q + m,        lo = sum_j min_c W[c][j],
 // and the float32 sequentially rounded score differs from S by less than delta, so a window can only
 // pass the threshold if sum_q >= qthr.  Both filters are packed into one 32-bit entry (low / high half),
-// and two adjacent taps share one 16-entry table indexed by the 4-bit pair of 2-bit codes.
+// and two adjacent taps share one 64-entry table indexed by the 6-bit pair of 3-bit symbols (A,C,G,T,N).
 static void build_filter_table(const float* lut, int m, int n_filters, float bias, uint32_t* qtab, uint32_t* qthr) {
   double rsum[2] = {0.0, 0.0}, lo[2] = {0.0, 0.0}, absmax = 0.0;
   double mn[2][MEPP_MAX_MOTIF_LEN];
@@ -37,20 +37,31 @@ static void build_filter_table(const float* lut, int m, int n_filters, float bia
   const double rmax = std::max(rsum[0], rsum[1]);
   const double scale = rmax > 0.0 ? 32767.0 / rmax * (1.0 - 1e-9) : 1.0;   // sums stay below 2^15
   // |float32 sequential sum - real sum| <= m roundings of at most ulp(absmax)/2 each; doubled for safety
-  const double delta = 2.0 * m * absmax * 5.97e-8 + 1e-6;
+  const double delta = 2.0 * (4.0 * m) * absmax * 5.97e-8 + 1e-6;   // up to 4 adds per tap (N bases)
   const double thr32 = -(double)bias;
+  // symbol 4 = N: the four quarter-weight adds sum (in real arithmetic) to the column mean
+  double qn[2][MEPP_MAX_MOTIF_LEN];
+  for (int f = 0; f < n_filters; ++f)
+    for (int j = 0; j < m; ++j) {
+      double mean = 0.0;
+      for (int c = 0; c < 4; ++c) mean += 0.25 * (double)lut[(j * 4 + c) * 2 + f];
+      qn[f][j] = std::floor((mean - mn[f][j]) * scale);
+      if (qn[f][j] < 0.0) qn[f][j] = 0.0;
+    }
   for (int t = 0; t < 16; ++t)
-    for (int e = 0; e < 16; ++e) {
+    for (int e = 0; e < 64; ++e) {
       uint32_t packed = 0;
       for (int f = 0; f < n_filters; ++f) {
         uint32_t q = 0;
         for (int h = 0; h < 2; ++h) {
-          const int j = 2 * t + h, c = (e >> (2 * h)) & 3;
-          if (j < m) q += (uint32_t)std::floor(((double)lut[(j * 4 + c) * 2 + f] - mn[f][j]) * scale);
+          const int j = 2 * t + h, sym = (e >> (3 * h)) & 7;
+          if (j >= m) continue;
+          if (sym < 4) q += (uint32_t)std::floor(((double)lut[(j * 4 + sym) * 2 + f] - mn[f][j]) * scale);
+          else q += (uint32_t)qn[f][j];
         }
         packed |= (q & 0xffffu) << (16 * f);
       }
-      qtab[t * 16 + e] = packed;
+      qtab[t * 64 + e] = packed;
     }
   // qthr[0] = qinit: per 16-bit half (0x8000 - pass bound), added to the packed sum so that "the half reaches
   // its bound" shows up as bit 15 of the half; 0 = can never pass, 0x8000 = always passes.  qthr[1] keeps the
@@ -83,8 +94,7 @@ int mepp_device_ok(void) {
   return major == 10 ? 1 : 0;
 }
 
-int64_t mepp_codes_words(int L) { return (L + 15) / 16 + 3; }
-int64_t mepp_nmask_words(int L) { return (L + 31) / 32 + 2; }
+int64_t mepp_sym_words(int L) { return (3 * (int64_t)L + 31) / 32 + 8; }
 int64_t mepp_pad32(int64_t n) { return (n + 31) / 32 * 32; }
 
 int64_t mepp_x_planes_bytes(int64_t m_rows, int64_t n_pad) {

@@ -1,58 +1,52 @@
-// K0: ASCII -> 2-bit codes + N mask + global GC ratio, and the Y (score / permuted
+// K0: ASCII -> 3-bit symbol stream (2-bit code + N flag) + global GC ratio, and the Y (score / permuted
 // score) GEMM operand.  Replaces mepp/onehot_dna.py:61-70, mepp/utils.py:141-194,
 // mepp/utils.py:275-308 and mepp/permutations.py:5-58 of the reference.
 #include "common.cuh"
 
 namespace mepp {
 
-// One thread per (word w, sequence n); consecutive threads = consecutive n so the
-// transposed stores are coalesced.  The ASCII reads are strided 16-byte segments.
-__global__ void pack_codes_kernel(const uint8_t* __restrict__ ascii, int64_t N, int L,
-                                  int64_t n_pad, int Wc, uint32_t* __restrict__ codes_T) {
+// 3-bit symbol of one ASCII base: A,C,G,T = 0..3 (onehot_dna.py:3), everything else (N, lower case
+// soft-masked bases, IUPAC codes) = 4, the reference's "N" rule (onehot_dna.py:23-30).
+__device__ __forceinline__ uint32_t base_symbol(uint8_t ch) {
+  return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
+}
+
+// One thread per (stream word w, sequence n); consecutive threads = consecutive n so the
+// transposed stores are coalesced.  Word w holds bits [32w, 32w+32) of the sequence's symbol
+// stream (base u at bits [3u, 3u+3)), i.e. parts of up to 12 bases.
+__global__ void pack_symbols_kernel(const uint8_t* __restrict__ ascii, int64_t N, int L,
+                                    int64_t n_pad, uint32_t* __restrict__ sym_T) {
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int w = blockIdx.y;
   if (n >= n_pad) return;
   uint32_t word = 0;
   if (n < N) {
-    int base = w * 16;
     const uint8_t* s = ascii + n * (int64_t)L;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      int p = base + i;
-      uint32_t c = 0;
-      if (p < L) {
-        uint8_t ch = s[p];
-        c = ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 0u;
-      }
-      word |= c << (2 * i);
+    const int bit0 = 32 * w;
+    const int u0 = bit0 / 3, u1 = (bit0 + 31) / 3;
+    for (int u = u0; u <= u1; ++u) {
+      if (u >= L) break;
+      const uint32_t sym = base_symbol(s[u]);
+      const int sh = 3 * u - bit0;
+      word |= sh >= 0 ? (sym << sh) : (sym >> (-sh));
     }
   }
-  codes_T[(int64_t)w * n_pad + n] = word;
+  sym_T[(int64_t)w * n_pad + n] = word;
 }
 
-// Mask words (32 bases each) and the GC covariate z[n] = (sum_l gc_l) / L with
-// gc_l = 1 for C/G, 0.5 for N (= every non upper-case-ACGT char), 0 otherwise.
-__global__ void pack_mask_gc_kernel(const uint8_t* __restrict__ ascii, int64_t N, int L,
-                                    int64_t n_pad, int Wm, uint32_t* __restrict__ nmask_T,
-                                    float* __restrict__ gc) {
+// The GC covariate z[n] = (sum_l gc_l) / L with gc_l = 1 for C/G, 0.5 for N (= every non
+// upper-case-ACGT char), 0 otherwise.
+__global__ void pack_gc_kernel(const uint8_t* __restrict__ ascii, int64_t N, int L, int64_t n_pad,
+                               float* __restrict__ gc) {
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_pad) return;
   int twice = 0;  // 2 * sum of gc_l, an exact integer
-  const uint8_t* s = ascii + n * (int64_t)L;
-  for (int w = 0; w < Wm; ++w) {
-    uint32_t word = 0;
-    if (n < N) {
-      for (int i = 0; i < 32; ++i) {
-        int p = w * 32 + i;
-        if (p < L) {
-          uint8_t ch = s[p];
-          bool acgt = (ch == 'A') | (ch == 'C') | (ch == 'G') | (ch == 'T');
-          if (!acgt) { word |= 1u << i; twice += 1; }
-          else if (ch == 'C' || ch == 'G') twice += 2;
-        }
-      }
+  if (n < N) {
+    const uint8_t* s = ascii + n * (int64_t)L;
+    for (int p = 0; p < L; ++p) {
+      const uint32_t sym = base_symbol(s[p]);
+      twice += sym == 4u ? 1 : ((sym == 1u || sym == 2u) ? 2 : 0);
     }
-    nmask_T[(int64_t)w * n_pad + n] = word;
   }
   // float32 sum of {0, .5, 1} is exact; one rounding in the division (utils.py:262-266)
   gc[n] = n < N ? (0.5f * (float)twice) / (float)L : 0.0f;
@@ -148,19 +142,17 @@ __global__ void y_colstats_kernel(const uint32_t* __restrict__ ysplit, const int
 
 extern "C" {
 
-int mepp_pack_dna(const uint8_t* ascii_dev, int64_t N, int L, uint32_t* codes_T_dev,
-                  uint32_t* nmask_T_dev, float* gc_dev, void* stream) {
+int mepp_pack_dna(const uint8_t* ascii_dev, int64_t N, int L, uint32_t* sym_T_dev, float* gc_dev, void* stream) {
   using namespace mepp;
-  MEPP_REQUIRE(ascii_dev && codes_T_dev && nmask_T_dev && gc_dev, "pack_dna: null pointer");
+  MEPP_REQUIRE(ascii_dev && sym_T_dev && gc_dev, "pack_dna: null pointer");
   MEPP_REQUIRE(N > 0 && L > 0, "pack_dna: empty input");
   MEPP_REQUIRE(mepp_device_ok(), "pack_dna: no sm_100 CUDA device (no CPU fallback)");
   int64_t n_pad = mepp_pad32(N);
-  int Wc = (int)mepp_codes_words(L), Wm = (int)mepp_nmask_words(L);
+  int W3 = (int)mepp_sym_words(L);
   cudaStream_t st = as_stream(stream);
-  dim3 grid((unsigned)((n_pad + 255) / 256), (unsigned)Wc);
-  pack_codes_kernel<<<grid, 256, 0, st>>>(ascii_dev, N, L, n_pad, Wc, codes_T_dev);
-  pack_mask_gc_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(ascii_dev, N, L, n_pad, Wm,
-                                                                      nmask_T_dev, gc_dev);
+  dim3 grid((unsigned)((n_pad + 255) / 256), (unsigned)W3);
+  pack_symbols_kernel<<<grid, 256, 0, st>>>(ascii_dev, N, L, n_pad, sym_T_dev);
+  pack_gc_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(ascii_dev, N, L, n_pad, gc_dev);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

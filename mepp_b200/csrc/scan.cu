@@ -1,4 +1,4 @@
-// K1: PWM scan of 2-bit packed DNA, both Conv1D filters in one pass, threshold +
+// K1: PWM scan of packed DNA (3-bit symbols: 2-bit code + N flag), both Conv1D filters in one pass, threshold +
 // ReLU, +-margin blur, fp16 hi/lo split of the blurred score written straight into
 // the GEMM's tiled A operand, plus the per-position / per-sequence side outputs.
 //
@@ -13,12 +13,13 @@
 //   quarter weights .25*W[A..T][j] one after the other;  s = fl32(acc + fl32(-thr)).
 //
 // Two-level evaluation.  Matches are rare (p = 1e-4 per strand), so every window first goes
-// through a conservative 16-bit integer pre-filter (host.cu: build_filter_table): pairs of
-// taps index a 16-entry table whose entries hold BOTH filters' quantised partial sums in
-// one 32-bit word, so one conflict-free LDS + one IADD advance two taps of two strands.
-// Only windows whose integer sum reaches the per-filter bound -- or that contain an N --
-// are queued and evaluated exactly in the canonical float32 order, warp-compacted so that
-// all 32 lanes work on candidates.  The filter has no false negatives by construction, so
+// through a conservative 15-bit integer pre-filter (host.cu: build_filter_table): pairs of
+// taps index a 64-entry table (6 bits = two 3-bit symbols, N included) whose entries hold BOTH
+// filters' quantised partial sums in one 32-bit word, so one LDS + one IADD advance two taps
+// of two strands (the 16 ACGT-only entries of a table sit in 16 distinct banks).
+// Only windows whose integer sum reaches the per-filter bound are queued and evaluated
+// exactly in the canonical float32 order, warp-compacted so that all 32 lanes work on
+// candidates.  The filter has no false negatives by construction, so
 // every reported score comes from the exact path and is bit-identical to the oracle.
 //
 // Work decomposition: one CTA = one k-block (32 sequences) x 4 tasks; one warp = one
@@ -34,9 +35,9 @@ constexpr int kRowStride = 36;  // floats per position row of the x0 staging buf
 constexpr int kQueue = 64;      // candidate ring (flushed whenever 32 are pending)
 
 struct ScanArgs {
-  const uint32_t* codes_T; const uint32_t* nmask_T; const float* zhat;
+  const uint32_t* sym_T; const float* zhat;
   int64_t N, n_pad, KB;
-  int L, T, margin, Wc, Wm, strideC, strideM;
+  int L, T, margin, W3, strideS;
   const float* lut; const float* bias; const int32_t* mlen; const int32_t* nfilt;
   const uint32_t* qtab; const uint32_t* qthr;
   uint8_t* x_planes; double* rowstats; int32_t* count; int32_t* density;
@@ -48,26 +49,22 @@ struct ScanArgs {
 // the kernel inside the instruction cache (an earlier variant specialised on motif length and
 // strand count, 26k SASS instructions, and spent most of its time on instruction fetch).
 struct TaskCtx {
-  const float2* s_lut; const uint32_t* s_codes; const uint32_t* s_mask; float* s_buf; const float* s_z;
+  const float2* s_lut; const uint32_t* s_sym; float* s_buf; const float* s_z;
   uint16_t* s_queue;
-  int t, kb, m, padl, mg, L, strideC, strideM, dual;
-  uint32_t mbits; float bias;
+  int t, kb, m, padl, mg, L, strideS, dual;
+  float bias;
 };
 
-// Exact canonical-order score of the window starting at base i of one sequence.
-__device__ __forceinline__ float exact_x0(const TaskCtx& c, const uint32_t* __restrict__ codes,
-                                          const uint32_t* __restrict__ mask, int i) {
-  const int cw = i >> 4, mw = i >> 5;
-  const uint32_t w0 = codes[cw], w1 = codes[cw + 1], w2 = codes[cw + 2];
-  const uint32_t lo = __funnelshift_r(w0, w1, 2 * (i & 15));
-  const uint32_t hi = __funnelshift_r(w1, w2, 2 * (i & 15));
-  const uint32_t nwin = __funnelshift_r(mask[mw], mask[mw + 1], i & 31) & c.mbits;
+// Exact canonical-order score of the window starting at base i of one sequence (`stream` = that
+// sequence's 3-bit symbol stream in shared memory).
+__device__ __forceinline__ float exact_x0(const TaskCtx& c, const uint32_t* __restrict__ stream, int i) {
   float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll 1
   for (int j = 0; j < c.m; ++j) {
-    const uint32_t code = (j < 16 ? (lo >> (2 * j)) : (hi >> (2 * (j - 16)))) & 3u;
+    const int bit = 3 * (i + j);
+    const uint32_t sym = __funnelshift_r(stream[bit >> 5], stream[(bit >> 5) + 1], bit & 31) & 7u;
     const float2* l4 = c.s_lut + j * 4;
-    if ((nwin >> j) & 1u) {
+    if (sym >= 4u) {
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         const float2 w = l4[cc];
@@ -75,7 +72,7 @@ __device__ __forceinline__ float exact_x0(const TaskCtx& c, const uint32_t* __re
         a1 = __fadd_rn(a1, __fmul_rn(0.25f, w.y));
       }
     } else {
-      const float2 w = l4[code];
+      const float2 w = l4[sym];
       a0 = __fadd_rn(a0, w.x);
       a1 = __fadd_rn(a1, w.y);
     }
@@ -95,7 +92,7 @@ __device__ __noinline__ bool flush_candidates(const ScanArgs& a, const TaskCtx& 
     const uint32_t e = c.s_queue[(q_head + lane) & (kQueue - 1)];
     const int s = (int)(e >> 8), b = (int)(e & 0xffu);
     const int p = base - c.mg + b;
-    const float x0 = exact_x0(c, c.s_codes + s * c.strideC, c.s_mask + s * c.strideM, p - c.padl);
+    const float x0 = exact_x0(c, c.s_sym + s * c.strideS, p - c.padl);
     if (x0 > 0.0f) {
       any_hit = true;
       c.s_buf[b * kRowStride + s] = x0;
@@ -197,57 +194,62 @@ __device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, in
   }
 }
 
-// Two adjacent pair tables (4 taps) from the byte of 2-bit codes in bits [2, 10) of `v4`
-// (v4 = window << 2).  `qbase` is the 1024-byte aligned shared address of the task's tables, so the
-// table offset is OR-ed in by the same LOP3 that masks the nibble.
-template <int G>
-__device__ __forceinline__ uint32_t group_sum(uint32_t qbase, uint32_t v4) {
-  uint32_t x0, x1;
-  const uint32_t a0 = (v4 & 0x3Cu) | qbase;
-  const uint32_t a1 = ((v4 >> 4) & 0x3Cu) | qbase;
-  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(x0) : "r"(a0), "n"((2 * G) * 64));
-  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(x1) : "r"(a1), "n"((2 * G + 1) * 64));
-  return x0 + x1;
+// Pair-slot lookup: slot T covers taps 2T, 2T+1 = bits [6T, 6T+6) of the window's symbol stream
+// (w_lo = the stream word holding bit 6T, w_hi = the next word, only used by the two slots that
+// straddle a word).  `qbase` is the 256-byte aligned shared address of the task's 16 x 256-byte
+// tables, so the same LOP3 that masks the 6-bit index ORs the table base in (slot offset = LDS immediate).
+template <int T>
+__device__ __forceinline__ uint32_t slot(uint32_t qbase, uint32_t w_lo, uint32_t w_hi) {
+  constexpr int off = (6 * T) % 32;
+  uint32_t v;
+  if constexpr (off + 6 > 32) v = __funnelshift_r(w_lo, w_hi, off - 2);
+  else if constexpr (off >= 2) v = w_lo >> (off - 2);
+  else v = w_lo << (2 - off);
+  const uint32_t addr = (v & 0xFCu) | qbase;
+  uint32_t x;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(x) : "r"(addr), "n"(T * 256));
+  return x;
 }
 
 __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const int kb,
-                                          const uint32_t* __restrict__ s_codes, const uint32_t* __restrict__ s_mask,
-                                          float2* __restrict__ s_lut, uint32_t* __restrict__ s_qtab,
-                                          float* __restrict__ s_buf, uint16_t* __restrict__ s_queue,
-                                          const float* __restrict__ s_z, const int lane) {
+                                          const uint32_t* __restrict__ s_sym, float2* __restrict__ s_lut,
+                                          uint32_t* __restrict__ s_qtab, float* __restrict__ s_buf,
+                                          uint16_t* __restrict__ s_queue, const float* __restrict__ s_z,
+                                          const int lane) {
   const unsigned full = 0xffffffffu;
   const int L = a.L, mg = a.margin;
   const int m = a.mlen[t];
-  const int g2 = (m + 3) >> 2;           // 4-tap groups (two 16-entry pair tables each)
+  const int np = (m + 1) >> 1;           // pair slots in use
   const int padl = (m - 1) / 2;          // motif_layers.py:99-101
   const int n_valid = L - m + 1;         // 'valid' convolution outputs
   const bool real = (int64_t)kb * 32 + lane < a.N;
 
   const float2* g_lut = reinterpret_cast<const float2*>(a.lut) + (size_t)t * (MEPP_MAX_MOTIF_LEN * 4);
   for (int i = lane; i < MEPP_MAX_MOTIF_LEN * 4; i += 32) s_lut[i] = g_lut[i];
-  for (int i = lane; i < 256; i += 32) s_qtab[i] = a.qtab[(size_t)t * 256 + i];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.qtab + (size_t)t * 1024);
+    uint4* dst = reinterpret_cast<uint4*>(s_qtab);
+    for (int i = lane; i < 256; i += 32) dst[i] = src[i];
+  }
   // qinit: per 16-bit half (0x8000 - pass bound), so "sum reaches the bound" <=> bit 15 of the half is set.
   // Padding sequences never produce candidates.
   const uint32_t qinit = real ? a.qthr[t * 2 + 0] : 0u;
   __syncwarp();
 
   TaskCtx c;
-  c.s_lut = s_lut; c.s_codes = s_codes; c.s_mask = s_mask; c.s_buf = s_buf; c.s_z = s_z; c.s_queue = s_queue;
-  c.t = t; c.kb = kb; c.m = m; c.padl = padl; c.mg = mg; c.L = L; c.strideC = a.strideC; c.strideM = a.strideM;
+  c.s_lut = s_lut; c.s_sym = s_sym; c.s_buf = s_buf; c.s_z = s_z; c.s_queue = s_queue;
+  c.t = t; c.kb = kb; c.m = m; c.padl = padl; c.mg = mg; c.L = L; c.strideS = a.strideS;
   c.dual = a.nfilt[t] == 2;
-  c.mbits = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
   c.bias = a.bias[t];
 
   const int nbuf = 32 + 2 * mg;
-  const uint32_t* my_codes = s_codes + lane * a.strideC;
-  const uint32_t* my_mask = s_mask + lane * a.strideM;
+  const uint32_t* my = s_sym + lane * a.strideS;
   const uint32_t qbase = (uint32_t)__cvta_generic_to_shared(s_qtab);
-  const uint32_t nmask_keep = real ? c.mbits : 0u;
 
-  // 96-bit shift register of 2-bit codes (bases i.., 16 per word) and 64-bit register of N bits,
-  // advanced by one base per position; refilled from shared memory every 16 / 32 positions.
-  uint32_t r0 = my_codes[0], r1 = my_codes[1], r2 = my_codes[2], n0 = my_mask[0], n1 = my_mask[1];
-  int next_cw = 3, next_mw = 2, left_c = 16, left_m = 32;
+  // 192-bit shift register over the symbol stream (window start at bit 0 of r0), advanced by one
+  // base (3 bits) per position and refilled with three new words every 32 positions.
+  uint32_t r0 = my[0], r1 = my[1], r2 = my[2], r3 = my[3], r4 = my[4], r5 = my[5];
+  int next_w = 6, left = 32;
   int q_head = 0, q_tail = 0;            // warp-uniform ring indices
   bool carry_nz = false;                 // previous chunk left non-zero x0 in the carried rows
 
@@ -263,7 +265,7 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
     // ---- phase A: integer pre-filter over positions base-mg+b, candidates queued ----
     // window starts i = base - mg + b - padl; only 0 <= i < n_valid are real windows
     const int i_first = base - mg + b_start - padl;
-    int b_lo = b_start + (i_first < 0 ? -i_first : 0);
+    const int b_lo = b_start + (i_first < 0 ? -i_first : 0);
     int b_hi = nbuf;
     {
       const int i_end = base - mg + nbuf - padl;      // exclusive
@@ -271,26 +273,29 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
     }
 #pragma unroll 1
     for (int b = b_lo; b < b_hi; ++b) {
-      const uint32_t v4 = r0 << 2;
-      uint32_t sum = qinit + group_sum<0>(qbase, v4) + group_sum<1>(qbase, r0 >> 6);
-      if (g2 > 2) {
-        sum += group_sum<2>(qbase, r0 >> 14) + group_sum<3>(qbase, r0 >> 22);
-        if (g2 > 4) {
-          sum += group_sum<4>(qbase, r1 << 2) + group_sum<5>(qbase, r1 >> 6);
-          if (g2 > 6) sum += group_sum<6>(qbase, r1 >> 14) + group_sum<7>(qbase, r1 >> 22);
+      uint32_t sum = qinit + slot<0>(qbase, r0, r1) + slot<1>(qbase, r0, r1) + slot<2>(qbase, r0, r1);
+      if (np > 3) {
+        sum += slot<3>(qbase, r0, r1) + slot<4>(qbase, r0, r1);
+        if (np > 5) {
+          sum += slot<5>(qbase, r0, r1) + slot<6>(qbase, r1, r2) + slot<7>(qbase, r1, r2);
+          if (np > 8) {
+            sum += slot<8>(qbase, r1, r2) + slot<9>(qbase, r1, r2) + slot<10>(qbase, r1, r2);
+            if (np > 11)
+              sum += slot<11>(qbase, r2, r3) + slot<12>(qbase, r2, r3) + slot<13>(qbase, r2, r3) +
+                     slot<14>(qbase, r2, r3) + slot<15>(qbase, r2, r3);
+          }
         }
       }
-      const bool cand = ((sum & 0x80008000u) | (n0 & nmask_keep)) != 0u;
+      const bool cand = (sum & 0x80008000u) != 0u;
       // advance the window by one base
-      r0 = __funnelshift_r(r0, r1, 2); r1 = __funnelshift_r(r1, r2, 2); r2 >>= 2;
-      n0 = __funnelshift_r(n0, n1, 1); n1 >>= 1;
-      if (--left_c == 0) { r2 = my_codes[next_cw++]; left_c = 16; }
-      if (--left_m == 0) { n1 = my_mask[next_mw++]; left_m = 32; }
+      r0 = __funnelshift_r(r0, r1, 3); r1 = __funnelshift_r(r1, r2, 3); r2 = __funnelshift_r(r2, r3, 3);
+      r3 = __funnelshift_r(r3, r4, 3); r4 = __funnelshift_r(r4, r5, 3); r5 >>= 3;
+      if (--left == 0) { r3 = my[next_w]; r4 = my[next_w + 1]; r5 = my[next_w + 2]; next_w += 3; left = 32; }
       const unsigned bal = __ballot_sync(full, cand);
       if (bal != 0u) {
         if (cand) {
-          const int slot = q_tail + __popc(bal & ((1u << lane) - 1u));
-          s_queue[slot & (kQueue - 1)] = (uint16_t)((lane << 8) | b);
+          const int slot_i = q_tail + __popc(bal & ((1u << lane) - 1u));
+          s_queue[slot_i & (kQueue - 1)] = (uint16_t)((lane << 8) | b);
         }
         q_tail += __popc(bal);
         if (q_tail - q_head >= 32) { new_nz |= flush_candidates(a, c, q_head, 32, base, lane); q_head += 32; }
@@ -309,23 +314,18 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const ScanArgs a)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = blockIdx.x;
   const int nbuf = 32 + 2 * a.margin;
-  // carve shared memory (the 1 KB filter tables come first: they must be 1024-byte aligned)
-  uint32_t* s_qtabs = reinterpret_cast<uint32_t*>(smem_raw);                            // [warps][256]
-  float* s_bufs = reinterpret_cast<float*>(s_qtabs + kScanWarps * 256);                 // [warps][nbuf][36]
+  // carve shared memory (the filter tables come first: the OR-merged index needs 256-byte alignment)
+  uint8_t* sm = smem_raw + ((256u - (uint32_t)(__cvta_generic_to_shared(smem_raw) & 255u)) & 255u);
+  uint32_t* s_qtabs = reinterpret_cast<uint32_t*>(sm);                                  // [warps][1024]
+  float* s_bufs = reinterpret_cast<float*>(s_qtabs + kScanWarps * 1024);                // [warps][nbuf][36]
   float2* s_luts = reinterpret_cast<float2*>(s_bufs + kScanWarps * nbuf * kRowStride);  // [warps][128]
-  uint32_t* s_codes = reinterpret_cast<uint32_t*>(s_luts + kScanWarps * MEPP_MAX_MOTIF_LEN * 4);
-  uint32_t* s_mask = s_codes + 32 * a.strideC;
-  float* s_z = reinterpret_cast<float*>(s_mask + 32 * a.strideM);                       // [32]
+  uint32_t* s_sym = reinterpret_cast<uint32_t*>(s_luts + kScanWarps * MEPP_MAX_MOTIF_LEN * 4);
+  float* s_z = reinterpret_cast<float*>(s_sym + 32 * a.strideS);                        // [32]
   uint16_t* s_queues = reinterpret_cast<uint16_t*>(s_z + 32);                           // [warps][kQueue]
-  if ((__cvta_generic_to_shared(smem_raw) & 1023) != 0) __trap();
 
-  for (int idx = threadIdx.x; idx < a.Wc * 32; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < a.W3 * 32; idx += blockDim.x) {
     const int s = idx & 31, w = idx >> 5;
-    s_codes[s * a.strideC + w] = a.codes_T[(int64_t)w * a.n_pad + (int64_t)kb * 32 + s];
-  }
-  for (int idx = threadIdx.x; idx < a.Wm * 32; idx += blockDim.x) {
-    const int s = idx & 31, w = idx >> 5;
-    s_mask[s * a.strideM + w] = a.nmask_T[(int64_t)w * a.n_pad + (int64_t)kb * 32 + s];
+    s_sym[s * a.strideS + w] = a.sym_T[(int64_t)w * a.n_pad + (int64_t)kb * 32 + s];
   }
   if (threadIdx.x < 32) {
     const int64_t n = (int64_t)kb * 32 + threadIdx.x;
@@ -337,21 +337,21 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const ScanArgs a)
   if (t >= a.T) return;
   float* s_buf = s_bufs + warp * nbuf * kRowStride;
   float2* s_lut = s_luts + warp * MEPP_MAX_MOTIF_LEN * 4;
-  uint32_t* s_qtab = s_qtabs + warp * 256;
+  uint32_t* s_qtab = s_qtabs + warp * 1024;
   uint16_t* s_queue = s_queues + warp * kQueue;
-  scan_task(a, t, kb, s_codes, s_mask, s_lut, s_qtab, s_buf, s_queue, s_z, lane);
+  scan_task(a, t, kb, s_sym, s_lut, s_qtab, s_buf, s_queue, s_z, lane);
 }
 
 }  // namespace mepp
 
-extern "C" int mepp_scan(const uint32_t* codes_T_dev, const uint32_t* nmask_T_dev, const float* zhat_dev,
+extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
                          int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
                          const int32_t* mlen_dev, const int32_t* nfilt_dev, const uint32_t* qtab_dev,
                          const uint32_t* qthr_dev, void* x_planes_dev, double* rowstats_dev, int32_t* count_dev,
                          int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
                          void* stream) {
   using namespace mepp;
-  MEPP_REQUIRE(codes_T_dev && nmask_T_dev && lut_dev && bias_dev && mlen_dev && nfilt_dev && qtab_dev && qthr_dev &&
+  MEPP_REQUIRE(sym_T_dev && lut_dev && bias_dev && mlen_dev && nfilt_dev && qtab_dev && qthr_dev &&
                x_planes_dev && rowstats_dev && count_dev && density_dev, "scan: null pointer");
   MEPP_REQUIRE(N > 0 && L > 0 && T > 0, "scan: empty input");
   MEPP_REQUIRE(margin >= 0 && margin <= MEPP_MAX_MARGIN, "scan: margin must be in [0, 16]");
@@ -359,11 +359,11 @@ extern "C" int mepp_scan(const uint32_t* codes_T_dev, const uint32_t* nmask_T_de
   MEPP_REQUIRE(mepp_device_ok(), "scan: no sm_100 CUDA device (no CPU fallback)");
   cudaStream_t st = as_stream(stream);
   ScanArgs a;
-  a.codes_T = codes_T_dev; a.nmask_T = nmask_T_dev; a.zhat = zhat_dev;
+  a.sym_T = sym_T_dev; a.zhat = zhat_dev;
   a.N = N; a.n_pad = mepp_pad32(N); a.KB = a.n_pad / kBlockK;
   a.L = L; a.T = T; a.margin = margin;
-  a.Wc = (int)mepp_codes_words(L); a.Wm = (int)mepp_nmask_words(L);
-  a.strideC = a.Wc | 1; a.strideM = a.Wm | 1;
+  a.W3 = (int)mepp_sym_words(L);
+  a.strideS = a.W3 | 1;
   a.lut = lut_dev; a.bias = bias_dev; a.mlen = mlen_dev; a.nfilt = nfilt_dev;
   a.qtab = qtab_dev; a.qthr = qthr_dev;
   a.x_planes = reinterpret_cast<uint8_t*>(x_planes_dev); a.rowstats = rowstats_dev;
@@ -371,8 +371,8 @@ extern "C" int mepp_scan(const uint32_t* codes_T_dev, const uint32_t* nmask_T_de
   a.hits = reinterpret_cast<HitRec*>(hits_dev); a.hits_cap = hits_cap; a.hit_count = hit_count_dev;
   const int nbuf = 32 + 2 * margin;
   size_t smem = sizeof(float) * kScanWarps * nbuf * kRowStride + sizeof(float2) * kScanWarps * MEPP_MAX_MOTIF_LEN * 4 +
-                sizeof(uint32_t) * kScanWarps * 256 + sizeof(uint32_t) * 32 * (a.strideC + a.strideM) +
-                sizeof(float) * 32 + sizeof(uint16_t) * kScanWarps * kQueue;
+                sizeof(uint32_t) * kScanWarps * 1024 + sizeof(uint32_t) * 32 * a.strideS +
+                sizeof(float) * 32 + sizeof(uint16_t) * kScanWarps * kQueue + 256 /* table alignment */;
   MEPP_REQUIRE(smem <= 200 * 1024, "scan: sequence too long for the shared-memory staging (L too large)");
   MEPP_CUDA_CHECK(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MEPP_CUDA_CHECK(cudaMemsetAsync(rowstats_dev, 0, sizeof(double) * 3 * (size_t)T * L, st));

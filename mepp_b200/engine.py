@@ -120,14 +120,12 @@ class Engine:
                 raise ValueError("need at least 4 sequences")
             self.N, self.L = N, L
             self.n_pad = int(_lib.lib.mepp_pad32(N))
-            Wc, Wm = int(_lib.lib.mepp_codes_words(L)), int(_lib.lib.mepp_nmask_words(L))
+            W3 = int(_lib.lib.mepp_sym_words(L))
             st = self._stream()
             ascii_d = self._to_dev(ascii_u8, torch.uint8).contiguous()
-            self.codes_T = torch.empty((Wc, self.n_pad), dtype=torch.int32, device=self.device)
-            self.nmask_T = torch.empty((Wm, self.n_pad), dtype=torch.int32, device=self.device)
+            self.sym_T = torch.empty((W3, self.n_pad), dtype=torch.int32, device=self.device)
             self.gc = torch.empty(self.n_pad, dtype=torch.float32, device=self.device)
-            _lib.check(_lib.lib.mepp_pack_dna(_ptr(ascii_d), N, L, _ptr(self.codes_T), _ptr(self.nmask_T),
-                                              _ptr(self.gc), st), "pack_dna")
+            _lib.check(_lib.lib.mepp_pack_dna(_ptr(ascii_d), N, L, _ptr(self.sym_T), _ptr(self.gc), st), "pack_dna")
             self.launches += 2
             self.use_gc = bool(use_gc)
             if self.use_gc:
@@ -308,7 +306,7 @@ class Engine:
             cap = int(hits_cap) if hits_cap else max(1 << 20, int(T * N * L * 2e-3))
             hits_d = self._buf('hits', cap * 16, torch.uint8)
         ev = self._mark(None, None)
-        _lib.check(_lib.lib.mepp_scan(_ptr(self.codes_T), _ptr(self.nmask_T), _ptr(self.zhat), N, L, T, int(margin),
+        _lib.check(_lib.lib.mepp_scan(_ptr(self.sym_T), _ptr(self.zhat), N, L, T, int(margin),
                                       _ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), _ptr(qtab_d), _ptr(qthr_d),
                                       _ptr(x_planes), _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap,
                                       _ptr(hit_count), st), "scan")

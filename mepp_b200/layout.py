@@ -22,3 +22,15 @@ def decode_y_planes(raw_u8, C, n_pad, BN, n_tiles_n):
     # -> (plane, KB, kc, e, NT, col)
     a = a.transpose(2, 1, 3, 5, 0, 4).reshape(2, KB * 32, n_tiles_n * BN)
     return a[0][:, :C], a[1][:, :C]
+
+
+def decode_symbols(sym_T, N, L):
+    """sym_T uint32 [W3][n_pad] (3 bits per base, continuous stream per sequence) -> int8 (N, L) symbols 0..4."""
+    w = np.ascontiguousarray(sym_T).view(np.uint32).astype(np.uint64)
+    out = np.zeros((N, L), dtype=np.int8)
+    for i in range(L):
+        bit = 3 * i
+        wi, off = bit >> 5, bit & 31
+        v = (w[wi, :N] | (w[wi + 1, :N] << np.uint64(32))) >> np.uint64(off)
+        out[:, i] = (v & np.uint64(7)).astype(np.int8)
+    return out

@@ -69,7 +69,7 @@ def motif_matrix_to_scan_table(motif_matrix, orientation='+', pseudocount=0.0001
     nf = C.c_int(0)
     thr = C.c_double(0.0)
     bgp = None if bg is None else _pd(np.asarray(bg, dtype=np.float64))
-    qtab = np.zeros(256, dtype=np.uint32)
+    qtab = np.zeros(1024, dtype=np.uint32)
     qthr = np.zeros(2, dtype=np.uint32)
     _lib.check(_lib.lib.mepp_motif_table(
         _pd(pwm), m, och, float(pseudocount), float(pvalue), bgp, 1 if honour_flags else 0, float(dp_precision),

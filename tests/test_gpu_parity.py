@@ -43,12 +43,8 @@ def test_pack_matches_oracle(cfg1):
     eng = _engine().stage(cfg1["ascii"], cfg1["scores"], cfg1["perm_idx"])
     N, L = cfg1["N"], cfg1["L"]
     codes = staging.ascii_to_codes(cfg1["ascii"])
-    cT = eng.codes_T.cpu().numpy().view(np.uint32)
-    mT = eng.nmask_T.cpu().numpy().view(np.uint32)
-    dec = np.zeros((N, L), dtype=np.int8)
-    for i in range(L):
-        c = (cT[i // 16, :N] >> (2 * (i % 16))) & 3
-        dec[:, i] = np.where(((mT[i // 32, :N] >> (i % 32)) & 1) == 1, 4, c)
+    from mepp_b200 import layout
+    dec = layout.decode_symbols(eng.sym_T.cpu().numpy(), N, L)
     assert np.array_equal(dec, codes)
     assert np.array_equal(eng.gc[:N].cpu().numpy(), staging.gc_ratio_global(codes))   # bit-exact float32
     assert (eng.gc[N:].cpu().numpy() == 0).all()

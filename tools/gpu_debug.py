@@ -25,13 +25,7 @@ def main():
     torch.cuda.synchronize()
     codes = staging.ascii_to_codes(ascii_u8)
     # ---- pack
-    cT = eng.codes_T.cpu().numpy().view(np.uint32)
-    mT = eng.nmask_T.cpu().numpy().view(np.uint32)
-    dec = np.zeros((N, L), dtype=np.int8)
-    for i in range(L):
-        c = (cT[i // 16, :N] >> (2 * (i % 16))) & 3
-        nb = (mT[i // 32, :N] >> (i % 32)) & 1
-        dec[:, i] = np.where(nb == 1, 4, c)
+    dec = layout.decode_symbols(eng.sym_T.cpu().numpy(), N, L)
     print("pack codes equal:", np.array_equal(dec, codes), flush=True)
     z_or = staging.gc_ratio_global(codes)
     print("gc equal:", np.array_equal(eng.gc[:N].cpu().numpy(), z_or), flush=True)
