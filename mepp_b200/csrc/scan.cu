@@ -53,6 +53,8 @@ struct TaskCtx {
   uint16_t* s_queue;
   int t, kb, m, padl, mg, L, strideS, dual;
   float bias;
+  int64_t tile_stride;   // bytes between consecutive m-tiles of the A operand
+  uint8_t* x_base;       // A operand + this k-block's offset inside an m-tile row
 };
 
 // Exact canonical-order score of the window starting at base i of one sequence (`stream` = that
@@ -146,7 +148,8 @@ __device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, in
         }
         if (k > 1) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) xb[q] = __fdiv_rn(xb[q], kf);
+          for (int q = 0; q < 8; ++q)
+            if (xb[q] != 0.0f) xb[q] = __fdiv_rn(xb[q], kf);   // (0 / k takes the slow division path)
         }
       }
       // row sums over this k-block's 32 sequences (float64), reduced over the 4 kc lanes
@@ -185,11 +188,10 @@ __device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, in
       }
     }
     if (valid) {
-      const int64_t r = (int64_t)c.t * L + p;
-      uint8_t* tile = a.x_planes + a_tile_offset(r >> 7, c.kb, a.KB);
-      const int row = (int)(r & 127);
-      *reinterpret_cast<uint4*>(tile + a_chunk_offset(0, kc, row)) = vh;
-      *reinterpret_cast<uint4*>(tile + a_chunk_offset(1, kc, row)) = vl;
+      const int r = c.t * L + p;                       // global row (< 2^31, checked on the host)
+      uint8_t* dst = c.x_base + (int64_t)(r >> 7) * c.tile_stride + ((kc * kBlockM + (r & 127)) << 4);
+      *reinterpret_cast<uint4*>(dst) = vh;
+      *reinterpret_cast<uint4*>(dst + kChunks * kBlockM * 16) = vl;
     }
   }
 }
@@ -215,7 +217,7 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
                                           const uint32_t* __restrict__ s_sym, float2* __restrict__ s_lut,
                                           uint32_t* __restrict__ s_qtab, float* __restrict__ s_buf,
                                           uint16_t* __restrict__ s_queue, const float* __restrict__ s_z,
-                                          const int lane) {
+                                          TaskCtx* __restrict__ s_ctx, const int lane) {
   const unsigned full = 0xffffffffu;
   const int L = a.L, mg = a.margin;
   const int m = a.mlen[t];
@@ -236,11 +238,18 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
   const uint32_t qinit = real ? a.qthr[t * 2 + 0] : 0u;
   __syncwarp();
 
-  TaskCtx c;
-  c.s_lut = s_lut; c.s_sym = s_sym; c.s_buf = s_buf; c.s_z = s_z; c.s_queue = s_queue;
-  c.t = t; c.kb = kb; c.m = m; c.padl = padl; c.mg = mg; c.L = L; c.strideS = a.strideS;
-  c.dual = a.nfilt[t] == 2;
-  c.bias = a.bias[t];
+  if (lane == 0) {
+    TaskCtx w;
+    w.s_lut = s_lut; w.s_sym = s_sym; w.s_buf = s_buf; w.s_z = s_z; w.s_queue = s_queue;
+    w.t = t; w.kb = kb; w.m = m; w.padl = padl; w.mg = mg; w.L = L; w.strideS = a.strideS;
+    w.dual = a.nfilt[t] == 2;
+    w.bias = a.bias[t];
+    w.tile_stride = a.KB * (int64_t)kATileBytes;
+    w.x_base = a.x_planes + (int64_t)kb * kATileBytes;
+    *s_ctx = w;
+  }
+  __syncwarp();
+  const TaskCtx& c = *s_ctx;
 
   const int nbuf = 32 + 2 * mg;
   const uint32_t* my = s_sym + lane * a.strideS;
@@ -309,7 +318,7 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
   }
 }
 
-__global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const __grid_constant__ ScanArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = blockIdx.x;
@@ -339,7 +348,8 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const ScanArgs a)
   float2* s_lut = s_luts + warp * MEPP_MAX_MOTIF_LEN * 4;
   uint32_t* s_qtab = s_qtabs + warp * 1024;
   uint16_t* s_queue = s_queues + warp * kQueue;
-  scan_task(a, t, kb, s_sym, s_lut, s_qtab, s_buf, s_queue, s_z, lane);
+  __shared__ TaskCtx s_ctxs[kScanWarps];
+  scan_task(a, t, kb, s_sym, s_lut, s_qtab, s_buf, s_queue, s_z, &s_ctxs[warp], lane);
 }
 
 }  // namespace mepp
@@ -354,6 +364,7 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
   MEPP_REQUIRE(sym_T_dev && lut_dev && bias_dev && mlen_dev && nfilt_dev && qtab_dev && qthr_dev &&
                x_planes_dev && rowstats_dev && count_dev && density_dev, "scan: null pointer");
   MEPP_REQUIRE(N > 0 && L > 0 && T > 0, "scan: empty input");
+  MEPP_REQUIRE((int64_t)T * L < (1LL << 31), "scan: T * L must be below 2^31");
   MEPP_REQUIRE(margin >= 0 && margin <= MEPP_MAX_MARGIN, "scan: margin must be in [0, 16]");
   MEPP_REQUIRE(hits_dev == nullptr || hit_count_dev != nullptr, "scan: hits need a hit counter");
   MEPP_REQUIRE(mepp_device_ok(), "scan: no sm_100 CUDA device (no CPU fallback)");
