@@ -169,3 +169,55 @@ def test_reference_entry_point_returns_the_reference_tuple(cfg1):
     assert np.array_equal(ranks_df['score'].to_numpy(), cfg1["scores"])
     sm = smoothed.motif_scores()
     assert np.allclose(sm, profile.blur(orc["X0"], 2, dtype=np.float32), atol=1e-6)
+
+
+def test_run_mepp_writes_the_reference_layout(tmp_path):
+    """mepp.run_mepp end to end on a small scored FASTA: directory layout of SURVEY.md 8b and numbers vs the oracle."""
+    import pandas as pd
+    import yaml
+    from mepp_b200 import synth, mepp as mepp_mod, batch as batch_mod, permutations
+    ascii_u8, scores = synth.synth_sequences(300, 120, seed=21)
+    rng = np.random.default_rng(0)
+    scores = np.round(rng.normal(5, 2, 300), 4).astype(np.float32)        # unsorted: run_mepp must order them
+    fa = tmp_path / "in.fa"
+    with open(fa, "w") as f:
+        for i in range(300):
+            f.write(f">seq{i:04d} {scores[i]:.4f}\n{ascii_u8[i].tobytes().decode()}\n")
+        f.write(">short 1.0\nACGT\n")                                    # dropped: not the max length
+    motifs = synth.synth_motifs(2, seed=5, m_lo=6, m_hi=10)
+    mf = tmp_path / "motifs.txt"
+    with open(mf, "w") as f:
+        for k, pwm in enumerate(motifs):
+            f.write(f">M{k} name{k}\n")
+            for row in pwm:
+                f.write("\t".join(f"{v:.6f}" for v in row) + "\n")
+    out = tmp_path / "out"
+    filepaths_df, html, cmap = mepp_mod.run_mepp(str(fa), str(mf), str(out), num_permutations=30, motif_margin=2,
+                                                motif_orientations=['+', '+/-'], permutation_seed=7, shuffle_seed=1)
+    assert list(filepaths_df.columns) == ['motif_id', 'orientation', 'outdir', 'params', 'log', 'retval', 'attempts']
+    assert len(filepaths_df) == 4 and (filepaths_df['retval'] == 0).all()
+    assert (out / "filepaths.tsv").exists() and (out / "filtered_data_df.tsv").exists()
+    assert (out / "dataset.element_spec.p").exists() and not (out / "dataset").exists()     # batch.py:187-188
+    fdf = pd.read_csv(out / "filtered_data_df.tsv", sep="\t")
+    assert len(fdf) == 300 and (np.diff(fdf['score'].to_numpy()) >= 0).all()
+    d = out / "m0-name0" / "orientation_fwd-rev"
+    for name in ("motif_matrix.npy", "wrapped_params.yaml", "wrapped_params.log", "params.yaml", "filepaths.yaml",
+                 "positions_df.tsv", "positions_df.pkl", "ranks_df.tsv", "ranks_df.pkl"):
+        assert (d / name).exists(), name
+    assert yaml.safe_load(open(d / "params.yaml"))['motif_orientation'] == '+/-'
+    # numbers: rebuild the oracle inputs exactly as run_mepp staged them
+    seq_sorted = np.stack([np.frombuffer(s.encode(), dtype=np.uint8) for s in fdf['sequence']])
+    codes = staging.ascii_to_codes(seq_sorted)
+    sc = fdf['score'].to_numpy().astype(np.float32)
+    perm = permutations.make_permutation_indices(300, 30, seed=7)
+    Y = staging.permuted_scores(sc, perm)
+    z = staging.gc_ratio_global(codes)
+    # file parsing divides counts by the column sum, so use the parsed matrix saved next to the results
+    pwm = np.load(d / "motif_matrix.npy")
+    orc = profile.profile_task(codes, Y, z, pwm, '+/-', margin=2)
+    pos = pd.read_pickle(d / "positions_df.pkl")
+    assert list(pos.columns) == profile.POSITIONS_COLUMNS
+    assert np.array_equal(pos['count'].to_numpy(), orc['positions']['count'])
+    assert _r_close(pos['positional_r'].to_numpy()[:, None], orc['r'][:, :1]).all()
+    ranks = pd.read_pickle(d / "ranks_df.pkl")
+    assert np.array_equal(ranks['density'].to_numpy(), orc['ranks']['density'])

@@ -191,3 +191,28 @@ def test_layout_decoders_roundtrip():
     raw = rng.integers(0, 1000, size=(MT, KB, 2, 4, 128, 8)).astype(np.float16)
     hi, lo = layout.decode_x_planes(raw.view(np.uint8).ravel(), m_rows, n_pad)
     assert hi[130, 41] == np.float32(raw[1, 1, 0, 1, 2, 1]) and lo[5, 7] == np.float32(raw[0, 0, 1, 0, 5, 7])
+
+
+def test_cli_flags_match_the_reference():
+    """Every flag of the reference's `mepp` command (mepp/cli.py:12-456) is accepted."""
+    from click.testing import CliRunner
+    from mepp_b200 import cli
+    flags = {o for p in cli.main.params for o in p.opts + p.secondary_opts}
+    expected = {'--fa', '--motifs', '--out', '--center', '--dgt', '--perms', '--batch', '--jobs', '--keepdata',
+                '--orientations', '--margin', '--pcount', '--pval', '--bg', '--ci', '--sigma', '--cmap', '--smoothing',
+                '--width', '--height', '--formats', '--dpi', '--gjobs', '--nogpu', '--attempts', '--minwait',
+                '--maxwait', '--cmethod', '--cmetric', '--tdpi', '--tformat', '--mtmethod', '--mtalpha',
+                '--thoroughmt', '--non-thoroughmt'}
+    assert expected <= flags
+    res = CliRunner().invoke(cli.main, ['--help'])
+    assert res.exit_code == 0 and '--help' in res.output
+    res = CliRunner().invoke(cli.main, ['--fa', 'x', '--motifs', 'y', '--out', 'z', '--nogpu'])
+    assert res.exit_code != 0 and 'no CPU fallback' in res.output
+
+
+def test_batch_paths_and_slugs():
+    from mepp_b200 import batch
+    assert batch.orientation_to_filepath == {'+': 'fwd', '-': 'rev', '+/-': 'fwd-rev'}
+    assert batch.motif_id_and_orientation_to_filepath('PAX5,Pax8 Paired,Homeobox', '+/-') == \
+        'pax5-pax8-paired-homeobox/orientation_fwd-rev'
+    assert batch.slugify('ohler_motif_2 DRE') == 'ohler-motif-2-dre'
