@@ -30,6 +30,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+GATHER_COLUMNS = ['positional_r', 'permutation_positional_r_lower', 'permutation_positional_r_upper',
+                  'permutation_positional_r_pval', 'integral_r', 'permutation_integral_r_pval', 'positional_r_pval',
+                  'count']
 METRIC = "Gbp*motifs/s scanned+profiled"
 UNIT = "Gbp*motifs/s"
 
@@ -182,9 +185,10 @@ def main():
         batch = eng.profile(my_tasks, margin=margin, tables=tables)
         full = None
         if world > 1:
-            cols = list(batch.positions)
-            block = np.empty((len(my_tasks), len(cols), L), dtype=np.float64)     # task-major, one row per column
-            for j, k in enumerate(cols):
+            # the small per-task profiles go to rank 0 (float32, one row per column; the full tables stay per rank,
+            # as run_batch writes each rank's task directories locally)
+            block = np.empty((len(my_tasks), len(GATHER_COLUMNS), L), dtype=np.float32)
+            for j, k in enumerate(GATHER_COLUMNS):
                 block[:, j, :] = batch.positions[k]
             full = parallel.gather_blocks(block, my_ids, T_total, device=dev)
         return batch, full

@@ -53,44 +53,58 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
-def gather_blocks(local_block, local_ids, n_total, device=None):
-    """Gather per-task result blocks to every rank (rank 0 uses them).
+def gather_blocks(local_block, local_ids, n_total, device=None, root_only=True):
+    """Gather per-task result blocks to rank 0 (every rank when root_only=False).
 
-    local_block: float64 array (T_local, ...) of this rank's tasks; local_ids: their global task indices.
-    Returns a (n_total, ...) array ordered by global task index.  One all_gather of a padded tensor."""
+    local_block: array (T_local, ...) of this rank's tasks (dtype kept: float32 blocks stay float32);
+    local_ids: their global task indices.  Returns a (n_total, ...) array ordered by global task index on
+    rank 0 (None on the other ranks when root_only).  One collective on a padded tensor; the task ids travel
+    in a second, tiny one."""
     import torch
     import torch.distributed as dist
-    local_block = np.ascontiguousarray(local_block, dtype=np.float64)
+    local_block = np.ascontiguousarray(local_block)
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        out = np.empty((n_total,) + local_block.shape[1:], dtype=np.float64)
+        out = np.empty((n_total,) + local_block.shape[1:], dtype=local_block.dtype)
         out[np.asarray(local_ids, dtype=np.int64)] = local_block
         return out
-    world = dist.get_world_size()
+    world, rank = dist.get_world_size(), dist.get_rank()
     t_max = (n_total + world - 1) // world + 1
-    item = int(np.prod(local_block.shape[1:])) if local_block.ndim > 1 else 1
-    pad = np.zeros((t_max, item + 1), dtype=np.float64)
-    pad[:, 0] = -1.0
     k = len(local_ids)
     if k > t_max:
         raise ValueError("shard larger than the padded gather block")
-    pad[:k, 0] = np.asarray(local_ids, dtype=np.float64)
-    pad[:k, 1:] = local_block.reshape(k, item)
-    send = torch.from_numpy(pad)
+    item_shape = local_block.shape[1:]
+    pad = np.zeros((t_max,) + item_shape, dtype=local_block.dtype)
+    pad[:k] = local_block
+    ids = np.full(t_max, -1, dtype=np.int64)
+    ids[:k] = np.asarray(local_ids, dtype=np.int64)
+    send, send_ids = torch.from_numpy(pad), torch.from_numpy(ids)
     if device is not None:
-        send = send.to(device)
-    recv = torch.empty((world * t_max, item + 1), dtype=torch.float64, device=send.device)
-    try:
-        dist.all_gather_into_tensor(recv, send)
-    except (RuntimeError, NotImplementedError):
-        parts = [torch.empty_like(send) for _ in range(world)]
-        dist.all_gather(parts, send)
-        recv = torch.cat(parts, dim=0)
-    rec = recv.cpu().numpy()
-    ids = rec[:, 0]
-    keep = ids >= 0
-    out = np.empty((n_total, item), dtype=np.float64)
-    out[ids[keep].astype(np.int64)] = rec[keep, 1:]
-    return out.reshape((n_total,) + local_block.shape[1:])
+        send, send_ids = send.to(device, non_blocking=True), send_ids.to(device, non_blocking=True)
+    recv = recv_ids = None
+    done = False
+    if root_only:
+        try:
+            if rank == 0:
+                recv = [torch.empty_like(send) for _ in range(world)]
+                recv_ids = [torch.empty_like(send_ids) for _ in range(world)]
+            dist.gather(send, recv, dst=0)
+            dist.gather(send_ids, recv_ids, dst=0)
+            done = True
+        except (RuntimeError, NotImplementedError):
+            done = False
+    if not done:
+        recv = [torch.empty_like(send) for _ in range(world)]
+        recv_ids = [torch.empty_like(send_ids) for _ in range(world)]
+        dist.all_gather(recv, send)
+        dist.all_gather(recv_ids, send_ids)
+    if root_only and rank != 0:
+        return None
+    rec = torch.cat(recv, dim=0).cpu().numpy()
+    rid = torch.cat(recv_ids, dim=0).cpu().numpy()
+    keep = rid >= 0
+    out = np.empty((n_total,) + item_shape, dtype=local_block.dtype)
+    out[rid[keep]] = rec[keep]
+    return out
 
 
 def barrier_and_max(seconds, device=None):

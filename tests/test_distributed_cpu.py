@@ -33,7 +33,10 @@ def _worker(rank, world, port, out_dir):
     costs = [parallel.task_cost(5 + i, 1 + i % 2) for i in range(n_total)]
     mine = parallel.shard_tasks(costs, w)[r]
     block = np.stack([np.full((3, 2), float(i)) + np.arange(6).reshape(3, 2) / 10 for i in mine])
-    full = parallel.gather_blocks(block, mine, n_total)
+    full = parallel.gather_blocks(block.astype(np.float32), mine, n_total)
+    assert (full is None) == (r != 0)
+    both = parallel.gather_blocks(block, mine, n_total, root_only=False)
+    assert both.shape == (n_total, 3, 2) and both.dtype == np.float64
     tmax = parallel.barrier_and_max(1.0 + r)
     if r == 0:
         np.save(os.path.join(out_dir, "full.npy"), full)
@@ -49,9 +52,9 @@ def test_gather_blocks_world2_gloo(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     full = np.load(tmp_path / "full.npy")
-    assert full.shape == (11, 3, 2)
+    assert full.shape == (11, 3, 2) and full.dtype == np.float32
     for i in range(11):
-        assert np.allclose(full[i], float(i) + np.arange(6).reshape(3, 2) / 10)
+        assert np.allclose(full[i], float(i) + np.arange(6).reshape(3, 2) / 10, atol=1e-6)
     assert np.load(tmp_path / "tmax.npy")[0] == 2.0
 
 
