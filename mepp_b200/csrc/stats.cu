@@ -114,6 +114,87 @@ __global__ void row_stats_kernel(const float* __restrict__ r, int L, int C, int 
   }
 }
 
+// One bitonic stage (block size K, partner distance J) on a row held as Q keys per lane
+// (element e = lane + 32 q), then the next stage; compile-time recursion keeps every register
+// index static.
+template <int Q, int K, int J>
+__device__ __forceinline__ void bitonic_stage(uint32_t (&key)[Q], const int lane) {
+  if constexpr (J >= 32) {
+    constexpr int jq = J >> 5;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int pq = q ^ jq;
+      if (pq > q) {
+        const bool up = ((32 * q) & K) == 0;     // K >= 64 here: direction depends on q only
+        const uint32_t a = key[q], b = key[pq];
+        const uint32_t lo = min(a, b), hi = max(a, b);
+        key[q] = up ? lo : hi;
+        key[pq] = up ? hi : lo;
+      }
+    }
+  } else {
+    const bool lower = (lane & J) == 0;          // this lane holds the smaller index of the pair
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const uint32_t mine = key[q];
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, J);
+      const bool up = ((lane + 32 * q) & K) == 0;
+      key[q] = (lower == up) ? min(mine, other) : max(mine, other);
+    }
+  }
+  if constexpr (J > 1) bitonic_stage<Q, K, J / 2>(key, lane);
+  else if constexpr (K < 32 * Q) bitonic_stage<Q, 2 * K, K>(key, lane);
+}
+
+// Warp-per-row variant for P <= 1024: the whole row lives in registers (Q = P_pow2 / 32 keys per
+// lane, element e = lane + 32 q), bitonic stages with partner distance >= 32 are register-to-register
+// compare-exchanges, smaller distances are warp shuffles; no shared memory, no block barriers.
+template <int Q>
+__global__ void __launch_bounds__(256) row_stats_warp_kernel(const float* __restrict__ r, int64_t n_rows, int C,
+                                                             int k_lo, int k_hi, float* __restrict__ full_os,
+                                                             int32_t* __restrict__ full_cnt,
+                                                             uint32_t* __restrict__ sorted_keys) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int P = C - 1;
+  const float* rr = r + row * C;
+  const float t0 = fabsf(rr[0]);
+  uint32_t key[Q];
+  int cnt = 0;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int e = lane + 32 * q;
+    uint32_t kk = 0xffffffffu;  // pads sort to the end
+    if (e < P) {
+      const float v = rr[1 + e];
+      kk = f2key(v);
+      cnt += fabsf(v) >= t0 ? 1 : 0;
+    }
+    key[q] = kk;
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(full, cnt, o);
+  bitonic_stage<Q, 2, 1>(key, lane);
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int e = lane + 32 * q;
+    if (e < P) sorted_keys[row * P + e] = key[q];
+  }
+  const int ranks[4] = {k_lo, min(k_lo + 1, P - 1), k_hi, min(k_hi + 1, P - 1)};
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int e = ranks[w];
+    uint32_t v = 0;
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+      if (q == (e >> 5)) v = key[q];
+    v = __shfl_sync(full, v, e & 31);
+    if (lane == 0) full_os[row * 4 + w] = key2f(v);
+  }
+  if (lane == 0) full_cnt[row] = cnt;
+}
+
 // Per task: sorted thresholds |r[l,0]| (ascending) for the pooled p-values.
 __global__ void thresholds_kernel(const float* __restrict__ r, int L, int C, int L_pow2,
                                   float* __restrict__ ts_sorted) {
@@ -299,11 +380,28 @@ int mepp_perm_stats(const float* r_dev, int T, int L, int C, int k_lo, int k_hi,
   unsigned long long* hist = reinterpret_cast<unsigned long long*>(w + keys_b + ts_b);
   MEPP_CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * (size_t)T * (L + 1), st));
 
-  const size_t row_smem = sizeof(uint32_t) * (size_t)P_pow2;
-  MEPP_CUDA_CHECK(cudaFuncSetAttribute(row_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
-  const int row_threads = P_pow2 >= 512 ? 256 : (P_pow2 >= 64 ? P_pow2 / 2 : 32);
-  row_stats_kernel<<<dim3((unsigned)L, (unsigned)T), row_threads, row_smem, st>>>(
-      r_dev, L, C, P_pow2, k_lo, k_hi, full_os_dev, full_cnt_dev, sorted_keys);
+  if (P_pow2 <= 1024) {
+    // rows in registers, one warp per row
+    const int64_t n_rows = (int64_t)T * L;
+    const unsigned blocks = (unsigned)((n_rows + 7) / 8);
+    const int Q = P_pow2 <= 32 ? 1 : P_pow2 / 32;
+#define MEPP_ROW_WARP(QQ) row_stats_warp_kernel<QQ><<<blocks, 256, 0, st>>>(r_dev, n_rows, C, k_lo, k_hi, full_os_dev, \
+                                                                           full_cnt_dev, sorted_keys)
+    switch (Q) {
+      case 1: MEPP_ROW_WARP(1); break;
+      case 2: MEPP_ROW_WARP(2); break;
+      case 4: MEPP_ROW_WARP(4); break;
+      case 8: MEPP_ROW_WARP(8); break;
+      case 16: MEPP_ROW_WARP(16); break;
+      default: MEPP_ROW_WARP(32); break;
+    }
+#undef MEPP_ROW_WARP
+  } else {
+    const size_t row_smem = sizeof(uint32_t) * (size_t)P_pow2;
+    MEPP_CUDA_CHECK(cudaFuncSetAttribute(row_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+    row_stats_kernel<<<dim3((unsigned)L, (unsigned)T), 256, row_smem, st>>>(
+        r_dev, L, C, P_pow2, k_lo, k_hi, full_os_dev, full_cnt_dev, sorted_keys);
+  }
 
   const size_t thr_smem = sizeof(uint32_t) * (size_t)L_pow2;
   MEPP_CUDA_CHECK(cudaFuncSetAttribute(thresholds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thr_smem));
