@@ -8,7 +8,10 @@
 //
 // Numerics: both operands are fp16 hi+lo splits (hi + lo carries ~22 mantissa
 // bits); three tcgen05.mma products hi*hi + hi*lo + lo*hi accumulate in fp32 in
-// TMEM (the dropped lo*lo term is < 2^-22 relative).
+// TMEM (the dropped lo*lo term is < 2^-22 relative).  The TMEM accumulator is drained
+// every kChunkKB k-blocks (1024 sequences) into fp32 registers of the epilogue warps and
+// restarted, so the fp32 accumulation error depends on the matches inside one chunk, not
+// on the number of sequences.
 //
 // Structure: persistent CTAs, one 128 x BN output tile at a time.
 //   warp 0   : producer -- one elected lane issues cp.async.bulk (TMA engine, 1-D
@@ -17,8 +20,10 @@
 //   warp 1   : TMEM allocator + MMA issuer -- one lane issues tcgen05.mma
 //              (cta_group::1, kind::f16, M=128, N=BN, K=16), tcgen05.commit frees
 //              smem stages and publishes finished accumulators
-//   warps 2-5: epilogue -- tcgen05.ld the fp32 accumulator (double buffered in
-//              TMEM: 2 x 256 columns) and store S
+//   warps 2-9: epilogue -- tcgen05.ld each finished chunk of the fp32 accumulator
+//              (double buffered in TMEM: 2 x 256 columns, so draining chunk i overlaps
+//              the MMAs of chunk i+1), add it into registers (128 columns per thread),
+//              store S after the last chunk
 // Operand tiles use the no-swizzle K-major canonical layout (8x16-byte core
 // matrices, LBO = stride between the two 16-byte K chunks of one MMA, SBO = stride
 // between 8-row groups), produced directly in that layout by scan.cu / pack.cu.
@@ -28,7 +33,8 @@
 namespace mepp {
 
 constexpr int kStages = 4;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // producer, MMA issuer, 8 epilogue warps
+constexpr int kChunkKB = 32;        // k-blocks (of 32 sequences) per TMEM accumulation chunk
 constexpr int kAccCols = 256;  // TMEM columns per accumulator buffer
 
 struct GemmArgs {
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const Gem
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -170,59 +176,71 @@ __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const Gem
       const uint32_t a_plane = kChunks * kBlockM * 16, b_plane = (uint32_t)kChunks * BN * 16;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kAccCols;
-        for (int64_t kb = 0; kb < KB; ++kb) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
+        for (int64_t kb0 = 0; kb0 < KB; kb0 += kChunkKB) {
+          const int64_t kb1 = kb0 + kChunkKB < KB ? kb0 + kChunkKB : KB;
+          mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
+          const uint32_t d_tmem = tmem_base + acc * kAccCols;
+          for (int64_t kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t sb = sa + a_bytes;
 #pragma unroll
-          for (int s = 0; s < kBlockK / 16; ++s) {
-            const uint32_t a_off = (uint32_t)s * 2u * kBlockM * 16u, b_off = (uint32_t)s * 2u * BN * 16u;
-            const uint64_t a_hi = make_desc(sa + a_off, a_lbo, a_sbo);
-            const uint64_t a_lo = make_desc(sa + a_plane + a_off, a_lbo, a_sbo);
-            const uint64_t b_hi = make_desc(sb + b_off, b_lbo, b_sbo);
-            const uint64_t b_lo = make_desc(sb + b_plane + b_off, b_lbo, b_sbo);
-            tc_mma_f16(d_tmem, a_hi, b_hi, idesc, (kb > 0 || s > 0) ? 1u : 0u);
-            tc_mma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
-            tc_mma_f16(d_tmem, a_lo, b_hi, idesc, 1u);
+            for (int s = 0; s < kBlockK / 16; ++s) {
+              const uint32_t a_off = (uint32_t)s * 2u * kBlockM * 16u, b_off = (uint32_t)s * 2u * BN * 16u;
+              const uint64_t a_hi = make_desc(sa + a_off, a_lbo, a_sbo);
+              const uint64_t a_lo = make_desc(sa + a_plane + a_off, a_lbo, a_sbo);
+              const uint64_t b_hi = make_desc(sb + b_off, b_lbo, b_sbo);
+              const uint64_t b_lo = make_desc(sb + b_plane + b_off, b_lbo, b_sbo);
+              tc_mma_f16(d_tmem, a_hi, b_hi, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+              tc_mma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+              tc_mma_f16(d_tmem, a_lo, b_hi, idesc, 1u);
+            }
+            tc_commit(smem_u32(&empty_bar[stage]));   // smem stage reusable once these MMAs retire
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(smem_u32(&empty_bar[stage]));   // smem stage reusable once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          tc_commit(smem_u32(&tfull_bar[acc]));       // chunk accumulator complete
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-        tc_commit(smem_u32(&tfull_bar[acc]));       // accumulator complete
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int h = (warp - 2) >> 2;     // which 128-column half of the accumulator this warp drains
     uint32_t acc = 0, acc_phase = 0;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int64_t mt = item / g.n_tiles_n, nt = item % g.n_tiles_n;
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-      tc_fence_after();
-      const int64_t row = mt * kBlockM + q * 32 + lane;
-      float* dst = g.S + row * g.ldS + nt * (int64_t)BN;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + (uint32_t)c0, v);
-        if (row < g.m_rows) {
+      float sum[128];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
-            o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
-            *reinterpret_cast<float4*>(dst + c0 + j) = o;
+      for (int j = 0; j < 128; ++j) sum[j] = 0.0f;
+      for (int64_t kb0 = 0; kb0 < KB; kb0 += kChunkKB) {
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          if (h * 128 + c0 < BN) {     // warp uniform
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + (uint32_t)(h * 128 + c0), v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(v[j]));
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      const int64_t row = mt * kBlockM + q * 32 + lane;
+      if (row < g.m_rows) {
+        float* dst = g.S + row * g.ldS + nt * (int64_t)BN + h * 128;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 4) {
+          if (h * 128 + c0 < BN)
+            *reinterpret_cast<float4*>(dst + c0) = make_float4(sum[c0], sum[c0 + 1], sum[c0 + 2], sum[c0 + 3]);
+        }
+      }
     }
   }
   tc_fence_before();
