@@ -181,8 +181,7 @@ def main():
     def e2e_step():
         """Public-API step from host buffers: stage + thresholds + all tasks (+ gather to rank 0 when sharded)."""
         eng.stage(h_ascii, h_scores, h_perm, use_gc=True)
-        tables = motif_layers.scan_tables(my_tasks)
-        batch = eng.profile(my_tasks, margin=margin, tables=tables)
+        batch = eng.profile(my_tasks, margin=margin)       # host thresholds are computed per group, overlapped
         full = None
         if world > 1:
             # the small per-task profiles go to rank 0 (float32, one row per column; the full tables stay per rank,

@@ -251,6 +251,245 @@ __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const Gem
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// EXPERIMENTAL, OFF BY DEFAULT (MEPP_GEMM_2CTA=1): measured SLOWER than the 1-CTA kernel above on
+// B200 (cfg 2: 31.7 ms vs 21.2 ms; tensor pipe 57 % active vs 99 %, profiles/r01_gemm_2cta_*), and
+// insensitive to the ring depth (3/4/6 stages identical) -- the pair's shared B operand path, not
+// staging, is the limit.  Kept because it is parity-green and documents the experiment.
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 columns), so the tensor
+// pipe's shared-memory operand traffic per SM drops from 12 KB to 8 KB per MMA and the ring
+// holds 6 stages.  The leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 (M = 256);
+// its commits are multicast to both CTAs' barriers.  The peer's bulk copies complete on the
+// peer's own full barrier; one peer thread forwards each completion to the leader with a remote
+// mbarrier arrive.  Each CTA drains its own 128 x BN accumulator half from its own TMEM.
+constexpr int kStages2 = 6;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tc_commit2_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+profile_gemm2_kernel(const GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();            // 0 = leader (issues the MMAs)
+  const int BN = g.BN, BH = BN / 2;                   // each CTA stages BH columns of B
+  const uint32_t a_bytes = kATileBytes;
+  const uint32_t bh_chunk = (uint32_t)BH * 16u;       // one (plane, kc) slab of this CTA's B half
+  const uint32_t b_bytes = 2u * kChunks * bh_chunk;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t n_stages = (uint32_t)g.variant;      // ring depth (runtime: 2..kStages2)
+  uint8_t* bar_area = smem + (size_t)n_stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_area);       // [kStages2] own bulk copies landed
+  uint64_t* pfull_bar = full_bar + n_stages;                        // [kStages2] (leader) peer's stage landed
+  uint64_t* empty_bar = pfull_bar + n_stages;                       // [kStages2] MMAs of the stage retired
+  uint64_t* tfull_bar = empty_bar + n_stages;                       // [2] accumulator chunk complete
+  uint64_t* tempty_bar = tfull_bar + 2;                             // [2] (leader) both CTAs drained the chunk
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < n_stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&pfull_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(2u * kAccCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // both CTAs' barriers exist before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int n_pairs_m = (g.n_tiles_m + 1) / 2;
+  const int64_t n_items = (int64_t)n_pairs_m * g.n_tiles_n;
+  const int64_t KB = g.KB;
+  const int64_t first = cluster_id_x(), step = num_clusters_x();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ producer (both CTAs)
+    // lane 0 arms the barrier and copies the A tile, lanes 1..8 copy one (plane, kc) slab of the B half each
+    // (nine bulk copies per stage from one lane would make the producer issue-bound)
+    if (lane < 1 + 2 * kChunks) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t item = first; item < n_items; item += step) {
+        const int64_t mp = item / g.n_tiles_n, nt = item % g.n_tiles_n;
+        int64_t mt = 2 * mp + rank;
+        if (mt >= g.n_tiles_m) mt = g.n_tiles_m - 1;   // odd tile count: the peer re-reads a valid tile, stores nothing
+        const uint8_t* a_src = g.A + a_tile_offset(mt, 0, KB);
+        const uint8_t* b_src = g.B + b_tile_offset(nt, 0, KB, BN) + (size_t)rank * bh_chunk;
+        const uint32_t full_tile_chunk = (uint32_t)BN * 16u;
+        for (int64_t kb = 0; kb < KB; ++kb) {
+          mbar_wait_cluster(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          if (lane == 0) {
+            mbar_expect_tx(fb, stage_bytes);
+            bulk_g2s(sa, a_src + kb * (int64_t)a_bytes, a_bytes, fb);
+          } else {
+            const int c = lane - 1;
+            bulk_g2s(sa + a_bytes + (uint32_t)c * bh_chunk,
+                     b_src + kb * (int64_t)b_tile_bytes(BN) + (size_t)c * full_tile_chunk, bh_chunk, fb);
+          }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 1) {
+      // ---------------------------------------------------------- peer: forward "stage landed" to the leader
+      uint32_t stage = 0, phase = 0;
+      for (int64_t item = first; item < n_items; item += step) {
+        for (int64_t kb = 0; kb < KB; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          mbar_arrive_remote(map_to_cta(smem_u32(&pfull_bar[stage]), 0));
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (lane == 0) {
+      // ---------------------------------------------------------- leader: MMA issuer
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * kBlockM) >> 4) << 24);
+      const uint32_t a_lbo = (uint32_t)kBlockM * 16u, b_lbo = bh_chunk, sbo = 128u;
+      const uint32_t a_plane = kChunks * kBlockM * 16, b_plane = (uint32_t)kChunks * bh_chunk;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int64_t item = first; item < n_items; item += step) {
+        for (int64_t kb0 = 0; kb0 < KB; kb0 += kChunkKB) {
+          const int64_t kb1 = kb0 + kChunkKB < KB ? kb0 + kChunkKB : KB;
+          mbar_wait_cluster(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kAccCols;
+          for (int64_t kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            mbar_wait_cluster(smem_u32(&pfull_bar[stage]), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t sb = sa + a_bytes;
+#pragma unroll
+            for (int s = 0; s < kBlockK / 16; ++s) {
+              const uint32_t a_off = (uint32_t)s * 2u * a_lbo, b_off = (uint32_t)s * 2u * b_lbo;
+              const uint64_t a_hi = make_desc(sa + a_off, a_lbo, sbo);
+              const uint64_t a_lo = make_desc(sa + a_plane + a_off, a_lbo, sbo);
+              const uint64_t b_hi = make_desc(sb + b_off, b_lbo, sbo);
+              const uint64_t b_lo = make_desc(sb + b_plane + b_off, b_lbo, sbo);
+              tc_mma2_f16(d_tmem, a_hi, b_hi, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+              tc_mma2_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+              tc_mma2_f16(d_tmem, a_lo, b_hi, idesc, 1u);
+            }
+            tc_commit2_mc(smem_u32(&empty_bar[stage]), (uint16_t)3);   // frees the stage in both CTAs
+            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+          }
+          tc_commit2_mc(smem_u32(&tfull_bar[acc]), (uint16_t)3);       // chunk complete, both CTAs
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int64_t item = first; item < n_items; item += step) {
+      const int64_t mp = item / g.n_tiles_n, nt = item % g.n_tiles_n;
+      const int64_t mt = 2 * mp + rank;
+      float sum[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) sum[j] = 0.0f;
+      for (int64_t kb0 = 0; kb0 < KB; kb0 += kChunkKB) {
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          if (h * 128 + c0 < BN) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + (uint32_t)(h * 128 + c0), v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(v[j]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(&tempty_bar[acc]), 0));   // leader's barrier
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      const int64_t row = mt * kBlockM + q * 32 + lane;
+      if (mt < g.n_tiles_m && row < g.m_rows) {
+        float* dst = g.S + row * g.ldS + nt * (int64_t)BN + h * 128;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 4) {
+          if (h * 128 + c0 < BN)
+            *reinterpret_cast<float4*>(dst + c0) = make_float4(sum[c0], sum[c0 + 1], sum[c0 + 2], sum[c0 + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // nobody leaves while the pair still signals / reads smem
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kAccCols) : "memory");
+  }
+}
+
 // Cross-check: the same contraction from the same fp16 planes on CUDA cores with
 // float64 accumulation (all four hi/lo products), for selected rows.
 __global__ void gemm_check_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B,
@@ -308,6 +547,22 @@ int mepp_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float*
   MEPP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int64_t n_items = (int64_t)g.n_tiles_m * g.n_tiles_n;
   unsigned grid = (unsigned)(n_items < sms ? n_items : sms);
+  const char* two = getenv("MEPP_GEMM_2CTA");
+  if (two && atoi(two) != 0 && g.BN % 32 == 0) {
+    const char* stg = getenv("MEPP_GEMM_STAGES");
+    int n_stages = stg ? atoi(stg) : kStages2;
+    if (n_stages < 2) n_stages = 2;
+    if (n_stages > kStages2) n_stages = kStages2;
+    g.variant = n_stages;
+    size_t smem2 = (size_t)n_stages * (kATileBytes + b_tile_bytes(g.BN) / 2) + 512;
+    MEPP_CUDA_CHECK(cudaFuncSetAttribute(profile_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    int64_t n_items2 = (int64_t)((g.n_tiles_m + 1) / 2) * g.n_tiles_n;
+    int64_t pairs = sms / 2;
+    if (n_items2 < pairs) pairs = n_items2;
+    profile_gemm2_kernel<<<(unsigned)(2 * pairs), kGemmThreads, smem2, as_stream(stream)>>>(g);
+    MEPP_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   profile_gemm_kernel<<<grid, kGemmThreads, smem, as_stream(stream)>>>(g);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;

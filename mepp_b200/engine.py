@@ -205,12 +205,11 @@ class Engine:
             center = 0
         if center > L:
             center = L - 1          # core.py:503-509
-        if tables is None:
-            tables = motif_layers.scan_tables(list(tasks), honour_flags=honour_flags, pseudocount=pseudocount,
-                                              pvalue=pvalue, bg=bg)
-        for tb in tables:
-            if tb['m'] > L:
+        tasks = list(tasks)
+        for pwm, _o in tasks:
+            if np.shape(pwm)[1] > L:
                 raise ValueError("motif longer than the sequences")
+        table_kw = dict(honour_flags=honour_flags, pseudocount=pseudocount, pvalue=pvalue, bg=bg)
         G = self.group_size()
         if T_all > 96:
             # at least three groups so that the host finalisation of one group overlaps the kernels of the next
@@ -219,8 +218,12 @@ class Engine:
         outs = []
         with torch.cuda.device(self.device):
             pending = None
+            all_tables = []
             for gi, (g0, g1) in enumerate(groups):
-                nxt = self._launch_group(tables[g0:g1], margin, return_hits, return_r, hits_cap,
+                # host threshold DP of this group only: the next group's tables are computed while this one runs
+                gt = tables[g0:g1] if tables is not None else motif_layers.scan_tables(tasks[g0:g1], **table_kw)
+                all_tables.extend(gt)
+                nxt = self._launch_group(gt, margin, return_hits, return_r, hits_cap,
                                          confidence_interval_pct, gi % 2)
                 if pending is not None:
                     outs.append(self._collect_group(pending, margin, confidence_interval_pct, center))
@@ -247,7 +250,7 @@ class Engine:
             order = np.lexsort((hits['pos'], hits['seq'], hits['task']))
             hits = hits[order]
         r = np.concatenate([o['r'] for o in outs], axis=0) if return_r else None
-        thr = np.array([tb['thr'] for tb in tables])
+        thr = np.array([tb['thr'] for tb in all_tables])
         return ProfileBatch(list(range(T_all)), positions, density[:, :N], self.scores, thr,
                             hit_counts=cat('hit_count'), hits=hits, r=r, n_seq=N)
 

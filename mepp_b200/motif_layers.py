@@ -78,6 +78,18 @@ def motif_matrix_to_scan_table(motif_matrix, orientation='+', pseudocount=0.0001
     return dict(lut=lut, bias=np.float32(bias.value), n_filters=nf.value, thr=thr.value, m=m, qtab=qtab, qthr=qthr)
 
 
+_POOLS = {}
+
+
+def _pool(n_threads=None):
+    """Persistent host thread pool for the threshold DP (ctypes drops the GIL)."""
+    import os
+    n = n_threads or min(32, os.cpu_count() or 1)
+    if n not in _POOLS:
+        _POOLS[n] = ThreadPoolExecutor(max_workers=n)
+    return _POOLS[n]
+
+
 def scan_tables(tasks, n_threads=None, **kw):
     """Scan tables for a list of (motif_matrix, orientation); the DP runs threaded (ctypes drops the GIL).
     '+' and dual tasks of the same motif share one threshold computation through a small cache."""
@@ -89,7 +101,6 @@ def scan_tables(tasks, n_threads=None, **kw):
         keys.append(key)
         cache.setdefault(key, (pwm, orient))
     uniq = list(cache.items())
-    with ThreadPoolExecutor(max_workers=n_threads) as ex:
-        res = list(ex.map(lambda kv: motif_matrix_to_scan_table(kv[1][0], kv[1][1], **kw), uniq))
+    res = list(_pool(n_threads).map(lambda kv: motif_matrix_to_scan_table(kv[1][0], kv[1][1], **kw), uniq))
     table = {kv[0]: r for kv, r in zip(uniq, res)}
     return [table[k] for k in keys]
