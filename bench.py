@@ -31,8 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GATHER_COLUMNS = ['positional_r', 'permutation_positional_r_lower', 'permutation_positional_r_upper',
-                  'permutation_positional_r_pval', 'integral_r', 'permutation_integral_r_pval', 'positional_r_pval',
-                  'count']
+                  'permutation_positional_r_pval']
 METRIC = "Gbp*motifs/s scanned+profiled"
 UNIT = "Gbp*motifs/s"
 

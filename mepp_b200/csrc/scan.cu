@@ -280,8 +280,8 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
       const int i_end = base - mg + nbuf - padl;      // exclusive
       if (i_end > n_valid) b_hi -= i_end - n_valid;
     }
-#pragma unroll 1
-    for (int b = b_lo; b < b_hi; ++b) {
+    // one window: pre-filter sum -> candidate flag, then advance the window by one base (3 bits)
+    auto eval_window = [&]() -> bool {
       uint32_t sum = qinit + slot<0>(qbase, r0, r1) + slot<1>(qbase, r0, r1) + slot<2>(qbase, r0, r1);
       if (np > 3) {
         sum += slot<3>(qbase, r0, r1) + slot<4>(qbase, r0, r1);
@@ -295,20 +295,51 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
           }
         }
       }
-      const bool cand = (sum & 0x80008000u) != 0u;
-      // advance the window by one base
       r0 = __funnelshift_r(r0, r1, 3); r1 = __funnelshift_r(r1, r2, 3); r2 = __funnelshift_r(r2, r3, 3);
       r3 = __funnelshift_r(r3, r4, 3); r4 = __funnelshift_r(r4, r5, 3); r5 >>= 3;
-      if (--left == 0) { r3 = my[next_w]; r4 = my[next_w + 1]; r5 = my[next_w + 2]; next_w += 3; left = 32; }
-      const unsigned bal = __ballot_sync(full, cand);
-      if (bal != 0u) {
-        if (cand) {
-          const int slot_i = q_tail + __popc(bal & ((1u << lane) - 1u));
-          s_queue[slot_i & (kQueue - 1)] = (uint16_t)((lane << 8) | b);
-        }
-        q_tail += __popc(bal);
-        if (q_tail - q_head >= 32) { new_nz |= flush_candidates(a, c, q_head, 32, base, lane); q_head += 32; }
+      return (sum & 0x80008000u) != 0u;
+    };
+    auto refill = [&]() { r3 = my[next_w]; r4 = my[next_w + 1]; r5 = my[next_w + 2]; next_w += 3; left = 32; };
+    // queue the candidates of buffer row b (ballot `bal`), flushing the ring whenever 32 are pending
+    auto push = [&](unsigned bal, bool cand, int b) {
+      if (cand) {
+        const int slot_i = q_tail + __popc(bal & ((1u << lane) - 1u));
+        s_queue[slot_i & (kQueue - 1)] = (uint16_t)((lane << 8) | b);
       }
+      q_tail += __popc(bal);
+      if (q_tail - q_head >= 32) { new_nz |= flush_candidates(a, c, q_head, 32, base, lane); q_head += 32; }
+    };
+    int b = b_lo;
+    // scalar steps until the refill counter is a multiple of 4, groups of 4 windows, scalar tail
+#pragma unroll 1
+    for (; b < b_hi && (left & 3) != 0; ++b) {
+      const bool cand = eval_window();
+      if (--left == 0) refill();
+      const unsigned bal = __ballot_sync(full, cand);
+      if (bal != 0u) push(bal, cand, b);
+    }
+#pragma unroll 1
+    for (; b + 4 <= b_hi; b += 4) {
+      uint32_t cb = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cb |= (eval_window() ? 1u : 0u) << u;   // 4 independent windows in flight
+      left -= 4;
+      if (left == 0) refill();
+      if (__any_sync(full, cb != 0u)) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool cand = (cb >> u) & 1u;
+          const unsigned bal = __ballot_sync(full, cand);
+          if (bal != 0u) push(bal, cand, b + u);
+        }
+      }
+    }
+#pragma unroll 1
+    for (; b < b_hi; ++b) {
+      const bool cand = eval_window();
+      if (--left == 0) refill();
+      const unsigned bal = __ballot_sync(full, cand);
+      if (bal != 0u) push(bal, cand, b);
     }
     if (q_tail != q_head) { new_nz |= flush_candidates(a, c, q_head, q_tail - q_head, base, lane); q_head = q_tail; }
     __syncwarp();

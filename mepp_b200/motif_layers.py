@@ -83,8 +83,8 @@ _POOLS = {}
 
 def _pool(n_threads=None):
     """Persistent host thread pool for the threshold DP (ctypes drops the GIL)."""
-    import os
-    n = n_threads or min(32, os.cpu_count() or 1)
+    from .parallel import host_threads
+    n = n_threads or host_threads()
     if n not in _POOLS:
         _POOLS[n] = ThreadPoolExecutor(max_workers=n)
     return _POOLS[n]

@@ -13,6 +13,17 @@ import os
 import numpy as np
 
 
+def host_threads():
+    """Host worker threads this process may use: MEPP_HOST_THREADS, else cores / ranks-on-this-node
+    (torchrun exports LOCAL_WORLD_SIZE), so that 8 ranks do not oversubscribe the host 8-fold."""
+    env = os.environ.get("MEPP_HOST_THREADS")
+    if env:
+        return max(1, int(env))
+    cores = os.cpu_count() or 1
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, min(32, cores // max(1, local_world)))
+
+
 def task_cost(m, n_filters):
     """Relative scan cost of a task; the GEMM / statistics cost is the same for every task."""
     return 8.0 + float(m) * float(n_filters)

@@ -16,10 +16,15 @@ from scipy import stats as _st
 _POOL = None
 
 
+def _threads():
+    from .parallel import host_threads
+    return host_threads()
+
+
 def _pool():
     global _POOL
     if _POOL is None:
-        _POOL = ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1))
+        _POOL = ThreadPoolExecutor(max_workers=_threads())
     return _POOL
 
 
@@ -30,7 +35,7 @@ def _t_sf2(abs_t, df):
     if x.size < 32768:
         return _sp.stdtr(df, x) * 2
     flat = x.reshape(-1)
-    n = min(32, os.cpu_count() or 1)
+    n = _threads()
     parts = list(_pool().map(lambda c: _sp.stdtr(df, c), np.array_split(flat, n)))
     return (np.concatenate(parts) * 2).reshape(x.shape)
 

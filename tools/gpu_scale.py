@@ -16,7 +16,8 @@ def main():
     n_motifs = int(os.environ.get("SCALE_MOTIFS", "0")) or None
     n_oracle = int(os.environ.get("SCALE_ORACLE", "2"))
     t0 = time.time()
-    cfg = synth.make_config(cfgname, n_motifs=n_motifs, n_seq=int(os.environ.get("SCALE_N", "0")) or None)
+    cfg = synth.make_config(cfgname, n_motifs=n_motifs, n_seq=int(os.environ.get("SCALE_N", "0")) or None,
+                            n_perm=int(os.environ.get("SCALE_P", "0")) or None)
     print(f"synth {cfgname}: N={cfg['N']} L={cfg['L']} P={cfg['P']} tasks={len(cfg['tasks'])} in {time.time()-t0:.1f}s",
           flush=True)
     tasks = [(pwm, o) for _, pwm, o in cfg["tasks"]]
@@ -46,6 +47,9 @@ def main():
     Y = staging.permuted_scores(cfg["scores"], cfg["perm_idx"])
     z = staging.gc_ratio_global(codes)
     sel = list(range(min(n_oracle, len(tasks))))
+    if not sel:
+        print("DONE (no oracle comparison)", flush=True)
+        return
     b2 = eng.profile([tasks[i] for i in sel], margin=cfg["margin"], return_r=True, return_hits=True)
     for j, i in enumerate(sel):
         t0 = time.time()
