@@ -20,7 +20,8 @@
  *            [3i, 3i+3) of the stream, word w of sequence n is sym_T[w][n] (transposed so that
  *            lanes = sequences read coalesced)
  *   X planes the match matrix as GEMM operand A, fp16 hi/lo split, tiled:
- *            [m_tile][k_block][plane 2][kc 4][row 128][8 seq] halves, row = task*L + position
+ *            [m_tile][k_block]{[plane 2][kc 4][row 128][8 seq] halves, 16-byte trailer}, row = task*L +
+ *            position; trailer word 0 bit h = "sequences [16h,16h+16) of the k-block hold a non-zero"
  *   Y planes the (1+P) score columns as GEMM operand B, same tiling with BN columns:
  *            [n_tile][k_block][plane 2][kc 4][col BN][8 seq] halves
  */
@@ -114,6 +115,10 @@ int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
  * S_dev: float [m_rows][ldS], ldS = n_tiles_n*BN. */
 int mepp_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float* S_dev,
                       int64_t m_rows, int C, int64_t n_pad, void* stream);
+/* Instrumentation: out2 = {K=16 MMA steps issued, K=16 steps total} accumulated over all
+ * mepp_profile_gemm launches of this process since the last reset (all-zero steps of X are skipped;
+ * synchronises the device). */
+int mepp_gemm_counters(unsigned long long* out2, int reset);
 /* CUDA-core cross-check of the same contraction from the same planes (float64 accumulate). */
 int mepp_profile_gemm_check(const void* x_planes_dev, const void* y_planes_dev, double* S_dev,
                             int64_t m_rows, int C, int64_t n_pad,

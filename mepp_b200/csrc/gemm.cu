@@ -112,6 +112,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// {K=16 steps issued, K=16 steps total} summed over all launches since the last reset (bench.py reports
+// the executed tensor rate and the fraction of all-zero steps that were skipped from these).
+__device__ unsigned long long g_mma_steps[2];
+
 __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -175,27 +179,37 @@ __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const Gem
       const uint32_t b_sbo = g.variant == 1 ? (uint32_t)BN * 16u : 128u;
       const uint32_t a_plane = kChunks * kBlockM * 16, b_plane = (uint32_t)kChunks * BN * 16;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      unsigned long long issued = 0, total = 0;
       for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        total += (unsigned long long)KB * (kBlockK / 16);
         for (int64_t kb0 = 0; kb0 < KB; kb0 += kChunkKB) {
           const int64_t kb1 = kb0 + kChunkKB < KB ? kb0 + kChunkKB : KB;
           mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kAccCols;
+          bool acc_valid = false;                      // has this chunk's accumulator been written yet?
           for (int64_t kb = kb0; kb < kb1; ++kb) {
             mbar_wait(smem_u32(&full_bar[stage]), phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t sb = sa + a_bytes;
+            // trailer of the A tile: bit s set <=> K=16 step s holds a non-zero x (scan.cu); zero steps are skipped
+            uint32_t nzmask = *reinterpret_cast<volatile uint32_t*>(smem + (size_t)stage * stage_bytes + kATileData);
+            if (g.variant == 2) nzmask = 3u;           // MEPP_GEMM_DESC_VARIANT=2: never skip (A/B testing)
 #pragma unroll
             for (int s = 0; s < kBlockK / 16; ++s) {
+              const bool last = (kb == kb1 - 1) && (s == kBlockK / 16 - 1);
+              if (!((nzmask >> s) & 1u) && !(last && !acc_valid)) continue;   // (an untouched chunk still needs one write)
               const uint32_t a_off = (uint32_t)s * 2u * kBlockM * 16u, b_off = (uint32_t)s * 2u * BN * 16u;
               const uint64_t a_hi = make_desc(sa + a_off, a_lbo, a_sbo);
               const uint64_t a_lo = make_desc(sa + a_plane + a_off, a_lbo, a_sbo);
               const uint64_t b_hi = make_desc(sb + b_off, b_lbo, b_sbo);
               const uint64_t b_lo = make_desc(sb + b_plane + b_off, b_lbo, b_sbo);
-              tc_mma_f16(d_tmem, a_hi, b_hi, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+              tc_mma_f16(d_tmem, a_hi, b_hi, idesc, acc_valid ? 1u : 0u);
               tc_mma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
               tc_mma_f16(d_tmem, a_lo, b_hi, idesc, 1u);
+              acc_valid = true;
+              ++issued;
             }
             tc_commit(smem_u32(&empty_bar[stage]));   // smem stage reusable once these MMAs retire
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -204,6 +218,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const Gem
           if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
       }
+      atomicAdd(&g_mma_steps[0], issued);
+      atomicAdd(&g_mma_steps[1], total);
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
@@ -540,7 +556,7 @@ int mepp_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float*
   g.n_tiles_m = (int)((m_rows + kBlockM - 1) / kBlockM);
   const char* var = getenv("MEPP_GEMM_DESC_VARIANT");
   g.variant = var ? atoi(var) : 0;
-  size_t smem = (size_t)kStages * (kATileBytes + b_tile_bytes(g.BN)) + 256;
+  size_t smem = (size_t)kStages * (kATileBytes + b_tile_bytes(g.BN)) + 256;   // A tiles include their 16-byte trailer
   MEPP_CUDA_CHECK(cudaFuncSetAttribute(profile_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   MEPP_CUDA_CHECK(cudaGetDevice(&dev));
@@ -565,6 +581,17 @@ int mepp_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float*
   }
   profile_gemm_kernel<<<grid, kGemmThreads, smem, as_stream(stream)>>>(g);
   MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mepp_gemm_counters(unsigned long long* out2, int reset) {
+  using namespace mepp;
+  MEPP_REQUIRE(mepp_device_ok(), "gemm_counters: no sm_100 CUDA device (no CPU fallback)");
+  if (out2) MEPP_CUDA_CHECK(cudaMemcpyFromSymbol(out2, g_mma_steps, sizeof(unsigned long long) * 2));
+  if (reset) {
+    const unsigned long long z[2] = {0ull, 0ull};
+    MEPP_CUDA_CHECK(cudaMemcpyToSymbol(g_mma_steps, z, sizeof(z)));
+  }
   return 0;
 }
 

@@ -189,9 +189,12 @@ __device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, in
     }
     if (valid) {
       const int r = c.t * L + p;                       // global row (< 2^31, checked on the host)
-      uint8_t* dst = c.x_base + (int64_t)(r >> 7) * c.tile_stride + ((kc * kBlockM + (r & 127)) << 4);
+      uint8_t* tile = c.x_base + (int64_t)(r >> 7) * c.tile_stride;
+      uint8_t* dst = tile + ((kc * kBlockM + (r & 127)) << 4);
       *reinterpret_cast<uint4*>(dst) = vh;
       *reinterpret_cast<uint4*>(dst + kChunks * kBlockM * 16) = vl;
+      if ((vh.x | vh.y | vh.z | vh.w | vl.x | vl.y | vl.z | vl.w) != 0u)   // rare: mark the K=16 half as non-zero
+        atomicOr(reinterpret_cast<unsigned int*>(tile + kATileData), 1u << (kc >> 1));
     }
   }
 }
@@ -383,6 +386,12 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const __grid_cons
   scan_task(a, t, kb, s_sym, s_lut, s_qtab, s_buf, s_queue, s_z, &s_ctxs[warp], lane);
 }
 
+// Clears the 16-byte "non-zero" trailer of every A tile (one thread per tile).
+__global__ void zero_trailers_kernel(uint8_t* __restrict__ x_planes, int64_t n_tiles) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_tiles) *reinterpret_cast<uint4*>(x_planes + i * kATileBytes + kATileData) = make_uint4(0u, 0u, 0u, 0u);
+}
+
 }  // namespace mepp
 
 extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
@@ -421,6 +430,12 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
   MEPP_CUDA_CHECK(cudaMemsetAsync(count_dev, 0, sizeof(int32_t) * (size_t)T * L, st));
   MEPP_CUDA_CHECK(cudaMemsetAsync(density_dev, 0, sizeof(int32_t) * (size_t)T * a.n_pad, st));
   if (hit_count_dev) MEPP_CUDA_CHECK(cudaMemsetAsync(hit_count_dev, 0, sizeof(unsigned long long), st));
+  {
+    // reset the per-tile "non-zero" trailers of every A tile this call writes
+    const int64_t n_tiles_m = ((int64_t)T * L + kBlockM - 1) / kBlockM;
+    const int64_t n_tiles = n_tiles_m * a.KB;
+    zero_trailers_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>(a.x_planes, n_tiles);
+  }
   dim3 grid((unsigned)a.KB, (unsigned)((T + kScanWarps - 1) / kScanWarps));
   MEPP_REQUIRE(grid.y <= 65535, "scan: too many tasks in one call");
   scan_kernel<<<grid, kScanWarps * 32, smem, st>>>(a);

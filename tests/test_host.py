@@ -188,9 +188,13 @@ def test_layout_decoders_roundtrip():
     rng = np.random.default_rng(0)
     m_rows, n_pad = 200, 64
     MT, KB = 2, 2
-    raw = rng.integers(0, 1000, size=(MT, KB, 2, 4, 128, 8)).astype(np.float16)
-    hi, lo = layout.decode_x_planes(raw.view(np.uint8).ravel(), m_rows, n_pad)
-    assert hi[130, 41] == np.float32(raw[1, 1, 0, 1, 2, 1]) and lo[5, 7] == np.float32(raw[0, 0, 1, 0, 5, 7])
+    data = rng.integers(0, 1000, size=(MT, KB, 2, 4, 128, 8)).astype(np.float16)
+    raw = np.zeros((MT * KB, 16384 + 16), dtype=np.uint8)
+    raw[:, :16384] = data.reshape(MT * KB, -1).view(np.uint8)
+    raw[:, 16384] = [1, 2, 3, 0]
+    hi, lo, flags = layout.decode_x_planes(raw.ravel(), m_rows, n_pad, with_flags=True)
+    assert hi[130, 41] == np.float32(data[1, 1, 0, 1, 2, 1]) and lo[5, 7] == np.float32(data[0, 0, 1, 0, 5, 7])
+    assert flags.tolist() == [[1, 2], [3, 0]]
 
 
 def test_cli_flags_match_the_reference():
@@ -216,3 +220,42 @@ def test_batch_paths_and_slugs():
     assert batch.motif_id_and_orientation_to_filepath('PAX5,Pax8 Paired,Homeobox', '+/-') == \
         'pax5-pax8-paired-homeobox/orientation_fwd-rev'
     assert batch.slugify('ohler_motif_2 DRE') == 'ohler-motif-2-dre'
+
+
+def test_filter_table_is_conservative(lib):
+    """The scan kernel's integer pre-filter (host.cu build_filter_table) must never reject a window whose
+    exact float32 score passes the threshold: check the bound on random windows, N bases included."""
+    from mepp_b200 import motif_layers, synth
+    rng = np.random.default_rng(9)
+    for pwm in synth.synth_motifs(6, seed=13, m_lo=3, m_hi=32) + list(synth.load_motif_library('ohler').values())[:3]:
+        for o in ('+', '-', '+/-'):
+            tab = motif_layers.motif_matrix_to_scan_table(pwm, o)
+            m, nf = tab['m'], tab['n_filters']
+            q = tab['qtab'].reshape(16, 64)
+            qinit = int(tab['qthr'][0])
+            syms = rng.integers(0, 5, size=(4000, m))
+            syms[:2000][syms[:2000] == 4] = rng.integers(0, 4, size=(syms[:2000] == 4).sum())   # half without N
+            # plant near-consensus windows so that real matches are present
+            best = np.argmax(tab['lut'][:m, :, 0], axis=1)
+            syms[:200] = best
+            syms[100:200, rng.integers(0, m, 100)] = rng.integers(0, 4, 100)
+            pad = np.zeros((syms.shape[0], 32), dtype=np.int64)
+            pad[:, :m] = syms
+            idx = pad[:, 0::2] | (pad[:, 1::2] << 3)
+            packed = q[np.arange(16)[None, :], idx].astype(np.int64).sum(axis=1) + qinit
+            passes = (packed & 0x80008000) != 0
+            # exact canonical float32 scores
+            W = tab['lut'][:m]
+            hit = np.zeros(len(syms), dtype=bool)
+            for f in range(nf):
+                acc = np.zeros(len(syms), dtype=np.float32)
+                for j in range(m):
+                    sj = syms[:, j]
+                    normal = acc + W[j, np.minimum(sj, 3), f]
+                    an = acc
+                    for c in range(4):
+                        an = an + np.float32(0.25) * W[j, c, f]
+                    acc = np.where(sj == 4, an, normal).astype(np.float32)
+                hit |= (acc + tab['bias']) > 0
+            assert not (hit & ~passes).any(), "pre-filter rejected a true match"
+            assert hit[:100].all() or tab['thr'] > W[:, :, 0].max(axis=1).sum()      # consensus windows do match
