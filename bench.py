@@ -200,7 +200,10 @@ def main():
     for _ in range(max(args.warmup, 1)):
         batch, full = e2e_step()
     tables = motif_layers.scan_tables(my_tasks)
-    d2h_bytes = int(sum(np.asarray(v).nbytes for v in batch.positions.values()) + batch.density.nbytes)
+    # bytes actually copied device -> host per step: r0, 4 order statistics, 3 counts per (task, position);
+    # density per (task, sequence); integrals per (task, column)
+    n_loc = len(my_tasks)
+    d2h_bytes = int(n_loc * L * (4 + 16 + 4 + 8 + 4) + n_loc * eng.n_pad * 4 + n_loc * (1 + P) * 8 + n_loc * 24)
 
     sampler = ClockSampler(local)
     sampler.start()

@@ -215,6 +215,8 @@ class Engine:
             # at least three groups so that the host finalisation of one group overlaps the kernels of the next
             G = min(G, max(32, -(-T_all // 3)))
         groups = [(g0, min(g0 + G, T_all)) for g0 in range(0, T_all, G)]
+        store = stats_host.alloc_positions(T_all, L, self.P)
+        density_all = np.empty((T_all, N), dtype=np.int32)
         outs = []
         with torch.cuda.device(self.device):
             pending = None
@@ -225,18 +227,18 @@ class Engine:
                 all_tables.extend(gt)
                 nxt = self._launch_group(gt, margin, return_hits, return_r, hits_cap,
                                          confidence_interval_pct, gi % 2)
+                nxt['t0'] = g0
                 if pending is not None:
-                    outs.append(self._collect_group(pending, margin, confidence_interval_pct, center))
+                    outs.append(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
                 pending = nxt
                 if return_hits or return_r:
                     # the match list / r buffers are reused by the next group: no overlap in this mode
-                    outs.append(self._collect_group(pending, margin, confidence_interval_pct, center))
+                    outs.append(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
                     pending = None
             if pending is not None:
-                outs.append(self._collect_group(pending, margin, confidence_interval_pct, center))
+                outs.append(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
         cat = lambda k: np.concatenate([o[k] for o in outs], axis=0)
-        density = cat('density')
-        positions = {k: np.concatenate([o['positions'][k] for o in outs], axis=0) for k in outs[0]['positions']}
+        positions = stats_host.positions_view(store, center)
         hits = None
         if return_hits:
             parts = []
@@ -244,14 +246,14 @@ class Engine:
             for o in outs:
                 h = o['hits'].copy()
                 h['task'] += off
-                off += o['density'].shape[0]
+                off += o['T']
                 parts.append(h)
             hits = np.concatenate(parts) if parts else np.zeros(0, dtype=HIT_DTYPE)
             order = np.lexsort((hits['pos'], hits['seq'], hits['task']))
             hits = hits[order]
         r = np.concatenate([o['r'] for o in outs], axis=0) if return_r else None
         thr = np.array([tb['thr'] for tb in all_tables])
-        return ProfileBatch(list(range(T_all)), positions, density[:, :N], self.scores, thr,
+        return ProfileBatch(list(range(T_all)), positions, density_all, self.scores, thr,
                             hit_counts=cat('hit_count'), hits=hits, r=r, n_seq=N)
 
     def _mark(self, prev, name):
@@ -359,17 +361,19 @@ class Engine:
         done.record(torch.cuda.current_stream(self.device))
         return dict(host=host, done=done, T=T, hits_d=hits_d, cap=cap, return_hits=return_hits)
 
-    def _collect_group(self, pend, margin, ci, center):
-        """Wait for one group's D2H copies and finalise its statistics on the host."""
+    def _collect_group(self, pend, margin, ci, store, density_all):
+        """Wait for one group's D2H copies and finalise its statistics on the host, straight into the
+        preallocated output store (rows t0 .. t0+T)."""
         pend['done'].synchronize()
         h = {k: v.numpy() for k, v in pend['host'].items()}
-        out = {}
+        t0, T = pend['t0'], pend['T']
         if self.P > 0:
             args = (h['full_os'], h['full_cnt'], h['semi_os'], h['semi_cnt'], h['integral'])
         else:
             args = (None, None, None, None, None)
-        out['positions'] = stats_host.finalize_positions(h['r0'], *args, h['count'], self.N, self.P, margin, ci, center)
-        out['density'] = h['density'].copy()
+        stats_host.finalize_into(store, t0, h['r0'], *args, h['count'], self.N, margin, ci)
+        density_all[t0:t0 + T] = h['density'][:, :self.N]
+        out = dict(T=T)
         nh = int(h['hit_count'][0])
         out['hit_count'] = np.array([nh], dtype=np.int64)
         if pend['return_hits']:

@@ -109,47 +109,86 @@ def smooth_counts(count, window):
     return out
 
 
-def finalize_positions(r0, full_os, full_cnt, semi_os, semi_cnt, integral, count, n_seq, P, margin,
-                       confidence_interval_pct=95, center=None, permutation_mode='semi'):
-    """Assemble the positions_df columns for T tasks.
+PER_POSITION = {  # column -> dtype of the per-(task, position) arrays the host materialises
+    'positional_r': np.float32,
+    'permutation_full_positional_r_lower': np.float64, 'permutation_full_positional_r_upper': np.float64,
+    'permutation_full_positional_r_pval': np.float64, 'permutation_semi_positional_r_pval': np.float64,
+    'positional_r_lower': np.float32, 'positional_r_upper': np.float32, 'positional_r_pval': np.float64,
+    'count': np.float64, 'smoothed_count': np.float64,
+}
+PER_TASK = ['permutation_semi_positional_r_lower', 'permutation_semi_positional_r_upper', 'integral_r',
+            'permutation_integral_r_lower', 'permutation_integral_r_upper', 'permutation_integral_r_pval']
+_PERM_ONLY = {'permutation_full_positional_r_lower', 'permutation_full_positional_r_upper',
+              'permutation_full_positional_r_pval', 'permutation_semi_positional_r_pval'}
 
-    r0 (T, L) f32; full_os (T, L, 4) f32; full_cnt (T, L); semi_os (T, 4) f32; semi_cnt (T, L);
-    integral (T, 1+P) f64; count (T, L).  Returns {column: (T, L) array} in reference order.
-    """
-    T, L = r0.shape
+
+def alloc_positions(T, L, P):
+    """Output store for T tasks: per-position arrays + per-task scalars (broadcast columns are never
+    materialised as (T, L) arrays)."""
+    pos = {k: np.empty((T, L), dtype=dt) for k, dt in PER_POSITION.items() if P > 0 or k not in _PERM_ONLY}
+    task = {k: np.empty(T, dtype=np.float32 if k == 'integral_r' else np.float64) for k in PER_TASK} if P > 0 else {}
+    return dict(pos=pos, task=task, T=T, L=L, P=P)
+
+
+def positions_view(store, center=None, permutation_mode='semi'):
+    """{column: (T, L) array or zero-copy broadcast view} in the reference's column order (core.py:286-374,
+    406-411, 617-618)."""
+    T, L, P = store['T'], store['L'], store['P']
     if center is None:
         center = L // 2
-    cols = {}
-    cols['positional_r'] = r0.astype(np.float32)
+    cols = dict(store['pos'])
     cols['position'] = np.broadcast_to(np.arange(L) - center, (T, L))
+    if P > 0:
+        for k in PER_TASK:
+            cols[k] = np.broadcast_to(store['task'][k][:, None], (T, L))
+        for suf in ('positional_r_lower', 'positional_r_upper', 'positional_r_pval'):
+            cols[f'permutation_{suf}'] = cols[f'permutation_{permutation_mode}_{suf}']
+    order = POSITIONS_COLUMNS if P > 0 else POSITIONS_COLUMNS_NO_PERM
+    return {k: cols[k] for k in order}
+
+
+def finalize_into(store, t0, r0, full_os, full_cnt, semi_os, semi_cnt, integral, count, n_seq, margin,
+                  confidence_interval_pct=95):
+    """Finalise one group of tasks (rows t0 .. t0+T of the store) from the GPU's order statistics / counts.
+
+    r0 (T, L) f32; full_os (T, L, 4) f32; full_cnt (T, L); semi_os (T, 4) f32; semi_cnt (T, L);
+    integral (T, 1+P) f64; count (T, L).  The inputs may be pinned staging buffers: everything is copied out.
+    """
+    T, L = r0.shape
+    P = store['P']
+    sl = slice(t0, t0 + T)
+    pos, task = store['pos'], store['task']
+    pos['positional_r'][sl] = r0
     if P > 0:
         q = percentile_q(confidence_interval_pct)
         (_, g_lo), (_, g_hi) = virtual_index(P, q[0]), virtual_index(P, q[1])
-        cols['permutation_full_positional_r_lower'] = lerp_f32(full_os[..., 0], full_os[..., 1], g_lo)
-        cols['permutation_full_positional_r_upper'] = lerp_f32(full_os[..., 2], full_os[..., 3], g_hi)
-        cols['permutation_full_positional_r_pval'] = full_cnt.astype(np.float64) / float(P)
+        pos['permutation_full_positional_r_lower'][sl] = lerp_f32(full_os[..., 0], full_os[..., 1], g_lo)
+        pos['permutation_full_positional_r_upper'][sl] = lerp_f32(full_os[..., 2], full_os[..., 3], g_hi)
+        np.divide(full_cnt, float(P), out=pos['permutation_full_positional_r_pval'][sl])
         (_, gs_lo), (_, gs_hi) = virtual_index(L * P, q[0]), virtual_index(L * P, q[1])
-        s_lo = lerp_f32(semi_os[:, 0], semi_os[:, 1], gs_lo)
-        s_hi = lerp_f32(semi_os[:, 2], semi_os[:, 3], gs_hi)
-        cols['permutation_semi_positional_r_lower'] = np.broadcast_to(s_lo[:, None], (T, L))
-        cols['permutation_semi_positional_r_upper'] = np.broadcast_to(s_hi[:, None], (T, L))
-        cols['permutation_semi_positional_r_pval'] = semi_cnt.astype(np.float64) / float(L * P)
-        for suf in ('positional_r_lower', 'positional_r_upper', 'positional_r_pval'):
-            cols[f'permutation_{suf}'] = cols[f'permutation_{permutation_mode}_{suf}']
+        task['permutation_semi_positional_r_lower'][sl] = lerp_f32(semi_os[:, 0], semi_os[:, 1], gs_lo)
+        task['permutation_semi_positional_r_upper'][sl] = lerp_f32(semi_os[:, 2], semi_os[:, 3], gs_hi)
+        np.divide(semi_cnt, float(L * P), out=pos['permutation_semi_positional_r_pval'][sl])
         # np.trapz on the float32 r array yields float32 (core.py:352); percentiles over the P permuted integrals
         integ32 = integral.astype(np.float32)
         ipct = np.percentile(integ32[:, 1:], q, axis=-1)
-        ipval = np.mean((integ32[:, 1:] >= integ32[:, 0:1]).astype(float), axis=-1)
-        cols['integral_r'] = np.broadcast_to(integ32[:, 0:1], (T, L))
-        cols['permutation_integral_r_lower'] = np.broadcast_to(ipct[0][:, None], (T, L))
-        cols['permutation_integral_r_upper'] = np.broadcast_to(ipct[1][:, None], (T, L))
-        cols['permutation_integral_r_pval'] = np.broadcast_to(ipval[:, None], (T, L))
-    lo, up, pv = parametric_ci(cols['positional_r'], n_seq, confidence_interval_pct)
-    cols['positional_r_lower'] = lo
-    cols['positional_r_upper'] = up
-    cols['positional_r_pval'] = pv
-    cnt = count.astype(np.float64)
-    cols['count'] = cnt
-    cols['smoothed_count'] = smooth_counts(cnt, 1 + 2 * margin) if margin > 0 else cnt
-    order = POSITIONS_COLUMNS if P > 0 else POSITIONS_COLUMNS_NO_PERM
-    return {k: cols[k] for k in order}
+        task['integral_r'][sl] = integ32[:, 0]
+        task['permutation_integral_r_lower'][sl] = ipct[0]
+        task['permutation_integral_r_upper'][sl] = ipct[1]
+        task['permutation_integral_r_pval'][sl] = np.mean((integ32[:, 1:] >= integ32[:, 0:1]).astype(float), axis=-1)
+    lo, up, pv = parametric_ci(pos['positional_r'][sl], n_seq, confidence_interval_pct)
+    pos['positional_r_lower'][sl] = lo
+    pos['positional_r_upper'][sl] = up
+    pos['positional_r_pval'][sl] = pv
+    pos['count'][sl] = count
+    pos['smoothed_count'][sl] = smooth_counts(pos['count'][sl], 1 + 2 * margin) if margin > 0 else count
+
+
+def finalize_positions(r0, full_os, full_cnt, semi_os, semi_cnt, integral, count, n_seq, P, margin,
+                       confidence_interval_pct=95, center=None, permutation_mode='semi'):
+    """One-shot form: {column: (T, L) array} in reference order for T tasks (see finalize_into)."""
+    T, L = r0.shape
+    store = alloc_positions(T, L, P)
+    finalize_into(store, 0, r0, full_os, full_cnt, semi_os, semi_cnt, integral, count, n_seq, margin,
+                  confidence_interval_pct)
+    return positions_view(store, center, permutation_mode)

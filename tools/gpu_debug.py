@@ -40,7 +40,8 @@ def main():
     # ---- scan
     tables = motif_layers.scan_tables(tasks)
     T = len(tasks)
-    out = eng._collect_group(eng._launch_group(tables, margin, True, True, None, 95, 0), margin, 95, None)
+    batch_dbg = eng.profile(tasks, margin=margin, tables=tables, return_hits=True, return_r=True)
+    out = dict(hits=batch_dbg.hits, r=batch_dbg.r, positions=batch_dbg.positions, density=batch_dbg.density)
     torch.cuda.synchronize()
     hits = out['hits']
     m_rows = T * L
