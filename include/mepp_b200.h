@@ -20,8 +20,9 @@
  *            [3i, 3i+3) of the stream, word w of sequence n is sym_T[w][n] (transposed so that
  *            lanes = sequences read coalesced)
  *   X planes the match matrix as GEMM operand A, fp16 hi/lo split, tiled:
- *            [m_tile][k_block]{[plane 2][kc 4][row 128][8 seq] halves, 16-byte trailer}, row = task*L +
- *            position; trailer word 0 bit h = "sequences [16h,16h+16) of the k-block hold a non-zero"
+ *            [m_tile][k_block][plane 2][kc 4][row 128][8 seq] halves, row = task*L + position, followed
+ *            by a bit array uint32 [m_tile][FW]: bit (2*k_block + h) = "sequences [16h, 16h+16) of the
+ *            k-block hold a non-zero value in this m-tile" (all-zero blocks are skipped by the GEMM)
  *   Y planes the (1+P) score columns as GEMM operand B, same tiling with BN columns:
  *            [n_tile][k_block][plane 2][kc 4][col BN][8 seq] halves
  */

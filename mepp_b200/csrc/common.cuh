@@ -29,10 +29,14 @@ int fail(const std::string& msg);
 constexpr int kBlockM = 128;          // rows (task*L + position) per tile
 constexpr int kBlockK = 32;           // sequences per k-block
 constexpr int kChunks = kBlockK / 8;  // 16-byte chunks (8 halves) per k-block
-constexpr int kATileData = 2 * kChunks * kBlockM * 16;   // 16384: hi+lo planes
-// Each A tile carries a 16-byte trailer: word 0 bit h is set by the scan kernel when the tile holds a
-// non-zero value among sequences [16h, 16h+16) of its k-block, so the GEMM skips all-zero K=16 steps.
-constexpr int kATileBytes = kATileData + 16;
+constexpr int kATileBytes = 2 * kChunks * kBlockM * 16;  // 16384: hi+lo planes
+// Behind the tiles the A operand carries a bit array: per m-tile FW words, bit (2*k_block + h) is set
+// by the scan kernel when the tile holds a non-zero value among sequences [16h, 16h+16) of the k-block;
+// the GEMM neither loads nor multiplies all-zero blocks.
+__host__ __device__ inline int64_t flag_words(int64_t KB) { return ((2 * KB + 31) / 32 + 3) / 4 * 4; }
+__host__ __device__ inline int64_t a_flags_offset(int64_t n_tiles_m, int64_t KB) {
+  return n_tiles_m * KB * (int64_t)kATileBytes;
+}
 
 __host__ __device__ inline int64_t a_tile_offset(int64_t m_tile, int64_t k_block, int64_t KB) {
   return (m_tile * KB + k_block) * (int64_t)kATileBytes;

@@ -39,9 +39,18 @@ constexpr int kAccCols = 256;  // TMEM columns per accumulator buffer
 
 struct GemmArgs {
   const uint8_t* A; const uint8_t* B; float* S;
+  const uint32_t* flags;    // non-zero bit array [n_tiles_m][FW] behind the A tiles (common.cuh)
   int64_t m_rows, ldS, KB;
   int BN, n_tiles_m, n_tiles_n, variant;
+  int FW, use_flags;        // use_flags = 0: treat every block as non-zero
 };
+
+// Does k-block kb of the current item have to be loaded and multiplied?  Yes if one of its two K=16
+// halves is flagged non-zero -- or if it is the last k-block of an accumulation chunk in which
+// nothing is flagged (every chunk writes its accumulator at least once, so the epilogue needs no flags).
+__device__ __forceinline__ uint32_t kb_bits(const uint32_t* f, int64_t kb) {
+  return (f[(2 * kb) >> 5] >> ((2 * kb) & 31)) & 3u;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -128,11 +137,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const Gem
   uint64_t* empty_bar = full_bar + kStages;                         // [kStages]
   uint64_t* tfull_bar = empty_bar + kStages;                        // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* ffull_bar = tempty_bar + 2;                             // [2] item's flag words staged in smem
+  uint64_t* fempty_bar = ffull_bar + 2;                             // [2] MMA issuer done with them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fempty_bar + 2);
+  uint32_t* s_flags = tmem_slot + 4;                                // [2][FW]
+  const int FW = g.FW;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&ffull_bar[s]), 1); mbar_init(smem_u32(&fempty_bar[s]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -151,22 +165,39 @@ __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const Gem
 
   if (warp == 0) {
     // ------------------------------------------------------------ producer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int64_t mt = item / g.n_tiles_n, nt = item % g.n_tiles_n;
+    // all lanes stage the item's flag words in shared memory, lane 0 then issues the bulk copies of the
+    // k-blocks that are not all-zero
+    uint32_t stage = 0, phase = 0, fbuf = 0, fphase = 0;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int64_t mt = item / g.n_tiles_n, nt = item % g.n_tiles_n;
+      const uint32_t* f = s_flags + fbuf * FW;
+      if (g.use_flags) {
+        if (lane == 0) mbar_wait(smem_u32(&fempty_bar[fbuf]), fphase ^ 1u);
+        __syncwarp();
+        for (int w = lane; w < FW; w += 32) s_flags[fbuf * FW + w] = g.flags[mt * FW + w];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&ffull_bar[fbuf]));
+      }
+      if (lane == 0) {
         const uint8_t* a_src = g.A + a_tile_offset(mt, 0, KB);
         const uint8_t* b_src = g.B + b_tile_offset(nt, 0, KB, BN);
-        for (int64_t kb = 0; kb < KB; ++kb) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, stage_bytes);
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          bulk_g2s(sa, a_src + kb * (int64_t)a_bytes, a_bytes, fb);
-          bulk_g2s(sa + a_bytes, b_src + kb * (int64_t)b_bytes, b_bytes, fb);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        for (int64_t kb0 = 0; kb0 < KB; kb0 += kChunkKB) {
+          const int64_t kb1 = kb0 + kChunkKB < KB ? kb0 + kChunkKB : KB;
+          const bool chunk_nz = !g.use_flags || (f[(2 * kb0) >> 5] | f[((2 * kb0) >> 5) + 1]) != 0u;
+          for (int64_t kb = kb0; kb < kb1; ++kb) {
+            if (g.use_flags && kb_bits(f, kb) == 0u && !(kb == kb1 - 1 && !chunk_nz)) continue;
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_expect_tx(fb, stage_bytes);
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            bulk_g2s(sa, a_src + kb * (int64_t)a_bytes, a_bytes, fb);
+            bulk_g2s(sa + a_bytes, b_src + kb * (int64_t)b_bytes, b_bytes, fb);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
         }
       }
+      __syncwarp();
+      if (++fbuf == 2) { fbuf = 0; fphase ^= 1u; }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
@@ -178,24 +209,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const Gem
       const uint32_t b_lbo = g.variant == 1 ? 128u : (uint32_t)BN * 16u;
       const uint32_t b_sbo = g.variant == 1 ? (uint32_t)BN * 16u : 128u;
       const uint32_t a_plane = kChunks * kBlockM * 16, b_plane = (uint32_t)kChunks * BN * 16;
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, fbuf = 0, fphase = 0;
       unsigned long long issued = 0, total = 0;
       for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         total += (unsigned long long)KB * (kBlockK / 16);
+        const uint32_t* f = s_flags + fbuf * FW;
+        if (g.use_flags) mbar_wait(smem_u32(&ffull_bar[fbuf]), fphase);
         for (int64_t kb0 = 0; kb0 < KB; kb0 += kChunkKB) {
           const int64_t kb1 = kb0 + kChunkKB < KB ? kb0 + kChunkKB : KB;
+          const bool chunk_nz = !g.use_flags || (f[(2 * kb0) >> 5] | f[((2 * kb0) >> 5) + 1]) != 0u;
           mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kAccCols;
           bool acc_valid = false;                      // has this chunk's accumulator been written yet?
           for (int64_t kb = kb0; kb < kb1; ++kb) {
+            // bit s set <=> K=16 step s of this k-block holds a non-zero x (scan.cu); all-zero blocks were not loaded
+            const uint32_t nzmask = g.use_flags ? kb_bits(f, kb) : 3u;
+            if (nzmask == 0u && !(kb == kb1 - 1 && !chunk_nz)) continue;
             mbar_wait(smem_u32(&full_bar[stage]), phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t sb = sa + a_bytes;
-            // trailer of the A tile: bit s set <=> K=16 step s holds a non-zero x (scan.cu); zero steps are skipped
-            uint32_t nzmask = *reinterpret_cast<volatile uint32_t*>(smem + (size_t)stage * stage_bytes + kATileData);
-            if (g.variant == 2) nzmask = 3u;           // MEPP_GEMM_DESC_VARIANT=2: never skip (A/B testing)
 #pragma unroll
             for (int s = 0; s < kBlockK / 16; ++s) {
               const bool last = (kb == kb1 - 1) && (s == kBlockK / 16 - 1);
@@ -217,6 +251,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const Gem
           tc_commit(smem_u32(&tfull_bar[acc]));       // chunk accumulator complete
           if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (g.use_flags) mbar_arrive(smem_u32(&fempty_bar[fbuf]));
+        if (++fbuf == 2) { fbuf = 0; fphase ^= 1u; }
       }
       atomicAdd(&g_mma_steps[0], issued);
       atomicAdd(&g_mma_steps[1], total);
@@ -556,7 +592,10 @@ int mepp_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float*
   g.n_tiles_m = (int)((m_rows + kBlockM - 1) / kBlockM);
   const char* var = getenv("MEPP_GEMM_DESC_VARIANT");
   g.variant = var ? atoi(var) : 0;
-  size_t smem = (size_t)kStages * (kATileBytes + b_tile_bytes(g.BN)) + 256;   // A tiles include their 16-byte trailer
+  g.FW = (int)flag_words(g.KB);
+  g.flags = reinterpret_cast<const uint32_t*>(g.A + a_flags_offset(g.n_tiles_m, g.KB));
+  g.use_flags = (g.FW <= 2048 && g.variant != 2) ? 1 : 0;   // MEPP_GEMM_DESC_VARIANT=2: never skip (A/B testing)
+  size_t smem = (size_t)kStages * (kATileBytes + b_tile_bytes(g.BN)) + 256 + (g.use_flags ? 2 * 4 * (size_t)g.FW : 0);
   MEPP_CUDA_CHECK(cudaFuncSetAttribute(profile_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   MEPP_CUDA_CHECK(cudaGetDevice(&dev));

@@ -99,7 +99,8 @@ int64_t mepp_pad32(int64_t n) { return (n + 31) / 32 * 32; }
 
 int64_t mepp_x_planes_bytes(int64_t m_rows, int64_t n_pad) {
   int64_t mt = (m_rows + mepp::kBlockM - 1) / mepp::kBlockM;
-  return mt * (n_pad / mepp::kBlockK) * (int64_t)mepp::kATileBytes;
+  int64_t KB = n_pad / mepp::kBlockK;
+  return mepp::a_flags_offset(mt, KB) + mt * mepp::flag_words(KB) * 4;
 }
 
 int mepp_choose_bn(int C, int* n_tiles_n) {

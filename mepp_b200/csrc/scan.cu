@@ -55,6 +55,8 @@ struct TaskCtx {
   float bias;
   int64_t tile_stride;   // bytes between consecutive m-tiles of the A operand
   uint8_t* x_base;       // A operand + this k-block's offset inside an m-tile row
+  unsigned int* flags;   // non-zero bit array [m_tile][FW]
+  int FW;
 };
 
 // Exact canonical-order score of the window starting at base i of one sequence (`stream` = that
@@ -193,8 +195,10 @@ __device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, in
       uint8_t* dst = tile + ((kc * kBlockM + (r & 127)) << 4);
       *reinterpret_cast<uint4*>(dst) = vh;
       *reinterpret_cast<uint4*>(dst + kChunks * kBlockM * 16) = vl;
-      if ((vh.x | vh.y | vh.z | vh.w | vl.x | vl.y | vl.z | vl.w) != 0u)   // rare: mark the K=16 half as non-zero
-        atomicOr(reinterpret_cast<unsigned int*>(tile + kATileData), 1u << (kc >> 1));
+      if ((vh.x | vh.y | vh.z | vh.w | vl.x | vl.y | vl.z | vl.w) != 0u) {  // rare: mark the K=16 block as non-zero
+        const int bit = 2 * c.kb + (kc >> 1);
+        atomicOr(c.flags + (int64_t)(r >> 7) * c.FW + (bit >> 5), 1u << (bit & 31));
+      }
     }
   }
 }
@@ -249,6 +253,9 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
     w.bias = a.bias[t];
     w.tile_stride = a.KB * (int64_t)kATileBytes;
     w.x_base = a.x_planes + (int64_t)kb * kATileBytes;
+    w.FW = (int)flag_words(a.KB);
+    w.flags = reinterpret_cast<unsigned int*>(
+        a.x_planes + a_flags_offset(((int64_t)a.T * L + kBlockM - 1) / kBlockM, a.KB));
     *s_ctx = w;
   }
   __syncwarp();
@@ -386,12 +393,6 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const __grid_cons
   scan_task(a, t, kb, s_sym, s_lut, s_qtab, s_buf, s_queue, s_z, &s_ctxs[warp], lane);
 }
 
-// Clears the 16-byte "non-zero" trailer of every A tile (one thread per tile).
-__global__ void zero_trailers_kernel(uint8_t* __restrict__ x_planes, int64_t n_tiles) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_tiles) *reinterpret_cast<uint4*>(x_planes + i * kATileBytes + kATileData) = make_uint4(0u, 0u, 0u, 0u);
-}
-
 }  // namespace mepp
 
 extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
@@ -431,10 +432,10 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
   MEPP_CUDA_CHECK(cudaMemsetAsync(density_dev, 0, sizeof(int32_t) * (size_t)T * a.n_pad, st));
   if (hit_count_dev) MEPP_CUDA_CHECK(cudaMemsetAsync(hit_count_dev, 0, sizeof(unsigned long long), st));
   {
-    // reset the per-tile "non-zero" trailers of every A tile this call writes
+    // reset the non-zero bit array behind the tiles
     const int64_t n_tiles_m = ((int64_t)T * L + kBlockM - 1) / kBlockM;
-    const int64_t n_tiles = n_tiles_m * a.KB;
-    zero_trailers_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>(a.x_planes, n_tiles);
+    MEPP_CUDA_CHECK(cudaMemsetAsync(a.x_planes + a_flags_offset(n_tiles_m, a.KB), 0,
+                                    (size_t)(n_tiles_m * flag_words(a.KB) * 4), st));
   }
   dim3 grid((unsigned)a.KB, (unsigned)((T + kScanWarps - 1) / kScanWarps));
   MEPP_REQUIRE(grid.y <= 65535, "scan: too many tasks in one call");

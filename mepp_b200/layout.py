@@ -4,18 +4,19 @@ import numpy as np
 
 
 def decode_x_planes(raw_u8, m_rows, n_pad, with_flags=False):
-    """[m_tile][k_block]{[plane 2][kc 4][row 128][8] fp16, 16-byte trailer} -> (hi, lo) float32 arrays
-    (m_rows, n_pad); with_flags also returns the per-(m_tile, k_block) non-zero masks (trailer word 0)."""
+    """[m_tile][k_block][plane 2][kc 4][row 128][8] fp16 (+ the non-zero bit array behind the tiles) ->
+    (hi, lo) float32 arrays (m_rows, n_pad); with_flags also returns the bit array as bool (MT, KB, 2)."""
     MT = (m_rows + 127) // 128
     KB = n_pad // 32
-    tile = 16384 + 16
-    raw = np.ascontiguousarray(raw_u8).view(np.uint8)[:MT * KB * tile].reshape(MT * KB, tile)
-    a = np.ascontiguousarray(raw[:, :16384]).view(np.float16).reshape(MT, KB, 2, 4, 128, 8).astype(np.float32)
+    raw = np.ascontiguousarray(raw_u8).view(np.uint8)
+    a = raw[:MT * KB * 16384].view(np.float16).reshape(MT, KB, 2, 4, 128, 8).astype(np.float32)
     # -> (plane, MT, row, KB, kc, e)
     a = a.transpose(2, 0, 4, 1, 3, 5).reshape(2, MT * 128, KB * 32)
     if with_flags:
-        flags = np.ascontiguousarray(raw[:, 16384:16388]).view(np.uint32).reshape(MT, KB)
-        return a[0][:m_rows], a[1][:m_rows], flags
+        FW = ((2 * KB + 31) // 32 + 3) // 4 * 4
+        words = raw[MT * KB * 16384:MT * KB * 16384 + MT * FW * 4].view(np.uint32).reshape(MT, FW)
+        bits = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(MT, FW * 32)
+        return a[0][:m_rows], a[1][:m_rows], bits[:, :2 * KB].reshape(MT, KB, 2).astype(bool)
     return a[0][:m_rows], a[1][:m_rows]
 
 

@@ -189,12 +189,13 @@ def test_layout_decoders_roundtrip():
     m_rows, n_pad = 200, 64
     MT, KB = 2, 2
     data = rng.integers(0, 1000, size=(MT, KB, 2, 4, 128, 8)).astype(np.float16)
-    raw = np.zeros((MT * KB, 16384 + 16), dtype=np.uint8)
-    raw[:, :16384] = data.reshape(MT * KB, -1).view(np.uint8)
-    raw[:, 16384] = [1, 2, 3, 0]
-    hi, lo, flags = layout.decode_x_planes(raw.ravel(), m_rows, n_pad, with_flags=True)
+    flags = np.zeros((MT, 4), dtype=np.uint32)
+    flags[0, 0] = 0b0110          # tile 0: k-block 0 half 1, k-block 1 half 0
+    flags[1, 0] = 0b1000          # tile 1: k-block 1 half 1
+    raw = np.concatenate([data.ravel().view(np.uint8), flags.ravel().view(np.uint8)])
+    hi, lo, nz = layout.decode_x_planes(raw, m_rows, n_pad, with_flags=True)
     assert hi[130, 41] == np.float32(data[1, 1, 0, 1, 2, 1]) and lo[5, 7] == np.float32(data[0, 0, 1, 0, 5, 7])
-    assert flags.tolist() == [[1, 2], [3, 0]]
+    assert nz.tolist() == [[[False, True], [True, False]], [[False, False], [False, True]]]
 
 
 def test_cli_flags_match_the_reference():
