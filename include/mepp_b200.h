@@ -127,13 +127,21 @@ int mepp_profile_gemm_check(const void* x_planes_dev, const void* y_planes_dev, 
 
 /* ------------------------------------------------------------------ correlation epilogue
  * core.py:182-267 (Pearson / partial correlation) + np.nan_to_num (core.py:602).
- * r_dev: float [m_rows][C].  use_z: 1 = partial correlation controlling z. */
+ * r_dev: float [m_rows][ldr] (ldr >= C).  use_z: 1 = partial correlation controlling z. */
 int mepp_correlation(const float* S_dev, int64_t ldS, const double* rowstats_dev,
                      const double* col_syz_dev, const double* ysum_dev, const double* zsum_host2,
-                     int64_t N, int64_t m_rows, int C, int use_z, float* r_dev, void* stream);
+                     int64_t N, int64_t m_rows, int C, int use_z, float* r_dev, int64_t ldr, void* stream);
+/* Fused form (what the engine runs): per-dataset column constants once, then the GEMM writes r directly
+ * (the same formulas, evaluated in float64 by the GEMM's epilogue warps; S never reaches HBM).
+ * colconst_dev: double [8 + 2*C].  r_dev: float [m_rows][ldr], ldr = n_tiles_n*BN. */
+int mepp_col_constants(const double* col_syz_dev, const double* ysum_dev, const double* zsum_host2,
+                       int64_t N, int C, int use_z, double* colconst_dev, void* stream);
+int mepp_profile_corr_gemm(const void* x_planes_dev, const void* y_planes_dev, const double* rowstats_dev,
+                           const double* colconst_dev, float* r_dev, int64_t m_rows, int C, int64_t n_pad,
+                           void* stream);
 
 /* ------------------------------------------------------------------ K3: permutation statistics
- * core.py:269-376 for T tasks of L positions and C = 1+P columns.
+ * core.py:269-376 for T tasks of L positions and C = 1+P columns (r_dev: float [T*L][ldr]).
  *   k_lo, k_hi: floor of the numpy "linear" virtual index for the two percentiles over P values
  *   ks_lo, ks_hi: same over L*P values (the pooled "semi" null)
  * Outputs (per task):
@@ -144,7 +152,7 @@ int mepp_correlation(const float* S_dev, int64_t ldS, const double* rowstats_dev
  *   integral  double [T][C]  : trapezoid over positions of |r[:,c]|
  * work_dev: scratch of mepp_perm_stats_work_bytes(T, L, C) bytes. */
 int64_t mepp_perm_stats_work_bytes(int T, int L, int C);
-int mepp_perm_stats(const float* r_dev, int T, int L, int C,
+int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C,
                     int k_lo, int k_hi, int64_t ks_lo, int64_t ks_hi,
                     float* full_os_dev, int32_t* full_cnt_dev, float* semi_os_dev,
                     long long* semi_cnt_dev, double* integral_dev, void* work_dev, void* stream);

@@ -45,9 +45,11 @@ SIGNATURES = {
     "mepp_profile_gemm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp]),
     "mepp_gemm_counters": (_i32, [C.POINTER(C.c_ulonglong), _i32]),
     "mepp_profile_gemm_check": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp]),
-    "mepp_correlation": (_i32, [_vp, _i64, _vp, _vp, _vp, _pd, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "mepp_correlation": (_i32, [_vp, _i64, _vp, _vp, _vp, _pd, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),
+    "mepp_col_constants": (_i32, [_vp, _vp, _pd, _i64, _i32, _i32, _vp, _vp]),
+    "mepp_profile_corr_gemm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _vp]),
     "mepp_perm_stats_work_bytes": (_i64, [_i32, _i32, _i32]),
-    "mepp_perm_stats": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64,
+    "mepp_perm_stats": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i64, _i64,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -29,6 +29,7 @@
 // between 8-row groups), produced directly in that layout by scan.cu / pack.cu.
 #include "common.cuh"
 #include <cstdlib>
+#include <cfloat>
 
 namespace mepp {
 
@@ -43,6 +44,9 @@ struct GemmArgs {
   int64_t m_rows, ldS, KB;
   int BN, n_tiles_m, n_tiles_n, variant;
   int FW, use_flags;        // use_flags = 0: treat every block as non-zero
+  // fused correlation epilogue (stats.cu: col_constants_kernel): when colconst != nullptr the epilogue writes
+  // r = nan_to_num(partial correlation) into S (as float [m_rows][ldS]) instead of the raw sums
+  const double* rowstats; const double* colconst; int C;
 };
 
 // Does k-block kb of the current item have to be loaded and multiplied?  Yes if one of its two K=16
@@ -287,10 +291,48 @@ __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const Gem
       const int64_t row = mt * kBlockM + q * 32 + lane;
       if (row < g.m_rows) {
         float* dst = g.S + row * g.ldS + nt * (int64_t)BN + h * 128;
+        if (g.colconst == nullptr) {
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 4) {
-          if (h * 128 + c0 < BN)
-            *reinterpret_cast<float4*>(dst + c0) = make_float4(sum[c0], sum[c0 + 1], sum[c0 + 2], sum[c0 + 3]);
+          for (int c0 = 0; c0 < 128; c0 += 4) {
+            if (h * 128 + c0 < BN)
+              *reinterpret_cast<float4*>(dst + c0) = make_float4(sum[c0], sum[c0 + 1], sum[c0 + 2], sum[c0 + 3]);
+          }
+        } else {
+          // fused correlation epilogue: core.py:182-193,255-265 in float64 + np.nan_to_num (core.py:602)
+          const double* cc = g.colconst;
+          const double n = cc[0], sy = cc[1], ay = cc[2], sz = cc[3], az = cc[4];
+          const bool use_z = cc[5] != 0.0;
+          const double sx = g.rowstats[row * 3 + 0], sxx = g.rowstats[row * 3 + 1], sxz = g.rowstats[row * 3 + 2];
+          const double ax = n * sxx - sx * sx;
+          const double inv_xy = 1.0 / sqrt(ax * ay);
+          const double sxsy = sx * sy;
+          double r_xz = 0.0, row_den = 1.0;
+          if (use_z) {
+            r_xz = (n * sxz - sx * sz) / sqrt(ax * az);
+            row_den = 1.0 / sqrt(1.0 - r_xz * r_xz);
+          }
+          const int col0 = (int)(nt * (int64_t)BN) + h * 128;
+#pragma unroll
+          for (int c0 = 0; c0 < 128; c0 += 4) {
+            if (h * 128 + c0 < BN) {
+              float o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int c = col0 + c0 + j;
+                float out = 0.0f;
+                if (c < g.C) {
+                  const double sxy = (double)sum[c0 + j] * (1.0 / (double)MEPP_X_SCALE);
+                  double r = (n * sxy - sxsy) * inv_xy;
+                  if (use_z) r = (r - r_xz * __ldg(cc + 8 + 2 * c)) * row_den * __ldg(cc + 9 + 2 * c);
+                  out = (float)r;
+                  if (out != out) out = 0.0f;
+                  else if (isinf(out)) out = out > 0 ? FLT_MAX : -FLT_MAX;
+                }
+                o[j] = out;
+              }
+              *reinterpret_cast<float4*>(dst + c0) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
         }
       }
     }
@@ -573,23 +615,25 @@ __global__ void gemm_check_kernel(const uint8_t* __restrict__ A, const uint8_t* 
 
 }  // namespace mepp
 
-extern "C" {
 
-int mepp_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float* S_dev, int64_t m_rows,
-                      int C, int64_t n_pad, void* stream) {
+
+static int launch_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float* out_dev, int64_t m_rows,
+                               int C, int64_t n_pad, const double* rowstats_dev, const double* colconst_dev,
+                               void* stream) {
   using namespace mepp;
-  MEPP_REQUIRE(x_planes_dev && y_planes_dev && S_dev, "profile_gemm: null pointer");
+  MEPP_REQUIRE(x_planes_dev && y_planes_dev && out_dev, "profile_gemm: null pointer");
   MEPP_REQUIRE(m_rows > 0 && C > 0 && n_pad > 0 && n_pad % kBlockK == 0, "profile_gemm: bad shape");
   MEPP_REQUIRE(mepp_device_ok(), "profile_gemm: no sm_100 CUDA device (no CPU fallback)");
   GemmArgs g;
   g.A = reinterpret_cast<const uint8_t*>(x_planes_dev);
   g.B = reinterpret_cast<const uint8_t*>(y_planes_dev);
-  g.S = S_dev;
+  g.S = out_dev;
   g.m_rows = m_rows;
   g.KB = n_pad / kBlockK;
   g.BN = mepp_choose_bn(C, &g.n_tiles_n);
   g.ldS = (int64_t)g.n_tiles_n * g.BN;
   g.n_tiles_m = (int)((m_rows + kBlockM - 1) / kBlockM);
+  g.rowstats = rowstats_dev; g.colconst = colconst_dev; g.C = C;
   const char* var = getenv("MEPP_GEMM_DESC_VARIANT");
   g.variant = var ? atoi(var) : 0;
   g.FW = (int)flag_words(g.KB);
@@ -603,7 +647,7 @@ int mepp_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float*
   int64_t n_items = (int64_t)g.n_tiles_m * g.n_tiles_n;
   unsigned grid = (unsigned)(n_items < sms ? n_items : sms);
   const char* two = getenv("MEPP_GEMM_2CTA");
-  if (two && atoi(two) != 0 && g.BN % 32 == 0) {
+  if (two && atoi(two) != 0 && g.BN % 32 == 0 && colconst_dev == nullptr) {
     const char* stg = getenv("MEPP_GEMM_STAGES");
     int n_stages = stg ? atoi(stg) : kStages2;
     if (n_stages < 2) n_stages = 2;
@@ -621,6 +665,20 @@ int mepp_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float*
   profile_gemm_kernel<<<grid, kGemmThreads, smem, as_stream(stream)>>>(g);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+extern "C" {
+
+int mepp_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float* S_dev, int64_t m_rows,
+                      int C, int64_t n_pad, void* stream) {
+  return launch_profile_gemm(x_planes_dev, y_planes_dev, S_dev, m_rows, C, n_pad, nullptr, nullptr, stream);
+}
+
+int mepp_profile_corr_gemm(const void* x_planes_dev, const void* y_planes_dev, const double* rowstats_dev,
+                           const double* colconst_dev, float* r_dev, int64_t m_rows, int C, int64_t n_pad,
+                           void* stream) {
+  if (!rowstats_dev || !colconst_dev) return mepp::fail("mepp_b200: profile_corr_gemm: null pointer");
+  return launch_profile_gemm(x_planes_dev, y_planes_dev, r_dev, m_rows, C, n_pad, rowstats_dev, colconst_dev, stream);
 }
 
 int mepp_gemm_counters(unsigned long long* out2, int reset) {

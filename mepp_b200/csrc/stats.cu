@@ -17,7 +17,7 @@ struct CorrArgs {
   const double* ysum;       // {sum y, sum y^2}
   double sz, szz, n;
   int64_t m_rows; int C; int use_z;
-  float* r;
+  float* r; int64_t ldr;
 };
 
 __device__ __forceinline__ float nan_to_num_f32(double v) {
@@ -46,7 +46,25 @@ __global__ void correlation_kernel(const CorrArgs a) {
     const double r_yz = (n * a.col_syz[c] - sy * a.sz) / sqrt(ay * az);
     r = (r_xy - r_xz * r_yz) / sqrt((1.0 - r_xz * r_xz) * (1.0 - r_yz * r_yz));
   }
-  a.r[row * a.C + c] = nan_to_num_f32(r);
+  a.r[row * a.ldr + c] = nan_to_num_f32(r);
+}
+
+// Per-dataset constants of the correlation epilogue fused into the GEMM (gemm.cu): header
+// {n, sy, ay, sz, az, use_z, -, -} then per column {r_yz[c], 1 / sqrt(1 - r_yz[c]^2)}.
+__global__ void col_constants_kernel(const double* __restrict__ col_syz, const double* __restrict__ ysum,
+                                     double sz, double szz, double n, int C, int use_z, double* __restrict__ cc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const double sy = ysum[0], syy = ysum[1];
+  const double ay = n * syy - sy * sy, az = n * szz - sz * sz;
+  if (c == 0) { cc[0] = n; cc[1] = sy; cc[2] = ay; cc[3] = sz; cc[4] = az; cc[5] = (double)use_z; cc[6] = 0.0; cc[7] = 0.0; }
+  if (c >= C) return;
+  double r_yz = 0.0, cden = 1.0;
+  if (use_z) {
+    r_yz = (n * col_syz[c] - sy * sz) / sqrt(ay * az);
+    cden = 1.0 / sqrt(1.0 - r_yz * r_yz);
+  }
+  cc[8 + 2 * c] = r_yz;
+  cc[9 + 2 * c] = cden;
 }
 
 // ------------------------------------------------------------------ K3 helpers
@@ -79,14 +97,14 @@ __device__ void bitonic_sort_keys(uint32_t* s, int n_pow2) {
 
 // Per (task, position): order statistics of the P permuted r values, the count of
 // |r_p| >= |r_0|, and the sorted row (as keys) for the pooled quantiles.
-__global__ void row_stats_kernel(const float* __restrict__ r, int L, int C, int P_pow2, int k_lo, int k_hi,
+__global__ void row_stats_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, int P_pow2, int k_lo, int k_hi,
                                  float* __restrict__ full_os, int32_t* __restrict__ full_cnt,
                                  uint32_t* __restrict__ sorted_keys) {
   extern __shared__ uint32_t s_keys[];
   __shared__ int s_cnt;
   const int P = C - 1;
   const int64_t row = (int64_t)blockIdx.y * L + blockIdx.x;
-  const float* rr = r + row * C;
+  const float* rr = r + row * ldr;
   const float t0 = fabsf(rr[0]);
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
@@ -150,7 +168,7 @@ __device__ __forceinline__ void bitonic_stage(uint32_t (&key)[Q], const int lane
 // lane, element e = lane + 32 q), bitonic stages with partner distance >= 32 are register-to-register
 // compare-exchanges, smaller distances are warp shuffles; no shared memory, no block barriers.
 template <int Q>
-__global__ void __launch_bounds__(256) row_stats_warp_kernel(const float* __restrict__ r, int64_t n_rows, int C,
+__global__ void __launch_bounds__(256) row_stats_warp_kernel(const float* __restrict__ r, int64_t ldr, int64_t n_rows, int C,
                                                              int k_lo, int k_hi, float* __restrict__ full_os,
                                                              int32_t* __restrict__ full_cnt,
                                                              uint32_t* __restrict__ sorted_keys) {
@@ -159,7 +177,7 @@ __global__ void __launch_bounds__(256) row_stats_warp_kernel(const float* __rest
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int P = C - 1;
-  const float* rr = r + row * C;
+  const float* rr = r + row * ldr;
   const float t0 = fabsf(rr[0]);
   uint32_t key[Q];
   int cnt = 0;
@@ -196,12 +214,12 @@ __global__ void __launch_bounds__(256) row_stats_warp_kernel(const float* __rest
 }
 
 // Per task: sorted thresholds |r[l,0]| (ascending) for the pooled p-values.
-__global__ void thresholds_kernel(const float* __restrict__ r, int L, int C, int L_pow2,
+__global__ void thresholds_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, int L_pow2,
                                   float* __restrict__ ts_sorted) {
   extern __shared__ uint32_t s_keys[];
   const int t = blockIdx.x;
   for (int i = threadIdx.x; i < L_pow2; i += blockDim.x)
-    s_keys[i] = i < L ? f2key(fabsf(r[((int64_t)t * L + i) * C])) : 0xffffffffu;
+    s_keys[i] = i < L ? f2key(fabsf(r[((int64_t)t * L + i) * ldr])) : 0xffffffffu;
   __syncthreads();
   bitonic_sort_keys(s_keys, L_pow2);
   for (int i = threadIdx.x; i < L; i += blockDim.x) ts_sorted[(int64_t)t * L + i] = key2f(s_keys[i]);
@@ -209,7 +227,7 @@ __global__ void thresholds_kernel(const float* __restrict__ r, int L, int C, int
 
 // Histogram of the pooled |r_perm| values against the task's sorted thresholds:
 // hist[idx] counts values with exactly idx thresholds <= |v|.
-__global__ void semi_hist_kernel(const float* __restrict__ r, int L, int C, const float* __restrict__ ts_sorted,
+__global__ void semi_hist_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, const float* __restrict__ ts_sorted,
                                  unsigned long long* __restrict__ hist) {
   extern __shared__ uint32_t s_raw[];
   float* s_ts = reinterpret_cast<float*>(s_raw);        // [L]
@@ -222,7 +240,7 @@ __global__ void semi_hist_kernel(const float* __restrict__ r, int L, int C, cons
   const int l0 = blockIdx.x * rows_per, l1 = min(L, l0 + rows_per);
   const int P = C - 1;
   for (int l = l0; l < l1; ++l) {
-    const float* rr = r + ((int64_t)t * L + l) * C + 1;
+    const float* rr = r + ((int64_t)t * L + l) * ldr + 1;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
       const float a = fabsf(rr[i]);
       int lo = 0, hi = L;  // upper_bound: number of thresholds <= a
@@ -239,7 +257,7 @@ __global__ void semi_hist_kernel(const float* __restrict__ r, int L, int C, cons
 }
 
 // Per task: semi_cnt[l] = #{pooled |v| >= |r[l,0]|} from the histogram (suffix sums).
-__global__ void semi_count_kernel(const float* __restrict__ r, int L, int C, const float* __restrict__ ts_sorted,
+__global__ void semi_count_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, const float* __restrict__ ts_sorted,
                                   unsigned long long* __restrict__ hist, long long* __restrict__ semi_cnt) {
   const int t = blockIdx.x;
   unsigned long long* h = hist + (int64_t)t * (L + 1);
@@ -251,7 +269,7 @@ __global__ void semi_count_kernel(const float* __restrict__ r, int L, int C, con
   __syncthreads();
   const float* ts = ts_sorted + (int64_t)t * L;
   for (int l = threadIdx.x; l < L; l += blockDim.x) {
-    const float a = fabsf(r[((int64_t)t * L + l) * C]);
+    const float a = fabsf(r[((int64_t)t * L + l) * ldr]);
     int lo = 0, hi = L;  // lower_bound: first j with ts[j] >= a  (ts[j] == a)
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -302,15 +320,15 @@ __global__ void semi_select_kernel(const uint32_t* __restrict__ sorted_keys, int
 }
 
 // integral[t][c] = trapezoid over positions of |r[:, c]| (np.trapz, dx = 1).
-__global__ void integral_kernel(const float* __restrict__ r, int L, int C, double* __restrict__ integral) {
+__global__ void integral_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, double* __restrict__ integral) {
   const int t = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float* rr = r + (int64_t)t * L * C + c;
+  const float* rr = r + (int64_t)t * L * ldr + c;
   double acc = 0.0;
   float prev = fabsf(rr[0]);
   for (int l = 1; l < L; ++l) {
-    const float cur = fabsf(rr[(int64_t)l * C]);
+    const float cur = fabsf(rr[(int64_t)l * ldr]);
     acc += 0.5 * ((double)prev + (double)cur);
     prev = cur;
   }
@@ -325,7 +343,7 @@ extern "C" {
 
 int mepp_correlation(const float* S_dev, int64_t ldS, const double* rowstats_dev, const double* col_syz_dev,
                      const double* ysum_dev, const double* zsum_host2, int64_t N, int64_t m_rows, int C,
-                     int use_z, float* r_dev, void* stream) {
+                     int use_z, float* r_dev, int64_t ldr, void* stream) {
   using namespace mepp;
   MEPP_REQUIRE(S_dev && rowstats_dev && ysum_dev && r_dev, "correlation: null pointer");
   MEPP_REQUIRE(!use_z || (col_syz_dev && zsum_host2), "correlation: z statistics missing");
@@ -334,16 +352,29 @@ int mepp_correlation(const float* S_dev, int64_t ldS, const double* rowstats_dev
   CorrArgs a;
   a.S = S_dev; a.ldS = ldS; a.rowstats = rowstats_dev; a.col_syz = col_syz_dev; a.ysum = ysum_dev;
   a.sz = use_z ? zsum_host2[0] : 0.0; a.szz = use_z ? zsum_host2[1] : 0.0; a.n = (double)N;
-  a.m_rows = m_rows; a.C = C; a.use_z = use_z; a.r = r_dev;
+  a.m_rows = m_rows; a.C = C; a.use_z = use_z; a.r = r_dev; a.ldr = ldr;
+  MEPP_REQUIRE(ldr >= C, "correlation: ldr must be >= C");
   // rows on grid.y (<= 65535): split large row counts over several launches
   const int64_t max_rows = 65535;
   for (int64_t r0 = 0; r0 < m_rows; r0 += max_rows) {
     CorrArgs b = a;
     const int64_t nr = m_rows - r0 < max_rows ? m_rows - r0 : max_rows;
-    b.S = a.S + r0 * ldS; b.rowstats = a.rowstats + r0 * 3; b.r = a.r + r0 * C; b.m_rows = nr;
+    b.S = a.S + r0 * ldS; b.rowstats = a.rowstats + r0 * 3; b.r = a.r + r0 * ldr; b.m_rows = nr;
     dim3 grid((unsigned)((C + 255) / 256), (unsigned)nr);
     correlation_kernel<<<grid, 256, 0, as_stream(stream)>>>(b);
   }
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mepp_col_constants(const double* col_syz_dev, const double* ysum_dev, const double* zsum_host2, int64_t N, int C,
+                       int use_z, double* colconst_dev, void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(ysum_dev && colconst_dev && C > 0, "col_constants: bad arguments");
+  MEPP_REQUIRE(!use_z || (col_syz_dev && zsum_host2), "col_constants: z statistics missing");
+  MEPP_REQUIRE(mepp_device_ok(), "col_constants: no sm_100 CUDA device (no CPU fallback)");
+  col_constants_kernel<<<(unsigned)((C + 255) / 256), 256, 0, as_stream(stream)>>>(
+      col_syz_dev, ysum_dev, use_z ? zsum_host2[0] : 0.0, use_z ? zsum_host2[1] : 0.0, (double)N, C, use_z, colconst_dev);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -356,7 +387,7 @@ int64_t mepp_perm_stats_work_bytes(int T, int L, int C) {
   return ((keys + 255) / 256 + (ts + 255) / 256 + (hist + 255) / 256) * 256;
 }
 
-int mepp_perm_stats(const float* r_dev, int T, int L, int C, int k_lo, int k_hi, int64_t ks_lo, int64_t ks_hi,
+int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C, int k_lo, int k_hi, int64_t ks_lo, int64_t ks_hi,
                     float* full_os_dev, int32_t* full_cnt_dev, float* semi_os_dev, long long* semi_cnt_dev,
                     double* integral_dev, void* work_dev, void* stream) {
   using namespace mepp;
@@ -364,6 +395,7 @@ int mepp_perm_stats(const float* r_dev, int T, int L, int C, int k_lo, int k_hi,
                "perm_stats: null pointer");
   const int P = C - 1;
   MEPP_REQUIRE(T > 0 && L > 0 && P >= 1, "perm_stats: needs at least one permutation");
+  MEPP_REQUIRE(ldr >= C, "perm_stats: ldr must be >= C");
   MEPP_REQUIRE(T <= 65535 && L <= 65535, "perm_stats: T and L must be <= 65535");
   MEPP_REQUIRE(k_lo >= 0 && k_lo < P && k_hi >= 0 && k_hi < P, "perm_stats: percentile index out of range");
   MEPP_REQUIRE(ks_lo >= 0 && ks_hi < (int64_t)L * P, "perm_stats: pooled percentile index out of range");
@@ -385,7 +417,7 @@ int mepp_perm_stats(const float* r_dev, int T, int L, int C, int k_lo, int k_hi,
     const int64_t n_rows = (int64_t)T * L;
     const unsigned blocks = (unsigned)((n_rows + 7) / 8);
     const int Q = P_pow2 <= 32 ? 1 : P_pow2 / 32;
-#define MEPP_ROW_WARP(QQ) row_stats_warp_kernel<QQ><<<blocks, 256, 0, st>>>(r_dev, n_rows, C, k_lo, k_hi, full_os_dev, \
+#define MEPP_ROW_WARP(QQ) row_stats_warp_kernel<QQ><<<blocks, 256, 0, st>>>(r_dev, ldr, n_rows, C, k_lo, k_hi, full_os_dev, \
                                                                            full_cnt_dev, sorted_keys)
     switch (Q) {
       case 1: MEPP_ROW_WARP(1); break;
@@ -400,22 +432,22 @@ int mepp_perm_stats(const float* r_dev, int T, int L, int C, int k_lo, int k_hi,
     const size_t row_smem = sizeof(uint32_t) * (size_t)P_pow2;
     MEPP_CUDA_CHECK(cudaFuncSetAttribute(row_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
     row_stats_kernel<<<dim3((unsigned)L, (unsigned)T), 256, row_smem, st>>>(
-        r_dev, L, C, P_pow2, k_lo, k_hi, full_os_dev, full_cnt_dev, sorted_keys);
+        r_dev, ldr, L, C, P_pow2, k_lo, k_hi, full_os_dev, full_cnt_dev, sorted_keys);
   }
 
   const size_t thr_smem = sizeof(uint32_t) * (size_t)L_pow2;
   MEPP_CUDA_CHECK(cudaFuncSetAttribute(thresholds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thr_smem));
-  thresholds_kernel<<<(unsigned)T, 256, thr_smem, st>>>(r_dev, L, C, L_pow2, ts_sorted);
+  thresholds_kernel<<<(unsigned)T, 256, thr_smem, st>>>(r_dev, ldr, L, C, L_pow2, ts_sorted);
 
   const size_t hist_smem = sizeof(uint32_t) * (size_t)(2 * L + 1);
   MEPP_CUDA_CHECK(cudaFuncSetAttribute(semi_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
   int chunks = (int)(((int64_t)L * P + 65535) / 65536);
   if (chunks < 1) chunks = 1;
   if (chunks > L) chunks = L;
-  semi_hist_kernel<<<dim3((unsigned)chunks, (unsigned)T), 256, hist_smem, st>>>(r_dev, L, C, ts_sorted, hist);
-  semi_count_kernel<<<(unsigned)T, 256, 0, st>>>(r_dev, L, C, ts_sorted, hist, semi_cnt_dev);
+  semi_hist_kernel<<<dim3((unsigned)chunks, (unsigned)T), 256, hist_smem, st>>>(r_dev, ldr, L, C, ts_sorted, hist);
+  semi_count_kernel<<<(unsigned)T, 256, 0, st>>>(r_dev, ldr, L, C, ts_sorted, hist, semi_cnt_dev);
   semi_select_kernel<<<dim3(4, (unsigned)T), 256, 0, st>>>(sorted_keys, L, P, ks_lo, ks_hi, semi_os_dev);
-  integral_kernel<<<dim3((unsigned)((C + 127) / 128), (unsigned)T), 128, 0, st>>>(r_dev, L, C, integral_dev);
+  integral_kernel<<<dim3((unsigned)((C + 127) / 128), (unsigned)T), 128, 0, st>>>(r_dev, ldr, L, C, integral_dev);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

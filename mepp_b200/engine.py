@@ -85,7 +85,8 @@ class Engine:
         self._bufs = {}
         self._pins = {}
         self.launches = 0   # kernels launched by this engine (bench.py reports it)
-        self.timing = None  # set to {} to collect per-stage CUDA-event times (ms) in _run_group
+        self.timing = None  # set to {} to collect per-stage CUDA-event times (ms)
+        self.fuse_correlation = True   # False: separate GEMM (S) + correlation kernels (tests / A-B runs)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -166,8 +167,21 @@ class Engine:
                                              _ptr(self.col_syz), _ptr(self.ysum), st), "build_y")
             self.launches += 3 if self.use_gc else 2
             self._zsum_host = None
+            self._colconst_dev = None
             self.staged = True
         return self
+
+    def _colconst(self):
+        """Per-dataset constants of the fused correlation epilogue (built once per stage())."""
+        if self._colconst_dev is None:
+            zsum = self._zsum()
+            cc = self.torch.empty(8 + 2 * self.C, dtype=self.torch.float64, device=self.device)
+            _lib.check(_lib.lib.mepp_col_constants(_ptr(self.col_syz), _ptr(self.ysum),
+                                                   zsum.ctypes.data_as(C.POINTER(C.c_double)), self.N, self.C,
+                                                   1 if self.use_gc else 0, _ptr(cc), self._stream()), "col_constants")
+            self.launches += 1
+            self._colconst_dev = cc
+        return self._colconst_dev
 
     def _zsum(self):
         if self._zsum_host is None:
@@ -180,8 +194,7 @@ class Engine:
     # ------------------------------------------------------------------ sizing
     def group_size(self):
         per_task = (self.L * self.n_pad * 4            # X planes (fp16 hi + lo)
-                    + self.L * self.ldS * 4            # S
-                    + self.L * self.C * 4              # r
+                    + self.L * self.ldS * 4            # r
                     + self.L * max(self.P, 1) * 4      # sorted keys
                     + self.n_pad * 4 + self.L * 64)
         g = max(1, min(self.max_group, self.mem_budget // max(per_task, 1)))
@@ -315,18 +328,26 @@ class Engine:
                                       _ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), _ptr(qtab_d), _ptr(qthr_d),
                                       _ptr(x_planes), _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap,
                                       _ptr(hit_count), st), "scan")
-        S = self._buf('S', (m_rows, self.ldS), torch.float32)
         ev = self._mark(ev, 'scan')
-        _lib.check(_lib.lib.mepp_profile_gemm(_ptr(x_planes), _ptr(self.y_planes), _ptr(S), m_rows, C_, self.n_pad,
-                                              st), "profile_gemm")
-        ev = self._mark(ev, 'gemm')
-        r = self._buf('r', (m_rows, C_), torch.float32)
-        zsum = self._zsum()
-        _lib.check(_lib.lib.mepp_correlation(_ptr(S), self.ldS, _ptr(rowstats), _ptr(self.col_syz), _ptr(self.ysum),
-                                             zsum.ctypes.data_as(C.POINTER(C.c_double)), N, m_rows, C_,
-                                             1 if self.use_gc else 0, _ptr(r), st), "correlation")
-        self.launches += 3 + (m_rows + 65534) // 65535 - 1
-        ev = self._mark(ev, 'correlation')
+        # tcgen05 GEMM with the correlation fused into its epilogue: r (m_rows, ldS) float32, S never reaches HBM
+        r = self._buf('r', (m_rows, self.ldS), torch.float32)
+        if self.fuse_correlation:
+            _lib.check(_lib.lib.mepp_profile_corr_gemm(_ptr(x_planes), _ptr(self.y_planes), _ptr(rowstats),
+                                                       _ptr(self._colconst()), _ptr(r), m_rows, C_, self.n_pad, st),
+                       "profile_corr_gemm")
+            self.launches += 2
+            ev = self._mark(ev, 'gemm')
+        else:
+            S = self._buf('S', (m_rows, self.ldS), torch.float32)
+            _lib.check(_lib.lib.mepp_profile_gemm(_ptr(x_planes), _ptr(self.y_planes), _ptr(S), m_rows, C_, self.n_pad,
+                                                  st), "profile_gemm")
+            ev = self._mark(ev, 'gemm')
+            zsum = self._zsum()
+            _lib.check(_lib.lib.mepp_correlation(_ptr(S), self.ldS, _ptr(rowstats), _ptr(self.col_syz), _ptr(self.ysum),
+                                                 zsum.ctypes.data_as(C.POINTER(C.c_double)), N, m_rows, C_,
+                                                 1 if self.use_gc else 0, _ptr(r), self.ldS, st), "correlation")
+            self.launches += 3 + (m_rows + 65534) // 65535 - 1
+            ev = self._mark(ev, 'correlation')
         dev = {}
         if P > 0:
             q = stats_host.percentile_q(ci)
@@ -340,18 +361,18 @@ class Engine:
             dev['semi_cnt'] = self._buf('semi_cnt', (T, L), torch.int64)
             dev['integral'] = self._buf('integral', (T, C_), torch.float64)
             work = self._buf('stats_work', int(_lib.lib.mepp_perm_stats_work_bytes(T, L, C_)), torch.uint8)
-            _lib.check(_lib.lib.mepp_perm_stats(_ptr(r), T, L, C_, k_lo, k_hi, ks_lo, ks_hi, _ptr(dev['full_os']),
+            _lib.check(_lib.lib.mepp_perm_stats(_ptr(r), self.ldS, T, L, C_, k_lo, k_hi, ks_lo, ks_hi, _ptr(dev['full_os']),
                                                 _ptr(dev['full_cnt']), _ptr(dev['semi_os']), _ptr(dev['semi_cnt']),
                                                 _ptr(dev['integral']), _ptr(work), st), "perm_stats")
             self.launches += 6
             ev = self._mark(ev, 'perm_stats')
         dev['r0'] = self._buf('r0', (T, L), torch.float32)
-        dev['r0'].copy_(r.view(T, L, C_)[:, :, 0])
+        dev['r0'].copy_(r.view(T, L, self.ldS)[:, :, 0])
         dev['count'] = count
         dev['density'] = density
         dev['hit_count'] = hit_count
         if return_r:
-            dev['r'] = r.view(T, L, C_)
+            dev['r'] = r.view(T, L, self.ldS)[:, :, :C_].contiguous()
         host = {}
         for k, t in dev.items():
             h = self._pinned(k, slot, t.shape, t.dtype)

@@ -138,6 +138,7 @@ def test_gemm_matches_float64_check_kernel():
     perm = synth.synth_permutations(4101, 300, seed=4)
     eng = _engine().stage(ascii_u8, scores, perm)
     motifs = synth.synth_motifs(3, seed=8)
+    eng.fuse_correlation = False
     eng.profile([(m, '+/-') for m in motifs], margin=2)
     m_rows = 3 * 130
     Sd = torch.empty((m_rows, eng.C), dtype=torch.float64, device='cuda')

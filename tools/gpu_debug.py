@@ -69,7 +69,10 @@ def main():
               f"{np.abs(rs[t*L:(t+1)*L,2]-sxz).max():.2e}", flush=True)
         print(f"   count equal {np.array_equal(out['positions']['count'][t], (X0>0).sum(0))} density equal "
               f"{np.array_equal(out['density'][t,:N], (X0>0).sum(1))}", flush=True)
-    # ---- GEMM vs float64 check kernel and vs host
+    # ---- GEMM vs float64 check kernel and vs host (unfused rerun so that S is materialised)
+    eng.fuse_correlation = False
+    eng.profile(tasks, margin=margin, tables=tables)
+    eng.fuse_correlation = True
     S = eng._bufs['S'][:m_rows * eng.ldS].view(m_rows, eng.ldS).cpu().numpy()[:, :eng.C].astype(np.float64)
     Sd = torch.empty((m_rows, eng.C), dtype=torch.float64, device='cuda')
     _lib.check(_lib.lib.mepp_profile_gemm_check(_ptr(eng._bufs['x_planes']), _ptr(eng.y_planes), _ptr(Sd), m_rows,

@@ -66,7 +66,10 @@ def main():
                     'permutation_semi_positional_r_upper', 'positional_r_lower', 'smoothed_count'):
             a, b = np.asarray(b2.positions[col][j], dtype=np.float64), np.asarray(orc['positions'][col], dtype=np.float64)
             print(f"     {col}: max abs diff {np.abs(a-b).max():.3e}", flush=True)
-    # S vs check kernel on selected rows of the last group run (b2)
+    # S vs check kernel on selected rows: rerun the same tasks with the unfused GEMM so that S is materialised
+    eng.fuse_correlation = False
+    eng.profile([tasks[i] for i in sel], margin=cfg["margin"])
+    eng.fuse_correlation = True
     m_rows = len(sel) * cfg["L"]
     rows = np.unique(np.random.default_rng(0).integers(0, m_rows, 64)).astype(np.int32)
     rows_d = torch.from_numpy(rows).cuda()
