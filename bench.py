@@ -260,7 +260,7 @@ def main():
     value = work_step * args.steps / dt_value / 1e9
     e2e_value = work_step * args.steps / dt_e2e / 1e9
     n_local = len(my_tasks)
-    groups = -(-n_local // eng.group_size())
+    groups = eng.last_groups
     # per-kernel rooflines from the CUDA-event stage times of the timed value region (rank 0's share)
     C_ = 1 + P
     scan_bytes = 4.0 * N * L * n_local * args.steps          # fp16 hi+lo planes written once (4 B / bp*task)

@@ -228,6 +228,7 @@ class Engine:
             # at least three groups so that the host finalisation of one group overlaps the kernels of the next
             G = min(G, max(32, -(-T_all // 3)))
         groups = [(g0, min(g0 + G, T_all)) for g0 in range(0, T_all, G)]
+        self.last_groups = len(groups)
         store = stats_host.alloc_positions(T_all, L, self.P)
         density_all = np.empty((T_all, N), dtype=np.int32)
         outs = []
