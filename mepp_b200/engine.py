@@ -12,6 +12,7 @@ PyTorch is used for device memory, streams and (in parallel.py) torch.distribute
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
@@ -57,6 +58,16 @@ class ProfileBatch:
         import pandas as pd
         return pd.DataFrame(dict(rank=np.arange(self.n_seq), score=self.scores,
                                  density=self.density[i].astype(np.float64)))
+
+    def heatmap(self, i, L, pixel_width, pixel_height, sigma=1.0):
+        """Clipped block-max of task i's score matrix on a pixel grid (plot.py:32-66, 106-145) from the match
+        list, without materialising the (N, L) matrix."""
+        from . import heatmap as _hm
+        if self.hits is None:
+            raise RuntimeError("profile() was called without return_hits=True")
+        h = self.hits[self.hits['task'] == i]
+        return _hm.compress_hits_to_pixels(h['seq'], h['pos'], h['x0'], (self.n_seq, L), pixel_width, pixel_height,
+                                           sigma)
 
     def motif_score_matrix(self, i, L):
         """Dense (N, L) float32 unsmoothed score matrix of task i rebuilt from the match list
@@ -225,8 +236,10 @@ class Engine:
         table_kw = dict(honour_flags=honour_flags, pseudocount=pseudocount, pvalue=pvalue, bg=bg)
         G = self.group_size()
         if T_all > 96:
-            # at least three groups so that the host finalisation of one group overlaps the kernels of the next
-            G = min(G, max(32, -(-T_all // 3)))
+            # several groups so that the host finalisation of one group overlaps the kernels of the next and the
+            # exposed finalisation of the last group stays small (4 measured best on cfg 2)
+            n_groups = int(os.environ.get("MEPP_GROUPS", "4"))
+            G = min(G, max(32, -(-T_all // n_groups)))
         groups = [(g0, min(g0 + G, T_all)) for g0 in range(0, T_all, G)]
         self.last_groups = len(groups)
         store = stats_host.alloc_positions(T_all, L, self.P)

@@ -260,3 +260,21 @@ def test_filter_table_is_conservative(lib):
                 hit |= (acc + tab['bias']) > 0
             assert not (hit & ~passes).any(), "pre-filter rejected a true match"
             assert hit[:100].all() or tab['thr'] > W[:, :, 0].max(axis=1).sum()      # consensus windows do match
+
+
+def test_heatmap_from_match_list_equals_dense_reduction():
+    """clip + block-max of the score matrix from its non-zero entries only."""
+    from mepp_b200 import heatmap
+    rng = np.random.default_rng(5)
+    N, L = 517, 203
+    X0 = np.zeros((N, L), dtype=np.float32)
+    k = 400
+    X0[rng.integers(0, N, k), rng.integers(0, L, k)] = rng.gamma(2.0, 1.0, k).astype(np.float32)
+    seq, pos = np.nonzero(X0)
+    for (pw, ph, sigma) in ((100, 60, 0.5), (1000, 1000, 1.0), (37, 11, None), (203, 517, 2.0)):
+        a = heatmap.compress_hits_to_pixels(seq, pos, X0[seq, pos], X0.shape, pw, ph, sigma)
+        b = heatmap.compress_dense_to_pixels(X0, pw, ph, sigma)
+        assert a.shape == b.shape and np.array_equal(a, b), (pw, ph, sigma)
+    assert heatmap.get_aspect_tensor((100000, 1000), 800, 600) == (167, 1)
+    empty = heatmap.compress_hits_to_pixels([], [], [], (10, 10), 5, 5)
+    assert empty.shape == (5, 5) and not empty.any()
