@@ -207,17 +207,47 @@ __device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, in
 // (w_lo = the stream word holding bit 6T, w_hi = the next word, only used by the two slots that
 // straddle a word).  `qbase` is the 256-byte aligned shared address of the task's 16 x 256-byte
 // tables, so the same LOP3 that masks the 6-bit index ORs the table base in (slot offset = LDS immediate).
-template <int T>
-__device__ __forceinline__ uint32_t slot(uint32_t qbase, uint32_t w_lo, uint32_t w_hi) {
-  constexpr int off = (6 * T) % 32;
+template <int T, int U>
+__device__ __forceinline__ uint32_t slot(uint32_t qbase, const uint32_t (&r)[6]) {
+  constexpr int bit = 6 * T + 3 * U;       // window U bases ahead of the register file's origin
+  constexpr int word = bit / 32, off = bit % 32;
   uint32_t v;
-  if constexpr (off + 6 > 32) v = __funnelshift_r(w_lo, w_hi, off - 2);
-  else if constexpr (off >= 2) v = w_lo >> (off - 2);
-  else v = w_lo << (2 - off);
+  if constexpr (off + 6 > 32) v = __funnelshift_r(r[word], r[word + 1], off - 2);
+  else if constexpr (off >= 2) v = r[word] >> (off - 2);
+  else v = r[word] << (2 - off);
   const uint32_t addr = (v & 0xFCu) | qbase;
   uint32_t x;
   asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(x) : "r"(addr), "n"(T * 256));
   return x;
+}
+
+// Pre-filter sum of the window U bases ahead of the register file's origin (np = pair slots in use).
+template <int U>
+__device__ __forceinline__ uint32_t window_sum(uint32_t qbase, uint32_t qinit, int np, const uint32_t (&r)[6]) {
+  uint32_t sum = qinit + slot<0, U>(qbase, r) + slot<1, U>(qbase, r) + slot<2, U>(qbase, r);
+  if (np > 3) {
+    sum += slot<3, U>(qbase, r) + slot<4, U>(qbase, r);
+    if (np > 5) {
+      sum += slot<5, U>(qbase, r);
+      if (np > 6) {
+        sum += slot<6, U>(qbase, r) + slot<7, U>(qbase, r);
+        if (np > 8) {
+          sum += slot<8, U>(qbase, r) + slot<9, U>(qbase, r) + slot<10, U>(qbase, r);
+          if (np > 11)
+            sum += slot<11, U>(qbase, r) + slot<12, U>(qbase, r) + slot<13, U>(qbase, r) +
+                   slot<14, U>(qbase, r) + slot<15, U>(qbase, r);
+        }
+      }
+    }
+  }
+  return sum;
+}
+
+template <int BITS>
+__device__ __forceinline__ void advance(uint32_t (&r)[6]) {
+  r[0] = __funnelshift_r(r[0], r[1], BITS); r[1] = __funnelshift_r(r[1], r[2], BITS);
+  r[2] = __funnelshift_r(r[2], r[3], BITS); r[3] = __funnelshift_r(r[3], r[4], BITS);
+  r[4] = __funnelshift_r(r[4], r[5], BITS); r[5] >>= BITS;
 }
 
 __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const int kb,
@@ -265,9 +295,9 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
   const uint32_t* my = s_sym + lane * a.strideS;
   const uint32_t qbase = (uint32_t)__cvta_generic_to_shared(s_qtab);
 
-  // 192-bit shift register over the symbol stream (window start at bit 0 of r0), advanced by one
-  // base (3 bits) per position and refilled with three new words every 32 positions.
-  uint32_t r0 = my[0], r1 = my[1], r2 = my[2], r3 = my[3], r4 = my[4], r5 = my[5];
+  // 192-bit shift register over the symbol stream (window start at bit 0 of r[0]), advanced by four
+  // bases (12 bits) per group of four windows and refilled with three new words every 32 positions.
+  uint32_t r[6] = {my[0], my[1], my[2], my[3], my[4], my[5]};
   int next_w = 6, left = 32;
   int q_head = 0, q_tail = 0;            // warp-uniform ring indices
   bool carry_nz = false;                 // previous chunk left non-zero x0 in the carried rows
@@ -290,26 +320,7 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
       const int i_end = base - mg + nbuf - padl;      // exclusive
       if (i_end > n_valid) b_hi -= i_end - n_valid;
     }
-    // one window: pre-filter sum -> candidate flag, then advance the window by one base (3 bits)
-    auto eval_window = [&]() -> bool {
-      uint32_t sum = qinit + slot<0>(qbase, r0, r1) + slot<1>(qbase, r0, r1) + slot<2>(qbase, r0, r1);
-      if (np > 3) {
-        sum += slot<3>(qbase, r0, r1) + slot<4>(qbase, r0, r1);
-        if (np > 5) {
-          sum += slot<5>(qbase, r0, r1) + slot<6>(qbase, r1, r2) + slot<7>(qbase, r1, r2);
-          if (np > 8) {
-            sum += slot<8>(qbase, r1, r2) + slot<9>(qbase, r1, r2) + slot<10>(qbase, r1, r2);
-            if (np > 11)
-              sum += slot<11>(qbase, r2, r3) + slot<12>(qbase, r2, r3) + slot<13>(qbase, r2, r3) +
-                     slot<14>(qbase, r2, r3) + slot<15>(qbase, r2, r3);
-          }
-        }
-      }
-      r0 = __funnelshift_r(r0, r1, 3); r1 = __funnelshift_r(r1, r2, 3); r2 = __funnelshift_r(r2, r3, 3);
-      r3 = __funnelshift_r(r3, r4, 3); r4 = __funnelshift_r(r4, r5, 3); r5 >>= 3;
-      return (sum & 0x80008000u) != 0u;
-    };
-    auto refill = [&]() { r3 = my[next_w]; r4 = my[next_w + 1]; r5 = my[next_w + 2]; next_w += 3; left = 32; };
+    auto refill = [&]() { r[3] = my[next_w]; r[4] = my[next_w + 1]; r[5] = my[next_w + 2]; next_w += 3; left = 32; };
     // queue the candidates of buffer row b (ballot `bal`), flushing the ring whenever 32 are pending
     auto push = [&](unsigned bal, bool cand, int b) {
       if (cand) {
@@ -323,22 +334,27 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
     // scalar steps until the refill counter is a multiple of 4, groups of 4 windows, scalar tail
 #pragma unroll 1
     for (; b < b_hi && (left & 3) != 0; ++b) {
-      const bool cand = eval_window();
+      const bool cand = (window_sum<0>(qbase, qinit, np, r) & 0x80008000u) != 0u;
+      advance<3>(r);
       if (--left == 0) refill();
       const unsigned bal = __ballot_sync(full, cand);
       if (bal != 0u) push(bal, cand, b);
     }
 #pragma unroll 1
     for (; b + 4 <= b_hi; b += 4) {
-      uint32_t cb = 0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) cb |= (eval_window() ? 1u : 0u) << u;   // 4 independent windows in flight
+      // four independent windows read the same registers at offsets 0, 3, 6, 9 bits; their pass bits
+      // (bit 15 / 31 of each packed sum) are merged into one word: window u lands on bits 15-u and 31-u
+      const uint32_t cb = (window_sum<0>(qbase, qinit, np, r) & 0x80008000u) |
+                          ((window_sum<1>(qbase, qinit, np, r) & 0x80008000u) >> 1) |
+                          ((window_sum<2>(qbase, qinit, np, r) & 0x80008000u) >> 2) |
+                          ((window_sum<3>(qbase, qinit, np, r) & 0x80008000u) >> 3);
+      advance<12>(r);
       left -= 4;
       if (left == 0) refill();
       if (__any_sync(full, cb != 0u)) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const bool cand = (cb >> u) & 1u;
+          const bool cand = (cb & (0x80008000u >> u)) != 0u;
           const unsigned bal = __ballot_sync(full, cand);
           if (bal != 0u) push(bal, cand, b + u);
         }
@@ -346,7 +362,8 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
     }
 #pragma unroll 1
     for (; b < b_hi; ++b) {
-      const bool cand = eval_window();
+      const bool cand = (window_sum<0>(qbase, qinit, np, r) & 0x80008000u) != 0u;
+      advance<3>(r);
       if (--left == 0) refill();
       const unsigned bal = __ballot_sync(full, cand);
       if (bal != 0u) push(bal, cand, b);
