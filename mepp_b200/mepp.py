@@ -60,6 +60,16 @@ def run_mepp(
     try:
         from .clustering import filepaths_df_to_clustering_results  # optional reporting layer (out of scope)
     except ImportError:
+        # tabular part of the results tables (no images / HTML): mepp.py:285-297 file names
+        from .summary import results_table
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0:
+            for motif_orientation in motif_orientations:
+                o = orientation_to_filepath[motif_orientation]
+                table = results_table(filepaths_df, motif_orientation, mt_method=mt_method, mt_alpha=mt_alpha,
+                                      thorough_mt=thorough_mt)
+                table.to_csv(normpath(f'{out_filepath}/results_table_orientation_{o}.tsv'), sep='\t', index=False)
+                table.to_pickle(normpath(f'{out_filepath}/results_table_orientation_{o}.pkl'))
         return filepaths_df, results_html_filepaths, clustermap_html_filepaths
     for motif_orientation in motif_orientations:
         o = orientation_to_filepath[motif_orientation]

@@ -198,6 +198,10 @@ def test_run_mepp_writes_the_reference_layout(tmp_path):
     assert list(filepaths_df.columns) == ['motif_id', 'orientation', 'outdir', 'params', 'log', 'retval', 'attempts']
     assert len(filepaths_df) == 4 and (filepaths_df['retval'] == 0).all()
     assert (out / "filepaths.tsv").exists() and (out / "filtered_data_df.tsv").exists()
+    for o in ('fwd', 'fwd-rev'):                                           # mepp.py:285-297 (tabular part)
+        tab = pd.read_csv(out / f"results_table_orientation_{o}.tsv", sep="\t")
+        assert {'motif_id', 'extreme_r', 'extreme_r_padj', 'extreme_r_sig', 'max_r_pos',
+                'integral_r_padj'} <= set(tab.columns) and len(tab) == 2
     assert (out / "dataset.element_spec.p").exists() and not (out / "dataset").exists()     # batch.py:187-188
     fdf = pd.read_csv(out / "filtered_data_df.tsv", sep="\t")
     assert len(fdf) == 300 and (np.diff(fdf['score'].to_numpy()) >= 0).all()
@@ -222,3 +226,68 @@ def test_run_mepp_writes_the_reference_layout(tmp_path):
     assert _r_close(pos['positional_r'].to_numpy()[:, None], orc['r'][:, :1]).all()
     ranks = pd.read_pickle(d / "ranks_df.pkl")
     assert np.array_equal(ranks['density'].to_numpy(), orc['ranks']['density'])
+
+
+def test_motif_length_and_margin_extremes():
+    """m = 1, 2, 3 and the maximum 32 at the maximum margin 16, on sequences shorter than the blur window
+    would like (L = 40) and on an L that is not a multiple of anything (L = 203)."""
+    from mepp_b200 import synth
+    rng = np.random.default_rng(12)
+    for L in (40, 203):
+        ascii_u8, scores = synth.synth_sequences(130, L, seed=5 + L, n_rate=0.01, lower_rate=0.01)
+        perm = synth.synth_permutations(130, 9, seed=4)
+        motifs = []
+        for m in (1, 2, 3, 32):
+            pwm = rng.dirichlet(np.full(4, 0.05), size=m).T          # sharp columns -> finite thresholds
+            motifs.append(pwm)
+        eng = _engine().stage(ascii_u8, scores, perm)
+        tasks = [(pwm, o) for pwm in motifs for o in ('+', '+/-')]
+        batch = eng.profile(tasks, margin=16, return_hits=True, return_r=True)
+        codes = staging.ascii_to_codes(ascii_u8)
+        Y = staging.permuted_scores(scores, perm)
+        z = staging.gc_ratio_global(codes)
+        for t, (pwm, o) in enumerate(tasks):
+            orc = profile.profile_task(codes, Y, z, pwm, o, margin=16)
+            assert np.array_equal(batch.motif_score_matrix(t, L).view(np.uint32), orc["X0"].view(np.uint32)), (L, t)
+            assert _r_close(batch.r[t], orc["r"]).all(), (L, t)
+            assert np.array_equal(np.asarray(batch.positions["smoothed_count"][t]), orc["positions"]["smoothed_count"])
+
+
+def test_honour_flags_changes_the_threshold_like_the_oracle():
+    """--motifpseudocount / --motifpvalue only reach the scan with honour_flags=True (the reference drops them,
+    core.py:513-534); with the flag the matches equal the oracle's at the same pseudocount / p-value."""
+    from mepp_b200 import synth
+    ascii_u8, scores = synth.synth_sequences(200, 101, seed=21)
+    perm = synth.synth_permutations(200, 5, seed=21)
+    motifs = synth.synth_motifs(3, seed=8, m_lo=6, m_hi=12)
+    eng = _engine().stage(ascii_u8, scores, perm)
+    tasks = [(m, '+/-') for m in motifs]
+    codes = staging.ascii_to_codes(ascii_u8)
+    default = eng.profile(tasks, margin=1, return_hits=True, pseudocount=0.01, pvalue=1e-3)
+    honoured = eng.profile(tasks, margin=1, return_hits=True, pseudocount=0.01, pvalue=1e-3, honour_flags=True)
+    differs = 0
+    for t, (pwm, o) in enumerate(tasks):
+        Wf, Wr, thr = profile.motif_weights(pwm, o)
+        assert default.thr[t] == thr
+        assert np.array_equal(default.motif_score_matrix(t, 101).view(np.uint32),
+                              profile.scan(codes, Wf, Wr, thr).view(np.uint32))
+        Wf, Wr, thr = profile.motif_weights(pwm, o, pseudocount=0.01, pvalue=1e-3)
+        assert honoured.thr[t] == thr
+        X0 = honoured.motif_score_matrix(t, 101)
+        assert np.array_equal(X0.view(np.uint32), profile.scan(codes, Wf, Wr, thr).view(np.uint32))
+        differs += int((X0 != 0).sum() != (default.motif_score_matrix(t, 101) != 0).sum())
+    assert differs > 0
+
+
+def test_heatmap_from_hits_equals_dense_block_max(cfg1):
+    from mepp_b200 import heatmap
+    eng = _engine().stage(cfg1["ascii"], cfg1["scores"], cfg1["perm_idx"])
+    tasks = [(pwm, o) for _, pwm, o in cfg1["tasks"]][:3]
+    batch = eng.profile(tasks, margin=cfg1["margin"], return_hits=True)
+    for t in range(len(tasks)):
+        X0 = batch.motif_score_matrix(t, cfg1["L"])
+        for pw, ph in ((100, 50), (201, 1000), (7, 13)):
+            a = batch.heatmap(t, cfg1["L"], pw, ph)
+            b = heatmap.compress_dense_to_pixels(X0, pw, ph)
+            assert a.shape == b.shape and np.array_equal(a, b)
+

@@ -278,3 +278,49 @@ def test_heatmap_from_match_list_equals_dense_reduction():
     assert heatmap.get_aspect_tensor((100000, 1000), 800, 600) == (167, 1)
     empty = heatmap.compress_hits_to_pixels([], [], [], (10, 10), 5, 5)
     assert empty.shape == (5, 5) and not empty.any()
+
+
+def test_multipletests_known_answers():
+    from mepp_b200.summary import multipletests
+    p = np.array([0.01, 0.04, 0.03, 0.005, 0.8])
+    rej, adj = multipletests(p, alpha=0.05, method='fdr_bh')
+    assert np.allclose(adj, [0.025, 0.05, 0.05, 0.025, 0.8]) and rej.tolist() == [True, True, True, True, False]
+    _, adj = multipletests(p, alpha=0.05, method='bonferroni')
+    assert np.allclose(adj, [0.05, 0.2, 0.15, 0.025, 1.0])
+    _, adj = multipletests(p, alpha=0.05, method='holm')
+    assert np.allclose(adj, [0.04, 0.09, 0.09, 0.025, 0.8])
+    _, adj = multipletests(p, alpha=0.05, method='fdr_by')
+    assert np.allclose(adj, np.minimum(np.array([0.025, 0.05, 0.05, 0.025, 0.8]) * (1 + 1/2 + 1/3 + 1/4 + 1/5), 1.0))
+    rng = np.random.default_rng(0)
+    q = np.concatenate([rng.uniform(0, 1e-4, 30), rng.uniform(0, 1, 300)])
+    for method in ('fdr_tsbky', 'fdr_tsbh', 'sidak', 'holm-sidak', 'simes-hochberg'):
+        rej, adj = multipletests(q, alpha=0.01, method=method)
+        assert adj.shape == q.shape and (adj <= 1).all()
+        assert method.startswith('fdr_ts') or (adj >= q - 1e-15).all()   # two-stage scales by m0/m < 1
+        assert (np.diff(adj[np.argsort(q)]) >= -1e-12).all()           # monotone in p
+    # two-stage BKY is never more conservative than BH at level alpha / (1 + alpha) when something is rejected
+    _, bky = multipletests(q, alpha=0.01, method='fdr_tsbky')
+    _, bh = multipletests(q, alpha=0.01, method='fdr_bh')
+    assert (bky <= bh * 1.01 + 1e-12).all()
+
+
+def test_minmax_stats_table():
+    import pandas as pd
+    from mepp_b200 import stats_host, summary
+    rng = np.random.default_rng(1)
+    T, L, P = 4, 30, 20
+    r0 = rng.normal(scale=0.05, size=(T, L)).astype(np.float32)
+    store = stats_host.alloc_positions(T, L, P)
+    full_os = np.sort(rng.normal(scale=0.05, size=(T, L, 4)).astype(np.float32), axis=-1)
+    stats_host.finalize_into(store, 0, r0, full_os, rng.integers(0, P, (T, L)), np.sort(rng.normal(size=(T, 4)).astype(np.float32)),
+                             rng.integers(0, L * P, (T, L)), np.abs(rng.normal(size=(T, 1 + P))), rng.integers(0, 3, (T, L)), 100, 2)
+    cols = stats_host.positions_view(store)
+    dfs = {f"m{t}": pd.DataFrame({k: np.array(v[t]) for k, v in cols.items()}) for t in range(T)}
+    st = summary.get_minmax_stats(dfs["m0"])
+    i = int(np.argmax(r0[0]))
+    assert st['max_r'] == r0[0, i] and st['max_r_pos'] == i - L // 2
+    assert st['max_r_pval'] == dfs["m0"]['permutation_positional_r_pval'][i]
+    for thorough in (True, False):
+        tab = summary.get_minmax_stats_df(dfs, mt_alpha=0.05, thorough_mt=thorough)
+        assert list(tab['motif_id']) == list(dfs) and {'extreme_r_padj', 'extreme_r_sig', 'integral_r_padj'} <= set(tab.columns)
+        assert (tab['extreme_r_padj'] >= tab['extreme_r_pval'] - 1e-15).all()
