@@ -97,7 +97,17 @@ int mepp_build_y(const float* yhat_dev, const int32_t* perm_dev, const float* zh
  * (motif_layers.py:80-165, core.py:25-145, core.py:415-470) for a group of T tasks.
  *   lut_dev   float [T][MEPP_MAX_MOTIF_LEN][4][2]   bias_dev float [T]
  *   mlen_dev  int32 [T]   nfilt_dev int32 [T]   qtab_dev uint32 [T][1024]   qthr_dev uint32 [T][2]
- *   x_planes_dev  A operand (rows t*L+l), written densely
+ *   units_dev optional int32 [n_units][2] = (task scanned, twin task or -1): the reference's default
+ *             orientations '+' and '+/-' of one motif (mepp.py:67-90) share filter 0 and its threshold
+ *             (motif_layers.py:36-76), so one pass over the sequences with the two-filter table of the
+ *             '+/-' task also yields the '+' task (x = relu of filter 0 alone).  Every task must appear
+ *             exactly once, as a scanned task or as a twin; a twin's own tables are not read.
+ *             NULL: every task is scanned on its own.
+ *   max_motif_len  upper bound of mlen over the scanned tasks (sizes the shared-memory pair tables;
+ *             a longer task traps); 0 = MEPP_MAX_MOTIF_LEN
+ *   x_planes_dev  A operand (rows t*L+l).  Must be ALL-ZERO on entry (tiles and flag words): X is ~99.9 % zeros,
+ *                 so the scan stores only the 16-byte pieces that hold a non-zero value and sets the flag bit
+ *                 of their 128 x 16 block.  mepp_x_planes_reset restores the all-zero state after the GEMM.
  *   rowstats_dev  double [T*L][3]: sum_n x, sum_n x^2, sum_n x*zhat  (x = blurred score); zeroed by the call
  *   count_dev     int32 [T*L]  : #sequences with an unsmoothed match at each position; zeroed by the call
  *   density_dev   int32 [T][n_pad]: #matches per sequence
@@ -106,9 +116,17 @@ int mepp_build_y(const float* yhat_dev, const int32_t* perm_dev, const float* zh
 int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
               int64_t N, int L, int T, int margin,
               const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev, const int32_t* nfilt_dev,
-              const uint32_t* qtab_dev, const uint32_t* qthr_dev,
+              const uint32_t* qtab_dev, const uint32_t* qthr_dev, const int32_t* units_dev, int n_units,
+              int max_motif_len,
               void* x_planes_dev, double* rowstats_dev, int32_t* count_dev, int32_t* density_dev,
               void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev, void* stream);
+
+/* Restore the all-zero state of an A operand that mepp_scan(..., N, L, T, margin, ...) wrote, from the
+ * match list of that call (every match dirties rows pos-margin..pos+margin of one 8-column group); a NULL
+ * or overflowed list clears the whole operand instead.  Call after the operand's last consumer. */
+int mepp_x_planes_reset(void* x_planes_dev, const void* hits_dev, int64_t hits_cap,
+                        const unsigned long long* hit_count_dev, int64_t N, int L, int T, int margin,
+                        void* stream);
 
 /* ------------------------------------------------------------------ K2: profile GEMM
  * S[r][c] = sum_n X[r][n] * Y[n][c] on tcgen05 tensor cores (fp16 hi/lo split, 3 products,

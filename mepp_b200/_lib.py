@@ -40,8 +40,9 @@ SIGNATURES = {
     "mepp_y_planes_bytes": (_i64, [_i32, _i64]),
     "mepp_pack_dna": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "mepp_build_y": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
-    "mepp_scan": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+    "mepp_scan": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                          _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "mepp_x_planes_reset": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]),
     "mepp_profile_gemm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp]),
     "mepp_gemm_counters": (_i32, [C.POINTER(C.c_ulonglong), _i32]),
     "mepp_profile_gemm_check": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp]),

@@ -94,7 +94,7 @@ int mepp_device_ok(void) {
   return major == 10 ? 1 : 0;
 }
 
-int64_t mepp_sym_words(int L) { return (3 * (int64_t)L + 31) / 32 + 8; }
+int64_t mepp_sym_words(int L) { return (3 * (int64_t)L + 31) / 32 + 12; }
 int64_t mepp_pad32(int64_t n) { return (n + 31) / 32 * 32; }
 
 int64_t mepp_x_planes_bytes(int64_t m_rows, int64_t n_pad) {

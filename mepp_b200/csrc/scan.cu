@@ -22,36 +22,45 @@
 // candidates.  The filter has no false negatives by construction, so
 // every reported score comes from the exact path and is bit-identical to the oracle.
 //
-// Work decomposition: one CTA = one k-block (32 sequences) x 4 tasks; one warp = one
-// task; in the filter pass one lane = one sequence walking the positions left to right.
+// Work decomposition: one warp = one scan unit (a task, or the '+/-' task of a motif together with its '+'
+// twin) x one k-block (32 sequences); in the filter pass one lane = one sequence walking the positions left
+// to right, eight windows per step, its 3-bit symbol stream read straight from global memory (word-transposed,
+// so a warp's load is one 128-byte line) and prefetched one refill ahead.  Warps share nothing; shared memory
+// only holds the unit's pair tables, its x0 staging rows and the candidate ring, ~14 KB per warp.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mepp {
 
 struct HitRec { int32_t task, seq, pos; float x0; };
 
-constexpr int kScanWarps = 4;
+constexpr int kScanWarps = 2;   // warps (= scan units) per CTA
 constexpr int kRowStride = 36;  // floats per position row of the x0 staging buffer (32 + 4 pad)
 constexpr int kQueue = 64;      // candidate ring (flushed whenever 32 are pending)
+constexpr int kGroup = 8;       // windows per pre-filter step
+constexpr int kAddr = 2 * (MEPP_MAX_MOTIF_LEN / 2) + 6;  // pair-index addresses a step can need
 
 struct ScanArgs {
   const uint32_t* sym_T; const float* zhat;
   int64_t N, n_pad, KB;
-  int L, T, margin, W3, strideS;
+  int L, T, margin, W3, qslots;
   const float* lut; const float* bias; const int32_t* mlen; const int32_t* nfilt;
   const uint32_t* qtab; const uint32_t* qthr;
+  const int32_t* units; int U;   // scan units: (task scanned, twin task fed by the same pass or -1); null = one per task
   uint8_t* x_planes; double* rowstats; int32_t* count; int32_t* density;
   HitRec* hits; int64_t hits_cap; unsigned long long* hit_count;
 };
 
-// Per-warp (= per task) state shared by the helper routines below.  The helpers are
-// deliberately NOT inlined and NOT templated: one small instruction stream for every task keeps
-// the kernel inside the instruction cache (an earlier variant specialised on motif length and
-// strand count, 26k SASS instructions, and spent most of its time on instruction fetch).
+// Per-warp (= per unit) state shared by the helper routines below.  The helpers are deliberately NOT
+// inlined and NOT templated on the task: one small instruction stream for every task keeps the kernel
+// inside the instruction cache (an earlier variant specialised on motif length and strand count, 26k SASS
+// instructions, and spent most of its time on instruction fetch).
 struct TaskCtx {
-  const float2* s_lut; const uint32_t* s_sym; float* s_buf; const float* s_z;
-  uint16_t* s_queue;
-  int t, kb, m, padl, mg, L, strideS, dual;
+  const float2* s_lut;     // exact float32 weights of the scanned task (shared copy)
+  const uint32_t* g_sym;   // sym_T + first sequence of the k-block: word w of sequence s at [w * n_pad + s]
+  float* s_buf; float* s_buf2; uint16_t* s_queue;
+  int64_t n_pad;
+  int t, t2, kb, m, padl, mg, L, dual;
   float bias;
   int64_t tile_stride;   // bytes between consecutive m-tiles of the A operand
   uint8_t* x_base;       // A operand + this k-block's offset inside an m-tile row
@@ -59,15 +68,23 @@ struct TaskCtx {
   int FW;
 };
 
-// Exact canonical-order score of the window starting at base i of one sequence (`stream` = that
-// sequence's 3-bit symbol stream in shared memory).
-__device__ __forceinline__ float exact_x0(const TaskCtx& c, const uint32_t* __restrict__ stream, int i) {
+// Exact canonical-order scores of the window starting at base i of sequence s of the k-block:
+// relu(filter 0) and relu(max over the task's filters).
+__device__ __forceinline__ void exact_x0(const TaskCtx& c, int s, int i, float& x_first, float& x_task) {
+  const uint32_t* g = c.g_sym + s;
+  const int bit0 = 3 * i, w0 = bit0 >> 5, sh = bit0 & 31;
+  uint32_t x[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) x[k] = __ldg(g + (int64_t)(w0 + k) * c.n_pad);
+  uint32_t r0 = __funnelshift_r(x[0], x[1], sh), r1 = __funnelshift_r(x[1], x[2], sh),
+           r2 = __funnelshift_r(x[2], x[3], sh), r3 = __funnelshift_r(x[3], x[4], sh);
   float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll 1
-  for (int j = 0; j < c.m; ++j) {
-    const int bit = 3 * (i + j);
-    const uint32_t sym = __funnelshift_r(stream[bit >> 5], stream[(bit >> 5) + 1], bit & 31) & 7u;
-    const float2* l4 = c.s_lut + j * 4;
+  const int m = c.m;
+  const float2* lut = c.s_lut;
+  auto tap = [&](int j) {
+    const uint32_t sym = r0 & 7u;
+    r0 = __funnelshift_r(r0, r1, 3); r1 = __funnelshift_r(r1, r2, 3); r2 = __funnelshift_r(r2, r3, 3); r3 >>= 3;
+    const float2* l4 = lut + j * 4;
     if (sym >= 4u) {
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
@@ -80,165 +97,225 @@ __device__ __forceinline__ float exact_x0(const TaskCtx& c, const uint32_t* __re
       a0 = __fadd_rn(a0, w.x);
       a1 = __fadd_rn(a1, w.y);
     }
+  };
+  int j = 0;
+#pragma unroll 1
+  for (; j + 4 <= m; j += 4) { tap(j); tap(j + 1); tap(j + 2); tap(j + 3); }
+#pragma unroll 1
+  for (; j < m; ++j) tap(j);
+  float sc = __fadd_rn(a0, c.bias);
+  x_first = fmaxf(sc, 0.0f);
+  if (c.dual) sc = fmaxf(sc, __fadd_rn(a1, c.bias));
+  x_task = fmaxf(sc, 0.0f);
+}
+
+// One match of task t: staging buffer, per-position / per-sequence counts, optional match list.
+__device__ __forceinline__ void publish_match(const ScanArgs& a, const TaskCtx& c, int t, float* buf, int b, int s,
+                                              int p, float x0) {
+  buf[b * kRowStride + s] = x0;
+  const int64_t ns = (int64_t)c.kb * 32 + s;
+  atomicAdd(&a.count[(int64_t)t * c.L + p], 1);
+  atomicAdd(&a.density[(int64_t)t * a.n_pad + ns], 1);
+  if (a.hit_count) {
+    const unsigned long long slot = atomicAdd(a.hit_count, 1ull);
+    if (a.hits && (int64_t)slot < a.hits_cap) {
+      HitRec rec; rec.task = t; rec.seq = (int32_t)ns; rec.pos = p; rec.x0 = x0;
+      a.hits[slot] = rec;
+    }
   }
-  float s = __fadd_rn(a0, c.bias);
-  if (c.dual) s = fmaxf(s, __fadd_rn(a1, c.bias));
-  return fmaxf(s, 0.0f);
 }
 
 // Evaluate up to 32 queued candidates (one per lane) exactly; publish matches.  Returns (warp
-// uniform) whether any candidate was a match.
-__device__ __noinline__ bool flush_candidates(const ScanArgs& a, const TaskCtx& c, int q_head, int count, int base,
-                                              int lane) {
+// uniform) bit 0: the unit's task got a match, bit 1: its twin (the '+' task sharing filter 0) got one.
+__device__ __noinline__ unsigned flush_candidates(const ScanArgs& a, const TaskCtx& c, int q_head, int count, int base,
+                                                  int lane) {
   __syncwarp();
-  bool any_hit = false;
+  bool hit = false, hit2 = false;
   if (lane < count) {
     const uint32_t e = c.s_queue[(q_head + lane) & (kQueue - 1)];
     const int s = (int)(e >> 8), b = (int)(e & 0xffu);
     const int p = base - c.mg + b;
-    const float x0 = exact_x0(c, c.s_sym + s * c.strideS, p - c.padl);
-    if (x0 > 0.0f) {
-      any_hit = true;
-      c.s_buf[b * kRowStride + s] = x0;
-      const int64_t ns = (int64_t)c.kb * 32 + s;
-      atomicAdd(&a.count[(int64_t)c.t * c.L + p], 1);
-      atomicAdd(&a.density[(int64_t)c.t * a.n_pad + ns], 1);
-      if (a.hit_count) {
-        const unsigned long long slot = atomicAdd(a.hit_count, 1ull);
-        if (a.hits && (int64_t)slot < a.hits_cap) {
-          HitRec rec; rec.task = c.t; rec.seq = (int32_t)ns; rec.pos = p; rec.x0 = x0;
-          a.hits[slot] = rec;
-        }
-      }
+    float x_first, x_task;
+    exact_x0(c, s, p - c.padl, x_first, x_task);
+    if (x_task > 0.0f) {
+      hit = true;
+      publish_match(a, c, c.t, c.s_buf, b, s, p, x_task);
+    }
+    if (c.t2 >= 0 && x_first > 0.0f) {
+      hit2 = true;
+      publish_match(a, c, c.t2, c.s_buf2, b, s, p, x_first);
     }
   }
-  return __any_sync(0xffffffffu, any_hit);
+  return (__any_sync(0xffffffffu, hit) ? 1u : 0u) | (__any_sync(0xffffffffu, hit2) ? 2u : 0u);
 }
 
-// Phase B of one 32-position chunk: blur, row sums, fp16 split, tiled store; lane = (kc, rsub).
-__device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, int base, bool chunk_nz, int lane) {
+// Phase B of one 32-position chunk that holds (or borders) matches: blur, row sums, fp16 split, tiled
+// store of the non-zero 16-byte pieces; lane = (kc, rsub).  Chunks without any match store nothing.
+__device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, int t, const float* s_buf, int base,
+                                         int lane) {
   const unsigned full = 0xffffffffu;
   const int kc = lane & 3, rsub = lane >> 2;
   const int mg = c.mg, L = c.L;
   const int k = 1 + 2 * mg;
   const float kf = (float)k;
+  const int64_t tile_stride = c.tile_stride;
+  uint8_t* const x_base = c.x_base;
 #pragma unroll 1
   for (int it = 0; it < 4; ++it) {
     const int rl = rsub + 8 * it;
     const int p = base + rl;
-    const bool valid = p < L;
+    const bool valid = p >= 0 && p < L;
     uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
-    if (chunk_nz) {                    // warp uniform; most chunks hold no match at all
-      const bool interior = valid && p >= mg && p <= L - 1 - mg;   // core.py:79-91 zero edges
-      float xb[8];
+    const bool interior = valid && p >= mg && p <= L - 1 - mg;   // core.py:79-91 zero edges
+    float xb[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) xb[q] = 0.0f;
-      if (interior) {
-        const float* row = c.s_buf + rl * kRowStride + kc * 8;  // buffer row rl+d <-> position p-mg+d
-        float4 u0 = *reinterpret_cast<const float4*>(row);
-        float4 u1 = *reinterpret_cast<const float4*>(row + 4);
-        xb[0] = u0.x; xb[1] = u0.y; xb[2] = u0.z; xb[3] = u0.w;
-        xb[4] = u1.x; xb[5] = u1.y; xb[6] = u1.z; xb[7] = u1.w;
+    for (int q = 0; q < 8; ++q) xb[q] = 0.0f;
+    if (interior) {
+      const float* row = s_buf + rl * kRowStride + kc * 8;  // buffer row rl+d <-> position p-mg+d
+      float4 u0 = *reinterpret_cast<const float4*>(row);
+      float4 u1 = *reinterpret_cast<const float4*>(row + 4);
+      xb[0] = u0.x; xb[1] = u0.y; xb[2] = u0.z; xb[3] = u0.w;
+      xb[4] = u1.x; xb[5] = u1.y; xb[6] = u1.z; xb[7] = u1.w;
 #pragma unroll 1
-        for (int d = 1; d < k; ++d) {
-          u0 = *reinterpret_cast<const float4*>(row + d * kRowStride);
-          u1 = *reinterpret_cast<const float4*>(row + d * kRowStride + 4);
-          xb[0] = __fadd_rn(xb[0], u0.x); xb[1] = __fadd_rn(xb[1], u0.y);
-          xb[2] = __fadd_rn(xb[2], u0.z); xb[3] = __fadd_rn(xb[3], u0.w);
-          xb[4] = __fadd_rn(xb[4], u1.x); xb[5] = __fadd_rn(xb[5], u1.y);
-          xb[6] = __fadd_rn(xb[6], u1.z); xb[7] = __fadd_rn(xb[7], u1.w);
-        }
-        if (k > 1) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (xb[q] != 0.0f) xb[q] = __fdiv_rn(xb[q], kf);   // (0 / k takes the slow division path)
-        }
+      for (int d = 1; d < k; ++d) {
+        u0 = *reinterpret_cast<const float4*>(row + d * kRowStride);
+        u1 = *reinterpret_cast<const float4*>(row + d * kRowStride + 4);
+        xb[0] = __fadd_rn(xb[0], u0.x); xb[1] = __fadd_rn(xb[1], u0.y);
+        xb[2] = __fadd_rn(xb[2], u0.z); xb[3] = __fadd_rn(xb[3], u0.w);
+        xb[4] = __fadd_rn(xb[4], u1.x); xb[5] = __fadd_rn(xb[5], u1.y);
+        xb[6] = __fadd_rn(xb[6], u1.z); xb[7] = __fadd_rn(xb[7], u1.w);
       }
-      // row sums over this k-block's 32 sequences (float64), reduced over the 4 kc lanes
-      double sx = 0.0, sxx = 0.0, sxz = 0.0;
-      bool nz = false;
+      if (k > 1) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) nz |= xb[q] != 0.0f;
-      if (nz) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const double v = (double)xb[q];
-          sx += v; sxx += v * v; sxz += v * (double)c.s_z[kc * 8 + q];
-        }
-      }
-      if (__any_sync(full, nz)) {
-        sx += __shfl_xor_sync(full, sx, 1);   sx += __shfl_xor_sync(full, sx, 2);
-        sxx += __shfl_xor_sync(full, sxx, 1); sxx += __shfl_xor_sync(full, sxx, 2);
-        sxz += __shfl_xor_sync(full, sxz, 1); sxz += __shfl_xor_sync(full, sxz, 2);
-        if (kc == 0 && valid && sxx != 0.0) {
-          double* rs = a.rowstats + ((int64_t)c.t * L + p) * 3;
-          atomicAdd(rs + 0, sx); atomicAdd(rs + 1, sxx); atomicAdd(rs + 2, sxz);
-        }
-      }
-      if (nz) {
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          __half h0, l0, h1, l1;
-          split_half(xb[2 * q] * MEPP_X_SCALE, h0, l0);
-          split_half(xb[2 * q + 1] * MEPP_X_SCALE, h1, l1);
-          h[q] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-          l[q] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-        }
-        vh = make_uint4(h[0], h[1], h[2], h[3]);
-        vl = make_uint4(l[0], l[1], l[2], l[3]);
+        for (int q = 0; q < 8; ++q)
+          if (xb[q] != 0.0f) xb[q] = __fdiv_rn(xb[q], kf);   // (0 / k takes the slow division path)
       }
     }
-    if (valid) {
-      const int r = c.t * L + p;                       // global row (< 2^31, checked on the host)
-      uint8_t* tile = c.x_base + (int64_t)(r >> 7) * c.tile_stride;
-      uint8_t* dst = tile + ((kc * kBlockM + (r & 127)) << 4);
+    // row sums over this k-block's 32 sequences (float64), reduced over the 4 kc lanes
+    double sx = 0.0, sxx = 0.0, sxz = 0.0;
+    bool nz = false;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) nz |= xb[q] != 0.0f;
+    if (nz) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const double v = (double)xb[q];
+        const int64_t n = (int64_t)c.kb * 32 + kc * 8 + q;     // (a padding sequence never holds a match)
+        const double z = (a.zhat && xb[q] != 0.0f && n < a.N) ? (double)__ldg(a.zhat + n) : 0.0;
+        sx += v; sxx += v * v; sxz += v * z;
+      }
+    }
+    if (__any_sync(full, nz)) {
+      sx += __shfl_xor_sync(full, sx, 1);   sx += __shfl_xor_sync(full, sx, 2);
+      sxx += __shfl_xor_sync(full, sxx, 1); sxx += __shfl_xor_sync(full, sxx, 2);
+      sxz += __shfl_xor_sync(full, sxz, 1); sxz += __shfl_xor_sync(full, sxz, 2);
+      if (kc == 0 && valid && sxx != 0.0) {
+        double* rs = a.rowstats + ((int64_t)t * L + p) * 3;
+        atomicAdd(rs + 0, sx); atomicAdd(rs + 1, sxx); atomicAdd(rs + 2, sxz);
+      }
+    }
+    if (nz) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        __half h0, l0, h1, l1;
+        split_half(xb[2 * q] * MEPP_X_SCALE, h0, l0);
+        split_half(xb[2 * q + 1] * MEPP_X_SCALE, h1, l1);
+        h[q] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        l[q] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+      vh = make_uint4(h[0], h[1], h[2], h[3]);
+      vl = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    if (nz && valid) {   // only pieces that hold a non-zero value are stored: the operand is all-zero on entry
+      const int r = t * L + p;                         // global row (< 2^31, checked on the host)
+      uint8_t* dst = x_base + (int64_t)(r >> 7) * tile_stride + ((kc * kBlockM + (r & 127)) << 4);
       *reinterpret_cast<uint4*>(dst) = vh;
       *reinterpret_cast<uint4*>(dst + kChunks * kBlockM * 16) = vl;
-      if ((vh.x | vh.y | vh.z | vh.w | vl.x | vl.y | vl.z | vl.w) != 0u) {  // rare: mark the K=16 block as non-zero
-        const int bit = 2 * c.kb + (kc >> 1);
-        atomicOr(c.flags + (int64_t)(r >> 7) * c.FW + (bit >> 5), 1u << (bit & 31));
-      }
+      const int bit = 2 * c.kb + (kc >> 1);            // mark the K=16 block as non-zero
+      atomicOr(c.flags + (int64_t)(r >> 7) * c.FW + (bit >> 5), 1u << (bit & 31));
     }
   }
 }
 
-// Pair-slot lookup: slot T covers taps 2T, 2T+1 = bits [6T, 6T+6) of the window's symbol stream
-// (w_lo = the stream word holding bit 6T, w_hi = the next word, only used by the two slots that
-// straddle a word).  `qbase` is the 256-byte aligned shared address of the task's 16 x 256-byte
-// tables, so the same LOP3 that masks the 6-bit index ORs the table base in (slot offset = LDS immediate).
-template <int T, int U>
-__device__ __forceinline__ uint32_t slot(uint32_t qbase, const uint32_t (&r)[6]) {
-  constexpr int bit = 6 * T + 3 * U;       // window U bases ahead of the register file's origin
-  constexpr int word = bit / 32, off = bit % 32;
+// Shared-memory address of the pair-table entry selected by the two symbols at bits [3K, 3K+6) of the
+// shift register: (index << 2) | table base.  `qbase` is the 256-byte aligned shared address of the
+// unit's tables (slot T = 256 bytes at qbase + 256 T, the slot offset goes into the LDS immediate), so the
+// LOP3 that masks the 6-bit index also ORs the base in.
+template <int K>
+__device__ __forceinline__ uint32_t pair_addr(uint32_t qbase, const uint32_t (&r)[6]) {
+  constexpr int bit = 3 * K, word = bit / 32, off = bit % 32;
   uint32_t v;
   if constexpr (off + 6 > 32) v = __funnelshift_r(r[word], r[word + 1], off - 2);
   else if constexpr (off >= 2) v = r[word] >> (off - 2);
   else v = r[word] << (2 - off);
-  const uint32_t addr = (v & 0xFCu) | qbase;
+  return (v & 0xFCu) | qbase;
+}
+template <int K0, int K1>
+__device__ __forceinline__ void pair_addrs(uint32_t qbase, const uint32_t (&r)[6], uint32_t (&A)[kAddr]) {
+  if constexpr (K0 < K1) {
+    A[K0] = pair_addr<K0>(qbase, r);
+    pair_addrs<K0 + 1, K1>(qbase, r, A);
+  }
+}
+template <int T>
+__device__ __forceinline__ uint32_t lds_slot(uint32_t addr) {
   uint32_t x;
   asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(x) : "r"(addr), "n"(T * 256));
   return x;
 }
-
-// Pre-filter sum of the window U bases ahead of the register file's origin (np = pair slots in use).
-template <int U>
-__device__ __forceinline__ uint32_t window_sum(uint32_t qbase, uint32_t qinit, int np, const uint32_t (&r)[6]) {
-  uint32_t sum = qinit + slot<0, U>(qbase, r) + slot<1, U>(qbase, r) + slot<2, U>(qbase, r);
+// Slots [T0, T1) of the eight windows of a step.  Window U slot T reads taps U+2T, U+2T+1, i.e. the
+// pair index at bits [3(U+2T), +6): the same index serves window U slot T and window U+2 slot T-1, so a
+// step extracts 2 np + 6 indices for its 8 np lookups.  One basic block of independent loads.
+template <int T0, int T1>
+__device__ __forceinline__ void add_slots(const uint32_t (&A)[kAddr], uint32_t (&s)[kGroup]) {
+  if constexpr (T0 < T1) {
+    s[0] += lds_slot<T0>(A[2 * T0 + 0]); s[1] += lds_slot<T0>(A[2 * T0 + 1]);
+    s[2] += lds_slot<T0>(A[2 * T0 + 2]); s[3] += lds_slot<T0>(A[2 * T0 + 3]);
+    s[4] += lds_slot<T0>(A[2 * T0 + 4]); s[5] += lds_slot<T0>(A[2 * T0 + 5]);
+    s[6] += lds_slot<T0>(A[2 * T0 + 6]); s[7] += lds_slot<T0>(A[2 * T0 + 7]);
+    add_slots<T0 + 1, T1>(A, s);
+  }
+}
+template <int T0, int T1>
+__device__ __forceinline__ void ladder_step(uint32_t qbase, const uint32_t (&r)[6], uint32_t (&A)[kAddr],
+                                            uint32_t (&s)[kGroup]) {
+  pair_addrs<(T0 == 0 ? 0 : 2 * T0 + 6), 2 * T1 + 6>(qbase, r, A);
+  add_slots<T0, T1>(A, s);
+}
+// The eight packed window sums of a step (np = pair slots in use); the slot-count ladder is walked once for
+// all eight windows.
+__device__ __forceinline__ void window_sums(uint32_t qbase, uint32_t qinit, int np, const uint32_t (&r)[6],
+                                            uint32_t (&s)[kGroup]) {
+  uint32_t A[kAddr];
+#pragma unroll
+  for (int u = 0; u < kGroup; ++u) s[u] = qinit;
+  ladder_step<0, 3>(qbase, r, A, s);
   if (np > 3) {
-    sum += slot<3, U>(qbase, r) + slot<4, U>(qbase, r);
+    ladder_step<3, 5>(qbase, r, A, s);
     if (np > 5) {
-      sum += slot<5, U>(qbase, r);
+      ladder_step<5, 6>(qbase, r, A, s);
       if (np > 6) {
-        sum += slot<6, U>(qbase, r) + slot<7, U>(qbase, r);
+        ladder_step<6, 8>(qbase, r, A, s);
         if (np > 8) {
-          sum += slot<8, U>(qbase, r) + slot<9, U>(qbase, r) + slot<10, U>(qbase, r);
-          if (np > 11)
-            sum += slot<11, U>(qbase, r) + slot<12, U>(qbase, r) + slot<13, U>(qbase, r) +
-                   slot<14, U>(qbase, r) + slot<15, U>(qbase, r);
+          ladder_step<8, 11>(qbase, r, A, s);
+          if (np > 11) ladder_step<11, 16>(qbase, r, A, s);
         }
       }
     }
+  }
+}
+// One window at the register file's origin (tail of the last chunk only).
+__device__ __noinline__ uint32_t window_sum1(uint32_t qbase, uint32_t qinit, int np, uint32_t r0, uint32_t r1,
+                                             uint32_t r2, uint32_t r3) {
+  uint32_t sum = qinit;
+#pragma unroll 1
+  for (int T = 0; T < np; ++T) {
+    const uint32_t idx = r0 & 63u;
+    uint32_t x;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(qbase + (uint32_t)T * 256u + idx * 4u));
+    sum += x;
+    r0 = __funnelshift_r(r0, r1, 6); r1 = __funnelshift_r(r1, r2, 6); r2 = __funnelshift_r(r2, r3, 6); r3 >>= 6;
   }
   return sum;
 }
@@ -250,39 +327,50 @@ __device__ __forceinline__ void advance(uint32_t (&r)[6]) {
   r[4] = __funnelshift_r(r[4], r[5], BITS); r[5] >>= BITS;
 }
 
-__device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const int kb,
-                                          const uint32_t* __restrict__ s_sym, float2* __restrict__ s_lut,
-                                          uint32_t* __restrict__ s_qtab, float* __restrict__ s_buf,
-                                          uint16_t* __restrict__ s_queue, const float* __restrict__ s_z,
-                                          TaskCtx* __restrict__ s_ctx, const int lane) {
+__device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const int t2, const int kb,
+                                          uint32_t* __restrict__ s_qtab, float2* __restrict__ s_lut,
+                                          float* __restrict__ s_buf,
+                                          float* __restrict__ s_buf2, uint16_t* __restrict__ s_queue,
+                                          uint32_t* __restrict__ s_ring, TaskCtx* __restrict__ s_ctx,
+                                          const int lane) {
   const unsigned full = 0xffffffffu;
   const int L = a.L, mg = a.margin;
   const int m = a.mlen[t];
   const int np = (m + 1) >> 1;           // pair slots in use
+  // the slot-count ladder of window_sums reads whole buckets: 3, 5, 6, 8, 11 or 16 slots
+  const int nslot = np <= 3 ? 3 : np <= 5 ? 5 : np <= 6 ? 6 : np <= 8 ? 8 : np <= 11 ? 11 : 16;
+  if (nslot > a.qslots) __trap();        // contract of mepp_scan: max_motif_len bounds every task
   const int padl = (m - 1) / 2;          // motif_layers.py:99-101
   const int n_valid = L - m + 1;         // 'valid' convolution outputs
   const bool real = (int64_t)kb * 32 + lane < a.N;
+  const int nbuf = 32 + 2 * mg;
 
-  const float2* g_lut = reinterpret_cast<const float2*>(a.lut) + (size_t)t * (MEPP_MAX_MOTIF_LEN * 4);
-  for (int i = lane; i < MEPP_MAX_MOTIF_LEN * 4; i += 32) s_lut[i] = g_lut[i];
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.qtab + (size_t)t * 1024);
     uint4* dst = reinterpret_cast<uint4*>(s_qtab);
-    for (int i = lane; i < 256; i += 32) dst[i] = src[i];
+    for (int i = lane; i < nslot * 16; i += 32) dst[i] = __ldg(src + i);   // (unused slots are zero)
+    const float2* g_lut = reinterpret_cast<const float2*>(a.lut) + (size_t)t * (MEPP_MAX_MOTIF_LEN * 4);
+    for (int i = lane; i < m * 4; i += 32) s_lut[i] = __ldg(g_lut + i);
   }
+  for (int b = 0; b < nbuf; ++b) s_buf[b * kRowStride + lane] = 0.0f;
+  if (t2 >= 0)
+    for (int b = 0; b < nbuf; ++b) s_buf2[b * kRowStride + lane] = 0.0f;
   // qinit: per 16-bit half (0x8000 - pass bound), so "sum reaches the bound" <=> bit 15 of the half is set.
   // Padding sequences never produce candidates.
   const uint32_t qinit = real ? a.qthr[t * 2 + 0] : 0u;
-  __syncwarp();
-
+  const int64_t tile_stride = a.KB * (int64_t)kATileBytes;
+  uint8_t* const x_base = a.x_planes + (int64_t)kb * kATileBytes;
   if (lane == 0) {
     TaskCtx w;
-    w.s_lut = s_lut; w.s_sym = s_sym; w.s_buf = s_buf; w.s_z = s_z; w.s_queue = s_queue;
-    w.t = t; w.kb = kb; w.m = m; w.padl = padl; w.mg = mg; w.L = L; w.strideS = a.strideS;
+    w.s_lut = s_lut;
+    w.g_sym = a.sym_T + (int64_t)kb * 32;
+    w.s_buf = s_buf; w.s_buf2 = s_buf2; w.s_queue = s_queue;
+    w.n_pad = a.n_pad;
+    w.t = t; w.t2 = t2; w.kb = kb; w.m = m; w.padl = padl; w.mg = mg; w.L = L;
     w.dual = a.nfilt[t] == 2;
     w.bias = a.bias[t];
-    w.tile_stride = a.KB * (int64_t)kATileBytes;
-    w.x_base = a.x_planes + (int64_t)kb * kATileBytes;
+    w.tile_stride = tile_stride;
+    w.x_base = x_base;
     w.FW = (int)flag_words(a.KB);
     w.flags = reinterpret_cast<unsigned int*>(
         a.x_planes + a_flags_offset(((int64_t)a.T * L + kBlockM - 1) / kBlockM, a.KB));
@@ -291,87 +379,130 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
   __syncwarp();
   const TaskCtx& c = *s_ctx;
 
-  const int nbuf = 32 + 2 * mg;
-  const uint32_t* my = s_sym + lane * a.strideS;
+  const uint32_t* my = a.sym_T + (int64_t)kb * 32 + lane;   // this lane's sequence: word w at my[w * n_pad]
+  const int64_t wstride = a.n_pad;
   const uint32_t qbase = (uint32_t)__cvta_generic_to_shared(s_qtab);
 
-  // 192-bit shift register over the symbol stream (window start at bit 0 of r[0]), advanced by four
-  // bases (12 bits) per group of four windows and refilled with three new words every 32 positions.
-  uint32_t r[6] = {my[0], my[1], my[2], my[3], my[4], my[5]};
-  int next_w = 6, left = 32;
+  // 192-bit shift register over the symbol stream (window start at bit 0 of r[0]), advanced by eight
+  // bases (24 bits) per step and refilled with three words every 32 windows.  The refill words travel
+  // global -> shared with cp.async one refill ahead (two stages of 3 x 32 words per warp; every lane
+  // copies and reads only its own words), so no register ever waits on a global load.
+  // The register starts `lead` (0..7) windows before the first real one, so that the first chunk holds a
+  // multiple of eight windows (32 + mg - padl + lead) like every later chunk (32): steps never straddle a
+  // refill and chunk rows stay aligned with the 8-row groups of the tiled stores.  The lead windows read
+  // zero bits in front of the stream; their candidates are dropped (rows below the first real one).
+  const int lead = (kGroup - ((32 + mg - padl) % kGroup)) % kGroup;
+  const int lsh = 3 * lead;              // left shift of the stream inside the register (0..21 bits)
+  uint32_t r[6], carry;
+  {
+    uint32_t w[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w[k] = __ldg(my + (int64_t)k * wstride);
+    r[0] = w[0] << lsh;
+#pragma unroll
+    for (int k = 1; k < 6; ++k) r[k] = __funnelshift_l(w[k - 1], w[k], lsh);
+    carry = w[5];
+  }
+  const uint32_t* pnext = my + 6 * wstride;
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(s_ring + lane);
+  uint32_t stage = 0u;                   // byte offset of the stage holding the next refill (0 / 384)
+  auto prefetch = [&](uint32_t st) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring0 + st + (uint32_t)k * 128u),
+                   "l"(pnext + (int64_t)k * wstride) : "memory");
+    pnext += 3 * wstride;
+  };
+  prefetch(0u);
+  int left = 32;
   int q_head = 0, q_tail = 0;            // warp-uniform ring indices
-  bool carry_nz = false;                 // previous chunk left non-zero x0 in the carried rows
+  unsigned dcar = 0u, dbody = 0u;        // staging rows [0, 2 mg) / [2 mg, nbuf) may hold non-zero x0 (bit 1: twin)
 
+  // Chunk origin: the first chunk starts e positions before the sequence so that it holds a multiple of
+  // eight windows (32 + mg - padl - e); every later chunk holds 32, so steps never straddle a refill.
+  const int e = (((mg - padl) % kGroup) + kGroup) % kGroup;
   for (int base = 0; base < L; base += 32) {
     int b_start = 0;
     if (base != 0) {
-      // carry the last 2*margin rows of the previous chunk to the front
-      for (int b = 0; b < 2 * mg; ++b) s_buf[b * kRowStride + lane] = s_buf[(32 + b) * kRowStride + lane];
       b_start = 2 * mg;
+      // staging rows: carry the last 2*margin rows to the front, clear the rest (only what can be non-zero)
+#pragma unroll 1
+      for (unsigned bit = 1u; bit <= (t2 >= 0 ? 2u : 1u); bit <<= 1) {
+        float* buf = bit == 1u ? s_buf : s_buf2;
+        if (dbody & bit) {
+          for (int b = 0; b < 2 * mg; ++b) buf[b * kRowStride + lane] = buf[(32 + b) * kRowStride + lane];
+          for (int b = 2 * mg; b < nbuf; ++b) buf[b * kRowStride + lane] = 0.0f;
+          dcar |= bit; dbody &= ~bit;
+        } else if (dcar & bit) {
+          for (int b = 0; b < 2 * mg; ++b) buf[b * kRowStride + lane] = 0.0f;
+          dcar &= ~bit;
+        }
+      }
     }
-    for (int b = b_start; b < nbuf; ++b) s_buf[b * kRowStride + lane] = 0.0f;
-    bool new_nz = false;
     // ---- phase A: integer pre-filter over positions base-mg+b, candidates queued ----
     // window starts i = base - mg + b - padl; only 0 <= i < n_valid are real windows
     const int i_first = base - mg + b_start - padl;
-    const int b_lo = b_start + (i_first < 0 ? -i_first : 0);
+    const int b_lo = b_start + (i_first < 0 ? -i_first : 0);   // first real window of the chunk
+    int b = base == 0 ? b_lo - lead : b_lo;
     int b_hi = nbuf;
     {
       const int i_end = base - mg + nbuf - padl;      // exclusive
       if (i_end > n_valid) b_hi -= i_end - n_valid;
     }
-    auto refill = [&]() { r[3] = my[next_w]; r[4] = my[next_w + 1]; r[5] = my[next_w + 2]; next_w += 3; left = 32; };
-    // queue the candidates of buffer row b (ballot `bal`), flushing the ring whenever 32 are pending
-    auto push = [&](unsigned bal, bool cand, int b) {
+    auto refill = [&]() {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      uint32_t n[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(n[k]) : "r"(ring0 + stage + (uint32_t)k * 128u) : "memory");
+      r[3] = __funnelshift_l(carry, n[0], lsh); r[4] = __funnelshift_l(n[0], n[1], lsh);
+      r[5] = __funnelshift_l(n[1], n[2], lsh);
+      carry = n[2];
+      stage ^= 384u;
+      prefetch(stage);
+      left = 32;
+    };
+    // queue the candidates of buffer row bb (ballot `bal`), flushing the ring whenever 32 are pending
+    auto push = [&](unsigned bal, bool cand, int bb) {
       if (cand) {
         const int slot_i = q_tail + __popc(bal & ((1u << lane) - 1u));
-        s_queue[slot_i & (kQueue - 1)] = (uint16_t)((lane << 8) | b);
+        s_queue[slot_i & (kQueue - 1)] = (uint16_t)((lane << 8) | bb);
       }
       q_tail += __popc(bal);
-      if (q_tail - q_head >= 32) { new_nz |= flush_candidates(a, c, q_head, 32, base, lane); q_head += 32; }
+      if (q_tail - q_head >= 32) { dbody |= flush_candidates(a, c, q_head, 32, base, lane); q_head += 32; }
     };
-    int b = b_lo;
-    // scalar steps until the refill counter is a multiple of 4, groups of 4 windows, scalar tail
 #pragma unroll 1
-    for (; b < b_hi && (left & 3) != 0; ++b) {
-      const bool cand = (window_sum<0>(qbase, qinit, np, r) & 0x80008000u) != 0u;
-      advance<3>(r);
-      if (--left == 0) refill();
-      const unsigned bal = __ballot_sync(full, cand);
-      if (bal != 0u) push(bal, cand, b);
-    }
-#pragma unroll 1
-    for (; b + 4 <= b_hi; b += 4) {
-      // four independent windows read the same registers at offsets 0, 3, 6, 9 bits; their pass bits
-      // (bit 15 / 31 of each packed sum) are merged into one word: window u lands on bits 15-u and 31-u
-      const uint32_t cb = (window_sum<0>(qbase, qinit, np, r) & 0x80008000u) |
-                          ((window_sum<1>(qbase, qinit, np, r) & 0x80008000u) >> 1) |
-                          ((window_sum<2>(qbase, qinit, np, r) & 0x80008000u) >> 2) |
-                          ((window_sum<3>(qbase, qinit, np, r) & 0x80008000u) >> 3);
-      advance<12>(r);
-      left -= 4;
+    for (; b + kGroup <= b_hi; b += kGroup) {
+      uint32_t s[kGroup];
+      window_sums(qbase, qinit, np, r, s);
+      advance<3 * kGroup>(r);
+      left -= kGroup;
       if (left == 0) refill();
-      if (__any_sync(full, cb != 0u)) {
+      // pass bit = bit 15 / 31 of a packed sum
+      const uint32_t any = (s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) & 0x80008000u;
+      if (__any_sync(full, any != 0u)) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool cand = (cb & (0x80008000u >> u)) != 0u;
+        for (int u = 0; u < kGroup; ++u) {
+          const bool cand = (s[u] & 0x80008000u) != 0u;
           const unsigned bal = __ballot_sync(full, cand);
-          if (bal != 0u) push(bal, cand, b + u);
+          if (bal != 0u && b + u >= b_lo) push(bal, cand, b + u);
         }
       }
     }
 #pragma unroll 1
-    for (; b < b_hi; ++b) {
-      const bool cand = (window_sum<0>(qbase, qinit, np, r) & 0x80008000u) != 0u;
+    for (; b < b_hi; ++b) {                       // fewer than eight windows left: end of the sequence
+      const bool cand = (window_sum1(qbase, qinit, np, r[0], r[1], r[2], r[3]) & 0x80008000u) != 0u;
       advance<3>(r);
       if (--left == 0) refill();
       const unsigned bal = __ballot_sync(full, cand);
-      if (bal != 0u) push(bal, cand, b);
+      if (bal != 0u && b >= b_lo) push(bal, cand, b);
     }
-    if (q_tail != q_head) { new_nz |= flush_candidates(a, c, q_head, q_tail - q_head, base, lane); q_head = q_tail; }
+    if (q_tail != q_head) { dbody |= flush_candidates(a, c, q_head, q_tail - q_head, base, lane); q_head = q_tail; }
     __syncwarp();
-    store_chunk(a, c, base, carry_nz | new_nz, lane);
-    carry_nz = new_nz;
+    // ---- phase B: blur + split + store, only for chunks that hold or border a match ----
+    const unsigned nzb = dcar | dbody;
+    if (nzb & 1u) store_chunk(a, c, t, s_buf, base, lane);
+    if (nzb & 2u) store_chunk(a, c, t2, s_buf2, base, lane);
     __syncwarp();
   }
 }
@@ -381,47 +512,92 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = blockIdx.x;
   const int nbuf = 32 + 2 * a.margin;
-  // carve shared memory (the filter tables come first: the OR-merged index needs 256-byte alignment)
+  const int nb = a.units ? 2 : 1;                                                       // twin staging buffers
+  // carve shared memory (the pair tables come first: the OR-merged index needs 256-byte alignment)
   uint8_t* sm = smem_raw + ((256u - (uint32_t)(__cvta_generic_to_shared(smem_raw) & 255u)) & 255u);
-  uint32_t* s_qtabs = reinterpret_cast<uint32_t*>(sm);                                  // [warps][1024]
-  float* s_bufs = reinterpret_cast<float*>(s_qtabs + kScanWarps * 1024);                // [warps][nbuf][36]
-  float2* s_luts = reinterpret_cast<float2*>(s_bufs + kScanWarps * nbuf * kRowStride);  // [warps][128]
-  uint32_t* s_sym = reinterpret_cast<uint32_t*>(s_luts + kScanWarps * MEPP_MAX_MOTIF_LEN * 4);
-  float* s_z = reinterpret_cast<float*>(s_sym + 32 * a.strideS);                        // [32]
-  uint16_t* s_queues = reinterpret_cast<uint16_t*>(s_z + 32);                           // [warps][kQueue]
-
-  for (int idx = threadIdx.x; idx < a.W3 * 32; idx += blockDim.x) {
-    const int s = idx & 31, w = idx >> 5;
-    s_sym[s * a.strideS + w] = a.sym_T[(int64_t)w * a.n_pad + (int64_t)kb * 32 + s];
-  }
-  if (threadIdx.x < 32) {
-    const int64_t n = (int64_t)kb * 32 + threadIdx.x;
-    s_z[threadIdx.x] = (a.zhat && n < a.N) ? a.zhat[n] : 0.0f;
-  }
-  __syncthreads();
-
-  const int t = blockIdx.y * kScanWarps + warp;
-  if (t >= a.T) return;
-  float* s_buf = s_bufs + warp * nbuf * kRowStride;
-  float2* s_lut = s_luts + warp * MEPP_MAX_MOTIF_LEN * 4;
-  uint32_t* s_qtab = s_qtabs + warp * 1024;
-  uint16_t* s_queue = s_queues + warp * kQueue;
+  uint32_t* s_qtabs = reinterpret_cast<uint32_t*>(sm);                                  // [warps][qslots * 64]
+  float* s_bufs = reinterpret_cast<float*>(s_qtabs + kScanWarps * a.qslots * 64);       // [warps][nb][nbuf][36]
+  uint32_t* s_rings = reinterpret_cast<uint32_t*>(s_bufs + kScanWarps * nb * nbuf * kRowStride);   // [warps][2][3][32]
+  float2* s_luts = reinterpret_cast<float2*>(s_rings + kScanWarps * 192);                         // [warps][qslots * 8]
+  uint16_t* s_queues = reinterpret_cast<uint16_t*>(s_luts + kScanWarps * a.qslots * 8);           // [warps][kQueue]
   __shared__ TaskCtx s_ctxs[kScanWarps];
-  scan_task(a, t, kb, s_sym, s_lut, s_qtab, s_buf, s_queue, s_z, &s_ctxs[warp], lane);
+
+  const int u = blockIdx.y * kScanWarps + warp;
+  if (u >= a.U) return;
+  const int t = a.units ? a.units[2 * u] : u;
+  const int t2 = a.units ? a.units[2 * u + 1] : -1;
+  float* s_buf = s_bufs + warp * nb * nbuf * kRowStride;
+  float* s_buf2 = s_buf + (nb - 1) * nbuf * kRowStride;
+  scan_task(a, t, t2, kb, s_qtabs + warp * a.qslots * 64, s_luts + warp * a.qslots * 8, s_buf, s_buf2, s_queues + warp * kQueue, s_rings + warp * 192,
+            &s_ctxs[warp], lane);
+}
+
+// Restores the all-zero state of the A operand after its consumer ran: every match (task, seq, pos) of the
+// list dirtied the 16-byte pieces of rows pos-margin .. pos+margin in its sequence's 8-column group (both
+// planes).  If the list overflowed (or there is none) the whole tile region is cleared instead.
+__global__ void x_planes_reset_kernel(uint8_t* __restrict__ x_planes, const HitRec* __restrict__ hits,
+                                      int64_t hits_cap, const unsigned long long* __restrict__ hit_count, int L,
+                                      int margin, int64_t KB, int64_t tile_bytes) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  const int64_t n_hits = hits ? (int64_t)*hit_count : -1;
+  if (n_hits < 0 || n_hits > hits_cap) {
+    uint4* p = reinterpret_cast<uint4*>(x_planes);
+    for (int64_t i = tid; i < tile_bytes / 16; i += nthr) p[i] = z4;
+    return;
+  }
+  const int k = 2 * margin + 1;
+  const int64_t tile_stride = KB * (int64_t)kATileBytes;
+  for (int64_t i = tid; i < n_hits * k; i += nthr) {
+    const HitRec h = hits[i / k];
+    const int p = h.pos - margin + (int)(i % k);
+    if (p < 0 || p >= L) continue;
+    const int r = h.task * L + p;
+    const int kb = h.seq >> 5, kc = (h.seq & 31) >> 3;
+    uint8_t* dst = x_planes + (int64_t)(r >> 7) * tile_stride + (int64_t)kb * kATileBytes +
+                   ((kc * kBlockM + (r & 127)) << 4);
+    *reinterpret_cast<uint4*>(dst) = z4;
+    *reinterpret_cast<uint4*>(dst + kChunks * kBlockM * 16) = z4;
+  }
 }
 
 }  // namespace mepp
 
+extern "C" int mepp_x_planes_reset(void* x_planes_dev, const void* hits_dev, int64_t hits_cap,
+                                   const unsigned long long* hit_count_dev, int64_t N, int L, int T, int margin,
+                                   void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(x_planes_dev != nullptr, "x_planes_reset: null pointer");
+  MEPP_REQUIRE(N > 0 && L > 0 && T > 0 && margin >= 0 && margin <= MEPP_MAX_MARGIN, "x_planes_reset: bad arguments");
+  MEPP_REQUIRE(hits_dev == nullptr || hit_count_dev != nullptr, "x_planes_reset: the match list needs its counter");
+  MEPP_REQUIRE(mepp_device_ok(), "x_planes_reset: no sm_100 CUDA device (no CPU fallback)");
+  cudaStream_t st = as_stream(stream);
+  const int64_t KB = mepp_pad32(N) / kBlockK;
+  const int64_t n_tiles_m = ((int64_t)T * L + kBlockM - 1) / kBlockM;
+  const int64_t tile_bytes = a_flags_offset(n_tiles_m, KB);
+  x_planes_reset_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<uint8_t*>(x_planes_dev),
+                                                 reinterpret_cast<const HitRec*>(hits_dev), hits_cap, hit_count_dev, L,
+                                                 margin, KB, tile_bytes);
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  MEPP_CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<uint8_t*>(x_planes_dev) + tile_bytes, 0,
+                                  (size_t)(n_tiles_m * flag_words(KB) * 4), st));
+  return 0;
+}
+
 extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
                          int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
                          const int32_t* mlen_dev, const int32_t* nfilt_dev, const uint32_t* qtab_dev,
-                         const uint32_t* qthr_dev, void* x_planes_dev, double* rowstats_dev, int32_t* count_dev,
+                         const uint32_t* qthr_dev, const int32_t* units_dev, int n_units, int max_motif_len,
+                         void* x_planes_dev, double* rowstats_dev, int32_t* count_dev,
                          int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
                          void* stream) {
   using namespace mepp;
   MEPP_REQUIRE(sym_T_dev && lut_dev && bias_dev && mlen_dev && nfilt_dev && qtab_dev && qthr_dev &&
                x_planes_dev && rowstats_dev && count_dev && density_dev, "scan: null pointer");
   MEPP_REQUIRE(N > 0 && L > 0 && T > 0, "scan: empty input");
+  MEPP_REQUIRE(units_dev == nullptr || (n_units > 0 && n_units <= T), "scan: bad unit list");
+  MEPP_REQUIRE(max_motif_len >= 0 && max_motif_len <= MEPP_MAX_MOTIF_LEN, "scan: max_motif_len outside [0, 32]");
   MEPP_REQUIRE((int64_t)T * L < (1LL << 31), "scan: T * L must be below 2^31");
   MEPP_REQUIRE(margin >= 0 && margin <= MEPP_MAX_MARGIN, "scan: margin must be in [0, 16]");
   MEPP_REQUIRE(hits_dev == nullptr || hit_count_dev != nullptr, "scan: hits need a hit counter");
@@ -432,18 +608,27 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
   a.N = N; a.n_pad = mepp_pad32(N); a.KB = a.n_pad / kBlockK;
   a.L = L; a.T = T; a.margin = margin;
   a.W3 = (int)mepp_sym_words(L);
-  a.strideS = a.W3 | 1;
+  {
+    const int np = max_motif_len > 0 ? (max_motif_len + 1) / 2 : MEPP_MAX_MOTIF_LEN / 2;
+    a.qslots = np <= 3 ? 3 : np <= 5 ? 5 : np <= 6 ? 6 : np <= 8 ? 8 : np <= 11 ? 11 : 16;   // whole ladder buckets
+  }
   a.lut = lut_dev; a.bias = bias_dev; a.mlen = mlen_dev; a.nfilt = nfilt_dev;
   a.qtab = qtab_dev; a.qthr = qthr_dev;
+  a.units = units_dev; a.U = units_dev ? n_units : T;
   a.x_planes = reinterpret_cast<uint8_t*>(x_planes_dev); a.rowstats = rowstats_dev;
   a.count = count_dev; a.density = density_dev;
   a.hits = reinterpret_cast<HitRec*>(hits_dev); a.hits_cap = hits_cap; a.hit_count = hit_count_dev;
   const int nbuf = 32 + 2 * margin;
-  size_t smem = sizeof(float) * kScanWarps * nbuf * kRowStride + sizeof(float2) * kScanWarps * MEPP_MAX_MOTIF_LEN * 4 +
-                sizeof(uint32_t) * kScanWarps * 1024 + sizeof(uint32_t) * 32 * a.strideS +
-                sizeof(float) * 32 + sizeof(uint16_t) * kScanWarps * kQueue + 256 /* table alignment */;
-  MEPP_REQUIRE(smem <= 200 * 1024, "scan: sequence too long for the shared-memory staging (L too large)");
+  size_t smem = sizeof(float) * kScanWarps * (units_dev ? 2 : 1) * nbuf * kRowStride +
+                sizeof(uint32_t) * kScanWarps * a.qslots * 64 + sizeof(uint16_t) * kScanWarps * kQueue +
+                sizeof(uint32_t) * kScanWarps * 192 + sizeof(float2) * kScanWarps * a.qslots * 8 +
+                256 /* table alignment */;
   MEPP_CUDA_CHECK(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    static int carveout = [] { const char* e = getenv("MEPP_SCAN_CARVEOUT"); return e ? atoi(e) : -2; }();
+    if (carveout >= -1)
+      MEPP_CUDA_CHECK(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+  }
   MEPP_CUDA_CHECK(cudaMemsetAsync(rowstats_dev, 0, sizeof(double) * 3 * (size_t)T * L, st));
   MEPP_CUDA_CHECK(cudaMemsetAsync(count_dev, 0, sizeof(int32_t) * (size_t)T * L, st));
   MEPP_CUDA_CHECK(cudaMemsetAsync(density_dev, 0, sizeof(int32_t) * (size_t)T * a.n_pad, st));
@@ -454,7 +639,7 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
     MEPP_CUDA_CHECK(cudaMemsetAsync(a.x_planes + a_flags_offset(n_tiles_m, a.KB), 0,
                                     (size_t)(n_tiles_m * flag_words(a.KB) * 4), st));
   }
-  dim3 grid((unsigned)a.KB, (unsigned)((T + kScanWarps - 1) / kScanWarps));
+  dim3 grid((unsigned)a.KB, (unsigned)((a.U + kScanWarps - 1) / kScanWarps));
   MEPP_REQUIRE(grid.y <= 65535, "scan: too many tasks in one call");
   scan_kernel<<<grid, kScanWarps * 32, smem, st>>>(a);
   MEPP_CUDA_CHECK(cudaGetLastError());

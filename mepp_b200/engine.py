@@ -80,6 +80,32 @@ class ProfileBatch:
         return X0
 
 
+def scan_units(tables):
+    """Pair every two-filter ('+/-') task with a one-filter task that has the same filter 0, bias and length
+    (the '+' orientation of the same motif: motif_layers.py:36-76 gives both the threshold of W): one pass of
+    the scan kernel then serves both.  Returns int32 (U, 2) rows (task scanned, twin or -1), or None when no
+    pair exists."""
+    singles = {}
+    for t, tb in enumerate(tables):
+        if tb['n_filters'] == 1:
+            key = (tb['m'], float(tb['bias']), tb['lut'][:, :, 0].tobytes())
+            singles.setdefault(key, []).append(t)
+    units, twinned = [], set()
+    for t, tb in enumerate(tables):
+        if tb['n_filters'] == 2:
+            cand = singles.get((tb['m'], float(tb['bias']), tb['lut'][:, :, 0].tobytes()))
+            if cand:
+                u = cand.pop(0)
+                twinned.add(u)
+                units.append((t, u))
+            else:
+                units.append((t, -1))
+    if not twinned:
+        return None
+    units.extend((t, -1) for t, tb in enumerate(tables) if tb['n_filters'] == 1 and t not in twinned)
+    return np.array(units, dtype=np.int32)
+
+
 class Engine:
     def __init__(self, device=None, mem_budget_bytes=32 << 30, max_group=512):
         torch = _torch()
@@ -98,6 +124,7 @@ class Engine:
         self.launches = 0   # kernels launched by this engine (bench.py reports it)
         self.timing = None  # set to {} to collect per-stage CUDA-event times (ms)
         self.fuse_correlation = True   # False: separate GEMM (S) + correlation kernels (tests / A-B runs)
+        self.share_scans = os.environ.get("MEPP_SHARE_SCANS", "1") != "0"   # '+' rides on the '+/-' pass of its motif
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -240,6 +267,7 @@ class Engine:
             # exposed finalisation of the last group stays small (4 measured best on cfg 2)
             n_groups = int(os.environ.get("MEPP_GROUPS", "4"))
             G = min(G, max(32, -(-T_all // n_groups)))
+        G += G & 1 if G < T_all else 0      # even: the ('+', '+/-') pair of a motif stays in one group
         groups = [(g0, min(g0 + G, T_all)) for g0 in range(0, T_all, G)]
         self.last_groups = len(groups)
         store = stats_host.alloc_positions(T_all, L, self.P)
@@ -283,6 +311,17 @@ class Engine:
         return ProfileBatch(list(range(T_all)), positions, density_all, self.scores, thr,
                             hit_counts=cat('hit_count'), hits=hits, r=r, n_seq=N)
 
+    def _reset_x_planes(self):
+        """Restore the all-zero state of the A operand the last scan wrote (match-list driven, see
+        mepp_x_planes_reset).  Deferred to the next use so that the operand can be inspected after profile()."""
+        p = getattr(self, '_x_pending', None)
+        if p is None:
+            return
+        self._x_pending = None
+        _lib.check(_lib.lib.mepp_x_planes_reset(_ptr(p['x']), _ptr(p['hits']), p['cap'], _ptr(p['hit_count']),
+                                                p['N'], p['L'], p['T'], p['margin'], self._stream()), "x_planes_reset")
+        self.launches += 1
+
     def _mark(self, prev, name):
         """CUDA-event stage timer on the launching stream (only when self.timing is a dict)."""
         if self.timing is None:
@@ -317,6 +356,7 @@ class Engine:
         T = len(tables)
         L, N, C_, P = self.L, self.N, self.C, self.P
         st = self._stream()
+        self._reset_x_planes()     # before any scratch buffer of the previous group is reused
         m_rows = T * L
         lut = np.stack([tb['lut'] for tb in tables]).astype(np.float32)
         bias = np.array([tb['bias'] for tb in tables], dtype=np.float32)
@@ -326,22 +366,26 @@ class Engine:
         qthr = np.stack([tb['qthr'] for tb in tables]).view(np.int32)
         lut_d, bias_d, mlen_d, nfilt_d, qtab_d, qthr_d = (self._to_dev(lut), self._to_dev(bias), self._to_dev(mlen),
                                                           self._to_dev(nfilt), self._to_dev(qtab), self._to_dev(qthr))
+        units = scan_units(tables) if self.share_scans else None
+        units_d = self._to_dev(units) if units is not None else None
+        n_units = len(units) if units is not None else 0
+        self.last_units = n_units if units is not None else T
         x_bytes = int(_lib.lib.mepp_x_planes_bytes(m_rows, self.n_pad))
         x_planes = self._buf('x_planes', x_bytes, torch.uint8, zero=True)
         rowstats = self._buf('rowstats', (m_rows, 3), torch.float64)
         count = self._buf('count', (T, L), torch.int32)
         density = self._buf('density', (T, self.n_pad), torch.int32)
         hit_count = self._buf('hit_count', (1,), torch.int64)
-        hits_d = None
-        cap = 0
-        if return_hits:
-            cap = int(hits_cap) if hits_cap else max(1 << 20, int(T * N * L * 2e-3))
-            hits_d = self._buf('hits', cap * 16, torch.uint8)
+        # the match list is always kept: it is also what restores the all-zero state of x_planes after the GEMM
+        cap = int(hits_cap) if hits_cap else max(1 << 20, int(T * N * L * 2e-3))
+        hits_d = self._buf('hits', cap * 16, torch.uint8)
         ev = self._mark(None, None)
         _lib.check(_lib.lib.mepp_scan(_ptr(self.sym_T), _ptr(self.zhat), N, L, T, int(margin),
                                       _ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), _ptr(qtab_d), _ptr(qthr_d),
-                                      _ptr(x_planes), _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap,
+                                      _ptr(units_d), n_units, int(mlen.max()), _ptr(x_planes), _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap,
                                       _ptr(hit_count), st), "scan")
+        # the scan stored only the non-zero pieces; the operand goes back to all-zero before its next use
+        self._x_pending = dict(x=x_planes, hits=hits_d, cap=cap, hit_count=hit_count, N=N, L=L, T=T, margin=int(margin))
         ev = self._mark(ev, 'scan')
         # tcgen05 GEMM with the correlation fused into its epilogue: r (m_rows, ldS) float32, S never reaches HBM
         r = self._buf('r', (m_rows, self.ldS), torch.float32)

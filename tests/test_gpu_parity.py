@@ -291,3 +291,60 @@ def test_heatmap_from_hits_equals_dense_block_max(cfg1):
             b = heatmap.compress_dense_to_pixels(X0, pw, ph)
             assert a.shape == b.shape and np.array_equal(a, b)
 
+
+
+def test_shared_scan_units_equal_separate_scans():
+    """'+' tasks ride on the '+/-' pass of the same motif (engine.scan_units); out-of-order pairs, unpaired
+    tasks and '-' tasks in the same call; results equal the one-scan-per-task path and the oracle."""
+    from mepp_b200 import synth
+    from mepp_b200.engine import scan_units
+    from mepp_b200 import motif_layers
+    ascii_u8, scores = synth.synth_sequences(257, 150, seed=31, n_rate=0.02)
+    perm = synth.synth_permutations(257, 11, seed=31)
+    m = synth.synth_motifs(4, seed=17, m_lo=5, m_hi=20)
+    tasks = [(m[0], '+'), (m[0], '+/-'), (m[1], '+/-'), (m[2], '-'), (m[3], '+'), (m[1], '+'), (m[2], '+/-')]
+    units = scan_units(motif_layers.scan_tables(tasks))
+    assert sorted(map(tuple, units.tolist())) == [(1, 0), (2, 5), (3, -1), (4, -1), (6, -1)]
+    eng = _engine().stage(ascii_u8, scores, perm)
+    assert eng.share_scans
+    shared = eng.profile(tasks, margin=3, return_hits=True, return_r=True)
+    assert eng.last_units == 5
+    eng.share_scans = False
+    separate = eng.profile(tasks, margin=3, return_hits=True, return_r=True)
+    assert eng.last_units == 7
+    assert np.array_equal(shared.hits, separate.hits)
+    assert np.array_equal(shared.density, separate.density)
+    assert np.allclose(shared.r, separate.r, rtol=1e-6, atol=1e-9)
+    codes = staging.ascii_to_codes(ascii_u8)
+    Y = staging.permuted_scores(scores, perm)
+    z = staging.gc_ratio_global(codes)
+    for t, (pwm, o) in enumerate(tasks):
+        orc = profile.profile_task(codes, Y, z, pwm, o, margin=3)
+        assert np.array_equal(shared.motif_score_matrix(t, 150).view(np.uint32), orc["X0"].view(np.uint32)), t
+        assert _r_close(shared.r[t], orc["r"]).all(), t
+
+
+def test_scan_is_deterministic_after_longer_motifs():
+    """Regression: the pair tables of a scan unit are staged in shared memory in whole ladder buckets (3, 5, 6, 8,
+    11, 16 slots); slots past the motif's own must be zero, not what an earlier, longer motif left there."""
+    from mepp_b200 import synth
+    rng = np.random.default_rng(77)
+    ascii_u8, scores = synth.synth_sequences(4096, 512, seed=8, n_rate=0.005)
+    perm = synth.synth_permutations(4096, 7, seed=8)
+    mk = lambda m: rng.dirichlet(np.full(4, 0.3), size=m).T
+    long_tasks = [(mk(32), '+/-') for _ in range(8)]
+    short_tasks = [(mk(m), o) for m in (13, 14, 9, 10, 11, 17, 21, 22) for o in ('+', '+/-')]
+    eng = _engine().stage(ascii_u8, scores, perm)
+    ref = None
+    for rep in range(3):
+        eng.profile(long_tasks, margin=2)                       # fills every table slot with non-zero entries
+        got = eng.profile(short_tasks, margin=2, return_hits=True)
+        if ref is None:
+            ref = got
+            codes = staging.ascii_to_codes(ascii_u8)
+            for t in (0, 1, 2, 3):
+                Wf, Wr, thr = profile.motif_weights(*short_tasks[t])
+                assert np.array_equal(got.motif_score_matrix(t, 512).view(np.uint32),
+                                      profile.scan(codes, Wf, Wr, thr).view(np.uint32))
+        else:
+            assert np.array_equal(got.hits, ref.hits), rep
