@@ -39,6 +39,7 @@ extern "C" {
 #define MEPP_B200_ABI_VERSION 1
 #define MEPP_MAX_MOTIF_LEN 32   /* taps held in a 64-bit code window */
 #define MEPP_MAX_MARGIN 16
+#define MEPP_ENTRY_LISTS 64     /* sub-lists of the sparse form of X (power of two) */
 #define MEPP_X_SCALE 256.0f     /* X is stored as 256*x in the fp16 planes (exact) */
 
 int         mepp_abi_version(void);
@@ -103,6 +104,12 @@ int mepp_build_y(const float* yhat_dev, const int32_t* perm_dev, const float* zh
  *             '+/-' task also yields the '+' task (x = relu of filter 0 alone).  Every task must appear
  *             exactly once, as a scanned task or as a twin; a twin's own tables are not read.
  *             NULL: every task is scanned on its own.
+ *   entries_dev   optional sparse form of X for mepp_profile_sparse: {int32 row, int32 seq, float x, pad}
+ *                 records, one per non-zero of the blurred score matrix, in MEPP_ENTRY_LISTS sub-lists of
+ *                 entry_cap / MEPP_ENTRY_LISTS records each (sub-list = k-block % MEPP_ENTRY_LISTS);
+ *                 entry_count_dev uint64[16 * MEPP_ENTRY_LISTS]: record count of sub-list j at [16 j] (a count
+ *                 may exceed the sub-list capacity: then use the tiled path),
+ *                 row_nnz_dev int32 [T*L + 1] non-zeros per row.  x_planes_dev may be NULL when given.
  *   max_motif_len  upper bound of mlen over the scanned tasks (sizes the shared-memory pair tables;
  *             a longer task traps); 0 = MEPP_MAX_MOTIF_LEN
  *   x_planes_dev  A operand (rows t*L+l).  Must be ALL-ZERO on entry (tiles and flag words): X is ~99.9 % zeros,
@@ -119,13 +126,32 @@ int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
               const uint32_t* qtab_dev, const uint32_t* qthr_dev, const int32_t* units_dev, int n_units,
               int max_motif_len,
               void* x_planes_dev, double* rowstats_dev, int32_t* count_dev, int32_t* density_dev,
-              void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev, void* stream);
+              void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
+              void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
+              void* stream);
 
 /* Restore the all-zero state of an A operand that mepp_scan(..., N, L, T, margin, ...) wrote, from the
  * match list of that call (every match dirties rows pos-margin..pos+margin of one 8-column group); a NULL
  * or overflowed list clears the whole operand instead.  Call after the operand's last consumer. */
 int mepp_x_planes_reset(void* x_planes_dev, const void* hits_dev, int64_t hits_cap,
                         const unsigned long long* hit_count_dev, int64_t N, int L, int T, int margin,
+                        void* stream);
+
+/* ------------------------------------------------------------------ K2s: sparse profile
+ * r = correlation(S = X . Y) like mepp_profile_corr_gemm, for X given as the scan's entry list: the
+ * records are binned by row and every row of S is gathered from the rows of Y (float32, row-major
+ * [n_pad][mepp_y_rows_ld(C)], built once per dataset by mepp_build_y_rows), float64 accumulation.
+ * Cost is proportional to the number of non-zeros of X (4 KB of L2 traffic each at P = 1000); the
+ * tensor-core GEMM below costs the same whatever X holds.  Nothing is written if the entry list
+ * overflowed (*entry_count_dev > entry_cap): the caller then takes the tiled path.
+ * work_dev: mepp_profile_sparse_work_bytes(m_rows, entry_cap) bytes; row_nnz_dev is consumed. */
+int64_t mepp_y_rows_ld(int C);
+int mepp_build_y_rows(const float* yhat_dev, const int32_t* perm_dev, int64_t N, int P, float* y_rows_dev,
+                      void* stream);
+int64_t mepp_profile_sparse_work_bytes(int64_t m_rows, int64_t entry_cap);
+int mepp_profile_sparse(const void* entries_dev, const unsigned long long* entry_count_dev, int64_t entry_cap,
+                        int32_t* row_nnz_dev, const float* y_rows_dev, const double* rowstats_dev,
+                        const double* colconst_dev, float* r_dev, int64_t ldr, int64_t m_rows, int C, void* work_dev,
                         void* stream);
 
 /* ------------------------------------------------------------------ K2: profile GEMM

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libmepp_b200.so")
 
 MAX_MOTIF_LEN = 32
 MAX_MARGIN = 16
+ENTRY_LISTS = 64          # MEPP_ENTRY_LISTS
 X_SCALE = 256.0
 
 if not os.path.exists(LIB_PATH):
@@ -41,7 +42,11 @@ SIGNATURES = {
     "mepp_pack_dna": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "mepp_build_y": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "mepp_scan": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
-                         _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+                         _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "mepp_y_rows_ld": (_i64, [_i32]),
+    "mepp_build_y_rows": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "mepp_profile_sparse_work_bytes": (_i64, [_i64, _i64]),
+    "mepp_profile_sparse": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     "mepp_x_planes_reset": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]),
     "mepp_profile_gemm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp]),
     "mepp_gemm_counters": (_i32, [C.POINTER(C.c_ulonglong), _i32]),

@@ -138,9 +138,41 @@ __global__ void y_colstats_kernel(const uint32_t* __restrict__ ysplit, const int
   }
 }
 
+// Row-major float32 copy of Y for the sparse profile path: y_rows[n][c] = hi + lo of the same fp16 split the
+// tiled operand holds (exactly representable in float32), zero in the padding rows / columns.
+__global__ void y_rows_kernel(const float* __restrict__ yhat, const int32_t* __restrict__ perm, int64_t N,
+                              int64_t n_pad, int C, int64_t ldY, float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = blockIdx.y;
+  if (c >= ldY) return;
+  float v = 0.0f;
+  if (c < C && n < N) {
+    const int64_t src = c == 0 ? n : (int64_t)perm[(c - 1) * N + n];
+    __half h, l;
+    split_half(yhat[src], h, l);
+    v = __half2float(h) + __half2float(l);
+  }
+  out[n * ldY + c] = v;
+}
+
 }  // namespace mepp
 
 extern "C" {
+
+int mepp_build_y_rows(const float* yhat_dev, const int32_t* perm_dev, int64_t N, int P, float* y_rows_dev,
+                      void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(yhat_dev && y_rows_dev, "build_y_rows: null pointer");
+  MEPP_REQUIRE(N > 0 && P >= 0 && (P == 0 || perm_dev), "build_y_rows: bad arguments");
+  MEPP_REQUIRE(mepp_device_ok(), "build_y_rows: no sm_100 CUDA device (no CPU fallback)");
+  const int C = 1 + P;
+  const int64_t ldY = mepp_y_rows_ld(C), n_pad = mepp_pad32(N);
+  MEPP_REQUIRE(n_pad <= 65535 * 1024LL, "build_y_rows: too many sequences");
+  dim3 grid((unsigned)((ldY + 255) / 256), (unsigned)n_pad);
+  y_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(yhat_dev, perm_dev, N, n_pad, C, ldY, y_rows_dev);
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 int mepp_pack_dna(const uint8_t* ascii_dev, int64_t N, int L, uint32_t* sym_T_dev, float* gc_dev, void* stream) {
   using namespace mepp;

@@ -33,6 +33,7 @@
 namespace mepp {
 
 struct HitRec { int32_t task, seq, pos; float x0; };
+struct XEntry { int32_t row, seq; float x; uint32_t pad; };   // one non-zero of the blurred score matrix
 
 constexpr int kScanWarps = 2;   // warps (= scan units) per CTA
 constexpr int kRowStride = 36;  // floats per position row of the x0 staging buffer (32 + 4 pad)
@@ -49,6 +50,9 @@ struct ScanArgs {
   const int32_t* units; int U;   // scan units: (task scanned, twin task fed by the same pass or -1); null = one per task
   uint8_t* x_planes; double* rowstats; int32_t* count; int32_t* density;
   HitRec* hits; int64_t hits_cap; unsigned long long* hit_count;
+  // sparse form of X (optional): MEPP_ENTRY_LISTS sub-lists of sub_cap records, list = k-block % lists (one
+  // counter per 128-byte line, so that the appends do not serialise on one L2 address)
+  XEntry* entries; int64_t sub_cap; unsigned long long* entry_count; int32_t* row_nnz;
 };
 
 // Per-warp (= per unit) state shared by the helper routines below.  The helpers are deliberately NOT
@@ -98,11 +102,8 @@ __device__ __forceinline__ void exact_x0(const TaskCtx& c, int s, int i, float& 
       a1 = __fadd_rn(a1, w.y);
     }
   };
-  int j = 0;
 #pragma unroll 1
-  for (; j + 4 <= m; j += 4) { tap(j); tap(j + 1); tap(j + 2); tap(j + 3); }
-#pragma unroll 1
-  for (; j < m; ++j) tap(j);
+  for (int j = 0; j < m; ++j) tap(j);
   float sc = __fadd_rn(a0, c.bias);
   x_first = fmaxf(sc, 0.0f);
   if (c.dual) sc = fmaxf(sc, __fadd_rn(a1, c.bias));
@@ -213,6 +214,36 @@ __device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, in
         double* rs = a.rowstats + ((int64_t)t * L + p) * 3;
         atomicAdd(rs + 0, sx); atomicAdd(rs + 1, sxx); atomicAdd(rs + 2, sxz);
       }
+      if (a.entries) {
+        // sparse form of X: one record per non-zero, appended to the k-block's sub-list in warp-sized batches
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cnt += xb[q] != 0.0f;
+        int pre = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(full, pre, o);
+          if (lane >= o) pre += v;
+        }
+        const int total = __shfl_sync(full, pre, 31);
+        const int list = c.kb & (MEPP_ENTRY_LISTS - 1);
+        unsigned long long slot0 = 0ull;
+        if (lane == 0) slot0 = atomicAdd(a.entry_count + list * 16, (unsigned long long)total);
+        slot0 = __shfl_sync(full, slot0, 0) + (unsigned long long)(pre - cnt);
+        if (cnt != 0) {
+          const int r = t * L + p;
+          atomicAdd(a.row_nnz + r, cnt);
+          uint4* dst = reinterpret_cast<uint4*>(a.entries + (int64_t)list * a.sub_cap);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (xb[q] != 0.0f) {
+              if ((int64_t)slot0 < a.sub_cap)
+                dst[slot0] = make_uint4((uint32_t)r, (uint32_t)(c.kb * 32 + kc * 8 + q), __float_as_uint(xb[q]), 0u);
+              ++slot0;
+            }
+          }
+        }
+      }
     }
     if (nz) {
       uint32_t h[4], l[4];
@@ -227,7 +258,7 @@ __device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, in
       vh = make_uint4(h[0], h[1], h[2], h[3]);
       vl = make_uint4(l[0], l[1], l[2], l[3]);
     }
-    if (nz && valid) {   // only pieces that hold a non-zero value are stored: the operand is all-zero on entry
+    if (nz && valid && a.x_planes) {   // only pieces that hold a non-zero value are stored: the operand is all-zero on entry
       const int r = t * L + p;                         // global row (< 2^31, checked on the host)
       uint8_t* dst = x_base + (int64_t)(r >> 7) * tile_stride + ((kc * kBlockM + (r & 127)) << 4);
       *reinterpret_cast<uint4*>(dst) = vh;
@@ -372,8 +403,8 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
     w.tile_stride = tile_stride;
     w.x_base = x_base;
     w.FW = (int)flag_words(a.KB);
-    w.flags = reinterpret_cast<unsigned int*>(
-        a.x_planes + a_flags_offset(((int64_t)a.T * L + kBlockM - 1) / kBlockM, a.KB));
+    w.flags = a.x_planes ? reinterpret_cast<unsigned int*>(
+        a.x_planes + a_flags_offset(((int64_t)a.T * L + kBlockM - 1) / kBlockM, a.KB)) : nullptr;
     *s_ctx = w;
   }
   __syncwarp();
@@ -481,11 +512,19 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
       // pass bit = bit 15 / 31 of a packed sum
       const uint32_t any = (s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) & 0x80008000u;
       if (__any_sync(full, any != 0u)) {
+        // rare: merge the pass bits (window u -> bits 15-u and 31-u) and walk the windows that have candidates
+        uint32_t cb = 0u;
 #pragma unroll
-        for (int u = 0; u < kGroup; ++u) {
-          const bool cand = (s[u] & 0x80008000u) != 0u;
+        for (int u = 0; u < kGroup; ++u) cb |= (s[u] & 0x80008000u) >> u;
+        uint32_t wm = __reduce_or_sync(full, cb);
+        wm = (wm | (wm >> 16)) & 0xff00u;            // bit 15-u set: some lane has a candidate in window u
+#pragma unroll 1
+        while (wm != 0u) {
+          const int u = 15 - (31 - __clz(wm));       // lowest window first
+          wm &= ~(0x8000u >> u);
+          const bool cand = (cb & (0x80008000u >> u)) != 0u;
           const unsigned bal = __ballot_sync(full, cand);
-          if (bal != 0u && b + u >= b_lo) push(bal, cand, b + u);
+          if (b + u >= b_lo) push(bal, cand, b + u);
         }
       }
     }
@@ -591,10 +630,15 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
                          const uint32_t* qthr_dev, const int32_t* units_dev, int n_units, int max_motif_len,
                          void* x_planes_dev, double* rowstats_dev, int32_t* count_dev,
                          int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
-                         void* stream) {
+                         void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev,
+                         int32_t* row_nnz_dev, void* stream) {
   using namespace mepp;
   MEPP_REQUIRE(sym_T_dev && lut_dev && bias_dev && mlen_dev && nfilt_dev && qtab_dev && qthr_dev &&
-               x_planes_dev && rowstats_dev && count_dev && density_dev, "scan: null pointer");
+               rowstats_dev && count_dev && density_dev, "scan: null pointer");
+  MEPP_REQUIRE(x_planes_dev || entries_dev, "scan: neither the tiled operand nor the entry list was requested");
+  MEPP_REQUIRE(entries_dev == nullptr || (entry_count_dev && row_nnz_dev && entry_cap >= MEPP_ENTRY_LISTS &&
+                                          entry_cap % MEPP_ENTRY_LISTS == 0),
+               "scan: the entry list needs its counters and a capacity that is a multiple of MEPP_ENTRY_LISTS");
   MEPP_REQUIRE(N > 0 && L > 0 && T > 0, "scan: empty input");
   MEPP_REQUIRE(units_dev == nullptr || (n_units > 0 && n_units <= T), "scan: bad unit list");
   MEPP_REQUIRE(max_motif_len >= 0 && max_motif_len <= MEPP_MAX_MOTIF_LEN, "scan: max_motif_len outside [0, 32]");
@@ -618,6 +662,8 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
   a.x_planes = reinterpret_cast<uint8_t*>(x_planes_dev); a.rowstats = rowstats_dev;
   a.count = count_dev; a.density = density_dev;
   a.hits = reinterpret_cast<HitRec*>(hits_dev); a.hits_cap = hits_cap; a.hit_count = hit_count_dev;
+  a.entries = reinterpret_cast<XEntry*>(entries_dev); a.sub_cap = entry_cap / MEPP_ENTRY_LISTS;
+  a.entry_count = entry_count_dev; a.row_nnz = row_nnz_dev;
   const int nbuf = 32 + 2 * margin;
   size_t smem = sizeof(float) * kScanWarps * (units_dev ? 2 : 1) * nbuf * kRowStride +
                 sizeof(uint32_t) * kScanWarps * a.qslots * 64 + sizeof(uint16_t) * kScanWarps * kQueue +
@@ -633,7 +679,11 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
   MEPP_CUDA_CHECK(cudaMemsetAsync(count_dev, 0, sizeof(int32_t) * (size_t)T * L, st));
   MEPP_CUDA_CHECK(cudaMemsetAsync(density_dev, 0, sizeof(int32_t) * (size_t)T * a.n_pad, st));
   if (hit_count_dev) MEPP_CUDA_CHECK(cudaMemsetAsync(hit_count_dev, 0, sizeof(unsigned long long), st));
-  {
+  if (entries_dev) {
+    MEPP_CUDA_CHECK(cudaMemsetAsync(entry_count_dev, 0, sizeof(unsigned long long) * 16 * MEPP_ENTRY_LISTS, st));
+    MEPP_CUDA_CHECK(cudaMemsetAsync(row_nnz_dev, 0, sizeof(int32_t) * ((size_t)T * L + 1), st));
+  }
+  if (x_planes_dev) {
     // reset the non-zero bit array behind the tiles
     const int64_t n_tiles_m = ((int64_t)T * L + kBlockM - 1) / kBlockM;
     MEPP_CUDA_CHECK(cudaMemsetAsync(a.x_planes + a_flags_offset(n_tiles_m, a.KB), 0,

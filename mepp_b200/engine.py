@@ -80,6 +80,11 @@ class ProfileBatch:
         return X0
 
 
+SPARSE_DENSITY_MAX = 5e-3     # expected non-zero fraction of X up to which the sparse profile path is used
+SPARSE_ENTRY_DENSITY = 8e-3   # capacity of the entry list as a fraction of T * N * L
+MIN_ENTRY_CAP = 1 << 20
+
+
 def scan_units(tables):
     """Pair every two-filter ('+/-') task with a one-filter task that has the same filter 0, bias and length
     (the '+' orientation of the same motif: motif_layers.py:36-76 gives both the threshold of W): one pass of
@@ -125,6 +130,8 @@ class Engine:
         self.timing = None  # set to {} to collect per-stage CUDA-event times (ms)
         self.fuse_correlation = True   # False: separate GEMM (S) + correlation kernels (tests / A-B runs)
         self.share_scans = os.environ.get("MEPP_SHARE_SCANS", "1") != "0"   # '+' rides on the '+/-' pass of its motif
+        self.profile_path = os.environ.get("MEPP_PROFILE_PATH", "auto")     # 'auto' | 'sparse' | 'tensor'
+        self.last_paths = []
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -204,10 +211,34 @@ class Engine:
             _lib.check(_lib.lib.mepp_build_y(_ptr(yhat_d), _ptr(perm_d), _ptr(self.zhat), N, P, _ptr(self.y_planes),
                                              _ptr(self.col_syz), _ptr(self.ysum), st), "build_y")
             self.launches += 3 if self.use_gc else 2
+            # row-major float32 Y for the sparse profile path (built lazily: 4 * n_pad * ldY bytes)
+            self._yhat_d, self._perm_d, self._y_rows = yhat_d, perm_d, None
             self._zsum_host = None
             self._colconst_dev = None
             self.staged = True
         return self
+
+    def _yrows(self):
+        if self._y_rows is None:
+            ldY = int(_lib.lib.mepp_y_rows_ld(self.C))
+            self._y_rows = self.torch.empty((self.n_pad, ldY), dtype=self.torch.float32, device=self.device)
+            _lib.check(_lib.lib.mepp_build_y_rows(_ptr(self._yhat_d), _ptr(self._perm_d), self.N, self.P,
+                                                  _ptr(self._y_rows), self._stream()), "build_y_rows")
+            self.launches += 1
+        return self._y_rows
+
+    def choose_path(self, tables, margin):
+        """'sparse' (gather of Y rows per non-zero of X) or 'tensor' (tcgen05 GEMM over the tiled operand).
+        The sparse path costs ~4 (1 + P) bytes of L2 traffic per non-zero, the GEMM the same whatever X holds:
+        with the reference's p = 1e-4 threshold X is ~1e-3 dense and the sparse path wins by ~4x; the
+        break-even is near 5e-3."""
+        if self.profile_path in ('sparse', 'tensor'):
+            return self.profile_path
+        y_rows_bytes = 4 * self.n_pad * int(_lib.lib.mepp_y_rows_ld(self.C))
+        if not self.fuse_correlation or y_rows_bytes > self.mem_budget // 2:
+            return 'tensor'
+        pv = max((tb.get('pvalue', 1e-4) * tb['n_filters'] for tb in tables), default=1e-4)
+        return 'sparse' if pv * (2 * int(margin) + 1) <= SPARSE_DENSITY_MAX else 'tensor'
 
     def _colconst(self):
         """Per-dataset constants of the fused correlation epilogue (built once per stage())."""
@@ -350,10 +381,12 @@ class Engine:
             self._pins[key] = cur
         return cur[:need].view(tuple(int(x) for x in shape))
 
-    def _launch_group(self, tables, margin, return_hits, return_r, hits_cap, ci, slot):
+    def _launch_group(self, tables, margin, return_hits, return_r, hits_cap, ci, slot, path=None):
         """Enqueue every kernel of one task group plus the D2H copies of its results (no host sync)."""
         torch = self.torch
         T = len(tables)
+        path = path or self.choose_path(tables, margin)
+        self.last_paths.append(path)
         L, N, C_, P = self.L, self.N, self.C, self.P
         st = self._stream()
         self._reset_x_planes()     # before any scratch buffer of the previous group is reused
@@ -370,8 +403,16 @@ class Engine:
         units_d = self._to_dev(units) if units is not None else None
         n_units = len(units) if units is not None else 0
         self.last_units = n_units if units is not None else T
-        x_bytes = int(_lib.lib.mepp_x_planes_bytes(m_rows, self.n_pad))
-        x_planes = self._buf('x_planes', x_bytes, torch.uint8, zero=True)
+        x_planes = entries = entry_count = row_nnz = None
+        entry_cap = 0
+        if path == 'tensor':
+            x_bytes = int(_lib.lib.mepp_x_planes_bytes(m_rows, self.n_pad))
+            x_planes = self._buf('x_planes', x_bytes, torch.uint8, zero=True)
+        else:
+            entry_cap = -(-max(MIN_ENTRY_CAP, int(T * N * L * SPARSE_ENTRY_DENSITY)) // _lib.ENTRY_LISTS) * _lib.ENTRY_LISTS
+            entries = self._buf('entries', entry_cap * 16, torch.uint8)
+            entry_count = self._buf('entry_count', (16 * _lib.ENTRY_LISTS,), torch.int64)
+            row_nnz = self._buf('row_nnz', (m_rows + 1,), torch.int32)
         rowstats = self._buf('rowstats', (m_rows, 3), torch.float64)
         count = self._buf('count', (T, L), torch.int32)
         density = self._buf('density', (T, self.n_pad), torch.int32)
@@ -382,14 +423,24 @@ class Engine:
         ev = self._mark(None, None)
         _lib.check(_lib.lib.mepp_scan(_ptr(self.sym_T), _ptr(self.zhat), N, L, T, int(margin),
                                       _ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), _ptr(qtab_d), _ptr(qthr_d),
-                                      _ptr(units_d), n_units, int(mlen.max()), _ptr(x_planes), _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap,
-                                      _ptr(hit_count), st), "scan")
-        # the scan stored only the non-zero pieces; the operand goes back to all-zero before its next use
-        self._x_pending = dict(x=x_planes, hits=hits_d, cap=cap, hit_count=hit_count, N=N, L=L, T=T, margin=int(margin))
+                                      _ptr(units_d), n_units, int(mlen.max()), _ptr(x_planes), _ptr(rowstats), _ptr(count),
+                                      _ptr(density), _ptr(hits_d), cap, _ptr(hit_count), _ptr(entries), entry_cap,
+                                      _ptr(entry_count), _ptr(row_nnz), st), "scan")
+        if path == 'tensor':
+            # the scan stored only the non-zero pieces; the operand goes back to all-zero before its next use
+            self._x_pending = dict(x=x_planes, hits=hits_d, cap=cap, hit_count=hit_count, N=N, L=L, T=T,
+                                   margin=int(margin))
         ev = self._mark(ev, 'scan')
         # tcgen05 GEMM with the correlation fused into its epilogue: r (m_rows, ldS) float32, S never reaches HBM
         r = self._buf('r', (m_rows, self.ldS), torch.float32)
-        if self.fuse_correlation:
+        if path == 'sparse':
+            work = self._buf('sparse_work', int(_lib.lib.mepp_profile_sparse_work_bytes(m_rows, entry_cap)), torch.uint8)
+            _lib.check(_lib.lib.mepp_profile_sparse(_ptr(entries), _ptr(entry_count), entry_cap, _ptr(row_nnz),
+                                                    _ptr(self._yrows()), _ptr(rowstats), _ptr(self._colconst()), _ptr(r),
+                                                    self.ldS, m_rows, C_, _ptr(work), st), "profile_sparse")
+            self.launches += 3
+            ev = self._mark(ev, 'gemm')
+        elif self.fuse_correlation:
             _lib.check(_lib.lib.mepp_profile_corr_gemm(_ptr(x_planes), _ptr(self.y_planes), _ptr(rowstats),
                                                        _ptr(self._colconst()), _ptr(r), m_rows, C_, self.n_pad, st),
                        "profile_corr_gemm")
@@ -429,6 +480,8 @@ class Engine:
         dev['count'] = count
         dev['density'] = density
         dev['hit_count'] = hit_count
+        if path == 'sparse':
+            dev['entry_count'] = entry_count
         if return_r:
             dev['r'] = r.view(T, L, self.ldS)[:, :, :C_].contiguous()
         host = {}
@@ -438,7 +491,8 @@ class Engine:
             host[k] = h
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(self.device))
-        return dict(host=host, done=done, T=T, hits_d=hits_d, cap=cap, return_hits=return_hits)
+        return dict(host=host, done=done, T=T, hits_d=hits_d, cap=cap, return_hits=return_hits, path=path,
+                    entry_cap=entry_cap, slot=slot, tables=tables, return_r=return_r, hits_cap=hits_cap)
 
     def _collect_group(self, pend, margin, ci, store, density_all):
         """Wait for one group's D2H copies and finalise its statistics on the host, straight into the
@@ -446,6 +500,12 @@ class Engine:
         pend['done'].synchronize()
         h = {k: v.numpy() for k, v in pend['host'].items()}
         t0, T = pend['t0'], pend['T']
+        if pend['path'] == 'sparse' and int(h['entry_count'][::16].max()) > pend['entry_cap'] // _lib.ENTRY_LISTS:
+            # X turned out denser than the entry list allows for: redo this group on the tensor-core path
+            redo = self._launch_group(pend['tables'], margin, pend['return_hits'], pend['return_r'], pend['hits_cap'],
+                                      ci, pend['slot'], path='tensor')
+            redo['t0'] = t0
+            return self._collect_group(redo, margin, ci, store, density_all)
         if self.P > 0:
             args = (h['full_os'], h['full_cnt'], h['semi_os'], h['semi_cnt'], h['integral'])
         else:

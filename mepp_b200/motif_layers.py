@@ -75,7 +75,8 @@ def motif_matrix_to_scan_table(motif_matrix, orientation='+', pseudocount=0.0001
         _pd(pwm), m, och, float(pseudocount), float(pvalue), bgp, 1 if honour_flags else 0, float(dp_precision),
         lut.ctypes.data_as(C.POINTER(C.c_float)), C.byref(bias), C.byref(nf), C.byref(thr),
         qtab.ctypes.data, qthr.ctypes.data), "motif_table")
-    return dict(lut=lut, bias=np.float32(bias.value), n_filters=nf.value, thr=thr.value, m=m, qtab=qtab, qthr=qthr)
+    return dict(lut=lut, bias=np.float32(bias.value), n_filters=nf.value, thr=thr.value, m=m, qtab=qtab, qthr=qthr,
+                pvalue=float(pvalue) if honour_flags else 0.0001)
 
 
 _POOLS = {}

@@ -348,3 +348,39 @@ def test_scan_is_deterministic_after_longer_motifs():
                                       profile.scan(codes, Wf, Wr, thr).view(np.uint32))
         else:
             assert np.array_equal(got.hits, ref.hits), rep
+
+
+def test_sparse_and_tensor_profile_paths_agree(monkeypatch):
+    """The gather path (entry list -> CSR -> float64 sums of Y rows) and the tcgen05 GEMM path give the same
+    profiles; an entry list that overflows falls back to the GEMM path for that group."""
+    from mepp_b200 import synth, engine as engine_mod
+    ascii_u8, scores = synth.synth_sequences(1500, 260, seed=12, n_rate=0.01)
+    perm = synth.synth_permutations(1500, 37, seed=12)
+    motifs = synth.synth_motifs(6, seed=4, m_lo=5, m_hi=18)
+    tasks = [(m, o) for m in motifs for o in ('+', '+/-')]
+    eng = _engine().stage(ascii_u8, scores, perm)
+    eng.profile_path = 'sparse'
+    sp = eng.profile(tasks, margin=2, return_r=True, return_hits=True)
+    assert set(eng.last_paths) == {'sparse'}
+    eng.profile_path = 'tensor'
+    eng.last_paths = []
+    tc = eng.profile(tasks, margin=2, return_r=True, return_hits=True)
+    assert set(eng.last_paths) == {'tensor'}
+    assert np.array_equal(sp.hits, tc.hits)
+    assert _r_close(sp.r, tc.r).all()
+    codes = staging.ascii_to_codes(ascii_u8)
+    Y = staging.permuted_scores(scores, perm)
+    z = staging.gc_ratio_global(codes)
+    for t in (0, 1, 6, 7):
+        orc = profile.profile_task(codes, Y, z, tasks[t][0], tasks[t][1], margin=2)
+        assert _r_close(sp.r[t], orc["r"], rel=2e-6, floor_frac=2e-6).all(), t    # float64 sums: tighter than the GEMM
+    for col in ('positional_r', 'permutation_positional_r_lower', 'integral_r'):
+        assert np.allclose(np.asarray(sp.positions[col]), np.asarray(tc.positions[col]), rtol=1e-4, atol=1e-7), col
+    # overflow -> fallback
+    monkeypatch.setattr(engine_mod, 'SPARSE_ENTRY_DENSITY', 1e-9)
+    monkeypatch.setattr(engine_mod, 'MIN_ENTRY_CAP', 16)
+    eng.profile_path = 'sparse'
+    eng.last_paths = []
+    fb = eng.profile(tasks, margin=2, return_r=True)
+    assert eng.last_paths == ['sparse', 'tensor']
+    assert np.array_equal(fb.r, tc.r) or _r_close(fb.r, tc.r).all()
