@@ -201,6 +201,23 @@ int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C,
                     float* full_os_dev, int32_t* full_cnt_dev, float* semi_os_dev,
                     long long* semi_cnt_dev, double* integral_dev, void* work_dev, void* stream);
 
+/* ------------------------------------------------------------------ K4: output columns
+ * The per-position / per-task columns of core.get_positional_r_df (core.py:286-374), the parametric
+ * Fisher-z interval and t-test (core.py:380-413, float32 arithmetic) and the smoothed counts
+ * (core.py:438-454) of one task group, from the outputs of mepp_perm_stats / mepp_scan.  g_* are the
+ * interpolation weights of numpy's 'linear' percentile at k_* (per position over P values, pooled over
+ * L*P values); z_margin = float32(norm.ppf(1 - alpha/2) * sqrt(1 / (n_seq - 3))).
+ * out_dev (mepp_finalize_out_bytes): float64 [full_lower, full_upper, full_pval, semi_pval, pval, count,
+ * smoothed_count][T*L], float32 [positional_r, lower, upper][T*L], then (8-byte aligned) float64
+ * [semi_lower, semi_upper, integral_lower, integral_upper, integral_pval][T], float32 [integral_r][T].
+ * With C == 1 (no permutations) the permutation columns are left untouched. */
+int64_t mepp_finalize_out_bytes(int T, int L);
+int mepp_finalize_positions(const float* r_dev, int64_t ldr, int T, int L, int C, const float* full_os_dev,
+                            const int32_t* full_cnt_dev, const float* semi_os_dev, const long long* semi_cnt_dev,
+                            const double* integral_dev, const int32_t* count_dev, int64_t n_seq, int margin,
+                            int k_lo, int k_hi, double g_lo, double g_hi, double gs_lo, double gs_hi, float z_margin,
+                            void* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -475,9 +475,25 @@ class Engine:
                                                 _ptr(dev['integral']), _ptr(work), st), "perm_stats")
             self.launches += 6
             ev = self._mark(ev, 'perm_stats')
-        dev['r0'] = self._buf('r0', (T, L), torch.float32)
-        dev['r0'].copy_(r.view(T, L, self.ldS)[:, :, 0])
-        dev['count'] = count
+        # K4: every output column of the group on the device; the host only copies the block into the result table
+        out_d = self._buf('finalized', int(_lib.lib.mepp_finalize_out_bytes(T, L)), torch.uint8)
+        if P > 0:
+            _, g_lo = stats_host.virtual_index(P, q[0])
+            _, g_hi = stats_host.virtual_index(P, q[1])
+            _, gs_lo = stats_host.virtual_index(L * P, q[0])
+            _, gs_hi = stats_host.virtual_index(L * P, q[1])
+            fin = (dev['full_os'], dev['full_cnt'], dev['semi_os'], dev['semi_cnt'], dev['integral'])
+        else:
+            k_lo = k_hi = 0
+            g_lo = g_hi = gs_lo = gs_hi = 0.0
+            fin = (None,) * 5
+        _lib.check(_lib.lib.mepp_finalize_positions(_ptr(r), self.ldS, T, L, C_, *[_ptr(x) for x in fin], _ptr(count), N,
+                                                    int(margin), k_lo, k_hi, g_lo, g_hi, gs_lo, gs_hi,
+                                                    float(stats_host.z_margin_f32(N, ci)), _ptr(out_d), st),
+                   "finalize_positions")
+        self.launches += 2 if P > 0 else 1
+        ev = self._mark(ev, 'finalize')
+        dev = {'finalized': out_d}
         dev['density'] = density
         dev['hit_count'] = hit_count
         if path == 'sparse':
@@ -506,11 +522,7 @@ class Engine:
                                       ci, pend['slot'], path='tensor')
             redo['t0'] = t0
             return self._collect_group(redo, margin, ci, store, density_all)
-        if self.P > 0:
-            args = (h['full_os'], h['full_cnt'], h['semi_os'], h['semi_cnt'], h['integral'])
-        else:
-            args = (None, None, None, None, None)
-        stats_host.finalize_into(store, t0, h['r0'], *args, h['count'], self.N, margin, ci)
+        stats_host.store_finalized(store, t0, h['finalized'], T, self.L)
         density_all[t0:t0 + T] = h['density'][:, :self.N]
         out = dict(T=T)
         nh = int(h['hit_count'][0])

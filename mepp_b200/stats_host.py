@@ -192,3 +192,39 @@ def finalize_positions(r0, full_os, full_cnt, semi_os, semi_cnt, integral, count
     finalize_into(store, 0, r0, full_os, full_cnt, semi_os, semi_cnt, integral, count, n_seq, margin,
                   confidence_interval_pct)
     return positions_view(store, center, permutation_mode)
+
+
+FINALIZED_F64 = ['permutation_full_positional_r_lower', 'permutation_full_positional_r_upper',
+                 'permutation_full_positional_r_pval', 'permutation_semi_positional_r_pval', 'positional_r_pval',
+                 'count', 'smoothed_count']
+FINALIZED_F32 = ['positional_r', 'positional_r_lower', 'positional_r_upper']
+FINALIZED_TASK_F64 = ['permutation_semi_positional_r_lower', 'permutation_semi_positional_r_upper',
+                      'permutation_integral_r_lower', 'permutation_integral_r_upper', 'permutation_integral_r_pval']
+
+
+def z_margin_f32(num_samples, confidence_interval_pct=95):
+    """float32(norm.ppf(1 - alpha / 2) * sqrt(1 / (n - 3))) of core.py:393-397."""
+    alpha = 1.0 - (confidence_interval_pct / 100.0)
+    return np.float32(_st.norm.ppf(1.0 - alpha / 2.0) * np.sqrt(1.0 / (num_samples - 3)))
+
+
+def store_finalized(store, t0, buf, T, L):
+    """Copy the output block of mepp_finalize_positions (include/mepp_b200.h, K4) of one task group into rows
+    t0 .. t0+T of the store.  buf: uint8 array (may be a pinned staging buffer)."""
+    P = store['P']
+    TL = T * L
+    sl = slice(t0, t0 + T)
+    pos, task = store['pos'], store['task']
+    d64 = buf[:TL * 56].view(np.float64).reshape(7, T, L)
+    f32 = buf[TL * 56:TL * 68].view(np.float32).reshape(3, T, L)
+    for i, k in enumerate(FINALIZED_F64):
+        if k in pos:
+            pos[k][sl] = d64[i]
+    for i, k in enumerate(FINALIZED_F32):
+        pos[k][sl] = f32[i]
+    if P > 0:
+        off = (TL * 68 + 7) & ~7
+        t64 = buf[off:off + T * 40].view(np.float64).reshape(5, T)
+        for i, k in enumerate(FINALIZED_TASK_F64):
+            task[k][sl] = t64[i]
+        task['integral_r'][sl] = buf[off + T * 40:off + T * 44].view(np.float32)

@@ -384,3 +384,55 @@ def test_sparse_and_tensor_profile_paths_agree(monkeypatch):
     fb = eng.profile(tasks, margin=2, return_r=True)
     assert eng.last_paths == ['sparse', 'tensor']
     assert np.array_equal(fb.r, tc.r) or _r_close(fb.r, tc.r).all()
+
+
+@pytest.mark.parametrize("T,L,P,margin", [(3, 101, 37, 2), (2, 64, 1000, 0), (1, 33, 1, 5), (2, 7, 0, 4)])
+def test_device_finalisation_equals_host_finalisation(T, L, P, margin):
+    """K4 (mepp_finalize_positions) against stats_host.finalize_into (the numpy restatement of core.py:286-413) on
+    the same K3 outputs: interpolated percentiles / p-values / counts identical, float32 Fisher-z columns within
+    2 ulp (logf / expf), t-test p-value within 1e-9 relative of scipy's stdtr."""
+    import ctypes as C
+    from mepp_b200 import _lib, stats_host
+    from mepp_b200.engine import _ptr
+    _engine()
+    rng = np.random.default_rng(T * 1000 + L)
+    Cc = 1 + P
+    n_seq = 5000
+    r_h = (rng.normal(scale=0.02, size=(T * L, Cc))).astype(np.float32)
+    r_h[0, 0] = 0.0
+    r_h[1, 0] = 0.93                                       # a large |t|: tiny p-value
+    r = torch.from_numpy(r_h).cuda()
+    count = torch.from_numpy(rng.integers(0, 9, (T, L)).astype(np.int32)).cuda()
+    q = stats_host.percentile_q(95)
+    dev = [None] * 5
+    k_lo = k_hi = 0
+    g = [0.0] * 4
+    if P > 0:
+        k_lo, g[0] = stats_host.virtual_index(P, q[0]); k_hi, g[1] = stats_host.virtual_index(P, q[1])
+        ks_lo, g[2] = stats_host.virtual_index(L * P, q[0]); ks_hi, g[3] = stats_host.virtual_index(L * P, q[1])
+        dev = [torch.empty((T, L, 4), dtype=torch.float32, device='cuda'), torch.empty((T, L), dtype=torch.int32, device='cuda'),
+               torch.empty((T, 4), dtype=torch.float32, device='cuda'), torch.empty((T, L), dtype=torch.int64, device='cuda'),
+               torch.empty((T, Cc), dtype=torch.float64, device='cuda')]
+        work = torch.empty(int(_lib.lib.mepp_perm_stats_work_bytes(T, L, Cc)), dtype=torch.uint8, device='cuda')
+        _lib.check(_lib.lib.mepp_perm_stats(_ptr(r), Cc, T, L, Cc, k_lo, k_hi, ks_lo, ks_hi, *[_ptr(x) for x in dev],
+                                            _ptr(work), None), "perm_stats")
+    out = torch.empty(int(_lib.lib.mepp_finalize_out_bytes(T, L)), dtype=torch.uint8, device='cuda')
+    _lib.check(_lib.lib.mepp_finalize_positions(_ptr(r), Cc, T, L, Cc, *[_ptr(x) for x in dev], _ptr(count), n_seq, margin,
+                                                k_lo, k_hi, g[0], g[1], g[2], g[3],
+                                                float(stats_host.z_margin_f32(n_seq, 95)), _ptr(out), None), "finalize")
+    torch.cuda.synchronize()
+    got = stats_host.alloc_positions(T, L, P)
+    stats_host.store_finalized(got, 0, out.cpu().numpy(), T, L)
+    ref = stats_host.alloc_positions(T, L, P)
+    host = [x.cpu().numpy() if x is not None else None for x in dev]
+    stats_host.finalize_into(ref, 0, r_h.reshape(T, L, Cc)[:, :, 0].copy(), *host, count.cpu().numpy(), n_seq, margin, 95)
+    for k in ref['pos']:
+        a, b = got['pos'][k], ref['pos'][k]
+        if k in ('positional_r_lower', 'positional_r_upper'):
+            assert np.abs(a - b).max() <= 3e-7 * max(1.0, np.abs(b).max()), k
+        elif k == 'positional_r_pval':
+            assert np.allclose(a, b, rtol=1e-9, atol=1e-300), (k, np.abs(a / b - 1).max())
+        else:
+            assert np.array_equal(a, b, equal_nan=True), k
+    for k in ref['task']:
+        assert np.array_equal(got['task'][k], ref['task'][k]), k
