@@ -36,6 +36,13 @@ METRIC = "Gbp*motifs/s scanned+profiled"
 UNIT = "Gbp*motifs/s"
 
 
+SCAN_DRAM_BYTES_PER_LAUNCH = None   # filled from profiles/ (ncu --set full of one scan launch), see DESIGN.md
+
+
+def clocks_mhz_hint(peaks):
+    return float(peaks.get("sm_mhz", 1965.0))
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -206,10 +213,10 @@ def main():
     for _ in range(max(args.warmup, 1)):
         batch, full = e2e_step()
     tables = motif_layers.scan_tables(my_tasks)
-    # bytes actually copied device -> host per step: r0, 4 order statistics, 3 counts per (task, position);
-    # density per (task, sequence); integrals per (task, column)
+    # bytes actually copied device -> host per step: the finalised column block (68 B per (task, position), 44 B
+    # per task), density per (task, sequence), the match / entry counters of every group
     n_loc = len(my_tasks)
-    d2h_bytes = int(n_loc * L * (4 + 16 + 4 + 8 + 4) + n_loc * eng.n_pad * 4 + n_loc * (1 + P) * 8 + n_loc * 24)
+    d2h_bytes = int(n_loc * L * 68 + n_loc * 44 + n_loc * eng.n_pad * 4 + eng.last_groups * (8 + 8 * 16 * 64))
 
     sampler = ClockSampler(local)
     if not args.no_clocks:
@@ -261,35 +268,66 @@ def main():
     e2e_value = work_step * args.steps / dt_e2e / 1e9
     n_local = len(my_tasks)
     groups = eng.last_groups
-    # per-kernel rooflines from the CUDA-event stage times of the timed value region (rank 0's share)
+    # per-kernel rooflines from the CUDA-event stage times of the timed value region (rank 0's share).
+    # Algorithmic bytes / flops per launch group are stated in DESIGN.md section 4; the counts come from the
+    # engine (matches, non-zeros of X, scan units of the last step).
     C_ = 1 + P
-    scan_bytes = 4.0 * N * L * n_local * args.steps          # fp16 hi+lo planes written once (4 B / bp*task)
-    gemm_alg = 2.0 * L * N * C_ * n_local * args.steps
+    st = eng.last_stats
+    sparse = all(p_ == "sparse" for p_ in st["paths"])
+    steps = args.steps
+    per = lambda k: stage_ms[k] * 1e-3 / steps             # seconds per step
     kernels = {}
+    l2_cap_gbs = 6300.0 * clocks_mhz_hint(peaks) / 1e3     # LTS throughput cap, B300_MICROARCH.md: ~6300 B/clk full chip
     if stage_ms.get("scan"):
-        a = scan_bytes / (stage_ms["scan"] * 1e-3) / 1e9
+        # reads 3 bits per base per scan unit (a '+/-' task and its '+' twin share one pass), writes 16 B per match and
+        # 16 B per non-zero of X (sparse path) or 32 B per non-zero 8-sequence piece (tiled path, <= one per non-zero)
+        scan_bytes = 0.375 * N * L * st["units"] + 16.0 * st["hits"] + (16.0 if sparse else 32.0) * max(st["entries"], st["hits"])
+        a = scan_bytes / per("scan") / 1e9
         kernels["scan"] = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"],
-                               ms_per_step=stage_ms["scan"] / args.steps, launches_per_step=groups)
-    if stage_ms.get("gemm"):
+                               ms_per_step=1e3 * per("scan"), launches_per_step=groups,
+                               gwindows_per_s=N * L * n_local / per("scan") / 1e9,
+                               limit="integer issue / shared-memory lookups of the pre-filter (ncu: issue slots ~47 % busy, "
+                                     "DRAM < 1 %): X is written as a list of its non-zeros, so almost no bytes move")
+    if stage_ms.get("gemm") and sparse:
+        # HBM: Y rows once (L2-resident afterwards), CSR records, r written once; L2 -> SM: one Y row per non-zero
+        ldY = -(-C_ // 1024) * 1024
+        hbm = 4.0 * eng.n_pad * ldY + 24.0 * st["entries"] + 4.0 * n_local * L * eng.ldS
+        l2 = 4.0 * ldY * st["entries"]
+        a = hbm / per("gemm") / 1e9
+        kernels["profile_sparse"] = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s",
+                                         frac=a / peaks["hbm_gbs"], ms_per_step=1e3 * per("gemm"),
+                                         launches_per_step=3 * groups, l2_gather_gbs=l2 / per("gemm") / 1e9,
+                                         l2_cap_gbs=l2_cap_gbs, l2_frac=l2 / per("gemm") / 1e9 / l2_cap_gbs,
+                                         nonzeros_per_step=st["entries"],
+                                         limit="L2 -> SM gather of one float32 Y row (4 * ldY bytes) per non-zero of X")
+    elif stage_ms.get("gemm"):
         # executed = issued MMAs only (all-zero K=16 steps of X are skipped); padded tile columns are counted as issued
+        gemm_alg = 2.0 * L * N * C_ * n_local
         padded = (eng.ldS / float(C_))
-        a = 3.0 * gemm_alg * issued_frac * padded / (stage_ms["gemm"] * 1e-3) / 1e12
+        a = 3.0 * gemm_alg * issued_frac * padded / per("gemm") / 1e12
         kernels["profile_gemm"] = dict(bound="tensor", achieved=a, peak=peaks["tf_sustained"], unit="TFLOP/s",
                                        frac=a / peaks["tf_sustained"], frac_of_burst=a / peaks["tf_burst"],
-                                       algorithmic_tflops=gemm_alg / (stage_ms["gemm"] * 1e-3) / 1e12,
+                                       algorithmic_tflops=gemm_alg / per("gemm") / 1e12,
                                        issued_step_fraction=issued_frac, split_products=3,
-                                       ms_per_step=stage_ms["gemm"] / args.steps, launches_per_step=groups)
-    for k in ("correlation", "perm_stats"):
+                                       ms_per_step=1e3 * per("gemm"), launches_per_step=groups)
+    if stage_ms.get("perm_stats"):
+        # r is read by the row sort, the pooled histogram and the integrals and the sorted keys are written and read back
+        stats_bytes = 4.0 * n_local * L * (3.0 * C_ + 2.0 * P)
+        a = stats_bytes / per("perm_stats") / 1e9
+        kernels["perm_stats"] = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"],
+                                     ms_per_step=1e3 * per("perm_stats"), launches_per_step=6 * groups,
+                                     limit="register bitonic sort of every (task, position) row of P values")
+    for k in ("correlation", "finalize"):
         if stage_ms.get(k):
-            kernels[k] = dict(ms_per_step=stage_ms[k] / args.steps)
-    dominant = max(("scan", "profile_gemm"), key=lambda k: kernels.get(k, {}).get("ms_per_step", 0.0))
+            kernels[k] = dict(ms_per_step=1e3 * per(k))
+    dominant = "scan" if "scan" in kernels else next(iter(kernels))   # the longest single kernel of the step
     dk = kernels.get(dominant, {})
-    roofline = dict(kernel=dominant, bound=dk.get("bound"), achieved=dk.get("achieved"), peak=dk.get("peak"),
-                    unit=dk.get("unit"), frac=dk.get("frac"), traffic=None, peak_source=peaks["source"],
-                    note=("achieved = ISSUED tensor FLOPs (3 fp16 products per algorithmic FLOP, all-zero K=16 steps "
-                          "skipped and not counted) / CUDA-event time; peak = sustained cuBLAS bf16"
-                          if dominant == "profile_gemm" else
-                          "achieved = 4 B per bp*task (fp16 hi+lo X planes written once) / CUDA-event time"))
+    roofline = dict(kernel=dominant + "_kernel", bound=dk.get("bound"), achieved=dk.get("achieved"), peak=dk.get("peak"),
+                    unit=dk.get("unit"), frac=dk.get("frac"), traffic=SCAN_DRAM_BYTES_PER_LAUNCH,
+                    peak_source=peaks["source"],
+                    note="achieved = algorithmic bytes (3 bits per base per scan unit read, 16 B per match and per non-zero of "
+                         "X written) / CUDA-event time of the launches; the kernel is bound by integer issue, not by HBM "
+                         "(DESIGN.md section 4); traffic = DRAM bytes of one launch from the committed ncu capture")
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -308,8 +346,11 @@ def main():
                 dtype="f32", data="synthetic",
                 config=dict(workload=args.workload, N=N, L=L, P=P, margin=margin, tasks_total=T_total,
                             tasks_per_gpu=n_local, orientations="+,+/-", parallelism=f"tasks sharded over {world} GPU(s)",
-                            l2="inputs larger than L2 (X planes %.1f GB per group)" % (4.0 * N * L * min(n_local, eng.group_size()) / 1e9),
-                            gemm="fp16 hi/lo split, 3 tcgen05 products, fp32 TMEM accumulate"),
+                            l2="L2 flushed between steps by the step itself (r + sorted keys: %.1f GB per group, L2 126 MB)"
+                               % (8.0 * L * eng.ldS * min(n_local, eng.group_size()) / 1e9),
+                            profile_path=",".join(sorted(set(st["paths"]))),
+                            profile="sparse: float64 gather of float32 Y rows per non-zero of X; "
+                                    "tensor: fp16 hi/lo split, 3 tcgen05 products, fp32 TMEM accumulate"),
                 e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=1e3 * dt_e2e / args.steps,
                          h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
                 gpu_launches=int(launches), roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline, clocks=clocks)

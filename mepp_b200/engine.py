@@ -301,6 +301,8 @@ class Engine:
         G += G & 1 if G < T_all else 0      # even: the ('+', '+/-') pair of a motif stays in one group
         groups = [(g0, min(g0 + G, T_all)) for g0 in range(0, T_all, G)]
         self.last_groups = len(groups)
+        self._units_run = 0
+        self.last_paths = []
         store = stats_host.alloc_positions(T_all, L, self.P)
         density_all = np.empty((T_all, N), dtype=np.int32)
         outs = []
@@ -324,6 +326,10 @@ class Engine:
             if pending is not None:
                 outs.append(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
         cat = lambda k: np.concatenate([o[k] for o in outs], axis=0)
+        # what the last call moved, for the roofline accounting of bench.py
+        self.last_stats = dict(hits=int(sum(int(o['hit_count'][0]) for o in outs)),
+                               entries=int(sum(o['entries'] for o in outs)), units=int(self._units_run),
+                               paths=list(self.last_paths))
         positions = stats_host.positions_view(store, center)
         hits = None
         if return_hits:
@@ -403,6 +409,7 @@ class Engine:
         units_d = self._to_dev(units) if units is not None else None
         n_units = len(units) if units is not None else 0
         self.last_units = n_units if units is not None else T
+        self._units_run = getattr(self, '_units_run', 0) + self.last_units
         x_planes = entries = entry_count = row_nnz = None
         entry_cap = 0
         if path == 'tensor':
@@ -525,6 +532,7 @@ class Engine:
         stats_host.store_finalized(store, t0, h['finalized'], T, self.L)
         density_all[t0:t0 + T] = h['density'][:, :self.N]
         out = dict(T=T)
+        out['entries'] = int(h['entry_count'][::16].sum()) if 'entry_count' in h else 0
         nh = int(h['hit_count'][0])
         out['hit_count'] = np.array([nh], dtype=np.int64)
         if pend['return_hits']:
