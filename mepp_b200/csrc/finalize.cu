@@ -8,6 +8,7 @@
 // (difference taken in float32, combination in float64, upper form for gamma >= 0.5).
 #include "common.cuh"
 #include <cfloat>
+#include <cmath>
 
 namespace mepp {
 
@@ -45,21 +46,22 @@ __device__ double betacf(double a, double b, double x) {
 }
 
 // Regularised incomplete beta I_x(a, b); xc = 1 - x is passed separately (no cancellation near x = 1).
-__device__ double incbet(double a, double b, double x, double xc) {
+// lnbeta = lgamma(a + b) - lgamma(a) - lgamma(b) is the same for every element of a call.
+__device__ double incbet(double a, double b, double x, double xc, double lnbeta) {
   if (!(x > 0.0)) return 0.0;
   if (!(xc > 0.0)) return 1.0;
-  const double bt = exp(lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log(xc));
+  const double bt = exp(lnbeta + a * log(x) + b * log(xc));
   if (x < (a + 1.0) / (a + b + 2.0)) return bt * betacf(a, b, x) / a;
   return 1.0 - bt * betacf(b, a, xc) / b;
 }
 
 // 2 * scipy.stats.t.sf(|t|, df) = I_{df / (df + t^2)}(df / 2, 1 / 2)   (core.py:410)
-__device__ double t_two_sided(double t, double df) {
+__device__ double t_two_sided(double t, double df, double lnbeta) {
   if (t != t) return t;
   const double t2 = t * t;
   if (isinf(t2)) return 0.0;
   const double den = df + t2;
-  return incbet(0.5 * df, 0.5, df / den, t2 / den);
+  return incbet(0.5 * df, 0.5, df / den, t2 / den, lnbeta);
 }
 
 struct FinalizeArgs {
@@ -70,6 +72,7 @@ struct FinalizeArgs {
   double n_seq; int margin;
   int k_lo, k_hi; double g_lo, g_hi, gs_lo, gs_hi;
   float z_margin;
+  double lnbeta;   // lgamma(df/2 + 1/2) - lgamma(df/2) - lgamma(1/2), df = n_seq - 1
   uint8_t* out;
 };
 
@@ -102,7 +105,7 @@ __global__ void finalize_positions_kernel(const FinalizeArgs a) {
   f32[1 * TL + i] = __fdiv_rn(__fsub_rn(el, 1.0f), __fadd_rn(el, 1.0f));
   f32[2 * TL + i] = __fdiv_rn(__fsub_rn(eu, 1.0f), __fadd_rn(eu, 1.0f));
   const float t = __fdiv_rn(r, sqrtf(__fdiv_rn(__fsub_rn(1.0f, __fmul_rn(r, r)), (float)(a.n_seq - 2.0))));
-  d64[4 * TL + i] = t_two_sided((double)fabsf(t), a.n_seq - 1.0);
+  d64[4 * TL + i] = t_two_sided((double)fabsf(t), a.n_seq - 1.0, a.lnbeta);
   // match counts and their centred rolling mean with the edges filled from the first / last full window
   const int32_t* cnt = a.count + (i - l);
   d64[5 * TL + i] = (double)cnt[l];
@@ -211,9 +214,13 @@ int mepp_finalize_positions(const float* r_dev, int64_t ldr, int T, int L, int C
   a.n_seq = (double)n_seq; a.margin = margin;
   a.k_lo = k_lo; a.k_hi = k_hi; a.g_lo = g_lo; a.g_hi = g_hi; a.gs_lo = gs_lo; a.gs_hi = gs_hi;
   a.z_margin = z_margin;
+  {
+    const double df = (double)n_seq - 1.0;
+    a.lnbeta = lgamma(0.5 * df + 0.5) - lgamma(0.5 * df) - lgamma(0.5);
+  }
   a.out = reinterpret_cast<uint8_t*>(out_dev);
   const int64_t TL = (int64_t)T * L;
-  finalize_positions_kernel<<<(unsigned)((TL + 127) / 128), 128, 0, st>>>(a);
+  finalize_positions_kernel<<<(unsigned)((TL + 63) / 64), 64, 0, st>>>(a);
   if (P > 0) {
     int P_pow2 = 1;
     while (P_pow2 < P) P_pow2 <<= 1;

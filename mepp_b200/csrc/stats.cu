@@ -68,6 +68,7 @@ __global__ void col_constants_kernel(const double* __restrict__ col_syz, const d
 }
 
 // ------------------------------------------------------------------ K3 helpers
+constexpr int kRadixBins = 2048;   // 11-bit digits of the pooled radix select
 // Monotone float -> uint key (total order; -0 < +0).
 __device__ __forceinline__ uint32_t f2key(float f) {
   uint32_t u = __float_as_uint(f);
@@ -99,9 +100,11 @@ __device__ void bitonic_sort_keys(uint32_t* s, int n_pow2) {
 // |r_p| >= |r_0|, and the sorted row (as keys) for the pooled quantiles.
 __global__ void row_stats_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, int P_pow2, int k_lo, int k_hi,
                                  float* __restrict__ full_os, int32_t* __restrict__ full_cnt,
-                                 uint32_t* __restrict__ sorted_keys) {
+                                 uint32_t* __restrict__ hist1) {
   extern __shared__ uint32_t s_keys[];
   __shared__ int s_cnt;
+  __shared__ uint32_t s_h[kRadixBins];
+  for (int i = threadIdx.x; i < kRadixBins; i += blockDim.x) s_h[i] = 0u;
   const int P = C - 1;
   const int64_t row = (int64_t)blockIdx.y * L + blockIdx.x;
   const float* rr = r + row * ldr;
@@ -121,8 +124,12 @@ __global__ void row_stats_kernel(const float* __restrict__ r, int64_t ldr, int L
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
   __syncthreads();
+  // first digit of the pooled radix select (see radix_pass_kernel)
+  for (int i = threadIdx.x; i < P; i += blockDim.x) atomicAdd(&s_h[s_keys[i] >> 21], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kRadixBins; i += blockDim.x)
+    if (s_h[i]) atomicAdd(&hist1[(int64_t)blockIdx.y * kRadixBins + i], s_h[i]);
   bitonic_sort_keys(s_keys, P_pow2);
-  for (int i = threadIdx.x; i < P; i += blockDim.x) sorted_keys[row * P + i] = s_keys[i];
   if (threadIdx.x == 0) {
     const int k1 = min(k_lo + 1, P - 1), k3 = min(k_hi + 1, P - 1);
     float* o = full_os + row * 4;
@@ -164,53 +171,240 @@ __device__ __forceinline__ void bitonic_stage(uint32_t (&key)[Q], const int lane
   else if constexpr (K < 32 * Q) bitonic_stage<Q, 2 * K, K>(key, lane);
 }
 
-// Warp-per-row variant for P <= 1024: the whole row lives in registers (Q = P_pow2 / 32 keys per
-// lane, element e = lane + 32 q), bitonic stages with partner distance >= 32 are register-to-register
-// compare-exchanges, smaller distances are warp shuffles; no shared memory, no block barriers.
-template <int Q>
-__global__ void __launch_bounds__(256) row_stats_warp_kernel(const float* __restrict__ r, int64_t ldr, int64_t n_rows, int C,
-                                                             int k_lo, int k_hi, float* __restrict__ full_os,
-                                                             int32_t* __restrict__ full_cnt,
-                                                             uint32_t* __restrict__ sorted_keys) {
+// Warp-per-row variant for P <= 1024: the whole row lives in registers (Q = P_pow2 / 32 keys per lane, element
+// e = lane + 32 q).  FAST: only the few smallest / largest values matter (the interval ranks sit in the tails), so
+// instead of sorting the row the warp bounds each tail with a pivot -- the m-th smallest of the 64 minima of the
+// half-lane groups is >= the m-th smallest element -- compacts the <= 64 values beyond the pivot and sorts those;
+// a row with more than 64 candidates (heavy ties) falls through to the full bitonic network, whose stages with
+// partner distance >= 32 are register compare-exchanges and smaller distances warp shuffles.
+// grid = (row chunks, T): a CTA also accumulates the first digit of the pooled radix select for its task.
+constexpr int kRowWarps = 4;
+template <int Q, bool FAST>
+__global__ void __launch_bounds__(kRowWarps * 32, 3) row_stats_warp_kernel(const float* __restrict__ r, int64_t ldr, int L, int C,
+                                                                           int rows_per_cta, int k_lo, int k_hi,
+                                                                           float* __restrict__ full_os,
+                                                                           int32_t* __restrict__ full_cnt,
+                                                                           uint32_t* __restrict__ hist1) {
   const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
+  __shared__ uint32_t s_h[kRadixBins];
+  __shared__ uint32_t s_cand[kRowWarps][2][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = blockIdx.y;
   const int P = C - 1;
-  const float* rr = r + row * ldr;
-  const float t0 = fabsf(rr[0]);
-  uint32_t key[Q];
-  int cnt = 0;
+  for (int i = threadIdx.x; i < kRadixBins; i += blockDim.x) s_h[i] = 0u;
+  __syncthreads();
+  const int l0 = blockIdx.x * rows_per_cta, l1 = min(L, l0 + rows_per_cta);
+  const int r1 = min(k_lo + 1, P - 1), r3 = min(k_hi + 1, P - 1);
+  const unsigned lt = (1u << lane) - 1u;
+  // the row after this one is loaded while this one is processed (the loads of a row are the only long latency)
+  float nxt[Q];
+  float nxt0 = 0.0f;
+  auto load_row = [&](int l) {
+    const float* rr = r + ((int64_t)t * L + l) * ldr;
+    nxt0 = rr[0];
 #pragma unroll
-  for (int q = 0; q < Q; ++q) {
-    const int e = lane + 32 * q;
-    uint32_t kk = 0xffffffffu;  // pads sort to the end
-    if (e < P) {
-      const float v = rr[1 + e];
-      kk = f2key(v);
-      cnt += fabsf(v) >= t0 ? 1 : 0;
+    for (int q = 0; q < Q; ++q) {
+      const int e = lane + 32 * q;
+      nxt[q] = e < P ? rr[1 + e] : 0.0f;
     }
-    key[q] = kk;
-  }
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(full, cnt, o);
-  bitonic_stage<Q, 2, 1>(key, lane);
+  };
+  if (l0 + warp < l1) load_row(l0 + warp);
+#pragma unroll 1
+  for (int l = l0 + warp; l < l1; l += kRowWarps) {
+    const int64_t row = (int64_t)t * L + l;
+    const float t0 = fabsf(nxt0);
+    uint32_t key[Q];
+    int cnt = 0;
 #pragma unroll
-  for (int q = 0; q < Q; ++q) {
-    const int e = lane + 32 * q;
-    if (e < P) sorted_keys[row * P + e] = key[q];
-  }
-  const int ranks[4] = {k_lo, min(k_lo + 1, P - 1), k_hi, min(k_hi + 1, P - 1)};
+    for (int q = 0; q < Q; ++q) {
+      const int e = lane + 32 * q;
+      uint32_t kk = 0xffffffffu;  // pads sort to the end
+      if (e < P) {
+        const float v = nxt[q];
+        kk = f2key(v);
+        cnt += fabsf(v) >= t0 ? 1 : 0;
+        atomicAdd(&s_h[kk >> 21], 1u);
+      }
+      key[q] = kk;
+    }
+    if (l + kRowWarps < l1) load_row(l + kRowWarps);
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(full, cnt, o);
+    if (lane == 0) full_cnt[row] = cnt;
+    if constexpr (FAST) {
+      const int m_lo = r1 + 1, m_hi = P - k_hi;          // values needed from either tail (<= 64, checked on the host)
+      uint32_t gmin[2] = {0xffffffffu, 0xffffffffu}, gmax[2] = {0u, 0u};
 #pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    const int e = ranks[w];
-    uint32_t v = 0;
+      for (int q = 0; q < Q; ++q) {
+        const uint32_t kh = (lane + 32 * q) < P ? key[q] : 0u;
+        gmin[q / (Q / 2)] = min(gmin[q / (Q / 2)], key[q]);
+        gmax[q / (Q / 2)] = max(gmax[q / (Q / 2)], kh);
+      }
+      bitonic_stage<2, 2, 1>(gmin, lane);
+      bitonic_stage<2, 2, 1>(gmax, lane);
+      const int e_lo = m_lo - 1, e_hi = 64 - m_hi;
+      const uint32_t pivot_lo = __shfl_sync(full, (e_lo >> 5) ? gmin[1] : gmin[0], e_lo & 31);
+      const uint32_t pivot_hi = __shfl_sync(full, (e_hi >> 5) ? gmax[1] : gmax[0], e_hi & 31);
+      int n_lo = 0, n_hi = 0;
+      uint32_t* c_lo = s_cand[warp][0];
+      uint32_t* c_hi = s_cand[warp][1];
 #pragma unroll
-    for (int q = 0; q < Q; ++q)
-      if (q == (e >> 5)) v = key[q];
-    v = __shfl_sync(full, v, e & 31);
-    if (lane == 0) full_os[row * 4 + w] = key2f(v);
+      for (int q = 0; q < Q; ++q) {
+        const bool real = (lane + 32 * q) < P;
+        const bool is_lo = key[q] <= pivot_lo && real;
+        const bool is_hi = key[q] >= pivot_hi && real;
+        const unsigned b_lo = __ballot_sync(full, is_lo), b_hi = __ballot_sync(full, is_hi);
+        if (b_lo) {
+          const int pos = n_lo + __popc(b_lo & lt);
+          if (is_lo && pos < 64) c_lo[pos] = key[q];
+          n_lo += __popc(b_lo);
+        }
+        if (b_hi) {
+          const int pos = n_hi + __popc(b_hi & lt);
+          if (is_hi && pos < 64) c_hi[pos] = key[q];
+          n_hi += __popc(b_hi);
+        }
+      }
+      if (n_lo <= 64 && n_hi <= 64) {
+        __syncwarp();
+        uint32_t a[2], b[2];
+        a[0] = lane < n_lo ? c_lo[lane] : 0xffffffffu;  a[1] = lane + 32 < n_lo ? c_lo[lane + 32] : 0xffffffffu;
+        b[0] = lane < n_hi ? c_hi[lane] : 0u;           b[1] = lane + 32 < n_hi ? c_hi[lane + 32] : 0u;
+        bitonic_stage<2, 2, 1>(a, lane);
+        bitonic_stage<2, 2, 1>(b, lane);
+        // a: the n_lo smallest values ascending; b: (64 - n_hi) zero pads, then the n_hi largest ascending
+        const int i2 = k_hi - P + 64, i3 = r3 - P + 64;
+        const uint32_t v0 = __shfl_sync(full, (k_lo >> 5) ? a[1] : a[0], k_lo & 31);
+        const uint32_t v1 = __shfl_sync(full, (r1 >> 5) ? a[1] : a[0], r1 & 31);
+        const uint32_t v2 = __shfl_sync(full, (i2 >> 5) ? b[1] : b[0], i2 & 31);
+        const uint32_t v3 = __shfl_sync(full, (i3 >> 5) ? b[1] : b[0], i3 & 31);
+        if (lane == 0)
+          *reinterpret_cast<float4*>(full_os + row * 4) = make_float4(key2f(v0), key2f(v1), key2f(v2), key2f(v3));
+        __syncwarp();
+        continue;
+      }
+    }
+    bitonic_stage<Q, 2, 1>(key, lane);
+    const int ranks[4] = {k_lo, r1, k_hi, r3};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int e = ranks[w];
+      uint32_t v = 0;
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        if (q == (e >> 5)) v = key[q];
+      v = __shfl_sync(full, v, e & 31);
+      if (lane == 0) full_os[row * 4 + w] = key2f(v);
+    }
   }
-  if (lane == 0) full_cnt[row] = cnt;
+  __syncthreads();
+  for (int i = threadIdx.x; i < kRadixBins; i += blockDim.x)
+    if (s_h[i]) atomicAdd(&hist1[(int64_t)t * kRadixBins + i], s_h[i]);
+}
+
+// ---- pooled order statistics: exact radix select (11 + 11 + 10 bits of the order-preserving key) over the L * P
+// permuted values of a task.  The first digit is histogrammed by the row kernels above; radix_pick_kernel turns a
+// histogram into (bin holding the rank, rank inside the bin); radix_pass_kernel histograms the next digit of the
+// values whose prefix matches; four independent targets per task (ranks ks_lo, ks_lo+1, ks_hi, ks_hi+1).
+struct RadixState { uint32_t prefix[4]; unsigned long long rank[4]; };
+
+// grid = T, block = 128 (one warp per target).  digit_bits: width of the digit just histogrammed; shift: its position.
+__global__ void radix_pick_kernel(const uint32_t* __restrict__ hist, int hists_per_task, int n_bins, int shift,
+                                  RadixState* __restrict__ state, long long ks_lo, long long ks_hi, long long M, int first,
+                                  float* __restrict__ semi_os) {
+  const int t = blockIdx.x, j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RadixState* s = state + t;
+  unsigned long long rank;
+  uint32_t prefix = 0u;
+  if (first) {
+    long long rk = j == 0 ? ks_lo : j == 1 ? ks_lo + 1 : j == 2 ? ks_hi : ks_hi + 1;
+    rank = (unsigned long long)(rk > M - 1 ? M - 1 : rk);
+  } else {
+    rank = s->rank[j];
+    prefix = s->prefix[j];
+  }
+  const uint32_t* h = hist + ((int64_t)t * hists_per_task + (hists_per_task > 1 ? j : 0)) * kRadixBins;
+  // two levels: every lane sums a contiguous run of n_bins / 32 bins, the runs are scanned across the warp, then
+  // the run holding the rank is scanned bin by bin
+  const int per = n_bins >> 5;                          // 64 or 32 bins per lane
+  unsigned long long tot = 0ull;
+  {
+    const uint4* h4 = reinterpret_cast<const uint4*>(h + lane * per);
+    for (int i = 0; i < per / 4; ++i) {
+      const uint4 v = h4[i];
+      tot += (unsigned long long)v.x + v.y + v.z + v.w;
+    }
+  }
+  unsigned long long inc = tot;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  unsigned hit = __ballot_sync(0xffffffffu, inc > rank);
+  const int run = hit ? __ffs(hit) - 1 : 31;
+  unsigned long long before = __shfl_sync(0xffffffffu, inc - tot, run);
+  // inside the run: per / 32 bins per lane
+  const int sub = per >> 5;                             // 2 or 1
+  const uint32_t* hr = h + run * per + lane * sub;
+  const unsigned long long b0 = hr[0], b1 = sub == 2 ? hr[1] : 0ull;
+  unsigned long long inc2 = b0 + b1;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long u = __shfl_up_sync(0xffffffffu, inc2, o);
+    if (lane >= o) inc2 += u;
+  }
+  hit = __ballot_sync(0xffffffffu, before + inc2 > rank);
+  const int src = hit ? __ffs(hit) - 1 : 31;
+  const unsigned long long before_l = before + __shfl_sync(0xffffffffu, inc2 - (b0 + b1), src);
+  const unsigned long long s0 = __shfl_sync(0xffffffffu, b0, src);
+  int bin = run * per + src * sub;
+  unsigned long long in_bin = rank - before_l;
+  if (sub == 2 && before_l + s0 <= rank) { bin += 1; in_bin -= s0; }
+  if (lane == 0) {
+    prefix |= (uint32_t)bin << shift;
+    s->prefix[j] = prefix;
+    s->rank[j] = in_bin;
+    if (shift == 0) semi_os[t * 4 + j] = key2f(prefix);
+  }
+}
+
+// grid = (row chunks, T).  hist[t][j][digit] += 1 for every value whose bits above `shift + bits` equal target j's prefix.
+__global__ void __launch_bounds__(256) radix_pass_kernel(const float* __restrict__ r, int64_t ldr, int L, int C,
+                                                         int rows_per_cta, int shift, int bits,
+                                                         const RadixState* __restrict__ state, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_h[4][kRadixBins];
+  const int t = blockIdx.y;
+  const int P = C - 1;
+  for (int i = threadIdx.x; i < 4 * kRadixBins; i += blockDim.x) (&s_h[0][0])[i] = 0u;
+  const RadixState st = state[t];
+  const int hs = shift + bits;                          // bits below the prefix
+  const uint32_t p0 = st.prefix[0] >> hs, p1 = st.prefix[1] >> hs, p2 = st.prefix[2] >> hs, p3 = st.prefix[3] >> hs;
+  const uint32_t mask = (1u << bits) - 1u;
+  __syncthreads();
+  const int l0 = blockIdx.x * rows_per_cta, l1 = min(L, l0 + rows_per_cta);
+  for (int l = l0; l < l1; l += 4) {                    // four rows at a time: four loads in flight per thread
+    const float* rr = r + ((int64_t)t * L + l) * ldr + 1;
+    const int nr = min(4, l1 - l);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = j < nr ? rr[(int64_t)j * ldr + i] : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nr) {
+          const uint32_t k = f2key(v[j]);
+          const uint32_t hi = k >> hs, d = (k >> shift) & mask;
+          if (hi == p0) atomicAdd(&s_h[0][d], 1u);
+          if (hi == p1) atomicAdd(&s_h[1][d], 1u);
+          if (hi == p2) atomicAdd(&s_h[2][d], 1u);
+          if (hi == p3) atomicAdd(&s_h[3][d], 1u);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * kRadixBins; i += blockDim.x) {
+    const uint32_t v = (&s_h[0][0])[i];
+    if (v) atomicAdd(&hist[(int64_t)t * 4 * kRadixBins + i], v);
+  }
 }
 
 // Per task: sorted thresholds |r[l,0]| (ascending) for the pooled p-values.
@@ -261,10 +455,23 @@ __global__ void semi_count_kernel(const float* __restrict__ r, int64_t ldr, int 
                                   unsigned long long* __restrict__ hist, long long* __restrict__ semi_cnt) {
   const int t = blockIdx.x;
   unsigned long long* h = hist + (int64_t)t * (L + 1);
-  // in-place suffix sum by one thread (L is small); h[j] becomes sum_{idx >= j} hist[idx]
-  if (threadIdx.x == 0) {
-    unsigned long long run = 0;
-    for (int j = L; j >= 0; --j) { run += h[j]; h[j] = run; }
+  // in-place suffix sum, h[j] becomes sum_{idx >= j} hist[idx]: per-thread segments + a scan of the segment totals
+  {
+    __shared__ unsigned long long s_part[256];
+    const int n = L + 1;
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int lo = threadIdx.x * per, hi = min(n, lo + per);
+    unsigned long long sum = 0ull;
+    for (int j = lo; j < hi; ++j) sum += h[j];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long run = 0ull;
+      for (int i = (int)blockDim.x - 1; i >= 0; --i) { const unsigned long long v = s_part[i]; s_part[i] = run; run += v; }
+    }
+    __syncthreads();
+    unsigned long long run = s_part[threadIdx.x];      // sum of the segments to the right
+    for (int j = hi - 1; j >= lo; --j) { run += h[j]; h[j] = run; }
   }
   __syncthreads();
   const float* ts = ts_sorted + (int64_t)t * L;
@@ -280,45 +487,6 @@ __global__ void semi_count_kernel(const float* __restrict__ r, int64_t ldr, int 
   }
 }
 
-// Pooled order statistics by bisection on the key space over the sorted rows.
-// grid = (4 targets, T); smallest key K with #{keys <= K} >= rank+1.
-__global__ void semi_select_kernel(const uint32_t* __restrict__ sorted_keys, int L, int P,
-                                   long long ks_lo, long long ks_hi, float* __restrict__ semi_os) {
-  __shared__ unsigned long long s_red[32];
-  __shared__ unsigned long long s_total;
-  const int t = blockIdx.y;
-  const long long M = (long long)L * P;
-  long long rank = blockIdx.x == 0 ? ks_lo : blockIdx.x == 1 ? ks_lo + 1 : blockIdx.x == 2 ? ks_hi : ks_hi + 1;
-  if (rank > M - 1) rank = M - 1;
-  const uint32_t* base = sorted_keys + (int64_t)t * L * P;
-  uint32_t klo = 0u, khi = 0xffffffffu;
-  while (klo < khi) {
-    const uint32_t mid = klo + ((khi - klo) >> 1);
-    unsigned long long cnt = 0;
-    for (int l = threadIdx.x; l < L; l += blockDim.x) {
-      const uint32_t* row = base + (int64_t)l * P;
-      int lo = 0, hi = P;  // upper_bound(row, mid)
-      while (lo < hi) {
-        const int m = (lo + hi) >> 1;
-        if (row[m] <= mid) lo = m + 1; else hi = m;
-      }
-      cnt += (unsigned long long)lo;
-    }
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long tot = 0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w];
-      s_total = tot;
-    }
-    __syncthreads();
-    if ((long long)s_total >= rank + 1) khi = mid; else klo = mid + 1;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) semi_os[t * 4 + blockIdx.x] = key2f(klo);
-}
-
 // integral[t][c] = trapezoid over positions of |r[:, c]| (np.trapz, dx = 1).
 __global__ void integral_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, double* __restrict__ integral) {
   const int t = blockIdx.y;
@@ -327,7 +495,19 @@ __global__ void integral_kernel(const float* __restrict__ r, int64_t ldr, int L,
   const float* rr = r + (int64_t)t * L * ldr + c;
   double acc = 0.0;
   float prev = fabsf(rr[0]);
-  for (int l = 1; l < L; ++l) {
+  int l = 1;
+  for (; l + 8 <= L; l += 8) {                          // eight loads in flight, summed in position order
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = rr[(int64_t)(l + j) * ldr];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float cur = fabsf(v[j]);
+      acc += 0.5 * ((double)prev + (double)cur);
+      prev = cur;
+    }
+  }
+  for (; l < L; ++l) {
     const float cur = fabsf(rr[(int64_t)l * ldr]);
     acc += 0.5 * ((double)prev + (double)cur);
     prev = cur;
@@ -379,12 +559,16 @@ int mepp_col_constants(const double* col_syz_dev, const double* ysum_dev, const 
   return 0;
 }
 
+static int64_t up256(int64_t v) { return (v + 255) / 256 * 256; }
+
 int64_t mepp_perm_stats_work_bytes(int T, int L, int C) {
-  const int64_t P = C - 1;
-  int64_t keys = (int64_t)T * L * (P > 0 ? P : 1) * 4;
-  int64_t ts = (int64_t)T * L * 4;
-  int64_t hist = (int64_t)T * (L + 1) * 8;
-  return ((keys + 255) / 256 + (ts + 255) / 256 + (hist + 255) / 256) * 256;
+  (void)C;
+  const int64_t ts = up256((int64_t)T * L * 4);                     // sorted |r0| thresholds
+  const int64_t hist = up256((int64_t)T * (L + 1) * 8);             // pooled histogram against the thresholds
+  const int64_t h1 = up256((int64_t)T * mepp::kRadixBins * 4);      // radix select: first digit
+  const int64_t h23 = up256((int64_t)T * 4 * mepp::kRadixBins * 4); // second / third digit, four targets
+  const int64_t state = up256((int64_t)T * sizeof(mepp::RadixState));
+  return ts + hist + h1 + 2 * h23 + state;
 }
 
 int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C, int k_lo, int k_hi, int64_t ks_lo, int64_t ks_hi,
@@ -405,35 +589,51 @@ int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C, int k_
   MEPP_REQUIRE(L_pow2 <= 16384, "perm_stats: at most 16384 positions");
   cudaStream_t st = as_stream(stream);
   uint8_t* w = reinterpret_cast<uint8_t*>(work_dev);
-  const int64_t keys_b = ((int64_t)T * L * P * 4 + 255) / 256 * 256;
-  const int64_t ts_b = ((int64_t)T * L * 4 + 255) / 256 * 256;
-  uint32_t* sorted_keys = reinterpret_cast<uint32_t*>(w);
-  float* ts_sorted = reinterpret_cast<float*>(w + keys_b);
-  unsigned long long* hist = reinterpret_cast<unsigned long long*>(w + keys_b + ts_b);
-  MEPP_CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * (size_t)T * (L + 1), st));
+  const int64_t ts_b = up256((int64_t)T * L * 4), hist_b = up256((int64_t)T * (L + 1) * 8);
+  const int64_t h1_b = up256((int64_t)T * kRadixBins * 4), h23_b = up256((int64_t)T * 4 * kRadixBins * 4);
+  float* ts_sorted = reinterpret_cast<float*>(w);
+  unsigned long long* hist = reinterpret_cast<unsigned long long*>(w + ts_b);
+  uint32_t* hist1 = reinterpret_cast<uint32_t*>(w + ts_b + hist_b);
+  uint32_t* hist2 = reinterpret_cast<uint32_t*>(w + ts_b + hist_b + h1_b);
+  uint32_t* hist3 = reinterpret_cast<uint32_t*>(w + ts_b + hist_b + h1_b + h23_b);
+  RadixState* state = reinterpret_cast<RadixState*>(w + ts_b + hist_b + h1_b + 2 * h23_b);
+  MEPP_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)(hist_b + h1_b + 2 * h23_b), st));
 
+  // rows per CTA: enough CTAs to fill the machine, few enough that the per-task histogram flushes stay cheap
+  int chunks_r = (148 * 16 + T - 1) / T;
+  if (chunks_r > (L + 7) / 8) chunks_r = (L + 7) / 8;
+  if (chunks_r < 1) chunks_r = 1;
+  const int rows_per_cta = (L + chunks_r - 1) / chunks_r;
+  chunks_r = (L + rows_per_cta - 1) / rows_per_cta;
   if (P_pow2 <= 1024) {
-    // rows in registers, one warp per row
-    const int64_t n_rows = (int64_t)T * L;
-    const unsigned blocks = (unsigned)((n_rows + 7) / 8);
+    // rows in registers, one warp per row; tail selection when both tails need at most 40 values
     const int Q = P_pow2 <= 32 ? 1 : P_pow2 / 32;
-#define MEPP_ROW_WARP(QQ) row_stats_warp_kernel<QQ><<<blocks, 256, 0, st>>>(r_dev, ldr, n_rows, C, k_lo, k_hi, full_os_dev, \
-                                                                           full_cnt_dev, sorted_keys)
+    const bool fast = Q >= 8 && (k_lo + 2) <= 40 && (P - k_hi) <= 40;
+    const dim3 grid((unsigned)chunks_r, (unsigned)T);
+#define MEPP_ROW_WARP(QQ, FF) row_stats_warp_kernel<QQ, FF><<<grid, kRowWarps * 32, 0, st>>>(r_dev, ldr, L, C, rows_per_cta, k_lo, k_hi, \
+                                                                                 full_os_dev, full_cnt_dev, hist1)
     switch (Q) {
-      case 1: MEPP_ROW_WARP(1); break;
-      case 2: MEPP_ROW_WARP(2); break;
-      case 4: MEPP_ROW_WARP(4); break;
-      case 8: MEPP_ROW_WARP(8); break;
-      case 16: MEPP_ROW_WARP(16); break;
-      default: MEPP_ROW_WARP(32); break;
+      case 1: MEPP_ROW_WARP(1, false); break;
+      case 2: MEPP_ROW_WARP(2, false); break;
+      case 4: MEPP_ROW_WARP(4, false); break;
+      case 8: if (fast) MEPP_ROW_WARP(8, true); else MEPP_ROW_WARP(8, false); break;
+      case 16: if (fast) MEPP_ROW_WARP(16, true); else MEPP_ROW_WARP(16, false); break;
+      default: if (fast) MEPP_ROW_WARP(32, true); else MEPP_ROW_WARP(32, false); break;
     }
 #undef MEPP_ROW_WARP
   } else {
     const size_t row_smem = sizeof(uint32_t) * (size_t)P_pow2;
     MEPP_CUDA_CHECK(cudaFuncSetAttribute(row_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
     row_stats_kernel<<<dim3((unsigned)L, (unsigned)T), 256, row_smem, st>>>(
-        r_dev, ldr, L, C, P_pow2, k_lo, k_hi, full_os_dev, full_cnt_dev, sorted_keys);
+        r_dev, ldr, L, C, P_pow2, k_lo, k_hi, full_os_dev, full_cnt_dev, hist1);
   }
+  // pooled order statistics: two more digits of the radix select
+  const long long M = (long long)L * P;
+  radix_pick_kernel<<<(unsigned)T, 128, 0, st>>>(hist1, 1, kRadixBins, 21, state, ks_lo, ks_hi, M, 1, semi_os_dev);
+  radix_pass_kernel<<<dim3((unsigned)chunks_r, (unsigned)T), 256, 0, st>>>(r_dev, ldr, L, C, rows_per_cta, 10, 11, state, hist2);
+  radix_pick_kernel<<<(unsigned)T, 128, 0, st>>>(hist2, 4, kRadixBins, 10, state, ks_lo, ks_hi, M, 0, semi_os_dev);
+  radix_pass_kernel<<<dim3((unsigned)chunks_r, (unsigned)T), 256, 0, st>>>(r_dev, ldr, L, C, rows_per_cta, 0, 10, state, hist3);
+  radix_pick_kernel<<<(unsigned)T, 128, 0, st>>>(hist3, 4, 1024, 0, state, ks_lo, ks_hi, M, 0, semi_os_dev);
 
   const size_t thr_smem = sizeof(uint32_t) * (size_t)L_pow2;
   MEPP_CUDA_CHECK(cudaFuncSetAttribute(thresholds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thr_smem));
@@ -446,7 +646,6 @@ int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C, int k_
   if (chunks > L) chunks = L;
   semi_hist_kernel<<<dim3((unsigned)chunks, (unsigned)T), 256, hist_smem, st>>>(r_dev, ldr, L, C, ts_sorted, hist);
   semi_count_kernel<<<(unsigned)T, 256, 0, st>>>(r_dev, ldr, L, C, ts_sorted, hist, semi_cnt_dev);
-  semi_select_kernel<<<dim3(4, (unsigned)T), 256, 0, st>>>(sorted_keys, L, P, ks_lo, ks_hi, semi_os_dev);
   integral_kernel<<<dim3((unsigned)((C + 127) / 128), (unsigned)T), 128, 0, st>>>(r_dev, ldr, L, C, integral_dev);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;

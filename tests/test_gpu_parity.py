@@ -436,3 +436,47 @@ def test_device_finalisation_equals_host_finalisation(T, L, P, margin):
             assert np.array_equal(a, b, equal_nan=True), k
     for k in ref['task']:
         assert np.array_equal(got['task'][k], ref['task'][k]), k
+
+
+@pytest.mark.parametrize("T,L,P,ties", [(2, 50, 1000, False), (3, 40, 999, False), (2, 33, 257, False),
+                                        (1, 20, 2000, False), (2, 30, 1000, True), (2, 21, 100, False)])
+def test_perm_stats_against_numpy(T, L, P, ties):
+    """K3 on its own: per-row order statistics (tail selection in registers, full sort for heavy ties or wide
+    intervals), counts, pooled counts and the pooled order statistics (radix select) against numpy sorts."""
+    from mepp_b200 import _lib, stats_host
+    from mepp_b200.engine import _ptr
+    _engine()
+    rng = np.random.default_rng(P + L)
+    Cc = 1 + P
+    ld = Cc + 3
+    r_h = np.zeros((T * L, ld), dtype=np.float32)
+    vals = rng.normal(scale=0.03, size=(T * L, Cc)).astype(np.float32)
+    if ties:
+        vals = (np.round(vals * 40) / 40).astype(np.float32)          # a handful of distinct values
+    r_h[:, :Cc] = vals
+    r = torch.from_numpy(r_h).cuda()
+    for ci in (95, 80):
+        q = stats_host.percentile_q(ci)
+        k_lo, _ = stats_host.virtual_index(P, q[0]); k_hi, _ = stats_host.virtual_index(P, q[1])
+        ks_lo, _ = stats_host.virtual_index(L * P, q[0]); ks_hi, _ = stats_host.virtual_index(L * P, q[1])
+        full_os = torch.empty((T, L, 4), dtype=torch.float32, device='cuda'); full_cnt = torch.empty((T, L), dtype=torch.int32, device='cuda')
+        semi_os = torch.empty((T, 4), dtype=torch.float32, device='cuda'); semi_cnt = torch.empty((T, L), dtype=torch.int64, device='cuda')
+        integral = torch.empty((T, Cc), dtype=torch.float64, device='cuda')
+        work = torch.empty(int(_lib.lib.mepp_perm_stats_work_bytes(T, L, Cc)), dtype=torch.uint8, device='cuda')
+        _lib.check(_lib.lib.mepp_perm_stats(_ptr(r), ld, T, L, Cc, k_lo, k_hi, ks_lo, ks_hi, _ptr(full_os), _ptr(full_cnt),
+                                            _ptr(semi_os), _ptr(semi_cnt), _ptr(integral), _ptr(work), None), "perm_stats")
+        torch.cuda.synchronize()
+        perm = vals[:, 1:].reshape(T, L, P)
+        r0 = vals[:, 0].reshape(T, L)
+        srt = np.sort(perm, axis=-1)
+        want = np.stack([srt[..., k_lo], srt[..., min(k_lo + 1, P - 1)], srt[..., k_hi], srt[..., min(k_hi + 1, P - 1)]], axis=-1)
+        assert np.array_equal(full_os.cpu().numpy(), want), (ci, "per-row order statistics")
+        assert np.array_equal(full_cnt.cpu().numpy(), (np.abs(perm) >= np.abs(r0)[..., None]).sum(-1))
+        pooled = np.sort(perm.reshape(T, L * P), axis=-1)
+        M = L * P
+        wants = np.stack([pooled[:, ks_lo], pooled[:, min(ks_lo + 1, M - 1)], pooled[:, ks_hi], pooled[:, min(ks_hi + 1, M - 1)]], axis=-1)
+        assert np.array_equal(semi_os.cpu().numpy(), wants), (ci, "pooled order statistics")
+        ap = np.abs(perm).reshape(T, 1, L * P)
+        assert np.array_equal(semi_cnt.cpu().numpy(), (ap >= np.abs(r0)[..., None]).sum(-1))
+        integ = 0.5 * (np.abs(vals.reshape(T, L, Cc)[:, 1:].astype(np.float64)) + np.abs(vals.reshape(T, L, Cc)[:, :-1].astype(np.float64)))
+        assert np.allclose(integral.cpu().numpy(), integ.sum(1), rtol=1e-12)
