@@ -171,130 +171,153 @@ __device__ __forceinline__ void bitonic_stage(uint32_t (&key)[Q], const int lane
   else if constexpr (K < 32 * Q) bitonic_stage<Q, 2 * K, K>(key, lane);
 }
 
-// Warp-per-row variant for P <= 1024: the whole row lives in registers (Q = P_pow2 / 32 keys per lane, element
-// e = lane + 32 q).  FAST: only the few smallest / largest values matter (the interval ranks sit in the tails), so
-// instead of sorting the row the warp bounds each tail with a pivot -- the m-th smallest of the 64 minima of the
-// half-lane groups is >= the m-th smallest element -- compacts the <= 64 values beyond the pivot and sorts those;
-// a row with more than 64 candidates (heavy ties) falls through to the full bitonic network, whose stages with
-// partner distance >= 32 are register compare-exchanges and smaller distances warp shuffles.
+// Warp-per-row kernel for P <= 1024.  A row is staged in shared memory (cp.async, the next row of the warp in
+// flight while this one is processed) and turned into order-preserving keys in place.  Only the few smallest /
+// largest values matter (the interval ranks sit in the tails), so instead of sorting the row the warp bounds each
+// tail with a pivot -- the m-th smallest of the 64 minima of the half-lane groups is >= the m-th smallest element
+// -- compacts the <= 64 values beyond the pivot and sorts those in registers.  Rows with more than 64 candidates
+// (heavy ties) and intervals that need more than 40 values per tail take a bitonic sort of the staged row.
 // grid = (row chunks, T): a CTA also accumulates the first digit of the pooled radix select for its task.
 constexpr int kRowWarps = 4;
-template <int Q, bool FAST>
-__global__ void __launch_bounds__(kRowWarps * 32, 3) row_stats_warp_kernel(const float* __restrict__ r, int64_t ldr, int L, int C,
-                                                                           int rows_per_cta, int k_lo, int k_hi,
-                                                                           float* __restrict__ full_os,
-                                                                           int32_t* __restrict__ full_cnt,
-                                                                           uint32_t* __restrict__ hist1) {
+
+__device__ __forceinline__ void warp_sort_smem(uint32_t* s, int n_pow2, int lane) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n_pow2; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint32_t a = s[i], b = s[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { s[i] = b; s[ixj] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32) row_select_kernel(const float* __restrict__ r, int64_t ldr, int L, int C,
+                                                                    int P_pow2, int rows_per_cta, int k_lo, int k_hi,
+                                                                    int fast, float* __restrict__ full_os,
+                                                                    int32_t* __restrict__ full_cnt,
+                                                                    uint32_t* __restrict__ hist1) {
   const unsigned full = 0xffffffffu;
+  extern __shared__ __align__(16) uint32_t s_dyn[];     // [warps][2][P_pow2] row buffers
   __shared__ uint32_t s_h[kRadixBins];
   __shared__ uint32_t s_cand[kRowWarps][2][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = blockIdx.y;
   const int P = C - 1;
+  const int Q = P_pow2 >> 5;                            // >= 1
   for (int i = threadIdx.x; i < kRadixBins; i += blockDim.x) s_h[i] = 0u;
   __syncthreads();
   const int l0 = blockIdx.x * rows_per_cta, l1 = min(L, l0 + rows_per_cta);
   const int r1 = min(k_lo + 1, P - 1), r3 = min(k_hi + 1, P - 1);
+  const int m_lo = r1 + 1, m_hi = P - k_hi;             // values needed from either tail
   const unsigned lt = (1u << lane) - 1u;
-  // the row after this one is loaded while this one is processed (the loads of a row are the only long latency)
-  float nxt[Q];
-  float nxt0 = 0.0f;
-  auto load_row = [&](int l) {
-    const float* rr = r + ((int64_t)t * L + l) * ldr;
-    nxt0 = rr[0];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const int e = lane + 32 * q;
-      nxt[q] = e < P ? rr[1 + e] : 0.0f;
-    }
+  uint32_t* buf0 = s_dyn + (size_t)warp * 2 * P_pow2;
+  auto prefetch = [&](int l, uint32_t* dst) {
+    const float* rr = r + ((int64_t)t * L + l) * ldr + 1;
+    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+    for (int e = lane; e < P; e += 32)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * (uint32_t)e), "l"(rr + e) : "memory");
   };
-  if (l0 + warp < l1) load_row(l0 + warp);
+  int cur = 0;
+  if (l0 + warp < l1) prefetch(l0 + warp, buf0);
 #pragma unroll 1
   for (int l = l0 + warp; l < l1; l += kRowWarps) {
     const int64_t row = (int64_t)t * L + l;
-    const float t0 = fabsf(nxt0);
-    uint32_t key[Q];
+    uint32_t* key = buf0 + cur * P_pow2;
+    const float t0 = fabsf(r[row * ldr]);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    if (l + kRowWarps < l1) prefetch(l + kRowWarps, buf0 + (cur ^ 1) * P_pow2);
+    cur ^= 1;
+    // keys in place, count of |v| >= |r0|, first radix digit, minima / maxima of the two half-lane groups
     int cnt = 0;
-#pragma unroll
+    uint32_t gmin0 = 0xffffffffu, gmin1 = 0xffffffffu, gmax0 = 0u, gmax1 = 0u;
+    const int half = Q > 1 ? Q >> 1 : 1;
+#pragma unroll 4
     for (int q = 0; q < Q; ++q) {
       const int e = lane + 32 * q;
-      uint32_t kk = 0xffffffffu;  // pads sort to the end
+      uint32_t kk = 0xffffffffu;                        // pads sort to the end
       if (e < P) {
-        const float v = nxt[q];
+        const float v = __uint_as_float(key[e]);
         kk = f2key(v);
         cnt += fabsf(v) >= t0 ? 1 : 0;
         atomicAdd(&s_h[kk >> 21], 1u);
+        if (q >= half) { gmin1 = min(gmin1, kk); gmax1 = max(gmax1, kk); }
+        else { gmin0 = min(gmin0, kk); gmax0 = max(gmax0, kk); }
       }
-      key[q] = kk;
+      key[e] = kk;
     }
-    if (l + kRowWarps < l1) load_row(l + kRowWarps);
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(full, cnt, o);
     if (lane == 0) full_cnt[row] = cnt;
-    if constexpr (FAST) {
-      const int m_lo = r1 + 1, m_hi = P - k_hi;          // values needed from either tail (<= 64, checked on the host)
-      uint32_t gmin[2] = {0xffffffffu, 0xffffffffu}, gmax[2] = {0u, 0u};
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const uint32_t kh = (lane + 32 * q) < P ? key[q] : 0u;
-        gmin[q / (Q / 2)] = min(gmin[q / (Q / 2)], key[q]);
-        gmax[q / (Q / 2)] = max(gmax[q / (Q / 2)], kh);
-      }
+    __syncwarp();
+    bool done = false;
+    if (fast) {
+      uint32_t gmin[2] = {gmin0, gmin1}, gmax[2] = {gmax0, gmax1};
       bitonic_stage<2, 2, 1>(gmin, lane);
       bitonic_stage<2, 2, 1>(gmax, lane);
-      const int e_lo = m_lo - 1, e_hi = 64 - m_hi;
-      const uint32_t pivot_lo = __shfl_sync(full, (e_lo >> 5) ? gmin[1] : gmin[0], e_lo & 31);
-      const uint32_t pivot_hi = __shfl_sync(full, (e_hi >> 5) ? gmax[1] : gmax[0], e_hi & 31);
-      int n_lo = 0, n_hi = 0;
-      uint32_t* c_lo = s_cand[warp][0];
-      uint32_t* c_hi = s_cand[warp][1];
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const bool real = (lane + 32 * q) < P;
-        const bool is_lo = key[q] <= pivot_lo && real;
-        const bool is_hi = key[q] >= pivot_hi && real;
-        const unsigned b_lo = __ballot_sync(full, is_lo), b_hi = __ballot_sync(full, is_hi);
-        if (b_lo) {
-          const int pos = n_lo + __popc(b_lo & lt);
-          if (is_lo && pos < 64) c_lo[pos] = key[q];
-          n_lo += __popc(b_lo);
+      const uint32_t row_min = __shfl_sync(full, gmin[0], 0), row_max = __shfl_sync(full, gmax[1], 31);
+      if (row_min == row_max) {                         // a constant row (e.g. r = 0 where nothing matched)
+        if (lane == 0) {
+          const float v = key2f(row_min);
+          *reinterpret_cast<float4*>(full_os + row * 4) = make_float4(v, v, v, v);
         }
-        if (b_hi) {
-          const int pos = n_hi + __popc(b_hi & lt);
-          if (is_hi && pos < 64) c_hi[pos] = key[q];
-          n_hi += __popc(b_hi);
+        done = true;
+      } else {
+        const int e_lo = m_lo - 1, e_hi = 64 - m_hi;
+        const uint32_t pivot_lo = __shfl_sync(full, (e_lo >> 5) ? gmin[1] : gmin[0], e_lo & 31);
+        const uint32_t pivot_hi = __shfl_sync(full, (e_hi >> 5) ? gmax[1] : gmax[0], e_hi & 31);
+        int n_lo = 0, n_hi = 0;
+        uint32_t* c_lo = s_cand[warp][0];
+        uint32_t* c_hi = s_cand[warp][1];
+#pragma unroll 4
+        for (int q = 0; q < Q; ++q) {
+          const int e = lane + 32 * q;
+          const uint32_t kk = key[e];
+          const bool real = e < P;
+          const bool is_lo = kk <= pivot_lo && real;
+          const bool is_hi = kk >= pivot_hi && real;
+          const unsigned b_lo = __ballot_sync(full, is_lo), b_hi = __ballot_sync(full, is_hi);
+          if (b_lo) {
+            const int pos = n_lo + __popc(b_lo & lt);
+            if (is_lo && pos < 64) c_lo[pos] = kk;
+            n_lo += __popc(b_lo);
+          }
+          if (b_hi) {
+            const int pos = n_hi + __popc(b_hi & lt);
+            if (is_hi && pos < 64) c_hi[pos] = kk;
+            n_hi += __popc(b_hi);
+          }
+        }
+        if (n_lo <= 64 && n_hi <= 64) {
+          __syncwarp();
+          uint32_t a[2], b[2];
+          a[0] = lane < n_lo ? c_lo[lane] : 0xffffffffu;  a[1] = lane + 32 < n_lo ? c_lo[lane + 32] : 0xffffffffu;
+          b[0] = lane < n_hi ? c_hi[lane] : 0u;           b[1] = lane + 32 < n_hi ? c_hi[lane + 32] : 0u;
+          bitonic_stage<2, 2, 1>(a, lane);
+          bitonic_stage<2, 2, 1>(b, lane);
+          // a: the n_lo smallest values ascending; b: (64 - n_hi) zero pads, then the n_hi largest ascending
+          const int i2 = k_hi - P + 64, i3 = r3 - P + 64;
+          const uint32_t v0 = __shfl_sync(full, (k_lo >> 5) ? a[1] : a[0], k_lo & 31);
+          const uint32_t v1 = __shfl_sync(full, (r1 >> 5) ? a[1] : a[0], r1 & 31);
+          const uint32_t v2 = __shfl_sync(full, (i2 >> 5) ? b[1] : b[0], i2 & 31);
+          const uint32_t v3 = __shfl_sync(full, (i3 >> 5) ? b[1] : b[0], i3 & 31);
+          if (lane == 0)
+            *reinterpret_cast<float4*>(full_os + row * 4) = make_float4(key2f(v0), key2f(v1), key2f(v2), key2f(v3));
+          done = true;
         }
       }
-      if (n_lo <= 64 && n_hi <= 64) {
-        __syncwarp();
-        uint32_t a[2], b[2];
-        a[0] = lane < n_lo ? c_lo[lane] : 0xffffffffu;  a[1] = lane + 32 < n_lo ? c_lo[lane + 32] : 0xffffffffu;
-        b[0] = lane < n_hi ? c_hi[lane] : 0u;           b[1] = lane + 32 < n_hi ? c_hi[lane + 32] : 0u;
-        bitonic_stage<2, 2, 1>(a, lane);
-        bitonic_stage<2, 2, 1>(b, lane);
-        // a: the n_lo smallest values ascending; b: (64 - n_hi) zero pads, then the n_hi largest ascending
-        const int i2 = k_hi - P + 64, i3 = r3 - P + 64;
-        const uint32_t v0 = __shfl_sync(full, (k_lo >> 5) ? a[1] : a[0], k_lo & 31);
-        const uint32_t v1 = __shfl_sync(full, (r1 >> 5) ? a[1] : a[0], r1 & 31);
-        const uint32_t v2 = __shfl_sync(full, (i2 >> 5) ? b[1] : b[0], i2 & 31);
-        const uint32_t v3 = __shfl_sync(full, (i3 >> 5) ? b[1] : b[0], i3 & 31);
-        if (lane == 0)
-          *reinterpret_cast<float4*>(full_os + row * 4) = make_float4(key2f(v0), key2f(v1), key2f(v2), key2f(v3));
-        __syncwarp();
-        continue;
-      }
     }
-    bitonic_stage<Q, 2, 1>(key, lane);
-    const int ranks[4] = {k_lo, r1, k_hi, r3};
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const int e = ranks[w];
-      uint32_t v = 0;
-#pragma unroll
-      for (int q = 0; q < Q; ++q)
-        if (q == (e >> 5)) v = key[q];
-      v = __shfl_sync(full, v, e & 31);
-      if (lane == 0) full_os[row * 4 + w] = key2f(v);
+    if (!done) {
+      warp_sort_smem(key, P_pow2, lane);
+      if (lane == 0)
+        *reinterpret_cast<float4*>(full_os + row * 4) =
+            make_float4(key2f(key[k_lo]), key2f(key[r1]), key2f(key[k_hi]), key2f(key[r3]));
     }
+    __syncwarp();
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kRadixBins; i += blockDim.x)
@@ -606,21 +629,13 @@ int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C, int k_
   const int rows_per_cta = (L + chunks_r - 1) / chunks_r;
   chunks_r = (L + rows_per_cta - 1) / rows_per_cta;
   if (P_pow2 <= 1024) {
-    // rows in registers, one warp per row; tail selection when both tails need at most 40 values
-    const int Q = P_pow2 <= 32 ? 1 : P_pow2 / 32;
-    const bool fast = Q >= 8 && (k_lo + 2) <= 40 && (P - k_hi) <= 40;
-    const dim3 grid((unsigned)chunks_r, (unsigned)T);
-#define MEPP_ROW_WARP(QQ, FF) row_stats_warp_kernel<QQ, FF><<<grid, kRowWarps * 32, 0, st>>>(r_dev, ldr, L, C, rows_per_cta, k_lo, k_hi, \
-                                                                                 full_os_dev, full_cnt_dev, hist1)
-    switch (Q) {
-      case 1: MEPP_ROW_WARP(1, false); break;
-      case 2: MEPP_ROW_WARP(2, false); break;
-      case 4: MEPP_ROW_WARP(4, false); break;
-      case 8: if (fast) MEPP_ROW_WARP(8, true); else MEPP_ROW_WARP(8, false); break;
-      case 16: if (fast) MEPP_ROW_WARP(16, true); else MEPP_ROW_WARP(16, false); break;
-      default: if (fast) MEPP_ROW_WARP(32, true); else MEPP_ROW_WARP(32, false); break;
-    }
-#undef MEPP_ROW_WARP
+    // one warp per row, rows staged in shared memory; tail selection when both tails need at most 40 values
+    const int Pp = P_pow2 < 32 ? 32 : P_pow2;
+    const int fast = (Pp >= 256 && (k_lo + 2) <= 40 && (P - k_hi) <= 40) ? 1 : 0;
+    const size_t smem = sizeof(uint32_t) * (size_t)kRowWarps * 2 * Pp;
+    MEPP_CUDA_CHECK(cudaFuncSetAttribute(row_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    row_select_kernel<<<dim3((unsigned)chunks_r, (unsigned)T), kRowWarps * 32, smem, st>>>(
+        r_dev, ldr, L, C, Pp, rows_per_cta, k_lo, k_hi, fast, full_os_dev, full_cnt_dev, hist1);
   } else {
     const size_t row_smem = sizeof(uint32_t) * (size_t)P_pow2;
     MEPP_CUDA_CHECK(cudaFuncSetAttribute(row_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
