@@ -142,8 +142,8 @@ __global__ void y_colstats_kernel(const uint32_t* __restrict__ ysplit, const int
 // tiled operand holds (exactly representable in float32), zero in the padding rows / columns.
 __global__ void y_rows_kernel(const float* __restrict__ yhat, const int32_t* __restrict__ perm, int64_t N,
                               int64_t n_pad, int C, int64_t ldY, float* __restrict__ out) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t n = blockIdx.y;
+  const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  const int64_t n = blockIdx.x;
   if (c >= ldY) return;
   float v = 0.0f;
   if (c < C && n < N) {
@@ -167,8 +167,8 @@ int mepp_build_y_rows(const float* yhat_dev, const int32_t* perm_dev, int64_t N,
   MEPP_REQUIRE(mepp_device_ok(), "build_y_rows: no sm_100 CUDA device (no CPU fallback)");
   const int C = 1 + P;
   const int64_t ldY = mepp_y_rows_ld(C), n_pad = mepp_pad32(N);
-  MEPP_REQUIRE(n_pad <= 65535 * 1024LL, "build_y_rows: too many sequences");
-  dim3 grid((unsigned)((ldY + 255) / 256), (unsigned)n_pad);
+  MEPP_REQUIRE(n_pad < (1LL << 31) && (ldY + 255) / 256 <= 65535, "build_y_rows: shape too large");
+  dim3 grid((unsigned)n_pad, (unsigned)((ldY + 255) / 256));
   y_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(yhat_dev, perm_dev, N, n_pad, C, ldY, y_rows_dev);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
