@@ -67,6 +67,11 @@ int mepp_motif_table(const double* pwm, int m, int orientation_char,
                      double dp_precision,
                      float* lut, float* bias, int* n_filters, double* thr,
                      uint32_t* qtab, uint32_t* qthr);
+/* Same table for a threshold that is already known: the '+' and '+/-' orientations of a motif share
+ * filter 0 and its threshold (motif_layers.py:36-76), so the DP runs once per motif. */
+int mepp_motif_table_with_threshold(const double* pwm, int m, int orientation_char, double pseudocount,
+                                    const double* bg_in, int use_flags, double thr, float* lut, float* bias,
+                                    int* n_filters, uint32_t* qtab, uint32_t* qthr);
 
 /* ------------------------------------------------------------------ layout sizes */
 int64_t mepp_sym_words(int L);              /* W3 */
@@ -180,6 +185,9 @@ int mepp_correlation(const float* S_dev, int64_t ldS, const double* rowstats_dev
  * colconst_dev: double [8 + 2*C].  r_dev: float [m_rows][ldr], ldr = n_tiles_n*BN. */
 int mepp_col_constants(const double* col_syz_dev, const double* ysum_dev, const double* zsum_host2,
                        int64_t N, int C, int use_z, double* colconst_dev, void* stream);
+/* Same, with {sum zhat, sum zhat^2} read from device memory (no host synchronisation). */
+int mepp_col_constants_dev(const double* col_syz_dev, const double* ysum_dev, const double* zsum_dev, int64_t N, int C,
+                           int use_z, double* colconst_dev, void* stream);
 int mepp_profile_corr_gemm(const void* x_planes_dev, const void* y_planes_dev, const double* rowstats_dev,
                            const double* colconst_dev, float* r_dev, int64_t m_rows, int C, int64_t n_pad,
                            void* stream);

@@ -34,6 +34,7 @@ SIGNATURES = {
     "mepp_log_odds": (_i32, [_pd, _i32, _pd, _f64, _pd]),
     "mepp_threshold_from_p": (_i32, [_pd, _i32, _pd, _f64, _f64, _pd]),
     "mepp_motif_table": (_i32, [_pd, _i32, _i32, _f64, _f64, _pd, _i32, _f64, _pf, _pf, _pi, _pd, _vp, _vp]),
+    "mepp_motif_table_with_threshold": (_i32, [_pd, _i32, _i32, _f64, _pd, _i32, _f64, _pf, _pf, _pi, _vp, _vp]),
     "mepp_sym_words": (_i64, [_i32]),
     "mepp_pad32": (_i64, [_i64]),
     "mepp_x_planes_bytes": (_i64, [_i64, _i64]),
@@ -56,6 +57,7 @@ SIGNATURES = {
     "mepp_profile_gemm_check": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp]),
     "mepp_correlation": (_i32, [_vp, _i64, _vp, _vp, _vp, _pd, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),
     "mepp_col_constants": (_i32, [_vp, _vp, _pd, _i64, _i32, _i32, _vp, _vp]),
+    "mepp_col_constants_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "mepp_profile_corr_gemm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _vp]),
     "mepp_perm_stats_work_bytes": (_i64, [_i32, _i32, _i32]),
     "mepp_perm_stats": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i64, _i64,

@@ -64,8 +64,7 @@ def run_batch(
              normpath(f'{out_filepath}/' + motif_id_and_orientation_to_filepath(motif_id, orient)))
             for motif_id in motif_matrix_dict for orient in motif_orientations]      # batch.py:73-90 order
     tasks = [(motif_matrix_dict[mid], o) for mid, o, _ in tups]
-    costs = [parallel.task_cost(np.shape(pwm)[1], 1 if o in ('+', '-') else 2) for pwm, o in tasks]
-    my_ids = parallel.shard_tasks(costs, world)[rank]
+    my_ids = parallel.shard_task_units(tasks, world)[rank]      # orientation pairs of a motif stay on one rank
 
     rows = {}
     batch = None

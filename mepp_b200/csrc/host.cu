@@ -160,8 +160,8 @@ int mepp_threshold_from_p(const double* W, int m, const double* bg, double p,
     for (int j = 0; j < 4; ++j) {
       long s = mat[j * m + i] - minV;
       double b = bg[j];
-      const double* src = t0.data();
-      double* dst = t1.data() + s;
+      const double* __restrict__ src = t0.data();
+      double* __restrict__ dst = t1.data() + s;
       for (long r = 0; r <= hi; ++r) dst[r] += b * src[r];
       new_hi = std::max(new_hi, hi + s);
     }
@@ -178,10 +178,10 @@ int mepp_threshold_from_p(const double* W, int m, const double* bg, double p,
   return 0;
 }
 
-int mepp_motif_table(const double* pwm, int m, int orientation_char,
-                     double pseudocount, double pvalue, const double* bg_in, int use_flags,
-                     double dp_precision, float* lut, float* bias, int* n_filters, double* thr_out,
-                     uint32_t* qtab, uint32_t* qthr) {
+static int motif_table_impl(const double* pwm, int m, int orientation_char,
+                            double pseudocount, double pvalue, const double* bg_in, int use_flags,
+                            double dp_precision, const double* thr_given, float* lut, float* bias, int* n_filters,
+                            double* thr_out, uint32_t* qtab, uint32_t* qthr) {
   MEPP_REQUIRE(pwm && lut && bias && n_filters, "motif_table: null argument");
   MEPP_REQUIRE(m >= 1 && m <= MEPP_MAX_MOTIF_LEN, "motif_table: motif length must be in [1, 32]");
   double bg[4] = {0.25, 0.25, 0.25, 0.25};
@@ -203,7 +203,8 @@ int mepp_motif_table(const double* pwm, int m, int orientation_char,
     f1 = Wr.data();  // dual: filter 1 = W[::-1,::-1], shared bias -thr(W) (:66-74)
   }
   double thr = 0.0;
-  if (mepp_threshold_from_p(f0, m, bg, pv, dp_precision, &thr)) return 1;
+  if (thr_given) thr = *thr_given;
+  else if (mepp_threshold_from_p(f0, m, bg, pv, dp_precision, &thr)) return 1;
   for (int k = 0; k < MEPP_MAX_MOTIF_LEN * 8; ++k) lut[k] = 0.0f;
   for (int j = 0; j < m; ++j)
     for (int c = 0; c < 4; ++c) {
@@ -215,6 +216,21 @@ int mepp_motif_table(const double* pwm, int m, int orientation_char,
   if (thr_out) *thr_out = thr;
   if (qtab && qthr) mepp::build_filter_table(lut, m, *n_filters, *bias, qtab, qthr);
   return 0;
+}
+
+int mepp_motif_table(const double* pwm, int m, int orientation_char,
+                     double pseudocount, double pvalue, const double* bg_in, int use_flags,
+                     double dp_precision, float* lut, float* bias, int* n_filters, double* thr_out,
+                     uint32_t* qtab, uint32_t* qthr) {
+  return motif_table_impl(pwm, m, orientation_char, pseudocount, pvalue, bg_in, use_flags, dp_precision, nullptr, lut,
+                          bias, n_filters, thr_out, qtab, qthr);
+}
+
+int mepp_motif_table_with_threshold(const double* pwm, int m, int orientation_char, double pseudocount,
+                                    const double* bg_in, int use_flags, double thr, float* lut, float* bias,
+                                    int* n_filters, uint32_t* qtab, uint32_t* qthr) {
+  return motif_table_impl(pwm, m, orientation_char, pseudocount, 0.0, bg_in, use_flags, 0.0, &thr, lut, bias, n_filters,
+                          nullptr, qtab, qthr);
 }
 
 }  // extern "C"

@@ -52,8 +52,10 @@ __global__ void correlation_kernel(const CorrArgs a) {
 // Per-dataset constants of the correlation epilogue fused into the GEMM (gemm.cu): header
 // {n, sy, ay, sz, az, use_z, -, -} then per column {r_yz[c], 1 / sqrt(1 - r_yz[c]^2)}.
 __global__ void col_constants_kernel(const double* __restrict__ col_syz, const double* __restrict__ ysum,
-                                     double sz, double szz, double n, int C, int use_z, double* __restrict__ cc) {
+                                     double sz, double szz, const double* __restrict__ zsum_dev, double n, int C,
+                                     int use_z, double* __restrict__ cc) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (zsum_dev) { sz = zsum_dev[0]; szz = zsum_dev[1]; }
   const double sy = ysum[0], syy = ysum[1];
   const double ay = n * syy - sy * sy, az = n * szz - sz * sz;
   if (c == 0) { cc[0] = n; cc[1] = sy; cc[2] = ay; cc[3] = sz; cc[4] = az; cc[5] = (double)use_z; cc[6] = 0.0; cc[7] = 0.0; }
@@ -577,7 +579,20 @@ int mepp_col_constants(const double* col_syz_dev, const double* ysum_dev, const 
   MEPP_REQUIRE(!use_z || (col_syz_dev && zsum_host2), "col_constants: z statistics missing");
   MEPP_REQUIRE(mepp_device_ok(), "col_constants: no sm_100 CUDA device (no CPU fallback)");
   col_constants_kernel<<<(unsigned)((C + 255) / 256), 256, 0, as_stream(stream)>>>(
-      col_syz_dev, ysum_dev, use_z ? zsum_host2[0] : 0.0, use_z ? zsum_host2[1] : 0.0, (double)N, C, use_z, colconst_dev);
+      col_syz_dev, ysum_dev, use_z ? zsum_host2[0] : 0.0, use_z ? zsum_host2[1] : 0.0, nullptr, (double)N, C, use_z,
+      colconst_dev);
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mepp_col_constants_dev(const double* col_syz_dev, const double* ysum_dev, const double* zsum_dev, int64_t N, int C,
+                           int use_z, double* colconst_dev, void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(ysum_dev && colconst_dev && C > 0, "col_constants: bad arguments");
+  MEPP_REQUIRE(!use_z || (col_syz_dev && zsum_dev), "col_constants: z statistics missing");
+  MEPP_REQUIRE(mepp_device_ok(), "col_constants: no sm_100 CUDA device (no CPU fallback)");
+  col_constants_kernel<<<(unsigned)((C + 255) / 256), 256, 0, as_stream(stream)>>>(
+      col_syz_dev, ysum_dev, 0.0, 0.0, use_z ? zsum_dev : nullptr, (double)N, C, use_z, colconst_dev);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -243,11 +243,10 @@ class Engine:
     def _colconst(self):
         """Per-dataset constants of the fused correlation epilogue (built once per stage())."""
         if self._colconst_dev is None:
-            zsum = self._zsum()
             cc = self.torch.empty(8 + 2 * self.C, dtype=self.torch.float64, device=self.device)
-            _lib.check(_lib.lib.mepp_col_constants(_ptr(self.col_syz), _ptr(self.ysum),
-                                                   zsum.ctypes.data_as(C.POINTER(C.c_double)), self.N, self.C,
-                                                   1 if self.use_gc else 0, _ptr(cc), self._stream()), "col_constants")
+            _lib.check(_lib.lib.mepp_col_constants_dev(_ptr(self.col_syz), _ptr(self.ysum), _ptr(self._zsum_dev), self.N,
+                                                       self.C, 1 if self.use_gc else 0, _ptr(cc), self._stream()),
+                       "col_constants")
             self.launches += 1
             self._colconst_dev = cc
         return self._colconst_dev
@@ -309,9 +308,12 @@ class Engine:
         with torch.cuda.device(self.device):
             pending = None
             all_tables = []
+            # host threshold DP: every group's tables are submitted to the host thread pool now and collected when
+            # the group is launched, so the DP of the later groups runs while the earlier ones are on the GPU
+            futures = None if tables is not None else [motif_layers.scan_tables_async(tasks[g0:g1], **table_kw)
+                                                       for g0, g1 in groups]
             for gi, (g0, g1) in enumerate(groups):
-                # host threshold DP of this group only: the next group's tables are computed while this one runs
-                gt = tables[g0:g1] if tables is not None else motif_layers.scan_tables(tasks[g0:g1], **table_kw)
+                gt = tables[g0:g1] if tables is not None else futures[gi]()
                 all_tables.extend(gt)
                 nxt = self._launch_group(gt, margin, return_hits, return_r, hits_cap,
                                          confidence_interval_pct, gi % 2)

@@ -91,17 +91,53 @@ def _pool(n_threads=None):
     return _POOLS[n]
 
 
-def scan_tables(tasks, n_threads=None, **kw):
-    """Scan tables for a list of (motif_matrix, orientation); the DP runs threaded (ctypes drops the GIL).
-    '+' and dual tasks of the same motif share one threshold computation through a small cache."""
-    cache = {}
+def _table_with_threshold(motif_matrix, orientation, thr, pseudocount=0.0001, pvalue=0.0001, bg=None,
+                          honour_flags=False, dp_precision=DP_PRECISION):
+    """Scan table of a task whose threshold is already known (the '+' and dual orientations of a motif share it)."""
+    pwm = np.ascontiguousarray(motif_matrix, dtype=np.float64)
+    m = pwm.shape[1]
+    och = ord('+') if orientation == '+' else ord('-') if orientation == '-' else ord('d')
+    lut = np.zeros((_lib.MAX_MOTIF_LEN, 4, 2), dtype=np.float32)
+    bias = C.c_float(0.0)
+    nf = C.c_int(0)
+    bgp = _pd(np.ascontiguousarray(bg, dtype=np.float64)) if bg is not None else None
+    qtab = np.zeros(1024, dtype=np.uint32)
+    qthr = np.zeros(2, dtype=np.uint32)
+    _lib.check(_lib.lib.mepp_motif_table_with_threshold(
+        _pd(pwm), m, och, float(pseudocount), bgp, 1 if honour_flags else 0, float(thr),
+        lut.ctypes.data_as(C.POINTER(C.c_float)), C.byref(bias), C.byref(nf), qtab.ctypes.data, qthr.ctypes.data),
+        "motif_table_with_threshold")
+    return dict(lut=lut, bias=np.float32(bias.value), n_filters=nf.value, thr=float(thr), m=m, qtab=qtab, qthr=qthr,
+                pvalue=float(pvalue) if honour_flags else 0.0001)
+
+
+def scan_tables_async(tasks, n_threads=None, **kw):
+    """Submit the scan tables of a list of (motif_matrix, orientation) to the host thread pool (the threshold DP runs
+    in C, ctypes drops the GIL) and return a function that waits for them.  One DP per distinct (motif, filter-0
+    orientation): the '+' and dual tasks of a motif share the threshold of W (motif_layers.py:36-76)."""
+    first = {}
     keys = []
     for pwm, orient in tasks:
         o = orient if orient in ('+', '-') else 'd'
-        key = (np.ascontiguousarray(pwm, dtype=np.float64).tobytes(), np.shape(pwm), o)
-        keys.append(key)
-        cache.setdefault(key, (pwm, orient))
-    uniq = list(cache.items())
-    res = list(_pool(n_threads).map(lambda kv: motif_matrix_to_scan_table(kv[1][0], kv[1][1], **kw), uniq))
-    table = {kv[0]: r for kv, r in zip(uniq, res)}
-    return [table[k] for k in keys]
+        key = (np.ascontiguousarray(pwm, dtype=np.float64).tobytes(), np.shape(pwm), '-' if o == '-' else 'f')
+        keys.append((key, o))
+        first.setdefault(key, (pwm, orient))
+    pool = _pool(n_threads)
+    fut = {key: pool.submit(motif_matrix_to_scan_table, pwm, orient, **kw) for key, (pwm, orient) in first.items()}
+
+    def collect():
+        done, out = {}, []
+        for (key, o), (pwm, orient) in zip(keys, tasks):
+            if (key, o) not in done:
+                base = fut[key].result()
+                base_o = first[key][1] if first[key][1] in ('+', '-') else 'd'
+                done[(key, o)] = base if base_o == o else _table_with_threshold(pwm, orient, base['thr'], **kw)
+            out.append(done[(key, o)])
+        return out
+
+    return collect
+
+
+def scan_tables(tasks, n_threads=None, **kw):
+    """Scan tables for a list of (motif_matrix, orientation) (see scan_tables_async)."""
+    return scan_tables_async(tasks, n_threads, **kw)()

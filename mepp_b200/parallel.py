@@ -42,6 +42,25 @@ def shard_tasks(costs, world_size):
     return [sorted(s) for s in shards]
 
 
+def shard_task_units(tasks, world_size):
+    """shard_tasks over scan units: consecutive tasks with the same motif matrix (the reference's task order is
+    motif outer, orientation inner, batch.py:73-90) stay on one rank, so that the '+' orientation can ride on the
+    '+/-' pass of its motif (engine.scan_units).  tasks: [(motif_matrix (4, m), orientation)]."""
+    units, costs = [], []
+    prev = None
+    for i, (pwm, o) in enumerate(tasks):
+        key = (np.shape(pwm), np.ascontiguousarray(pwm).tobytes())
+        c = task_cost(np.shape(pwm)[1], 1 if o in ('+', '-') else 2)
+        if key == prev:
+            units[-1].append(i)
+            costs[-1] = max(costs[-1], c)          # the twin rides on the dual pass
+        else:
+            units.append([i])
+            costs.append(c)
+        prev = key
+    return [sorted(i for u in s for i in units[u]) for s in shard_tasks(costs, world_size)]
+
+
 def init_from_env(backend=None):
     """Initialise torch.distributed from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun).  Returns
     (rank, world_size, local_rank); a single-process run needs no process group."""

@@ -63,3 +63,16 @@ def test_gather_blocks_single_process():
     blk = np.arange(12, dtype=float).reshape(3, 4)
     out = parallel.gather_blocks(blk, [2, 0, 1], 3)
     assert np.array_equal(out[2], blk[0]) and np.array_equal(out[0], blk[1])
+
+
+def test_shard_task_units_keeps_orientation_pairs_together():
+    import numpy as np
+    from mepp_b200 import parallel
+    rng = np.random.default_rng(0)
+    motifs = [rng.random((4, m)) for m in (6, 8, 8, 12, 20, 9, 15)]
+    tasks = [(pwm, o) for pwm in motifs for o in ('+', '+/-')]
+    for world in (1, 2, 3):
+        shards = parallel.shard_task_units(tasks, world)
+        assert sorted(i for s in shards for i in s) == list(range(len(tasks)))
+        for s in shards:
+            assert all((i ^ 1) in s for i in s)            # task 2k and 2k+1 (same motif) on the same rank
