@@ -299,7 +299,7 @@ def main():
                                      "DRAM < 1 %): X is written as a list of its non-zeros, so almost no bytes move")
     if stage_ms.get("gemm") and sparse:
         # HBM: Y rows once (L2-resident afterwards), CSR records, r written once; L2 -> SM: one Y row per non-zero
-        ldY = -(-C_ // 1024) * 1024
+        ldY = -(-C_ // 512) * 512
         hbm = 4.0 * eng.n_pad * ldY + 24.0 * st["entries"] + 4.0 * n_local * L * eng.ldS
         l2 = 4.0 * ldY * st["entries"]
         a = hbm / per("gemm") / 1e9

@@ -7,7 +7,7 @@
 //     S[r, :] = sum over the non-zeros (n, x) of row r of   x * Y[n, :]
 // The scan kernel appends one record per non-zero; here they are binned by row (counting sort: offsets
 // by prefix sum, fill with a per-row cursor) and every warp gathers the Y rows of one X row for a slab of
-// 1024 columns, accumulating exact fp32 x fp32 products in float64.  Y (n_pad x ldY float32, 80 MB at
+// 512 columns, accumulating exact fp32 x fp32 products in float64.  Y (n_pad x ldY float32, 80 MB at
 // N = 20 000, P = 1000) stays L2-resident; the kernel is bound by L2 -> SM bandwidth (4 KB per non-zero).
 #include "common.cuh"
 #include <cfloat>
@@ -69,18 +69,29 @@ struct SparseArgs {
   int64_t m_rows; int C; int n_slabs;
 };
 
-__device__ __forceinline__ void fma8(double (&acc)[32], double x, const float4 (&v)[8]) {
+// float -> double without the F2F pipe (16 lanes / clk / SM on B200, a quarter of the DFMA rate; measured with
+// tools/micro/fp64_rate.cu): rebias the exponent with integer ops.  Exact for normal floats; +-0 maps to
+// +-2^-127 (Y holds no denormals, and a zero of Y then contributes |x| * 6e-39 to a sum of magnitude >> 1).
+__device__ __forceinline__ double f2d(float f) {
+  const uint32_t u = __float_as_uint(f);
+  const uint32_t hi = ((((u >> 3) & 0x0fffffffu) + 0x38000000u)) | (u & 0x80000000u);
+  return __hiloint2double((int)hi, (int)(u << 29));
+}
+
+constexpr int kSlabCols = 512;   // columns of S per warp: lane holds slab*512 + j*128 + lane*4 + {0..3}, j < 4
+
+__device__ __forceinline__ void fma4(double (&acc)[16], double x, const float4 (&v)[4]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    acc[4 * j + 0] = fma(x, (double)v[j].x, acc[4 * j + 0]);
-    acc[4 * j + 1] = fma(x, (double)v[j].y, acc[4 * j + 1]);
-    acc[4 * j + 2] = fma(x, (double)v[j].z, acc[4 * j + 2]);
-    acc[4 * j + 3] = fma(x, (double)v[j].w, acc[4 * j + 3]);
+  for (int j = 0; j < 4; ++j) {
+    acc[4 * j + 0] = fma(x, f2d(v[j].x), acc[4 * j + 0]);
+    acc[4 * j + 1] = fma(x, f2d(v[j].y), acc[4 * j + 1]);
+    acc[4 * j + 2] = fma(x, f2d(v[j].z), acc[4 * j + 2]);
+    acc[4 * j + 3] = fma(x, f2d(v[j].w), acc[4 * j + 3]);
   }
 }
 
-// One warp = one (row, slab of 1024 columns); lane holds columns slab*1024 + j*128 + lane*4 + {0..3}, j < 8.
-__global__ void __launch_bounds__(256) profile_sparse_kernel(const __grid_constant__ SparseArgs a) {
+// One warp = one (row, slab of 512 columns); four non-zeros (16 x 512 B of Y) in flight per warp.
+__global__ void __launch_bounds__(256, 3) profile_sparse_kernel(const __grid_constant__ SparseArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -94,32 +105,30 @@ __global__ void __launch_bounds__(256) profile_sparse_kernel(const __grid_consta
     const int64_t row = item / a.n_slabs;
     const int slab = (int)(item - row * a.n_slabs);
     const int beg = a.offsets[row], end = a.offsets[row + 1];
-    const float4* yb = reinterpret_cast<const float4*>(a.y_rows) + (int64_t)slab * 256 + lane;
-    double acc[32];
+    const float4* yb = reinterpret_cast<const float4*>(a.y_rows) + (int64_t)slab * (kSlabCols / 4) + lane;
+    double acc[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-    int e = beg;
-    uint2 nx0 = make_uint2(0u, 0u), nx1 = nx0;
-    if (e < end) nx0 = __ldg(a.csr + e);
-    if (e + 1 < end) nx1 = __ldg(a.csr + e + 1);
+    for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+    auto rec = [&](int e) { return e < end ? __ldg(a.csr + e) : make_uint2(0u, 0u); };   // (row 0, x = 0) past the end
+    uint2 c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = rec(beg + k);
 #pragma unroll 1
-    for (; e < end; e += 2) {
-      const uint2 e0 = nx0, e1 = nx1;
-      const bool two = e + 1 < end;
-      nx0 = make_uint2(0u, 0u); nx1 = nx0;
-      if (e + 2 < end) nx0 = __ldg(a.csr + e + 2);
-      if (e + 3 < end) nx1 = __ldg(a.csr + e + 3);
-      const float4* y0 = yb + (int64_t)e0.x * ld4;
-      const float4* y1 = yb + (int64_t)e1.x * ld4;     // (e1 = row 0 with x = 0 when the list is odd)
-      float4 v0[8], v1[8];
+    for (int e = beg; e < end; e += 4) {
+      float4 v[4][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v0[j] = __ldg(y0 + j * 32);
-      if (two) {
+      for (int k = 0; k < 4; ++k) {
+        const float4* y = yb + (int64_t)c[k].x * ld4;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v1[j] = __ldg(y1 + j * 32);
+        for (int j = 0; j < 4; ++j) v[k][j] = __ldg(y + j * 32);
       }
-      fma8(acc, (double)__uint_as_float(e0.y), v0);
-      if (two) fma8(acc, (double)__uint_as_float(e1.y), v1);
+      uint2 nx[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nx[k] = rec(e + 4 + k);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) fma4(acc, (double)__uint_as_float(c[k].y), v[k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c[k] = nx[k];
     }
     // correlation epilogue: core.py:182-193,255-265 in float64 + np.nan_to_num (core.py:602)
     const double sx = a.rowstats[row * 3 + 0], sxx = a.rowstats[row * 3 + 1], sxz = a.rowstats[row * 3 + 2];
@@ -133,17 +142,20 @@ __global__ void __launch_bounds__(256) profile_sparse_kernel(const __grid_consta
     }
     float* dst = a.r + row * a.ldr;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c0 = slab * 1024 + j * 128 + lane * 4;
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = slab * kSlabCols + j * 128 + lane * 4;
       if (c0 < a.ldr) {
         float o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int c = c0 + k;
+          const int col = c0 + k;
           float out = 0.0f;
-          if (c < a.C) {
+          if (col < a.C) {
             double rr = (n * acc[4 * j + k] - sxsy) * inv_xy;
-            if (use_z) rr = (rr - r_xz * __ldg(cc + 8 + 2 * c)) * row_den * __ldg(cc + 9 + 2 * c);
+            if (use_z) {
+              const double2 cz = __ldg(reinterpret_cast<const double2*>(cc + 8 + 2 * col));
+              rr = (rr - r_xz * cz.x) * row_den * cz.y;
+            }
             out = (float)rr;
             if (out != out) out = 0.0f;
             else if (isinf(out)) out = out > 0 ? FLT_MAX : -FLT_MAX;
@@ -160,7 +172,7 @@ __global__ void __launch_bounds__(256) profile_sparse_kernel(const __grid_consta
 
 extern "C" {
 
-int64_t mepp_y_rows_ld(int C) { return ((int64_t)C + 1023) / 1024 * 1024; }
+int64_t mepp_y_rows_ld(int C) { return ((int64_t)C + mepp::kSlabCols - 1) / mepp::kSlabCols * mepp::kSlabCols; }
 
 int64_t mepp_profile_sparse_work_bytes(int64_t m_rows, int64_t entry_cap) {
   return ((m_rows + 2) * 4 + 255) / 256 * 256 + entry_cap * 8;
@@ -188,8 +200,8 @@ int mepp_profile_sparse(const void* entries_dev, const unsigned long long* entry
   a.csr = csr; a.offsets = offsets;
   a.y_rows = y_rows_dev; a.ldY = mepp_y_rows_ld(C);
   a.rowstats = rowstats_dev; a.colconst = colconst_dev; a.r = r_dev; a.ldr = ldr;
-  a.m_rows = m_rows; a.C = C; a.n_slabs = (int)(a.ldY / 1024);
-  profile_sparse_kernel<<<148 * 6, 256, 0, st>>>(a);
+  a.m_rows = m_rows; a.C = C; a.n_slabs = (int)(a.ldY / kSlabCols);
+  profile_sparse_kernel<<<148 * 16, 256, 0, st>>>(a);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
