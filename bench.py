@@ -82,6 +82,10 @@ class ClockSampler:
         """Stop polling (NVML polling stalls CUDA API calls: +25 ms per end-to-end step was measured)."""
         if self.proc is not None and self.proc.poll() is None:
             self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2.0)            # really gone before the end-to-end region starts
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
 
     def stop(self, t0, t1):
         if self.proc is None:
@@ -245,7 +249,8 @@ def main():
 
     # (2) end to end from pinned host buffers (clock sampler halted: its NVML polling slows host-side CUDA calls)
     sampler.halt()
-    e2e_step()                                             # untimed: the first step after the sampler stops is erratic
+    for _ in range(2):                                     # untimed: the first steps after the sampler stops are erratic
+        e2e_step()
     sync_all()
     import gc
     gc.collect()

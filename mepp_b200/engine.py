@@ -126,6 +126,7 @@ class Engine:
         self.staged = False
         self._bufs = {}
         self._pins = {}
+        self._copy_stream = None
         self.launches = 0   # kernels launched by this engine (bench.py reports it)
         self.timing = None  # set to {} to collect per-stage CUDA-event times (ms)
         self.fuse_correlation = True   # False: separate GEMM (S) + correlation kernels (tests / A-B runs)
@@ -420,12 +421,14 @@ class Engine:
         else:
             entry_cap = -(-max(MIN_ENTRY_CAP, int(T * N * L * SPARSE_ENTRY_DENSITY)) // _lib.ENTRY_LISTS) * _lib.ENTRY_LISTS
             entries = self._buf('entries', entry_cap * 16, torch.uint8)
-            entry_count = self._buf('entry_count', (16 * _lib.ENTRY_LISTS,), torch.int64)
+            entry_count = self._buf(f'entry_count{slot}', (16 * _lib.ENTRY_LISTS,), torch.int64)
             row_nnz = self._buf('row_nnz', (m_rows + 1,), torch.int32)
         rowstats = self._buf('rowstats', (m_rows, 3), torch.float64)
         count = self._buf('count', (T, L), torch.int32)
-        density = self._buf('density', (T, self.n_pad), torch.int32)
-        hit_count = self._buf('hit_count', (1,), torch.int64)
+        # buffers that travel to the host are per staging slot: their copies run on a side stream while the next
+        # group's kernels already write the other slot
+        density = self._buf(f'density{slot}', (T, self.n_pad), torch.int32)
+        hit_count = self._buf(f'hit_count{slot}', (1,), torch.int64)
         # the match list is always kept: it is also what restores the all-zero state of x_planes after the GEMM
         cap = int(hits_cap) if hits_cap else max(1 << 20, int(T * N * L * 2e-3))
         hits_d = self._buf('hits', cap * 16, torch.uint8)
@@ -485,7 +488,7 @@ class Engine:
             self.launches += 10
             ev = self._mark(ev, 'perm_stats')
         # K4: every output column of the group on the device; the host only copies the block into the result table
-        out_d = self._buf('finalized', int(_lib.lib.mepp_finalize_out_bytes(T, L)), torch.uint8)
+        out_d = self._buf(f'finalized{slot}', int(_lib.lib.mepp_finalize_out_bytes(T, L)), torch.uint8)
         if P > 0:
             _, g_lo = stats_host.virtual_index(P, q[0])
             _, g_hi = stats_host.virtual_index(P, q[1])
@@ -510,14 +513,23 @@ class Engine:
         if return_r:
             dev['r'] = r.view(T, L, self.ldS)[:, :, :C_].contiguous()
         host = {}
-        for k, t in dev.items():
-            h = self._pinned(k, slot, t.shape, t.dtype)
-            h.copy_(t, non_blocking=True)
-            host[k] = h
-        done = torch.cuda.Event()
-        done.record(torch.cuda.current_stream(self.device))
+        # device -> host on a side stream: the next group's kernels do not wait for the copies
+        compute = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        ready = torch.cuda.Event()
+        ready.record(compute)
+        self._copy_stream.wait_event(ready)
+        with torch.cuda.stream(self._copy_stream):
+            for k, t in dev.items():
+                h = self._pinned(k, slot, t.shape, t.dtype)
+                h.copy_(t, non_blocking=True)
+                host[k] = h
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
         return dict(host=host, done=done, T=T, hits_d=hits_d, cap=cap, return_hits=return_hits, path=path,
-                    entry_cap=entry_cap, slot=slot, tables=tables, return_r=return_r, hits_cap=hits_cap)
+                    entry_cap=entry_cap, slot=slot, tables=tables, return_r=return_r, hits_cap=hits_cap,
+                    dev=dev)    # (keeps the copied tensors alive until the side stream is done with them)
 
     def _collect_group(self, pend, margin, ci, store, density_all):
         """Wait for one group's D2H copies and finalise its statistics on the host, straight into the
