@@ -80,6 +80,16 @@ class ProfileBatch:
         return X0
 
 
+_COPY_POOLS = {}
+
+
+def _copy_pool(n):
+    from concurrent.futures import ThreadPoolExecutor
+    if n not in _COPY_POOLS:
+        _COPY_POOLS[n] = ThreadPoolExecutor(max_workers=n, thread_name_prefix="mepp-copy")
+    return _COPY_POOLS[n]
+
+
 SPARSE_DENSITY_MAX = 5e-3     # expected non-zero fraction of X up to which the sparse profile path is used
 SPARSE_ENTRY_DENSITY = 8e-3   # capacity of the entry list as a fraction of T * N * L
 MIN_ENTRY_CAP = 1 << 20
@@ -133,6 +143,7 @@ class Engine:
         self.share_scans = os.environ.get("MEPP_SHARE_SCANS", "1") != "0"   # '+' rides on the '+/-' pass of its motif
         self.profile_path = os.environ.get("MEPP_PROFILE_PATH", "auto")     # 'auto' | 'sparse' | 'tensor'
         self.last_paths = []
+        self.copy_threads = int(os.environ.get("MEPP_COPY_THREADS", "4"))
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -543,8 +554,21 @@ class Engine:
                                       ci, pend['slot'], path='tensor')
             redo['t0'] = t0
             return self._collect_group(redo, margin, ci, store, density_all)
-        stats_host.store_finalized(store, t0, h['finalized'], T, self.L)
-        density_all[t0:t0 + T] = h['density'][:, :self.N]
+        # host side of a group = copies of the finalised block and of the densities into the result table;
+        # split over a few threads (memcpy drops the GIL) so that the exposed tail of the last group stays short
+        N = self.N
+
+        def job(a, b):
+            stats_host.store_finalized(store, t0, h['finalized'], T, self.L, a, b)
+            density_all[t0 + a:t0 + b] = h['density'][a:b, :N]
+
+        n_chunks = max(1, min(self.copy_threads, T // 8))
+        bounds = [T * i // n_chunks for i in range(n_chunks + 1)]
+        if n_chunks == 1:
+            job(0, T)
+        else:
+            for f in [_copy_pool(self.copy_threads).submit(job, bounds[i], bounds[i + 1]) for i in range(n_chunks)]:
+                f.result()
         out = dict(T=T)
         out['entries'] = int(h['entry_count'][::16].sum()) if 'entry_count' in h else 0
         nh = int(h['hit_count'][0])

@@ -208,23 +208,24 @@ def z_margin_f32(num_samples, confidence_interval_pct=95):
     return np.float32(_st.norm.ppf(1.0 - alpha / 2.0) * np.sqrt(1.0 / (num_samples - 3)))
 
 
-def store_finalized(store, t0, buf, T, L):
-    """Copy the output block of mepp_finalize_positions (include/mepp_b200.h, K4) of one task group into rows
-    t0 .. t0+T of the store.  buf: uint8 array (may be a pinned staging buffer)."""
+def store_finalized(store, t0, buf, T, L, a=0, b=None):
+    """Copy tasks a .. b of the output block of mepp_finalize_positions (include/mepp_b200.h, K4) of one task group
+    of T tasks into rows t0+a .. t0+b of the store.  buf: uint8 array (may be a pinned staging buffer)."""
     P = store['P']
     TL = T * L
-    sl = slice(t0, t0 + T)
+    b = T if b is None else b
+    sl = slice(t0 + a, t0 + b)
     pos, task = store['pos'], store['task']
     d64 = buf[:TL * 56].view(np.float64).reshape(7, T, L)
     f32 = buf[TL * 56:TL * 68].view(np.float32).reshape(3, T, L)
     for i, k in enumerate(FINALIZED_F64):
         if k in pos:
-            pos[k][sl] = d64[i]
+            pos[k][sl] = d64[i, a:b]
     for i, k in enumerate(FINALIZED_F32):
-        pos[k][sl] = f32[i]
+        pos[k][sl] = f32[i, a:b]
     if P > 0:
         off = (TL * 68 + 7) & ~7
         t64 = buf[off:off + T * 40].view(np.float64).reshape(5, T)
         for i, k in enumerate(FINALIZED_TASK_F64):
-            task[k][sl] = t64[i]
-        task['integral_r'][sl] = buf[off + T * 40:off + T * 44].view(np.float32)
+            task[k][sl] = t64[i, a:b]
+        task['integral_r'][sl] = buf[off + T * 40:off + T * 44].view(np.float32)[a:b]
