@@ -21,13 +21,13 @@ __device__ __forceinline__ double lerp_f32(float a, float b, double gamma) {
 
 // Continued fraction of the incomplete beta function (modified Lentz; converges in O(sqrt(max(a, b))) steps).
 __device__ double betacf(double a, double b, double x) {
-  const double tiny = 1e-300, eps = 1e-16;
+  const double tiny = 1e-300, eps = 1e-15;   // (1e-16 is below what d * c can reach: the loop then runs to its cap)
   const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
   double c = 1.0, d = 1.0 - qab * x / qap;
   if (fabs(d) < tiny) d = tiny;
   d = 1.0 / d;
   double h = d;
-  for (int m = 1; m <= 20000; ++m) {
+  for (int m = 1; m <= 3000; ++m) {
     const double m2 = 2.0 * m;
     double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
     d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;

@@ -391,18 +391,60 @@ __global__ void radix_pick_kernel(const uint32_t* __restrict__ hist, int hists_p
   }
 }
 
-// grid = (row chunks, T).  hist[t][j][digit] += 1 for every value whose bits above `shift + bits` equal target j's prefix.
-__global__ void __launch_bounds__(256) radix_pass_kernel(const float* __restrict__ r, int64_t ldr, int L, int C,
-                                                         int rows_per_cta, int shift, int bits,
-                                                         const RadixState* __restrict__ state, uint32_t* __restrict__ hist) {
-  __shared__ uint32_t s_h[4][kRadixBins];
+// Per task: sorted thresholds |r[l,0]| (ascending) for the pooled p-values, and a table that narrows the search
+// among them: the bit patterns of non-negative floats are ordered like the floats, so bin(a) = (bits(a) - bits(t_min))
+// >> shift is monotone; tab[b] = index of the first threshold whose bin is >= b (kNarrowBins + 1 entries, shift
+// chosen so that t_max lands in the last bin).  thr_par[t] = {bits(t_min), shift}.
+constexpr int kNarrowBins = 4096;
+__global__ void thresholds_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, int L_pow2,
+                                  float* __restrict__ ts_sorted, uint16_t* __restrict__ tab, uint32_t* __restrict__ thr_par) {
+  extern __shared__ uint32_t s_keys[];
+  const int t = blockIdx.x;
+  for (int i = threadIdx.x; i < L_pow2; i += blockDim.x)
+    s_keys[i] = i < L ? __float_as_uint(fabsf(r[((int64_t)t * L + i) * ldr])) : 0xffffffffu;
+  __syncthreads();
+  bitonic_sort_keys(s_keys, L_pow2);
+  for (int i = threadIdx.x; i < L; i += blockDim.x) ts_sorted[(int64_t)t * L + i] = __uint_as_float(s_keys[i]);
+  const uint32_t kmin = s_keys[0], kmax = s_keys[L - 1];
+  int shift = 0;
+  while (((kmax - kmin) >> shift) >= (uint32_t)kNarrowBins) ++shift;
+  uint16_t* tb = tab + (int64_t)t * (kNarrowBins + 2);
+  for (int j = threadIdx.x; j < L; j += blockDim.x) {
+    const int bj = (int)((s_keys[j] - kmin) >> shift);
+    const int bp = j == 0 ? -1 : (int)((s_keys[j - 1] - kmin) >> shift);
+    for (int b = bp + 1; b <= bj; ++b) tb[b] = (uint16_t)j;      // first threshold with bin >= b
+  }
+  const int b_last = (int)((kmax - kmin) >> shift);
+  for (int b = b_last + 1 + threadIdx.x; b <= kNarrowBins; b += blockDim.x) tb[b] = (uint16_t)L;
+  if (threadIdx.x == 0) { thr_par[2 * t] = kmin; thr_par[2 * t + 1] = (uint32_t)shift; }
+}
+
+// One pass over the permuted values of a task for two things: (1) the histogram of the pooled |r_perm| values
+// against the task's sorted thresholds, hist[idx] = number of values with exactly idx thresholds <= |v| (the
+// narrowing table leaves a search range of a few thresholds); (2) the second digit of the pooled radix select.
+// grid = (row chunks, T); dynamic shared memory: thresholds [L], hist [L + 1], tab [kNarrowBins + 2] (uint16),
+// radix histograms [4][kRadixBins].
+__global__ void __launch_bounds__(256) pooled_pass_kernel(const float* __restrict__ r, int64_t ldr, int L, int C,
+                                                          int rows_per_cta, const float* __restrict__ ts_sorted,
+                                                          const uint16_t* __restrict__ tab,
+                                                          const uint32_t* __restrict__ thr_par,
+                                                          const RadixState* __restrict__ state,
+                                                          unsigned long long* __restrict__ hist,
+                                                          uint32_t* __restrict__ hist2) {
+  extern __shared__ uint32_t s_raw[];
+  float* s_ts = reinterpret_cast<float*>(s_raw);        // [L]
+  uint32_t* s_hist = s_raw + L;                         // [L + 1]
+  uint32_t* s_h2 = s_hist + L + 1;                      // [4][kRadixBins]
+  uint16_t* s_tab = reinterpret_cast<uint16_t*>(s_h2 + 4 * kRadixBins);   // [kNarrowBins + 2]
   const int t = blockIdx.y;
   const int P = C - 1;
-  for (int i = threadIdx.x; i < 4 * kRadixBins; i += blockDim.x) (&s_h[0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) s_ts[i] = ts_sorted[(int64_t)t * L + i];
+  for (int i = threadIdx.x; i <= L; i += blockDim.x) s_hist[i] = 0;
+  for (int i = threadIdx.x; i < 4 * kRadixBins; i += blockDim.x) s_h2[i] = 0u;
+  for (int i = threadIdx.x; i < kNarrowBins + 2; i += blockDim.x) s_tab[i] = tab[(int64_t)t * (kNarrowBins + 2) + i];
+  const uint32_t kmin = thr_par[2 * t], shift = thr_par[2 * t + 1];
   const RadixState st = state[t];
-  const int hs = shift + bits;                          // bits below the prefix
-  const uint32_t p0 = st.prefix[0] >> hs, p1 = st.prefix[1] >> hs, p2 = st.prefix[2] >> hs, p3 = st.prefix[3] >> hs;
-  const uint32_t mask = (1u << bits) - 1u;
+  const uint32_t p0 = st.prefix[0] >> 21, p1 = st.prefix[1] >> 21, p2 = st.prefix[2] >> 21, p3 = st.prefix[3] >> 21;
   __syncthreads();
   const int l0 = blockIdx.x * rows_per_cta, l1 = min(L, l0 + rows_per_cta);
   for (int l = l0; l < l1; l += 4) {                    // four rows at a time: four loads in flight per thread
@@ -415,64 +457,34 @@ __global__ void __launch_bounds__(256) radix_pass_kernel(const float* __restrict
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (j < nr) {
+          const float a = fabsf(v[j]);
+          const uint32_t ab = __float_as_uint(a);
+          int lo = 0, hi = 0;                           // below every threshold: none is <= a
+          if (ab >= kmin) {
+            const uint32_t b = min((ab - kmin) >> shift, (uint32_t)kNarrowBins);
+            lo = s_tab[b];
+            hi = b < (uint32_t)kNarrowBins ? s_tab[b + 1] : L;
+          }
+          while (lo < hi) {                             // upper_bound inside the bin: number of thresholds <= a
+            const int mid = (lo + hi) >> 1;
+            if (s_ts[mid] <= a) lo = mid + 1; else hi = mid;
+          }
+          atomicAdd(&s_hist[lo], 1u);
           const uint32_t k = f2key(v[j]);
-          const uint32_t hi = k >> hs, d = (k >> shift) & mask;
-          if (hi == p0) atomicAdd(&s_h[0][d], 1u);
-          if (hi == p1) atomicAdd(&s_h[1][d], 1u);
-          if (hi == p2) atomicAdd(&s_h[2][d], 1u);
-          if (hi == p3) atomicAdd(&s_h[3][d], 1u);
+          const uint32_t top = k >> 21, d = (k >> 10) & 2047u;
+          if (top == p0) atomicAdd(&s_h2[0 * kRadixBins + d], 1u);
+          if (top == p1) atomicAdd(&s_h2[1 * kRadixBins + d], 1u);
+          if (top == p2) atomicAdd(&s_h2[2 * kRadixBins + d], 1u);
+          if (top == p3) atomicAdd(&s_h2[3 * kRadixBins + d], 1u);
         }
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 4 * kRadixBins; i += blockDim.x) {
-    const uint32_t v = (&s_h[0][0])[i];
-    if (v) atomicAdd(&hist[(int64_t)t * 4 * kRadixBins + i], v);
-  }
-}
-
-// Per task: sorted thresholds |r[l,0]| (ascending) for the pooled p-values.
-__global__ void thresholds_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, int L_pow2,
-                                  float* __restrict__ ts_sorted) {
-  extern __shared__ uint32_t s_keys[];
-  const int t = blockIdx.x;
-  for (int i = threadIdx.x; i < L_pow2; i += blockDim.x)
-    s_keys[i] = i < L ? f2key(fabsf(r[((int64_t)t * L + i) * ldr])) : 0xffffffffu;
-  __syncthreads();
-  bitonic_sort_keys(s_keys, L_pow2);
-  for (int i = threadIdx.x; i < L; i += blockDim.x) ts_sorted[(int64_t)t * L + i] = key2f(s_keys[i]);
-}
-
-// Histogram of the pooled |r_perm| values against the task's sorted thresholds:
-// hist[idx] counts values with exactly idx thresholds <= |v|.
-__global__ void semi_hist_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, const float* __restrict__ ts_sorted,
-                                 unsigned long long* __restrict__ hist) {
-  extern __shared__ uint32_t s_raw[];
-  float* s_ts = reinterpret_cast<float*>(s_raw);        // [L]
-  uint32_t* s_hist = s_raw + L;                         // [L + 1]
-  const int t = blockIdx.y;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) s_ts[i] = ts_sorted[(int64_t)t * L + i];
-  for (int i = threadIdx.x; i <= L; i += blockDim.x) s_hist[i] = 0;
-  __syncthreads();
-  const int rows_per = (L + gridDim.x - 1) / gridDim.x;
-  const int l0 = blockIdx.x * rows_per, l1 = min(L, l0 + rows_per);
-  const int P = C - 1;
-  for (int l = l0; l < l1; ++l) {
-    const float* rr = r + ((int64_t)t * L + l) * ldr + 1;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-      const float a = fabsf(rr[i]);
-      int lo = 0, hi = L;  // upper_bound: number of thresholds <= a
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (s_ts[mid] <= a) lo = mid + 1; else hi = mid;
-      }
-      atomicAdd(&s_hist[lo], 1u);
-    }
-  }
-  __syncthreads();
   for (int i = threadIdx.x; i <= L; i += blockDim.x)
     if (s_hist[i]) atomicAdd(&hist[(int64_t)t * (L + 1) + i], (unsigned long long)s_hist[i]);
+  for (int i = threadIdx.x; i < 4 * kRadixBins; i += blockDim.x)
+    if (s_h2[i]) atomicAdd(&hist2[(int64_t)t * 4 * kRadixBins + i], s_h2[i]);
 }
 
 // Per task: semi_cnt[l] = #{pooled |v| >= |r[l,0]|} from the histogram (suffix sums).
@@ -512,32 +524,60 @@ __global__ void semi_count_kernel(const float* __restrict__ r, int64_t ldr, int 
   }
 }
 
-// integral[t][c] = trapezoid over positions of |r[:, c]| (np.trapz, dx = 1).
-__global__ void integral_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, double* __restrict__ integral) {
+// integral[t][c] = trapezoid over positions of |r[:, c]| (np.trapz, dx = 1); the same pass histograms the third
+// (last, 10-bit) digit of the pooled radix select.  grid = (column blocks, T), one thread per column.
+__global__ void __launch_bounds__(128) integral_pass_kernel(const float* __restrict__ r, int64_t ldr, int L, int C,
+                                                            const RadixState* __restrict__ state,
+                                                            double* __restrict__ integral, uint32_t* __restrict__ hist3) {
+  __shared__ uint32_t s_h3[4][1024];
   const int t = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float* rr = r + (int64_t)t * L * ldr + c;
-  double acc = 0.0;
-  float prev = fabsf(rr[0]);
-  int l = 1;
-  for (; l + 8 <= L; l += 8) {                          // eight loads in flight, summed in position order
-    float v[8];
+  for (int i = threadIdx.x; i < 4 * 1024; i += blockDim.x) (&s_h3[0][0])[i] = 0u;
+  const RadixState st = state[t];
+  const uint32_t p0 = st.prefix[0] >> 10, p1 = st.prefix[1] >> 10, p2 = st.prefix[2] >> 10, p3 = st.prefix[3] >> 10;
+  __syncthreads();
+  if (c < C) {
+    const float* rr = r + (int64_t)t * L * ldr + c;
+    const bool perm = c >= 1;                            // column 0 is the unpermuted profile: not in the pooled null
+    auto digit = [&](float v) {
+      const uint32_t k = f2key(v);
+      const uint32_t top = k >> 10, d = k & 1023u;
+      if (top == p0) atomicAdd(&s_h3[0][d], 1u);
+      if (top == p1) atomicAdd(&s_h3[1][d], 1u);
+      if (top == p2) atomicAdd(&s_h3[2][d], 1u);
+      if (top == p3) atomicAdd(&s_h3[3][d], 1u);
+    };
+    double acc = 0.0;
+    const float v0 = rr[0];
+    if (perm) digit(v0);
+    float prev = fabsf(v0);
+    int l = 1;
+    for (; l + 8 <= L; l += 8) {                          // eight loads in flight, summed in position order
+      float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = rr[(int64_t)(l + j) * ldr];
+      for (int j = 0; j < 8; ++j) v[j] = rr[(int64_t)(l + j) * ldr];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float cur = fabsf(v[j]);
+      for (int j = 0; j < 8; ++j) {
+        if (perm) digit(v[j]);
+        const float cur = fabsf(v[j]);
+        acc += 0.5 * ((double)prev + (double)cur);
+        prev = cur;
+      }
+    }
+    for (; l < L; ++l) {
+      const float v = rr[(int64_t)l * ldr];
+      if (perm) digit(v);
+      const float cur = fabsf(v);
       acc += 0.5 * ((double)prev + (double)cur);
       prev = cur;
     }
+    integral[(int64_t)t * C + c] = acc;
   }
-  for (; l < L; ++l) {
-    const float cur = fabsf(rr[(int64_t)l * ldr]);
-    acc += 0.5 * ((double)prev + (double)cur);
-    prev = cur;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * 1024; i += blockDim.x) {
+    const uint32_t v = (&s_h3[0][0])[i];
+    if (v) atomicAdd(&hist3[(int64_t)t * 4 * kRadixBins + (i >> 10) * kRadixBins + (i & 1023)], v);
   }
-  integral[(int64_t)t * C + c] = acc;
 }
 
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -606,7 +646,8 @@ int64_t mepp_perm_stats_work_bytes(int T, int L, int C) {
   const int64_t h1 = up256((int64_t)T * mepp::kRadixBins * 4);      // radix select: first digit
   const int64_t h23 = up256((int64_t)T * 4 * mepp::kRadixBins * 4); // second / third digit, four targets
   const int64_t state = up256((int64_t)T * sizeof(mepp::RadixState));
-  return ts + hist + h1 + 2 * h23 + state;
+  const int64_t tab = up256((int64_t)T * (mepp::kNarrowBins + 2) * 2) + up256((int64_t)T * 8);   // narrowing table + parameters
+  return ts + hist + h1 + 2 * h23 + state + tab;
 }
 
 int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C, int k_lo, int k_hi, int64_t ks_lo, int64_t ks_hi,
@@ -635,6 +676,9 @@ int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C, int k_
   uint32_t* hist2 = reinterpret_cast<uint32_t*>(w + ts_b + hist_b + h1_b);
   uint32_t* hist3 = reinterpret_cast<uint32_t*>(w + ts_b + hist_b + h1_b + h23_b);
   RadixState* state = reinterpret_cast<RadixState*>(w + ts_b + hist_b + h1_b + 2 * h23_b);
+  const int64_t state_b = up256((int64_t)T * sizeof(RadixState)), tab_b = up256((int64_t)T * (kNarrowBins + 2) * 2);
+  uint16_t* tab = reinterpret_cast<uint16_t*>(w + ts_b + hist_b + h1_b + 2 * h23_b + state_b);
+  uint32_t* thr_par = reinterpret_cast<uint32_t*>(w + ts_b + hist_b + h1_b + 2 * h23_b + state_b + tab_b);
   MEPP_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)(hist_b + h1_b + 2 * h23_b), st));
 
   // rows per CTA: enough CTAs to fill the machine, few enough that the per-task histogram flushes stay cheap
@@ -657,26 +701,22 @@ int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C, int k_
     row_stats_kernel<<<dim3((unsigned)L, (unsigned)T), 256, row_smem, st>>>(
         r_dev, ldr, L, C, P_pow2, k_lo, k_hi, full_os_dev, full_cnt_dev, hist1);
   }
-  // pooled order statistics: two more digits of the radix select
+  // pooled statistics: the first radix digit is in hist1; the second rides on the pass that histograms the
+  // pooled |r| against the thresholds, the third on the pass that integrates the columns
   const long long M = (long long)L * P;
   radix_pick_kernel<<<(unsigned)T, 128, 0, st>>>(hist1, 1, kRadixBins, 21, state, ks_lo, ks_hi, M, 1, semi_os_dev);
-  radix_pass_kernel<<<dim3((unsigned)chunks_r, (unsigned)T), 256, 0, st>>>(r_dev, ldr, L, C, rows_per_cta, 10, 11, state, hist2);
-  radix_pick_kernel<<<(unsigned)T, 128, 0, st>>>(hist2, 4, kRadixBins, 10, state, ks_lo, ks_hi, M, 0, semi_os_dev);
-  radix_pass_kernel<<<dim3((unsigned)chunks_r, (unsigned)T), 256, 0, st>>>(r_dev, ldr, L, C, rows_per_cta, 0, 10, state, hist3);
-  radix_pick_kernel<<<(unsigned)T, 128, 0, st>>>(hist3, 4, 1024, 0, state, ks_lo, ks_hi, M, 0, semi_os_dev);
-
   const size_t thr_smem = sizeof(uint32_t) * (size_t)L_pow2;
   MEPP_CUDA_CHECK(cudaFuncSetAttribute(thresholds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thr_smem));
-  thresholds_kernel<<<(unsigned)T, 256, thr_smem, st>>>(r_dev, ldr, L, C, L_pow2, ts_sorted);
-
-  const size_t hist_smem = sizeof(uint32_t) * (size_t)(2 * L + 1);
-  MEPP_CUDA_CHECK(cudaFuncSetAttribute(semi_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-  int chunks = (int)(((int64_t)L * P + 65535) / 65536);
-  if (chunks < 1) chunks = 1;
-  if (chunks > L) chunks = L;
-  semi_hist_kernel<<<dim3((unsigned)chunks, (unsigned)T), 256, hist_smem, st>>>(r_dev, ldr, L, C, ts_sorted, hist);
+  thresholds_kernel<<<(unsigned)T, 256, thr_smem, st>>>(r_dev, ldr, L, C, L_pow2, ts_sorted, tab, thr_par);
+  const size_t pool_smem = sizeof(uint32_t) * (size_t)(2 * L + 1 + 4 * kRadixBins) + sizeof(uint16_t) * (kNarrowBins + 2);
+  MEPP_CUDA_CHECK(cudaFuncSetAttribute(pooled_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem));
+  pooled_pass_kernel<<<dim3((unsigned)chunks_r, (unsigned)T), 256, pool_smem, st>>>(r_dev, ldr, L, C, rows_per_cta, ts_sorted,
+                                                                                  tab, thr_par, state, hist, hist2);
   semi_count_kernel<<<(unsigned)T, 256, 0, st>>>(r_dev, ldr, L, C, ts_sorted, hist, semi_cnt_dev);
-  integral_kernel<<<dim3((unsigned)((C + 127) / 128), (unsigned)T), 128, 0, st>>>(r_dev, ldr, L, C, integral_dev);
+  radix_pick_kernel<<<(unsigned)T, 128, 0, st>>>(hist2, 4, kRadixBins, 10, state, ks_lo, ks_hi, M, 0, semi_os_dev);
+  integral_pass_kernel<<<dim3((unsigned)((C + 127) / 128), (unsigned)T), 128, 0, st>>>(r_dev, ldr, L, C, state, integral_dev,
+                                                                                      hist3);
+  radix_pick_kernel<<<(unsigned)T, 128, 0, st>>>(hist3, 4, 1024, 0, state, ks_lo, ks_hi, M, 0, semi_os_dev);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
