@@ -70,6 +70,7 @@ struct TaskCtx {
   uint8_t* x_base;       // A operand + this k-block's offset inside an m-tile row
   unsigned int* flags;   // non-zero bit array [m_tile][FW]
   int FW;
+  unsigned long long rowmask[2];   // staging rows that hold a match (bit b = row b), per staging buffer
 };
 
 // Exact canonical-order scores of the window starting at base i of sequence s of the k-block:
@@ -111,9 +112,10 @@ __device__ __forceinline__ void exact_x0(const TaskCtx& c, int s, int i, float& 
 }
 
 // One match of task t: staging buffer, per-position / per-sequence counts, optional match list.
-__device__ __forceinline__ void publish_match(const ScanArgs& a, const TaskCtx& c, int t, float* buf, int b, int s,
+__device__ __forceinline__ void publish_match(const ScanArgs& a, TaskCtx& c, int which, int t, float* buf, int b, int s,
                                               int p, float x0) {
   buf[b * kRowStride + s] = x0;
+  atomicOr(&c.rowmask[which], 1ull << b);
   const int64_t ns = (int64_t)c.kb * 32 + s;
   atomicAdd(&a.count[(int64_t)t * c.L + p], 1);
   atomicAdd(&a.density[(int64_t)t * a.n_pad + ns], 1);
@@ -128,7 +130,7 @@ __device__ __forceinline__ void publish_match(const ScanArgs& a, const TaskCtx& 
 
 // Evaluate up to 32 queued candidates (one per lane) exactly; publish matches.  Returns (warp
 // uniform) bit 0: the unit's task got a match, bit 1: its twin (the '+' task sharing filter 0) got one.
-__device__ __noinline__ unsigned flush_candidates(const ScanArgs& a, const TaskCtx& c, int q_head, int count, int base,
+__device__ __noinline__ unsigned flush_candidates(const ScanArgs& a, TaskCtx& c, int q_head, int count, int base,
                                                   int lane) {
   __syncwarp();
   bool hit = false, hit2 = false;
@@ -140,11 +142,11 @@ __device__ __noinline__ unsigned flush_candidates(const ScanArgs& a, const TaskC
     exact_x0(c, s, p - c.padl, x_first, x_task);
     if (x_task > 0.0f) {
       hit = true;
-      publish_match(a, c, c.t, c.s_buf, b, s, p, x_task);
+      publish_match(a, c, 0, c.t, c.s_buf, b, s, p, x_task);
     }
     if (c.t2 >= 0 && x_first > 0.0f) {
       hit2 = true;
-      publish_match(a, c, c.t2, c.s_buf2, b, s, p, x_first);
+      publish_match(a, c, 1, c.t2, c.s_buf2, b, s, p, x_first);
     }
   }
   return (__any_sync(0xffffffffu, hit) ? 1u : 0u) | (__any_sync(0xffffffffu, hit2) ? 2u : 0u);
@@ -152,8 +154,8 @@ __device__ __noinline__ unsigned flush_candidates(const ScanArgs& a, const TaskC
 
 // Phase B of one 32-position chunk that holds (or borders) matches: blur, row sums, fp16 split, tiled
 // store of the non-zero 16-byte pieces; lane = (kc, rsub).  Chunks without any match store nothing.
-__device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, int t, const float* s_buf, int base,
-                                         int lane) {
+__device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, int t, const float* s_buf,
+                                         unsigned long long rowmask, int base, int lane) {
   const unsigned full = 0xffffffffu;
   const int kc = lane & 3, rsub = lane >> 2;
   const int mg = c.mg, L = c.L;
@@ -161,8 +163,10 @@ __device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, in
   const float kf = (float)k;
   const int64_t tile_stride = c.tile_stride;
   uint8_t* const x_base = c.x_base;
+  const unsigned long long wmask = (1ull << (8 + 2 * mg)) - 1ull;   // staging rows feeding eight output rows
 #pragma unroll 1
   for (int it = 0; it < 4; ++it) {
+    if (((rowmask >> (8 * it)) & wmask) == 0ull) continue;          // no match in this row group's blur window
     const int rl = rsub + 8 * it;
     const int p = base + rl;
     const bool valid = p >= 0 && p < L;
@@ -396,6 +400,7 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
     w.s_lut = s_lut;
     w.g_sym = a.sym_T + (int64_t)kb * 32;
     w.s_buf = s_buf; w.s_buf2 = s_buf2; w.s_queue = s_queue;
+    w.rowmask[0] = 0ull; w.rowmask[1] = 0ull;
     w.n_pad = a.n_pad;
     w.t = t; w.t2 = t2; w.kb = kb; w.m = m; w.padl = padl; w.mg = mg; w.L = L;
     w.dual = a.nfilt[t] == 2;
@@ -408,7 +413,7 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
     *s_ctx = w;
   }
   __syncwarp();
-  const TaskCtx& c = *s_ctx;
+  TaskCtx& c = *s_ctx;
 
   const uint32_t* my = a.sym_T + (int64_t)kb * 32 + lane;   // this lane's sequence: word w at my[w * n_pad]
   const int64_t wstride = a.n_pad;
@@ -449,9 +454,6 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
   int q_head = 0, q_tail = 0;            // warp-uniform ring indices
   unsigned dcar = 0u, dbody = 0u;        // staging rows [0, 2 mg) / [2 mg, nbuf) may hold non-zero x0 (bit 1: twin)
 
-  // Chunk origin: the first chunk starts e positions before the sequence so that it holds a multiple of
-  // eight windows (32 + mg - padl - e); every later chunk holds 32, so steps never straddle a refill.
-  const int e = (((mg - padl) % kGroup) + kGroup) % kGroup;
   for (int base = 0; base < L; base += 32) {
     int b_start = 0;
     if (base != 0) {
@@ -464,7 +466,9 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
           for (int b = 0; b < 2 * mg; ++b) buf[b * kRowStride + lane] = buf[(32 + b) * kRowStride + lane];
           for (int b = 2 * mg; b < nbuf; ++b) buf[b * kRowStride + lane] = 0.0f;
           dcar |= bit; dbody &= ~bit;
+          if (lane == 0) c.rowmask[bit >> 1] >>= 32;
         } else if (dcar & bit) {
+          if (lane == 0) c.rowmask[bit >> 1] = 0ull;
           for (int b = 0; b < 2 * mg; ++b) buf[b * kRowStride + lane] = 0.0f;
           dcar &= ~bit;
         }
@@ -540,8 +544,8 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
     __syncwarp();
     // ---- phase B: blur + split + store, only for chunks that hold or border a match ----
     const unsigned nzb = dcar | dbody;
-    if (nzb & 1u) store_chunk(a, c, t, s_buf, base, lane);
-    if (nzb & 2u) store_chunk(a, c, t2, s_buf2, base, lane);
+    if (nzb & 1u) store_chunk(a, c, t, s_buf, c.rowmask[0], base, lane);
+    if (nzb & 2u) store_chunk(a, c, t2, s_buf2, c.rowmask[1], base, lane);
     __syncwarp();
   }
 }
