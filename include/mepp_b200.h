@@ -149,7 +149,9 @@ int mepp_x_planes_reset(void* x_planes_dev, const void* hits_dev, int64_t hits_c
  * Cost is proportional to the number of non-zeros of X (4 KB of L2 traffic each at P = 1000); the
  * tensor-core GEMM below costs the same whatever X holds.  Nothing is written if the entry list
  * overflowed (*entry_count_dev > entry_cap): the caller then takes the tiled path.
- * work_dev: mepp_profile_sparse_work_bytes(m_rows, entry_cap) bytes; row_nnz_dev is consumed. */
+ * work_dev: mepp_profile_sparse_work_bytes(m_rows, entry_cap) bytes, beginning with int32 offsets[m_rows + 2]
+ * (CSR row offsets; offsets[m_rows] = number of non-zeros, offsets[m_rows + 1] = 1 if the list overflowed);
+ * row_nnz_dev is consumed. */
 int64_t mepp_y_rows_ld(int C);
 int mepp_build_y_rows(const float* yhat_dev, const int32_t* perm_dev, int64_t N, int P, float* y_rows_dev,
                       void* stream);

@@ -249,7 +249,7 @@ __device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, in
         }
       }
     }
-    if (nz) {
+    if (nz && a.x_planes) {
       uint32_t h[4], l[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {

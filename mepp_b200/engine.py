@@ -462,6 +462,7 @@ class Engine:
                                                     _ptr(self._yrows()), _ptr(rowstats), _ptr(self._colconst()), _ptr(r),
                                                     self.ldS, m_rows, C_, _ptr(work), st), "profile_sparse")
             self.launches += 3
+            nnz_d = work[m_rows * 4:m_rows * 4 + 4].view(torch.int32)     # offsets[m_rows] = non-zeros of X
             ev = self._mark(ev, 'gemm')
         elif self.fuse_correlation:
             _lib.check(_lib.lib.mepp_profile_corr_gemm(_ptr(x_planes), _ptr(self.y_planes), _ptr(rowstats),
@@ -521,6 +522,7 @@ class Engine:
         dev['hit_count'] = hit_count
         if path == 'sparse':
             dev['entry_count'] = entry_count
+            dev['nnz'] = nnz_d
         if return_r:
             dev['r'] = r.view(T, L, self.ldS)[:, :, :C_].contiguous()
         host = {}
@@ -570,7 +572,7 @@ class Engine:
             for f in [_copy_pool(self.copy_threads).submit(job, bounds[i], bounds[i + 1]) for i in range(n_chunks)]:
                 f.result()
         out = dict(T=T)
-        out['entries'] = int(h['entry_count'][::16].sum()) if 'entry_count' in h else 0
+        out['entries'] = int(h['nnz'][0]) if 'nnz' in h else 0
         nh = int(h['hit_count'][0])
         out['hit_count'] = np.array([nh], dtype=np.int64)
         if pend['return_hits']:
