@@ -329,7 +329,7 @@ def main():
         stats_bytes = 4.0 * n_local * L * (3.0 * C_ + 2.0 * P)
         a = stats_bytes / per("perm_stats") / 1e9
         kernels["perm_stats"] = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"],
-                                     ms_per_step=1e3 * per("perm_stats"), launches_per_step=9 * groups,
+                                     ms_per_step=1e3 * per("perm_stats"), launches_per_step=10 * groups,
                                      limit="per-row tail selection in registers, pooled histogram search, 3-digit radix select: ALU / shared-memory atomics")
     for k in ("correlation", "finalize"):
         if stage_ms.get(k):

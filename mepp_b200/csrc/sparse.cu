@@ -23,26 +23,46 @@ constexpr int kScanThreads = 1024;
 __global__ void __launch_bounds__(kScanThreads) csr_offsets_kernel(const int32_t* __restrict__ row_nnz, int64_t m_rows,
                                                                    const unsigned long long* __restrict__ entry_count,
                                                                    int64_t sub_cap, int32_t* __restrict__ offsets) {
-  __shared__ int32_t part[kScanThreads];
-  const int tid = threadIdx.x;
-  if (tid == 0) offsets[m_rows + 1] = 0;
+  __shared__ int32_t s_warp[32];
+  __shared__ int32_t s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { offsets[m_rows + 1] = 0; s_base = 0; }
   __syncthreads();
   if (tid < MEPP_ENTRY_LISTS && (int64_t)entry_count[tid * 16] > sub_cap) offsets[m_rows + 1] = 1;
-  const int64_t per = (m_rows + kScanThreads - 1) / kScanThreads;
-  const int64_t lo = tid * per, hi = lo + per < m_rows ? lo + per : m_rows;
-  int32_t s = 0;
-  for (int64_t i = lo; i < hi; ++i) s += row_nnz[i];
-  part[tid] = s;
-  __syncthreads();
-  for (int o = 1; o < kScanThreads; o <<= 1) {       // Hillis-Steele inclusive scan of the partial sums
-    const int32_t v = tid >= o ? part[tid - o] : 0;
+  // tiles of 4096 rows: four consecutive rows per thread (coalesced), scan inside the thread, the warp, the block
+  for (int64_t tile = 0; tile < m_rows; tile += 4 * kScanThreads) {
+    const int64_t i0 = tile + 4 * tid;
+    int32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = i0 + k < m_rows ? row_nnz[i0 + k] : 0;
+    const int32_t mine = v[0] + v[1] + v[2] + v[3];
+    int32_t inc = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    part[tid] += v;
+    if (warp == 0) {
+      int32_t w = s_warp[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t u = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += u;
+      }
+      s_warp[lane] = w;                               // inclusive scan of the warp totals
+    }
+    __syncthreads();
+    int32_t run = s_base + (warp ? s_warp[warp - 1] : 0) + inc - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < m_rows) offsets[i0 + k] = run;
+      run += v[k];
+    }
+    __syncthreads();
+    if (tid == kScanThreads - 1) s_base = run;
     __syncthreads();
   }
-  int32_t run = part[tid] - s;
-  for (int64_t i = lo; i < hi; ++i) { offsets[i] = run; run += row_nnz[i]; }
-  if (tid == kScanThreads - 1) offsets[m_rows] = part[tid];
+  if (tid == 0) offsets[m_rows] = s_base;
 }
 
 // csr[offsets[row] + k] = (seq, x) for the k-th record of the row that arrives (cursor = row_nnz counted down)

@@ -526,9 +526,10 @@ __global__ void semi_count_kernel(const float* __restrict__ r, int64_t ldr, int 
 
 // integral[t][c] = trapezoid over positions of |r[:, c]| (np.trapz, dx = 1); the same pass histograms the third
 // (last, 10-bit) digit of the pooled radix select.  grid = (column blocks, T), one thread per column.
+constexpr int kIntChunks = 4;   // row chunks of the integral pass (partial sums, added in order afterwards)
 __global__ void __launch_bounds__(128) integral_pass_kernel(const float* __restrict__ r, int64_t ldr, int L, int C,
                                                             const RadixState* __restrict__ state,
-                                                            double* __restrict__ integral, uint32_t* __restrict__ hist3) {
+                                                            double* __restrict__ partial, uint32_t* __restrict__ hist3) {
   __shared__ uint32_t s_h3[4][1024];
   const int t = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -547,37 +548,58 @@ __global__ void __launch_bounds__(128) integral_pass_kernel(const float* __restr
       if (top == p2) atomicAdd(&s_h3[2][d], 1u);
       if (top == p3) atomicAdd(&s_h3[3][d], 1u);
     };
+    // rows [la, lb) of this chunk: their radix digits, and the trapezoids between rows la-1 .. lb-1
+    const int per = (L + kIntChunks - 1) / kIntChunks;
+    const int la = blockIdx.z * per, lb = min(L, la + per);
     double acc = 0.0;
-    const float v0 = rr[0];
-    if (perm) digit(v0);
-    float prev = fabsf(v0);
-    int l = 1;
-    for (; l + 8 <= L; l += 8) {                          // eight loads in flight, summed in position order
-      float v[8];
+    if (la < lb) {
+      int l = la;
+      float prev;
+      if (la == 0) {
+        const float v0 = rr[0];
+        if (perm) digit(v0);
+        prev = fabsf(v0);
+        l = 1;
+      } else {
+        prev = fabsf(rr[(int64_t)(la - 1) * ldr]);
+      }
+      for (; l + 8 <= lb; l += 8) {                        // eight loads in flight, summed in position order
+        float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = rr[(int64_t)(l + j) * ldr];
+        for (int j = 0; j < 8; ++j) v[j] = rr[(int64_t)(l + j) * ldr];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (perm) digit(v[j]);
-        const float cur = fabsf(v[j]);
+        for (int j = 0; j < 8; ++j) {
+          if (perm) digit(v[j]);
+          const float cur = fabsf(v[j]);
+          acc += 0.5 * ((double)prev + (double)cur);
+          prev = cur;
+        }
+      }
+      for (; l < lb; ++l) {
+        const float v = rr[(int64_t)l * ldr];
+        if (perm) digit(v);
+        const float cur = fabsf(v);
         acc += 0.5 * ((double)prev + (double)cur);
         prev = cur;
       }
     }
-    for (; l < L; ++l) {
-      const float v = rr[(int64_t)l * ldr];
-      if (perm) digit(v);
-      const float cur = fabsf(v);
-      acc += 0.5 * ((double)prev + (double)cur);
-      prev = cur;
-    }
-    integral[(int64_t)t * C + c] = acc;
+    partial[((int64_t)t * kIntChunks + blockIdx.z) * C + c] = acc;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 4 * 1024; i += blockDim.x) {
     const uint32_t v = (&s_h3[0][0])[i];
     if (v) atomicAdd(&hist3[(int64_t)t * 4 * kRadixBins + (i >> 10) * kRadixBins + (i & 1023)], v);
   }
+}
+
+// integral[t][c] = the row-chunk partial sums of integral_pass_kernel added in chunk order
+__global__ void integral_sum_kernel(const double* __restrict__ partial, int C, double* __restrict__ integral) {
+  const int t = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double acc = 0.0;
+  for (int k = 0; k < kIntChunks; ++k) acc += partial[((int64_t)t * kIntChunks + k) * C + c];
+  integral[(int64_t)t * C + c] = acc;
 }
 
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -640,14 +662,14 @@ int mepp_col_constants_dev(const double* col_syz_dev, const double* ysum_dev, co
 static int64_t up256(int64_t v) { return (v + 255) / 256 * 256; }
 
 int64_t mepp_perm_stats_work_bytes(int T, int L, int C) {
-  (void)C;
   const int64_t ts = up256((int64_t)T * L * 4);                     // sorted |r0| thresholds
   const int64_t hist = up256((int64_t)T * (L + 1) * 8);             // pooled histogram against the thresholds
   const int64_t h1 = up256((int64_t)T * mepp::kRadixBins * 4);      // radix select: first digit
   const int64_t h23 = up256((int64_t)T * 4 * mepp::kRadixBins * 4); // second / third digit, four targets
   const int64_t state = up256((int64_t)T * sizeof(mepp::RadixState));
   const int64_t tab = up256((int64_t)T * (mepp::kNarrowBins + 2) * 2) + up256((int64_t)T * 8);   // narrowing table + parameters
-  return ts + hist + h1 + 2 * h23 + state + tab;
+  const int64_t part = up256((int64_t)T * mepp::kIntChunks * C * 8);   // row-chunk partial sums of the integrals
+  return ts + hist + h1 + 2 * h23 + state + tab + part;
 }
 
 int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C, int k_lo, int k_hi, int64_t ks_lo, int64_t ks_hi,
@@ -679,6 +701,7 @@ int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C, int k_
   const int64_t state_b = up256((int64_t)T * sizeof(RadixState)), tab_b = up256((int64_t)T * (kNarrowBins + 2) * 2);
   uint16_t* tab = reinterpret_cast<uint16_t*>(w + ts_b + hist_b + h1_b + 2 * h23_b + state_b);
   uint32_t* thr_par = reinterpret_cast<uint32_t*>(w + ts_b + hist_b + h1_b + 2 * h23_b + state_b + tab_b);
+  double* partial = reinterpret_cast<double*>(w + ts_b + hist_b + h1_b + 2 * h23_b + state_b + tab_b + up256((int64_t)T * 8));
   MEPP_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)(hist_b + h1_b + 2 * h23_b), st));
 
   // rows per CTA: enough CTAs to fill the machine, few enough that the per-task histogram flushes stay cheap
@@ -714,8 +737,9 @@ int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C, int k_
                                                                                   tab, thr_par, state, hist, hist2);
   semi_count_kernel<<<(unsigned)T, 256, 0, st>>>(r_dev, ldr, L, C, ts_sorted, hist, semi_cnt_dev);
   radix_pick_kernel<<<(unsigned)T, 128, 0, st>>>(hist2, 4, kRadixBins, 10, state, ks_lo, ks_hi, M, 0, semi_os_dev);
-  integral_pass_kernel<<<dim3((unsigned)((C + 127) / 128), (unsigned)T), 128, 0, st>>>(r_dev, ldr, L, C, state, integral_dev,
-                                                                                      hist3);
+  integral_pass_kernel<<<dim3((unsigned)((C + 127) / 128), (unsigned)T, kIntChunks), 128, 0, st>>>(r_dev, ldr, L, C, state,
+                                                                                                  partial, hist3);
+  integral_sum_kernel<<<dim3((unsigned)((C + 127) / 128), (unsigned)T), 128, 0, st>>>(partial, C, integral_dev);
   radix_pick_kernel<<<(unsigned)T, 128, 0, st>>>(hist3, 4, 1024, 0, state, ks_lo, ks_hi, M, 0, semi_os_dev);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
