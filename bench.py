@@ -249,8 +249,8 @@ def main():
 
     # (2) end to end from pinned host buffers (clock sampler halted: its NVML polling slows host-side CUDA calls)
     sampler.halt()
-    for _ in range(2):                                     # untimed: the first steps after the sampler stops are erratic
-        e2e_step()
+    for _ in range(max(args.warmup, 3)):                   # untimed warm-up of the end-to-end path (the first steps after
+        e2e_step()                                         # the switch from the device-resident loop are erratic)
     sync_all()
     import gc
     gc.collect()

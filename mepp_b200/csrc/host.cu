@@ -129,6 +129,16 @@ int mepp_log_odds(const double* pwm, int m, const double* bg, double ps, double*
   return 0;
 }
 
+// dst[r] += b * src[r]: the inner loop of the threshold DP (a few 1e6 updates per motif).  Compiled for AVX2 as
+// well and dispatched at load time; every lane does the same multiply and add, so the results do not depend on
+// the vector width.
+#if defined(__GNUC__) && defined(__x86_64__) && !defined(__CUDA_ARCH__)
+__attribute__((target_clones("avx2", "default")))
+#endif
+static void dp_axpy(double* __restrict__ dst, const double* __restrict__ src, double b, long n) {
+  for (long r = 0; r < n; ++r) dst[r] += b * src[r];
+}
+
 // MOODS.tools.threshold_from_p: distribution of the integer-rounded score under
 // bg by dynamic programming, then the smallest grid score whose upper tail <= p.
 int mepp_threshold_from_p(const double* W, int m, const double* bg, double p,
@@ -160,9 +170,7 @@ int mepp_threshold_from_p(const double* W, int m, const double* bg, double p,
     for (int j = 0; j < 4; ++j) {
       long s = mat[j * m + i] - minV;
       double b = bg[j];
-      const double* __restrict__ src = t0.data();
-      double* __restrict__ dst = t1.data() + s;
-      for (long r = 0; r <= hi; ++r) dst[r] += b * src[r];
+      dp_axpy(t1.data() + s, t0.data(), b, hi + 1);
       new_hi = std::max(new_hi, hi + s);
     }
     std::fill(t0.begin(), t0.begin() + hi + 1, 0.0);
