@@ -72,6 +72,24 @@ int mepp_motif_table(const double* pwm, int m, int orientation_char,
 int mepp_motif_table_with_threshold(const double* pwm, int m, int orientation_char, double pseudocount,
                                     const double* bg_in, int use_flags, double thr, float* lut, float* bias,
                                     int* n_filters, uint32_t* qtab, uint32_t* qthr);
+/* Thresholds on the device (the host DP above is the longest host-side piece of an end-to-end step).
+ * mepp_prepare_tables (host, no DP): for T tasks given as zero-padded (4, 32) matrices pwms[T][4][32] with lengths
+ * mlen[T] and orientations ochar[T] ('+', '-', anything else = both strands): lut float [T][32][4][2], nfilt [T],
+ * qtab uint32 [T][1024], qpar double [T][4] (what the pass bounds need besides the threshold), and for the
+ * threshold DP of filter 0: smat int32 [T][32][4] (integer scores shifted to >= 0), dp_par double [T][8] =
+ * {bg[4], p, precision, m * min score, score range R}.
+ * mepp_thresholds_dp (device): threshold_from_p for U units (any subset of the tasks: upload their smat / mlen /
+ * dp_par rows); scratch_dev holds two arrays of R_u + 1 doubles per unit at element offset scratch_off_dev[u].
+ * mepp_task_thresholds (device): bias = float(-thr), qthr pass bounds and the threshold of every task from the
+ * thresholds of the units (unit_of_task: the '+' and '+/-' orientations of a motif share one). */
+int mepp_prepare_tables(const double* pwms, const int32_t* mlen, const int32_t* ochar, int T, double pseudocount,
+                        double pvalue, const double* bg_in, int use_flags, double dp_precision, float* lut,
+                        int32_t* nfilt, uint32_t* qtab, double* qpar, int32_t* smat, double* dp_par);
+int mepp_thresholds_dp(const int32_t* smat_dev, const int32_t* mlen_dev, const double* par_dev,
+                       const long long* scratch_off_dev, double* scratch_dev, double* thr_dev, int U, void* stream);
+int mepp_task_thresholds(const double* thr_unit_dev, const int32_t* unit_of_task_dev, const double* qpar_dev,
+                         const int32_t* mlen_dev, const int32_t* nfilt_dev, int T, float* bias_dev, uint32_t* qthr_dev,
+                         double* thr_task_dev, void* stream);
 
 /* ------------------------------------------------------------------ layout sizes */
 int64_t mepp_sym_words(int L);              /* W3 */

@@ -35,6 +35,9 @@ SIGNATURES = {
     "mepp_threshold_from_p": (_i32, [_pd, _i32, _pd, _f64, _f64, _pd]),
     "mepp_motif_table": (_i32, [_pd, _i32, _i32, _f64, _f64, _pd, _i32, _f64, _pf, _pf, _pi, _pd, _vp, _vp]),
     "mepp_motif_table_with_threshold": (_i32, [_pd, _i32, _i32, _f64, _pd, _i32, _f64, _pf, _pf, _pi, _vp, _vp]),
+    "mepp_prepare_tables": (_i32, [_vp, _vp, _vp, _i32, _f64, _f64, _pd, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mepp_thresholds_dp": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "mepp_task_thresholds": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "mepp_sym_words": (_i64, [_i32]),
     "mepp_pad32": (_i64, [_i64]),
     "mepp_x_planes_bytes": (_i64, [_i64, _i64]),

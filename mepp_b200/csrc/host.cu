@@ -22,7 +22,9 @@ namespace mepp {
 // and the float32 sequentially rounded score differs from S by less than delta, so a window can only
 // pass the threshold if sum_q >= qthr.  Both filters are packed into one 32-bit entry (low / high half),
 // and two adjacent taps share one 64-entry table indexed by the 6-bit pair of 3-bit symbols (A,C,G,T,N).
-static void build_filter_table(const float* lut, int m, int n_filters, float bias, uint32_t* qtab, uint32_t* qthr) {
+// qpar (optional, 4 doubles): {scale, delta, lo[0], lo[1]}, what the pass bounds need besides the threshold.
+static void build_filter_table(const float* lut, int m, int n_filters, float bias, uint32_t* qtab, uint32_t* qthr,
+                               double* qpar = nullptr) {
   double rsum[2] = {0.0, 0.0}, lo[2] = {0.0, 0.0}, absmax = 0.0;
   double mn[2][MEPP_MAX_MOTIF_LEN];
   for (int f = 0; f < n_filters; ++f)
@@ -39,6 +41,7 @@ static void build_filter_table(const float* lut, int m, int n_filters, float bia
   // |float32 sequential sum - real sum| <= m roundings of at most ulp(absmax)/2 each; doubled for safety
   const double delta = 2.0 * (4.0 * m) * absmax * 5.97e-8 + 1e-6;   // up to 4 adds per tap (N bases)
   const double thr32 = -(double)bias;
+  if (qpar) { qpar[0] = scale; qpar[1] = delta; qpar[2] = lo[0]; qpar[3] = lo[1]; }
   // symbol 4 = N: the four quarter-weight adds sum (in real arithmetic) to the column mean
   double qn[2][MEPP_MAX_MOTIF_LEN];
   for (int f = 0; f < n_filters; ++f)
@@ -223,6 +226,67 @@ static int motif_table_impl(const double* pwm, int m, int orientation_char,
   *n_filters = f1 ? 2 : 1;
   if (thr_out) *thr_out = thr;
   if (qtab && qthr) mepp::build_filter_table(lut, m, *n_filters, *bias, qtab, qthr);
+  return 0;
+}
+
+int mepp_prepare_tables(const double* pwms, const int32_t* mlen, const int32_t* ochar, int T, double pseudocount,
+                        double pvalue, const double* bg_in, int use_flags, double dp_precision, float* lut,
+                        int32_t* nfilt, uint32_t* qtab, double* qpar, int32_t* smat, double* dp_par) {
+  MEPP_REQUIRE(pwms && mlen && ochar && lut && nfilt && qtab && qpar && smat && dp_par && T > 0,
+               "prepare_tables: bad arguments");
+  double bg[4] = {0.25, 0.25, 0.25, 0.25};
+  double ps = 1e-4, pv = 1e-4;  // core.py:513-534 never forwards the user's values
+  if (use_flags) {
+    ps = pseudocount; pv = pvalue;
+    if (bg_in) for (int j = 0; j < 4; ++j) bg[j] = bg_in[j];
+  }
+  for (int t = 0; t < T; ++t) {
+    const int m = mlen[t];
+    MEPP_REQUIRE(m >= 1 && m <= MEPP_MAX_MOTIF_LEN, "prepare_tables: motif length must be in [1, 32]");
+    // the padded (4, 32) matrix of task t -> contiguous (4, m)
+    double pwm[4 * MEPP_MAX_MOTIF_LEN], W[4 * MEPP_MAX_MOTIF_LEN], Wr[4 * MEPP_MAX_MOTIF_LEN];
+    for (int c = 0; c < 4; ++c)
+      for (int j = 0; j < m; ++j) pwm[c * m + j] = pwms[((size_t)t * 4 + c) * MEPP_MAX_MOTIF_LEN + j];
+    if (mepp_log_odds(pwm, m, bg, ps, W)) return 1;
+    for (int c = 0; c < 4; ++c)
+      for (int j = 0; j < m; ++j) Wr[c * m + j] = W[(3 - c) * m + (m - 1 - j)];
+    const double* f0 = W;
+    const double* f1 = nullptr;
+    if (ochar[t] == '-') f0 = Wr;
+    else if (ochar[t] != '+') f1 = Wr;
+    float* l = lut + (size_t)t * MEPP_MAX_MOTIF_LEN * 8;
+    for (int k = 0; k < MEPP_MAX_MOTIF_LEN * 8; ++k) l[k] = 0.0f;
+    for (int j = 0; j < m; ++j)
+      for (int c = 0; c < 4; ++c) {
+        l[(j * 4 + c) * 2 + 0] = (float)f0[c * m + j];
+        l[(j * 4 + c) * 2 + 1] = f1 ? (float)f1[c * m + j] : 0.0f;
+      }
+    nfilt[t] = f1 ? 2 : 1;
+    uint32_t qthr_unused[2];
+    mepp::build_filter_table(l, m, nfilt[t], 0.0f, qtab + (size_t)t * 1024, qthr_unused, qpar + (size_t)t * 4);
+    // integer matrix of filter 0 for the threshold DP, shifted to >= 0 (mepp_threshold_from_p)
+    long mat[4 * MEPP_MAX_MOTIF_LEN];
+    for (int k = 0; k < 4 * m; ++k) {
+      const double v = f0[k];
+      mat[k] = v > 0.0 ? (long)(dp_precision * v + 0.5) : (long)(dp_precision * v - 0.5);
+    }
+    long maxT = 0, minV = std::numeric_limits<long>::max();
+    for (int i = 0; i < m; ++i) {
+      long mx = mat[i], mn = mat[i];
+      for (int j = 1; j < 4; ++j) { mx = std::max(mx, mat[j * m + i]); mn = std::min(mn, mat[j * m + i]); }
+      maxT += mx;
+      minV = std::min(minV, mn);
+    }
+    const long R = maxT - (long)m * minV;
+    MEPP_REQUIRE(R >= 0 && R < (1L << 28), "prepare_tables: score range too large");
+    int32_t* sm = smat + (size_t)t * MEPP_MAX_MOTIF_LEN * 4;
+    for (int k = 0; k < MEPP_MAX_MOTIF_LEN * 4; ++k) sm[k] = 0;
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < 4; ++j) sm[i * 4 + j] = (int32_t)(mat[j * m + i] - minV);
+    double* dp = dp_par + (size_t)t * 8;
+    dp[0] = bg[0]; dp[1] = bg[1]; dp[2] = bg[2]; dp[3] = bg[3];
+    dp[4] = pv; dp[5] = dp_precision; dp[6] = (double)((long)m * minV); dp[7] = (double)R;
+  }
   return 0;
 }
 

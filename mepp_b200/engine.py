@@ -121,6 +121,42 @@ def scan_units(tables):
     return np.array(units, dtype=np.int32)
 
 
+class DeviceTables:
+    """Scan tables of a task range [g0, g1) of a call whose thresholds were computed on the device."""
+
+    def __init__(self, dev, host, g0, g1):
+        self.dev, self.host, self.g0, self.g1 = dev, host, g0, g1
+        self.mlen = host['mlen'][g0:g1]
+        self.nfilt = host['nfilt'][g0:g1]
+        self.pvalue = host['pvalue']
+
+    def __len__(self):
+        return self.g1 - self.g0
+
+    def slice(self, g0, g1):
+        return DeviceTables(self.dev, self.host, self.g0 + g0, self.g0 + g1)
+
+    def device_slices(self):
+        d, a, b = self.dev, self.g0, self.g1
+        return d['lut'][a:b], d['bias'][a:b], d['mlen'][a:b], d['nfilt'][a:b], d['qtab'][a:b], d['qthr'][a:b]
+
+    def units(self):
+        """(task scanned, twin or -1) rows like scan_units, from the pairing made when the tables were prepared."""
+        a, b = self.g0, self.g1
+        twin = self.host['twin_of'][a:b]
+        rows, twinned = [], set()
+        for t in range(b - a):
+            if self.nfilt[t] == 2:
+                u = int(twin[t]) - a if a <= twin[t] < b else -1
+                rows.append((t, u))
+                if u >= 0:
+                    twinned.add(u)
+        if not twinned:
+            return None
+        rows.extend((t, -1) for t in range(b - a) if self.nfilt[t] == 1 and t not in twinned)
+        return np.array(rows, dtype=np.int32)
+
+
 class Engine:
     def __init__(self, device=None, mem_budget_bytes=32 << 30, max_group=512):
         torch = _torch()
@@ -144,6 +180,7 @@ class Engine:
         self.profile_path = os.environ.get("MEPP_PROFILE_PATH", "auto")     # 'auto' | 'sparse' | 'tensor'
         self.last_paths = []
         self.copy_threads = int(os.environ.get("MEPP_COPY_THREADS", "4"))
+        self.device_tables = os.environ.get("MEPP_DEVICE_TABLES", "1") != "0"   # threshold DP on the GPU
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -239,6 +276,40 @@ class Engine:
             self.launches += 1
         return self._y_rows
 
+    def device_tables_for(self, tasks, **table_kw):
+        """Scan tables of a whole task list with the thresholds computed on the device: one host call for
+        everything that does not need the threshold, one launch of the threshold DP over the distinct
+        (motif, filter-0 orientation) units, one for the threshold-dependent table entries."""
+        torch = self.torch
+        host = motif_layers.prepare_tables(tasks, **table_kw)
+        T = len(tasks)
+        rows = host['unit_rows']
+        U = len(rows)
+        R = host['dp_par'][rows, 7].astype(np.int64)
+        off = np.zeros(U, dtype=np.int64)
+        off[1:] = np.cumsum(2 * (R[:-1] + 1))
+        n_scratch = int(off[-1] + 2 * (R[-1] + 1))
+        dev = dict(lut=self._to_dev(host['lut']), mlen=self._to_dev(host['mlen']), nfilt=self._to_dev(host['nfilt']),
+                   qtab=self._to_dev(host['qtab'].view(np.int32)),
+                   bias=torch.empty(T, dtype=torch.float32, device=self.device),
+                   qthr=torch.empty((T, 2), dtype=torch.int32, device=self.device),
+                   thr=torch.empty(T, dtype=torch.float64, device=self.device))
+        scratch = self._buf('dp_scratch', (n_scratch,), torch.float64)
+        thr_unit = torch.empty(U, dtype=torch.float64, device=self.device)
+        st = self._stream()
+        # (locals keep the uploaded inputs alive until both kernels are enqueued)
+        smat_d, umlen_d = self._to_dev(host['smat'][rows]), self._to_dev(host['mlen'][rows])
+        par_d, off_d = self._to_dev(host['dp_par'][rows]), self._to_dev(off)
+        uot_d, qpar_d = self._to_dev(host['unit_of_task']), self._to_dev(host['qpar'])
+        _lib.check(_lib.lib.mepp_thresholds_dp(_ptr(smat_d), _ptr(umlen_d), _ptr(par_d), _ptr(off_d), _ptr(scratch),
+                                               _ptr(thr_unit), U, st), "thresholds_dp")
+        _lib.check(_lib.lib.mepp_task_thresholds(_ptr(thr_unit), _ptr(uot_d), _ptr(qpar_d), _ptr(dev['mlen']),
+                                                 _ptr(dev['nfilt']), T, _ptr(dev['bias']), _ptr(dev['qthr']),
+                                                 _ptr(dev['thr']), st), "task_thresholds")
+        dev['_keep'] = (smat_d, umlen_d, par_d, off_d, uot_d, qpar_d, thr_unit)
+        self.launches += 2
+        return DeviceTables(dev, host, 0, T)
+
     def choose_path(self, tables, margin):
         """'sparse' (gather of Y rows per non-zero of X) or 'tensor' (tcgen05 GEMM over the tiled operand).
         The sparse path costs ~4 (1 + P) bytes of L2 traffic per non-zero, the GEMM the same whatever X holds:
@@ -249,7 +320,10 @@ class Engine:
         y_rows_bytes = 4 * self.n_pad * int(_lib.lib.mepp_y_rows_ld(self.C))
         if not self.fuse_correlation or y_rows_bytes > self.mem_budget // 2:
             return 'tensor'
-        pv = max((tb.get('pvalue', 1e-4) * tb['n_filters'] for tb in tables), default=1e-4)
+        if isinstance(tables, DeviceTables):
+            pv = tables.pvalue * int(tables.nfilt.max())
+        else:
+            pv = max((tb.get('pvalue', 1e-4) * tb['n_filters'] for tb in tables), default=1e-4)
         return 'sparse' if pv * (2 * int(margin) + 1) <= SPARSE_DENSITY_MAX else 'tensor'
 
     def _colconst(self):
@@ -322,11 +396,15 @@ class Engine:
             all_tables = []
             # host threshold DP: every group's tables are submitted to the host thread pool now and collected when
             # the group is launched, so the DP of the later groups runs while the earlier ones are on the GPU
-            futures = None if tables is not None else [motif_layers.scan_tables_async(tasks[g0:g1], **table_kw)
-                                                       for g0, g1 in groups]
+            dtab = futures = None
+            if tables is None and self.device_tables:
+                dtab = self.device_tables_for(tasks, **table_kw)
+            elif tables is None:
+                futures = [motif_layers.scan_tables_async(tasks[g0:g1], **table_kw) for g0, g1 in groups]
             for gi, (g0, g1) in enumerate(groups):
-                gt = tables[g0:g1] if tables is not None else futures[gi]()
-                all_tables.extend(gt)
+                gt = dtab.slice(g0, g1) if dtab is not None else tables[g0:g1] if tables is not None else futures[gi]()
+                if dtab is None:
+                    all_tables.extend(gt)
                 nxt = self._launch_group(gt, margin, return_hits, return_r, hits_cap,
                                          confidence_interval_pct, gi % 2)
                 nxt['t0'] = g0
@@ -358,7 +436,7 @@ class Engine:
             order = np.lexsort((hits['pos'], hits['seq'], hits['task']))
             hits = hits[order]
         r = np.concatenate([o['r'] for o in outs], axis=0) if return_r else None
-        thr = np.array([tb['thr'] for tb in all_tables])
+        thr = dtab.dev['thr'].cpu().numpy() if dtab is not None else np.array([tb['thr'] for tb in all_tables])
         return ProfileBatch(list(range(T_all)), positions, density_all, self.scores, thr,
                             hit_counts=cat('hit_count'), hits=hits, r=r, n_seq=N)
 
@@ -411,15 +489,21 @@ class Engine:
         st = self._stream()
         self._reset_x_planes()     # before any scratch buffer of the previous group is reused
         m_rows = T * L
-        lut = np.stack([tb['lut'] for tb in tables]).astype(np.float32)
-        bias = np.array([tb['bias'] for tb in tables], dtype=np.float32)
-        mlen = np.array([tb['m'] for tb in tables], dtype=np.int32)
-        nfilt = np.array([tb['n_filters'] for tb in tables], dtype=np.int32)
-        qtab = np.stack([tb['qtab'] for tb in tables]).view(np.int32)
-        qthr = np.stack([tb['qthr'] for tb in tables]).view(np.int32)
-        lut_d, bias_d, mlen_d, nfilt_d, qtab_d, qthr_d = (self._to_dev(lut), self._to_dev(bias), self._to_dev(mlen),
-                                                          self._to_dev(nfilt), self._to_dev(qtab), self._to_dev(qthr))
-        units = scan_units(tables) if self.share_scans else None
+        if isinstance(tables, DeviceTables):
+            # tables prepared for the whole call and thresholded on the device (mepp_thresholds_dp): slices
+            lut_d, bias_d, mlen_d, nfilt_d, qtab_d, qthr_d = tables.device_slices()
+            mlen = tables.mlen
+            units = tables.units() if self.share_scans else None
+        else:
+            lut = np.stack([tb['lut'] for tb in tables]).astype(np.float32)
+            bias = np.array([tb['bias'] for tb in tables], dtype=np.float32)
+            mlen = np.array([tb['m'] for tb in tables], dtype=np.int32)
+            nfilt = np.array([tb['n_filters'] for tb in tables], dtype=np.int32)
+            qtab = np.stack([tb['qtab'] for tb in tables]).view(np.int32)
+            qthr = np.stack([tb['qthr'] for tb in tables]).view(np.int32)
+            lut_d, bias_d, mlen_d, nfilt_d, qtab_d, qthr_d = (self._to_dev(lut), self._to_dev(bias), self._to_dev(mlen),
+                                                              self._to_dev(nfilt), self._to_dev(qtab), self._to_dev(qthr))
+            units = scan_units(tables) if self.share_scans else None
         units_d = self._to_dev(units) if units is not None else None
         n_units = len(units) if units is not None else 0
         self.last_units = n_units if units is not None else T

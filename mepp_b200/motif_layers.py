@@ -141,3 +141,54 @@ def scan_tables_async(tasks, n_threads=None, **kw):
 def scan_tables(tasks, n_threads=None, **kw):
     """Scan tables for a list of (motif_matrix, orientation) (see scan_tables_async)."""
     return scan_tables_async(tasks, n_threads, **kw)()
+
+
+def prepare_tables(tasks, pseudocount=0.0001, pvalue=0.0001, bg=None, honour_flags=False, dp_precision=DP_PRECISION):
+    """Everything of the scan tables that does not need the threshold, for a whole task list in one C call, plus the
+    inputs of the device threshold DP (include/mepp_b200.h: mepp_prepare_tables).  Returns a dict of numpy arrays;
+    `unit_of_task` maps every task to its threshold unit (the '+' and dual orientations of a motif share the
+    threshold of W, motif_layers.py:36-76), `unit_rows` are the task rows that represent the units, `twin_of`
+    pairs a dual task with the '+' task of the same motif (-1: none)."""
+    T = len(tasks)
+    pwms = np.zeros((T, 4, _lib.MAX_MOTIF_LEN), dtype=np.float64)
+    mlen = np.empty(T, dtype=np.int32)
+    ochar = np.empty(T, dtype=np.int32)
+    unit_index, unit_of_task, unit_rows = {}, np.empty(T, dtype=np.int32), []
+    plus_of, duals = {}, []
+    for t, (pwm, orient) in enumerate(tasks):
+        a = np.ascontiguousarray(pwm, dtype=np.float64)
+        if a.ndim != 2 or a.shape[0] != 4:
+            raise ValueError("motif_matrix must have shape (4, m)")
+        m = a.shape[1]
+        if not 1 <= m <= _lib.MAX_MOTIF_LEN:
+            raise ValueError(f"motif length {m} outside [1, {_lib.MAX_MOTIF_LEN}]")
+        pwms[t, :, :m] = a
+        mlen[t] = m
+        o = orient if orient in ('+', '-') else 'd'
+        ochar[t] = ord(o)
+        key = (a.tobytes(), m, '-' if o == '-' else 'f')
+        if key not in unit_index:
+            unit_index[key] = len(unit_rows)
+            unit_rows.append(t)
+        unit_of_task[t] = unit_index[key]
+        if o == '+':
+            plus_of.setdefault(key, []).append(t)
+        elif o == 'd':
+            duals.append((t, key))
+    twin_of = np.full(T, -1, dtype=np.int32)
+    for t, key in duals:
+        cand = plus_of.get(key)
+        if cand:
+            twin_of[t] = cand.pop(0)
+    out = dict(lut=np.empty((T, _lib.MAX_MOTIF_LEN, 4, 2), dtype=np.float32), nfilt=np.empty(T, dtype=np.int32),
+               qtab=np.empty((T, 1024), dtype=np.uint32), qpar=np.empty((T, 4), dtype=np.float64),
+               smat=np.empty((T, _lib.MAX_MOTIF_LEN, 4), dtype=np.int32), dp_par=np.empty((T, 8), dtype=np.float64),
+               mlen=mlen, unit_of_task=unit_of_task, unit_rows=np.array(unit_rows, dtype=np.int64), twin_of=twin_of,
+               pvalue=float(pvalue) if honour_flags else 0.0001)
+    bgp = _pd(np.ascontiguousarray(bg, dtype=np.float64)) if bg is not None else None
+    _lib.check(_lib.lib.mepp_prepare_tables(pwms.ctypes.data, mlen.ctypes.data, ochar.ctypes.data, T, float(pseudocount),
+                                            float(pvalue), bgp, 1 if honour_flags else 0, float(dp_precision),
+                                            out['lut'].ctypes.data, out['nfilt'].ctypes.data, out['qtab'].ctypes.data,
+                                            out['qpar'].ctypes.data, out['smat'].ctypes.data, out['dp_par'].ctypes.data),
+               "prepare_tables")
+    return out

@@ -480,3 +480,24 @@ def test_perm_stats_against_numpy(T, L, P, ties):
         assert np.array_equal(semi_cnt.cpu().numpy(), (ap >= np.abs(r0)[..., None]).sum(-1))
         integ = 0.5 * (np.abs(vals.reshape(T, L, Cc)[:, 1:].astype(np.float64)) + np.abs(vals.reshape(T, L, Cc)[:, :-1].astype(np.float64)))
         assert np.allclose(integral.cpu().numpy(), integ.sum(1), rtol=1e-12)
+
+
+def test_device_thresholds_equal_host_thresholds():
+    """The threshold DP on the device (mepp_thresholds_dp) gives bit-identical thresholds, biases and pass bounds
+    to the host DP (mepp_motif_table = MOODS threshold_from_p) for every motif of the shipped libraries, all
+    three orientations, and for honoured --motifpseudocount / --motifpvalue / background."""
+    from mepp_b200 import synth, motif_layers
+    eng = _engine()
+    tasks = []
+    for lib in ("ohler", "homer"):
+        motifs = synth.load_motif_library(lib)
+        tasks += [(pwm, o) for pwm in list(motifs.values())[:80] for o in ('+', '-', '+/-')]
+    for kw in (dict(), dict(honour_flags=True, pseudocount=0.01, pvalue=1e-3, bg=[0.3, 0.2, 0.2, 0.3])):
+        dt = eng.device_tables_for(tasks, **kw)
+        ref = motif_layers.scan_tables(tasks, **kw)
+        thr = dt.dev['thr'].cpu().numpy()
+        bias = dt.dev['bias'].cpu().numpy()
+        qthr = dt.dev['qthr'].cpu().numpy().view(np.uint32)
+        assert np.array_equal(thr, np.array([tb['thr'] for tb in ref]))
+        assert np.array_equal(bias, np.array([tb['bias'] for tb in ref], dtype=np.float32))
+        assert np.array_equal(qthr, np.stack([tb['qthr'] for tb in ref]))
