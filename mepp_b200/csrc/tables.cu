@@ -36,27 +36,100 @@ __global__ void __launch_bounds__(1024) threshold_dp_kernel(const int32_t* __res
     __syncthreads();
     const int s0 = s_s[0], s1 = s_s[1], s2 = s_s[2], s3 = s_s[3];
     const long long new_hi = hi + max(max(s0, s1), max(s2, s3));
-    for (long long q = threadIdx.x; q <= new_hi; q += blockDim.x) {
-      // dst[q] = sum over letters j (ascending) of bg[j] * src[q - s_j]: the scatter of the host loop, gathered
-      double acc = 0.0;
-      long long r = q - s0; if (r >= 0 && r <= hi) acc = __dadd_rn(acc, __dmul_rn(s_b[0], t0[r]));
-      r = q - s1;           if (r >= 0 && r <= hi) acc = __dadd_rn(acc, __dmul_rn(s_b[1], t0[r]));
-      r = q - s2;           if (r >= 0 && r <= hi) acc = __dadd_rn(acc, __dmul_rn(s_b[2], t0[r]));
-      r = q - s3;           if (r >= 0 && r <= hi) acc = __dadd_rn(acc, __dmul_rn(s_b[3], t0[r]));
-      t1[q] = acc;
+    // dst[q] = sum over letters j (ascending) of bg[j] * src[q - s_j]: the scatter of the host loop, gathered;
+    // four cells per thread and iteration so that sixteen loads are in flight
+    const double b0 = s_b[0], b1 = s_b[1], b2 = s_b[2], b3 = s_b[3];
+    for (long long q0 = threadIdx.x; q0 <= new_hi; q0 += 4 * blockDim.x) {
+      double x[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long q = q0 + (long long)k * blockDim.x;
+        long long r = q - s0; x[k][0] = (r >= 0 && r <= hi) ? t0[r] : -1.0;
+        r = q - s1;           x[k][1] = (r >= 0 && r <= hi) ? t0[r] : -1.0;
+        r = q - s2;           x[k][2] = (r >= 0 && r <= hi) ? t0[r] : -1.0;
+        r = q - s3;           x[k][3] = (r >= 0 && r <= hi) ? t0[r] : -1.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long q = q0 + (long long)k * blockDim.x;
+        if (q <= new_hi) {
+          double acc = 0.0;                            // (-1 marks "no such source cell": probabilities are >= 0)
+          if (x[k][0] >= 0.0) acc = __dadd_rn(acc, __dmul_rn(b0, x[k][0]));
+          if (x[k][1] >= 0.0) acc = __dadd_rn(acc, __dmul_rn(b1, x[k][1]));
+          if (x[k][2] >= 0.0) acc = __dadd_rn(acc, __dmul_rn(b2, x[k][2]));
+          if (x[k][3] >= 0.0) acc = __dadd_rn(acc, __dmul_rn(b3, x[k][3]));
+          t1[q] = acc;
+        }
+      }
     }
     __syncthreads();
     double* tmp = t0; t0 = t1; t1 = tmp;
     hi = new_hi;
   }
-  if (threadIdx.x == 0) {
-    const double p = pr[4], precision = pr[5], base = pr[6];
-    double sum = 0.0, out = base / precision;
-    for (long long r = R; r >= 0; --r) {
-      sum = __dadd_rn(sum, r <= hi ? t0[r] : 0.0);
-      if (sum > p) { out = (double)(r + (long long)base + 1) / precision; break; }
+  // tail: the smallest grid score whose upper tail is <= p, i.e. sum from the top until the sum exceeds p.  The
+  // sum is sequential like the host's (one thread), but the values are staged through shared memory by the whole
+  // block, 2048 at a time, so that the thread adds from shared memory instead of waiting on global loads.
+  __shared__ double s_tail[2048];
+  __shared__ int s_done;
+  __shared__ double s_sum;
+  __shared__ double s_wsum[32];
+  const double p = pr[4], precision = pr[5], base = pr[6];
+  // With a flat background and m <= 26 every probability is a multiple of 4^-m >= 2^-52 and every partial sum is
+  // exact in float64, so the order of the additions cannot matter: the tail is then summed by the whole block.
+  const bool exact = m <= 26 && pr[0] == 0.25 && pr[1] == 0.25 && pr[2] == 0.25 && pr[3] == 0.25;
+  if (threadIdx.x == 0) { s_done = 0; s_sum = 0.0; thr[u] = base / precision; }
+  __syncthreads();
+  for (long long top = R; top >= 0 && !s_done; top -= 2048) {
+    for (int k = threadIdx.x; k < 2048; k += blockDim.x) {
+      const long long r = top - k;
+      s_tail[k] = (r >= 0 && r <= hi) ? t0[r] : 0.0;
     }
-    thr[u] = out;
+    __syncthreads();
+    const int n = (int)min((long long)2048, top + 1);
+    if (exact) {
+      // inclusive scan of the 2048 staged values (two per thread), then the first index whose running sum > p
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const double a0 = s_tail[2 * threadIdx.x], a1 = s_tail[2 * threadIdx.x + 1];
+      double inc = a0 + a1;
+      for (int o = 1; o < 32; o <<= 1) {
+        const double v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      if (lane == 31) s_wsum[warp] = inc;
+      __syncthreads();
+      if (warp == 0) {
+        double w = s_wsum[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+          const double v = __shfl_up_sync(0xffffffffu, w, o);
+          if (lane >= o) w += v;
+        }
+        s_wsum[lane] = w;
+      }
+      __syncthreads();
+      const double before = s_sum + (warp ? s_wsum[warp - 1] : 0.0) + inc - (a0 + a1);   // sum of everything above
+      int first = 1 << 30;
+      if (before + a0 > p) first = 2 * threadIdx.x;
+      else if (before + a0 + a1 > p) first = 2 * threadIdx.x + 1;
+      if (first >= n) first = 1 << 30;
+      for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+      __syncthreads();
+      if (lane == 0) s_tail[warp] = (double)first;     // (s_tail is free again)
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int best = 1 << 30;
+        for (int w = 0; w < 32; ++w) best = min(best, (int)s_tail[w]);
+        if (best < n) { thr[u] = (double)(top - best + (long long)base + 1) / precision; s_done = 1; }
+        s_sum = s_sum + s_wsum[31];
+      }
+    } else if (threadIdx.x == 0) {
+      double sum = s_sum;
+      for (int k = 0; k < n; ++k) {
+        sum = __dadd_rn(sum, s_tail[k]);
+        if (sum > p) { thr[u] = (double)(top - k + (long long)base + 1) / precision; s_done = 1; break; }
+      }
+      s_sum = sum;
+    }
+    __syncthreads();
   }
 }
 

@@ -247,28 +247,68 @@ class Engine:
                 P = int(perm_idx.shape[0])
                 if tuple(perm_idx.shape) != (P, N):
                     raise ValueError("perm_idx must have shape (P, N)")
-                perm_d = self._to_dev(perm_idx, torch.int32).contiguous()
+                # the permutation indices (the bulk of the staged bytes) travel on the side stream: only the Y
+                # operands need them, and those are first used after the first scan of a call is in flight
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=self.device)
+                src = perm_idx if isinstance(perm_idx, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(perm_idx))
+                if src.dtype != torch.int32:
+                    src = src.to(torch.int32)
+                perm_d = self._buf('perm', (P, N), torch.int32)       # persistent: no cross-stream allocation
+                free = torch.cuda.Event()
+                free.record(torch.cuda.current_stream(self.device))   # earlier users of the buffer are done
+                self._copy_stream.wait_event(free)
+                with torch.cuda.stream(self._copy_stream):
+                    perm_d.copy_(src, non_blocking=True)
+                    self._perm_ready = torch.cuda.Event()
+                    self._perm_ready.record(self._copy_stream)
             else:
                 P, perm_d = 0, None
+                self._perm_ready = None
             self.P, self.C = P, 1 + P
             self.BN, self.n_tiles_n = _lib.choose_bn(self.C)
             self.ldS = self.BN * self.n_tiles_n
-            self.y_planes = torch.empty(int(_lib.lib.mepp_y_planes_bytes(self.C, self.n_pad)), dtype=torch.uint8,
-                                        device=self.device)
-            self.col_syz = torch.empty(self.C, dtype=torch.float64, device=self.device)
-            self.ysum = torch.empty(2, dtype=torch.float64, device=self.device)
-            _lib.check(_lib.lib.mepp_build_y(_ptr(yhat_d), _ptr(perm_d), _ptr(self.zhat), N, P, _ptr(self.y_planes),
-                                             _ptr(self.col_syz), _ptr(self.ysum), st), "build_y")
-            self.launches += 3 if self.use_gc else 2
-            # row-major float32 Y for the sparse profile path (built lazily: 4 * n_pad * ldY bytes)
+            # Y operands are built at first use (_ensure_y)
             self._yhat_d, self._perm_d, self._y_rows = yhat_d, perm_d, None
+            self._y_planes = self._col_syz = self._ysum = None
             self._zsum_host = None
             self._colconst_dev = None
             self.staged = True
         return self
 
+    def _ensure_y(self):
+        """Tiled Y operand, column sums and sum of squares (mepp_build_y), once per staged dataset."""
+        if self._ysum is None:
+            torch = self.torch
+            if self._perm_ready is not None:
+                torch.cuda.current_stream(self.device).wait_event(self._perm_ready)
+            self._y_planes = torch.empty(int(_lib.lib.mepp_y_planes_bytes(self.C, self.n_pad)), dtype=torch.uint8,
+                                         device=self.device)
+            self._col_syz = torch.empty(self.C, dtype=torch.float64, device=self.device)
+            self._ysum = torch.empty(2, dtype=torch.float64, device=self.device)
+            _lib.check(_lib.lib.mepp_build_y(_ptr(self._yhat_d), _ptr(self._perm_d), _ptr(self.zhat), self.N, self.P,
+                                             _ptr(self._y_planes), _ptr(self._col_syz), _ptr(self._ysum), self._stream()),
+                       "build_y")
+            self.launches += 3 if self.use_gc else 2
+
+    @property
+    def y_planes(self):
+        self._ensure_y()
+        return self._y_planes
+
+    @property
+    def col_syz(self):
+        self._ensure_y()
+        return self._col_syz
+
+    @property
+    def ysum(self):
+        self._ensure_y()
+        return self._ysum
+
     def _yrows(self):
         if self._y_rows is None:
+            self._ensure_y()
             ldY = int(_lib.lib.mepp_y_rows_ld(self.C))
             self._y_rows = self.torch.empty((self.n_pad, ldY), dtype=self.torch.float32, device=self.device)
             _lib.check(_lib.lib.mepp_build_y_rows(_ptr(self._yhat_d), _ptr(self._perm_d), self.N, self.P,
@@ -285,6 +325,12 @@ class Engine:
         T = len(tasks)
         rows = host['unit_rows']
         U = len(rows)
+        # longest units first: their CTAs take the longest (the DP costs ~ m * score range)
+        order = np.argsort(-host['dp_par'][rows, 7], kind='stable')
+        rank_of = np.empty(U, dtype=np.int32)
+        rank_of[order] = np.arange(U, dtype=np.int32)
+        rows = rows[order]
+        host = dict(host, unit_of_task=rank_of[host['unit_of_task']])
         R = host['dp_par'][rows, 7].astype(np.int64)
         off = np.zeros(U, dtype=np.int64)
         off[1:] = np.cumsum(2 * (R[:-1] + 1))
