@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.gpu_index)],
+                                          "-lms", "20", "-i", str(self.gpu_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -269,7 +269,7 @@ def main():
         print("e2e host ms per step:", e2e_times, file=sys.stderr, flush=True)
     dt_e2e = parallel.barrier_and_max(t3 - t2, device=dev if world > 1 else None)
     clocks = sampler.stop(t0, t1)
-    clocks["sampled"] = "during the device-resident timed region (50 ms period); halted for the e2e region"
+    clocks["sampled"] = "during the device-resident timed region (20 ms period); halted for the e2e region"
 
     if rank != 0:
         if world > 1:
@@ -326,11 +326,11 @@ def main():
                                        issued_step_fraction=issued_frac, split_products=3,
                                        ms_per_step=1e3 * per("gemm"), launches_per_step=groups)
     if stage_ms.get("perm_stats"):
-        # r is read by the row sort, the pooled histogram and the integrals and the sorted keys are written and read back
-        stats_bytes = 4.0 * n_local * L * (3.0 * C_ + 2.0 * P)
+        # r is streamed three times: row selection, pooled histogram + second radix digit, integrals + third digit
+        stats_bytes = 4.0 * n_local * L * 3.0 * C_
         a = stats_bytes / per("perm_stats") / 1e9
         kernels["perm_stats"] = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"],
-                                     ms_per_step=1e3 * per("perm_stats"), launches_per_step=10 * groups,
+                                     ms_per_step=1e3 * per("perm_stats"), launches_per_step=9 * groups,
                                      limit="per-row tail selection in registers, pooled histogram search, 3-digit radix select: ALU / shared-memory atomics")
     for k in ("correlation", "finalize"):
         if stage_ms.get(k):

@@ -627,7 +627,7 @@ class Engine:
             _lib.check(_lib.lib.mepp_perm_stats(_ptr(r), self.ldS, T, L, C_, k_lo, k_hi, ks_lo, ks_hi, _ptr(dev['full_os']),
                                                 _ptr(dev['full_cnt']), _ptr(dev['semi_os']), _ptr(dev['semi_cnt']),
                                                 _ptr(dev['integral']), _ptr(work), st), "perm_stats")
-            self.launches += 10
+            self.launches += 9
             ev = self._mark(ev, 'perm_stats')
         # K4: every output column of the group on the device; the host only copies the block into the result table
         out_d = self._buf(f'finalized{slot}', int(_lib.lib.mepp_finalize_out_bytes(T, L)), torch.uint8)
