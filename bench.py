@@ -301,6 +301,13 @@ def main():
         kernels["scan"] = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"],
                                ms_per_step=1e3 * per("scan"), launches_per_step=groups,
                                gwindows_per_s=N * L * n_local / per("scan") / 1e9,
+                               # a scan that writes X once moves 4 B per bp*task; this one emits X as a list of
+                               # its non-zeros, so per 8(d) it is reported as compute bound: adds = N * L * m * strands
+                               survey_4B_equiv_gbs=4.0 * N * L * n_local / per("scan") / 1e9,
+                               survey_4B_equiv_frac=4.0 * N * L * n_local / per("scan") / 1e9 / peaks["hbm_gbs"],
+                               tap_adds_per_s=float(N) * L * sum(pwm.shape[1] * (1 if o in ('+', '-') else 2)
+                                                                 for pwm, o in my_tasks) / per("scan"),
+                               int_add_peak_per_s=148 * 128 * clocks_mhz_hint(peaks) * 1e6,
                                limit="integer issue / shared-memory lookups of the pre-filter (ncu: issue slots ~47 % busy, "
                                      "DRAM < 1 %): X is written as a list of its non-zeros, so almost no bytes move")
     if stage_ms.get("gemm") and sparse:
