@@ -179,7 +179,8 @@ class Engine:
         self.share_scans = os.environ.get("MEPP_SHARE_SCANS", "1") != "0"   # '+' rides on the '+/-' pass of its motif
         self.profile_path = os.environ.get("MEPP_PROFILE_PATH", "auto")     # 'auto' | 'sparse' | 'tensor'
         self.last_paths = []
-        self.copy_threads = int(os.environ.get("MEPP_COPY_THREADS", "4"))
+        from .parallel import host_threads
+        self.copy_threads = int(os.environ.get("MEPP_COPY_THREADS", str(max(1, min(4, host_threads())))))
         self.device_tables = os.environ.get("MEPP_DEVICE_TABLES", "1") != "0"   # threshold DP on the GPU
 
     # ------------------------------------------------------------------ helpers
