@@ -21,6 +21,8 @@ def main():
     margin = cfg["margin"]
     tasks = [(pwm, o) for _, pwm, o in cfg["tasks"]] + [(cfg["tasks"][0][1], '-')]
     eng = Engine()
+    eng.profile_path = 'tensor'        # this tool inspects the tiled operands of the tcgen05 path, stage by stage
+    eng.fuse_correlation = False
     eng.stage(ascii_u8, scores, perm, use_gc=True)
     torch.cuda.synchronize()
     codes = staging.ascii_to_codes(ascii_u8)
