@@ -551,6 +551,10 @@ class Engine:
             lut_d, bias_d, mlen_d, nfilt_d, qtab_d, qthr_d = (self._to_dev(lut), self._to_dev(bias), self._to_dev(mlen),
                                                               self._to_dev(nfilt), self._to_dev(qtab), self._to_dev(qthr))
             units = scan_units(tables) if self.share_scans else None
+        if units is not None and len(units) > 2:
+            # longest motifs first and similar lengths side by side: the two warps of a CTA then finish together and the
+            # last wave of CTAs is the cheapest one
+            units = units[np.argsort(-mlen[units[:, 0]], kind='stable')]
         units_d = self._to_dev(units) if units is not None else None
         n_units = len(units) if units is not None else 0
         self.last_units = n_units if units is not None else T
