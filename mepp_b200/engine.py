@@ -92,6 +92,7 @@ def _copy_pool(n):
 
 SPARSE_DENSITY_MAX = 5e-3     # expected non-zero fraction of X up to which the sparse profile path is used
 SPARSE_ENTRY_DENSITY = 8e-3   # capacity of the entry list as a fraction of T * N * L
+SPARSE_SMALL_ENTRIES = 4e6    # expected non-zeros per group below which the sparse path is used whatever the density
 MIN_ENTRY_CAP = 1 << 20
 
 
@@ -362,6 +363,7 @@ class Engine:
         The sparse path costs ~4 (1 + P) bytes of L2 traffic per non-zero, the GEMM the same whatever X holds:
         with the reference's p = 1e-4 threshold X is ~1e-3 dense and the sparse path wins by ~4x; the
         break-even is near 5e-3."""
+        self._density_est = 0.0
         if self.profile_path in ('sparse', 'tensor'):
             return self.profile_path
         y_rows_bytes = 4 * self.n_pad * int(_lib.lib.mepp_y_rows_ld(self.C))
@@ -371,7 +373,12 @@ class Engine:
             pv = tables.pvalue * int(tables.nfilt.max())
         else:
             pv = max((tb.get('pvalue', 1e-4) * tb['n_filters'] for tb in tables), default=1e-4)
-        return 'sparse' if pv * (2 * int(margin) + 1) <= SPARSE_DENSITY_MAX else 'tensor'
+        density = pv * (2 * int(margin) + 1)
+        self._density_est = density
+        # small problems always take the sparse path (it is exact in x and its cost is negligible there); the tiled
+        # fp16 operands lose precision on rows of tiny scores, which only average out over many sequences
+        small = density * len(tables) * self.N * self.L <= SPARSE_SMALL_ENTRIES
+        return 'sparse' if density <= SPARSE_DENSITY_MAX or small else 'tensor'
 
     def _colconst(self):
         """Per-dataset constants of the fused correlation epilogue (built once per stage())."""
@@ -565,7 +572,8 @@ class Engine:
             x_bytes = int(_lib.lib.mepp_x_planes_bytes(m_rows, self.n_pad))
             x_planes = self._buf('x_planes', x_bytes, torch.uint8, zero=True)
         else:
-            entry_cap = -(-max(MIN_ENTRY_CAP, int(T * N * L * SPARSE_ENTRY_DENSITY)) // _lib.ENTRY_LISTS) * _lib.ENTRY_LISTS
+            dens = max(SPARSE_ENTRY_DENSITY, 2.0 * getattr(self, '_density_est', 0.0))
+            entry_cap = -(-max(MIN_ENTRY_CAP, int(T * N * L * dens)) // _lib.ENTRY_LISTS) * _lib.ENTRY_LISTS
             entries = self._buf('entries', entry_cap * 16, torch.uint8)
             entry_count = self._buf(f'entry_count{slot}', (16 * _lib.ENTRY_LISTS,), torch.int64)
             row_nnz = self._buf('row_nnz', (m_rows + 1,), torch.int32)
