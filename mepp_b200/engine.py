@@ -358,6 +358,30 @@ class Engine:
         self.launches += 2
         return DeviceTables(dev, host, 0, T)
 
+    def upload_tables(self, tables):
+        """Host scan tables (motif_layers.scan_tables) -> DeviceTables resident in HBM, so that repeated profile()
+        calls over the same task list move no table bytes."""
+        torch = self.torch
+        T = len(tables)
+        host = dict(mlen=np.array([tb['m'] for tb in tables], dtype=np.int32),
+                    nfilt=np.array([tb['n_filters'] for tb in tables], dtype=np.int32),
+                    pvalue=max((tb.get('pvalue', 1e-4) for tb in tables), default=1e-4),
+                    thr=np.array([tb['thr'] for tb in tables], dtype=np.float64))
+        units = scan_units(tables)
+        twin = np.full(T, -1, dtype=np.int32)
+        if units is not None:
+            for t, u in units:
+                if u >= 0:
+                    twin[t] = u
+        host['twin_of'] = twin
+        dev = dict(lut=self._to_dev(np.stack([tb['lut'] for tb in tables]).astype(np.float32)),
+                   bias=self._to_dev(np.array([tb['bias'] for tb in tables], dtype=np.float32)),
+                   mlen=self._to_dev(host['mlen']), nfilt=self._to_dev(host['nfilt']),
+                   qtab=self._to_dev(np.stack([tb['qtab'] for tb in tables]).view(np.int32)),
+                   qthr=self._to_dev(np.stack([tb['qthr'] for tb in tables]).view(np.int32)),
+                   thr=self._to_dev(host['thr']))
+        return DeviceTables(dev, host, 0, T)
+
     def choose_path(self, tables, margin):
         """'sparse' (gather of Y rows per non-zero of X) or 'tensor' (tcgen05 GEMM over the tiled operand).
         The sparse path costs ~4 (1 + P) bytes of L2 traffic per non-zero, the GEMM the same whatever X holds:
@@ -451,7 +475,9 @@ class Engine:
             # host threshold DP: every group's tables are submitted to the host thread pool now and collected when
             # the group is launched, so the DP of the later groups runs while the earlier ones are on the GPU
             dtab = futures = None
-            if tables is None and self.device_tables:
+            if isinstance(tables, DeviceTables):
+                dtab, tables = tables, None
+            elif tables is None and self.device_tables:
                 dtab = self.device_tables_for(tasks, **table_kw)
             elif tables is None:
                 futures = [motif_layers.scan_tables_async(tasks[g0:g1], **table_kw) for g0, g1 in groups]
