@@ -96,7 +96,7 @@ int64_t mepp_sym_words(int L);              /* W3 */
 int64_t mepp_pad32(int64_t n);              /* n_pad */
 int64_t mepp_x_planes_bytes(int64_t m_rows, int64_t n_pad);
 int     mepp_choose_bn(int C, int* n_tiles_n);  /* column tile width (multiple of 32, <=256) */
-int64_t mepp_y_planes_bytes(int C, int64_t n_pad);
+int64_t mepp_y_planes_bytes(int C, int64_t n_pad);   /* tiles + n_pad uint32 of scratch for mepp_build_y */
 
 /* ------------------------------------------------------------------ K0: pack
  * Replaces seq_to_mat / scored_fasta_df_to_dataset one-hot (onehot_dna.py:61-70,

@@ -114,10 +114,11 @@ int mepp_choose_bn(int C, int* n_tiles_n) {
   return bn;
 }
 
+// tiles of the B operand, followed by n_pad uint32 of scratch for mepp_build_y (the packed fp16 hi | lo of every score)
 int64_t mepp_y_planes_bytes(int C, int64_t n_pad) {
   int nt = 0;
   int bn = mepp_choose_bn(C, &nt);
-  return (int64_t)nt * (n_pad / mepp::kBlockK) * (int64_t)mepp::b_tile_bytes(bn);
+  return (int64_t)nt * (n_pad / mepp::kBlockK) * (int64_t)mepp::b_tile_bytes(bn) + n_pad * 4;
 }
 
 // MOODS.tools.log_odds: W[j][i] = ln((mat[j][i] + ps*bg[j]) / col_i) - ln(bg[j]).

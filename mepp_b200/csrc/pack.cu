@@ -200,8 +200,10 @@ int mepp_build_y(const float* yhat_dev, const int32_t* perm_dev, const float* zh
   int n_tiles_n = 0;
   int BN = mepp_choose_bn(C, &n_tiles_n);
   int64_t n_pad = mepp_pad32(N);
-  uint32_t* ysplit = nullptr;
-  MEPP_CUDA_CHECK(cudaMallocAsync(&ysplit, sizeof(uint32_t) * (size_t)N, st));
+  // scratch behind the tiles (mepp_y_planes_bytes reserves it): no stream-ordered allocation per call, whose pool
+  // trimming made single staging calls take 10-400 ms at random
+  uint32_t* ysplit = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(y_planes_dev) +
+                                                 (int64_t)n_tiles_n * (n_pad / kBlockK) * (int64_t)b_tile_bytes(BN));
   MEPP_CUDA_CHECK(cudaMemsetAsync(ysum_dev, 0, 2 * sizeof(double), st));
   y_split_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(yhat_dev, N, ysplit, ysum_dev);
   dim3 grid((unsigned)((n_pad / 8 + 127) / 128), (unsigned)(n_tiles_n * BN));
@@ -213,7 +215,6 @@ int mepp_build_y(const float* yhat_dev, const int32_t* perm_dev, const float* zh
     MEPP_CUDA_CHECK(cudaMemsetAsync(col_syz_dev, 0, sizeof(double) * (size_t)C, st));
   }
   MEPP_CUDA_CHECK(cudaGetLastError());
-  MEPP_CUDA_CHECK(cudaFreeAsync(ysplit, st));
   return 0;
 }
 
