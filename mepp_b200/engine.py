@@ -425,10 +425,10 @@ class Engine:
 
     # ------------------------------------------------------------------ sizing
     def group_size(self):
-        per_task = (self.L * self.n_pad * 4            # X planes (fp16 hi + lo)
+        """Tasks per group that fit the memory budget with the larger of the two profile paths (the tiled X operand)."""
+        per_task = (self.L * self.n_pad * 4            # X planes (fp16 hi + lo; the sparse path needs ~1 % of this)
                     + self.L * self.ldS * 4            # r
-                    + self.L * max(self.P, 1) * 4      # sorted keys
-                    + self.n_pad * 4 + self.L * 64)
+                    + 2 * (self.n_pad * 4 + self.L * 80))   # densities and finalised columns, two staging slots
         g = max(1, min(self.max_group, self.mem_budget // max(per_task, 1)))
         return int(g)
 

@@ -6,7 +6,6 @@ numpy's "linear" percentile interpolation, permutation p-values = count / n, the
 parametric Fisher-z confidence interval and t-test, and the rolling-mean count smoothing.
 Everything here is O(T * L) numpy on vectors the GPU already reduced.
 """
-import os
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
