@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/micro/fp64_rate tools/micro/fp64_rate.cu
 // Micro-benchmark: per-SM throughput of DFMA, F2F.F64.F32 and FFMA on this GPU (run under gpurun).
 #include <cstdio>
 #include <cuda_runtime.h>
