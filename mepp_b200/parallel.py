@@ -110,31 +110,45 @@ def gather_blocks(local_block, local_ids, n_total, device=None, root_only=True):
     send, send_ids = torch.from_numpy(pad), torch.from_numpy(ids)
     if device is not None:
         send, send_ids = send.to(device, non_blocking=True), send_ids.to(device, non_blocking=True)
-    recv = recv_ids = None
+    # one receive buffer (rank-major), the per-rank pieces are views of it; on the root it goes to the host in one copy
+    # into a cached pinned buffer
+    big = big_ids = None
     done = False
     if root_only:
         try:
             if rank == 0:
-                recv = [torch.empty_like(send) for _ in range(world)]
-                recv_ids = [torch.empty_like(send_ids) for _ in range(world)]
-            dist.gather(send, recv, dst=0)
-            dist.gather(send_ids, recv_ids, dst=0)
+                big = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+                big_ids = torch.empty((world, t_max), dtype=send_ids.dtype, device=send.device)
+            dist.gather(send, list(big.unbind(0)) if rank == 0 else None, dst=0)
+            dist.gather(send_ids, list(big_ids.unbind(0)) if rank == 0 else None, dst=0)
             done = True
         except (RuntimeError, NotImplementedError):
             done = False
     if not done:
-        recv = [torch.empty_like(send) for _ in range(world)]
-        recv_ids = [torch.empty_like(send_ids) for _ in range(world)]
-        dist.all_gather(recv, send)
-        dist.all_gather(recv_ids, send_ids)
+        big = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+        big_ids = torch.empty((world, t_max), dtype=send_ids.dtype, device=send.device)
+        dist.all_gather(list(big.unbind(0)), send)
+        dist.all_gather(list(big_ids.unbind(0)), send_ids)
     if root_only and rank != 0:
         return None
-    rec = torch.cat(recv, dim=0).cpu().numpy()
-    rid = torch.cat(recv_ids, dim=0).cpu().numpy()
-    keep = rid >= 0
+    if big.is_cuda:
+        key = (tuple(big.shape), big.dtype)
+        host = _PINNED.get(key)
+        if host is None:
+            host = _PINNED[key] = torch.empty(big.shape, dtype=big.dtype, pin_memory=True)
+        host.copy_(big, non_blocking=True)
+        rid = big_ids.cpu().numpy()                     # (synchronises the stream: the pinned copy is complete)
+        rec = host.numpy()
+    else:
+        rec, rid = big.numpy(), big_ids.numpy()
     out = np.empty((n_total,) + item_shape, dtype=local_block.dtype)
-    out[rid[keep]] = rec[keep]
+    for r_ in range(world):
+        k_ = int((rid[r_] >= 0).sum())                  # a rank's valid rows come first
+        out[rid[r_, :k_]] = rec[r_, :k_]
     return out
+
+
+_PINNED = {}
 
 
 def barrier_and_max(seconds, device=None):
