@@ -51,7 +51,9 @@ static void build_filter_table(const float* lut, int m, int n_filters, float bia
       qn[f][j] = std::floor((mean - mn[f][j]) * scale);
       if (qn[f][j] < 0.0) qn[f][j] = 0.0;
     }
-  for (int t = 0; t < 16; ++t)
+  const int n_slots = (m + 1) / 2;                     // slots past the motif hold zeros
+  for (int k = n_slots * 64; k < 16 * 64; ++k) qtab[k] = 0u;
+  for (int t = 0; t < n_slots; ++t)
     for (int e = 0; e < 64; ++e) {
       uint32_t packed = 0;
       for (int f = 0; f < n_filters; ++f) {

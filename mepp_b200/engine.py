@@ -174,6 +174,7 @@ class Engine:
         self._bufs = {}
         self._pins = {}
         self._copy_stream = None
+        self._aux_stream = None
         self.launches = 0   # kernels launched by this engine (bench.py reports it)
         self.timing = None  # set to {} to collect per-stage CUDA-event times (ms)
         self.fuse_correlation = True   # False: separate GEMM (S) + correlation kernels (tests / A-B runs)
@@ -337,23 +338,35 @@ class Engine:
         off = np.zeros(U, dtype=np.int64)
         off[1:] = np.cumsum(2 * (R[:-1] + 1))
         n_scratch = int(off[-1] + 2 * (R[-1] + 1))
-        dev = dict(lut=self._to_dev(host['lut']), mlen=self._to_dev(host['mlen']), nfilt=self._to_dev(host['nfilt']),
-                   qtab=self._to_dev(host['qtab'].view(np.int32)),
-                   bias=torch.empty(T, dtype=torch.float32, device=self.device),
-                   qthr=torch.empty((T, 2), dtype=torch.int32, device=self.device),
-                   thr=torch.empty(T, dtype=torch.float64, device=self.device))
+        # uploads and the two kernels run on an auxiliary stream, so that they overlap the staging copies of the
+        # dataset that are still in flight on the compute stream; the compute stream waits for them before the scan
+        compute = torch.cuda.current_stream(self.device)
+        if self._aux_stream is None:
+            self._aux_stream = torch.cuda.Stream(device=self.device)
         scratch = self._buf('dp_scratch', (n_scratch,), torch.float64)
-        thr_unit = torch.empty(U, dtype=torch.float64, device=self.device)
-        st = self._stream()
-        # (locals keep the uploaded inputs alive until both kernels are enqueued)
-        smat_d, umlen_d = self._to_dev(host['smat'][rows]), self._to_dev(host['mlen'][rows])
-        par_d, off_d = self._to_dev(host['dp_par'][rows]), self._to_dev(off)
-        uot_d, qpar_d = self._to_dev(host['unit_of_task']), self._to_dev(host['qpar'])
-        _lib.check(_lib.lib.mepp_thresholds_dp(_ptr(smat_d), _ptr(umlen_d), _ptr(par_d), _ptr(off_d), _ptr(scratch),
-                                               _ptr(thr_unit), U, st), "thresholds_dp")
-        _lib.check(_lib.lib.mepp_task_thresholds(_ptr(thr_unit), _ptr(uot_d), _ptr(qpar_d), _ptr(dev['mlen']),
-                                                 _ptr(dev['nfilt']), T, _ptr(dev['bias']), _ptr(dev['qthr']),
-                                                 _ptr(dev['thr']), st), "task_thresholds")
+        # (the scratch is free: the scans of the previous call waited for its DP, and that call has returned)
+        with torch.cuda.stream(self._aux_stream):
+            dev = dict(lut=self._to_dev(host['lut']), mlen=self._to_dev(host['mlen']), nfilt=self._to_dev(host['nfilt']),
+                       qtab=self._to_dev(host['qtab'].view(np.int32)),
+                       bias=torch.empty(T, dtype=torch.float32, device=self.device),
+                       qthr=torch.empty((T, 2), dtype=torch.int32, device=self.device),
+                       thr=torch.empty(T, dtype=torch.float64, device=self.device))
+            thr_unit = torch.empty(U, dtype=torch.float64, device=self.device)
+            st = self._stream()
+            smat_d, umlen_d = self._to_dev(host['smat'][rows]), self._to_dev(host['mlen'][rows])
+            par_d, off_d = self._to_dev(host['dp_par'][rows]), self._to_dev(off)
+            uot_d, qpar_d = self._to_dev(host['unit_of_task']), self._to_dev(host['qpar'])
+            _lib.check(_lib.lib.mepp_thresholds_dp(_ptr(smat_d), _ptr(umlen_d), _ptr(par_d), _ptr(off_d), _ptr(scratch),
+                                                   _ptr(thr_unit), U, st), "thresholds_dp")
+            _lib.check(_lib.lib.mepp_task_thresholds(_ptr(thr_unit), _ptr(uot_d), _ptr(qpar_d), _ptr(dev['mlen']),
+                                                     _ptr(dev['nfilt']), T, _ptr(dev['bias']), _ptr(dev['qthr']),
+                                                     _ptr(dev['thr']), st), "task_thresholds")
+            ready = torch.cuda.Event()
+            ready.record(self._aux_stream)
+        compute.wait_event(ready)
+        for t_ in list(dev.values()) + [smat_d, umlen_d, par_d, off_d, uot_d, qpar_d, thr_unit]:
+            t_.record_stream(compute)             # allocated on the auxiliary stream, read by the compute stream
+        # (kept alive with the tables: the kernels above read them asynchronously)
         dev['_keep'] = (smat_d, umlen_d, par_d, off_d, uot_d, qpar_d, thr_unit)
         self.launches += 2
         return DeviceTables(dev, host, 0, T)

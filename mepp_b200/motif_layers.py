@@ -155,18 +155,25 @@ def prepare_tables(tasks, pseudocount=0.0001, pvalue=0.0001, bg=None, honour_fla
     ochar = np.empty(T, dtype=np.int32)
     unit_index, unit_of_task, unit_rows = {}, np.empty(T, dtype=np.int32), []
     plus_of, duals = {}, []
-    for t, (pwm, orient) in enumerate(tasks):
-        a = np.ascontiguousarray(pwm, dtype=np.float64)
-        if a.ndim != 2 or a.shape[0] != 4:
-            raise ValueError("motif_matrix must have shape (4, m)")
-        m = a.shape[1]
-        if not 1 <= m <= _lib.MAX_MOTIF_LEN:
-            raise ValueError(f"motif length {m} outside [1, {_lib.MAX_MOTIF_LEN}]")
-        pwms[t, :, :m] = a
+    seen = {}                                   # id(matrix object) -> (bytes, m, row): orientations of one motif usually
+    for t, (pwm, orient) in enumerate(tasks):   # share the matrix object, which is then packed and hashed once
+        hit = seen.get(id(pwm))
+        if hit is None:
+            a = np.ascontiguousarray(pwm, dtype=np.float64)
+            if a.ndim != 2 or a.shape[0] != 4:
+                raise ValueError("motif_matrix must have shape (4, m)")
+            m = a.shape[1]
+            if not 1 <= m <= _lib.MAX_MOTIF_LEN:
+                raise ValueError(f"motif length {m} outside [1, {_lib.MAX_MOTIF_LEN}]")
+            pwms[t, :, :m] = a
+            hit = seen[id(pwm)] = (a.tobytes(), m, t, pwm)      # (the object is kept alive: ids are not reused)
+        else:
+            pwms[t] = pwms[hit[2]]
+        raw, m = hit[0], hit[1]
         mlen[t] = m
         o = orient if orient in ('+', '-') else 'd'
         ochar[t] = ord(o)
-        key = (a.tobytes(), m, '-' if o == '-' else 'f')
+        key = (raw, m, '-' if o == '-' else 'f')
         if key not in unit_index:
             unit_index[key] = len(unit_rows)
             unit_rows.append(t)
