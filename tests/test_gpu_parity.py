@@ -501,3 +501,25 @@ def test_device_thresholds_equal_host_thresholds():
         assert np.array_equal(thr, np.array([tb['thr'] for tb in ref]))
         assert np.array_equal(bias, np.array([tb['bias'] for tb in ref], dtype=np.float32))
         assert np.array_equal(qthr, np.stack([tb['qthr'] for tb in ref]))
+
+
+def test_tiled_operand_is_restored_even_when_the_match_list_overflows():
+    """Tensor path: the scan stores only non-zero pieces into an all-zero operand and mepp_x_planes_reset clears them
+    from the match list; with a match list that is too small the whole operand is cleared instead.  Either way a
+    later call on the same engine (other tasks, other margin) must see a clean operand."""
+    from mepp_b200 import synth
+    ascii_u8, scores = synth.synth_sequences(700, 180, seed=44, n_rate=0.01)
+    perm = synth.synth_permutations(700, 9, seed=44)
+    m = synth.synth_motifs(6, seed=23, m_lo=5, m_hi=14)
+    first = [(m[0], '+/-'), (m[1], '+'), (m[2], '-')]
+    second = [(m[3], '+'), (m[4], '+/-'), (m[5], '+/-'), (m[0], '+')]
+    ref_eng = _engine().stage(ascii_u8, scores, perm)
+    ref_eng.profile_path = 'tensor'
+    want = ref_eng.profile(second, margin=1, return_r=True)
+    for cap in (None, 4):                                     # list large enough / overflowing
+        eng = _engine().stage(ascii_u8, scores, perm)
+        eng.profile_path = 'tensor'
+        eng.profile(first, margin=5, hits_cap=cap)
+        got = eng.profile(second, margin=1, return_r=True)
+        assert np.allclose(got.r, want.r, rtol=1e-6, atol=1e-9), cap      # (row sums are float64 atomics: order may differ)
+        assert np.array_equal(got.density, want.density)
