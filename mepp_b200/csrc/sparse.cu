@@ -115,15 +115,20 @@ __global__ void __launch_bounds__(256, 3) profile_sparse_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t n_items = a.m_rows * a.n_slabs;
+  const int64_t n_items = ((a.m_rows + 7) / 8) * 8 * a.n_slabs;
   if (a.offsets[a.m_rows + 1] != 0) return;            // overflow: results come from the tiled path instead
   const int64_t ld4 = a.ldY >> 2;
   const double* cc = a.colconst;
   const double n = cc[0], sy = cc[1], ay = cc[2], sz = cc[3], az = cc[4];
   const bool use_z = cc[5] != 0.0;
   for (int64_t item = warp0; item < n_items; item += n_warps) {
-    const int64_t row = item / a.n_slabs;
-    const int slab = (int)(item - row * a.n_slabs);
+    // items are ordered so that the eight warps of a CTA take eight consecutive rows of one slab: the 2 * margin + 1
+    // rows a match touches gather the same row of Y, which then comes from L1 for all but the first of them
+    const int64_t blk = item / (8 * a.n_slabs);
+    const int rem = (int)(item - blk * 8 * a.n_slabs);
+    const int slab = rem >> 3;
+    const int64_t row = blk * 8 + (rem & 7);
+    if (row >= a.m_rows) continue;
     const int beg = a.offsets[row], end = a.offsets[row + 1];
     const float4* yb = reinterpret_cast<const float4*>(a.y_rows) + (int64_t)slab * (kSlabCols / 4) + lane;
     double acc[16];

@@ -90,7 +90,9 @@ def get_minmax_stats(positional_r_df):
     imin, imax = int(np.argmin(r)), int(np.argmax(r))      # first occurrence, like df[...].head(1)
     pval = df[f'{prefix}positional_r_pval'].to_numpy()
     pos = df['position'].to_numpy()
-    min_r, max_r = r[imin], r[imax]
+    # list(df[col])[0] in the reference yields Python floats: everything below is float64 arithmetic (utils.py:401-444)
+    min_r, max_r = float(r[imin]), float(r[imax])
+    pval, pos = pval.tolist(), pos.tolist()
     if np.abs(max_r) >= np.abs(min_r):
         ext = (max_r, pval[imax], pos[imax])
     else:

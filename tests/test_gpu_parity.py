@@ -523,3 +523,52 @@ def test_tiled_operand_is_restored_even_when_the_match_list_overflows():
         got = eng.profile(second, margin=1, return_r=True)
         assert np.allclose(got.r, want.r, rtol=1e-6, atol=1e-9), cap      # (row sums are float64 atomics: order may differ)
         assert np.array_equal(got.density, want.density)
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "d"])
+def test_device_statistics_equal_the_reference_golden_vectors(name):
+    """K3 + K4 (mepp_perm_stats, mepp_finalize_positions) on the r matrices of tests/golden/reference_stats.npz
+    against the columns the reference's own get_positional_r_df / add_parametric_confidence_intervals_to_positional_r_df
+    produced for them (tests/golden/make_reference_stat_fixtures.py)."""
+    import os
+    from mepp_b200 import _lib, stats_host
+    from mepp_b200.engine import _ptr
+    _engine()
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_stats.npz")) as z:
+        ref = {k: z[k] for k in z.files}
+    L, P, center, ci, n = (int(v) for v in ref[f"stat_{name}__args"])
+    want = {str(c): ref[f"stat_{name}__col__{c}"] for c in ref[f"stat_{name}__columns"]}
+    r_h = ref[f"stat_{name}__r"]
+    r_h = np.ascontiguousarray(r_h if r_h.ndim > 1 else r_h[:, None])
+    Cc = 1 + P
+    r = torch.from_numpy(r_h).cuda()
+    count = torch.zeros((1, L), dtype=torch.int32, device='cuda')
+    q = stats_host.percentile_q(ci)
+    dev, k_lo, k_hi, g = [None] * 5, 0, 0, [0.0] * 4
+    if P > 0:
+        k_lo, g[0] = stats_host.virtual_index(P, q[0]); k_hi, g[1] = stats_host.virtual_index(P, q[1])
+        ks_lo, g[2] = stats_host.virtual_index(L * P, q[0]); ks_hi, g[3] = stats_host.virtual_index(L * P, q[1])
+        dev = [torch.empty((1, L, 4), dtype=torch.float32, device='cuda'), torch.empty((1, L), dtype=torch.int32, device='cuda'),
+               torch.empty((1, 4), dtype=torch.float32, device='cuda'), torch.empty((1, L), dtype=torch.int64, device='cuda'),
+               torch.empty((1, Cc), dtype=torch.float64, device='cuda')]
+        work = torch.empty(int(_lib.lib.mepp_perm_stats_work_bytes(1, L, Cc)), dtype=torch.uint8, device='cuda')
+        _lib.check(_lib.lib.mepp_perm_stats(_ptr(r), Cc, 1, L, Cc, k_lo, k_hi, ks_lo, ks_hi, *[_ptr(x) for x in dev],
+                                            _ptr(work), None), "perm_stats")
+    out = torch.empty(int(_lib.lib.mepp_finalize_out_bytes(1, L)), dtype=torch.uint8, device='cuda')
+    _lib.check(_lib.lib.mepp_finalize_positions(_ptr(r), Cc, 1, L, Cc, *[_ptr(x) for x in dev], _ptr(count), n, 0,
+                                                k_lo, k_hi, g[0], g[1], g[2], g[3],
+                                                float(stats_host.z_margin_f32(n, ci)), _ptr(out), None), "finalize")
+    torch.cuda.synchronize()
+    store = stats_host.alloc_positions(1, L, P)
+    stats_host.store_finalized(store, 0, out.cpu().numpy(), 1, L)
+    got = stats_host.positions_view(store, None if center < 0 else center)
+    for k in want:
+        a, b = np.asarray(got[k][0], dtype=np.float64), np.asarray(want[k], dtype=np.float64)
+        if k in ('positional_r_lower', 'positional_r_upper'):
+            assert np.abs(a - b).max() <= 4e-7, k
+        elif k == 'positional_r_pval':
+            assert np.allclose(a, b, rtol=2e-5, atol=1e-300), k
+        elif k in ('integral_r', 'permutation_integral_r_lower', 'permutation_integral_r_upper'):
+            assert np.allclose(a, b, rtol=3e-7), k                    # float32 trapezoid sums: summation order
+        else:
+            assert np.array_equal(a, b), k
