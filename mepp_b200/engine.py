@@ -631,6 +631,7 @@ class Engine:
                                       _ptr(units_d), n_units, int(mlen.max()), _ptr(x_planes), _ptr(rowstats), _ptr(count),
                                       _ptr(density), _ptr(hits_d), cap, _ptr(hit_count), _ptr(entries), entry_cap,
                                       _ptr(entry_count), _ptr(row_nnz), st), "scan")
+        self.launches += 1
         if path == 'tensor':
             # the scan stored only the non-zero pieces; the operand goes back to all-zero before its next use
             self._x_pending = dict(x=x_planes, hits=hits_d, cap=cap, hit_count=hit_count, N=N, L=L, T=T,
