@@ -196,8 +196,12 @@ def main():
 
     def e2e_step():
         """Public-API step from host buffers: stage + thresholds + all tasks (+ gather to rank 0 when sharded)."""
-        eng.stage(h_ascii, h_scores, h_perm, use_gc=True)
-        batch = eng.profile(my_tasks, margin=margin)       # host thresholds are computed per group, overlapped
+        if world > 1:
+            # one host copy per node: rank 0 uploads, the other GPUs receive over NVLink (NCCL broadcast)
+            eng.stage_broadcast(*((h_ascii, h_scores, h_perm) if rank == 0 else (None, None, None)), use_gc=True, src=0)
+        else:
+            eng.stage(h_ascii, h_scores, h_perm, use_gc=True)
+        batch = eng.profile(my_tasks, margin=margin)       # thresholds on the device, groups pipelined
         full = None
         if world > 1:
             # the small per-task profiles go to rank 0 (float32, one row per column; the full tables stay per rank,
