@@ -241,18 +241,25 @@ def main():
     from mepp_b200 import _lib
     _lib.check(_lib.lib.mepp_gemm_counters(None, 1), "gemm_counters")
     launches0 = eng.launches
+    # timed on the device: CUDA events on the launching stream, a barrier + synchronize on both sides (every
+    # profile() call ends with a host wait for its last result copy, so the closing event is recorded after all of
+    # the step's work on the side streams); the host clock around the same region is kept as a cross-check
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    ev_a.record(torch.cuda.current_stream(dev))
     for _ in range(args.steps):
         eng.profile(my_tasks, margin=margin, tables=dev_tables)
+    ev_b.record(torch.cuda.current_stream(dev))
     sync_all()
     t1 = time.perf_counter()
+    wall_value = t1 - t0
     launches = eng.launches - launches0
     stage_ms = eng.collect_timing()
     eng.timing = None
     steps2 = (C.c_ulonglong * 2)()
     _lib.check(_lib.lib.mepp_gemm_counters(steps2, 0), "gemm_counters")
     issued_frac = (steps2[0] / steps2[1]) if steps2[1] else 1.0
-    dt_value = parallel.barrier_and_max(t1 - t0, device=dev if world > 1 else None)
+    dt_value = parallel.barrier_and_max(1e-3 * ev_a.elapsed_time(ev_b), device=dev if world > 1 else None)
 
     # (2) end to end from pinned host buffers (clock sampler halted: its NVML polling slows host-side CUDA calls)
     sampler.halt()
@@ -262,18 +269,23 @@ def main():
     for _ in range(max(args.warmup, 3)):                   # untimed warm-up of the end-to-end path (the first steps after
         e2e_step()                                         # the switch from the device-resident loop are erratic)
     sync_all()
+    ev_c, ev_d = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t2 = time.perf_counter()
+    ev_c.record(torch.cuda.current_stream(dev))
     e2e_times = []
     for _ in range(args.steps):
         ta = time.perf_counter()
         e2e_step()
         e2e_times.append(round(1e3 * (time.perf_counter() - ta), 1))
+    ev_d.record(torch.cuda.current_stream(dev))
     sync_all()
     t3 = time.perf_counter()
     gc.enable()
     if os.environ.get("MEPP_BENCH_DEBUG"):
         print("e2e host ms per step:", e2e_times, file=sys.stderr, flush=True)
-    dt_e2e = parallel.barrier_and_max(t3 - t2, device=dev if world > 1 else None)
+    # an end-to-end step ends on the host (results in the caller's arrays, gathered on rank 0), so the larger of the
+    # event time and the host clock is what a caller waits for
+    dt_e2e = parallel.barrier_and_max(max(1e-3 * ev_c.elapsed_time(ev_d), t3 - t2), device=dev if world > 1 else None)
     clocks = sampler.stop(t0, t1)
     clocks["sampled"] = "during the device-resident timed region (100 ms period); halted for the e2e region"
 
@@ -381,6 +393,10 @@ def main():
                                     "tensor: fp16 hi/lo split, 3 tcgen05 products, fp32 TMEM accumulate"),
                 e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=1e3 * dt_e2e / args.steps,
                          h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
+                timing=dict(how="CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks",
+                            host_clock_ms_per_step=1e3 * wall_value / args.steps,
+                            overlap="scan of group g+1 on the compute stream, profile / statistics / finalisation of "
+                                    "group g on a high-priority stream" if eng.overlap else "none"),
                 gpu_launches=int(launches), roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline, clocks=clocks)
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -40,6 +40,7 @@ extern "C" {
 #define MEPP_MAX_MOTIF_LEN 32   /* taps held in a 64-bit code window */
 #define MEPP_MAX_MARGIN 16
 #define MEPP_ENTRY_LISTS 64     /* sub-lists of the sparse form of X (power of two) */
+#define MEPP_BP_WORDS 72        /* uint32 words of a task record of the bit-parallel scan stage */
 #define MEPP_X_SCALE 256.0f     /* X is stored as 256*x in the fp16 planes (exact) */
 
 int         mepp_abi_version(void);
@@ -152,6 +153,37 @@ int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
               void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
               void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
               void* stream);
+
+/* ---- bit-parallel first stage of the scan (same reference code as mepp_scan: motif_layers.py:80-165) ----
+ * Matches are rare, so most windows can be discarded by counting "bad" letters: with a cut d0 on the per-tap
+ * penalty max_c W[c][j] - W[c][j], a window with K or more letters above the cut (at taps with one or two good
+ * letters) cannot reach the threshold (K, d0 chosen per task so that this is certain; N bases never count).  One
+ * lane = one sequence, one register word = 32 window starts, a 2-bit saturating counter per filter updated with
+ * logic ops on bit planes of the sequences.  The survivors are evaluated exactly as in mepp_scan, so the outputs
+ * are identical.
+ *   mepp_plane_words(L)   words per sequence and letter of the plane stream (word 0 and the tail are zero padding)
+ *   mepp_pack_planes      sym_T (mepp_pack_dna) -> planes_T uint32 [mepp_plane_words(L)][4][n_pad]:
+ *                         bit k of word w >= 1 of plane c = [base 32 (w - 1) + k is a letter other than c];
+ *                         N bases, positions past L and padding sequences are zero in every plane
+ *   mepp_scan_bitpar_tables   per task: counted taps, K and whether the task's unit takes the bit-parallel kernel
+ *                         (modelled cost <= cost_ratio x that of the pair tables: 0 = only units that can never
+ *                         match, 1 = the model's break-even, huge = every unit with a sound choice);
+ *                         bp_dev uint32 [T][MEPP_BP_WORDS]; needs the final bias (threshold) of every task
+ *   mepp_scan_bitpar      mepp_scan with the first stage chosen per unit; bp_scratch_dev int32 [4 * U + 2],
+ *                         U = n_units (or T without a unit list) */
+int64_t mepp_plane_words(int L);
+int mepp_pack_planes(const uint32_t* sym_T_dev, int64_t N, int L, uint32_t* planes_T_dev, void* stream);
+int mepp_scan_bitpar_tables(const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev,
+                            const int32_t* nfilt_dev, int T, double cost_ratio, uint32_t* bp_dev, void* stream);
+int mepp_scan_bitpar(const uint32_t* sym_T_dev, const float* zhat_dev,
+                     int64_t N, int L, int T, int margin,
+                     const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev, const int32_t* nfilt_dev,
+                     const uint32_t* qtab_dev, const uint32_t* qthr_dev, const int32_t* units_dev, int n_units,
+                     int max_motif_len,
+                     void* x_planes_dev, double* rowstats_dev, int32_t* count_dev, int32_t* density_dev,
+                     void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
+                     void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
+                     const uint32_t* planes_T_dev, const uint32_t* bp_dev, int32_t* bp_scratch_dev, void* stream);
 
 /* Restore the all-zero state of an A operand that mepp_scan(..., N, L, T, margin, ...) wrote, from the
  * match list of that call (every match dirties rows pos-margin..pos+margin of one 8-column group); a NULL

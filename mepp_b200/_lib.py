@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libmepp_b200.so")
 MAX_MOTIF_LEN = 32
 MAX_MARGIN = 16
 ENTRY_LISTS = 64          # MEPP_ENTRY_LISTS
+BP_WORDS = 72             # MEPP_BP_WORDS
 X_SCALE = 256.0
 
 if not os.path.exists(LIB_PATH):
@@ -47,6 +48,11 @@ SIGNATURES = {
     "mepp_build_y": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "mepp_scan": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                          _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "mepp_plane_words": (_i64, [_i32]),
+    "mepp_pack_planes": (_i32, [_vp, _i64, _i32, _vp, _vp]),
+    "mepp_scan_bitpar_tables": (_i32, [_vp, _vp, _vp, _vp, _i32, _f64, _vp, _vp]),
+    "mepp_scan_bitpar": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+                                _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mepp_y_rows_ld": (_i64, [_i32]),
     "mepp_build_y_rows": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "mepp_profile_sparse_work_bytes": (_i64, [_i64, _i64]),

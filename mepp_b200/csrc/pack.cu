@@ -52,6 +52,34 @@ __global__ void pack_gc_kernel(const uint8_t* __restrict__ ascii, int64_t N, int
   gc[n] = n < N ? (0.5f * (float)twice) / (float)L : 0.0f;
 }
 
+// "Not this letter" bit planes of the symbol stream for the bit-parallel pre-filter of the scan (csrc/scan.cu): thread
+// per (plane word w, sequence n).  Word w >= 1 of plane c holds bit k = [base 32 (w - 1) + k is a letter other than
+// c]; N bases and positions past the end of the sequence are zero in all four planes (never a "bad" letter); word 0
+// and the words behind the sequence are zero padding.  32 bases = exactly the symbol-stream words 3 (w - 1) .. + 2.
+__global__ void pack_planes_kernel(const uint32_t* __restrict__ sym_T, int64_t N, int64_t n_pad, int L, int WB,
+                                   uint32_t* __restrict__ planes_T) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = blockIdx.y;
+  if (n >= n_pad) return;
+  uint32_t pl[4] = {0u, 0u, 0u, 0u};
+  const int x0 = 32 * (w - 1);
+  if (w >= 1 && x0 < L && n < N) {   // (padding sequences stay zero)
+    const uint32_t a = sym_T[(int64_t)(3 * (w - 1)) * n_pad + n], b = sym_T[(int64_t)(3 * (w - 1) + 1) * n_pad + n],
+                   c = sym_T[(int64_t)(3 * (w - 1) + 2) * n_pad + n];
+    const unsigned long long lo = (unsigned long long)a | ((unsigned long long)b << 32);   // stream bits 0..63: bases 0..20
+    const unsigned long long hi = ((unsigned long long)b >> 31) | ((unsigned long long)c << 1);   // stream bits 63..95: bases 21..31
+    for (int k = 0; k < 32; ++k) {
+      const uint32_t sym = k < 21 ? (uint32_t)(lo >> (3 * k)) & 7u : (uint32_t)(hi >> (3 * (k - 21))) & 7u;
+      if (sym < 4u && x0 + k < L) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) pl[cc] |= (cc != (int)sym ? 1u : 0u) << k;
+      }
+    }
+  }
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) planes_T[((int64_t)w * 4 + cc) * n_pad + n] = pl[cc];
+}
+
 // ysplit[n] = fp16 hi | lo<<16 of yhat[n]; also accumulates sum and sum of squares
 // of the split-rounded values in float64 (identical for every permuted column).
 __global__ void y_split_kernel(const float* __restrict__ yhat, int64_t N, uint32_t* __restrict__ ysplit,
@@ -214,6 +242,21 @@ int mepp_build_y(const float* yhat_dev, const int32_t* perm_dev, const float* zh
   } else {
     MEPP_CUDA_CHECK(cudaMemsetAsync(col_syz_dev, 0, sizeof(double) * (size_t)C, st));
   }
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int64_t mepp_plane_words(int L) { return ((int64_t)L + 31) / 32 + 4; }
+
+int mepp_pack_planes(const uint32_t* sym_T_dev, int64_t N, int L, uint32_t* planes_T_dev, void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(sym_T_dev && planes_T_dev, "pack_planes: null pointer");
+  MEPP_REQUIRE(N > 0 && L > 0, "pack_planes: empty input");
+  MEPP_REQUIRE(mepp_device_ok(), "pack_planes: no sm_100 CUDA device (no CPU fallback)");
+  const int64_t n_pad = mepp_pad32(N);
+  const int WB = (int)mepp_plane_words(L);
+  dim3 grid((unsigned)((n_pad + 255) / 256), (unsigned)WB);
+  pack_planes_kernel<<<grid, 256, 0, as_stream(stream)>>>(sym_T_dev, N, n_pad, L, WB, planes_T_dev);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -53,6 +53,9 @@ struct ScanArgs {
   // sparse form of X (optional): MEPP_ENTRY_LISTS sub-lists of sub_cap records, list = k-block % lists (one
   // counter per 128-byte line, so that the appends do not serialise on one L2 address)
   XEntry* entries; int64_t sub_cap; unsigned long long* entry_count; int32_t* row_nnz;
+  // bit-parallel first stage (optional): one-hot bit planes of the sequences, per-task letter sets, and the
+  // number of units of this launch's list (device side: the list is partitioned by a kernel, see bp_partition_kernel)
+  const uint32_t* planes_T; const uint32_t* bp; const int32_t* unit_count;
 };
 
 // Per-warp (= per unit) state shared by the helper routines below.  The helpers are deliberately NOT
@@ -362,6 +365,66 @@ __device__ __forceinline__ void advance(uint32_t (&r)[6]) {
   r[4] = __funnelshift_r(r[4], r[5], BITS); r[5] >>= BITS;
 }
 
+// ---- bit-parallel first stage ------------------------------------------------------------------------
+// A match needs  sum_j pen_j(letter_j) < D,  pen_j(c) = max_c' W[c'][j] - W[c][j] >= 0,  D = sum_j max_c W[c][j] -
+// threshold + rounding slack.  With a cut d0, letter c is "bad" at tap j when pen_j(c) > d0; taps with one or two
+// good letters are counted.  A window with K or more bad letters at counted taps has a penalty of at least the K
+// smallest per-tap minima of the bad penalties, and (d0, K) are chosen (bp_tables_kernel) so that this bound
+// exceeds D: such a window cannot match -- no false negatives.  N bases are never bad (their penalty is only
+// known to be >= 0).  Lane = sequence; a register word holds 32 window starts.  The sequences are staged as four
+// "a letter other than c" bit planes, so the bad bits of a counted tap with good letter g are plane g shifted to
+// the tap's base (the AND of two planes for two good letters): per tap and filter one shift and two logic ops
+// on the 2-bit saturating counter, the plane words coming from shared memory (the load/store pipe is idle
+// here, the integer pipe is the limiter of the pair tables).  Survivors (typically < 1 % of the windows) go to the
+// exact evaluation, so every reported score still comes from the canonical float32 order.
+struct BpUnit {
+  int K, dual;                 // K = 0: no window of this unit can match
+  int n1[2], n2[2];            // counted taps per filter: one good letter / two good letters
+};
+// descriptors in shared memory: [filter][32] uint4 = (byte offset of plane gA, tap, byte offset of plane gB, -)
+__device__ __forceinline__ void bp_count(const uint4* __restrict__ desc, int n1, int n2, const uint8_t* __restrict__ my_words,
+                                         uint32_t& c0, uint32_t& c1) {
+#pragma unroll 4
+  for (int i = 0; i < n1; ++i) {
+    const uint2 d = *reinterpret_cast<const uint2*>(desc + i);
+    const uint2 q = *reinterpret_cast<const uint2*>(my_words + d.x);
+    const uint32_t bad = __funnelshift_r(q.x, q.y, d.y);
+    const uint32_t t = c1 | (c0 & bad);
+    c0 = (c0 ^ bad) | (c1 & c0); c1 = t;
+  }
+#pragma unroll 2
+  for (int i = n1; i < n1 + n2; ++i) {
+    const uint4 d = desc[i];
+    const uint2 qa = *reinterpret_cast<const uint2*>(my_words + d.x);
+    const uint2 qb = *reinterpret_cast<const uint2*>(my_words + d.z);
+    const uint32_t bad = __funnelshift_r(qa.x, qa.y, d.y) & __funnelshift_r(qb.x, qb.y, d.y);
+    const uint32_t t = c1 | (c0 & bad);
+    c0 = (c0 ^ bad) | (c1 & c0); c1 = t;
+  }
+}
+// Survivor mask of the 32 windows starting at bit `g` of the padded plane stream (plane word 0 is zero padding).
+// s_words: this warp's staging area [4 planes][32 lanes] uint2 (lo, hi): each lane only touches its own slots.
+__device__ __forceinline__ uint32_t bp_survivors(const uint32_t* __restrict__ pl, int64_t n_pad, int g, const BpUnit& u,
+                                                 const uint4* __restrict__ s_desc, uint2* __restrict__ s_words, int lane) {
+  if (u.K == 0) return 0u;
+  const int w0 = g >> 5, sh = g & 31;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t* p = pl + ((int64_t)w0 * 4 + c) * n_pad;
+    const uint32_t a = __ldg(p), b = __ldg(p + 4 * n_pad), d = __ldg(p + 8 * n_pad);
+    s_words[c * 32 + lane] = make_uint2(__funnelshift_r(a, b, sh), __funnelshift_r(b, d, sh));
+  }
+  const uint8_t* my_words = reinterpret_cast<const uint8_t*>(s_words + lane);
+  uint32_t a0 = 0u, a1 = 0u, b0 = 0u, b1 = 0u;   // counters of filter 0 (a) and filter 1 (b), bit-sliced
+  bp_count(s_desc, u.n1[0], u.n2[0], my_words, a0, a1);
+  const uint32_t rej0 = u.K == 1 ? (a0 | a1) : u.K == 2 ? a1 : (a0 & a1);
+  if (!u.dual) return ~rej0;
+  bp_count(s_desc + 32, u.n1[1], u.n2[1], my_words, b0, b1);
+  const uint32_t rej1 = u.K == 1 ? (b0 | b1) : u.K == 2 ? b1 : (b0 & b1);
+  return ~(rej0 & rej1);
+}
+
+template <bool BP>
 __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const int t2, const int kb,
                                           uint32_t* __restrict__ s_qtab, float2* __restrict__ s_lut,
                                           float* __restrict__ s_buf,
@@ -380,10 +443,27 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
   const bool real = (int64_t)kb * 32 + lane < a.N;
   const int nbuf = 32 + 2 * mg;
 
-  {
+  BpUnit bpu;
+  bpu.K = 0; bpu.dual = 0; bpu.n1[0] = bpu.n1[1] = bpu.n2[0] = bpu.n2[1] = 0;
+  if constexpr (BP) {
+    // counted taps of the unit (bp_tables_kernel): word f * 32 + i of the task's record = tap | gA << 8 | gB << 16
+    const uint32_t* rec = a.bp + (size_t)t * MEPP_BP_WORDS;
+    uint4* dst = reinterpret_cast<uint4*>(s_qtab);
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      const uint32_t w = __ldg(rec + f * 32 + lane);
+      dst[f * 32 + lane] = make_uint4(((w >> 8) & 3u) * 256u, w & 0xffu, ((w >> 16) & 3u) * 256u, 0u);
+    }
+    const uint32_t h = __ldg(rec + 64), cn = __ldg(rec + 65);
+    bpu.K = (int)(h & 0xffu); bpu.dual = ((h >> 16) & 0xffu) == 2u;
+    bpu.n1[0] = (int)(cn & 0xffu); bpu.n2[0] = (int)((cn >> 8) & 0xffu);
+    bpu.n1[1] = (int)((cn >> 16) & 0xffu); bpu.n2[1] = (int)(cn >> 24);
+  } else {
     const uint4* src = reinterpret_cast<const uint4*>(a.qtab + (size_t)t * 1024);
     uint4* dst = reinterpret_cast<uint4*>(s_qtab);
     for (int i = lane; i < nslot * 16; i += 32) dst[i] = __ldg(src + i);   // (unused slots are zero)
+  }
+  {
     const float2* g_lut = reinterpret_cast<const float2*>(a.lut) + (size_t)t * (MEPP_MAX_MOTIF_LEN * 4);
     for (int i = lane; i < m * 4; i += 32) s_lut[i] = __ldg(g_lut + i);
   }
@@ -429,8 +509,8 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
   // zero bits in front of the stream; their candidates are dropped (rows below the first real one).
   const int lead = (kGroup - ((32 + mg - padl) % kGroup)) % kGroup;
   const int lsh = 3 * lead;              // left shift of the stream inside the register (0..21 bits)
-  uint32_t r[6], carry;
-  {
+  uint32_t r[6] = {0u, 0u, 0u, 0u, 0u, 0u}, carry = 0u;
+  if constexpr (!BP) {
     uint32_t w[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) w[k] = __ldg(my + (int64_t)k * wstride);
@@ -439,6 +519,7 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
     for (int k = 1; k < 6; ++k) r[k] = __funnelshift_l(w[k - 1], w[k], lsh);
     carry = w[5];
   }
+  const uint32_t* const my_planes = BP ? a.planes_T + (int64_t)kb * 32 + lane : nullptr;
   const uint32_t* pnext = my + 6 * wstride;
   const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(s_ring + lane);
   uint32_t stage = 0u;                   // byte offset of the stage holding the next refill (0 / 384)
@@ -449,7 +530,7 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
                    "l"(pnext + (int64_t)k * wstride) : "memory");
     pnext += 3 * wstride;
   };
-  prefetch(0u);
+  if constexpr (!BP) prefetch(0u);
   int left = 32;
   int q_head = 0, q_tail = 0;            // warp-uniform ring indices
   unsigned dcar = 0u, dbody = 0u;        // staging rows [0, 2 mg) / [2 mg, nbuf) may hold non-zero x0 (bit 1: twin)
@@ -506,6 +587,26 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
       q_tail += __popc(bal);
       if (q_tail - q_head >= 32) { dbody |= flush_candidates(a, c, q_head, 32, base, lane); q_head += 32; }
     };
+    if constexpr (BP) {
+      // ---- phase A, bit-parallel: 32 window starts per word step (two steps in the first chunk: 32 + 2 mg rows) ----
+#pragma unroll 1
+      for (int b0 = b_start; b0 < nbuf; b0 += 32) {
+        const int r_lo = max(b_lo - b0, 0), r_hi = min(b_hi - b0, 32);   // rows of this step that are real windows
+        if (r_hi <= r_lo) continue;
+        uint32_t valid = (0xffffffffu >> (32 - (r_hi - r_lo))) << r_lo;
+        if (!real) valid = 0u;                                           // padding sequences produce no candidates
+        // window start of row b0 is base i0 = base - mg - padl + b0 >= -31; the plane stream starts one word early
+        uint32_t surv = bp_survivors(my_planes, wstride, base - mg - padl + b0 + 32, bpu,
+                                     reinterpret_cast<const uint4*>(s_qtab), reinterpret_cast<uint2*>(s_ring), lane) & valid;
+        while (__any_sync(full, surv != 0u)) {
+          const bool cand = surv != 0u;
+          const int bb = __ffs((int)surv) - 1;
+          surv &= surv - 1u;
+          const unsigned bal = __ballot_sync(full, cand);
+          push(bal, cand, b0 + bb);
+        }
+      }
+    } else {
 #pragma unroll 1
     for (; b + kGroup <= b_hi; b += kGroup) {
       uint32_t s[kGroup];
@@ -540,6 +641,7 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
       const unsigned bal = __ballot_sync(full, cand);
       if (bal != 0u && b >= b_lo) push(bal, cand, b);
     }
+    }
     if (q_tail != q_head) { dbody |= flush_candidates(a, c, q_head, q_tail - q_head, base, lane); q_head = q_tail; }
     __syncwarp();
     // ---- phase B: blur + split + store, only for chunks that hold or border a match ----
@@ -550,29 +652,196 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
   }
 }
 
+// words of a warp's table region: the pair tables, or (bit-parallel) 32 taps x 2 filters x uint4 letter masks
+__host__ __device__ inline int scan_table_words(int qslots, bool bp) { return bp && qslots < 4 ? 256 : qslots * 64; }
+
+template <bool BP>
 __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const __grid_constant__ ScanArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = blockIdx.x;
   const int nbuf = 32 + 2 * a.margin;
   const int nb = a.units ? 2 : 1;                                                       // twin staging buffers
+  const int tabw = scan_table_words(a.qslots, BP);
   // carve shared memory (the pair tables come first: the OR-merged index needs 256-byte alignment)
   uint8_t* sm = smem_raw + ((256u - (uint32_t)(__cvta_generic_to_shared(smem_raw) & 255u)) & 255u);
-  uint32_t* s_qtabs = reinterpret_cast<uint32_t*>(sm);                                  // [warps][qslots * 64]
-  float* s_bufs = reinterpret_cast<float*>(s_qtabs + kScanWarps * a.qslots * 64);       // [warps][nb][nbuf][36]
-  uint32_t* s_rings = reinterpret_cast<uint32_t*>(s_bufs + kScanWarps * nb * nbuf * kRowStride);   // [warps][2][3][32]
-  float2* s_luts = reinterpret_cast<float2*>(s_rings + kScanWarps * 192);                         // [warps][qslots * 8]
+  uint32_t* s_qtabs = reinterpret_cast<uint32_t*>(sm);                                  // [warps][tabw]
+  float* s_bufs = reinterpret_cast<float*>(s_qtabs + kScanWarps * tabw);                // [warps][nb][nbuf][36]
+  constexpr int ringw = BP ? 256 : 192;   // refill ring [2][3][32], or (bit-parallel) plane words [4][32] uint2
+  uint32_t* s_rings = reinterpret_cast<uint32_t*>(s_bufs + kScanWarps * nb * nbuf * kRowStride);   // [warps][ringw]
+  float2* s_luts = reinterpret_cast<float2*>(s_rings + kScanWarps * ringw);                        // [warps][qslots * 8]
   uint16_t* s_queues = reinterpret_cast<uint16_t*>(s_luts + kScanWarps * a.qslots * 8);           // [warps][kQueue]
   __shared__ TaskCtx s_ctxs[kScanWarps];
 
   const int u = blockIdx.y * kScanWarps + warp;
-  if (u >= a.U) return;
+  if (u >= (a.unit_count ? *a.unit_count : a.U)) return;
   const int t = a.units ? a.units[2 * u] : u;
   const int t2 = a.units ? a.units[2 * u + 1] : -1;
   float* s_buf = s_bufs + warp * nb * nbuf * kRowStride;
   float* s_buf2 = s_buf + (nb - 1) * nbuf * kRowStride;
-  scan_task(a, t, t2, kb, s_qtabs + warp * a.qslots * 64, s_luts + warp * a.qslots * 8, s_buf, s_buf2, s_queues + warp * kQueue, s_rings + warp * 192,
-            &s_ctxs[warp], lane);
+  scan_task<BP>(a, t, t2, kb, s_qtabs + warp * tabw, s_luts + warp * a.qslots * 8, s_buf, s_buf2, s_queues + warp * kQueue,
+                s_rings + warp * ringw, &s_ctxs[warp], lane);
+}
+
+// ---- tables of the bit-parallel first stage ----------------------------------------------------------
+// One warp per task: tries every distinct penalty of filter 0 as the cut d0 (one candidate per lane and round); a
+// candidate counts the taps with one or two good letters (n1, n2), takes the smallest K in {1, 2, 3} for which the
+// sum of the K smallest per-tap minima of the bad penalties exceeds D (soundness, see above), and is rated by a cost
+// model in integer-pipe cycles per 32 windows: counter updates + expected survivors on uniform DNA x the cost of an
+// exact evaluation.  The unit takes the bit-parallel kernel when that cost is below cost_ratio x the modelled
+// cost of the pair tables.  Filter 1 gets the same d0 and K; its bound is checked on its own penalties.
+// Record of task t (MEPP_BP_WORDS words): words f * 32 + i = counted tap i of filter f: tap | gA << 8 | gB << 16
+// (good letters; taps with one good letter first), word 64 = K | use << 8 | filters << 16 (K = 0: nothing can
+// match), word 65 = n1[0] | n2[0] << 8 | n1[1] << 16 | n2[1] << 24, word 66 / 67 = survivor rate / cost (float bits).
+__device__ __forceinline__ void bp_push3(double v, double& s1, double& s2, double& s3) {
+  if (v < s1) { s3 = s2; s2 = s1; s1 = v; }
+  else if (v < s2) { s3 = s2; s2 = v; }
+  else if (v < s3) s3 = v;
+}
+__global__ void __launch_bounds__(128) bp_tables_kernel(const float* __restrict__ lut, const float* __restrict__ bias,
+                                                        const int32_t* __restrict__ mlen, const int32_t* __restrict__ nfilt,
+                                                        int T, double cost_ratio, uint32_t* __restrict__ bp) {
+  __shared__ double s_pen[4][2][MEPP_MAX_MOTIF_LEN * 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 4 + warp;
+  if (t >= T) return;
+  const unsigned full = 0xffffffffu;
+  const int m = mlen[t], nf = nfilt[t];
+  const float* l = lut + (size_t)t * (MEPP_MAX_MOTIF_LEN * 8);
+  // per tap (lane = tap) and filter: penalties, column maximum and largest magnitude
+  double maxT[2], absmax[2];
+  for (int f = 0; f < 2; ++f) {
+    double cmax = 0.0, amax = 0.0;
+    if (lane < m) {
+      double w[4];
+      for (int c = 0; c < 4; ++c) w[c] = (double)l[(lane * 4 + c) * 2 + f];
+      cmax = fmax(fmax(w[0], w[1]), fmax(w[2], w[3]));
+      amax = fmax(fmax(fabs(w[0]), fabs(w[1])), fmax(fabs(w[2]), fabs(w[3])));
+      for (int c = 0; c < 4; ++c) s_pen[warp][f][lane * 4 + c] = cmax - w[c];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      cmax += __shfl_xor_sync(full, cmax, o);
+      amax += __shfl_xor_sync(full, amax, o);
+    }
+    maxT[f] = cmax; absmax[f] = amax;
+  }
+  __syncwarp();
+  const double* pen = s_pen[warp][0];
+  // float32 sequential sum vs real sum: <= 4 m roundings of at most ulp(absmax) / 2 each, doubled (host.cu: build_filter_table)
+  double D[2];
+  for (int f = 0; f < 2; ++f)
+    D[f] = maxT[f] + (double)bias[t] + (2.0 * (4.0 * m) * absmax[f] * 5.97e-8 + 1e-6);   // bias = float(-threshold)
+  double best_cost = 1e300, best_rate = 1.0;
+  int best_q = 0x7fffffff, best_K = 0;
+  for (int q = lane; q <= 4 * m; q += 32) {
+    const double d0 = q == 0 ? 0.0 : pen[q - 1];
+    double s1 = 1e300, s2 = 1e300, s3 = 1e300;            // three smallest per-tap minima of the bad penalties
+    double p0 = 1.0, p1 = 0.0, p2 = 0.0;                  // P(0, 1, 2 bad letters so far) on uniform DNA
+    int n1 = 0, n2 = 0;
+    for (int j = 0; j < m; ++j) {
+      int nbad = 0;
+      double mb = 1e300;
+      for (int c = 0; c < 4; ++c) {
+        const double v = pen[j * 4 + c];
+        if (v > d0) { ++nbad; mb = fmin(mb, v); }
+      }
+      if (nbad < 2) continue;                             // three or four good letters: the tap is not counted
+      n1 += nbad == 3; n2 += nbad == 2;
+      bp_push3(mb, s1, s2, s3);
+      const double pj = 0.25 * nbad, qj = 1.0 - pj;
+      p2 = p2 * qj + p1 * pj; p1 = p1 * qj + p0 * pj; p0 = p0 * qj;
+    }
+    int K = 0;
+    double rate = 1.0;
+    if (s1 < 1e299 && s1 > D[0]) { K = 1; rate = p0; }
+    else if (s2 < 1e299 && s1 + s2 > D[0]) { K = 2; rate = p0 + p1; }
+    else if (s3 < 1e299 && s1 + s2 + s3 > D[0]) { K = 3; rate = p0 + p1 + p2; }
+    const double cost = nf * (8.0 * n1 + 14.0 * n2) + 10240.0 * rate * nf;
+    if (K && (cost < best_cost || (cost == best_cost && q < best_q))) {
+      best_cost = cost; best_rate = rate; best_q = q; best_K = K;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double c2 = __shfl_xor_sync(full, best_cost, o), r2 = __shfl_xor_sync(full, best_rate, o);
+    const int q2 = __shfl_xor_sync(full, best_q, o), K2 = __shfl_xor_sync(full, best_K, o);
+    if (c2 < best_cost || (c2 == best_cost && q2 < best_q)) { best_cost = c2; best_rate = r2; best_q = q2; best_K = K2; }
+  }
+  uint32_t* rec = bp + (size_t)t * MEPP_BP_WORDS;
+  int use = 0, n1[2] = {0, 0}, n2[2] = {0, 0};
+  uint32_t desc[2] = {0u, 0u};
+  if (!(D[0] > 0.0)) {
+    best_K = 0; best_rate = 0.0; best_cost = 0.0; use = 1;   // the threshold is above every reachable score
+  } else if (best_K > 0) {
+    const double d0 = best_q == 0 ? 0.0 : pen[best_q - 1];
+    bool sound = true;
+    for (int f = 0; f < nf; ++f) {
+      const double* pf = s_pen[warp][f];
+      int nbad = 0, g[2] = {0, 0}, ng = 0;
+      double mb = 1e300;
+      if (lane < m)
+        for (int c = 0; c < 4; ++c) {
+          if (pf[lane * 4 + c] > d0) { ++nbad; mb = fmin(mb, pf[lane * 4 + c]); }
+          else if (ng < 2) g[ng++] = c;
+        }
+      const unsigned single = __ballot_sync(full, nbad == 3), dbl = __ballot_sync(full, nbad == 2);
+      n1[f] = __popc(single); n2[f] = __popc(dbl);
+      const unsigned below = (1u << lane) - 1u;
+      int pos = -1;
+      uint32_t w = 0u;
+      if (nbad == 3) { pos = __popc(single & below); w = (uint32_t)lane | ((uint32_t)g[0] << 8) | (0xffu << 16); }
+      if (nbad == 2) { pos = n1[f] + __popc(dbl & below); w = (uint32_t)lane | ((uint32_t)g[0] << 8) | ((uint32_t)g[1] << 16); }
+      // descriptor i of the filter goes to lane i
+      for (int src = 0; src < 32; ++src) {
+        const int p = __shfl_sync(full, pos, src);
+        const uint32_t ww = __shfl_sync(full, w, src);
+        if (p == lane) desc[f] = ww;
+      }
+      // the bound of this filter on its own penalties (filter 1 mirrors filter 0, so this only guards foreign tables)
+      if (nbad < 2) mb = 1e300;
+      double s1 = 1e300, s2 = 1e300, s3 = 1e300;
+      for (int src = 0; src < 32; ++src) bp_push3(__shfl_sync(full, mb, src), s1, s2, s3);
+      const double bound = best_K == 1 ? s1 : best_K == 2 ? (s2 < 1e299 ? s1 + s2 : 0.0) : (s3 < 1e299 ? s1 + s2 + s3 : 0.0);
+      if (!(bound < 1e299 && bound > D[f])) sound = false;
+    }
+    const double cost_pairs = 32.0 * 1.55 * m;             // the pair tables: ~1.55 integer-pipe cycles per tap and window
+    use = sound && best_cost <= cost_ratio * cost_pairs ? 1 : 0;
+  }
+  rec[lane] = desc[0];
+  rec[32 + lane] = desc[1];
+  if (lane == 0) {
+    rec[64] = (uint32_t)best_K | ((uint32_t)use << 8) | ((uint32_t)nf << 16);
+    rec[65] = (uint32_t)n1[0] | ((uint32_t)n2[0] << 8) | ((uint32_t)n1[1] << 16) | ((uint32_t)n2[1] << 24);
+    rec[66] = __float_as_uint((float)best_rate);
+    rec[67] = __float_as_uint((float)best_cost);
+    for (int k = 68; k < MEPP_BP_WORDS; ++k) rec[k] = 0u;
+  }
+}
+
+// Splits the unit list of a scan call by class (stable, so the host's ordering by motif length survives):
+// out = [pair-table units (U rows)][bit-parallel units (U rows)], counts[0 / 1] = their numbers.  One warp.
+__global__ void bp_partition_kernel(const int32_t* __restrict__ units, int U, const uint32_t* __restrict__ bp,
+                                    int32_t* __restrict__ out, int32_t* __restrict__ counts) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x;
+  int n0 = 0, n1 = 0;
+  for (int u0 = 0; u0 < U; u0 += 32) {
+    const int u = u0 + lane;
+    int t = 0, t2 = -1;
+    bool use = false;
+    if (u < U) {
+      t = units ? units[2 * u] : u;
+      t2 = units ? units[2 * u + 1] : -1;
+      use = ((bp[(size_t)t * MEPP_BP_WORDS + 64] >> 8) & 1u) != 0u;
+    }
+    const unsigned m1 = __ballot_sync(full, u < U && use), m0 = __ballot_sync(full, u < U && !use);
+    const unsigned below = (1u << lane) - 1u;
+    if (u < U) {
+      int32_t* dst = use ? out + 2 * (U + n1 + __popc(m1 & below)) : out + 2 * (n0 + __popc(m0 & below));
+      dst[0] = t; dst[1] = t2;
+    }
+    n0 += __popc(m0); n1 += __popc(m1);
+  }
+  if (lane == 0) { counts[0] = n0; counts[1] = n1; }
 }
 
 // Restores the all-zero state of the A operand after its consumer ran: every match (task, seq, pos) of the
@@ -628,15 +897,16 @@ extern "C" int mepp_x_planes_reset(void* x_planes_dev, const void* hits_dev, int
   return 0;
 }
 
-extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
-                         int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
-                         const int32_t* mlen_dev, const int32_t* nfilt_dev, const uint32_t* qtab_dev,
-                         const uint32_t* qthr_dev, const int32_t* units_dev, int n_units, int max_motif_len,
-                         void* x_planes_dev, double* rowstats_dev, int32_t* count_dev,
-                         int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
-                         void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev,
-                         int32_t* row_nnz_dev, void* stream) {
-  using namespace mepp;
+namespace mepp {
+static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
+                     int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
+                     const int32_t* mlen_dev, const int32_t* nfilt_dev, const uint32_t* qtab_dev,
+                     const uint32_t* qthr_dev, const int32_t* units_dev, int n_units, int max_motif_len,
+                     void* x_planes_dev, double* rowstats_dev, int32_t* count_dev,
+                     int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
+                     void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev,
+                     int32_t* row_nnz_dev, const uint32_t* planes_T_dev, const uint32_t* bp_dev, int32_t* bp_scratch_dev,
+                     void* stream) {
   MEPP_REQUIRE(sym_T_dev && lut_dev && bias_dev && mlen_dev && nfilt_dev && qtab_dev && qthr_dev &&
                rowstats_dev && count_dev && density_dev, "scan: null pointer");
   MEPP_REQUIRE(x_planes_dev || entries_dev, "scan: neither the tiled operand nor the entry list was requested");
@@ -649,6 +919,8 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
   MEPP_REQUIRE((int64_t)T * L < (1LL << 31), "scan: T * L must be below 2^31");
   MEPP_REQUIRE(margin >= 0 && margin <= MEPP_MAX_MARGIN, "scan: margin must be in [0, 16]");
   MEPP_REQUIRE(hits_dev == nullptr || hit_count_dev != nullptr, "scan: hits need a hit counter");
+  const bool bitpar = planes_T_dev != nullptr;
+  MEPP_REQUIRE(!bitpar || (bp_dev && bp_scratch_dev), "scan_bitpar: the bit planes need the task records and the scratch");
   MEPP_REQUIRE(mepp_device_ok(), "scan: no sm_100 CUDA device (no CPU fallback)");
   cudaStream_t st = as_stream(stream);
   ScanArgs a;
@@ -668,16 +940,20 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
   a.hits = reinterpret_cast<HitRec*>(hits_dev); a.hits_cap = hits_cap; a.hit_count = hit_count_dev;
   a.entries = reinterpret_cast<XEntry*>(entries_dev); a.sub_cap = entry_cap / MEPP_ENTRY_LISTS;
   a.entry_count = entry_count_dev; a.row_nnz = row_nnz_dev;
+  a.planes_T = planes_T_dev; a.bp = bp_dev; a.unit_count = nullptr;
   const int nbuf = 32 + 2 * margin;
-  size_t smem = sizeof(float) * kScanWarps * (units_dev ? 2 : 1) * nbuf * kRowStride +
-                sizeof(uint32_t) * kScanWarps * a.qslots * 64 + sizeof(uint16_t) * kScanWarps * kQueue +
-                sizeof(uint32_t) * kScanWarps * 192 + sizeof(float2) * kScanWarps * a.qslots * 8 +
-                256 /* table alignment */;
-  MEPP_CUDA_CHECK(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto smem_bytes = [&](bool bp) {
+    return sizeof(float) * kScanWarps * ((units_dev || bitpar) ? 2 : 1) * nbuf * kRowStride +
+           sizeof(uint32_t) * kScanWarps * scan_table_words(a.qslots, bp) + sizeof(uint16_t) * kScanWarps * kQueue +
+           sizeof(uint32_t) * kScanWarps * (bp ? 256 : 192) + sizeof(float2) * kScanWarps * a.qslots * 8 +
+           256 /* table alignment */;
+  };
+  const size_t smem = smem_bytes(false);
+  MEPP_CUDA_CHECK(cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     static int carveout = [] { const char* e = getenv("MEPP_SCAN_CARVEOUT"); return e ? atoi(e) : -2; }();
     if (carveout >= -1)
-      MEPP_CUDA_CHECK(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+      MEPP_CUDA_CHECK(cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
   }
   MEPP_CUDA_CHECK(cudaMemsetAsync(rowstats_dev, 0, sizeof(double) * 3 * (size_t)T * L, st));
   MEPP_CUDA_CHECK(cudaMemsetAsync(count_dev, 0, sizeof(int32_t) * (size_t)T * L, st));
@@ -695,7 +971,69 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
   }
   dim3 grid((unsigned)a.KB, (unsigned)((a.U + kScanWarps - 1) / kScanWarps));
   MEPP_REQUIRE(grid.y <= 65535, "scan: too many tasks in one call");
-  scan_kernel<<<grid, kScanWarps * 32, smem, st>>>(a);
+  if (!bitpar) {
+    scan_kernel<false><<<grid, kScanWarps * 32, smem, st>>>(a);
+    MEPP_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
+  // units split by class on the device (the class depends on the thresholds, which may have been computed there);
+  // both kernels are launched over the whole grid and leave at once past their list's end
+  const int U = a.U;
+  int32_t* lists = bp_scratch_dev;            // [2][U][2]
+  int32_t* counts = bp_scratch_dev + 4 * U;   // [2]
+  bp_partition_kernel<<<1, 32, 0, st>>>(units_dev, U, bp_dev, lists, counts);
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  const size_t smem_bp = smem_bytes(true);
+  MEPP_CUDA_CHECK(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bp));
+  ScanArgs b = a;
+  b.units = lists + 2 * U; b.unit_count = counts + 1;
+  scan_kernel<true><<<grid, kScanWarps * 32, smem_bp, st>>>(b);
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  a.units = lists; a.unit_count = counts;
+  scan_kernel<false><<<grid, kScanWarps * 32, smem, st>>>(a);
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+}  // namespace mepp
+
+extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
+                         int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
+                         const int32_t* mlen_dev, const int32_t* nfilt_dev, const uint32_t* qtab_dev,
+                         const uint32_t* qthr_dev, const int32_t* units_dev, int n_units, int max_motif_len,
+                         void* x_planes_dev, double* rowstats_dev, int32_t* count_dev,
+                         int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
+                         void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev,
+                         int32_t* row_nnz_dev, void* stream) {
+  return mepp::scan_impl(sym_T_dev, zhat_dev, N, L, T, margin, lut_dev, bias_dev, mlen_dev, nfilt_dev, qtab_dev, qthr_dev,
+                         units_dev, n_units, max_motif_len, x_planes_dev, rowstats_dev, count_dev, density_dev, hits_dev,
+                         hits_cap, hit_count_dev, entries_dev, entry_cap, entry_count_dev, row_nnz_dev, nullptr, nullptr,
+                         nullptr, stream);
+}
+
+extern "C" int mepp_scan_bitpar(const uint32_t* sym_T_dev, const float* zhat_dev,
+                                int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
+                                const int32_t* mlen_dev, const int32_t* nfilt_dev, const uint32_t* qtab_dev,
+                                const uint32_t* qthr_dev, const int32_t* units_dev, int n_units, int max_motif_len,
+                                void* x_planes_dev, double* rowstats_dev, int32_t* count_dev,
+                                int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
+                                void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev,
+                                int32_t* row_nnz_dev, const uint32_t* planes_T_dev, const uint32_t* bp_dev,
+                                int32_t* bp_scratch_dev, void* stream) {
+  MEPP_REQUIRE(planes_T_dev && bp_dev && bp_scratch_dev, "scan_bitpar: null pointer");
+  return mepp::scan_impl(sym_T_dev, zhat_dev, N, L, T, margin, lut_dev, bias_dev, mlen_dev, nfilt_dev, qtab_dev, qthr_dev,
+                         units_dev, n_units, max_motif_len, x_planes_dev, rowstats_dev, count_dev, density_dev, hits_dev,
+                         hits_cap, hit_count_dev, entries_dev, entry_cap, entry_count_dev, row_nnz_dev, planes_T_dev,
+                         bp_dev, bp_scratch_dev, stream);
+}
+
+extern "C" int mepp_scan_bitpar_tables(const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev,
+                                       const int32_t* nfilt_dev, int T, double cost_ratio, uint32_t* bp_dev,
+                                       void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(lut_dev && bias_dev && mlen_dev && nfilt_dev && bp_dev && T > 0, "scan_bitpar_tables: bad arguments");
+  MEPP_REQUIRE(mepp_device_ok(), "scan_bitpar_tables: no sm_100 CUDA device (no CPU fallback)");
+  bp_tables_kernel<<<(unsigned)((T + 3) / 4), 128, 0, as_stream(stream)>>>(lut_dev, bias_dev, mlen_dev, nfilt_dev, T,
+                                                                           cost_ratio, bp_dev);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -141,6 +141,11 @@ class DeviceTables:
         d, a, b = self.dev, self.g0, self.g1
         return d['lut'][a:b], d['bias'][a:b], d['mlen'][a:b], d['nfilt'][a:b], d['qtab'][a:b], d['qthr'][a:b]
 
+    def bp_slice(self):
+        """Records of the bit-parallel scan stage (mepp_scan_bitpar_tables) or None."""
+        bp = self.dev.get('bp')
+        return None if bp is None else bp[self.g0:self.g1]
+
     def units(self):
         """(task scanned, twin or -1) rows like scan_units, from the pairing made when the tables were prepared."""
         a, b = self.g0, self.g1
@@ -184,6 +189,15 @@ class Engine:
         from .parallel import host_threads
         self.copy_threads = int(os.environ.get("MEPP_COPY_THREADS", str(max(1, min(4, host_threads())))))
         self.device_tables = os.environ.get("MEPP_DEVICE_TABLES", "1") != "0"   # threshold DP on the GPU
+        # the scan of a group (integer-issue bound, no memory traffic) runs on the compute stream while the profile /
+        # statistics / finalisation chain of the previous group (L2- and HBM-bound) runs on a high-priority stream
+        self.overlap = os.environ.get("MEPP_OVERLAP", "1") != "0"
+        self._post_stream = None
+        self._post_done = {}
+        # bit-parallel first stage of the scan for the units whose expected survivor rate allows it
+        # (mepp_scan_bitpar); a unit takes it when its modelled cost is below MEPP_BP_COST_RATIO x the pair tables'
+        self.bitpar = os.environ.get("MEPP_SCAN_BITPAR", "0") != "0"
+        self.bp_cost_ratio = float(os.environ.get("MEPP_BP_COST_RATIO", "1.0"))
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -203,6 +217,8 @@ class Engine:
         need = int(np.prod(shape))
         cur = self._bufs.get(name)
         if cur is None or cur.numel() < need or cur.dtype != dtype:
+            if cur is not None:
+                torch.cuda.synchronize(self.device)     # (rare: kernels of the side streams may still read the old one)
             cur = (torch.zeros if zero else torch.empty)(need, dtype=dtype, device=self.device)
             self._bufs[name] = cur
         return cur[:need].view(shape)
@@ -225,6 +241,12 @@ class Engine:
             self.sym_T = torch.empty((W3, self.n_pad), dtype=torch.int32, device=self.device)
             self.gc = torch.empty(self.n_pad, dtype=torch.float32, device=self.device)
             _lib.check(_lib.lib.mepp_pack_dna(_ptr(ascii_d), N, L, _ptr(self.sym_T), _ptr(self.gc), st), "pack_dna")
+            self.planes_T = None
+            if self.bitpar:
+                WB = int(_lib.lib.mepp_plane_words(L))
+                self.planes_T = torch.empty((WB, 4, self.n_pad), dtype=torch.int32, device=self.device)
+                _lib.check(_lib.lib.mepp_pack_planes(_ptr(self.sym_T), N, L, _ptr(self.planes_T), st), "pack_planes")
+                self.launches += 1
             self.launches += 2
             self.use_gc = bool(use_gc)
             if self.use_gc:
@@ -355,6 +377,16 @@ class Engine:
             self.launches += 1
         return self._y_rows
 
+    def _bp_tables(self, lut_d, bias_d, mlen_d, nfilt_d, T):
+        """Task records of the bit-parallel scan stage (letter sets, K, class) on the current stream, or None."""
+        if not self.bitpar:
+            return None
+        bp = self.torch.empty((T, _lib.BP_WORDS), dtype=self.torch.int32, device=self.device)
+        _lib.check(_lib.lib.mepp_scan_bitpar_tables(_ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), T,
+                                                    self.bp_cost_ratio, _ptr(bp), self._stream()), "scan_bitpar_tables")
+        self.launches += 1
+        return bp
+
     def device_tables_for(self, tasks, **table_kw):
         """Scan tables of a whole task list with the thresholds computed on the device: one host call for
         everything that does not need the threshold, one launch of the threshold DP over the distinct
@@ -397,6 +429,9 @@ class Engine:
             _lib.check(_lib.lib.mepp_task_thresholds(_ptr(thr_unit), _ptr(uot_d), _ptr(qpar_d), _ptr(dev['mlen']),
                                                      _ptr(dev['nfilt']), T, _ptr(dev['bias']), _ptr(dev['qthr']),
                                                      _ptr(dev['thr']), st), "task_thresholds")
+            bp = self._bp_tables(dev['lut'], dev['bias'], dev['mlen'], dev['nfilt'], T)
+            if bp is not None:
+                dev['bp'] = bp
             ready = torch.cuda.Event()
             ready.record(self._aux_stream)
         compute.wait_event(ready)
@@ -429,6 +464,9 @@ class Engine:
                    qtab=self._to_dev(np.stack([tb['qtab'] for tb in tables]).view(np.int32)),
                    qthr=self._to_dev(np.stack([tb['qthr'] for tb in tables]).view(np.int32)),
                    thr=self._to_dev(host['thr']))
+        bp = self._bp_tables(dev['lut'], dev['bias'], dev['mlen'], dev['nfilt'], T)
+        if bp is not None:
+            dev['bp'] = bp
         return DeviceTables(dev, host, 0, T)
 
     def choose_path(self, tables, margin):
@@ -515,6 +553,7 @@ class Engine:
         self.last_groups = len(groups)
         self._units_run = 0
         self.last_paths = []
+        self._post_done.clear()     # (every chain of the previous call was waited for when its group was collected)
         store = stats_host.alloc_positions(T_all, L, self.P)
         density_all = np.empty((T_all, N), dtype=np.int32)
         outs = []
@@ -623,6 +662,7 @@ class Engine:
             lut_d, bias_d, mlen_d, nfilt_d, qtab_d, qthr_d = tables.device_slices()
             mlen = tables.mlen
             units = tables.units() if self.share_scans else None
+            bp_d = tables.bp_slice()
         else:
             lut = np.stack([tb['lut'] for tb in tables]).astype(np.float32)
             bias = np.array([tb['bias'] for tb in tables], dtype=np.float32)
@@ -633,6 +673,7 @@ class Engine:
             lut_d, bias_d, mlen_d, nfilt_d, qtab_d, qthr_d = (self._to_dev(lut), self._to_dev(bias), self._to_dev(mlen),
                                                               self._to_dev(nfilt), self._to_dev(qtab), self._to_dev(qthr))
             units = scan_units(tables) if self.share_scans else None
+            bp_d = self._bp_tables(lut_d, bias_d, mlen_d, nfilt_d, T)
         if units is not None and len(units) > 2:
             # longest motifs first and similar lengths side by side: the two warps of a CTA then finish together and the
             # last wave of CTAs is the cheapest one
@@ -649,119 +690,155 @@ class Engine:
         else:
             dens = max(SPARSE_ENTRY_DENSITY, 2.0 * getattr(self, '_density_est', 0.0))
             entry_cap = -(-max(MIN_ENTRY_CAP, int(T * N * L * dens)) // _lib.ENTRY_LISTS) * _lib.ENTRY_LISTS
-            entries = self._buf('entries', entry_cap * 16, torch.uint8)
+            entries = self._buf(f'entries{slot}', entry_cap * 16, torch.uint8)
             entry_count = self._buf(f'entry_count{slot}', (16 * _lib.ENTRY_LISTS,), torch.int64)
-            row_nnz = self._buf('row_nnz', (m_rows + 1,), torch.int32)
-        rowstats = self._buf('rowstats', (m_rows, 3), torch.float64)
-        count = self._buf('count', (T, L), torch.int32)
+            row_nnz = self._buf(f'row_nnz{slot}', (m_rows + 1,), torch.int32)
+        rowstats = self._buf(f'rowstats{slot}', (m_rows, 3), torch.float64)
+        count = self._buf(f'count{slot}', (T, L), torch.int32)
         # buffers that travel to the host are per staging slot: their copies run on a side stream while the next
         # group's kernels already write the other slot
         density = self._buf(f'density{slot}', (T, self.n_pad), torch.int32)
         hit_count = self._buf(f'hit_count{slot}', (1,), torch.int64)
         # the match list is always kept: it is also what restores the all-zero state of x_planes after the GEMM
         cap = int(hits_cap) if hits_cap else max(1 << 20, int(T * N * L * 2e-3))
-        hits_d = self._buf('hits', cap * 16, torch.uint8)
+        hits_d = self._buf(f'hits{slot}', cap * 16, torch.uint8)
         ev = self._mark(None, None)
-        _lib.check(_lib.lib.mepp_scan(_ptr(self.sym_T), _ptr(self.zhat), N, L, T, int(margin),
-                                      _ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), _ptr(qtab_d), _ptr(qthr_d),
-                                      _ptr(units_d), n_units, int(mlen.max()), _ptr(x_planes), _ptr(rowstats), _ptr(count),
-                                      _ptr(density), _ptr(hits_d), cap, _ptr(hit_count), _ptr(entries), entry_cap,
-                                      _ptr(entry_count), _ptr(row_nnz), st), "scan")
-        self.launches += 1
+        scan_args = (_ptr(self.sym_T), _ptr(self.zhat), N, L, T, int(margin),
+                     _ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), _ptr(qtab_d), _ptr(qthr_d),
+                     _ptr(units_d), n_units, int(mlen.max()), _ptr(x_planes), _ptr(rowstats), _ptr(count),
+                     _ptr(density), _ptr(hits_d), cap, _ptr(hit_count), _ptr(entries), entry_cap,
+                     _ptr(entry_count), _ptr(row_nnz))
+        if bp_d is not None and self.planes_T is not None:
+            # units split by class on the device; the bit-parallel units and the pair-table units run as two launches
+            bp_scratch = self._buf(f'bp_scratch{slot}', (4 * self.last_units + 2,), torch.int32)
+            _lib.check(_lib.lib.mepp_scan_bitpar(*scan_args, _ptr(self.planes_T), _ptr(bp_d), _ptr(bp_scratch), st),
+                       "scan_bitpar")
+            self.launches += 3
+            self.last_bp = (bp_d, bp_scratch, self.last_units)
+        else:
+            _lib.check(_lib.lib.mepp_scan(*scan_args, st), "scan")
+            self.launches += 1
         if path == 'tensor':
             # the scan stored only the non-zero pieces; the operand goes back to all-zero before its next use
             self._x_pending = dict(x=x_planes, hits=hits_d, cap=cap, hit_count=hit_count, N=N, L=L, T=T,
                                    margin=int(margin))
         ev = self._mark(ev, 'scan')
-        # tcgen05 GEMM with the correlation fused into its epilogue: r (m_rows, ldS) float32, S never reaches HBM
-        r = self._buf('r', (m_rows, self.ldS), torch.float32)
-        if path == 'sparse':
-            work = self._buf('sparse_work', int(_lib.lib.mepp_profile_sparse_work_bytes(m_rows, entry_cap)), torch.uint8)
-            _lib.check(_lib.lib.mepp_profile_sparse(_ptr(entries), _ptr(entry_count), entry_cap, _ptr(row_nnz),
-                                                    _ptr(self._yrows()), _ptr(rowstats), _ptr(self._colconst()), _ptr(r),
-                                                    self.ldS, m_rows, C_, _ptr(work), st), "profile_sparse")
-            self.launches += 3
-            nnz_d = work[m_rows * 4:m_rows * 4 + 4].view(torch.int32)     # offsets[m_rows] = non-zeros of X
-            ev = self._mark(ev, 'gemm')
-        elif self.fuse_correlation:
-            _lib.check(_lib.lib.mepp_profile_corr_gemm(_ptr(x_planes), _ptr(self.y_planes), _ptr(rowstats),
-                                                       _ptr(self._colconst()), _ptr(r), m_rows, C_, self.n_pad, st),
-                       "profile_corr_gemm")
-            self.launches += 2
-            ev = self._mark(ev, 'gemm')
-        else:
-            S = self._buf('S', (m_rows, self.ldS), torch.float32)
-            _lib.check(_lib.lib.mepp_profile_gemm(_ptr(x_planes), _ptr(self.y_planes), _ptr(S), m_rows, C_, self.n_pad,
-                                                  st), "profile_gemm")
-            ev = self._mark(ev, 'gemm')
-            zsum = self._zsum()
-            _lib.check(_lib.lib.mepp_correlation(_ptr(S), self.ldS, _ptr(rowstats), _ptr(self.col_syz), _ptr(self.ysum),
-                                                 zsum.ctypes.data_as(C.POINTER(C.c_double)), N, m_rows, C_,
-                                                 1 if self.use_gc else 0, _ptr(r), self.ldS, st), "correlation")
-            self.launches += 3 + (m_rows + 65534) // 65535 - 1
-            ev = self._mark(ev, 'correlation')
-        dev = {}
-        if P > 0:
-            q = stats_host.percentile_q(ci)
-            k_lo, _ = stats_host.virtual_index(P, q[0])
-            k_hi, _ = stats_host.virtual_index(P, q[1])
-            ks_lo, _ = stats_host.virtual_index(L * P, q[0])
-            ks_hi, _ = stats_host.virtual_index(L * P, q[1])
-            dev['full_os'] = self._buf('full_os', (T, L, 4), torch.float32)
-            dev['full_cnt'] = self._buf('full_cnt', (T, L), torch.int32)
-            dev['semi_os'] = self._buf('semi_os', (T, 4), torch.float32)
-            dev['semi_cnt'] = self._buf('semi_cnt', (T, L), torch.int64)
-            dev['integral'] = self._buf('integral', (T, C_), torch.float64)
-            work = self._buf('stats_work', int(_lib.lib.mepp_perm_stats_work_bytes(T, L, C_)), torch.uint8)
-            _lib.check(_lib.lib.mepp_perm_stats(_ptr(r), self.ldS, T, L, C_, k_lo, k_hi, ks_lo, ks_hi, _ptr(dev['full_os']),
-                                                _ptr(dev['full_cnt']), _ptr(dev['semi_os']), _ptr(dev['semi_cnt']),
-                                                _ptr(dev['integral']), _ptr(work), st), "perm_stats")
-            self.launches += 9
-            ev = self._mark(ev, 'perm_stats')
-        # K4: every output column of the group on the device; the host only copies the block into the result table
-        out_d = self._buf(f'finalized{slot}', int(_lib.lib.mepp_finalize_out_bytes(T, L)), torch.uint8)
-        if P > 0:
-            _, g_lo = stats_host.virtual_index(P, q[0])
-            _, g_hi = stats_host.virtual_index(P, q[1])
-            _, gs_lo = stats_host.virtual_index(L * P, q[0])
-            _, gs_hi = stats_host.virtual_index(L * P, q[1])
-            fin = (dev['full_os'], dev['full_cnt'], dev['semi_os'], dev['semi_cnt'], dev['integral'])
-        else:
-            k_lo = k_hi = 0
-            g_lo = g_hi = gs_lo = gs_hi = 0.0
-            fin = (None,) * 5
-        _lib.check(_lib.lib.mepp_finalize_positions(_ptr(r), self.ldS, T, L, C_, *[_ptr(x) for x in fin], _ptr(count), N,
-                                                    int(margin), k_lo, k_hi, g_lo, g_hi, gs_lo, gs_hi,
-                                                    float(stats_host.z_margin_f32(N, ci)), _ptr(out_d), st),
-                   "finalize_positions")
-        self.launches += 2 if P > 0 else 1
-        ev = self._mark(ev, 'finalize')
-        dev = {'finalized': out_d}
-        dev['density'] = density
-        dev['hit_count'] = hit_count
-        if path == 'sparse':
-            dev['entry_count'] = entry_count
-            dev['nnz'] = nnz_d
-        if return_r:
-            dev['r'] = r.view(T, L, self.ldS)[:, :, :C_].contiguous()
-        host = {}
-        # device -> host on a side stream: the next group's kernels do not wait for the copies
-        compute = torch.cuda.current_stream(self.device)
-        if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(device=self.device)
-        ready = torch.cuda.Event()
-        ready.record(compute)
-        self._copy_stream.wait_event(ready)
-        with torch.cuda.stream(self._copy_stream):
-            for k, t in dev.items():
-                h = self._pinned(k, slot, t.shape, t.dtype)
-                h.copy_(t, non_blocking=True)
-                host[k] = h
-            done = torch.cuda.Event()
-            done.record(self._copy_stream)
-        return dict(host=host, done=done, T=T, hits_d=hits_d, cap=cap, return_hits=return_hits, path=path,
-                    entry_cap=entry_cap, slot=slot, tables=tables, return_r=return_r, hits_cap=hits_cap,
-                    dev=dev)    # (keeps the copied tensors alive until the side stream is done with them)
+        # Everything after the scan runs as one chain.  With overlap it goes to a high-priority stream, so that the
+        # next group's scan (enqueued on the compute stream as soon as this call returns) shares the SMs with it: the
+        # scan is bound by integer issue and moves no memory, the chain is bound by L2 / HBM traffic.
+        overlap = (self.overlap and path == 'sparse' and self.fuse_correlation and not return_hits and not return_r)
+        compute_stream = torch.cuda.current_stream(self.device)
+        if overlap:
+            self._yrows()
+            self._colconst()          # (built once, on the compute stream, before the chain is handed over)
+            if self._post_stream is None:
+                self._post_stream = torch.cuda.Stream(device=self.device, priority=-1)
+            scanned = torch.cuda.Event()
+            scanned.record(compute_stream)
+        elif self._post_done:
+            torch.cuda.synchronize(self.device)   # a serial group after overlapped ones shares their scratch buffers
+            self._post_done.clear()
+
+        def chain():
+            nonlocal ev
+            st = self._stream()
+            # tcgen05 GEMM with the correlation fused into its epilogue: r (m_rows, ldS) float32, S never reaches HBM
+            r = self._buf('r', (m_rows, self.ldS), torch.float32)
+            if path == 'sparse':
+                work = self._buf('sparse_work', int(_lib.lib.mepp_profile_sparse_work_bytes(m_rows, entry_cap)), torch.uint8)
+                _lib.check(_lib.lib.mepp_profile_sparse(_ptr(entries), _ptr(entry_count), entry_cap, _ptr(row_nnz),
+                                                        _ptr(self._yrows()), _ptr(rowstats), _ptr(self._colconst()), _ptr(r),
+                                                        self.ldS, m_rows, C_, _ptr(work), st), "profile_sparse")
+                self.launches += 3
+                nnz_d = work[m_rows * 4:m_rows * 4 + 4].view(torch.int32)     # offsets[m_rows] = non-zeros of X
+                ev = self._mark(ev, 'gemm')
+            elif self.fuse_correlation:
+                _lib.check(_lib.lib.mepp_profile_corr_gemm(_ptr(x_planes), _ptr(self.y_planes), _ptr(rowstats),
+                                                           _ptr(self._colconst()), _ptr(r), m_rows, C_, self.n_pad, st),
+                           "profile_corr_gemm")
+                self.launches += 2
+                ev = self._mark(ev, 'gemm')
+            else:
+                S = self._buf('S', (m_rows, self.ldS), torch.float32)
+                _lib.check(_lib.lib.mepp_profile_gemm(_ptr(x_planes), _ptr(self.y_planes), _ptr(S), m_rows, C_, self.n_pad,
+                                                      st), "profile_gemm")
+                ev = self._mark(ev, 'gemm')
+                zsum = self._zsum()
+                _lib.check(_lib.lib.mepp_correlation(_ptr(S), self.ldS, _ptr(rowstats), _ptr(self.col_syz), _ptr(self.ysum),
+                                                     zsum.ctypes.data_as(C.POINTER(C.c_double)), N, m_rows, C_,
+                                                     1 if self.use_gc else 0, _ptr(r), self.ldS, st), "correlation")
+                self.launches += 3 + (m_rows + 65534) // 65535 - 1
+                ev = self._mark(ev, 'correlation')
+            dev = {}
+            if P > 0:
+                q = stats_host.percentile_q(ci)
+                k_lo, _ = stats_host.virtual_index(P, q[0])
+                k_hi, _ = stats_host.virtual_index(P, q[1])
+                ks_lo, _ = stats_host.virtual_index(L * P, q[0])
+                ks_hi, _ = stats_host.virtual_index(L * P, q[1])
+                dev['full_os'] = self._buf('full_os', (T, L, 4), torch.float32)
+                dev['full_cnt'] = self._buf('full_cnt', (T, L), torch.int32)
+                dev['semi_os'] = self._buf('semi_os', (T, 4), torch.float32)
+                dev['semi_cnt'] = self._buf('semi_cnt', (T, L), torch.int64)
+                dev['integral'] = self._buf('integral', (T, C_), torch.float64)
+                work = self._buf('stats_work', int(_lib.lib.mepp_perm_stats_work_bytes(T, L, C_)), torch.uint8)
+                _lib.check(_lib.lib.mepp_perm_stats(_ptr(r), self.ldS, T, L, C_, k_lo, k_hi, ks_lo, ks_hi, _ptr(dev['full_os']),
+                                                    _ptr(dev['full_cnt']), _ptr(dev['semi_os']), _ptr(dev['semi_cnt']),
+                                                    _ptr(dev['integral']), _ptr(work), st), "perm_stats")
+                self.launches += 9
+                ev = self._mark(ev, 'perm_stats')
+            # K4: every output column of the group on the device; the host only copies the block into the result table
+            out_d = self._buf(f'finalized{slot}', int(_lib.lib.mepp_finalize_out_bytes(T, L)), torch.uint8)
+            if P > 0:
+                _, g_lo = stats_host.virtual_index(P, q[0])
+                _, g_hi = stats_host.virtual_index(P, q[1])
+                _, gs_lo = stats_host.virtual_index(L * P, q[0])
+                _, gs_hi = stats_host.virtual_index(L * P, q[1])
+                fin = (dev['full_os'], dev['full_cnt'], dev['semi_os'], dev['semi_cnt'], dev['integral'])
+            else:
+                k_lo = k_hi = 0
+                g_lo = g_hi = gs_lo = gs_hi = 0.0
+                fin = (None,) * 5
+            _lib.check(_lib.lib.mepp_finalize_positions(_ptr(r), self.ldS, T, L, C_, *[_ptr(x) for x in fin], _ptr(count), N,
+                                                        int(margin), k_lo, k_hi, g_lo, g_hi, gs_lo, gs_hi,
+                                                        float(stats_host.z_margin_f32(N, ci)), _ptr(out_d), st),
+                       "finalize_positions")
+            self.launches += 2 if P > 0 else 1
+            ev = self._mark(ev, 'finalize')
+            dev = {'finalized': out_d}
+            dev['density'] = density
+            dev['hit_count'] = hit_count
+            if path == 'sparse':
+                dev['entry_count'] = entry_count
+                dev['nnz'] = nnz_d
+            if return_r:
+                dev['r'] = r.view(T, L, self.ldS)[:, :, :C_].contiguous()
+            host = {}
+            # device -> host on a side stream: the next group's kernels do not wait for the copies
+            compute = torch.cuda.current_stream(self.device)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            self._copy_stream.wait_event(ready)
+            with torch.cuda.stream(self._copy_stream):
+                for k, t in dev.items():
+                    h = self._pinned(k, slot, t.shape, t.dtype)
+                    h.copy_(t, non_blocking=True)
+                    host[k] = h
+                done = torch.cuda.Event()
+                done.record(self._copy_stream)
+            return dict(host=host, done=done, T=T, hits_d=hits_d, cap=cap, return_hits=return_hits, path=path,
+                        entry_cap=entry_cap, slot=slot, tables=tables, return_r=return_r, hits_cap=hits_cap,
+                        dev=dev, chain_done=ready)    # (keeps the copied tensors alive until the side stream is done with them)
+
+        if not overlap:
+            return chain()
+        with torch.cuda.stream(self._post_stream):
+            self._post_stream.wait_event(scanned)
+            out = chain()
+            self._post_done[slot] = out['chain_done']
+        return out
 
     def _collect_group(self, pend, margin, ci, store, density_all):
         """Wait for one group's D2H copies and finalise its statistics on the host, straight into the

@@ -572,3 +572,65 @@ def test_device_statistics_equal_the_reference_golden_vectors(name):
             assert np.allclose(a, b, rtol=3e-7), k                    # float32 trapezoid sums: summation order
         else:
             assert np.array_equal(a, b), k
+
+
+def test_bit_planes_match_the_codes(cfg1):
+    """mepp_pack_planes: "a letter other than c" planes of the staged sequences (N, positions past L and padding
+    sequences are zero in every plane)."""
+    eng = _engine()
+    eng.bitpar = True
+    eng.stage(cfg1["ascii"], cfg1["scores"], cfg1["perm_idx"])
+    N, L = cfg1["N"], cfg1["L"]
+    codes = staging.ascii_to_codes(cfg1["ascii"])
+    pl = eng.planes_T.cpu().numpy().view(np.uint32)               # (WB, 4, n_pad)
+    WB = pl.shape[0]
+    assert (pl[0] == 0).all() and (pl[:, :, N:] == 0).all(), (N, pl.shape)
+    bits = ((pl[1:, :, :N, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8)   # (WB-1, 4, N, 32)
+    bits = bits.transpose(1, 2, 0, 3).reshape(4, N, (WB - 1) * 32)
+    for c in range(4):
+        want = np.zeros((N, (WB - 1) * 32), dtype=np.uint8)
+        want[:, :L] = (codes != c) & (codes < 4)
+        assert np.array_equal(bits[c], want), c
+
+
+@pytest.mark.parametrize("cut", [0.0, 1e9])
+@pytest.mark.parametrize("orientations", [('+', '+/-'), ('-',), ('+/-',)])
+def test_scan_first_stages_agree_with_the_oracle(cut, orientations):
+    """Both first stages of the scan -- integer pair tables (cost ratio 0: only never-matching units take the
+    bit-parallel kernel) and bit-parallel bad-letter counters (huge ratio: every unit with a sound (d0, K)) -- feed the
+    same exact evaluation: matches bit-identical to the oracle; motif lengths 1..32, N-rich ragged sequences,
+    the shipped ohler motifs, a never-matching uniform motif, margins 0 and 7."""
+    from mepp_b200 import synth
+    ascii_u8, scores = synth.synth_sequences(203, 171, seed=41, n_rate=0.03, lower_rate=0.01)
+    ascii_u8[5, :] = ord('N')
+    ascii_u8[6, 3:] = ord('A')
+    perm = synth.synth_permutations(203, 9, seed=41)
+    rng = np.random.default_rng(12)
+    motifs = [rng.dirichlet(np.full(4, a), size=m).T for m, a in ((1, 0.3), (2, 0.3), (5, 0.2), (8, 0.3), (12, 0.5),
+                                                                   (17, 0.3), (25, 1.0), (32, 0.3))]
+    motifs += list(synth.load_motif_library("ohler").values())[:4] + [np.full((4, 7), 0.25)]
+    cons = np.full((4, 9), 1e-3); cons[[0, 0, 0, 0, 0, 0, 0, 0, 0], np.arange(9)] = 1.0      # poly-A: row 6 matches
+    motifs.append(cons / cons.sum(axis=0))
+    tasks = [(m, o) for m in motifs for o in orientations]
+    codes = staging.ascii_to_codes(ascii_u8)
+    for margin in (0, 7):
+        eng = _engine()
+        eng.bitpar = True
+        eng.bp_cost_ratio = cut
+        eng.stage(ascii_u8, scores, perm)
+        for use_device_tables in (True, False):
+            eng.device_tables = use_device_tables
+            got = eng.profile(tasks, margin=margin, return_hits=True)
+            bp, _scratch, U = eng.last_bp
+            use = ((bp.cpu().numpy().view(np.uint32)[:, 64] >> 8) & 1).astype(bool)
+            if cut == 0.0:
+                assert use.sum() <= 5 * len(orientations)           # only units whose threshold is out of reach
+            else:
+                assert use.sum() >= len(tasks) // 2
+            n_hits = 0
+            for t, (pwm, o) in enumerate(tasks):
+                Wf, Wr, thr = profile.motif_weights(pwm, o)
+                X0 = profile.scan(codes, Wf, Wr, thr)
+                n_hits += int((X0 > 0).sum())
+                assert np.array_equal(got.motif_score_matrix(t, 171).view(np.uint32), X0.view(np.uint32)), (t, o, margin)
+            assert n_hits > 15
