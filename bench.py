@@ -236,7 +236,6 @@ def main():
     dev_tables = eng.upload_tables(tables)               # device-resident: sequences, scores, permutations and tables
     eng.profile(my_tasks, margin=margin, tables=dev_tables)
     sync_all()
-    eng.timing = {}
     import ctypes as C
     from mepp_b200 import _lib
     _lib.check(_lib.lib.mepp_gemm_counters(None, 1), "gemm_counters")
@@ -254,8 +253,20 @@ def main():
     t1 = time.perf_counter()
     wall_value = t1 - t0
     launches = eng.launches - launches0
+    # per-kernel CUDA-event times: a serial pass (no overlap of the scan with the previous group's chain, so that
+    # every stage is timed alone on the launching stream) over the same inputs, right after the timed region
+    kernel_steps = max(1, min(args.steps, 5))
+    overlap_was = eng.overlap
+    eng.overlap = False
+    eng.profile(my_tasks, margin=margin, tables=dev_tables)
+    sync_all()
+    eng.timing = {}
+    for _ in range(kernel_steps):
+        eng.profile(my_tasks, margin=margin, tables=dev_tables)
+    sync_all()
     stage_ms = eng.collect_timing()
     eng.timing = None
+    eng.overlap = overlap_was
     steps2 = (C.c_ulonglong * 2)()
     _lib.check(_lib.lib.mepp_gemm_counters(steps2, 0), "gemm_counters")
     issued_frac = (steps2[0] / steps2[1]) if steps2[1] else 1.0
@@ -307,8 +318,8 @@ def main():
     C_ = 1 + P
     st = eng.last_stats
     sparse = all(p_ == "sparse" for p_ in st["paths"])
-    steps = args.steps
-    per = lambda k: stage_ms[k] * 1e-3 / steps             # seconds per step
+    steps = kernel_steps
+    per = lambda k: stage_ms[k] * 1e-3 / steps             # seconds per step (serial pass)
     kernels = {}
     l2_cap_gbs = 6300.0 * clocks_mhz_hint(peaks) / 1e3     # LTS throughput cap, B300_MICROARCH.md: ~6300 B/clk full chip
     if stage_ms.get("scan"):
@@ -396,7 +407,9 @@ def main():
                 timing=dict(how="CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks",
                             host_clock_ms_per_step=1e3 * wall_value / args.steps,
                             overlap="scan of group g+1 on the compute stream, profile / statistics / finalisation of "
-                                    "group g on a high-priority stream" if eng.overlap else "none"),
+                                    "group g on a high-priority stream" if eng.overlap else "none",
+                            kernels="per-kernel times: CUDA events on the launching stream in a serial pass of %d steps "
+                                    "(overlap off) right after the timed region" % kernel_steps),
                 gpu_launches=int(launches), roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline, clocks=clocks)
     print(json.dumps(line), flush=True)
     if world > 1:

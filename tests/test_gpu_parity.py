@@ -634,3 +634,58 @@ def test_scan_first_stages_agree_with_the_oracle(cut, orientations):
                 n_hits += int((X0 > 0).sum())
                 assert np.array_equal(got.motif_score_matrix(t, 171).view(np.uint32), X0.view(np.uint32)), (t, o, margin)
             assert n_hits > 15
+
+
+def test_full_size_config2_properties():
+    """BASELINE.json configs[1] at full size (20 000 x 1 kb, 162 HOMER-clustered motifs x {+, +/-}, 1000 permutations,
+    margin 2) through size-independent properties: (1) checksum of checksums -- per-position counts, per-sequence
+    densities and the match counter of every task add up to the same number; (2) the matches of a sample of sequences
+    (a sequence's matches do not depend on the other sequences) are bit-identical to the oracle's scan of that sample;
+    (3) a '+/-' task matches wherever its '+' twin does, with a score at least as high; (4) the overlapped schedule,
+    the serial schedule and the bit-parallel first stage give identical outputs; (5) |r| <= 1 and the permutation
+    p-values are multiples of 1 / P inside [0, 1]."""
+    from mepp_b200 import synth
+    cfg = synth.make_config("cfg2")
+    N, L, P = cfg["N"], cfg["L"], cfg["P"]
+    tasks = [(pwm, o) for _, pwm, o in cfg["tasks"]]
+    eng = _engine().stage(cfg["ascii"], cfg["scores"], cfg["perm_idx"])
+    assert eng.overlap
+    got = eng.profile(tasks, margin=cfg["margin"])
+    count = np.asarray(got.positions["count"])
+    assert np.array_equal(count.sum(axis=1), got.density.sum(axis=1))
+    assert int(got.hit_counts.sum()) == int(count.sum()) > 100 * len(tasks)      # (match counters are per task group)
+    r0 = np.asarray(got.positions["positional_r"])
+    assert np.isfinite(r0).all() and (np.abs(r0) <= 1.0 + 1e-6).all()
+    for col in ("permutation_full_positional_r_pval", "permutation_semi_positional_r_pval", "permutation_integral_r_pval"):
+        p = np.asarray(got.positions[col])
+        assert (p >= 0).all() and (p <= 1).all()
+    pf = np.asarray(got.positions["permutation_full_positional_r_pval"]) * P
+    assert np.abs(pf - np.round(pf)).max() < 1e-6
+    # (4) schedules and first stages
+    eng.overlap = False
+    serial = eng.profile(tasks, margin=cfg["margin"])
+    for k in got.positions:
+        assert np.array_equal(np.asarray(got.positions[k]), np.asarray(serial.positions[k]), equal_nan=True), k
+    assert np.array_equal(got.density, serial.density)
+    eng2 = _engine()
+    eng2.bitpar = True
+    eng2.stage(cfg["ascii"], cfg["scores"], cfg["perm_idx"])
+    bitpar = eng2.profile(tasks, margin=cfg["margin"])
+    assert np.array_equal(got.density, bitpar.density)
+    assert np.array_equal(count, np.asarray(bitpar.positions["count"]))
+    assert np.array_equal(r0, np.asarray(bitpar.positions["positional_r"]))
+    # (2) a sample of sequences against the oracle, a sample of tasks (every 23rd motif, both orientations)
+    sample = np.r_[0:40, N // 2:N // 2 + 40, N - 40:N]
+    pick = [t for t in range(len(tasks)) if (t // 2) % 23 == 0]
+    sub = eng.profile([tasks[t] for t in pick], margin=cfg["margin"], return_hits=True)
+    codes = staging.ascii_to_codes(cfg["ascii"][sample])
+    for j, t in enumerate(pick):
+        Wf, Wr, thr = profile.motif_weights(*tasks[t])
+        X0 = sub.motif_score_matrix(j, L)
+        assert np.array_equal(X0[sample].view(np.uint32), profile.scan(codes, Wf, Wr, thr).view(np.uint32)), t
+        assert np.array_equal((X0 > 0).sum(axis=1), got.density[t])
+    # (3) '+' (even rows) against '+/-' (odd rows) of the same motif
+    for j in range(0, len(pick) - 1, 2):
+        assert tasks[pick[j]][1] == '+' and tasks[pick[j + 1]][1] == '+/-'
+        Xp, Xd = sub.motif_score_matrix(j, L), sub.motif_score_matrix(j + 1, L)
+        assert (Xd >= Xp).all()
