@@ -402,18 +402,12 @@ __device__ __forceinline__ void bp_count(const uint4* __restrict__ desc, int n1,
     c0 = (c0 ^ bad) | (c1 & c0); c1 = t;
   }
 }
-// Survivor mask of the 32 windows starting at bit `g` of the padded plane stream (plane word 0 is zero padding).
+// Survivor mask of the 32 windows starting at base 32 * step: lo / hi = plane words of bases [32 step, 32 step + 64).
 // s_words: this warp's staging area [4 planes][32 lanes] uint2 (lo, hi): each lane only touches its own slots.
-__device__ __forceinline__ uint32_t bp_survivors(const uint32_t* __restrict__ pl, int64_t n_pad, int g, const BpUnit& u,
+__device__ __forceinline__ uint32_t bp_survivors(const uint32_t (&lo)[4], const uint32_t (&hi)[4], const BpUnit& u,
                                                  const uint4* __restrict__ s_desc, uint2* __restrict__ s_words, int lane) {
-  if (u.K == 0) return 0u;
-  const int w0 = g >> 5, sh = g & 31;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const uint32_t* p = pl + ((int64_t)w0 * 4 + c) * n_pad;
-    const uint32_t a = __ldg(p), b = __ldg(p + 4 * n_pad), d = __ldg(p + 8 * n_pad);
-    s_words[c * 32 + lane] = make_uint2(__funnelshift_r(a, b, sh), __funnelshift_r(b, d, sh));
-  }
+  for (int c = 0; c < 4; ++c) s_words[c * 32 + lane] = make_uint2(lo[c], hi[c]);
   const uint8_t* my_words = reinterpret_cast<const uint8_t*>(s_words + lane);
   uint32_t a0 = 0u, a1 = 0u, b0 = 0u, b1 = 0u;   // counters of filter 0 (a) and filter 1 (b), bit-sliced
   bp_count(s_desc, u.n1[0], u.n2[0], my_words, a0, a1);
@@ -422,6 +416,35 @@ __device__ __forceinline__ uint32_t bp_survivors(const uint32_t* __restrict__ pl
   bp_count(s_desc + 32, u.n1[1], u.n2[1], my_words, b0, b1);
   const uint32_t rej1 = u.K == 1 ? (b0 | b1) : u.K == 2 ? b1 : (b0 & b1);
   return ~(rej0 & rej1);
+}
+
+// Second stage for the survivors of the bit-parallel counters: the conservative integer sums of the pair tables
+// (host.cu: build_filter_table -- the same tables, bounds and "no false negatives" argument as the pair-table kernel),
+// one queued window per lane, the tables read from global memory (L1).  Windows that cannot reach their bound are
+// cleared from the survivor bitmap.  Queue entry = lane << 11 | step << 5 | bit (window start 32 step + bit).
+__device__ __noinline__ void bp_second_stage(const uint32_t* __restrict__ g_sym, int64_t n_pad, const uint32_t* __restrict__ tab,
+                                             uint32_t qinit, int np, const uint16_t* __restrict__ s_queue, int q_head,
+                                             int count, uint32_t* __restrict__ s_surv, int lane) {
+  __syncwarp();
+  if (lane < count) {
+    const uint32_t e = s_queue[(q_head + lane) & (kQueue - 1)];
+    const int s = (int)(e >> 11), step = (int)((e >> 5) & 63u), bit = (int)(e & 31u);
+    const int bit0 = 3 * (32 * step + bit), w0 = bit0 >> 5, sh = bit0 & 31;
+    const uint32_t* g = g_sym + s;
+    uint32_t x[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) x[k] = __ldg(g + (int64_t)(w0 + k) * n_pad);
+    uint32_t r0 = __funnelshift_r(x[0], x[1], sh), r1 = __funnelshift_r(x[1], x[2], sh),
+             r2 = __funnelshift_r(x[2], x[3], sh), r3 = __funnelshift_r(x[3], x[4], sh);
+    uint32_t sum = qinit;
+#pragma unroll 2
+    for (int T = 0; T < np; ++T) {
+      sum += __ldg(tab + T * 64 + (r0 & 63u));
+      r0 = __funnelshift_r(r0, r1, 6); r1 = __funnelshift_r(r1, r2, 6); r2 = __funnelshift_r(r2, r3, 6); r3 >>= 6;
+    }
+    if ((sum & 0x80008000u) == 0u) atomicAnd(&s_surv[step * 32 + s], ~(1u << bit));
+  }
+  __syncwarp();
 }
 
 template <bool BP>
@@ -519,7 +542,58 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
     for (int k = 1; k < 6; ++k) r[k] = __funnelshift_l(w[k - 1], w[k], lsh);
     carry = w[5];
   }
-  const uint32_t* const my_planes = BP ? a.planes_T + (int64_t)kb * 32 + lane : nullptr;
+  // ---- bit-parallel pre-pass: survivors of the whole sequence, then the integer second stage in full batches ----
+  uint32_t* const s_surv = s_ring + 256;   // [steps + 2][32 lanes]: bit k of word step = window start 32 step + k survives
+  if constexpr (BP) {
+    const int n_steps = (n_valid + 31) >> 5;
+    const uint32_t* pw = a.planes_T + (int64_t)kb * 32 + lane + 4 * wstride;   // plane word 1 = bases 0..31
+    uint32_t lo[4], hi[4], nx[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) { lo[cc] = __ldg(pw + cc * wstride); hi[cc] = __ldg(pw + (4 + cc) * wstride); }
+    pw += 8 * wstride;
+#pragma unroll 1
+    for (int step = 0; step < n_steps; ++step) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) nx[cc] = __ldg(pw + cc * wstride);      // next step's words (zero padding behind L)
+      pw += 4 * wstride;
+      uint32_t surv = 0u;
+      if (bpu.K != 0) {
+        surv = bp_survivors(lo, hi, bpu, reinterpret_cast<const uint4*>(s_qtab), reinterpret_cast<uint2*>(s_ring), lane);
+        const int left_w = n_valid - 32 * step;                               // real windows of this step
+        if (left_w < 32) surv &= 0xffffffffu >> (32 - left_w);
+        if (!real) surv = 0u;                                                 // padding sequences produce no candidates
+      }
+      s_surv[step * 32 + lane] = surv;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) { lo[cc] = hi[cc]; hi[cc] = nx[cc]; }
+    }
+    s_surv[n_steps * 32 + lane] = 0u;
+    s_surv[(n_steps + 1) * 32 + lane] = 0u;
+    __syncwarp();
+    if (bpu.K != 0) {
+      const uint32_t* tab = a.qtab + (size_t)t * 1024;
+      const uint32_t qinit2 = a.qthr[t * 2 + 0];
+      int qh = 0, qt = 0;
+#pragma unroll 1
+      for (int step = 0; step < n_steps; ++step) {
+        uint32_t w = s_surv[step * 32 + lane];
+        while (__any_sync(full, w != 0u)) {
+          const bool cand = w != 0u;
+          const int bb = __ffs((int)w) - 1;
+          w &= w - 1u;
+          const unsigned bal = __ballot_sync(full, cand);
+          if (cand) s_queue[(qt + __popc(bal & ((1u << lane) - 1u))) & (kQueue - 1)] = (uint16_t)((lane << 11) | (step << 5) | bb);
+          qt += __popc(bal);
+          if (qt - qh >= 32) {
+            bp_second_stage(a.sym_T + (int64_t)kb * 32, a.n_pad, tab, qinit2, np, s_queue, qh, 32, s_surv, lane);
+            qh += 32;
+          }
+        }
+      }
+      if (qt != qh) bp_second_stage(a.sym_T + (int64_t)kb * 32, a.n_pad, tab, qinit2, np, s_queue, qh, qt - qh, s_surv, lane);
+    }
+    __syncwarp();
+  }
   const uint32_t* pnext = my + 6 * wstride;
   const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(s_ring + lane);
   uint32_t stage = 0u;                   // byte offset of the stage holding the next refill (0 / 384)
@@ -536,6 +610,23 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
   unsigned dcar = 0u, dbody = 0u;        // staging rows [0, 2 mg) / [2 mg, nbuf) may hold non-zero x0 (bit 1: twin)
 
   for (int base = 0; base < L; base += 32) {
+    if constexpr (BP) {
+      // nothing carried over and no surviving window in reach of this chunk: nothing to evaluate, blur or store
+      if ((dcar | dbody) == 0u) {
+        const int ia = max(base - mg - padl + (base ? 2 * mg : 0), 0), ib = min(base - mg - padl + 32 + 2 * mg, n_valid);
+        uint32_t found = 0u;
+        if (ib > ia) {
+          const int wa = ia >> 5, wb = (ib - 1) >> 5;        // at most three words
+          for (int w = wa; w <= wb; ++w) {
+            uint32_t v = s_surv[w * 32 + lane];
+            if (w == wa) v &= 0xffffffffu << (ia & 31);
+            if (w == wb) v &= 0xffffffffu >> (31 - ((ib - 1) & 31));
+            found |= v;
+          }
+        }
+        if (!__any_sync(full, found != 0u)) continue;
+      }
+    }
     int b_start = 0;
     if (base != 0) {
       b_start = 2 * mg;
@@ -588,16 +679,17 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
       if (q_tail - q_head >= 32) { dbody |= flush_candidates(a, c, q_head, 32, base, lane); q_head += 32; }
     };
     if constexpr (BP) {
-      // ---- phase A, bit-parallel: 32 window starts per word step (two steps in the first chunk: 32 + 2 mg rows) ----
+      // ---- phase A, bit-parallel: the survivors of both stages were found up front (bitmap over window starts) ----
 #pragma unroll 1
       for (int b0 = b_start; b0 < nbuf; b0 += 32) {
         const int r_lo = max(b_lo - b0, 0), r_hi = min(b_hi - b0, 32);   // rows of this step that are real windows
         if (r_hi <= r_lo) continue;
-        uint32_t valid = (0xffffffffu >> (32 - (r_hi - r_lo))) << r_lo;
-        if (!real) valid = 0u;                                           // padding sequences produce no candidates
-        // window start of row b0 is base i0 = base - mg - padl + b0 >= -31; the plane stream starts one word early
-        uint32_t surv = bp_survivors(my_planes, wstride, base - mg - padl + b0 + 32, bpu,
-                                     reinterpret_cast<const uint4*>(s_qtab), reinterpret_cast<uint2*>(s_ring), lane) & valid;
+        const uint32_t valid = (0xffffffffu >> (32 - (r_hi - r_lo))) << r_lo;
+        const int i0 = base - mg - padl + b0;                            // window start of row b0 (>= -31)
+        uint32_t surv;
+        if (i0 >= 0) surv = __funnelshift_r(s_surv[(i0 >> 5) * 32 + lane], s_surv[((i0 >> 5) + 1) * 32 + lane], i0 & 31);
+        else surv = s_surv[lane] << (-i0);
+        surv &= valid;
         while (__any_sync(full, surv != 0u)) {
           const bool cand = surv != 0u;
           const int bb = __ffs((int)surv) - 1;
@@ -654,6 +746,7 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
 
 // words of a warp's table region: the pair tables, or (bit-parallel) 32 taps x 2 filters x uint4 letter masks
 __host__ __device__ inline int scan_table_words(int qslots, bool bp) { return bp && qslots < 4 ? 256 : qslots * 64; }
+__host__ __device__ inline int scan_ring_words(int L, bool bp) { return bp ? 256 + (L / 32 + 3) * 32 : 192; }
 
 template <bool BP>
 __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const __grid_constant__ ScanArgs a) {
@@ -667,7 +760,8 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const __grid_cons
   uint8_t* sm = smem_raw + ((256u - (uint32_t)(__cvta_generic_to_shared(smem_raw) & 255u)) & 255u);
   uint32_t* s_qtabs = reinterpret_cast<uint32_t*>(sm);                                  // [warps][tabw]
   float* s_bufs = reinterpret_cast<float*>(s_qtabs + kScanWarps * tabw);                // [warps][nb][nbuf][36]
-  constexpr int ringw = BP ? 256 : 192;   // refill ring [2][3][32], or (bit-parallel) plane words [4][32] uint2
+  // refill ring [2][3][32], or (bit-parallel) plane words [4][32] uint2 + survivor bitmap [L / 32 + 3][32]
+  const int ringw = scan_ring_words(a.L, BP);
   uint32_t* s_rings = reinterpret_cast<uint32_t*>(s_bufs + kScanWarps * nb * nbuf * kRowStride);   // [warps][ringw]
   float2* s_luts = reinterpret_cast<float2*>(s_rings + kScanWarps * ringw);                        // [warps][qslots * 8]
   uint16_t* s_queues = reinterpret_cast<uint16_t*>(s_luts + kScanWarps * a.qslots * 8);           // [warps][kQueue]
@@ -756,7 +850,7 @@ __global__ void __launch_bounds__(128) bp_tables_kernel(const float* __restrict_
     if (s1 < 1e299 && s1 > D[0]) { K = 1; rate = p0; }
     else if (s2 < 1e299 && s1 + s2 > D[0]) { K = 2; rate = p0 + p1; }
     else if (s3 < 1e299 && s1 + s2 + s3 > D[0]) { K = 3; rate = p0 + p1 + p2; }
-    const double cost = nf * (8.0 * n1 + 14.0 * n2) + 10240.0 * rate * nf;
+    const double cost = nf * (8.0 * n1 + 14.0 * n2) + 6144.0 * rate * nf;   // (~6 cycles per survivor: queue + second stage)
     if (K && (cost < best_cost || (cost == best_cost && q < best_q))) {
       best_cost = cost; best_rate = rate; best_q = q; best_K = K;
     }
@@ -919,7 +1013,7 @@ static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
   MEPP_REQUIRE((int64_t)T * L < (1LL << 31), "scan: T * L must be below 2^31");
   MEPP_REQUIRE(margin >= 0 && margin <= MEPP_MAX_MARGIN, "scan: margin must be in [0, 16]");
   MEPP_REQUIRE(hits_dev == nullptr || hit_count_dev != nullptr, "scan: hits need a hit counter");
-  const bool bitpar = planes_T_dev != nullptr;
+  const bool bitpar = planes_T_dev != nullptr && L <= 2016;   // (survivor queue entries hold a 6-bit word step)
   MEPP_REQUIRE(!bitpar || (bp_dev && bp_scratch_dev), "scan_bitpar: the bit planes need the task records and the scratch");
   MEPP_REQUIRE(mepp_device_ok(), "scan: no sm_100 CUDA device (no CPU fallback)");
   cudaStream_t st = as_stream(stream);
@@ -945,7 +1039,7 @@ static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
   auto smem_bytes = [&](bool bp) {
     return sizeof(float) * kScanWarps * ((units_dev || bitpar) ? 2 : 1) * nbuf * kRowStride +
            sizeof(uint32_t) * kScanWarps * scan_table_words(a.qslots, bp) + sizeof(uint16_t) * kScanWarps * kQueue +
-           sizeof(uint32_t) * kScanWarps * (bp ? 256 : 192) + sizeof(float2) * kScanWarps * a.qslots * 8 +
+           sizeof(uint32_t) * kScanWarps * scan_ring_words(L, bp) + sizeof(float2) * kScanWarps * a.qslots * 8 +
            256 /* table alignment */;
   };
   const size_t smem = smem_bytes(false);

@@ -14,6 +14,7 @@ ref = None
 for cut in cuts:
     eng = Engine()
     eng.bitpar = True
+    eng.overlap = False          # clean per-stage times
     eng.bp_cost_ratio = cut
     eng.stage(cfg["ascii"], cfg["scores"], cfg["perm_idx"], use_gc=True)
     tables = eng.upload_tables(motif_layers.scan_tables(tasks))
