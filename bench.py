@@ -172,6 +172,9 @@ def main():
     import torch
     from mepp_b200 import parallel, motif_layers, build
     build.build()
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # (NCCL's version banner: stdout carries ONE JSON line)
     rank, world, local = parallel.init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; mepp_b200 has no CPU fallback")
@@ -194,14 +197,20 @@ def main():
 
     eng = Engine(device=local)
 
+    phase_ms = []
+
     def e2e_step():
         """Public-API step from host buffers: stage + thresholds + all tasks (+ gather to rank 0 when sharded)."""
+        dbg = bool(os.environ.get("MEPP_BENCH_DEBUG"))
+        tq = [time.perf_counter()]
         if world > 1:
             # one host copy per node: rank 0 uploads, the other GPUs receive over NVLink (NCCL broadcast)
             eng.stage_broadcast(*((h_ascii, h_scores, h_perm) if rank == 0 else (None, None, None)), use_gc=True, src=0)
         else:
             eng.stage(h_ascii, h_scores, h_perm, use_gc=True)
+        tq.append(time.perf_counter())
         batch = eng.profile(my_tasks, margin=margin)       # thresholds on the device, groups pipelined
+        tq.append(time.perf_counter())
         full = None
         if world > 1:
             # the small per-task profiles go to rank 0 (float32, one row per column; the full tables stay per rank,
@@ -210,6 +219,9 @@ def main():
             for j, k in enumerate(GATHER_COLUMNS):
                 block[:, j, :] = batch.positions[k]
             full = parallel.gather_blocks(block, my_ids, T_total, device=dev)
+        if dbg:
+            tq.append(time.perf_counter())
+            phase_ms.append([round(1e3 * (b - a), 2) for a, b in zip(tq[:-1], tq[1:])])
         return batch, full
 
     def sync_all():
@@ -293,7 +305,8 @@ def main():
     t3 = time.perf_counter()
     gc.enable()
     if os.environ.get("MEPP_BENCH_DEBUG"):
-        print("e2e host ms per step:", e2e_times, file=sys.stderr, flush=True)
+        print(f"rank {rank} e2e host ms per step:", e2e_times, "phases (stage, profile, gather):",
+              phase_ms[-args.steps:], file=sys.stderr, flush=True)
     # an end-to-end step ends on the host (results in the caller's arrays, gathered on rank 0), so the larger of the
     # event time and the host clock is what a caller waits for
     dt_e2e = parallel.barrier_and_max(max(1e-3 * ev_c.elapsed_time(ev_d), t3 - t2), device=dev if world > 1 else None)

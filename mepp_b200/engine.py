@@ -271,7 +271,8 @@ class Engine:
             yhat_d = self._to_dev(yhat)
             if isinstance(perm_idx, torch.Tensor) and perm_idx.is_cuda:
                 P, perm_d = int(perm_idx.shape[0]), perm_idx          # already on the device (stage_broadcast)
-                self._perm_ready = None
+                self._perm_ready = getattr(self, '_bcast_perm_ready', None)   # its broadcast may still be in flight
+                self._bcast_perm_ready = None
             elif perm_idx is not None and int(perm_idx.shape[0]) > 0:
                 P = int(perm_idx.shape[0])
                 if tuple(perm_idx.shape) != (P, N):
@@ -325,16 +326,27 @@ class Engine:
             ascii_d = self._buf('ascii_bc', (N, L), torch.uint8)
             scores_d = self._buf('scores_bc', (N,), torch.float32)
             perm_d = self._buf('perm', (P, N), torch.int32) if P > 0 else None
+            as_t = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dt)
             if me:
-                as_t = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dt)
                 ascii_d.copy_(as_t(ascii_u8, torch.uint8), non_blocking=True)
                 scores_d.copy_(as_t(scores, torch.float32), non_blocking=True)
-                if P > 0:
-                    perm_d.copy_(as_t(perm_idx, torch.int32), non_blocking=True)
             dist.broadcast(ascii_d, src)
             dist.broadcast(scores_d, src)
+            self._bcast_perm_ready = None
             if P > 0:
-                dist.broadcast(perm_d, src)
+                # the permutation indices (the bulk of the bytes) travel on the side stream, upload and broadcast:
+                # only the Y operands need them, and those are first used after the first scan is in flight
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=self.device)
+                free = torch.cuda.Event()
+                free.record(torch.cuda.current_stream(self.device))   # earlier users of the buffer are done
+                self._copy_stream.wait_event(free)
+                with torch.cuda.stream(self._copy_stream):
+                    if me:
+                        perm_d.copy_(as_t(perm_idx, torch.int32), non_blocking=True)
+                    dist.broadcast(perm_d, src)
+                    self._bcast_perm_ready = torch.cuda.Event()
+                    self._bcast_perm_ready.record(self._copy_stream)
             return self.stage(ascii_d, scores_d.cpu().numpy(), perm_d, use_gc=use_gc)
 
     def _ensure_y(self):

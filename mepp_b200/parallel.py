@@ -103,13 +103,26 @@ def gather_blocks(local_block, local_ids, n_total, device=None, root_only=True):
     if k > t_max:
         raise ValueError("shard larger than the padded gather block")
     item_shape = local_block.shape[1:]
-    pad = np.zeros((t_max,) + item_shape, dtype=local_block.dtype)
-    pad[:k] = local_block
     ids = np.full(t_max, -1, dtype=np.int64)
     ids[:k] = np.asarray(local_ids, dtype=np.int64)
-    send, send_ids = torch.from_numpy(pad), torch.from_numpy(ids)
+    # the task ids of a sharding do not change from call to call: their collective runs once per (shard, device)
+    ids_key = (ids.tobytes(), n_total, world, str(device), bool(root_only))
+    cached_ids = _GATHERED_IDS.get(ids_key)
     if device is not None:
-        send, send_ids = send.to(device, non_blocking=True), send_ids.to(device, non_blocking=True)
+        # padded send block in a cached pinned buffer: one host copy, one asynchronous upload
+        skey = ('send', (t_max,) + tuple(item_shape), local_block.dtype.str)
+        pin = _PINNED.get(skey)
+        if pin is None:
+            pin = _PINNED[skey] = torch.zeros((t_max,) + tuple(item_shape), dtype=torch.from_numpy(local_block[:0]).dtype,
+                                              pin_memory=True)
+        pin.numpy()[:k] = local_block
+        send = pin.to(device, non_blocking=True)
+        send_ids = torch.from_numpy(ids).to(device, non_blocking=True) if cached_ids is None else None
+    else:
+        pad = np.zeros((t_max,) + item_shape, dtype=local_block.dtype)
+        pad[:k] = local_block
+        send = torch.from_numpy(pad)
+        send_ids = torch.from_numpy(ids) if cached_ids is None else None
     # one receive buffer (rank-major), the per-rank pieces are views of it; on the root it goes to the host in one copy
     # into a cached pinned buffer
     big = big_ids = None
@@ -118,29 +131,36 @@ def gather_blocks(local_block, local_ids, n_total, device=None, root_only=True):
         try:
             if rank == 0:
                 big = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
-                big_ids = torch.empty((world, t_max), dtype=send_ids.dtype, device=send.device)
             dist.gather(send, list(big.unbind(0)) if rank == 0 else None, dst=0)
-            dist.gather(send_ids, list(big_ids.unbind(0)) if rank == 0 else None, dst=0)
+            if cached_ids is None:
+                if rank == 0:
+                    big_ids = torch.empty((world, t_max), dtype=send_ids.dtype, device=send.device)
+                dist.gather(send_ids, list(big_ids.unbind(0)) if rank == 0 else None, dst=0)
             done = True
         except (RuntimeError, NotImplementedError):
             done = False
     if not done:
         big = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
-        big_ids = torch.empty((world, t_max), dtype=send_ids.dtype, device=send.device)
         dist.all_gather(list(big.unbind(0)), send)
-        dist.all_gather(list(big_ids.unbind(0)), send_ids)
+        if cached_ids is None:
+            big_ids = torch.empty((world, t_max), dtype=send_ids.dtype, device=send.device)
+            dist.all_gather(list(big_ids.unbind(0)), send_ids)
+    if cached_ids is None:
+        # (every rank remembers that the ids travelled; only a receiving rank keeps them)
+        _GATHERED_IDS[ids_key] = big_ids.cpu().numpy() if big_ids is not None else True
     if root_only and rank != 0:
         return None
+    rid = _GATHERED_IDS[ids_key]
     if big.is_cuda:
         key = (tuple(big.shape), big.dtype)
         host = _PINNED.get(key)
         if host is None:
             host = _PINNED[key] = torch.empty(big.shape, dtype=big.dtype, pin_memory=True)
         host.copy_(big, non_blocking=True)
-        rid = big_ids.cpu().numpy()                     # (synchronises the stream: the pinned copy is complete)
+        torch.cuda.current_stream(big.device).synchronize()     # the pinned copy is complete
         rec = host.numpy()
     else:
-        rec, rid = big.numpy(), big_ids.numpy()
+        rec = big.numpy()
     out = np.empty((n_total,) + item_shape, dtype=local_block.dtype)
     for r_ in range(world):
         k_ = int((rid[r_] >= 0).sum())                  # a rank's valid rows come first
@@ -149,6 +169,7 @@ def gather_blocks(local_block, local_ids, n_total, device=None, root_only=True):
 
 
 _PINNED = {}
+_GATHERED_IDS = {}
 
 
 def barrier_and_max(seconds, device=None):
