@@ -27,6 +27,10 @@
 // to right, eight windows per step, its 3-bit symbol stream read straight from global memory (word-transposed,
 // so a warp's load is one 128-byte line) and prefetched one refill ahead.  Warps share nothing; shared memory
 // only holds the unit's pair tables, its x0 staging rows and the candidate ring, ~14 KB per warp.
+//
+// scan_kernel<true> is the optional bit-parallel variant (mepp_scan_bitpar): a first stage that counts "bad" letters
+// with logic ops on bit planes of the sequences, the pair-table sums as a second stage, then the same exact
+// evaluation and the same phase B.  Identical outputs; measured slower on cfg 2, off by default.
 #include <stdlib.h>
 #include "common.cuh"
 
