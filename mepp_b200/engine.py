@@ -308,8 +308,9 @@ class Engine:
 
     def stage_broadcast(self, ascii_u8=None, scores=None, perm_idx=None, use_gc=True, src=0):
         """Multi-GPU staging from ONE host copy: rank `src` passes the host arrays (the other ranks pass None), the
-        device copies reach the other GPUs by NCCL broadcast over NVLink instead of one host upload per rank (eight
-        ranks uploading 100 MB each out of the same host memory were the slowest part of an 8-GPU end-to-end step)."""
+        device copies reach the other GPUs by NCCL broadcast over NVLink instead of one host upload per rank.  The
+        permutation indices (the bulk of the bytes) are uploaded and broadcast on the side stream, behind the first
+        scan (8-GPU end-to-end step on cfg 2: 38.3 -> 35.2 ms together with the leaner result gather)."""
         torch = self.torch
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

@@ -37,6 +37,12 @@ def _worker(rank, world, port, out_dir):
     assert (full is None) == (r != 0)
     both = parallel.gather_blocks(block, mine, n_total, root_only=False)
     assert both.shape == (n_total, 3, 2) and both.dtype == np.float64
+    # repeated calls reuse the gathered task ids (one collective less); the data are new every time
+    again = parallel.gather_blocks((block * 2).astype(np.float32), mine, n_total)
+    if r == 0:
+        assert np.allclose(again, 2 * full)
+    again_all = parallel.gather_blocks(block * 3, mine, n_total, root_only=False)
+    assert np.allclose(again_all, 3 * both)
     tmax = parallel.barrier_and_max(1.0 + r)
     if r == 0:
         np.save(os.path.join(out_dir, "full.npy"), full)
