@@ -36,7 +36,7 @@ METRIC = "Gbp*motifs/s scanned+profiled"
 UNIT = "Gbp*motifs/s"
 
 
-SCAN_DRAM_BYTES_PER_LAUNCH = 16.7e6   # dram__bytes_read + write of one scan launch (82 tasks of cfg 2), ncu --set full:
+SCAN_DRAM_BYTES_PER_LAUNCH = 16.0e6   # dram__bytes_read + write of one scan launch (82 tasks of cfg 2), ncu --set full:
                                       # profiles/r01_final_kernels_ncu_summary.txt
 
 
