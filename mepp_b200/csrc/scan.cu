@@ -453,7 +453,7 @@ __device__ __noinline__ void bp_second_stage(const uint32_t* __restrict__ g_sym,
 
 template <bool BP>
 __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const int t2, const int kb,
-                                          uint32_t* __restrict__ s_qtab, float2* __restrict__ s_lut,
+                                          uint32_t* __restrict__ s_qtab, float2* s_lut,
                                           float* __restrict__ s_buf,
                                           float* __restrict__ s_buf2, uint16_t* __restrict__ s_queue,
                                           uint32_t* __restrict__ s_ring, TaskCtx* __restrict__ s_ctx,
@@ -492,7 +492,12 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
   }
   {
     const float2* g_lut = reinterpret_cast<const float2*>(a.lut) + (size_t)t * (MEPP_MAX_MOTIF_LEN * 4);
-    for (int i = lane; i < m * 4; i += 32) s_lut[i] = __ldg(g_lut + i);
+    // the exact weights: a shared copy for the bit-parallel kernel (its exact path is busy); the pair-table kernel
+    // evaluates ~1e-4 of the windows exactly and reads them from global memory (L1), which frees up to 2 KB per CTA
+    if constexpr (BP)
+      for (int i = lane; i < m * 4; i += 32) s_lut[i] = __ldg(g_lut + i);
+    else
+      s_lut = const_cast<float2*>(g_lut);
   }
   for (int b = 0; b < nbuf; ++b) s_buf[b * kRowStride + lane] = 0.0f;
   if (t2 >= 0)
@@ -768,7 +773,8 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const __grid_cons
   const int ringw = scan_ring_words(a.L, BP);
   uint32_t* s_rings = reinterpret_cast<uint32_t*>(s_bufs + kScanWarps * nb * nbuf * kRowStride);   // [warps][ringw]
   float2* s_luts = reinterpret_cast<float2*>(s_rings + kScanWarps * ringw);                        // [warps][qslots * 8]
-  uint16_t* s_queues = reinterpret_cast<uint16_t*>(s_luts + kScanWarps * a.qslots * 8);           // [warps][kQueue]
+  const int lutw = BP ? a.qslots * 8 : 0;                                                         // (float2 per warp)
+  uint16_t* s_queues = reinterpret_cast<uint16_t*>(s_luts + kScanWarps * lutw);                   // [warps][kQueue]
   __shared__ TaskCtx s_ctxs[kScanWarps];
 
   const int u = blockIdx.y * kScanWarps + warp;
@@ -777,7 +783,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const __grid_cons
   const int t2 = a.units ? a.units[2 * u + 1] : -1;
   float* s_buf = s_bufs + warp * nb * nbuf * kRowStride;
   float* s_buf2 = s_buf + (nb - 1) * nbuf * kRowStride;
-  scan_task<BP>(a, t, t2, kb, s_qtabs + warp * tabw, s_luts + warp * a.qslots * 8, s_buf, s_buf2, s_queues + warp * kQueue,
+  scan_task<BP>(a, t, t2, kb, s_qtabs + warp * tabw, s_luts + warp * lutw, s_buf, s_buf2, s_queues + warp * kQueue,
                 s_rings + warp * ringw, &s_ctxs[warp], lane);
 }
 
@@ -1043,7 +1049,7 @@ static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
   auto smem_bytes = [&](bool bp) {
     return sizeof(float) * kScanWarps * ((units_dev || bitpar) ? 2 : 1) * nbuf * kRowStride +
            sizeof(uint32_t) * kScanWarps * scan_table_words(a.qslots, bp) + sizeof(uint16_t) * kScanWarps * kQueue +
-           sizeof(uint32_t) * kScanWarps * scan_ring_words(L, bp) + sizeof(float2) * kScanWarps * a.qslots * 8 +
+           sizeof(uint32_t) * kScanWarps * scan_ring_words(L, bp) + (bp ? sizeof(float2) * kScanWarps * a.qslots * 8 : 0) +
            256 /* table alignment */;
   };
   const size_t smem = smem_bytes(false);
