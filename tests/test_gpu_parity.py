@@ -689,3 +689,54 @@ def test_full_size_config2_properties():
         assert tasks[pick[j]][1] == '+' and tasks[pick[j + 1]][1] == '+/-'
         Xp, Xd = sub.motif_score_matrix(j, L), sub.motif_score_matrix(j + 1, L)
         assert (Xd >= Xp).all()
+
+
+def test_bitpar_records_are_sound_for_the_shipped_libraries():
+    """The (cut, count) choice of the bit-parallel first stage is made on the device (bp_tables_kernel).  Independent
+    check in numpy, for every motif of the three shipped libraries and the orientations '+', '-', '+/-': with the
+    counted taps and good letters read back from the task records, the sum of the K smallest per-tap minima of the
+    bad letters' penalties exceeds  max score - threshold + rounding slack  for each filter -- a window the counters
+    reject cannot match (scan.cu, "bit-parallel first stage")."""
+    from mepp_b200 import synth, motif_layers, _lib
+    eng = _engine()
+    eng.bitpar = True
+    eng.bp_cost_ratio = 1e9
+    tasks = []
+    for name in ("ohler", "homer_clustered", "homer"):
+        for pwm in synth.load_motif_library(name).values():
+            tasks += [(pwm, o) for o in ('+', '-', '+/-')]
+    ascii_u8, scores = synth.synth_sequences(64, 80, seed=1)
+    eng.stage(ascii_u8, scores, None)
+    tables = motif_layers.scan_tables(tasks)
+    dt = eng.upload_tables(tables)
+    bp = dt.dev['bp'].cpu().numpy().view(np.uint32)
+    assert bp.shape == (len(tasks), _lib.BP_WORDS)
+    n_used = n_never = 0
+    for t, tb in enumerate(tables):
+        m, nf = tb['m'], tb['n_filters']
+        K, use, nfr = int(bp[t, 64] & 0xff), int((bp[t, 64] >> 8) & 1), int((bp[t, 64] >> 16) & 0xff)
+        assert nfr == nf
+        if not use:
+            continue
+        counts = [(int(bp[t, 65] >> (16 * f)) & 0xff, int(bp[t, 65] >> (16 * f + 8)) & 0xff) for f in range(2)]
+        for f in range(nf):
+            W = tb['lut'][:m, :, f].astype(np.float64)                       # (m, 4) float32 weights as doubles
+            pen = W.max(axis=1, keepdims=True) - W
+            D = W.max(axis=1).sum() + float(tb['bias']) + 2.0 * (4.0 * m) * np.abs(W).max(axis=1).sum() * 5.97e-8 + 1e-6
+            if K == 0:
+                assert D <= 0.0, (t, f)                                      # nothing can match
+                n_never += f == 0
+                continue
+            n1, n2 = counts[f]
+            mins, taps = [], set()
+            for i in range(n1 + n2):
+                w = int(bp[t, 32 * f + i])
+                j, good = w & 0xff, {(w >> 8) & 0xff} | ({(w >> 16) & 0xff} if i >= n1 else set())
+                assert j < m and j not in taps and all(g < 4 for g in good), (t, f, i)
+                taps.add(j)
+                bad = [pen[j, c] for c in range(4) if c not in good]
+                mins.append(min(bad))
+                assert min(bad) > max(pen[j, c] for c in good), (t, f, j)   # every bad letter costs more than a good one
+            assert len(mins) >= K and np.sort(mins)[:K].sum() > D, (t, f, K)
+        n_used += 1
+    assert n_used > len(tasks) // 2 and n_never > 0
