@@ -185,6 +185,25 @@ int mepp_scan_bitpar(const uint32_t* sym_T_dev, const float* zhat_dev,
                      void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
                      const uint32_t* planes_T_dev, const uint32_t* bp_dev, int32_t* bp_scratch_dev, void* stream);
 
+/* ---- lean scan for the sparse path (optional, MEPP_SCAN_LEAN=1; same reference code as mepp_scan) ----
+ * The scan only finds and publishes matches (count, density, match list) and drops them into fixed-capacity buckets
+ * per (task, k-block of 32 sequences); a second kernel sorts every bucket by (sequence, position) and builds the
+ * entries of the blurred score matrix, row_nnz and rowstats from it (a row belongs to the first match inside its
+ * window; float32 sum in position order, IEEE division: the values mepp_scan produces).  No staging rows in shared
+ * memory, no per-chunk blur.  buckets_dev: mepp_scan_lean_bucket_bytes(T, N) bytes; bucket_count_dev int32
+ * [T * n_pad / 32].  If a bucket overflows (more than 64 matches of a task in 32 sequences) entry_count_dev[1] is
+ * non-zero and the group has to be redone with mepp_scan. */
+int64_t mepp_scan_lean_bucket_bytes(int T, int64_t N);
+int mepp_scan_lean(const uint32_t* sym_T_dev, const float* zhat_dev,
+                   int64_t N, int L, int T, int margin,
+                   const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev, const int32_t* nfilt_dev,
+                   const uint32_t* qtab_dev, const uint32_t* qthr_dev, const int32_t* units_dev, int n_units,
+                   int max_motif_len,
+                   double* rowstats_dev, int32_t* count_dev, int32_t* density_dev,
+                   void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
+                   void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
+                   void* buckets_dev, int32_t* bucket_count_dev, void* stream);
+
 /* Restore the all-zero state of an A operand that mepp_scan(..., N, L, T, margin, ...) wrote, from the
  * match list of that call (every match dirties rows pos-margin..pos+margin of one 8-column group); a NULL
  * or overflowed list clears the whole operand instead.  Call after the operand's last consumer. */

@@ -60,7 +60,11 @@ struct ScanArgs {
   // bit-parallel first stage (optional): one-hot bit planes of the sequences, per-task letter sets, and the
   // number of units of this launch's list (device side: the list is partitioned by a kernel, see bp_partition_kernel)
   const uint32_t* planes_T; const uint32_t* bp; const int32_t* unit_count;
+  // lean mode (optional, sparse path): the scan only finds and publishes matches; they also go to fixed-capacity
+  // buckets per (task, k-block), from which bucket_entries_kernel builds the blurred entries and the row sums
+  int lean; uint2* buckets; int32_t* bucket_count;
 };
+constexpr int kBucketCap = 64;   // matches per (task, k-block) bucket; an overflow sends the group through the full scan
 
 // Per-warp (= per unit) state shared by the helper routines below.  The helpers are deliberately NOT
 // inlined and NOT templated on the task: one small instruction stream for every task keeps the kernel
@@ -121,8 +125,14 @@ __device__ __forceinline__ void exact_x0(const TaskCtx& c, int s, int i, float& 
 // One match of task t: staging buffer, per-position / per-sequence counts, optional match list.
 __device__ __forceinline__ void publish_match(const ScanArgs& a, TaskCtx& c, int which, int t, float* buf, int b, int s,
                                               int p, float x0) {
-  buf[b * kRowStride + s] = x0;
-  atomicOr(&c.rowmask[which], 1ull << b);
+  if (a.lean) {
+    const int64_t bkt = (int64_t)t * a.KB + c.kb;
+    const int slot = atomicAdd(&a.bucket_count[bkt], 1);
+    if (slot < kBucketCap) a.buckets[bkt * kBucketCap + slot] = make_uint2(((uint32_t)s << 16) | (uint32_t)p, __float_as_uint(x0));
+  } else {
+    buf[b * kRowStride + s] = x0;
+    atomicOr(&c.rowmask[which], 1ull << b);
+  }
   const int64_t ns = (int64_t)c.kb * 32 + s;
   atomicAdd(&a.count[(int64_t)t * c.L + p], 1);
   atomicAdd(&a.density[(int64_t)t * a.n_pad + ns], 1);
@@ -499,9 +509,11 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
     else
       s_lut = const_cast<float2*>(g_lut);
   }
-  for (int b = 0; b < nbuf; ++b) s_buf[b * kRowStride + lane] = 0.0f;
-  if (t2 >= 0)
-    for (int b = 0; b < nbuf; ++b) s_buf2[b * kRowStride + lane] = 0.0f;
+  if (!a.lean) {
+    for (int b = 0; b < nbuf; ++b) s_buf[b * kRowStride + lane] = 0.0f;
+    if (t2 >= 0)
+      for (int b = 0; b < nbuf; ++b) s_buf2[b * kRowStride + lane] = 0.0f;
+  }
   // qinit: per 16-bit half (0x8000 - pass bound), so "sum reaches the bound" <=> bit 15 of the half is set.
   // Padding sequences never produce candidates.
   const uint32_t qinit = real ? a.qthr[t * 2 + 0] : 0u;
@@ -685,7 +697,11 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
         s_queue[slot_i & (kQueue - 1)] = (uint16_t)((lane << 8) | bb);
       }
       q_tail += __popc(bal);
-      if (q_tail - q_head >= 32) { dbody |= flush_candidates(a, c, q_head, 32, base, lane); q_head += 32; }
+      if (q_tail - q_head >= 32) {
+        const unsigned got = flush_candidates(a, c, q_head, 32, base, lane);
+        if (!a.lean) dbody |= got;
+        q_head += 32;
+      }
     };
     if constexpr (BP) {
       // ---- phase A, bit-parallel: the survivors of both stages were found up front (bitmap over window starts) ----
@@ -743,7 +759,11 @@ __device__ __forceinline__ void scan_task(const ScanArgs& a, const int t, const 
       if (bal != 0u && b >= b_lo) push(bal, cand, b);
     }
     }
-    if (q_tail != q_head) { dbody |= flush_candidates(a, c, q_head, q_tail - q_head, base, lane); q_head = q_tail; }
+    if (q_tail != q_head) {
+      const unsigned got = flush_candidates(a, c, q_head, q_tail - q_head, base, lane);
+      if (!a.lean) dbody |= got;
+      q_head = q_tail;
+    }
     __syncwarp();
     // ---- phase B: blur + split + store, only for chunks that hold or border a match ----
     const unsigned nzb = dcar | dbody;
@@ -769,9 +789,10 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const __grid_cons
   uint8_t* sm = smem_raw + ((256u - (uint32_t)(__cvta_generic_to_shared(smem_raw) & 255u)) & 255u);
   uint32_t* s_qtabs = reinterpret_cast<uint32_t*>(sm);                                  // [warps][tabw]
   float* s_bufs = reinterpret_cast<float*>(s_qtabs + kScanWarps * tabw);                // [warps][nb][nbuf][36]
+  const int bufw = a.lean ? 0 : nb * nbuf * kRowStride;                                 // (no staging rows in lean mode)
   // refill ring [2][3][32], or (bit-parallel) plane words [4][32] uint2 + survivor bitmap [L / 32 + 3][32]
   const int ringw = scan_ring_words(a.L, BP);
-  uint32_t* s_rings = reinterpret_cast<uint32_t*>(s_bufs + kScanWarps * nb * nbuf * kRowStride);   // [warps][ringw]
+  uint32_t* s_rings = reinterpret_cast<uint32_t*>(s_bufs + kScanWarps * bufw);                     // [warps][ringw]
   float2* s_luts = reinterpret_cast<float2*>(s_rings + kScanWarps * ringw);                        // [warps][qslots * 8]
   const int lutw = BP ? a.qslots * 8 : 0;                                                         // (float2 per warp)
   uint16_t* s_queues = reinterpret_cast<uint16_t*>(s_luts + kScanWarps * lutw);                   // [warps][kQueue]
@@ -781,8 +802,8 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_kernel(const __grid_cons
   if (u >= (a.unit_count ? *a.unit_count : a.U)) return;
   const int t = a.units ? a.units[2 * u] : u;
   const int t2 = a.units ? a.units[2 * u + 1] : -1;
-  float* s_buf = s_bufs + warp * nb * nbuf * kRowStride;
-  float* s_buf2 = s_buf + (nb - 1) * nbuf * kRowStride;
+  float* s_buf = s_bufs + warp * bufw;
+  float* s_buf2 = s_buf + (a.lean ? 0 : (nb - 1) * nbuf * kRowStride);
   scan_task<BP>(a, t, t2, kb, s_qtabs + warp * tabw, s_luts + warp * lutw, s_buf, s_buf2, s_queues + warp * kQueue,
                 s_rings + warp * ringw, &s_ctxs[warp], lane);
 }
@@ -1002,6 +1023,105 @@ extern "C" int mepp_x_planes_reset(void* x_planes_dev, const void* hits_dev, int
 }
 
 namespace mepp {
+// Lean mode, second half: one warp per (task, k-block) bucket of matches.  The matches are sorted by (sequence,
+// position); a row of the blurred matrix belongs to the first match inside its window, which sums the window's
+// matches in position order in float32 (adding the zeros of the dense window would change nothing), divides by k
+// and emits the entry, the non-zero count of the row and the row sums -- the same values store_chunk produces
+// from the staging rows (tools/proto_match_blur.py is the numpy form of this).  A bucket that overflowed is counted
+// in entry_count[1] (the sub-list counters sit at [16 j]); the caller then redoes the group with the full scan.
+__global__ void __launch_bounds__(128) bucket_entries_kernel(const uint2* __restrict__ buckets,
+                                                             const int32_t* __restrict__ bucket_count, int64_t n_buckets,
+                                                             int64_t KB, int L, int margin, int64_t N,
+                                                             const float* __restrict__ zhat, XEntry* __restrict__ entries,
+                                                             int64_t sub_cap, unsigned long long* __restrict__ entry_count,
+                                                             int32_t* __restrict__ row_nnz, double* __restrict__ rowstats) {
+  __shared__ uint32_t s_key[4][2][kBucketCap];
+  __shared__ float s_val[4][2][kBucketCap];
+  const unsigned full = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t bkt = (int64_t)blockIdx.x * 4 + warp;
+  if (bkt >= n_buckets) return;
+  const int n = bucket_count[bkt];
+  if (n == 0) return;
+  if (n > kBucketCap) {
+    if (lane == 0) atomicAdd(entry_count + 1, 1ull);        // word 1 of the counter block: "a bucket overflowed"
+    return;
+  }
+  const int t = (int)(bkt / KB), kb = (int)(bkt % KB);
+  const uint2* rec = buckets + bkt * kBucketCap;
+  for (int i = lane; i < n; i += 32) {
+    const uint2 r = rec[i];
+    s_key[warp][0][i] = r.x;                                // sequence (0..31) << 16 | position
+    s_val[warp][0][i] = __uint_as_float(r.y);
+  }
+  __syncwarp();
+  // rank sort (n <= 64, the keys of a task's bucket are distinct)
+  for (int i = lane; i < n; i += 32) {
+    const uint32_t k = s_key[warp][0][i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += s_key[warp][0][j] < k;
+    s_key[warp][1][rank] = k;
+    s_val[warp][1][rank] = s_val[warp][0][i];
+  }
+  __syncwarp();
+  const uint32_t* key = s_key[warp][1];
+  const float* val = s_val[warp][1];
+  const int mg = margin, k = 2 * margin + 1;
+  const float kf = (float)k;
+  // rows owned by match i: window contains it and no earlier match of the same sequence
+  int lo = 0, hi = -1, seq = 0;
+  int cnt = 0;
+  const int i = lane, i2 = lane + 32;
+  auto owned = [&](int idx, int& r_lo, int& r_hi, int& sq) {
+    r_lo = 0; r_hi = -1; sq = 0;
+    if (idx >= n) return;
+    sq = (int)(key[idx] >> 16);
+    const int pos = (int)(key[idx] & 0xffffu);
+    r_lo = max(pos - mg, mg);
+    r_hi = min(pos + mg, L - 1 - mg);
+    if (idx > 0 && (int)(key[idx - 1] >> 16) == sq) r_lo = max(r_lo, (int)(key[idx - 1] & 0xffffu) + mg + 1);
+  };
+  int lo2, hi2, seq2;
+  owned(i, lo, hi, seq);
+  owned(i2, lo2, hi2, seq2);
+  cnt = max(hi - lo + 1, 0) + max(hi2 - lo2 + 1, 0);
+  // one slot reservation per warp in the k-block's sub-list
+  int pre = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(full, pre, o);
+    if (lane >= o) pre += v;
+  }
+  const int total = __shfl_sync(full, pre, 31);
+  if (total == 0) return;
+  const int list = kb & (MEPP_ENTRY_LISTS - 1);
+  unsigned long long slot = 0ull;
+  if (lane == 0) slot = atomicAdd(entry_count + list * 16, (unsigned long long)total);
+  slot = __shfl_sync(full, slot, 0) + (unsigned long long)(pre - cnt);
+  uint4* dst = reinterpret_cast<uint4*>(entries + (int64_t)list * sub_cap);
+  auto emit = [&](int idx, int r_lo, int r_hi, int sq) {
+    const int64_t ns = (int64_t)kb * 32 + sq;
+    const double z = (zhat && ns < N) ? (double)__ldg(zhat + ns) : 0.0;
+    for (int p = r_lo; p <= r_hi; ++p) {
+      float acc = 0.0f;
+      for (int j = idx; j < n && (int)(key[j] >> 16) == sq && (int)(key[j] & 0xffffu) <= p + mg; ++j)
+        acc = __fadd_rn(acc, val[j]);
+      const float xb = k > 1 ? __fdiv_rn(acc, kf) : acc;
+      const int r = t * L + p;
+      if ((int64_t)slot < sub_cap) dst[slot] = make_uint4((uint32_t)r, (uint32_t)ns, __float_as_uint(xb), 0u);
+      ++slot;
+      atomicAdd(row_nnz + r, 1);
+      const double v = (double)xb;
+      double* rs = rowstats + (int64_t)r * 3;
+      atomicAdd(rs + 0, v); atomicAdd(rs + 1, v * v); atomicAdd(rs + 2, v * z);
+    }
+  };
+  emit(i, lo, hi, seq);
+  emit(i2, lo2, hi2, seq2);
+}
+}  // namespace mepp
+
+namespace mepp {
 static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
                      int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
                      const int32_t* mlen_dev, const int32_t* nfilt_dev, const uint32_t* qtab_dev,
@@ -1010,7 +1130,7 @@ static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
                      int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
                      void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev,
                      int32_t* row_nnz_dev, const uint32_t* planes_T_dev, const uint32_t* bp_dev, int32_t* bp_scratch_dev,
-                     void* stream) {
+                     void* buckets_dev, int32_t* bucket_count_dev, void* stream) {
   MEPP_REQUIRE(sym_T_dev && lut_dev && bias_dev && mlen_dev && nfilt_dev && qtab_dev && qthr_dev &&
                rowstats_dev && count_dev && density_dev, "scan: null pointer");
   MEPP_REQUIRE(x_planes_dev || entries_dev, "scan: neither the tiled operand nor the entry list was requested");
@@ -1045,9 +1165,13 @@ static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
   a.entries = reinterpret_cast<XEntry*>(entries_dev); a.sub_cap = entry_cap / MEPP_ENTRY_LISTS;
   a.entry_count = entry_count_dev; a.row_nnz = row_nnz_dev;
   a.planes_T = planes_T_dev; a.bp = bp_dev; a.unit_count = nullptr;
+  const bool lean = buckets_dev != nullptr;
+  MEPP_REQUIRE(!lean || (bucket_count_dev && entries_dev && !x_planes_dev && L <= 65535 && !bitpar),
+               "scan_lean: needs the bucket counters and the entry list, no tiled operand, L <= 65535");
+  a.lean = lean ? 1 : 0; a.buckets = reinterpret_cast<uint2*>(buckets_dev); a.bucket_count = bucket_count_dev;
   const int nbuf = 32 + 2 * margin;
   auto smem_bytes = [&](bool bp) {
-    return sizeof(float) * kScanWarps * ((units_dev || bitpar) ? 2 : 1) * nbuf * kRowStride +
+    return (lean ? 0 : sizeof(float) * kScanWarps * ((units_dev || bitpar) ? 2 : 1) * nbuf * kRowStride) +
            sizeof(uint32_t) * kScanWarps * scan_table_words(a.qslots, bp) + sizeof(uint16_t) * kScanWarps * kQueue +
            sizeof(uint32_t) * kScanWarps * scan_ring_words(L, bp) + (bp ? sizeof(float2) * kScanWarps * a.qslots * 8 : 0) +
            256 /* table alignment */;
@@ -1075,9 +1199,17 @@ static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
   }
   dim3 grid((unsigned)a.KB, (unsigned)((a.U + kScanWarps - 1) / kScanWarps));
   MEPP_REQUIRE(grid.y <= 65535, "scan: too many tasks in one call");
+  if (lean) MEPP_CUDA_CHECK(cudaMemsetAsync(bucket_count_dev, 0, sizeof(int32_t) * (size_t)T * a.KB, st));
   if (!bitpar) {
     scan_kernel<false><<<grid, kScanWarps * 32, smem, st>>>(a);
     MEPP_CUDA_CHECK(cudaGetLastError());
+    if (lean) {
+      const int64_t n_buckets = (int64_t)T * a.KB;
+      bucket_entries_kernel<<<(unsigned)((n_buckets + 3) / 4), 128, 0, st>>>(
+          a.buckets, bucket_count_dev, n_buckets, a.KB, L, margin, N, zhat_dev, a.entries, a.sub_cap, entry_count_dev,
+          row_nnz_dev, rowstats_dev);
+      MEPP_CUDA_CHECK(cudaGetLastError());
+    }
     return 0;
   }
   // units split by class on the device (the class depends on the thresholds, which may have been computed there);
@@ -1111,7 +1243,7 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
   return mepp::scan_impl(sym_T_dev, zhat_dev, N, L, T, margin, lut_dev, bias_dev, mlen_dev, nfilt_dev, qtab_dev, qthr_dev,
                          units_dev, n_units, max_motif_len, x_planes_dev, rowstats_dev, count_dev, density_dev, hits_dev,
                          hits_cap, hit_count_dev, entries_dev, entry_cap, entry_count_dev, row_nnz_dev, nullptr, nullptr,
-                         nullptr, stream);
+                         nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int mepp_scan_bitpar(const uint32_t* sym_T_dev, const float* zhat_dev,
@@ -1127,7 +1259,26 @@ extern "C" int mepp_scan_bitpar(const uint32_t* sym_T_dev, const float* zhat_dev
   return mepp::scan_impl(sym_T_dev, zhat_dev, N, L, T, margin, lut_dev, bias_dev, mlen_dev, nfilt_dev, qtab_dev, qthr_dev,
                          units_dev, n_units, max_motif_len, x_planes_dev, rowstats_dev, count_dev, density_dev, hits_dev,
                          hits_cap, hit_count_dev, entries_dev, entry_cap, entry_count_dev, row_nnz_dev, planes_T_dev,
-                         bp_dev, bp_scratch_dev, stream);
+                         bp_dev, bp_scratch_dev, nullptr, nullptr, stream);
+}
+
+extern "C" int64_t mepp_scan_lean_bucket_bytes(int T, int64_t N) {
+  return (int64_t)T * (mepp_pad32(N) / mepp::kBlockK) * mepp::kBucketCap * 8;
+}
+
+extern "C" int mepp_scan_lean(const uint32_t* sym_T_dev, const float* zhat_dev,
+                              int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
+                              const int32_t* mlen_dev, const int32_t* nfilt_dev, const uint32_t* qtab_dev,
+                              const uint32_t* qthr_dev, const int32_t* units_dev, int n_units, int max_motif_len,
+                              double* rowstats_dev, int32_t* count_dev,
+                              int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
+                              void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev,
+                              int32_t* row_nnz_dev, void* buckets_dev, int32_t* bucket_count_dev, void* stream) {
+  MEPP_REQUIRE(buckets_dev && bucket_count_dev && entries_dev, "scan_lean: null pointer");
+  return mepp::scan_impl(sym_T_dev, zhat_dev, N, L, T, margin, lut_dev, bias_dev, mlen_dev, nfilt_dev, qtab_dev, qthr_dev,
+                         units_dev, n_units, max_motif_len, nullptr, rowstats_dev, count_dev, density_dev, hits_dev,
+                         hits_cap, hit_count_dev, entries_dev, entry_cap, entry_count_dev, row_nnz_dev, nullptr, nullptr,
+                         nullptr, buckets_dev, bucket_count_dev, stream);
 }
 
 extern "C" int mepp_scan_bitpar_tables(const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev,

@@ -197,6 +197,9 @@ class Engine:
         # bit-parallel first stage of the scan for the units whose expected survivor rate allows it
         # (mepp_scan_bitpar); a unit takes it when its modelled cost is below MEPP_BP_COST_RATIO x the pair tables'
         self.bitpar = os.environ.get("MEPP_SCAN_BITPAR", "0") != "0"
+        # lean scan for the sparse path (mepp_scan_lean): matches only, the blurred entries are built from buckets of
+        # matches by a second kernel
+        self.lean = os.environ.get("MEPP_SCAN_LEAN", "1") != "0"
         self.bp_cost_ratio = float(os.environ.get("MEPP_BP_COST_RATIO", "1.0"))
 
     # ------------------------------------------------------------------ helpers
@@ -721,7 +724,13 @@ class Engine:
                      _ptr(units_d), n_units, int(mlen.max()), _ptr(x_planes), _ptr(rowstats), _ptr(count),
                      _ptr(density), _ptr(hits_d), cap, _ptr(hit_count), _ptr(entries), entry_cap,
                      _ptr(entry_count), _ptr(row_nnz))
-        if bp_d is not None and self.planes_T is not None:
+        if self.lean and path == 'sparse' and not (bp_d is not None and self.planes_T is not None) and L <= 65535:
+            buckets = self._buf(f'buckets{slot}', int(_lib.lib.mepp_scan_lean_bucket_bytes(T, N)), torch.uint8)
+            bucket_count = self._buf(f'bucket_count{slot}', (T * (self.n_pad // 32),), torch.int32)
+            lean_args = scan_args[:15] + scan_args[16:] + (_ptr(buckets), _ptr(bucket_count))   # (no tiled operand)
+            _lib.check(_lib.lib.mepp_scan_lean(*lean_args, st), "scan_lean")
+            self.launches += 2
+        elif bp_d is not None and self.planes_T is not None:
             # units split by class on the device; the bit-parallel units and the pair-table units run as two launches
             bp_scratch = self._buf(f'bp_scratch{slot}', (4 * self.last_units + 2,), torch.int32)
             _lib.check(_lib.lib.mepp_scan_bitpar(*scan_args, _ptr(self.planes_T), _ptr(bp_d), _ptr(bp_scratch), st),
@@ -859,7 +868,8 @@ class Engine:
         pend['done'].synchronize()
         h = {k: v.numpy() for k, v in pend['host'].items()}
         t0, T = pend['t0'], pend['T']
-        if pend['path'] == 'sparse' and int(h['entry_count'][::16].max()) > pend['entry_cap'] // _lib.ENTRY_LISTS:
+        if pend['path'] == 'sparse' and (int(h['entry_count'][::16].max()) > pend['entry_cap'] // _lib.ENTRY_LISTS
+                                          or int(h['entry_count'][1]) != 0):      # ([1]: a lean-scan bucket overflowed)
             # X turned out denser than the entry list allows for: redo this group on the tensor-core path
             redo = self._launch_group(pend['tables'], margin, pend['return_hits'], pend['return_r'], pend['hits_cap'],
                                       ci, pend['slot'], path='tensor')
