@@ -338,10 +338,14 @@ def main():
     if stage_ms.get("scan"):
         # reads 3 bits per base per scan unit (a '+/-' task and its '+' twin share one pass), writes 16 B per match and
         # 16 B per non-zero of X (sparse path) or 32 B per non-zero 8-sequence piece (tiled path, <= one per non-zero)
-        scan_bytes = 0.375 * N * L * st["units"] + 16.0 * st["hits"] + (16.0 if sparse else 32.0) * max(st["entries"], st["hits"])
+        lean = bool(getattr(eng, "lean", False)) and sparse       # matches also go to buckets (8 B each), read back once
+        scan_bytes = (0.375 * N * L * st["units"] + (32.0 if lean else 16.0) * st["hits"]
+                      + (16.0 if sparse else 32.0) * max(st["entries"], st["hits"]))
         a = scan_bytes / per("scan") / 1e9
         kernels["scan"] = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"],
-                               ms_per_step=1e3 * per("scan"), launches_per_step=groups,
+                               ms_per_step=1e3 * per("scan"), launches_per_step=groups * (2 if lean else 1),
+                               form="lean: matches only + entries built from per-(task, k-block) buckets" if lean
+                                    else "full: blur and entries from staging rows inside the scan",
                                gwindows_per_s=N * L * n_local / per("scan") / 1e9,
                                # a scan that writes X once moves 4 B per bp*task; this one emits X as a list of
                                # its non-zeros, so per 8(d) it is reported as compute bound: adds = N * L * m * strands
