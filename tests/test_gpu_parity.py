@@ -740,3 +740,42 @@ def test_bitpar_records_are_sound_for_the_shipped_libraries():
             assert len(mins) >= K and np.sort(mins)[:K].sum() > D, (t, f, K)
         n_used += 1
     assert n_used > len(tasks) // 2 and n_never > 0
+
+
+@pytest.mark.parametrize("N,L,margin,seed,long_run", [(333, 77, 0, 1, True), (333, 150, 2, 2, False),
+                                                      (1000, 201, 5, 3, False), (257, 64, 16, 4, False)])
+def test_lean_scan_equals_full_scan(N, L, margin, seed, long_run):
+    """mepp_scan_lean (matches only + entries built from per-(task, k-block) buckets, the default on the sparse path)
+    against mepp_scan (blur and entries from staging rows): identical matches, counts and densities, r within 1e-6;
+    runs of overlapping matches in one sequence; a long run overflows its bucket and the group falls back to the
+    full scan (then on the tensor path, hence the wider tolerance).  Same cases as tools/gpu_lean_check.py."""
+    from mepp_b200 import synth
+    ascii_u8, scores = synth.synth_sequences(N, L, seed=seed, n_rate=0.02, lower_rate=0.01)
+    if long_run:
+        ascii_u8[6, :] = ord('A')
+    else:
+        ascii_u8[6, 20:32] = ord('A')
+    perm = synth.synth_permutations(N, 13, seed=seed)
+    motifs = synth.synth_motifs(6, seed=seed, m_lo=4, m_hi=min(32, L // 3))
+    cons = np.full((4, 9), 1e-3); cons[0, :] = 1.0
+    motifs.append(cons / cons.sum(axis=0))
+    tasks = [(m, o) for m in motifs for o in ('+', '+/-')] + [(motifs[0], '-')]
+    res, paths = [], []
+    for lean in (False, True):
+        eng = _engine()
+        eng.lean = lean
+        eng.stage(ascii_u8, scores, perm)
+        res.append(eng.profile(tasks, margin=margin, return_hits=True, return_r=True))
+        paths.append(list(eng.last_paths))
+    full, lean = res
+    assert paths[0] == ['sparse'] and paths[1] == (['sparse', 'tensor'] if long_run else ['sparse'])
+    assert len(full.hits) > 20
+    assert np.array_equal(full.hits, lean.hits)
+    assert np.array_equal(full.density, lean.density)
+    assert np.array_equal(np.asarray(full.positions['count']), np.asarray(lean.positions['count']))
+    tol = dict(rtol=1e-6, atol=1e-9) if paths[0] == paths[1] else dict(rtol=1e-4, atol=1e-6)
+    assert np.allclose(full.r, lean.r, **tol)
+    codes = staging.ascii_to_codes(ascii_u8)
+    for t in (0, 1, len(tasks) - 3, len(tasks) - 2):
+        Wf, Wr, thr = profile.motif_weights(*tasks[t])
+        assert np.array_equal(lean.motif_score_matrix(t, L).view(np.uint32), profile.scan(codes, Wf, Wr, thr).view(np.uint32)), t
