@@ -345,3 +345,23 @@ def test_prepare_tables_matches_per_task_tables():
         # the DP inputs reproduce the host threshold when run through the host DP semantics
         R = prep['dp_par'][:, 7]
         assert (R >= 0).all() and (prep['smat'] >= 0).all()
+
+
+def test_match_driven_blur_is_bit_identical_to_the_dense_blur():
+    """The lean scan builds the blurred entries from the sorted match list (bucket_entries_kernel in csrc/scan.cu);
+    tools/proto_match_blur.py is its numpy form: identical bits to the dense float32 blur of core.py:59-145
+    (sequential sum in position order, IEEE division), for isolated and overlapping matches, zeroed edges included,
+    and against the oracle's blur for margins 0 ... 16."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("proto_match_blur", os.path.join(here, "..", "tools", "proto_match_blur.py"))
+    proto = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(proto)
+    from oracle import profile
+    for margin in (0, 1, 2, 5, 16):
+        assert proto._check(margin=margin, seed=margin) > 0
+        rng = np.random.default_rng(100 + margin)
+        X0 = np.where(rng.random((40, 97)) < 0.01, rng.gamma(2.0, 1.0, size=(40, 97)), 0.0).astype(np.float32)
+        dense = proto.dense_blur_f32(X0, margin)
+        assert np.allclose(dense, profile.blur(X0, margin, dtype=np.float64), rtol=3e-7, atol=0)
