@@ -395,7 +395,7 @@ def main():
                     peak_source=peaks["source"],
                     note="achieved = algorithmic bytes (3 bits per base per scan unit read, 16 B per match and per non-zero of "
                          "X written) / CUDA-event time of the launches; the kernel is bound by integer issue, not by HBM "
-                         "(DESIGN.md section 4); traffic = DRAM bytes of one launch from the committed ncu capture")
+                         "(DESIGN.md section 4); traffic = DRAM bytes of one launch from the committed ncu capture (full-form kernel)")
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
