@@ -204,6 +204,19 @@ int mepp_scan_lean(const uint32_t* sym_T_dev, const float* zhat_dev,
                    void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
                    void* buckets_dev, int32_t* bucket_count_dev, void* stream);
 
+/* Both options together (experimental, not yet validated on a GPU; MEPP_SCAN_BITPAR_LEAN=1): arguments of
+ * mepp_scan_lean plus the three bit-parallel ones of mepp_scan_bitpar. */
+int mepp_scan_bitpar_lean(const uint32_t* sym_T_dev, const float* zhat_dev,
+                          int64_t N, int L, int T, int margin,
+                          const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev, const int32_t* nfilt_dev,
+                          const uint32_t* qtab_dev, const uint32_t* qthr_dev, const int32_t* units_dev, int n_units,
+                          int max_motif_len,
+                          double* rowstats_dev, int32_t* count_dev, int32_t* density_dev,
+                          void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
+                          void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
+                          const uint32_t* planes_T_dev, const uint32_t* bp_dev, int32_t* bp_scratch_dev,
+                          void* buckets_dev, int32_t* bucket_count_dev, void* stream);
+
 /* Restore the all-zero state of an A operand that mepp_scan(..., N, L, T, margin, ...) wrote, from the
  * match list of that call (every match dirties rows pos-margin..pos+margin of one 8-column group); a NULL
  * or overflowed list clears the whole operand instead.  Call after the operand's last consumer. */

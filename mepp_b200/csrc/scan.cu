@@ -1166,7 +1166,7 @@ static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
   a.entry_count = entry_count_dev; a.row_nnz = row_nnz_dev;
   a.planes_T = planes_T_dev; a.bp = bp_dev; a.unit_count = nullptr;
   const bool lean = buckets_dev != nullptr;
-  MEPP_REQUIRE(!lean || (bucket_count_dev && entries_dev && !x_planes_dev && L <= 65535 && !bitpar),
+  MEPP_REQUIRE(!lean || (bucket_count_dev && entries_dev && !x_planes_dev && L <= 65535),
                "scan_lean: needs the bucket counters and the entry list, no tiled operand, L <= 65535");
   a.lean = lean ? 1 : 0; a.buckets = reinterpret_cast<uint2*>(buckets_dev); a.bucket_count = bucket_count_dev;
   const int nbuf = 32 + 2 * margin;
@@ -1228,6 +1228,13 @@ static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
   a.units = lists; a.unit_count = counts;
   scan_kernel<false><<<grid, kScanWarps * 32, smem, st>>>(a);
   MEPP_CUDA_CHECK(cudaGetLastError());
+  if (lean) {
+    const int64_t n_buckets = (int64_t)T * a.KB;
+    bucket_entries_kernel<<<(unsigned)((n_buckets + 3) / 4), 128, 0, st>>>(
+        a.buckets, bucket_count_dev, n_buckets, a.KB, L, margin, N, zhat_dev, a.entries, a.sub_cap, entry_count_dev,
+        row_nnz_dev, rowstats_dev);
+    MEPP_CUDA_CHECK(cudaGetLastError());
+  }
   return 0;
 }
 }  // namespace mepp
@@ -1291,4 +1298,24 @@ extern "C" int mepp_scan_bitpar_tables(const float* lut_dev, const float* bias_d
                                                                            cost_ratio, bp_dev);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+// Both options together (experimental, MEPP_SCAN_BITPAR_LEAN=1; written at the end of round 1 and NOT yet run on a
+// GPU): the bit-parallel first stage on top of the lean form.
+extern "C" int mepp_scan_bitpar_lean(const uint32_t* sym_T_dev, const float* zhat_dev,
+                                     int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
+                                     const int32_t* mlen_dev, const int32_t* nfilt_dev, const uint32_t* qtab_dev,
+                                     const uint32_t* qthr_dev, const int32_t* units_dev, int n_units, int max_motif_len,
+                                     double* rowstats_dev, int32_t* count_dev,
+                                     int32_t* density_dev, void* hits_dev, int64_t hits_cap,
+                                     unsigned long long* hit_count_dev, void* entries_dev, int64_t entry_cap,
+                                     unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
+                                     const uint32_t* planes_T_dev, const uint32_t* bp_dev, int32_t* bp_scratch_dev,
+                                     void* buckets_dev, int32_t* bucket_count_dev, void* stream) {
+  MEPP_REQUIRE(planes_T_dev && bp_dev && bp_scratch_dev && buckets_dev && bucket_count_dev && entries_dev,
+               "scan_bitpar_lean: null pointer");
+  return mepp::scan_impl(sym_T_dev, zhat_dev, N, L, T, margin, lut_dev, bias_dev, mlen_dev, nfilt_dev, qtab_dev, qthr_dev,
+                         units_dev, n_units, max_motif_len, nullptr, rowstats_dev, count_dev, density_dev, hits_dev,
+                         hits_cap, hit_count_dev, entries_dev, entry_cap, entry_count_dev, row_nnz_dev, planes_T_dev,
+                         bp_dev, bp_scratch_dev, buckets_dev, bucket_count_dev, stream);
 }

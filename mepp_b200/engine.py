@@ -724,7 +724,18 @@ class Engine:
                      _ptr(units_d), n_units, int(mlen.max()), _ptr(x_planes), _ptr(rowstats), _ptr(count),
                      _ptr(density), _ptr(hits_d), cap, _ptr(hit_count), _ptr(entries), entry_cap,
                      _ptr(entry_count), _ptr(row_nnz))
-        if self.lean and path == 'sparse' and not (bp_d is not None and self.planes_T is not None) and L <= 65535:
+        if (self.lean and path == 'sparse' and bp_d is not None and self.planes_T is not None and L <= 2016
+                and os.environ.get("MEPP_SCAN_BITPAR_LEAN", "0") != "0"):
+            # experimental, not yet validated on a GPU: bit-parallel first stage on top of the lean form
+            buckets = self._buf(f'buckets{slot}', int(_lib.lib.mepp_scan_lean_bucket_bytes(T, N)), torch.uint8)
+            bucket_count = self._buf(f'bucket_count{slot}', (T * (self.n_pad // 32),), torch.int32)
+            bp_scratch = self._buf(f'bp_scratch{slot}', (4 * self.last_units + 2,), torch.int32)
+            both_args = scan_args[:15] + scan_args[16:] + (_ptr(self.planes_T), _ptr(bp_d), _ptr(bp_scratch),
+                                                           _ptr(buckets), _ptr(bucket_count))
+            _lib.check(_lib.lib.mepp_scan_bitpar_lean(*both_args, st), "scan_bitpar_lean")
+            self.launches += 4
+            self.last_bp = (bp_d, bp_scratch, self.last_units)
+        elif self.lean and path == 'sparse' and not (bp_d is not None and self.planes_T is not None) and L <= 65535:
             buckets = self._buf(f'buckets{slot}', int(_lib.lib.mepp_scan_lean_bucket_bytes(T, N)), torch.uint8)
             bucket_count = self._buf(f'bucket_count{slot}', (T * (self.n_pad // 32),), torch.int32)
             lean_args = scan_args[:15] + scan_args[16:] + (_ptr(buckets), _ptr(bucket_count))   # (no tiled operand)
