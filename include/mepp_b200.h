@@ -204,18 +204,30 @@ int mepp_scan_lean(const uint32_t* sym_T_dev, const float* zhat_dev,
                    void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
                    void* buckets_dev, int32_t* bucket_count_dev, void* stream);
 
-/* Both options together (experimental, not yet validated on a GPU; MEPP_SCAN_BITPAR_LEAN=1): arguments of
- * mepp_scan_lean plus the three bit-parallel ones of mepp_scan_bitpar. */
-int mepp_scan_bitpar_lean(const uint32_t* sym_T_dev, const float* zhat_dev,
-                          int64_t N, int L, int T, int margin,
-                          const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev, const int32_t* nfilt_dev,
-                          const uint32_t* qtab_dev, const uint32_t* qthr_dev, const int32_t* units_dev, int n_units,
-                          int max_motif_len,
-                          double* rowstats_dev, int32_t* count_dev, int32_t* density_dev,
-                          void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
-                          void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
-                          const uint32_t* planes_T_dev, const uint32_t* bp_dev, int32_t* bp_scratch_dev,
-                          void* buckets_dev, int32_t* bucket_count_dev, void* stream);
+/* ---- tensor-core first stage of the lean scan (default on the sparse path; MEPP_SCAN_TC=0 switches back) ----
+ * Replaces the same reference code as mepp_scan (the Keras Conv1D of mepp/motif_layers.py:50-76, 80-165): the
+ * convolution over the one-hot sequence runs as tcgen05.mma.kind::i8 products of the flat one-hot stream
+ * (mepp_pack_onehot: 4 bytes per base, overlapping 16-byte-strided rows = windows four bases apart) with conservatively
+ * quantised int8 weights (4 window phases x 2 strands x units as columns); only the sign of the int32 accumulators is
+ * read back from TMEM.  The filter has no false negatives; its survivors are scored in the canonical float32 order and
+ * published exactly like mepp_scan_lean's matches (same outputs, same bucket / entry / rowstats contract, same
+ * overflow flag in entry_count_dev[1]).
+ * onehot_dev: mepp_onehot_words(N, L) uint32.  units_host / mlen_host: host copies of the unit list (null = one unit per
+ * task, like units_dev) and of the motif lengths of all T tasks (the N-tile plan is made on the host).
+ * work_dev: mepp_scan_tc_work_bytes(N, L, units) bytes of scratch (weights, candidate lists).
+ * dbg_acc_dev (optional, int32 [128][dbg_ld]): raw accumulators of the first 128 windows, for bring-up tests. */
+int64_t mepp_onehot_words(int64_t N, int L);
+int mepp_pack_onehot(const uint8_t* ascii_dev, int64_t N, int L, uint32_t* onehot_dev, void* stream);
+int64_t mepp_scan_tc_work_bytes(int64_t N, int L, int n_units);
+int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_dev, const float* zhat_dev,
+                 int64_t N, int L, int T, int margin,
+                 const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev, const int32_t* nfilt_dev,
+                 const int32_t* units_dev, const int32_t* units_host, int n_units, const int32_t* mlen_host,
+                 double* rowstats_dev, int32_t* count_dev, int32_t* density_dev,
+                 void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
+                 void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
+                 void* buckets_dev, int32_t* bucket_count_dev, void* work_dev, int64_t work_bytes,
+                 int32_t* dbg_acc_dev, int dbg_ld, void* stream);
 
 /* Restore the all-zero state of an A operand that mepp_scan(..., N, L, T, margin, ...) wrote, from the
  * match list of that call (every match dirties rows pos-margin..pos+margin of one 8-column group); a NULL

@@ -56,8 +56,11 @@ SIGNATURES = {
     "mepp_scan_lean_bucket_bytes": (_i64, [_i32, _i64]),
     "mepp_scan_lean": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                               _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "mepp_scan_bitpar_lean": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
-                                     _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mepp_onehot_words": (_i64, [_i64, _i32]),
+    "mepp_pack_onehot": (_i32, [_vp, _i64, _i32, _vp, _vp]),
+    "mepp_scan_tc_work_bytes": (_i64, [_i64, _i32, _i32]),
+    "mepp_scan_tc": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
+                            _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp]),
     "mepp_y_rows_ld": (_i64, [_i32]),
     "mepp_build_y_rows": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "mepp_profile_sparse_work_bytes": (_i64, [_i64, _i64]),

@@ -33,6 +33,7 @@
 // evaluation and the same phase B.  Identical outputs; measured slower on cfg 2, off by default.
 #include <stdlib.h>
 #include "common.cuh"
+#include "tcscan.cuh"
 
 namespace mepp {
 
@@ -1166,8 +1167,8 @@ static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
   a.entry_count = entry_count_dev; a.row_nnz = row_nnz_dev;
   a.planes_T = planes_T_dev; a.bp = bp_dev; a.unit_count = nullptr;
   const bool lean = buckets_dev != nullptr;
-  MEPP_REQUIRE(!lean || (bucket_count_dev && entries_dev && !x_planes_dev && L <= 65535),
-               "scan_lean: needs the bucket counters and the entry list, no tiled operand, L <= 65535");
+  MEPP_REQUIRE(!lean || (bucket_count_dev && entries_dev && !x_planes_dev && !bitpar && L <= 65535),
+               "scan_lean: needs the bucket counters and the entry list, no tiled operand, no bit planes, L <= 65535");
   a.lean = lean ? 1 : 0; a.buckets = reinterpret_cast<uint2*>(buckets_dev); a.bucket_count = bucket_count_dev;
   const int nbuf = 32 + 2 * margin;
   auto smem_bytes = [&](bool bp) {
@@ -1300,22 +1301,211 @@ extern "C" int mepp_scan_bitpar_tables(const float* lut_dev, const float* bias_d
   return 0;
 }
 
-// Both options together (experimental, MEPP_SCAN_BITPAR_LEAN=1; written at the end of round 1 and NOT yet run on a
-// GPU): the bit-parallel first stage on top of the lean form.
-extern "C" int mepp_scan_bitpar_lean(const uint32_t* sym_T_dev, const float* zhat_dev,
-                                     int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
-                                     const int32_t* mlen_dev, const int32_t* nfilt_dev, const uint32_t* qtab_dev,
-                                     const uint32_t* qthr_dev, const int32_t* units_dev, int n_units, int max_motif_len,
-                                     double* rowstats_dev, int32_t* count_dev,
-                                     int32_t* density_dev, void* hits_dev, int64_t hits_cap,
-                                     unsigned long long* hit_count_dev, void* entries_dev, int64_t entry_cap,
-                                     unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
-                                     const uint32_t* planes_T_dev, const uint32_t* bp_dev, int32_t* bp_scratch_dev,
-                                     void* buckets_dev, int32_t* bucket_count_dev, void* stream) {
-  MEPP_REQUIRE(planes_T_dev && bp_dev && bp_scratch_dev && buckets_dev && bucket_count_dev && entries_dev,
-               "scan_bitpar_lean: null pointer");
-  return mepp::scan_impl(sym_T_dev, zhat_dev, N, L, T, margin, lut_dev, bias_dev, mlen_dev, nfilt_dev, qtab_dev, qthr_dev,
-                         units_dev, n_units, max_motif_len, nullptr, rowstats_dev, count_dev, density_dev, hits_dev,
-                         hits_cap, hit_count_dev, entries_dev, entry_cap, entry_count_dev, row_nnz_dev, planes_T_dev,
-                         bp_dev, bp_scratch_dev, buckets_dev, bucket_count_dev, stream);
+
+// ---- tensor-core first stage (tcscan.cu) + exact evaluation of its candidates ----------------------------------
+namespace mepp {
+// One thread per candidate {row, unit << 2 | phase}: the window starts at flat base 4 row + phase of the one-hot
+// stream, i.e. at base i of sequence seq; windows that run over the end of their sequence (or of the data) and the
+// padding unit slots of an N-tile are dropped here.  Survivors are scored in the canonical float32 order
+// (exact_x0's order: taps ascending, one add per base, four quarter-weight adds for N, bias last) and published
+// exactly like the lean scan's matches (buckets, counts, densities, match list).
+__global__ void __launch_bounds__(128) tc_exact_kernel(const ScanArgs a, const uint2* __restrict__ cand,
+                                                       const uint32_t* __restrict__ cand_count, uint32_t list_cap,
+                                                       int unit_base, int n_units_launch) {
+  const int64_t list = blockIdx.x;
+  uint32_t cnt = cand_count[list];
+  if (cnt > list_cap) {
+    if (threadIdx.x == 0) atomicAdd(a.entry_count + 1, 1ull);     // overflow: the caller redoes the group (like a bucket)
+    cnt = list_cap;
+  }
+  const uint2* my = cand + list * (int64_t)list_cap;
+  for (uint32_t idx = threadIdx.x; idx < cnt; idx += blockDim.x) {
+    const uint2 rec = my[idx];
+    const int ul = (int)(rec.y >> 2), phi = (int)(rec.y & 3u);
+    if (ul >= n_units_launch) continue;
+    const int u = unit_base + ul;
+    const int t = a.units ? a.units[2 * u] : u;
+    const int t2 = a.units ? a.units[2 * u + 1] : -1;
+    const int m = a.mlen[t];
+    const int64_t b = 4 * (int64_t)rec.x + phi;
+    const int64_t seq = b / a.L;
+    const int i = (int)(b - seq * a.L);
+    if (seq >= a.N || i + m > a.L) continue;
+    // exact scores of both filters
+    const uint32_t* gsym = a.sym_T + seq;
+    const int bit0 = 3 * i, w0 = bit0 >> 5, sh = bit0 & 31;
+    uint32_t x[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) x[k] = __ldg(gsym + (int64_t)(w0 + k) * a.n_pad);
+    uint32_t r0 = __funnelshift_r(x[0], x[1], sh), r1 = __funnelshift_r(x[1], x[2], sh),
+             r2 = __funnelshift_r(x[2], x[3], sh), r3 = __funnelshift_r(x[3], x[4], sh);
+    const float2* lut = reinterpret_cast<const float2*>(a.lut) + (size_t)t * (MEPP_MAX_MOTIF_LEN * 4);
+    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll 1
+    for (int j = 0; j < m; ++j) {
+      const uint32_t sym = r0 & 7u;
+      r0 = __funnelshift_r(r0, r1, 3); r1 = __funnelshift_r(r1, r2, 3); r2 = __funnelshift_r(r2, r3, 3); r3 >>= 3;
+      const float2* l4 = lut + j * 4;
+      if (sym >= 4u) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float2 w = __ldg(l4 + cc);
+          a0 = __fadd_rn(a0, __fmul_rn(0.25f, w.x));
+          a1 = __fadd_rn(a1, __fmul_rn(0.25f, w.y));
+        }
+      } else {
+        const float2 w = __ldg(l4 + sym);
+        a0 = __fadd_rn(a0, w.x);
+        a1 = __fadd_rn(a1, w.y);
+      }
+    }
+    const float bias = a.bias[t];
+    float sc = __fadd_rn(a0, bias);
+    const float x_first = fmaxf(sc, 0.0f);
+    if (a.nfilt[t] == 2) sc = fmaxf(sc, __fadd_rn(a1, bias));
+    const float x_task = fmaxf(sc, 0.0f);
+    const int p = i + (m - 1) / 2;                 // motif_layers.py:99-101
+    const int kb = (int)(seq >> 5), s = (int)(seq & 31);
+    auto publish = [&](int tt, float x0) {
+      const int64_t bkt = (int64_t)tt * a.KB + kb;
+      const int slot = atomicAdd(&a.bucket_count[bkt], 1);
+      if (slot < kBucketCap) a.buckets[bkt * kBucketCap + slot] = make_uint2(((uint32_t)s << 16) | (uint32_t)p, __float_as_uint(x0));
+      atomicAdd(&a.count[(int64_t)tt * a.L + p], 1);
+      atomicAdd(&a.density[(int64_t)tt * a.n_pad + seq], 1);
+      if (a.hit_count) {
+        const unsigned long long hs = atomicAdd(a.hit_count, 1ull);
+        if (a.hits && (int64_t)hs < a.hits_cap) {
+          HitRec h; h.task = tt; h.seq = (int32_t)seq; h.pos = p; h.x0 = x0;
+          a.hits[hs] = h;
+        }
+      }
+    };
+    if (x_task > 0.0f) publish(t, x_task);
+    if (t2 >= 0 && x_first > 0.0f) publish(t2, x_first);
+  }
+}
+}  // namespace mepp
+
+extern "C" int64_t mepp_scan_tc_work_bytes(int64_t N, int L, int n_units) {
+  using namespace mepp;
+  // weight operands of every launch (<= 8 columns x 160 channels per unit, plus tile padding), candidate lists, counters
+  const int64_t lists = 148 * 2 * kTcEpiWarps;                        // (up to 2x the SM count of a B200)
+  const double expect = (double)N * (double)L * (double)(n_units < 256 ? n_units : 256) * 4e-3 / (148.0 * kTcEpiWarps);
+  int64_t cap = (int64_t)expect + 2048;
+  if (cap > (1 << 22)) cap = 1 << 22;
+  return 1024 + (int64_t)(n_units + n_units / 8 + 64) * 8 * 160 + lists * 16 + lists * cap * 8 + 1024;
+}
+
+extern "C" int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_dev, const float* zhat_dev,
+                            int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
+                            const int32_t* mlen_dev, const int32_t* nfilt_dev, const int32_t* units_dev,
+                            const int32_t* units_host, int n_units, const int32_t* mlen_host,
+                            double* rowstats_dev, int32_t* count_dev, int32_t* density_dev, void* hits_dev,
+                            int64_t hits_cap, unsigned long long* hit_count_dev, void* entries_dev, int64_t entry_cap,
+                            unsigned long long* entry_count_dev, int32_t* row_nnz_dev, void* buckets_dev,
+                            int32_t* bucket_count_dev, void* work_dev, int64_t work_bytes, int32_t* dbg_acc_dev, int dbg_ld,
+                            void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(sym_T_dev && onehot_dev && lut_dev && bias_dev && mlen_dev && nfilt_dev && mlen_host && rowstats_dev &&
+               count_dev && density_dev && entries_dev && entry_count_dev && row_nnz_dev && buckets_dev &&
+               bucket_count_dev && work_dev, "scan_tc: null pointer");
+  MEPP_REQUIRE(N > 0 && L > 0 && T > 0 && L <= 65535, "scan_tc: bad sizes (L <= 65535)");
+  MEPP_REQUIRE((units_dev == nullptr) == (units_host == nullptr), "scan_tc: the unit list is needed on both sides");
+  MEPP_REQUIRE(units_dev == nullptr || (n_units > 0 && n_units <= T), "scan_tc: bad unit list");
+  MEPP_REQUIRE((int64_t)T * L < (1LL << 31), "scan_tc: T * L must be below 2^31");
+  MEPP_REQUIRE(margin >= 0 && margin <= MEPP_MAX_MARGIN, "scan_tc: margin must be in [0, 16]");
+  MEPP_REQUIRE(entry_cap >= MEPP_ENTRY_LISTS && entry_cap % MEPP_ENTRY_LISTS == 0, "scan_tc: bad entry capacity");
+  MEPP_REQUIRE(hits_dev == nullptr || hit_count_dev != nullptr, "scan_tc: hits need a hit counter");
+  MEPP_REQUIRE(N * (int64_t)L / 4 < (1LL << 32), "scan_tc: N * L must be below 2^34");
+  MEPP_REQUIRE(mepp_device_ok(), "scan_tc: no sm_100 CUDA device (no CPU fallback)");
+  cudaStream_t st = as_stream(stream);
+  const int U = units_dev ? n_units : T;
+  MEPP_REQUIRE(work_bytes >= mepp_scan_tc_work_bytes(N, L, U), "scan_tc: work buffer too small");
+  ScanArgs a;
+  a.sym_T = sym_T_dev; a.zhat = zhat_dev;
+  a.N = N; a.n_pad = mepp_pad32(N); a.KB = a.n_pad / kBlockK;
+  a.L = L; a.T = T; a.margin = margin; a.W3 = (int)mepp_sym_words(L); a.qslots = 0;
+  a.lut = lut_dev; a.bias = bias_dev; a.mlen = mlen_dev; a.nfilt = nfilt_dev; a.qtab = nullptr; a.qthr = nullptr;
+  a.units = units_dev; a.U = U;
+  a.x_planes = nullptr; a.rowstats = rowstats_dev; a.count = count_dev; a.density = density_dev;
+  a.hits = reinterpret_cast<HitRec*>(hits_dev); a.hits_cap = hits_cap; a.hit_count = hit_count_dev;
+  a.entries = reinterpret_cast<XEntry*>(entries_dev); a.sub_cap = entry_cap / MEPP_ENTRY_LISTS;
+  a.entry_count = entry_count_dev; a.row_nnz = row_nnz_dev;
+  a.planes_T = nullptr; a.bp = nullptr; a.unit_count = nullptr;
+  a.lean = 1; a.buckets = reinterpret_cast<uint2*>(buckets_dev); a.bucket_count = bucket_count_dev;
+  MEPP_CUDA_CHECK(cudaMemsetAsync(rowstats_dev, 0, sizeof(double) * 3 * (size_t)T * L, st));
+  MEPP_CUDA_CHECK(cudaMemsetAsync(count_dev, 0, sizeof(int32_t) * (size_t)T * L, st));
+  MEPP_CUDA_CHECK(cudaMemsetAsync(density_dev, 0, sizeof(int32_t) * (size_t)T * a.n_pad, st));
+  if (hit_count_dev) MEPP_CUDA_CHECK(cudaMemsetAsync(hit_count_dev, 0, sizeof(unsigned long long), st));
+  MEPP_CUDA_CHECK(cudaMemsetAsync(entry_count_dev, 0, sizeof(unsigned long long) * 16 * MEPP_ENTRY_LISTS, st));
+  MEPP_CUDA_CHECK(cudaMemsetAsync(row_nnz_dev, 0, sizeof(int32_t) * ((size_t)T * L + 1), st));
+  MEPP_CUDA_CHECK(cudaMemsetAsync(bucket_count_dev, 0, sizeof(int32_t) * (size_t)T * a.KB, st));
+  // work buffer: [weights][counters][candidate lists]
+  const int grid = tc_scan_grid();
+  const int64_t lists = (int64_t)grid * kTcEpiWarps;
+  uint8_t* wk = reinterpret_cast<uint8_t*>(work_dev);
+  wk += (1024 - (reinterpret_cast<uintptr_t>(wk) & 1023)) & 1023;
+  uint8_t* B_dev = wk;
+  const int64_t b_region = ((int64_t)(U + U / 8 + 64) * 8 * 160 + 1023) / 1024 * 1024;
+  uint32_t* counts_dev = reinterpret_cast<uint32_t*>(wk + b_region);
+  uint2* cand_dev = reinterpret_cast<uint2*>(wk + b_region + ((lists * 4 + 1023) / 1024 * 1024));
+  const int64_t cand_bytes = work_bytes - (reinterpret_cast<uint8_t*>(cand_dev) - reinterpret_cast<uint8_t*>(work_dev));
+  int64_t cap64 = cand_bytes / (lists * 8);
+  MEPP_REQUIRE(cap64 >= 256, "scan_tc: work buffer too small for the candidate lists");
+  if (cap64 > (1 << 22)) cap64 = 1 << 22;
+  TcScanArgs g;
+  g.onehot = reinterpret_cast<const uint8_t*>(onehot_dev);
+  g.n_mtiles = (N * (int64_t)L + kTcBasesPerTile - 1) / kTcBasesPerTile;
+  g.cand = cand_dev; g.cand_count = counts_dev; g.list_cap = (uint32_t)cap64;
+  g.dbg_acc = dbg_acc_dev; g.dbg_ld = dbg_ld;
+  // launches: consecutive units, <= 32 per N-tile, <= kTcMaxTiles tiles and <= kTcMaxBBytes of weights per launch
+  int u0 = 0;
+  int64_t b_used = 0;
+  while (u0 < U) {
+    TcLaunch ln;
+    ln.n_tiles = 0; ln.ks_max = 1; ln.b_bytes = 0;
+    int u = u0;
+    while (u < U && ln.n_tiles < kTcMaxTiles) {
+      const int nu = U - u < 32 ? U - u : 32;
+      int mmax = 1;
+      for (int k = 0; k < nu; ++k) {
+        const int t = units_host ? units_host[2 * (u + k)] : u + k;
+        MEPP_REQUIRE(t >= 0 && t < T, "scan_tc: unit list refers to a task outside [0, T)");
+        const int m = mlen_host[t];
+        MEPP_REQUIRE(m >= 1 && m <= MEPP_MAX_MOTIF_LEN, "scan_tc: motif length outside [1, 32]");
+        if (m > mmax) mmax = m;
+      }
+      TcTile tl;
+      tl.ksteps = (uint16_t)((4 * (mmax + 3) + 31) / 32);
+      tl.bn = (uint16_t)(32 * ((nu + 3) / 4));
+      tl.unit0 = (uint16_t)(u - u0);
+      tl.n_units = (uint16_t)nu;
+      tl.b_off = ln.b_bytes;
+      const uint32_t bytes = (uint32_t)tl.ksteps * 2u * tl.bn * 16u;
+      if (ln.b_bytes + bytes > (uint32_t)kTcMaxBBytes) break;
+      ln.b_bytes += bytes;
+      if (tl.ksteps > ln.ks_max) ln.ks_max = tl.ksteps;
+      ln.tiles[ln.n_tiles++] = tl;
+      u += nu;
+    }
+    MEPP_REQUIRE(ln.n_tiles > 0, "scan_tc: a tile does not fit the weight operand");
+    for (int k = ln.n_tiles; k < kTcMaxTiles; ++k) { ln.tiles[k].b_off = 0; ln.tiles[k].ksteps = 0; ln.tiles[k].bn = 0; ln.tiles[k].unit0 = 0; ln.tiles[k].n_units = 0; }
+    MEPP_REQUIRE(b_used + ln.b_bytes <= b_region, "scan_tc: weight region overflow");
+    uint8_t* B_launch = B_dev + b_used;
+    b_used += ((int64_t)ln.b_bytes + 1023) / 1024 * 1024;
+    if (tc_build_weights(ln, lut_dev, bias_dev, mlen_dev, nfilt_dev, units_dev, u0, U, B_launch, st)) return 1;
+    g.B = B_launch;
+    if (tc_scan_launch(ln, g, st)) return 1;
+    int n_lists = grid;
+    if ((int64_t)n_lists > g.n_mtiles) n_lists = (int)g.n_mtiles;
+    tc_exact_kernel<<<(unsigned)(n_lists * kTcEpiWarps), 128, 0, st>>>(a, g.cand, g.cand_count, g.list_cap, u0, u - u0);
+    MEPP_CUDA_CHECK(cudaGetLastError());
+    u0 = u;
+  }
+  const int64_t n_buckets = (int64_t)T * a.KB;
+  bucket_entries_kernel<<<(unsigned)((n_buckets + 3) / 4), 128, 0, st>>>(
+      a.buckets, bucket_count_dev, n_buckets, a.KB, L, margin, N, zhat_dev, a.entries, a.sub_cap, entry_count_dev,
+      row_nnz_dev, rowstats_dev);
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
 }

@@ -186,6 +186,7 @@ class Engine:
         self.share_scans = os.environ.get("MEPP_SHARE_SCANS", "1") != "0"   # '+' rides on the '+/-' pass of its motif
         self.profile_path = os.environ.get("MEPP_PROFILE_PATH", "auto")     # 'auto' | 'sparse' | 'tensor'
         self.last_paths = []
+        self.fallbacks = []
         from .parallel import host_threads
         self.copy_threads = int(os.environ.get("MEPP_COPY_THREADS", str(max(1, min(4, host_threads())))))
         self.device_tables = os.environ.get("MEPP_DEVICE_TABLES", "1") != "0"   # threshold DP on the GPU
@@ -200,6 +201,8 @@ class Engine:
         # lean scan for the sparse path (mepp_scan_lean): matches only, the blurred entries are built from buckets of
         # matches by a second kernel
         self.lean = os.environ.get("MEPP_SCAN_LEAN", "1") != "0"
+        # tensor-core first stage of the lean scan (mepp_scan_tc: tcgen05 int8 products over the one-hot stream)
+        self.tc_scan = os.environ.get("MEPP_SCAN_TC", "1") != "0"
         self.bp_cost_ratio = float(os.environ.get("MEPP_BP_COST_RATIO", "1.0"))
 
     # ------------------------------------------------------------------ helpers
@@ -244,6 +247,11 @@ class Engine:
             self.sym_T = torch.empty((W3, self.n_pad), dtype=torch.int32, device=self.device)
             self.gc = torch.empty(self.n_pad, dtype=torch.float32, device=self.device)
             _lib.check(_lib.lib.mepp_pack_dna(_ptr(ascii_d), N, L, _ptr(self.sym_T), _ptr(self.gc), st), "pack_dna")
+            self.onehot = None
+            if self.tc_scan and self.lean and L <= 65535:
+                self.onehot = torch.empty(int(_lib.lib.mepp_onehot_words(N, L)), dtype=torch.int32, device=self.device)
+                _lib.check(_lib.lib.mepp_pack_onehot(_ptr(ascii_d), N, L, _ptr(self.onehot), st), "pack_onehot")
+                self.launches += 1
             self.planes_T = None
             if self.bitpar:
                 WB = int(_lib.lib.mepp_plane_words(L))
@@ -663,12 +671,13 @@ class Engine:
             self._pins[key] = cur
         return cur[:need].view(tuple(int(x) for x in shape))
 
-    def _launch_group(self, tables, margin, return_hits, return_r, hits_cap, ci, slot, path=None):
+    def _launch_group(self, tables, margin, return_hits, return_r, hits_cap, ci, slot, path=None, lean=None):
         """Enqueue every kernel of one task group plus the D2H copies of its results (no host sync)."""
         torch = self.torch
         T = len(tables)
         path = path or self.choose_path(tables, margin)
         self.last_paths.append(path)
+        use_lean = self.lean if lean is None else bool(lean)
         L, N, C_, P = self.L, self.N, self.C, self.P
         st = self._stream()
         self._reset_x_planes()     # before any scratch buffer of the previous group is reused
@@ -697,6 +706,7 @@ class Engine:
         units_d = self._to_dev(units) if units is not None else None
         n_units = len(units) if units is not None else 0
         self.last_units = n_units if units is not None else T
+        self._last_units_arr = units
         self._units_run = getattr(self, '_units_run', 0) + self.last_units
         x_planes = entries = entry_count = row_nnz = None
         entry_cap = 0
@@ -724,24 +734,31 @@ class Engine:
                      _ptr(units_d), n_units, int(mlen.max()), _ptr(x_planes), _ptr(rowstats), _ptr(count),
                      _ptr(density), _ptr(hits_d), cap, _ptr(hit_count), _ptr(entries), entry_cap,
                      _ptr(entry_count), _ptr(row_nnz))
-        if (self.lean and path == 'sparse' and bp_d is not None and self.planes_T is not None and L <= 2016
-                and os.environ.get("MEPP_SCAN_BITPAR_LEAN", "0") != "0"):
-            # experimental, not yet validated on a GPU: bit-parallel first stage on top of the lean form
+        bitpar_on = bp_d is not None and self.planes_T is not None      # (the experimental first stage keeps its own path)
+        if use_lean and self.tc_scan and path == 'sparse' and getattr(self, 'onehot', None) is not None and not bitpar_on:
             buckets = self._buf(f'buckets{slot}', int(_lib.lib.mepp_scan_lean_bucket_bytes(T, N)), torch.uint8)
             bucket_count = self._buf(f'bucket_count{slot}', (T * (self.n_pad // 32),), torch.int32)
-            bp_scratch = self._buf(f'bp_scratch{slot}', (4 * self.last_units + 2,), torch.int32)
-            both_args = scan_args[:15] + scan_args[16:] + (_ptr(self.planes_T), _ptr(bp_d), _ptr(bp_scratch),
-                                                           _ptr(buckets), _ptr(bucket_count))
-            _lib.check(_lib.lib.mepp_scan_bitpar_lean(*both_args, st), "scan_bitpar_lean")
+            wbytes = int(_lib.lib.mepp_scan_tc_work_bytes(N, L, self.last_units))
+            tc_work = self._buf('tc_work', wbytes, torch.uint8)
+            units_h = np.ascontiguousarray(units, dtype=np.int32) if units is not None else None
+            mlen_h = np.ascontiguousarray(mlen, dtype=np.int32)
+            dbg = getattr(self, '_tc_dbg', None)
+            _lib.check(_lib.lib.mepp_scan_tc(
+                _ptr(self.sym_T), _ptr(self.onehot), _ptr(self.zhat), N, L, T, int(margin), _ptr(lut_d), _ptr(bias_d),
+                _ptr(mlen_d), _ptr(nfilt_d), _ptr(units_d), units_h.ctypes.data if units_h is not None else None, n_units,
+                mlen_h.ctypes.data, _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap, _ptr(hit_count),
+                _ptr(entries), entry_cap, _ptr(entry_count), _ptr(row_nnz), _ptr(buckets), _ptr(bucket_count),
+                _ptr(tc_work), wbytes, _ptr(dbg), int(dbg.shape[1]) if dbg is not None else 0, st), "scan_tc")
             self.launches += 4
-            self.last_bp = (bp_d, bp_scratch, self.last_units)
-        elif self.lean and path == 'sparse' and not (bp_d is not None and self.planes_T is not None) and L <= 65535:
+            self.last_scan = 'tc'
+        elif use_lean and path == 'sparse' and not bitpar_on and L <= 65535:
+            self.last_scan = 'lean'
             buckets = self._buf(f'buckets{slot}', int(_lib.lib.mepp_scan_lean_bucket_bytes(T, N)), torch.uint8)
             bucket_count = self._buf(f'bucket_count{slot}', (T * (self.n_pad // 32),), torch.int32)
             lean_args = scan_args[:15] + scan_args[16:] + (_ptr(buckets), _ptr(bucket_count))   # (no tiled operand)
             _lib.check(_lib.lib.mepp_scan_lean(*lean_args, st), "scan_lean")
             self.launches += 2
-        elif bp_d is not None and self.planes_T is not None:
+        elif bitpar_on:
             # units split by class on the device; the bit-parallel units and the pair-table units run as two launches
             bp_scratch = self._buf(f'bp_scratch{slot}', (4 * self.last_units + 2,), torch.int32)
             _lib.check(_lib.lib.mepp_scan_bitpar(*scan_args, _ptr(self.planes_T), _ptr(bp_d), _ptr(bp_scratch), st),
@@ -751,6 +768,7 @@ class Engine:
         else:
             _lib.check(_lib.lib.mepp_scan(*scan_args, st), "scan")
             self.launches += 1
+            self.last_scan = 'full'
         if path == 'tensor':
             # the scan stored only the non-zero pieces; the operand goes back to all-zero before its next use
             self._x_pending = dict(x=x_planes, hits=hits_d, cap=cap, hit_count=hit_count, N=N, L=L, T=T,
@@ -879,13 +897,17 @@ class Engine:
         pend['done'].synchronize()
         h = {k: v.numpy() for k, v in pend['host'].items()}
         t0, T = pend['t0'], pend['T']
-        if pend['path'] == 'sparse' and (int(h['entry_count'][::16].max()) > pend['entry_cap'] // _lib.ENTRY_LISTS
-                                          or int(h['entry_count'][1]) != 0):      # ([1]: a lean-scan bucket overflowed)
-            # X turned out denser than the entry list allows for: redo this group on the tensor-core path
-            redo = self._launch_group(pend['tables'], margin, pend['return_hits'], pend['return_r'], pend['hits_cap'],
-                                      ci, pend['slot'], path='tensor')
-            redo['t0'] = t0
-            return self._collect_group(redo, margin, ci, store, density_all)
+        if pend['path'] == 'sparse':
+            list_full = int(h['entry_count'][::16].max()) > pend['entry_cap'] // _lib.ENTRY_LISTS
+            lean_full = int(h['entry_count'][1]) != 0      # a bucket (or a candidate list) of the lean scan overflowed
+            if list_full or lean_full:
+                # a lean overflow (a run of matches inside 32 sequences) is redone by the full-form scan, still on the
+                # sparse path; only an X too dense for the entry list goes to the tensor-core path
+                self.fallbacks.append('tensor' if list_full else 'full-scan')
+                redo = self._launch_group(pend['tables'], margin, pend['return_hits'], pend['return_r'], pend['hits_cap'],
+                                          ci, pend['slot'], path='tensor' if list_full else 'sparse', lean=False)
+                redo['t0'] = t0
+                return self._collect_group(redo, margin, ci, store, density_all)
         # host side of a group = copies of the finalised block and of the densities into the result table;
         # split over a few threads (memcpy drops the GIL) so that the exposed tail of the last group stays short
         N = self.N
