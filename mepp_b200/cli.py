@@ -53,7 +53,7 @@ _MTMETHODS = ['fdr_tsbky', 'bonferroni', 'sidak', 'holm-sidak', 'holm', 'simes-h
 @click.option('--cmetric', 'cluster_metric', type=click.Choice(_CMETRICS, case_sensitive=False), default='correlation')
 @click.option('--tdpi', 'table_image_dpi', type=int, default=100)
 @click.option('--tformat', 'table_image_format', type=click.Choice(['png', 'svg'], case_sensitive=False), default='png')
-@click.option('--mtmethod', 'mt_method', type=click.Choice(_MTMETHODS, case_sensitive=False), default='fdr_tsbky')
+@click.option('--mtmethod', 'mt_method', type=click.Choice(_MTMETHODS, case_sensitive=False), default='fdr_by')
 @click.option('--mtalpha', 'mt_alpha', type=float, default=0.01)
 @click.option('--thoroughmt', 'thorough_mt', flag_value=True, default=True)
 @click.option('--non-thoroughmt', 'thorough_mt', flag_value=False, default=True)

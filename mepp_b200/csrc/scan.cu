@@ -1457,16 +1457,27 @@ extern "C" int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_de
   g.onehot = reinterpret_cast<const uint8_t*>(onehot_dev);
   g.n_mtiles = (N * (int64_t)L + kTcBasesPerTile - 1) / kTcBasesPerTile;
   g.cand = cand_dev; g.cand_count = counts_dev; g.list_cap = (uint32_t)cap64;
-  g.dbg_acc = dbg_acc_dev; g.dbg_ld = dbg_ld;
-  // launches: consecutive units, <= 32 per N-tile, <= kTcMaxTiles tiles and <= kTcMaxBBytes of weights per launch
+  g.dbg_acc = dbg_ld > 0 ? dbg_acc_dev : nullptr; g.dbg_ld = dbg_ld;
+  g.dbg_clk = dbg_ld < 0 ? reinterpret_cast<unsigned long long*>(dbg_acc_dev) : nullptr;   // (dbg_ld < 0: cycle stamps)
+  { static const int mode = [] { const char* e = getenv("MEPP_TC_MODE"); const char* p = getenv("MEPP_TC_PARK_NS");
+                                 return (e ? atoi(e) & 255 : 0) | ((p ? atoi(p) : 0) << 8); }(); g.mode = mode; }
+  // The units of a launch are dealt EVENLY over its N-tiles (e.g. 41 units -> 24 + 17, not 32 + 9): an N-tile comes back
+  // to the same accumulator stage on the next stream tile and has to wait for its own epilogue (commit, TMEM reads,
+  // barrier hand-over: ~450 cycles, cycle stamps of tools/gpu_tc_clk.py), which only the OTHER N-tile's products can
+  // cover; and N stays >= ~160, where the MMA is bound by the tensor pipe rather than by its operand reads.
+  // (MEPP_TC_TILES_PER_LAUNCH = 1: one N-tile per launch, measured slower -- the stream is scanned once per launch.)
+  static const int tiles_per_launch = [] { const char* e = getenv("MEPP_TC_TILES_PER_LAUNCH"); int v = e ? atoi(e) : kTcMaxTiles;
+                                           return v < 1 ? 1 : v > kTcMaxTiles ? kTcMaxTiles : v; }();
+  const int n_ntiles = (U + kTcUnitsPerTile - 1) / kTcUnitsPerTile;
+  const int units_per_tile = ((U + n_ntiles - 1) / n_ntiles + 3) / 4 * 4;
   int u0 = 0;
   int64_t b_used = 0;
   while (u0 < U) {
     TcLaunch ln;
     ln.n_tiles = 0; ln.ks_max = 1; ln.b_bytes = 0;
     int u = u0;
-    while (u < U && ln.n_tiles < kTcMaxTiles) {
-      const int nu = U - u < 32 ? U - u : 32;
+    while (u < U && ln.n_tiles < tiles_per_launch) {
+      const int nu = U - u < units_per_tile ? U - u : units_per_tile;
       int mmax = 1;
       for (int k = 0; k < nu; ++k) {
         const int t = units_host ? units_host[2 * (u + k)] : u + k;

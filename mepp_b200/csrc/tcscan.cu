@@ -9,7 +9,8 @@
 // chunk of the same rows lies 16 bytes further: LBO = 16 bytes) -- and the four window phases are four shifted
 // copies of the weights in the B operand.  One tcgen05.mma.kind::i8 (M = 128 windows, N = up to 256 columns =
 // 32 scan units x 4 phases x 2 strands, K = 32 channels = 8 taps) replaces 128 x 256 table lookups of the
-// CUDA-core pre-filter; the int32 accumulators stay in TMEM and only their SIGN is read back.
+// CUDA-core pre-filter; the int32 accumulators stay in TMEM and only their SIGN is read back.  (N-tiles are 128
+// columns = 16 units wide: four accumulator stages fit the 512 TMEM columns.)
 //
 // Conservative integer weights (tc_weights_kernel): per filter, penalties pen_j(c) = max_c' W[c'][j] - W[c][j] >= 0
 // are scaled by s = 127 / D, D = sum_j max_j - threshold + rounding slack, and floored: q = -min(128, floor(s pen)).
@@ -19,18 +20,23 @@
 // Survivors (~3e-4 of the windows) are appended to per-warp candidate lists; scan.cu evaluates them in the
 // canonical float32 order, so every reported score still comes from the exact path.
 //
-// Structure: persistent CTAs (one per SM), warp 0 = producer (cp.async.bulk of the weights once, then a 4-stage
-// ring of 2 KB stream tiles), warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue (tcgen05.ld of the
-// double-buffered 2 x 256-column accumulator, AND-reduction of the sign bits, candidate compaction).
+// Structure: persistent CTAs (one per SM), warp 0 = producer (cp.async.bulk of the weights once, then a 16-stage
+// ring of 2 KB stream tiles), warp 1 = TMEM allocator + MMA issuer, warps 2-17 = epilogue in four independent groups
+// (tcgen05.ld.pack::16b of a 4 x 128-column accumulator ring, AND-reduction of the sign bits, candidate compaction):
+// a barrier hand-over costs ~250 cycles whatever the work, so four N-tiles are in flight.
 #include "tcscan.cuh"
 #include "tcgen05.cuh"
+#include <stdlib.h>
 
 namespace mepp {
 
-constexpr int kTcThreads = 320;
-constexpr int kTcStages = 4;
+constexpr int kTcIssuers = 2;
+constexpr int kTcThreads = 32 * (1 + kTcIssuers + kTcEpiWarps);   // producer, MMA issuers, epilogue warps
+constexpr int kTcStages = 16;     // stream tiles in flight: a 2 KB bulk copy takes ~1.5 us, a tile ~0.25 us of work
 constexpr int kTcStageBytes = 2304;   // 2048 + 32 * ks_max, ks_max <= 5 (motifs up to 32 taps + 3 phases)
-constexpr int kTcAccCols = 256;
+constexpr int kTcAccCols = 256;    // TMEM columns of one accumulator stage = widest N-tile (N = 256 keeps the MMA
+                                   // compute bound: at N = 128 the operand reads from shared memory halve its rate)
+constexpr int kTcAccStages = 2;    // one stage per MMA issuer: 2 x 256 columns = the whole TMEM
 
 __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -41,6 +47,19 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// 32 accumulator columns as 16 registers: .pack::16b keeps the low halves of two adjacent columns in one register (the
+// accumulators of this kernel fit 16 bits: |4 (127 + sum q)| <= 4 * 128 * 32), so the sign test needs half the
+// registers and half the logic ops.
+__device__ __forceinline__ void tmem_ld16p_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+
+template <bool PACK>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_constant__ TcLaunch ln,
                                                                 const __grid_constant__ TcScanArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -50,28 +69,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
   uint8_t* sA = smem + b_pad;
   uint64_t* afull = reinterpret_cast<uint64_t*>(sA + kTcStages * kTcStageBytes);   // [kTcStages]
   uint64_t* aempty = afull + kTcStages;                                            // [kTcStages]
-  uint64_t* tfull = aempty + kTcStages;                                            // [2]
-  uint64_t* tempty = tfull + 2;                                                    // [2]
-  uint64_t* bfull = tempty + 2;                                                    // [1]
+  uint64_t* tfull = aempty + kTcStages;                                            // [4 groups][kTcAccStages]
+  uint64_t* tempty = tfull + 4 * kTcAccStages;                                     // [kTcAccStages]
+  uint64_t* bfull = tempty + kTcAccStages;                                         // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  // per N-tile: {B descriptor low word of K-step 0, instruction descriptor, K-steps, B K-step stride >> 4}
+  __shared__ uint4 s_nt[kTcMaxTiles];
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcStages; ++s) { mbar_init(smem_u32(&afull[s]), 1); mbar_init(smem_u32(&aempty[s]), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), kTcEpiWarps); }
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(smem_u32(&afull[s]), 1); mbar_init(smem_u32(&aempty[s]), kTcIssuers); }
+    // an accumulator stage (256 columns) is drained by two groups of four epilogue warps, 128 columns each
+    // "accumulator ready" is signalled per (epilogue group, stage): a parity wait only tells adjacent phases apart, so
+    // every waiter has to see every phase of its barrier -- a group skips the N-tiles of a stage that other groups
+    // drain, and two of a group's items on different stages are not ordered (tools/sim_tc_pipeline.py checks the protocol)
+    for (int s = 0; s < 4 * kTcAccStages; ++s) mbar_init(smem_u32(&tfull[s]), 1);
+    for (int s = 0; s < kTcAccStages; ++s) mbar_init(smem_u32(&tempty[s]), 8);
     mbar_init(smem_u32(bfull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(tmem_slot)), "r"(2u * kTcAccCols) : "memory");
+                 ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(kTcAccStages * kTcAccCols)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 2 && lane < ln.n_tiles) {
+    // K-major, no-swizzle descriptors: low word = start >> 4 | LBO >> 4 << 16, high word = SBO >> 4 | version 1 << 14.
+    //   B: [kstep][16-byte K chunk][column][16 bytes]: LBO = 16 bn, SBO 128
+    const TcTile tl = ln.tiles[lane];
+    const uint32_t bn = tl.bn;
+    // instruction descriptor: D = s32 (2 at [4,6)), A = u8 (0 at [7,10)), B = s8 (1 at [10,13)), K-major both,
+    // N >> 3 at [17,23), M >> 4 at [24,29)
+    const uint32_t idesc = (2u << 4) | (1u << 10) | ((bn >> 3) << 17) | ((uint32_t)(kTcRowsPerTile >> 4) << 24);
+    s_nt[lane] = make_uint4((((smem_u32(sB) + tl.b_off) & 0x3FFFFu) >> 4) | (bn << 16), idesc, tl.ksteps, 2u * bn);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const uint32_t a_bytes = 2048u + 32u * (uint32_t)ln.ks_max;
+  const int n_tiles = ln.n_tiles;
+  const uint32_t park_ns = (uint32_t)g.mode >> 8;      // suspend-time hint of the barrier waits (0: plain try_wait loop)
 
   if (warp == 0) {
     // ------------------------------------------------------------ producer
@@ -84,104 +122,177 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
       }
       uint32_t stage = 0, phase = 0;
       for (int64_t tile = blockIdx.x; tile < g.n_mtiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&aempty[stage]), phase ^ 1u);
+        mbar_wait_parked(smem_u32(&aempty[stage]), phase ^ 1u, park_ns);
         const uint32_t fb = smem_u32(&afull[stage]);
-        mbar_expect_tx(fb, a_bytes);
-        bulk_g2s(smem_u32(sA + stage * kTcStageBytes), g.onehot + tile * 2048, a_bytes, fb);
+        if (g.mode & 8) { mbar_arrive(fb); }        // (timing experiment: no stream copies)
+        else {
+          mbar_expect_tx(fb, a_bytes);
+          bulk_g2s(smem_u32(sA + stage * kTcStageBytes), g.onehot + tile * 2048, a_bytes, fb);
+        }
         if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      mbar_wait(smem_u32(bfull), 0u);
+  } else if (warp <= kTcIssuers) {
+    // ------------------------------------------------------------ MMA issuers (warps 1, 2)
+    // Issuer i owns accumulator stage i and the N-tiles with (running N-tile number) % 2 == i.  tcgen05.mma holds
+    // its issuing thread until the tensor pipe takes the instruction, and a lone warp needs ~300 cycles for the
+    // barrier waits and bookkeeping around an N-tile (measured with the cycle stamps of tools/gpu_tc_clk.py): with two
+    // issuers the pipe works on one N-tile while the other issuer does its bookkeeping.  The whole warp walks the loop
+    // (uniform datapath), one lane issues; everything an N-tile needs is one 16-byte table entry.
+    //   A: row r = bytes [16 r + 32 ks, +32) of the stream tile (overlapping rows): LBO 16, SBO 128
+    const uint32_t me = (uint32_t)(warp - 1);
+    const uint32_t kDescHi = 8u | (1u << 14);
+    mbar_wait_parked(smem_u32(bfull), 0u, park_ns);
+    tc_fence_after();
+    const bool issuer = lane == 0;
+    const uint32_t a_lo_base = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t tfull_me = smem_u32(&tfull[me]), tempty_me = smem_u32(&tempty[me]);   // tfull[group * 2 + stage]
+    const uint32_t d_tmem = tmem_base + me * kTcAccCols;
+    uint32_t stage = 0, phase = 0, nseq = 0, iseq = 0, acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < g.n_mtiles; tile += gridDim.x) {
+      mbar_wait_parked(smem_u32(&afull[stage]), phase, park_ns);
       tc_fence_after();
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      const uint32_t sb0 = smem_u32(sB);
-      for (int64_t tile = blockIdx.x; tile < g.n_mtiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&afull[stage]), phase);
+      const uint32_t a_lo = a_lo_base + stage * (uint32_t)(kTcStageBytes / 16);
+      for (int nt = 0; nt < n_tiles; ++nt, ++nseq) {
+        const uint4 c = s_nt[nt];
+        const uint32_t n_halves = c.w > 256u ? 2u : 1u;        // (c.w = 2 bn: more than four 32-column chunks)
+        const uint32_t item0 = iseq;
+        iseq += n_halves;
+        if ((nseq & 1u) != me) continue;
+        mbar_wait(tempty_me, acc_phase ^ 1u);        // (two spinning warps cost little; a parked wait wakes ~60 cycles later)
+        acc_phase ^= 1u;
         tc_fence_after();
-        const uint32_t sa = smem_u32(sA + stage * kTcStageBytes);
-        for (int nt = 0; nt < ln.n_tiles; ++nt) {
-          const TcTile tl = ln.tiles[nt];
-          const uint32_t bn = tl.bn;
-          // instruction descriptor: D = s32 (2 at [4,6)), A = u8 (0 at [7,10)), B = s8 (1 at [10,13)), K-major both,
-          // N >> 3 at [17,23), M >> 4 at [24,29)
-          const uint32_t idesc = (2u << 4) | (1u << 10) | ((bn >> 3) << 17) | ((uint32_t)(kTcRowsPerTile >> 4) << 24);
-          mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1u);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * kTcAccCols;
-          const uint32_t sb = sb0 + tl.b_off;
-          for (uint32_t ks = 0; ks < tl.ksteps; ++ks) {
-            // A: row r = bytes [16 r + 32 ks, +32) of the stream tile (overlapping rows): LBO 16, SBO 128
-            const uint64_t a_desc = make_desc(sa + ks * 32u, 16u, 128u);
-            const uint64_t b_desc = make_desc(sb + ks * 2u * bn * 16u, bn * 16u, 128u);
-            tc_mma_i8(d_tmem, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
+        if (g.dbg_clk && blockIdx.x == 0 && issuer && nseq < 256) g.dbg_clk[nseq] = clock64();
+        if (issuer) {
+          if (!(g.mode & 2)) {
+#pragma unroll
+            for (uint32_t ks = 0; ks < 5; ++ks)
+              if (ks < c.z)
+                tc_mma_i8(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + 2u * ks), ((uint64_t)kDescHi << 32) | (c.x + ks * c.w),
+                          c.y, ks > 0 ? 1u : 0u);
           }
-          tc_commit(smem_u32(&tfull[acc]));
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          tc_commit(tfull_me + (item0 & 3u) * (8u * kTcAccStages));              // the group(s) that drain this N-tile
+          if (n_halves == 2u) tc_commit(tfull_me + ((item0 + 1u) & 3u) * (8u * kTcAccStages));
+          if (g.dbg_clk && blockIdx.x == 0 && nseq < 256) g.dbg_clk[256 + nseq] = clock64();
         }
-        tc_commit(smem_u32(&aempty[stage]));     // the stream tile is free once this tile's MMAs retire
-        if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        __syncwarp();
       }
+      if (issuer) tc_commit(smem_u32(&aempty[stage]));     // the stream tile is free once both issuers' MMAs retired
+      __syncwarp();
+      if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // ------------------------------------------------------------ epilogue (warps 3..18)
+    // Four groups of four warps (one warp per TMEM lane quarter).  Work items are the non-empty 128-column halves of
+    // the N-tiles in running order; item i belongs to group i % 4, so the groups never wait for each other and share
+    // the work evenly whatever the N-tile widths.  A warp's instruction stream is one dependent chain (wait, load,
+    // AND-reduce, vote, branch): it takes four warps per scheduler to keep the issue slots busy.
     const unsigned full = 0xffffffffu;
-    const int ew = warp - 2, q = warp & 3, h = ew >> 2;
-    uint32_t acc = 0, acc_phase = 0, my_count = 0;
+    const int ew = warp - (1 + kTcIssuers), q = warp & 3, gidx = ew >> 2;
+    uint32_t my_count = 0, nseq = 0, iseq = 0, seen0 = 0, seen1 = 0;   // seen: this group's items per stage so far
     const int64_t list = (int64_t)blockIdx.x * kTcEpiWarps + ew;
     uint2* const my_list = g.cand + list * (int64_t)g.list_cap;
     for (int64_t tile = blockIdx.x; tile < g.n_mtiles; tile += gridDim.x) {
       const uint32_t row = (uint32_t)(tile * kTcRowsPerTile) + (uint32_t)(q * 32 + lane);
       int dbg_col = 0;
-      for (int nt = 0; nt < ln.n_tiles; ++nt) {
-        const TcTile tl = ln.tiles[nt];
-        mbar_wait(smem_u32(&tfull[acc]), acc_phase);
-        tc_fence_after();
-        const int n_chunks = tl.bn >> 5;
-        for (int c = h; c < n_chunks; c += 2) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTcAccCols + (uint32_t)(c * 32), v);
-          if (g.dbg_acc != nullptr && tile == 0) {
+      for (int nt = 0; nt < n_tiles; ++nt, ++nseq) {
+        const uint4 cst = s_nt[nt];
+        const int bn = (int)(cst.w >> 1), n_chunks = bn >> 5;
+        const int n_halves = n_chunks > 4 ? 2 : 1;
+        for (int hf = 0; hf < n_halves; ++hf, ++iseq) {
+          if ((int)(iseq & 3u) != gidx) continue;
+          const uint32_t acc = nseq & 1u;
+          const uint32_t acc_phase = (acc ? seen1 : seen0) & 1u;
+          if (acc) ++seen1; else ++seen0;
+          mbar_wait_parked(smem_u32(&tfull[gidx * kTcAccStages + acc]), acc_phase, park_ns);
+          tc_fence_after();
+          const bool stamp = g.dbg_clk && blockIdx.x == 0 && lane == 0 && (ew & 3) == 0 && hf == 0 && nseq < 256;
+          if (stamp) g.dbg_clk[512 + nseq] = clock64();
+          const int c0 = 4 * hf, nc = n_chunks - c0 < 4 ? n_chunks - c0 : 4;     // this item's chunks: c0 .. c0 + nc - 1
+          // the item's columns are read with one wait, and the accumulator stage is handed back to its MMA issuer
+          // before the values are looked at
+          uint32_t v[4][PACK ? 16 : 32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) g.dbg_acc[(int64_t)(q * 32 + lane) * g.dbg_ld + dbg_col + c * 32 + j] = (int32_t)v[j];
+          for (int k = 0; k < 4; ++k)
+            if (k < nc && !(g.mode & 1)) {
+              const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTcAccCols + (uint32_t)((c0 + k) * 32);
+              if constexpr (PACK) tmem_ld16p_nowait(ta, v[k]);
+              else tmem_ld32_nowait(ta, v[k]);
+            }
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(smem_u32(&tempty[acc]));
+            if (n_halves == 1) mbar_arrive(smem_u32(&tempty[acc]));     // (nobody drains the empty other half)
           }
-          uint32_t t = v[0];
+          if (stamp) g.dbg_clk[768 + nseq] = clock64();
+          if (!(g.mode & 5)) {
+            if (g.dbg_acc != nullptr && tile == 0) {
 #pragma unroll
-          for (int j = 1; j < 32; ++j) t &= v[j];
-          const bool has = (int32_t)t >= 0;           // some accumulator of this row is non-negative
-          if (__any_sync(full, has)) {
-            uint32_t cm = 0u;                        // bit p: (unit p / 4 of the chunk, phase p % 4) passes on a strand
-            if (has) {
+              for (int k = 0; k < 4; ++k) {
+                if (k >= nc) break;
+                int32_t* d = g.dbg_acc + (int64_t)(q * 32 + lane) * g.dbg_ld + dbg_col + (c0 + k) * 32;
+                if constexpr (PACK) {
 #pragma unroll
-              for (int p = 0; p < 16; ++p)
-                if ((int32_t)(v[2 * p] & v[2 * p + 1]) >= 0) cm |= 1u << p;
+                  for (int j = 0; j < 16; ++j) { d[2 * j] = (int32_t)(int16_t)(v[k][j] & 0xffffu); d[2 * j + 1] = (int32_t)(int16_t)(v[k][j] >> 16); }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) d[j] = (int32_t)v[k][j];
+                }
+              }
             }
-            const int n = __popc(cm);
-            int pre = n;
+            // sign tests of all chunks first (independent AND trees), one vote for the whole item
+            constexpr int NV = PACK ? 16 : 32;
+            uint32_t hasm = 0u;                      // bit k: some accumulator of this row in chunk k is non-negative
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const int x = __shfl_up_sync(full, pre, o);
-              if (lane >= o) pre += x;
+            for (int k = 0; k < 4; ++k) {
+              if (k >= nc) break;
+              uint32_t t = v[k][0];
+#pragma unroll
+              for (int j = 1; j < NV; ++j) t &= v[k][j];
+              const bool has = PACK ? (t & 0x80008000u) != 0x80008000u : (int32_t)t >= 0;
+              hasm |= has ? 1u << k : 0u;
             }
-            const int total = __shfl_sync(full, pre, 31);
-            uint32_t slot = my_count + (uint32_t)(pre - n);
-            my_count += (uint32_t)total;
-            const uint32_t ubase = ((uint32_t)tl.unit0 + (uint32_t)c * 4u) << 2;
-            while (cm != 0u) {
-              const int p = __ffs((int)cm) - 1;
-              cm &= cm - 1u;
-              if (slot < g.list_cap) my_list[slot] = make_uint2(row, ubase + (uint32_t)p);
-              ++slot;
+            if (__any_sync(full, hasm != 0u)) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k >= nc) break;
+                unsigned bal = __ballot_sync(full, (hasm >> k) & 1u);      // lanes (rows) with a candidate in chunk k
+                if (bal == 0u) continue;
+                uint32_t cm = 0u;                    // bit p: (unit p / 4 of the chunk, phase p % 4) passes on a strand
+                if ((hasm >> k) & 1u) {
+#pragma unroll
+                  for (int p = 0; p < 16; ++p) {
+                    bool pass;
+                    if constexpr (PACK) pass = (v[k][p] & 0x80008000u) != 0x80008000u;
+                    else pass = (int32_t)(v[k][2 * p] & v[k][2 * p + 1]) >= 0;
+                    if (pass) cm |= 1u << p;
+                  }
+                }
+                const uint32_t ubase = ((uint32_t)ln.tiles[nt].unit0 + (uint32_t)(c0 + k) * 4u) << 2;
+                // the few lanes with candidates take their turn: slots my_count .. in lane order
+                while (bal != 0u) {
+                  const int src = __ffs((int)bal) - 1;
+                  bal &= bal - 1u;
+                  const int n = __popc(__shfl_sync(full, cm, src));
+                  if (lane == src) {
+                    uint32_t slot = my_count;
+                    while (cm != 0u) {
+                      const int p = __ffs((int)cm) - 1;
+                      cm &= cm - 1u;
+                      if (slot < g.list_cap) my_list[slot] = make_uint2(row, ubase + (uint32_t)p);
+                      ++slot;
+                    }
+                  }
+                  my_count += (uint32_t)n;
+                }
+              }
             }
           }
+          if (stamp) g.dbg_clk[1024 + nseq] = clock64();
         }
-        dbg_col += tl.bn;
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty[acc]));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        dbg_col += bn;
       }
     }
     if (lane == 0) g.cand_count[list] = my_count;
@@ -190,7 +301,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kTcAccCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(kTcAccStages * kTcAccCols)) : "memory");
   }
 }
 
@@ -269,7 +380,7 @@ int tc_scan_grid() {
 int tc_build_weights(const TcLaunch& ln, const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev,
                      const int32_t* nfilt_dev, const int32_t* units_dev, int unit_base, int n_units_total, uint8_t* B_dev,
                      cudaStream_t st) {
-  dim3 grid((unsigned)ln.n_tiles, 32u);
+  dim3 grid((unsigned)ln.n_tiles, (unsigned)kTcUnitsPerTile);
   tc_weights_kernel<<<grid, 128, 0, st>>>(ln, lut_dev, bias_dev, mlen_dev, nfilt_dev, units_dev, unit_base, n_units_total,
                                           B_dev);
   MEPP_CUDA_CHECK(cudaGetLastError());
@@ -277,13 +388,19 @@ int tc_build_weights(const TcLaunch& ln, const float* lut_dev, const float* bias
 }
 
 int tc_scan_launch(const TcLaunch& ln, const TcScanArgs& a, cudaStream_t st) {
-  const size_t smem = ((size_t)ln.b_bytes + 1023) / 1024 * 1024 + (size_t)kTcStages * kTcStageBytes + 256;
+  const size_t smem = ((size_t)ln.b_bytes + 1023) / 1024 * 1024 + (size_t)kTcStages * kTcStageBytes + 1024 /* barriers */;
   MEPP_REQUIRE(ln.b_bytes <= (uint32_t)kTcMaxBBytes && ln.ks_max >= 1 && 2048 + 32 * ln.ks_max <= kTcStageBytes,
                "scan_tc: weight operand or motif length outside the kernel's limits");
-  MEPP_CUDA_CHECK(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const bool pack = [] { const char* e = getenv("MEPP_TC_PACK"); return e ? atoi(e) != 0 : true; }();
   int grid = tc_scan_grid();
   if ((int64_t)grid > a.n_mtiles) grid = (int)a.n_mtiles;
-  tc_scan_kernel<<<grid, kTcThreads, smem, st>>>(ln, a);
+  if (pack) {
+    MEPP_CUDA_CHECK(cudaFuncSetAttribute(tc_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_scan_kernel<true><<<grid, kTcThreads, smem, st>>>(ln, a);
+  } else {
+    MEPP_CUDA_CHECK(cudaFuncSetAttribute(tc_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_scan_kernel<false><<<grid, kTcThreads, smem, st>>>(ln, a);
+  }
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

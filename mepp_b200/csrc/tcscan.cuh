@@ -5,10 +5,11 @@
 namespace mepp {
 
 constexpr int kTcMaxTiles = 8;            // N-tiles (of <= 32 scan units = 256 columns) per launch
+constexpr int kTcUnitsPerTile = 32;
 constexpr int kTcRowsPerTile = 128;       // windows (at a stride of four bases) per M-tile
 constexpr int kTcBasesPerTile = 4 * kTcRowsPerTile;
-constexpr int kTcEpiWarps = 8;            // candidate lists per CTA (one per epilogue warp)
-constexpr int kTcMaxBBytes = 180 * 1024;  // weight operand resident in shared memory
+constexpr int kTcEpiWarps = 16;           // epilogue warps = candidate lists per CTA
+constexpr int kTcMaxBBytes = 176 * 1024;  // weight operand resident in shared memory
 
 // One N-tile of a launch: `n_units` scan units starting at unit `unit0` of the launch's unit list, 8 columns each
 // (4 phases x 2 filters), K = 32 * ksteps one-hot channels (4 per base), weights at byte `b_off` of the operand.
@@ -33,6 +34,8 @@ struct TcScanArgs {
   uint32_t list_cap;
   int32_t* dbg_acc;           // optional: raw accumulators of M-tile 0 [128][dbg_ld]
   int dbg_ld;
+  unsigned long long* dbg_clk;   // optional: cycle stamps of CTA 0's pipeline, [5][256] (bring-up / tuning only)
+  int mode;                   // timing experiments only (MEPP_TC_MODE): 1 no epilogue work, 2 no MMAs, 4 loads but no tests
 };
 
 int tc_scan_grid();   // CTAs of a launch (one per SM)

@@ -748,7 +748,8 @@ def test_lean_scan_equals_full_scan(N, L, margin, seed, long_run):
     """mepp_scan_lean (matches only + entries built from per-(task, k-block) buckets, the default on the sparse path)
     against mepp_scan (blur and entries from staging rows): identical matches, counts and densities, r within 1e-6;
     runs of overlapping matches in one sequence; a long run overflows its bucket and the group falls back to the
-    full scan (then on the tensor path, hence the wider tolerance).  Same cases as tools/gpu_lean_check.py."""
+    full-form scan on the sparse path.  The lean form is run with both first stages: the CUDA-core pair tables
+    (mepp_scan_lean) and the tcgen05 int8 products over the one-hot stream (mepp_scan_tc, the default)."""
     from mepp_b200 import synth
     ascii_u8, scores = synth.synth_sequences(N, L, seed=seed, n_rate=0.02, lower_rate=0.01)
     if long_run:
@@ -760,21 +761,30 @@ def test_lean_scan_equals_full_scan(N, L, margin, seed, long_run):
     cons = np.full((4, 9), 1e-3); cons[0, :] = 1.0
     motifs.append(cons / cons.sum(axis=0))
     tasks = [(m, o) for m in motifs for o in ('+', '+/-')] + [(motifs[0], '-')]
-    res, paths = [], []
-    for lean in (False, True):
+    res, paths, scans, fallbacks = [], [], [], []
+    for lean, tc in ((False, False), (True, False), (True, True)):
         eng = _engine()
-        eng.lean = lean
+        eng.lean, eng.tc_scan = lean, tc
         eng.stage(ascii_u8, scores, perm)
         res.append(eng.profile(tasks, margin=margin, return_hits=True, return_r=True))
         paths.append(list(eng.last_paths))
-    full, lean = res
-    assert paths[0] == ['sparse'] and paths[1] == (['sparse', 'tensor'] if long_run else ['sparse'])
+        scans.append(eng.last_scan)
+        fallbacks.append(list(eng.fallbacks))
+    full = res[0]
+    # a bucket overflow is redone by the full-form scan, still on the sparse path (no detour over the tiled operands)
+    assert paths[0] == ['sparse'] and fallbacks[0] == []
+    for k in (1, 2):
+        assert paths[k] == (['sparse', 'sparse'] if long_run else ['sparse']), paths
+        assert fallbacks[k] == (['full-scan'] if long_run else []), fallbacks
+    assert scans == (['full', 'full', 'full'] if long_run else ['full', 'lean', 'tc']), scans
     assert len(full.hits) > 20
-    assert np.array_equal(full.hits, lean.hits)
-    assert np.array_equal(full.density, lean.density)
-    assert np.array_equal(np.asarray(full.positions['count']), np.asarray(lean.positions['count']))
-    tol = dict(rtol=1e-6, atol=1e-9) if paths[0] == paths[1] else dict(rtol=1e-4, atol=1e-6)
-    assert np.allclose(full.r, lean.r, **tol)
+    for lean in res[1:]:
+        assert np.array_equal(full.hits, lean.hits)
+        assert np.array_equal(full.density, lean.density)
+        assert np.array_equal(np.asarray(full.positions['count']), np.asarray(lean.positions['count']))
+        assert np.allclose(full.r, lean.r, rtol=1e-6, atol=1e-9)
+    assert np.array_equal(res[1].r, res[2].r)          # the two lean forms publish the same matches: identical entries
+    lean = res[2]
     codes = staging.ascii_to_codes(ascii_u8)
     for t in (0, 1, len(tasks) - 3, len(tasks) - 2):
         Wf, Wr, thr = profile.motif_weights(*tasks[t])

@@ -209,6 +209,28 @@ def test_cli_flags_match_the_reference():
                 '--maxwait', '--cmethod', '--cmetric', '--tdpi', '--tformat', '--mtmethod', '--mtalpha',
                 '--thoroughmt', '--non-thoroughmt'}
     assert expected <= flags
+    # names, destinations, defaults, flag-ness and required-ness of every option equal the reference's
+    # (tests/golden/reference_cli_options.json, made from mepp/cli.py by tests/golden/make_cli_fixture.py)
+    import json
+    import multiprocessing
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_cli_options.json')) as f:
+        ref_opts = json.load(f)
+    assert len(ref_opts) == 35
+    ours = {o: p for p in cli.main.params for o in p.opts + p.secondary_opts}
+    for ro in ref_opts:
+        for flag in ro['flags']:
+            p = ours[flag]
+            assert p.name == ro['dest'], flag
+            assert bool(p.required) == ro['required'], flag
+            assert bool(getattr(p, 'is_flag', False)) == (ro['is_flag'] or ro['flag_value'] is not None), flag
+            if ro['flag_value'] is not None:
+                assert p.flag_value == eval(ro['flag_value']), flag
+            if ro['default'] is not None:
+                want = eval(ro['default'], {'multiprocessing': multiprocessing})
+                got = p.default
+                assert (tuple(got) if isinstance(want, tuple) else got) == want, (flag, got, want)
+            elif not ro['is_flag']:
+                assert p.default is None, flag
     res = CliRunner().invoke(cli.main, ['--help'])
     assert res.exit_code == 0 and '--help' in res.output
     res = CliRunner().invoke(cli.main, ['--fa', 'x', '--motifs', 'y', '--out', 'z', '--nogpu'])
@@ -365,3 +387,20 @@ def test_match_driven_blur_is_bit_identical_to_the_dense_blur():
         X0 = np.where(rng.random((40, 97)) < 0.01, rng.gamma(2.0, 1.0, size=(40, 97)), 0.0).astype(np.float32)
         dense = proto.dense_blur_f32(X0, margin)
         assert np.allclose(dense, profile.blur(X0, margin, dtype=np.float64), rtol=3e-7, atol=0)
+
+
+def test_tc_scan_pipeline_protocol_has_no_deadlock():
+    """Barrier protocol of the tensor-core scan kernel (csrc/tcscan.cu), simulated on the CPU with random scheduling and
+    randomly delayed asynchronous arrivals (tools/sim_tc_pipeline.py): every mix of N-tile widths runs to completion."""
+    import importlib.util
+    import random
+    spec = importlib.util.spec_from_file_location(
+        "sim_tc_pipeline", os.path.join(os.path.dirname(__file__), "..", "tools", "sim_tc_pipeline.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    rnd = random.Random(11)
+    cases = [[256, 96], [64], [256], [192, 160], [256, 256, 128], [96, 64, 32]]
+    cases += [[32 * rnd.randint(1, 8) for _ in range(rnd.randint(1, 8))] for _ in range(4)]
+    for bns in cases:
+        for seed in range(2):
+            assert sim.run(40, bns, seed=seed), (bns, seed)

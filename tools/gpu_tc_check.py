@@ -57,12 +57,14 @@ def main():
     isn = ~np.isin(a, np.frombuffer(b"ACGT", dtype=np.uint8))
     oh[:a.size][isn] = 1
     flat = oh.reshape(-1)
-    # the launch plan of mepp_scan_tc: consecutive units, 32 per tile
+    # the launch plan of mepp_scan_tc: consecutive units dealt evenly over the ceil(U / 32) N-tiles of one launch
     bad = 0
     col = 0
     U = len(units)
-    for u0 in range(0, U, 32):
-        nu = min(32, U - u0)
+    n_ntiles = (U + 31) // 32
+    per = ((U + n_ntiles - 1) // n_ntiles + 3) // 4 * 4
+    for u0 in range(0, U, per):
+        nu = min(per, U - u0)
         bn = 32 * ((nu + 3) // 4)
         mmax = max(tables[units[u0 + k][0]]['m'] for k in range(nu))
         K = 32 * ((4 * (mmax + 3) + 31) // 32)
