@@ -9,9 +9,15 @@ correlation -> permutation statistics) over every task of the workload on synthe
 of the named shape.  `value` times steps whose inputs are already staged in HBM; `e2e` times the
 same step through the public API from pinned HOST buffers: H2D of sequences / scores /
 permutation indices, 2-bit pack, score-operand build, host MOODS thresholds, all tasks, and D2H of
-every result table.  With --gpus N the tasks are sharded over N ranks (weak scaling: N copies of
-the task list, one per GPU; every rank stages its own replica) and the per-task tables are
-gathered to rank 0 with one NCCL collective.
+every result table.  With --gpus N the ONE task list of the workload is sharded over N ranks, as the
+reference fans one list of motif x orientation tasks over its workers (mepp/batch.py:73-140):
+strong scaling, the default; `--scaling weak` runs N copies of the list instead.  Every rank stages
+its own replica (the upload is split over the ranks and all-gathered over NVLink) and the per-task
+tables are gathered to rank 0 with one NCCL collective.
+
+After the timed regions rank 0 checks a few tasks of the workload AT FULL SIZE against the oracle
+(`accuracy`: SURVEY.md section 8d's gates) and times the CPU port on a bounded sample (`cpu_baseline`).
+`--mode fullrun` times run_mepp itself, wall clock: scored FASTA file -> every task directory.
 
 --impl reference times the CPU baseline (oracle/baseline.py: the reference's algorithm on the
 host cores; the reference's own TensorFlow/MOODS code cannot run in this image) on a bounded
@@ -24,6 +30,11 @@ import subprocess
 import sys
 import threading
 import time
+
+if "reference" in sys.argv:
+    # the CPU arm uses every host core: torchrun exports OMP_NUM_THREADS=1, which would throttle its BLAS calls
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
 
 import numpy as np
 
@@ -111,12 +122,22 @@ class ClockSampler:
                     power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
 
 
-def build_workload(workload, world):
+def build_workload(workload, world, scaling="strong"):
     from mepp_b200 import synth
     cfg = synth.make_config(workload)
     base = [(pwm, o) for _, pwm, o in cfg["tasks"]]
-    tasks = base * world                       # weak scaling: per-GPU work fixed
+    # strong: the ONE task list of the workload, sharded over the ranks (mepp/batch.py:73-140 fans one list over its
+    # workers); weak: a copy of the list per GPU
+    tasks = base * world if scaling == "weak" else base
     return cfg, tasks
+
+
+def bench_config(args, cfg, n_tasks):
+    """`config` of the JSON line: the same keys and values for both arms (the driver compares them)."""
+    return dict(workload=args.workload, N=cfg["N"], L=cfg["L"], P=cfg["P"], margin=cfg["margin"], tasks_total=n_tasks,
+                orientations=",".join(sorted({o for _, _, o in cfg["tasks"]})), scaling=args.scaling,
+                l2="no flush needed: every step streams far more than the 126 MB L2 (the correlation matrix r alone is "
+                   "4 MB per task, written and re-read by the statistics)")
 
 
 def run_reference(args, rank, world):
@@ -124,12 +145,13 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import baseline, staging
-    cfg, tasks = build_workload(args.workload, 1)
+    cfg, tasks = build_workload(args.workload, world, args.scaling)
     codes = staging.ascii_to_codes(cfg["ascii"])
     Y = staging.permuted_scores(cfg["scores"], cfg["perm_idx"])
     z = staging.gc_ratio_global(codes)
     cores = os.cpu_count() or 1
-    per_step_budget = max(2.0, min(20.0, 100.0 / max(1, args.steps + args.warmup)))
+    # a step = a bounded sample of the workload: whole tasks until the step's share of ~2 minutes is spent (at least one)
+    per_step_budget = min(20.0, 120.0 / max(1, args.steps + args.warmup))
     n_done = 0
     for _ in range(args.warmup):
         baseline.time_sample(codes, Y, z, tasks, cfg["margin"], threads=cores, budget_s=per_step_budget / 2)
@@ -143,21 +165,50 @@ def run_reference(args, rank, world):
               f"N={cfg['N']} L={cfg['L']} P={cfg['P']}), float32 scan in C + BLAS sgemm profile + numpy stats")
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * total_t / max(1, args.steps), higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=args.workload, N=cfg["N"], L=cfg["L"], P=cfg["P"], margin=cfg["margin"],
-                            tasks=len(tasks)),
+                scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
+                config=bench_config(args, cfg, len(tasks)),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
+def accuracy_block(eng, cfg, my_tasks, my_ids, n_check, margin):
+    """SURVEY.md 8(d) accuracy gates on a few of this rank's tasks at FULL size: the device results of the default
+    path (the kernels the timed steps ran) against the oracle."""
+    from oracle import checks, staging
+    n_loc = len(my_tasks)
+    if n_loc == 0 or n_check <= 0:
+        return None
+    # the first motif in both orientations (planted signal), one from the middle, the last one
+    pick = sorted({0, min(1, n_loc - 1), (n_loc // 2) & ~1, n_loc - 1})[:max(1, n_check)]
+    sel = [my_tasks[i] for i in pick]
+    t0 = time.perf_counter()
+    got = eng.profile(sel, margin=margin, return_hits=True, return_r=True)
+    hits = got.hits.copy()
+    codes = staging.ascii_to_codes(cfg["ascii"])
+    Y = staging.permuted_scores(cfg["scores"], cfg["perm_idx"])
+    z = staging.gc_ratio_global(codes)
+    rep = checks.accuracy_report(codes, Y, z, sel, [my_ids[i] for i in pick], margin, hits, got.r, got.positions)
+    rep["scan_form"] = getattr(eng, "last_scan", None)
+    rep["profile_path"] = ",".join(sorted(set(eng.last_paths)))
+    rep["seconds"] = round(time.perf_counter() - t0, 1)
+    return rep
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--workload", default="cfg3", help="cfg1 .. cfg5 of BASELINE.json (default: cfg3, the north-star target)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the workload's one task list sharded over the GPUs; weak: one copy of the list per GPU")
+    ap.add_argument("--mode", default="step", choices=["step", "fullrun"],
+                    help="step: the hot path per step (the JSON line of the contract); fullrun: run_mepp wall clock, "
+                         "scored FASTA file -> complete output directory")
+    ap.add_argument("--no-accuracy", action="store_true", help="skip the full-size oracle check of a few tasks")
+    ap.add_argument("--accuracy-tasks", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not run the nvidia-smi clock sampler")
     args = ap.parse_args()
@@ -183,7 +234,7 @@ def main():
     from mepp_b200.engine import Engine
     import torch.distributed as dist
 
-    cfg, tasks = build_workload(args.workload, world)
+    cfg, tasks = build_workload(args.workload, world, args.scaling)
     N, L, P, margin = cfg["N"], cfg["L"], cfg["P"], cfg["margin"]
     T_total = len(tasks)
     my_ids = parallel.shard_task_units(tasks, world)[rank]    # LPT over (motif) units: orientation pairs stay together
@@ -193,7 +244,9 @@ def main():
     h_ascii = torch.from_numpy(cfg["ascii"]).pin_memory()
     h_scores = torch.from_numpy(cfg["scores"]).pin_memory()
     h_perm = torch.from_numpy(cfg["perm_idx"]).pin_memory()
-    h2d_bytes = h_ascii.numel() + 4 * h_scores.numel() + 4 * h_perm.numel() + len(my_tasks) * (32 * 4 * 2 * 4 + 12)
+    # host -> device bytes of one end-to-end step on this rank (sharded upload + all-gather when world > 1)
+    h2d_bytes = (-(-h_ascii.shape[0] // world) * h_ascii.shape[1] + 4 * h_scores.numel()
+                 + 4 * -(-h_perm.shape[0] // world) * h_perm.shape[1] + len(my_tasks) * (32 * 4 * 2 * 4 + 12))
 
     eng = Engine(device=local)
 
@@ -204,8 +257,8 @@ def main():
         dbg = bool(os.environ.get("MEPP_BENCH_DEBUG"))
         tq = [time.perf_counter()]
         if world > 1:
-            # one host copy per node: rank 0 uploads, the other GPUs receive over NVLink (NCCL broadcast)
-            eng.stage_broadcast(*((h_ascii, h_scores, h_perm) if rank == 0 else (None, None, None)), use_gc=True, src=0)
+            # every rank uploads 1 / world of the sequences and permutation indices, all-gathered over NVLink
+            eng.stage_allgather(h_ascii, h_scores, h_perm, use_gc=True)
         else:
             eng.stage(h_ascii, h_scores, h_perm, use_gc=True)
         tq.append(time.perf_counter())
@@ -236,7 +289,8 @@ def main():
     # bytes actually copied device -> host per step: the finalised column block (68 B per (task, position), 44 B
     # per task), density per (task, sequence), the match / entry counters of every group
     n_loc = len(my_tasks)
-    d2h_bytes = int(n_loc * L * 68 + n_loc * 44 + n_loc * eng.n_pad * 4 + eng.last_groups * (8 + 8 * 16 * 64))
+    d2h_bytes = int(n_loc * L * 68 + n_loc * 44 + n_loc * eng.n_pad * (2 if L <= 65535 else 4)
+                    + eng.last_groups * (8 + 8 * 16 * 64))
 
     sampler = ClockSampler(local)
     if not args.no_clocks:
@@ -397,6 +451,10 @@ def main():
                          "X written) / CUDA-event time of the launches; the kernel is bound by integer issue, not by HBM "
                          "(DESIGN.md section 4); traffic = DRAM bytes of one launch from the committed ncu capture (full-form kernel)")
 
+    accuracy = None
+    if not args.no_accuracy:
+        accuracy = accuracy_block(eng, cfg, my_tasks, my_ids, args.accuracy_tasks, margin)
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import baseline, staging
@@ -410,15 +468,15 @@ def main():
                                    f"float32 scan in C + BLAS sgemm profile + numpy statistics")
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 1),
-                ms_per_step=1e3 * dt_value / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                ms_per_step=1e3 * dt_value / args.steps, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                 dtype="f32", data="synthetic",
-                config=dict(workload=args.workload, N=N, L=L, P=P, margin=margin, tasks_total=T_total,
-                            tasks_per_gpu=n_local, orientations="+,+/-", parallelism=f"tasks sharded over {world} GPU(s)",
-                            l2="L2 flushed between steps by the step itself (r + sorted keys: %.1f GB per group, L2 126 MB)"
-                               % (8.0 * L * eng.ldS * min(n_local, eng.group_size()) / 1e9),
-                            profile_path=",".join(sorted(set(st["paths"]))),
-                            profile="sparse: float64 gather of float32 Y rows per non-zero of X; "
-                                    "tensor: fp16 hi/lo split, 3 tcgen05 products, fp32 TMEM accumulate"),
+                config=bench_config(args, cfg, T_total),
+                details=dict(tasks_per_gpu=n_local, parallelism=f"tasks sharded over {world} GPU(s)",
+                             scan_form=getattr(eng, "last_scan", None),
+                             profile_path=",".join(sorted(set(st["paths"]))),
+                             profile="sparse: float64 gather of float32 Y rows per non-zero of X; "
+                                     "tensor: fp16 hi/lo split, 3 tcgen05 products, fp32 TMEM accumulate",
+                             fallbacks=list(eng.fallbacks)),
                 e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=1e3 * dt_e2e / args.steps,
                          h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
                 timing=dict(how="CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks",
@@ -427,7 +485,8 @@ def main():
                                     "group g on a high-priority stream" if eng.overlap else "none",
                             kernels="per-kernel times: CUDA events on the launching stream in a serial pass of %d steps "
                                     "(overlap off) right after the timed region" % kernel_steps),
-                gpu_launches=int(launches), roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline, clocks=clocks)
+                gpu_launches=int(launches), roofline=roofline, kernels=kernels, accuracy=accuracy,
+                cpu_baseline=cpu_baseline, clocks=clocks)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

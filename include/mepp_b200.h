@@ -322,6 +322,11 @@ int mepp_finalize_positions(const float* r_dev, int64_t ldr, int T, int L, int C
                             int k_lo, int k_hi, double g_lo, double g_hi, double gs_lo, double gs_hi, float z_margin,
                             void* out_dev, void* stream);
 
+/* density [n] int32 (matches per (task, sequence), mepp_scan) -> uint16 (saturating; a count is <= L) for the copy to
+ * the host: what core.get_motif_density_by_rank returns per task (core.py:456-470) needs 2 bytes per sequence.
+ * n must be a multiple of 4 (rows are padded to 32 sequences). */
+int mepp_density_u16(const int32_t* density_dev, int64_t n, uint16_t* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -183,9 +183,30 @@ __global__ void finalize_tasks_kernel(const FinalizeArgs a, int P_pow2) {
   }
 }
 
+// density (matches per sequence, <= L <= 65535) narrowed for the copy to the host: at cfg 3 the int32 form is 130 MB per step
+__global__ void density_u16_kernel(const int32_t* __restrict__ in, int64_t n4, uint2* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int4 v = reinterpret_cast<const int4*>(in)[i];
+  const uint32_t a = (uint32_t)min(v.x, 65535), b = (uint32_t)min(v.y, 65535);
+  const uint32_t c = (uint32_t)min(v.z, 65535), d = (uint32_t)min(v.w, 65535);
+  out[i] = make_uint2(a | (b << 16), c | (d << 16));
+}
+
 }  // namespace mepp
 
 extern "C" {
+
+int mepp_density_u16(const int32_t* density_dev, int64_t n, uint16_t* out_dev, void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(density_dev && out_dev && n > 0 && (n & 3) == 0, "density_u16: bad arguments (n must be a multiple of 4)");
+  MEPP_REQUIRE(mepp_device_ok(), "density_u16: no sm_100 CUDA device (no CPU fallback)");
+  const int64_t n4 = n / 4;
+  density_u16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, as_stream(stream)>>>(density_dev, n4,
+                                                                               reinterpret_cast<uint2*>(out_dev));
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 int64_t mepp_finalize_out_bytes(int T, int L) {
   const int64_t TL = (int64_t)T * L;

@@ -361,6 +361,50 @@ class Engine:
                     self._bcast_perm_ready.record(self._copy_stream)
             return self.stage(ascii_d, scores_d.cpu().numpy(), perm_d, use_gc=use_gc)
 
+    def stage_allgather(self, ascii_u8, scores, perm_idx=None, use_gc=True):
+        """Multi-GPU staging when EVERY rank holds the host arrays (each rank parsed the same files, or generated the
+        same synthetic dataset): rank k uploads only the k-th slice of the sequences and of the permutation indices
+        through its own PCIe link, and the slices are all-gathered over NVLink / NVSwitch -- the host -> device bytes
+        per rank shrink with the number of GPUs instead of staying at one full replica per rank (500 MB at cfg 3).
+        The permutation indices travel on the side stream, behind the first scan."""
+        torch = self.torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return self.stage(ascii_u8, scores, perm_idx, use_gc=use_gc)
+        world, rank = dist.get_world_size(), dist.get_rank()
+        as_t = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dt)
+        with torch.cuda.device(self.device):
+            N, L = int(ascii_u8.shape[0]), int(ascii_u8.shape[1])
+            P = 0 if perm_idx is None else int(perm_idx.shape[0])
+            ra = -(-N // world)                                   # sequence rows per rank (the last slice may be short)
+            ascii_all = self._buf('ascii_ag', (world * ra, L), torch.uint8)
+            send_a = self._buf('ascii_ag_send', (ra, L), torch.uint8)
+            a0, a1 = min(N, rank * ra), min(N, (rank + 1) * ra)
+            if a1 > a0:
+                send_a[:a1 - a0].copy_(as_t(ascii_u8, torch.uint8)[a0:a1], non_blocking=True)
+            dist.all_gather_into_tensor(ascii_all, send_a)
+            perm_d = None
+            self._bcast_perm_ready = None
+            if P > 0:
+                rp = -(-P // world)
+                perm_all = self._buf('perm', (world * rp, N), torch.int32)
+                send_p = self._buf('perm_ag_send', (rp, N), torch.int32)
+                p0, p1 = min(P, rank * rp), min(P, (rank + 1) * rp)
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=self.device)
+                free = torch.cuda.Event()
+                free.record(torch.cuda.current_stream(self.device))   # earlier users of the buffers are done
+                self._copy_stream.wait_event(free)
+                with torch.cuda.stream(self._copy_stream):
+                    if p1 > p0:
+                        send_p[:p1 - p0].copy_(as_t(perm_idx, torch.int32)[p0:p1], non_blocking=True)
+                    dist.all_gather_into_tensor(perm_all, send_p)
+                    self._bcast_perm_ready = torch.cuda.Event()
+                    self._bcast_perm_ready.record(self._copy_stream)
+                perm_d = perm_all[:P]
+            s_host = scores.numpy() if isinstance(scores, torch.Tensor) else np.asarray(scores)
+            return self.stage(ascii_all[:N], s_host, perm_d, use_gc=use_gc)
+
     def _ensure_y(self):
         """Tiled Y operand, column sums and sum of squares (mepp_build_y), once per staged dataset."""
         if self._ysum is None:
@@ -579,7 +623,8 @@ class Engine:
         self.last_paths = []
         self._post_done.clear()     # (every chain of the previous call was waited for when its group was collected)
         store = stats_host.alloc_positions(T_all, L, self.P)
-        density_all = np.empty((T_all, N), dtype=np.int32)
+        # matches per (task, sequence): <= L, so two bytes do whenever L <= 65535 (half the result bytes of a step)
+        density_all = np.empty((T_all, N), dtype=np.uint16 if L <= 65535 else np.int32)
         outs = []
         with torch.cuda.device(self.device):
             pending = None
@@ -857,7 +902,13 @@ class Engine:
             self.launches += 2 if P > 0 else 1
             ev = self._mark(ev, 'finalize')
             dev = {'finalized': out_d}
-            dev['density'] = density
+            if L <= 65535:
+                d16 = self._buf(f'density16_{slot}', (T, self.n_pad), torch.int16)
+                _lib.check(_lib.lib.mepp_density_u16(_ptr(density), T * self.n_pad, _ptr(d16), st), "density_u16")
+                self.launches += 1
+                dev['density'] = d16
+            else:
+                dev['density'] = density
             dev['hit_count'] = hit_count
             if path == 'sparse':
                 dev['entry_count'] = entry_count
@@ -914,7 +965,7 @@ class Engine:
 
         def job(a, b):
             stats_host.store_finalized(store, t0, h['finalized'], T, self.L, a, b)
-            density_all[t0 + a:t0 + b] = h['density'][a:b, :N]
+            density_all[t0 + a:t0 + b] = h['density'].view(density_all.dtype)[a:b, :N]
 
         n_chunks = max(1, min(self.copy_threads, T // 8))
         bounds = [T * i // n_chunks for i in range(n_chunks + 1)]

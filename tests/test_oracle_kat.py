@@ -184,3 +184,40 @@ def test_c_restatement_equals_numpy_oracle():
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
             for mg in (0, 2):
                 assert np.array_equal(profile.blur(a, mg, dtype=np.float32), cref.blur(a, mg))
+
+
+def test_accuracy_report_gates_pass_on_oracle_output_and_fail_on_a_perturbed_one():
+    """oracle/checks.py (the accuracy block of bench.py): the oracle's own dense results satisfy every gate, a
+    dropped match / a shifted r do not."""
+    from oracle import checks, profile, staging
+    from mepp_b200 import synth
+    cfg = synth.make_config("cfg1", n_seq=300, n_motifs=2, n_perm=40)
+    codes = staging.ascii_to_codes(cfg["ascii"])
+    Y = staging.permuted_scores(cfg["scores"], cfg["perm_idx"])
+    z = staging.gc_ratio_global(codes)
+    tasks = [(pwm, o) for _, pwm, o in cfg["tasks"]]
+    hit_dtype = np.dtype([('task', np.int32), ('seq', np.int32), ('pos', np.int32), ('x0', np.float32)])
+    hits, rs, pos = [], [], {}
+    for k, (pwm, o) in enumerate(tasks):
+        Wf, Wr, thr = profile.motif_weights(pwm, o)
+        X0 = profile.scan(codes, Wf, Wr, thr)
+        s, p = np.nonzero(X0)
+        h = np.zeros(s.size, dtype=hit_dtype)
+        h['task'], h['seq'], h['pos'], h['x0'] = k, s, p, X0[s, p]
+        hits.append(h)
+        X = profile.blur(X0, cfg["margin"], dtype=np.float32)
+        r = np.nan_to_num(profile.positional_correlation(X.astype(np.float64), Y.astype(np.float64),
+                                                         z.astype(np.float64)), nan=0.0).astype(np.float32)
+        rs.append(r)
+        cols = profile.positional_r_columns(r)
+        for name, v in cols.items():
+            pos.setdefault(name, []).append(np.asarray(v))
+    hits = np.concatenate(hits)
+    r = np.stack(rs)
+    pos = {k: np.stack(v) for k, v in pos.items()}
+    rep = checks.accuracy_report(codes, Y, z, tasks, list(range(len(tasks))), cfg["margin"], hits, r, pos, threads=2)
+    assert rep["match_sets_equal"] and rep["match_scores_bit_equal"] and rep["r_within_1e5_gate"]
+    assert rep["pvalue_flips"] == 0 and rep["ci_max_abs_err"] < 1e-6 and rep["matches_checked"] == hits.size > 0
+    bad = checks.accuracy_report(codes, Y, z, tasks, list(range(len(tasks))), cfg["margin"], hits[1:], r * 1.001, pos,
+                                 threads=2)
+    assert not bad["match_sets_equal"] and not bad["r_within_1e5_gate"]
