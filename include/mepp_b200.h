@@ -327,6 +327,16 @@ int mepp_finalize_positions(const float* r_dev, int64_t ldr, int T, int L, int C
  * n must be a multiple of 4 (rows are padded to 32 sequences). */
 int mepp_density_u16(const int32_t* density_dev, int64_t n, uint16_t* out_dev, void* stream);
 
+/* ------------------------------------------------------------------ host: output tables
+ * Tab-separated table of numeric columns, byte-identical to pandas.DataFrame.to_csv(path, sep='\t', index=False)
+ * (how mepp/single.py:223-241 writes positions_df.tsv / ranks_df.tsv): header_line = the tab-joined column names,
+ * col_kind[c]: 0 float64, 1 float32, 2 int64, 3 int32, 4 uint16 (as an integer), 5 uint16 printed as float64;
+ * col_ptr[c] / col_stride_bytes[c]: first element and byte stride of column c (a stride of 0 repeats one value, for
+ * the columns the reference broadcasts over all rows).  Floats are written as numpy's str(): shortest digits that
+ * round-trip in the column's precision, positional for 1e-4 <= |x| < 1e16, NaN as the empty string.  Host only. */
+int mepp_write_tsv(const char* path, const char* header_line, int n_cols, const int32_t* col_kind,
+                   const void* const* col_ptr, const int64_t* col_stride_bytes, int64_t n_rows);
+
 #ifdef __cplusplus
 }
 #endif

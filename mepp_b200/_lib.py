@@ -68,6 +68,7 @@ SIGNATURES = {
     "mepp_finalize_out_bytes": (_i64, [_i32, _i32]),
     "mepp_finalize_positions": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32,
                                        C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, _vp, _vp]),
+    "mepp_write_tsv": (_i32, [C.c_char_p, C.c_char_p, _i32, _vp, _vp, _vp, _i64]),
     "mepp_density_u16": (_i32, [_vp, _i64, _vp, _vp]),
     "mepp_x_planes_reset": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]),
     "mepp_profile_gemm": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp]),

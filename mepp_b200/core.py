@@ -40,12 +40,14 @@ class ProcessedDataset:
 
 
 def profile_tasks(dataset, tasks, motif_margin=0, confidence_interval_pct=95, center=None, return_hits=False,
-                  return_r=False, honour_flags=False, motif_pseudocount=0.0001, motif_pvalue=0.0001, bg=None):
-    """Batched hot path: tasks = [(motif_matrix (4, m), orientation), ...] -> engine.ProfileBatch."""
+                  return_r=False, honour_flags=False, motif_pseudocount=0.0001, motif_pvalue=0.0001, bg=None,
+                  on_group=None):
+    """Batched hot path: tasks = [(motif_matrix (4, m), orientation), ...] -> engine.ProfileBatch.
+    on_group(t0, t1, positions, density) is called when the results of tasks t0 .. t1-1 are on the host."""
     eng = dataset.engine()
     return eng.profile(tasks, margin=motif_margin, confidence_interval_pct=confidence_interval_pct, center=center,
                        return_hits=return_hits, return_r=return_r, honour_flags=honour_flags,
-                       pseudocount=motif_pseudocount, pvalue=motif_pvalue, bg=bg)
+                       pseudocount=motif_pseudocount, pvalue=motif_pvalue, bg=bg, on_group=on_group)
 
 
 def dataset_and_motif_matrix_to_profile_data(

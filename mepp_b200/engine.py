@@ -590,8 +590,11 @@ class Engine:
     # ------------------------------------------------------------------ tasks
     def profile(self, tasks, margin=0, confidence_interval_pct=95, center=None, return_hits=False,
                 return_r=False, hits_cap=None, tables=None, honour_flags=False, pseudocount=1e-4, pvalue=1e-4,
-                bg=None):
-        """Run (motif_matrix (4, m), orientation) tasks.  Returns a ProfileBatch."""
+                bg=None, on_group=None):
+        """Run (motif_matrix (4, m), orientation) tasks.  Returns a ProfileBatch.  on_group(t0, t1, positions,
+        density), if given, is called as soon as the results of tasks t0 .. t1-1 are in the host tables (rows t0 .. t1-1
+        of the {column: (T, L)} positions and of the (T, N) density are final): the caller can serialise them while
+        the later groups are still on the GPU."""
         if not self.staged:
             raise RuntimeError("Engine.stage() must be called first")
         if not 0 <= int(margin) <= _lib.MAX_MARGIN:
@@ -626,6 +629,13 @@ class Engine:
         # matches per (task, sequence): <= L, so two bytes do whenever L <= 65535 (half the result bytes of a step)
         density_all = np.empty((T_all, N), dtype=np.uint16 if L <= 65535 else np.int32)
         outs = []
+        pos_view = stats_host.positions_view(store, center) if on_group is not None else None
+
+        def collected(o):
+            outs.append(o)
+            if on_group is not None:
+                on_group(o['t0'], o['t0'] + o['T'], pos_view, density_all)
+
         with torch.cuda.device(self.device):
             pending = None
             all_tables = []
@@ -646,14 +656,14 @@ class Engine:
                                          confidence_interval_pct, gi % 2)
                 nxt['t0'] = g0
                 if pending is not None:
-                    outs.append(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
+                    collected(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
                 pending = nxt
                 if return_hits or return_r:
                     # the match list / r buffers are reused by the next group: no overlap in this mode
-                    outs.append(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
+                    collected(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
                     pending = None
             if pending is not None:
-                outs.append(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
+                collected(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
         cat = lambda k: np.concatenate([o[k] for o in outs], axis=0)
         # what the last call moved, for the roofline accounting of bench.py
         self.last_stats = dict(hits=int(sum(int(o['hit_count'][0]) for o in outs)),
@@ -974,7 +984,7 @@ class Engine:
         else:
             for f in [_copy_pool(self.copy_threads).submit(job, bounds[i], bounds[i + 1]) for i in range(n_chunks)]:
                 f.result()
-        out = dict(T=T)
+        out = dict(T=T, t0=t0)
         out['entries'] = int(h['nnz'][0]) if 'nnz' in h else 0
         nh = int(h['hit_count'][0])
         out['hit_count'] = np.array([nh], dtype=np.int64)

@@ -99,11 +99,18 @@ def scored_fasta_filepath_to_dicts(fasta_filepath, **kwargs):
         return scored_fasta_file_to_dicts(fasta_file, **kwargs)
 
 
-def save_dataset(dataset, path, compression=None, element_spec_suffix='.element_spec.p', delete_existing=False):
+def save_dataset(dataset, path, compression=None, element_spec_suffix='.element_spec.p', delete_existing=False,
+                 arrays=True):
+    """io.py:97-115.  arrays=False writes only the element_spec sidecar (run_batch, when the dataset directory is
+    removed again right after the run)."""
     normpath = os.path.normpath(path)
     if delete_existing and os.path.exists(normpath):
         shutil.rmtree(normpath)
     os.makedirs(normpath, exist_ok=True)
+    if not arrays:
+        with open(os.path.normpath(f'{path}{element_spec_suffix}'), 'wb') as f:
+            p.dump(dataset.element_spec, f)
+        return
     arrays = dict(ascii=dataset.ascii, scores=dataset.scores, has_gc=np.array(dataset.has_gc),
                   batch_size=np.array(dataset.batch_size if dataset.batch_size is not None else -1))
     if dataset.perm_idx is not None:

@@ -14,6 +14,9 @@ from .utils import (append_gc_ratios_to_dataset, filter_scored_fasta_df, force_c
                     order_scored_fasta_df, scored_fasta_df_to_dataset, scored_fasta_dicts_to_df)
 
 
+LAST_RUN_TIMINGS = {}      # wall-clock phases of the last run_mepp call of this process (bench.py --mode fullrun)
+
+
 def run_mepp(
     scored_fasta_filepath, motifs_filepath, out_filepath,
     center=None, degenerate_pct_thresh=100, num_permutations=1000, batch_size=1000,
@@ -28,34 +31,83 @@ def run_mepp(
     permutation_seed=None, shuffle_seed=None
 ):
     gc_ratio_type = 'global'                                               # mepp.py:96
+    import time
+    import numpy as np
+    import torch.distributed as dist
+    timings = LAST_RUN_TIMINGS
+    timings.clear()
+    t_run = time.perf_counter()
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    rank = dist.get_rank() if multi else 0
     os.makedirs(normpath(out_filepath), exist_ok=True)
     if no_gpu:
         force_cpu_only()
     else:
         manage_gpu_memory()
-    sequence_dict, score_dict, description_dict = scored_fasta_filepath_to_dicts(scored_fasta_filepath)
-    scored_fasta_df = order_scored_fasta_df(
-        filter_scored_fasta_df(scored_fasta_dicts_to_df(sequence_dict, score_dict, description_dict),
-                               degenerate_pct_thresh=degenerate_pct_thresh),
-        random_state=shuffle_seed)
-    scored_fasta_df.to_csv(normpath(f'{out_filepath}/filtered_data_df.tsv'), sep='\t', index=False)
-    scored_fasta_df.to_pickle(normpath(f'{out_filepath}/filtered_data_df.pkl'))
-    dataset = add_permuted_scores_to_dataset(
-        append_gc_ratios_to_dataset(scored_fasta_df_to_dataset(scored_fasta_df, batch_size=batch_size,
-                                                               n_jobs=n_cpu_jobs), gc_ratio_type=gc_ratio_type),
-        batch_size=batch_size, num_permutations=num_permutations, seed=permutation_seed)
-    motif_matrix_dict, _motif_consensus_dict = motif_matrix_filepath_to_dicts(motifs_filepath)
-    filepaths_df = run_batch(
-        dataset=dataset, motif_matrix_dict=motif_matrix_dict, out_filepath=out_filepath, center=center,
-        motif_orientations=motif_orientations, motif_margin=motif_margin, motif_pseudocount=motif_pseudocount,
-        motif_pvalue=motif_pvalue, bg=bg, confidence_interval_pct=confidence_interval_pct,
-        motif_score_sigma=motif_score_sigma, motif_score_cmap=motif_score_cmap,
-        rank_smoothing_factor=rank_smoothing_factor, figure_width=figure_width, figure_height=figure_height,
-        save_datasets=save_datasets, keep_dataset=keep_dataset, save_profile_data=save_profile_data,
-        save_motif_score_matrix=save_motif_score_matrix, save_figures=True, figure_formats=figure_formats,
-        figure_dpi=figure_dpi, n_jobs=n_gpu_jobs, no_gpu=no_gpu, stop_max_attempt_number=stop_max_attempt_number,
-        wait_random_min=wait_random_min, wait_random_max=wait_random_max)
-    filepaths_df.to_csv(normpath(f'{out_filepath}/filepaths.tsv'), sep='\t', index=False)     # mepp.py:197-199
+    # the writer processes of the task directories start now, so that their interpreter start-up (numpy, pandas)
+    # is hidden behind the parsing of the inputs
+    from .writer import TaskWriter
+    try:
+        big = os.path.getsize(scored_fasta_filepath) > (16 << 20)
+    except (OSError, TypeError):
+        big = False
+    task_writer = TaskWriter(None, prestart=big)
+    try:
+        if multi:
+            # every rank parses the same files; the shuffle and permutation seeds (unseeded in the reference:
+            # utils.py:117, permutations.py:33-37) are drawn ONCE, on rank 0, so that all ranks order the rows and
+            # permute the scores identically; only rank 0 writes the run-level files
+            seeds = [shuffle_seed if shuffle_seed is not None else int(np.random.SeedSequence().entropy % (1 << 32)),
+                     permutation_seed if permutation_seed is not None else
+                     int(np.random.SeedSequence().entropy % (1 << 63))]
+            dist.broadcast_object_list(seeds, src=0)
+            shuffle_seed, permutation_seed = seeds
+        sequence_dict, score_dict, description_dict = scored_fasta_filepath_to_dicts(scored_fasta_filepath)
+        scored_fasta_df = order_scored_fasta_df(
+            filter_scored_fasta_df(scored_fasta_dicts_to_df(sequence_dict, score_dict, description_dict),
+                                   degenerate_pct_thresh=degenerate_pct_thresh),
+            random_state=shuffle_seed)
+        timings['parse_filter_order_s'] = time.perf_counter() - t_run
+        # filtered_data_df.{tsv,pkl} (mepp.py:99-104; 100 MB of text at cfg 3) are written by a thread beside the
+        # staging of the dataset and the tasks
+        from concurrent.futures import ThreadPoolExecutor
+        side = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mepp-filtered-df")
+
+        def write_filtered():
+            scored_fasta_df.to_csv(normpath(f'{out_filepath}/filtered_data_df.tsv'), sep='\t', index=False)
+            scored_fasta_df.to_pickle(normpath(f'{out_filepath}/filtered_data_df.pkl'))
+
+        filtered_written = side.submit(write_filtered) if rank == 0 else None
+        t0 = time.perf_counter()
+        dataset = add_permuted_scores_to_dataset(
+            append_gc_ratios_to_dataset(scored_fasta_df_to_dataset(scored_fasta_df, batch_size=batch_size,
+                                                                   n_jobs=n_cpu_jobs), gc_ratio_type=gc_ratio_type),
+            batch_size=batch_size, num_permutations=num_permutations, seed=permutation_seed)
+        task_writer.set_scores(dataset.scores)
+        motif_matrix_dict, _motif_consensus_dict = motif_matrix_filepath_to_dicts(motifs_filepath)
+        timings['dataset_permutations_motifs_s'] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        filepaths_df = run_batch(
+            dataset=dataset, motif_matrix_dict=motif_matrix_dict, out_filepath=out_filepath, center=center,
+            motif_orientations=motif_orientations, motif_margin=motif_margin, motif_pseudocount=motif_pseudocount,
+            motif_pvalue=motif_pvalue, bg=bg, confidence_interval_pct=confidence_interval_pct,
+            motif_score_sigma=motif_score_sigma, motif_score_cmap=motif_score_cmap,
+            rank_smoothing_factor=rank_smoothing_factor, figure_width=figure_width, figure_height=figure_height,
+            save_datasets=save_datasets, keep_dataset=keep_dataset, save_profile_data=save_profile_data,
+            save_motif_score_matrix=save_motif_score_matrix, save_figures=True, figure_formats=figure_formats,
+            figure_dpi=figure_dpi, n_jobs=n_gpu_jobs, no_gpu=no_gpu, stop_max_attempt_number=stop_max_attempt_number,
+            wait_random_min=wait_random_min, wait_random_max=wait_random_max, task_writer=task_writer)
+        timings['run_batch_s'] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        if filtered_written is not None:
+            filtered_written.result()
+        side.shutdown(wait=True)
+        timings['wait_filtered_df_s'] = time.perf_counter() - t0
+    finally:
+        task_writer.close()
+    if rank == 0:
+        filepaths_df.to_csv(normpath(f'{out_filepath}/filepaths.tsv'), sep='\t', index=False)     # mepp.py:197-199
+    timings['total_s'] = time.perf_counter() - t_run
     results_html_filepaths, clustermap_html_filepaths = {}, {}
     try:
         from .clustering import filepaths_df_to_clustering_results  # optional reporting layer (out of scope)

@@ -9,13 +9,35 @@ matrix itself is only ever materialised on the GPU, as the tiled fp16 GEMM opera
 import numpy as np
 
 
-def make_permutation_indices(num_sequences, num_permutations, seed=None):
-    """(P, N) int32; row p is a uniform random permutation (numpy Generator PCG64(seed))."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    out = np.empty((num_permutations, num_sequences), dtype=np.int32)
-    base = np.arange(num_sequences, dtype=np.int32)
-    for p in range(num_permutations):
-        out[p] = rng.permutation(base)
+PERM_CHUNK = 64     # rows per independent random stream: the result does not depend on the number of threads
+
+
+def make_permutation_indices(num_sequences, num_permutations, seed=None, threads=None, out=None):
+    """(P, N) int32; row p is a uniform random permutation.  Rows are drawn in chunks of PERM_CHUNK, chunk c from
+    numpy Generator(PCG64(SeedSequence(seed, spawn_key=(c,)))), so that the chunks can be filled by several host
+    threads (numpy shuffles without the GIL; 1000 x 100 000 indices: 2.7 s on one core) and a seed still fixes every
+    index.  seed=None draws fresh entropy once."""
+    from concurrent.futures import ThreadPoolExecutor
+    from .parallel import host_threads
+    P, N = int(num_permutations), int(num_sequences)
+    if out is None:
+        out = np.empty((P, N), dtype=np.int32)
+    entropy = np.random.SeedSequence(seed).entropy
+    base = np.arange(N, dtype=np.int32)
+
+    def fill(c):
+        rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(entropy, spawn_key=(c,))))
+        for p in range(c * PERM_CHUNK, min(P, (c + 1) * PERM_CHUNK)):
+            out[p] = rng.permutation(base)
+
+    n_chunks = -(-P // PERM_CHUNK)
+    threads = host_threads() if threads is None else int(threads)
+    if threads <= 1 or n_chunks <= 1 or P * N < (1 << 22):
+        for c in range(n_chunks):
+            fill(c)
+    else:
+        with ThreadPoolExecutor(max_workers=min(threads, n_chunks)) as ex:
+            list(ex.map(fill, range(n_chunks)))
     return out
 
 

@@ -36,7 +36,18 @@ def filter_scored_fasta_df(scored_fasta_df, degenerate_pct_thresh=100, sequence_
         sequence_length = df['length'].max()
     if sequence_length is not None:
         df = df[df['length'] == sequence_length].copy()
-    df['degenerate_pct'] = df['sequence'].map(get_degenerate_pct)
+    seqs = list(df['sequence'])
+    if sequence_length is not None and seqs:
+        # all rows have one length now: the share of characters outside ACGT (upper case; onehot_dna.py:41-53) of every
+        # sequence from one byte matrix instead of one Python call per sequence
+        try:
+            from .onehot_dna import _IS_ACGT
+            a = seqs_to_ascii(seqs, int(sequence_length))
+            df['degenerate_pct'] = 100.0 * (~_IS_ACGT[a]).sum(axis=1) / float(sequence_length)
+        except ValueError:                      # (rows of unequal byte length: per-sequence path)
+            df['degenerate_pct'] = df['sequence'].map(get_degenerate_pct)
+    else:
+        df['degenerate_pct'] = df['sequence'].map(get_degenerate_pct)
     return df[df['degenerate_pct'] <= degenerate_pct_thresh].copy().reset_index(drop=True)
 
 

@@ -2,6 +2,8 @@
 oracle on the same seeded inputs.  Bit-exact for match positions / scores / counts; profiles,
 confidence intervals within 1e-5 relative (with a floor tied to the row scale); p-values
 reported with their discrete flips."""
+import os
+
 import numpy as np
 import pytest
 
@@ -226,6 +228,43 @@ def test_run_mepp_writes_the_reference_layout(tmp_path):
     assert _r_close(pos['positional_r'].to_numpy()[:, None], orc['r'][:, :1]).all()
     ranks = pd.read_pickle(d / "ranks_df.pkl")
     assert np.array_equal(ranks['density'].to_numpy(), orc['ranks']['density'])
+
+
+def test_run_batch_isolates_a_poisoned_motif(tmp_path):
+    """One motif the kernels cannot take (40 positions > 32) and one non-finite matrix fail ALONE -- retval 1 and a
+    reason in wrapped_params.log for their rows of filepaths_df, like a failed child process of the reference
+    (single.py:392-406, batch.py:174-185); every other task runs and its tables are what pandas would write."""
+    import pandas as pd
+    from mepp_b200 import synth, batch as batch_mod, utils as mutils, permutations
+    from mepp_b200.dataset import ScoredDataset
+    ascii_u8, scores = synth.synth_sequences(400, 150, seed=33)
+    ds = permutations.add_permuted_scores_to_dataset(
+        mutils.append_gc_ratios_to_dataset(ScoredDataset(ascii_u8, scores)), num_permutations=25, seed=3)
+    good = synth.synth_motifs(3, seed=8, m_lo=6, m_hi=12)
+    long_pwm = np.full((4, 40), 0.25)
+    nan_pwm = good[0].copy()
+    nan_pwm[0, 0] = np.nan
+    motifs = {'G0 a': good[0], 'TOO_LONG x': long_pwm, 'G1 b': good[1], 'BAD nan': nan_pwm, 'G2 c': good[2]}
+    fdf = batch_mod.run_batch(ds, motifs, str(tmp_path / 'out'), motif_orientations=['+', '+/-'], motif_margin=2)
+    assert len(fdf) == 10
+    bad = fdf['motif_id'].isin(['TOO_LONG x', 'BAD nan'])
+    assert (fdf.loc[bad, 'retval'] == 1).all() and (fdf.loc[~bad, 'retval'] == 0).all()
+    assert (fdf['attempts'] == 1).all()
+    for _, row in fdf[bad].iterrows():
+        assert os.path.exists(row['params']) and os.path.exists(os.path.join(row['outdir'], 'motif_matrix.npy'))
+        assert ('at most 32' in open(row['log']).read()) or ('non-finite' in open(row['log']).read())
+        assert not os.path.exists(os.path.join(row['outdir'], 'positions_df.tsv'))
+    for _, row in fdf[~bad].iterrows():
+        assert open(row['log']).read() == ''
+        for name in ('positions_df', 'ranks_df'):
+            df = pd.read_pickle(os.path.join(row['outdir'], f'{name}.pkl'))
+            assert open(os.path.join(row['outdir'], f'{name}.tsv')).read() == df.to_csv(sep='\t', index=False)
+    # the good tasks equal a run without the poisoned motifs
+    ref = batch_mod.run_batch(ds.replace(), {k: v for k, v in motifs.items() if k.startswith('G')},
+                              str(tmp_path / 'ref'), motif_orientations=['+', '+/-'], motif_margin=2)
+    for (_, a), (_, b) in zip(fdf[~bad].iterrows(), ref.iterrows()):
+        pa, pb = (pd.read_pickle(os.path.join(r['outdir'], 'positions_df.pkl')) for r in (a, b))
+        assert pa.equals(pb)
 
 
 def test_motif_length_and_margin_extremes():

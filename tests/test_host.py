@@ -404,3 +404,106 @@ def test_tc_scan_pipeline_protocol_has_no_deadlock():
     for bns in cases:
         for seed in range(2):
             assert sim.run(40, bns, seed=seed), (bns, seed)
+
+
+def test_native_tsv_writer_is_byte_identical_to_pandas(tmp_path):
+    """mepp_write_tsv (csrc/writer.cu) against DataFrame.to_csv(sep='\\t', index=False) -- how single.py:223-241
+    writes positions_df.tsv / ranks_df.tsv: shortest digits per column precision, numpy's positional / scientific
+    rule, NaN as the empty string, broadcast (stride 0) columns."""
+    import pandas as pd
+    from mepp_b200 import writer
+    rng = np.random.Generator(np.random.PCG64(5))
+    n = 4000
+    special = np.array([0.0, -0.0, 1.0, -1.0, 1e-4, 9.999999e-5, 1e-5, 1.5e-7, 1e15, 9.999999999999998e15, 1e16, 1.2345e22,
+                        np.nan, np.inf, -np.inf, 5e-324, 1.7976931348623157e308, 0.1, 1 / 3, 123456.789, 2.5e-300, 3.0])
+    f64 = np.concatenate([special, rng.normal(size=n - special.size) * 10.0 ** rng.integers(-12, 20, n - special.size)])
+    f32 = np.concatenate([special.astype(np.float32), (rng.normal(size=n - special.size) *
+                                                       10.0 ** rng.integers(-10, 12, n - special.size)).astype(np.float32)])
+    cols = {
+        'positional_r': f32, 'permutation_full_positional_r_lower': f64,
+        'position': np.arange(n) - n // 2, 'count': rng.integers(0, 50, n).astype(np.float64),
+        'i32': rng.integers(-2 ** 31, 2 ** 31 - 1, n).astype(np.int32),
+        'integral_r': np.broadcast_to(np.float32(0.123456789), (n,)),
+        'bcast64': np.broadcast_to(np.float64(-1.25e-9), (n,)),
+        'u16': rng.integers(0, 65535, n).astype(np.uint16),
+    }
+    a, b = str(tmp_path / 'a.tsv'), str(tmp_path / 'b.tsv')
+    writer.write_tsv(a, cols)
+    pd.DataFrame({k: np.array(v) for k, v in cols.items()}).to_csv(b, sep='\t', index=False)
+    assert open(a, 'rb').read() == open(b, 'rb').read()
+    # density: uint16 on the wire, float64 in the reference's ranks_df (core.py:456-470)
+    dens = rng.integers(0, 7, n).astype(np.uint16)
+    scores = rng.normal(5, 2, n).astype(np.float32)
+    writer.write_tsv(a, dict(rank=np.arange(n), score=scores, density=dens), float_uint16=('density',))
+    pd.DataFrame(dict(rank=np.arange(n), score=scores, density=dens.astype(np.float64))).to_csv(b, sep='\t', index=False)
+    assert open(a, 'rb').read() == open(b, 'rb').read()
+    # empty table, and a dtype the native writer does not take (falls to pandas, same bytes by construction)
+    writer.write_tsv(a, dict(x=np.zeros(0), y=np.zeros(0, dtype=np.int64)))
+    assert open(a).read() == 'x\ty\n'
+    writer.write_tsv(a, dict(s=np.array(['p', 'q'], dtype=object), v=np.array([1.5, 2.5])))
+    assert open(a).read() == 's\tv\np\t1.5\nq\t2.5\n'
+
+
+def test_libyaml_dump_equals_the_python_emitter(tmp_path):
+    """writer.yaml_dump (libyaml) writes the text yaml.dump(..., default_flow_style=False, allow_unicode=True) does
+    (single.py:280-302) for the parameter / filepath dictionaries of a task."""
+    import yaml
+    from mepp_b200 import writer
+    from mepp_b200.single import _task_filepaths
+    params = dict(dataset_filepath='out/dataset', motif_matrix_filepath='out/x/orientation_fwd/motif_matrix.npy',
+                  motif_id='MA0001.1 AGL3 é', output_filepath='out/x', center=None, motif_orientation='+/-',
+                  motif_margin=2, motif_pseudocount=0.0001, motif_pvalue=1e-4, bg=None, confidence_interval_pct=95,
+                  motif_score_sigma=0.5, motif_score_cmap='gray', rank_smoothing_factor=5, figure_width=10,
+                  figure_height=10, save_datasets=False, save_profile_data=True, save_motif_score_matrix=False,
+                  save_figures=True, figure_formats=['png', 'svg'], figure_dpi=300, no_gpu=False,
+                  bg_list=[0.25, 0.25, 0.25, 0.25])
+    fps = _task_filepaths('out/x', 'out/dataset', 'out/x/motif_matrix.npy', ['png', 'svg'])
+    for obj in (params, fps):
+        p = str(tmp_path / 'o.yaml')
+        writer.yaml_dump(obj, p)
+        assert open(p, encoding='utf8').read() == yaml.dump(obj, Dumper=yaml.Dumper, default_flow_style=False,
+                                                            allow_unicode=True)
+        assert yaml.safe_load(open(p, encoding='utf8')) == obj
+
+
+def test_task_writer_pool_writes_the_reference_layout_and_isolates_failures(tmp_path):
+    """writer.TaskWriter: spawned writer processes produce the files of single.py:198-302 / 342-391 per task; a job
+    that fails (an error recorded by the scheduler, or an unwritable path) yields retval 1 for that task only."""
+    import pandas as pd
+    from mepp_b200 import writer
+    from mepp_b200.single import _task_filepaths
+    rng = np.random.Generator(np.random.PCG64(9))
+    N, L = 500, 60
+    scores = np.sort(rng.normal(5, 2, N)).astype(np.float32)
+    tw = writer.TaskWriter(scores, n_workers=2)
+    jobs = []
+    for i in range(3):
+        outdir = str(tmp_path / f'm{i}' / 'orientation_fwd')
+        fps = _task_filepaths(outdir, str(tmp_path / 'dataset'), f'{outdir}/motif_matrix.npy', ['png'])
+        fps.pop('mepp_plot')
+        pos = dict(positional_r=rng.normal(size=L).astype(np.float32), position=np.arange(L) - L // 2,
+                   integral_r=np.broadcast_to(np.float32(0.5), (L,)), count=rng.integers(0, 9, L).astype(np.float64))
+        job = dict(outdir=outdir, motif_matrix=np.full((4, 6), 0.25), wrapped_params=dict(motif_id=f'm{i}', center=None),
+                   params=dict(motif_id=f'm{i}'), filepaths=fps, positions=pos,
+                   density=rng.integers(0, 4, N).astype(np.uint16), motif_score_matrix=None, save_profile_data=True,
+                   save_motif_score_matrix=False, error='motif longer than 32 taps' if i == 1 else None)
+        jobs.append(job)
+        tw.submit(job)
+    res = tw.results()
+    tw.close()
+    assert [r[0] for r in res] == [0, 1, 0]
+    assert 'motif longer than 32 taps' in open(res[1][2]).read() and open(res[0][2]).read() == ''
+    for i in (0, 2):
+        d = jobs[i]['outdir']
+        for f in ('motif_matrix.npy', 'wrapped_params.yaml', 'wrapped_params.log', 'params.yaml', 'filepaths.yaml',
+                  'positions_df.tsv', 'positions_df.pkl', 'ranks_df.tsv', 'ranks_df.pkl'):
+            assert os.path.exists(os.path.join(d, f)), f
+        ranks = pd.read_pickle(os.path.join(d, 'ranks_df.pkl'))
+        assert list(ranks.columns) == ['rank', 'score', 'density'] and ranks['density'].dtype == np.float64
+        tsv = pd.read_csv(os.path.join(d, 'ranks_df.tsv'), sep='\t')
+        assert np.array_equal(tsv['density'].to_numpy(), jobs[i]['density'].astype(np.float64))
+        assert np.array_equal(tsv['score'].to_numpy().astype(np.float32), scores)
+        pos = pd.read_pickle(os.path.join(d, 'positions_df.pkl'))
+        assert list(pos.columns) == list(jobs[i]['positions'])
+        assert open(os.path.join(d, 'positions_df.tsv')).read() == pos.to_csv(sep='\t', index=False)
+    assert not os.path.exists(os.path.join(jobs[1]['outdir'], 'positions_df.tsv'))
