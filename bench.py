@@ -287,6 +287,10 @@ def main():
                     help="step: the hot path per step (the JSON line of the contract); fullrun: run_mepp wall clock, "
                          "scored FASTA file -> complete output directory")
     ap.add_argument("--fullrun-repeats", type=int, default=1, help="timed run_mepp runs after the warm-up run")
+    ap.add_argument("--no-fullrun", action="store_true", help="skip the run_mepp wall-clock measurement of the step line")
+    ap.add_argument("--simulate-world", type=int, default=0,
+                    help="diagnostic: one process runs only shard 0 of this many shards of the task list (the per-rank "
+                         "work of a strong-scaling run); the printed value is NOT a bench value")
     ap.add_argument("--no-accuracy", action="store_true", help="skip the full-size oracle check of a few tasks")
     ap.add_argument("--accuracy-tasks", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -330,6 +334,8 @@ def main():
         return
     T_total = len(tasks)
     my_ids = parallel.shard_task_units(tasks, world)[rank]    # LPT over (motif) units: orientation pairs stay together
+    if args.simulate_world > 1 and world == 1:
+        my_ids = parallel.shard_task_units(tasks, args.simulate_world)[0]
     my_tasks = [tasks[i] for i in my_ids]
 
     # pinned host inputs (the e2e path copies them every step)
@@ -403,10 +409,21 @@ def main():
     # the step's work on the side streams); the host clock around the same region is kept as a cross-check
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    # a stream of steps through the asynchronous form of the call: the host side of step k's last task group (wait for
+    # its result copies, move them into step k's tables) runs while step k + 1 is on the GPU; every step's complete
+    # result tables are on the host when its result() returns, and the last one inside the timed region
+    eng.host_timing = {}
     ev_a.record(torch.cuda.current_stream(dev))
+    prev = None
     for _ in range(args.steps):
-        eng.profile(my_tasks, margin=margin, tables=dev_tables)
+        cur = eng.profile_async(my_tasks, margin=margin, tables=dev_tables)
+        if prev is not None:
+            prev.result()
+        prev = cur
+    prev.result()
     ev_b.record(torch.cuda.current_stream(dev))
+    host_phases = {k: round(v / max(1, args.steps), 3) for k, v in eng.host_timing.items() if k != 'calls'}
+    eng.host_timing = None
     sync_all()
     t1 = time.perf_counter()
     wall_value = t1 - t0
@@ -458,6 +475,11 @@ def main():
     dt_e2e = parallel.barrier_and_max(max(1e-3 * ev_c.elapsed_time(ev_d), t3 - t2), device=dev if world > 1 else None)
     clocks = sampler.stop(t0, t1)
     clocks["sampled"] = "during the device-resident timed region (100 ms period); halted for the e2e region"
+
+    # (3) the metric's second half: run_mepp wall clock, files in -> output directory out (every rank takes part)
+    fullrun = None
+    if not args.no_fullrun and args.simulate_world <= 1:
+        fullrun = run_fullrun(args, rank, world, cfg)
 
     if rank != 0:
         if world > 1:
@@ -568,7 +590,7 @@ def main():
                              profile_path=",".join(sorted(set(st["paths"]))),
                              profile="sparse: float64 gather of float32 Y rows per non-zero of X; "
                                      "tensor: fp16 hi/lo split, 3 tcgen05 products, fp32 TMEM accumulate",
-                             fallbacks=list(eng.fallbacks)),
+                             fallbacks=list(eng.fallbacks), host_ms_per_step=host_phases),
                 e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=1e3 * dt_e2e / args.steps,
                          h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
                 timing=dict(how="CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks",
@@ -577,7 +599,7 @@ def main():
                                     "group g on a high-priority stream" if eng.overlap else "none",
                             kernels="per-kernel times: CUDA events on the launching stream in a serial pass of %d steps "
                                     "(overlap off) right after the timed region" % kernel_steps),
-                gpu_launches=int(launches), roofline=roofline, kernels=kernels, accuracy=accuracy,
+                gpu_launches=int(launches), roofline=roofline, kernels=kernels, accuracy=accuracy, fullrun=fullrun,
                 cpu_baseline=cpu_baseline, clocks=clocks)
     print(json.dumps(line), flush=True)
     if world > 1:

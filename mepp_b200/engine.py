@@ -163,6 +163,20 @@ class DeviceTables:
         return np.array(rows, dtype=np.int32)
 
 
+class PendingProfile:
+    """A profile_async() call whose last task group may still be on the GPU."""
+
+    def __init__(self, eng, T_all, center, margin, ci, return_hits, return_r, on_group, n_groups):
+        self.eng, self.T_all, self.center, self.margin, self.ci = eng, T_all, center, margin, ci
+        self.return_hits, self.return_r, self.on_group, self.n_groups = return_hits, return_r, on_group, n_groups
+        self.outs, self.paths, self.all_tables = [], [], []
+        self.units = 0
+        self.dtab = self.store = self.density_all = self.pos_view = self.batch = None
+
+    def result(self):
+        return self.eng._finish(self)
+
+
 class Engine:
     def __init__(self, device=None, mem_budget_bytes=32 << 30, max_group=512):
         torch = _torch()
@@ -182,6 +196,7 @@ class Engine:
         self._aux_stream = None
         self.launches = 0   # kernels launched by this engine (bench.py reports it)
         self.timing = None  # set to {} to collect per-stage CUDA-event times (ms)
+        self.host_timing = None   # set to {} to accumulate the host-side phases of profile() calls (ms)
         self.fuse_correlation = True   # False: separate GEMM (S) + correlation kernels (tests / A-B runs)
         self.share_scans = os.environ.get("MEPP_SHARE_SCANS", "1") != "0"   # '+' rides on the '+/-' pass of its motif
         self.profile_path = os.environ.get("MEPP_PROFILE_PATH", "auto")     # 'auto' | 'sparse' | 'tensor'
@@ -195,6 +210,8 @@ class Engine:
         self.overlap = os.environ.get("MEPP_OVERLAP", "1") != "0"
         self._post_stream = None
         self._post_done = {}
+        self._carry = None          # the in-flight last group of a profile_async() call
+        self._slot = 0              # staging slot of the next task group (two slots, alternating over ALL launches)
         # bit-parallel first stage of the scan for the units whose expected survivor rate allows it
         # (mepp_scan_bitpar); a unit takes it when its modelled cost is below MEPP_BP_COST_RATIO x the pair tables'
         self.bitpar = os.environ.get("MEPP_SCAN_BITPAR", "0") != "0"
@@ -234,6 +251,7 @@ class Engine:
         """Stage one dataset: ascii (N, L) uint8, scores (N,) float32 (rows already ordered as the
         reference's order_scored_fasta_df leaves them), perm_idx (P, N) int32 or None."""
         torch = self.torch
+        self._drain()
         with torch.cuda.device(self.device):
             N, L = int(ascii_u8.shape[0]), int(ascii_u8.shape[1])
             if N < 4:
@@ -588,10 +606,13 @@ class Engine:
         return int(g)
 
     # ------------------------------------------------------------------ tasks
-    def profile(self, tasks, margin=0, confidence_interval_pct=95, center=None, return_hits=False,
-                return_r=False, hits_cap=None, tables=None, honour_flags=False, pseudocount=1e-4, pvalue=1e-4,
-                bg=None, on_group=None):
-        """Run (motif_matrix (4, m), orientation) tasks.  Returns a ProfileBatch.  on_group(t0, t1, positions,
+    def profile_async(self, tasks, margin=0, confidence_interval_pct=95, center=None, return_hits=False,
+                      return_r=False, hits_cap=None, tables=None, honour_flags=False, pseudocount=1e-4, pvalue=1e-4,
+                      bg=None, on_group=None):
+        """Enqueue (motif_matrix (4, m), orientation) tasks; returns a PendingProfile whose result() is the
+        ProfileBatch.  The last task group of the call stays in flight: its device -> host copies and the host side of
+        its results overlap whatever the caller enqueues next (the next profile_async call of a stream of task lists),
+        and are completed by result() at the latest.  At most one call is left in flight.  on_group(t0, t1, positions,
         density), if given, is called as soon as the results of tasks t0 .. t1-1 are in the host tables (rows t0 .. t1-1
         of the {column: (T, L)} positions and of the (T, N) density are final): the caller can serialise them while
         the later groups are still on the GPU."""
@@ -621,24 +642,18 @@ class Engine:
             G = min(G, max(32, -(-T_all // n_groups)))
         G += G & 1 if G < T_all else 0      # even: the ('+', '+/-') pair of a motif stays in one group
         groups = [(g0, min(g0 + G, T_all)) for g0 in range(0, T_all, G)]
-        self.last_groups = len(groups)
-        self._units_run = 0
-        self.last_paths = []
-        self._post_done.clear()     # (every chain of the previous call was waited for when its group was collected)
-        store = stats_host.alloc_positions(T_all, L, self.P)
+        call = PendingProfile(self, T_all, center, margin, confidence_interval_pct, return_hits, return_r, on_group,
+                              len(groups))
+        call.store = stats_host.alloc_positions(T_all, L, self.P)
         # matches per (task, sequence): <= L, so two bytes do whenever L <= 65535 (half the result bytes of a step)
-        density_all = np.empty((T_all, N), dtype=np.uint16 if L <= 65535 else np.int32)
-        outs = []
-        pos_view = stats_host.positions_view(store, center) if on_group is not None else None
-
-        def collected(o):
-            outs.append(o)
-            if on_group is not None:
-                on_group(o['t0'], o['t0'] + o['T'], pos_view, density_all)
-
+        call.density_all = np.empty((T_all, N), dtype=np.uint16 if L <= 65535 else np.int32)
+        call.pos_view = stats_host.positions_view(call.store, center) if on_group is not None else None
+        import time as _time
+        t_begin = _time.perf_counter()
         with torch.cuda.device(self.device):
-            pending = None
-            all_tables = []
+            # the last group of the PREVIOUS call may still be in flight (profile_async): it is collected, like any
+            # group, right after the next group has been enqueued, so the GPU never waits for the host side of a call
+            pending, self._carry = self._carry, None
             # host threshold DP: every group's tables are submitted to the host thread pool now and collected when
             # the group is launched, so the DP of the later groups runs while the earlier ones are on the GPU
             dtab = futures = None
@@ -648,30 +663,76 @@ class Engine:
                 dtab = self.device_tables_for(tasks, **table_kw)
             elif tables is None:
                 futures = [motif_layers.scan_tables_async(tasks[g0:g1], **table_kw) for g0, g1 in groups]
+            call.dtab = dtab
             for gi, (g0, g1) in enumerate(groups):
                 gt = dtab.slice(g0, g1) if dtab is not None else tables[g0:g1] if tables is not None else futures[gi]()
                 if dtab is None:
-                    all_tables.extend(gt)
-                nxt = self._launch_group(gt, margin, return_hits, return_r, hits_cap,
-                                         confidence_interval_pct, gi % 2)
+                    call.all_tables.extend(gt)
+                slot, self._slot = self._slot, self._slot ^ 1
+                nxt = self._launch_group(gt, margin, return_hits, return_r, hits_cap, confidence_interval_pct, slot)
                 nxt['t0'] = g0
+                nxt['call'] = call
+                call.units += self.last_units
+                call.paths.append(nxt['path'])
                 if pending is not None:
-                    collected(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
+                    self._collect(pending)
                 pending = nxt
                 if return_hits or return_r:
                     # the match list / r buffers are reused by the next group: no overlap in this mode
-                    collected(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
+                    self._collect(pending)
                     pending = None
-            if pending is not None:
-                collected(self._collect_group(pending, margin, confidence_interval_pct, store, density_all))
+            self._carry = pending
+        if self.host_timing is not None:
+            self.host_timing['enqueue_ms'] = self.host_timing.get('enqueue_ms', 0.0) + 1e3 * (_time.perf_counter() - t_begin)
+        return call
+
+    def profile(self, tasks, **kw):
+        """Run (motif_matrix (4, m), orientation) tasks.  Returns a ProfileBatch (= profile_async(...).result())."""
+        return self.profile_async(tasks, **kw).result()
+
+    def _collect(self, pend):
+        """Collect one in-flight group into the tables of the call it belongs to."""
+        call = pend['call']
+        o = self._collect_group(pend, call.margin, call.ci, call.store, call.density_all)
+        call.outs.append(o)
+        if call.on_group is not None:
+            call.on_group(o['t0'], o['t0'] + o['T'], call.pos_view, call.density_all)
+
+    def _drain(self):
+        """Collect whatever is still in flight (before the staged buffers change)."""
+        if self._carry is not None:
+            pend, self._carry = self._carry, None
+            with self.torch.cuda.device(self.device):
+                self._collect(pend)
+
+    def _finish(self, call):
+        if call.batch is not None:
+            return call.batch
+        import time as _time
+        if self._carry is not None and self._carry['call'] is call:
+            t0 = _time.perf_counter()
+            pend, self._carry = self._carry, None
+            with self.torch.cuda.device(self.device):
+                self._collect(pend)
+            if self.host_timing is not None:
+                # the exposed tail of a call: wait for the last group's copies, move its block into the result tables
+                ht = self.host_timing
+                ht['calls'] = ht.get('calls', 0) + 1
+                ht['last_wait_ms'] = ht.get('last_wait_ms', 0.0) + 1e3 * (self._last_wait_end - t0)
+                ht['last_copy_ms'] = ht.get('last_copy_ms', 0.0) + 1e3 * (_time.perf_counter() - self._last_wait_end)
+        outs = call.outs
+        if sum(o['T'] for o in outs) != call.T_all:
+            raise RuntimeError("profile: a task group was never collected")
         cat = lambda k: np.concatenate([o[k] for o in outs], axis=0)
         # what the last call moved, for the roofline accounting of bench.py
+        self.last_groups = call.n_groups
+        self.last_paths = list(call.paths)
         self.last_stats = dict(hits=int(sum(int(o['hit_count'][0]) for o in outs)),
-                               entries=int(sum(o['entries'] for o in outs)), units=int(self._units_run),
-                               paths=list(self.last_paths))
-        positions = stats_host.positions_view(store, center)
+                               entries=int(sum(o['entries'] for o in outs)), units=int(call.units),
+                               paths=list(call.paths))
+        positions = stats_host.positions_view(call.store, call.center)
         hits = None
-        if return_hits:
+        if call.return_hits:
             parts = []
             off = 0
             for o in outs:
@@ -682,10 +743,19 @@ class Engine:
             hits = np.concatenate(parts) if parts else np.zeros(0, dtype=HIT_DTYPE)
             order = np.lexsort((hits['pos'], hits['seq'], hits['task']))
             hits = hits[order]
-        r = np.concatenate([o['r'] for o in outs], axis=0) if return_r else None
-        thr = dtab.dev['thr'].cpu().numpy() if dtab is not None else np.array([tb['thr'] for tb in all_tables])
-        return ProfileBatch(list(range(T_all)), positions, density_all, self.scores, thr,
-                            hit_counts=cat('hit_count'), hits=hits, r=r, n_seq=N)
+        r = np.concatenate([o['r'] for o in outs], axis=0) if call.return_r else None
+        dtab = call.dtab
+        if dtab is not None:
+            thr_all = dtab.host.get('_thr_np')
+            if thr_all is None:
+                thr_all = dtab.host['_thr_np'] = dtab.dev['thr'].cpu().numpy()     # (once per table set)
+            thr = thr_all[dtab.g0:dtab.g1]
+        else:
+            thr = np.array([tb['thr'] for tb in call.all_tables])
+        call.batch = ProfileBatch(list(range(call.T_all)), positions, call.density_all, self.scores, thr,
+                                  hit_counts=cat('hit_count'), hits=hits, r=r, n_seq=self.N)
+        call.store = call.pos_view = call.on_group = None
+        return call.batch
 
     def _reset_x_planes(self):
         """Restore the all-zero state of the A operand the last scan wrote (match-list driven, see
@@ -731,7 +801,6 @@ class Engine:
         torch = self.torch
         T = len(tables)
         path = path or self.choose_path(tables, margin)
-        self.last_paths.append(path)
         use_lean = self.lean if lean is None else bool(lean)
         L, N, C_, P = self.L, self.N, self.C, self.P
         st = self._stream()
@@ -956,6 +1025,8 @@ class Engine:
         """Wait for one group's D2H copies and finalise its statistics on the host, straight into the
         preallocated output store (rows t0 .. t0+T)."""
         pend['done'].synchronize()
+        import time as _time
+        self._last_wait_end = _time.perf_counter()
         h = {k: v.numpy() for k, v in pend['host'].items()}
         t0, T = pend['t0'], pend['T']
         if pend['path'] == 'sparse':
@@ -968,6 +1039,9 @@ class Engine:
                 redo = self._launch_group(pend['tables'], margin, pend['return_hits'], pend['return_r'], pend['hits_cap'],
                                           ci, pend['slot'], path='tensor' if list_full else 'sparse', lean=False)
                 redo['t0'] = t0
+                redo['call'] = pend.get('call')
+                if redo['call'] is not None:
+                    redo['call'].paths.append(redo['path'])
                 return self._collect_group(redo, margin, ci, store, density_all)
         # host side of a group = copies of the finalised block and of the densities into the result table;
         # split over a few threads (memcpy drops the GIL) so that the exposed tail of the last group stays short
