@@ -249,6 +249,16 @@ int mepp_x_planes_reset(void* x_planes_dev, const void* hits_dev, int64_t hits_c
 int64_t mepp_y_rows_ld(int C);
 int mepp_build_y_rows(const float* yhat_dev, const int32_t* perm_dev, int64_t N, int P, float* y_rows_dev,
                       void* stream);
+/* Match-driven form of the sparse profile (default): the blur commutes with the contraction, so r is built from ONE
+ * gathered row of Y per match -- hits_dev / hit_count_dev / count_dev as mepp_scan leaves them, rowstats_dev the
+ * float32-blur row sums -- instead of one per non-zero of the blurred matrix (2 margin + 1 times fewer bytes).  Same
+ * outputs as mepp_profile_sparse up to the float32 rounding of the blurred value (<= 6e-8 relative per term).  A match
+ * list longer than hits_cap leaves r untouched (the caller sees hit_count > hits_cap and redoes the group). */
+int64_t mepp_profile_matches_work_bytes(int64_t m_rows, int64_t hits_cap);
+int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_count_dev, int64_t hits_cap,
+                         const int32_t* count_dev, int T, int L, int margin, const float* y_rows_dev,
+                         const double* rowstats_dev, const double* colconst_dev, float* r_dev, int64_t ldr, int C,
+                         void* work_dev, void* stream);
 int64_t mepp_profile_sparse_work_bytes(int64_t m_rows, int64_t entry_cap);
 int mepp_profile_sparse(const void* entries_dev, const unsigned long long* entry_count_dev, int64_t entry_cap,
                         int32_t* row_nnz_dev, const float* y_rows_dev, const double* rowstats_dev,

@@ -64,7 +64,7 @@ def run_batch(
     motif_score_cmap='gray', rank_smoothing_factor=5, figure_width=10, figure_height=10, save_datasets=False,
     save_profile_data=True, save_motif_score_matrix=False, save_figures=True, figure_formats=['png', 'svg'],
     figure_dpi=300, n_jobs=1, free_dataset=True, keep_dataset=False, progress_wrapper=None, no_gpu=False,
-    stop_max_attempt_number=3, wait_random_min=1.0, wait_random_max=2.0, task_writer=None
+    stop_max_attempt_number=3, wait_random_min=1.0, wait_random_max=2.0, task_writer=None, dp_precision=None
 ):
     """batch.py:28-190.  `task_writer` (a writer.TaskWriter) is an extension: run_mepp starts the writer processes
     before it parses its inputs and hands them over."""
@@ -95,6 +95,8 @@ def run_batch(
     good = [i for i in my_ids if errors[i] is None]
     attempts = {i: 1 for i in my_ids}
 
+    from .motif_layers import DP_PRECISION
+    dp_grid = DP_PRECISION if dp_precision is None else dp_precision     # recorded in every params.yaml
     tw = task_writer
     own_writer = tw is None
     if own_writer:
@@ -114,7 +116,7 @@ def run_batch(
             motif_score_cmap=motif_score_cmap, rank_smoothing_factor=rank_smoothing_factor, figure_width=figure_width,
             figure_height=figure_height, save_datasets=save_datasets, save_profile_data=save_profile_data,
             save_motif_score_matrix=save_motif_score_matrix, save_figures=True, figure_formats=list(figure_formats),
-            figure_dpi=figure_dpi, no_gpu=no_gpu)
+            figure_dpi=figure_dpi, no_gpu=no_gpu, dp_precision=float(dp_grid))
         fps = _task_filepaths(outdir, dataset_filepath, motif_matrix_filepath, figure_formats)
         fps.pop('mepp_plot', None)                 # figures: plotting layer, out of scope
         tw.submit(dict(outdir=outdir, motif_matrix=np.asarray(motif_matrix_dict[motif_id]), wrapped_params=params,
@@ -135,7 +137,8 @@ def run_batch(
                 submit(ids[j], {k: v[j] for k, v in positions.items()}, density[j])
 
         batch = profile_tasks(dataset, sel, motif_margin=motif_margin, confidence_interval_pct=confidence_interval_pct,
-                              center=center, return_hits=save_motif_score_matrix, on_group=on_group)
+                              center=center, return_hits=save_motif_score_matrix, on_group=on_group,
+                              dp_precision=dp_precision)
         if save_motif_score_matrix:
             for j, i in enumerate(ids):
                 submit(i, {k: v[j] for k, v in batch.positions.items()}, batch.density[j],

@@ -41,13 +41,14 @@ class ProcessedDataset:
 
 def profile_tasks(dataset, tasks, motif_margin=0, confidence_interval_pct=95, center=None, return_hits=False,
                   return_r=False, honour_flags=False, motif_pseudocount=0.0001, motif_pvalue=0.0001, bg=None,
-                  on_group=None):
+                  on_group=None, dp_precision=None):
     """Batched hot path: tasks = [(motif_matrix (4, m), orientation), ...] -> engine.ProfileBatch.
     on_group(t0, t1, positions, density) is called when the results of tasks t0 .. t1-1 are on the host."""
     eng = dataset.engine()
     return eng.profile(tasks, margin=motif_margin, confidence_interval_pct=confidence_interval_pct, center=center,
                        return_hits=return_hits, return_r=return_r, honour_flags=honour_flags,
-                       pseudocount=motif_pseudocount, pvalue=motif_pvalue, bg=bg, on_group=on_group)
+                       pseudocount=motif_pseudocount, pvalue=motif_pvalue, bg=bg, on_group=on_group,
+                       dp_precision=dp_precision)
 
 
 def dataset_and_motif_matrix_to_profile_data(
@@ -59,9 +60,10 @@ def dataset_and_motif_matrix_to_profile_data(
     motif_pvalue=0.0001,
     bg=None,
     confidence_interval_pct=95,
-    center=None
+    center=None,
+    dp_precision=None
 ):
-    """Same signature and return as core.py:490-632:
+    """Same signature and return as core.py:490-632 (dp_precision: extension, grid of the MOODS threshold DP):
     (motif_score_matrix, positions_df, ranks_df, processed_dataset, smoothed_processed_dataset).
 
     As in the reference, motif_pseudocount / motif_pvalue / bg are accepted but do not reach the
@@ -70,7 +72,8 @@ def dataset_and_motif_matrix_to_profile_data(
     """
     sequence_length = get_sequence_length_from_dataset(dataset)
     batch = profile_tasks(dataset, [(motif_matrix, orientation)], motif_margin=motif_margin,
-                          confidence_interval_pct=confidence_interval_pct, center=center, return_hits=True)
+                          confidence_interval_pct=confidence_interval_pct, center=center, return_hits=True,
+                          dp_precision=dp_precision)
     motif_score_matrix = batch.motif_score_matrix(0, sequence_length)
     positions_df = batch.positions_df(0)
     ranks_df = batch.ranks_df(0)

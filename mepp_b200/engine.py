@@ -221,6 +221,11 @@ class Engine:
         # tensor-core first stage of the lean scan (mepp_scan_tc: tcgen05 int8 products over the one-hot stream)
         self.tc_scan = os.environ.get("MEPP_SCAN_TC", "1") != "0"
         self.bp_cost_ratio = float(os.environ.get("MEPP_BP_COST_RATIO", "1.0"))
+        # sparse profile from the match list (one row of Y per match; the blur commutes with the contraction) instead of
+        # the blurred entries (one per non-zero).  Built, exact to 1e-7, but slower on B200 (cfg 3: 24.3 vs 22.9 ms per
+        # step): both forms are bound by instruction issue, not bytes, and the per-position bookkeeping of the match
+        # form costs more than the conversions it saves.  Off by default.
+        self.sparse_matches = os.environ.get("MEPP_SPARSE_FORM", "entries") == "matches"
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -608,7 +613,7 @@ class Engine:
     # ------------------------------------------------------------------ tasks
     def profile_async(self, tasks, margin=0, confidence_interval_pct=95, center=None, return_hits=False,
                       return_r=False, hits_cap=None, tables=None, honour_flags=False, pseudocount=1e-4, pvalue=1e-4,
-                      bg=None, on_group=None):
+                      bg=None, on_group=None, dp_precision=None):
         """Enqueue (motif_matrix (4, m), orientation) tasks; returns a PendingProfile whose result() is the
         ProfileBatch.  The last task group of the call stays in flight: its device -> host copies and the host side of
         its results overlap whatever the caller enqueues next (the next profile_async call of a stream of task lists),
@@ -634,6 +639,8 @@ class Engine:
             if np.shape(pwm)[1] > L:
                 raise ValueError("motif longer than the sequences")
         table_kw = dict(honour_flags=honour_flags, pseudocount=pseudocount, pvalue=pvalue, bg=bg)
+        if dp_precision is not None:
+            table_kw['dp_precision'] = float(dp_precision)       # grid of the MOODS threshold DP (motif_layers.DP_PRECISION)
         G = self.group_size()
         if T_all > 96:
             # several groups so that the host finalisation of one group overlaps the kernels of the next and the
@@ -796,10 +803,12 @@ class Engine:
             self._pins[key] = cur
         return cur[:need].view(tuple(int(x) for x in shape))
 
-    def _launch_group(self, tables, margin, return_hits, return_r, hits_cap, ci, slot, path=None, lean=None):
+    def _launch_group(self, tables, margin, return_hits, return_r, hits_cap, ci, slot, path=None, lean=None,
+                      matches=None):
         """Enqueue every kernel of one task group plus the D2H copies of its results (no host sync)."""
         torch = self.torch
         T = len(tables)
+        use_matches = self.sparse_matches if matches is None else bool(matches)
         path = path or self.choose_path(tables, margin)
         use_lean = self.lean if lean is None else bool(lean)
         L, N, C_, P = self.L, self.N, self.C, self.P
@@ -919,7 +928,16 @@ class Engine:
             st = self._stream()
             # tcgen05 GEMM with the correlation fused into its epilogue: r (m_rows, ldS) float32, S never reaches HBM
             r = self._buf('r', (m_rows, self.ldS), torch.float32)
-            if path == 'sparse':
+            if path == 'sparse' and use_matches:
+                # one gathered row of Y per MATCH (the blur commutes with the contraction), not per blurred non-zero
+                work = self._buf('match_work', int(_lib.lib.mepp_profile_matches_work_bytes(m_rows, cap)), torch.uint8)
+                _lib.check(_lib.lib.mepp_profile_matches(_ptr(hits_d), _ptr(hit_count), cap, _ptr(count), T, L, int(margin),
+                                                         _ptr(self._yrows()), _ptr(rowstats), _ptr(self._colconst()),
+                                                         _ptr(r), self.ldS, C_, _ptr(work), st), "profile_matches")
+                self.launches += 3
+                nnz_d = work[m_rows * 4:m_rows * 4 + 4].view(torch.int32)     # offsets[m_rows] = matches of the group
+                ev = self._mark(ev, 'gemm')
+            elif path == 'sparse':
                 work = self._buf('sparse_work', int(_lib.lib.mepp_profile_sparse_work_bytes(m_rows, entry_cap)), torch.uint8)
                 _lib.check(_lib.lib.mepp_profile_sparse(_ptr(entries), _ptr(entry_count), entry_cap, _ptr(row_nnz),
                                                         _ptr(self._yrows()), _ptr(rowstats), _ptr(self._colconst()), _ptr(r),
@@ -1010,6 +1028,7 @@ class Engine:
                 done = torch.cuda.Event()
                 done.record(self._copy_stream)
             return dict(host=host, done=done, T=T, hits_d=hits_d, cap=cap, return_hits=return_hits, path=path,
+                        use_matches=use_matches,
                         entry_cap=entry_cap, slot=slot, tables=tables, return_r=return_r, hits_cap=hits_cap,
                         dev=dev, chain_done=ready)    # (keeps the copied tensors alive until the side stream is done with them)
 
@@ -1032,12 +1051,16 @@ class Engine:
         if pend['path'] == 'sparse':
             list_full = int(h['entry_count'][::16].max()) > pend['entry_cap'] // _lib.ENTRY_LISTS
             lean_full = int(h['entry_count'][1]) != 0      # a bucket (or a candidate list) of the lean scan overflowed
-            if list_full or lean_full:
+            hits_full = pend.get('use_matches') and int(h['hit_count'][0]) > pend['cap']
+            if list_full or lean_full or hits_full:
                 # a lean overflow (a run of matches inside 32 sequences) is redone by the full-form scan, still on the
-                # sparse path; only an X too dense for the entry list goes to the tensor-core path
-                self.fallbacks.append('tensor' if list_full else 'full-scan')
+                # sparse path (from the blurred entries when the match list itself was too short); only an X too dense
+                # for the entry list goes to the tensor-core path
+                self.fallbacks.append('tensor' if list_full else 'full-scan' if lean_full else 'entries')
                 redo = self._launch_group(pend['tables'], margin, pend['return_hits'], pend['return_r'], pend['hits_cap'],
-                                          ci, pend['slot'], path='tensor' if list_full else 'sparse', lean=False)
+                                          ci, pend['slot'], path='tensor' if list_full else 'sparse',
+                                          lean=False if lean_full or list_full else None,
+                                          matches=False if hits_full else None)
                 redo['t0'] = t0
                 redo['call'] = pend.get('call')
                 if redo['call'] is not None:

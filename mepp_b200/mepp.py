@@ -28,7 +28,7 @@ def run_mepp(
     stop_max_attempt_number=3, wait_random_min=1.0, wait_random_max=2.0,
     cluster_method='average', cluster_metric='correlation', mepp_plot_format='png', table_image_dpi=100,
     table_image_format='png', mt_method='fdr_tsbky', mt_alpha=0.01, thorough_mt=True, no_gpu=False,
-    permutation_seed=None, shuffle_seed=None
+    permutation_seed=None, shuffle_seed=None, dp_precision=None
 ):
     gc_ratio_type = 'global'                                               # mepp.py:96
     import time
@@ -96,7 +96,8 @@ def run_mepp(
             save_datasets=save_datasets, keep_dataset=keep_dataset, save_profile_data=save_profile_data,
             save_motif_score_matrix=save_motif_score_matrix, save_figures=True, figure_formats=figure_formats,
             figure_dpi=figure_dpi, n_jobs=n_gpu_jobs, no_gpu=no_gpu, stop_max_attempt_number=stop_max_attempt_number,
-            wait_random_min=wait_random_min, wait_random_max=wait_random_max, task_writer=task_writer)
+            wait_random_min=wait_random_min, wait_random_max=wait_random_max, task_writer=task_writer,
+            dp_precision=dp_precision)
         timings['run_batch_s'] = time.perf_counter() - t0
         t0 = time.perf_counter()
         if filtered_written is not None:

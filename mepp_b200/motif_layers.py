@@ -10,12 +10,19 @@ MOODS' C++ on the host.
 import ctypes as C
 from concurrent.futures import ThreadPoolExecutor
 
+import os
+
 import numpy as np
 
 from . import _lib
 
 # MOODS' integer grid for the p-value DP (SURVEY.md section 8c fixes 1000.0).
-DP_PRECISION = 1000.0
+# Grid of the integer DP of MOODS' threshold_from_p: scores are rounded to multiples of 1 / DP_PRECISION.  MOODS >= 1.9.3
+# (the reference pins MOODS-python >= 1.9.4, setup.py:19) uses DEFAULT_DP_PRECISION = 2000; older builds used 1000
+# (PVAL_DP_MULTIPLIER) -- that is the grid SURVEY.md section 8c restates.  Neither can be checked against MOODS in this
+# image; 2000 is the default, MEPP_DP_PRECISION / the dp_precision keyword select the other one, and every task's
+# params.yaml records the grid that was used.
+DP_PRECISION = float(os.environ.get("MEPP_DP_PRECISION", "2000"))
 
 
 def flat_bg(alphabet_size=4):

@@ -89,9 +89,9 @@ def run_single(
     motif_orientation='+', motif_margin=0, motif_pseudocount=0.0001, motif_pvalue=0.0001, bg=None,
     confidence_interval_pct=95, motif_score_sigma=1.0, motif_score_cmap='gray', rank_smoothing_factor=5,
     figure_width=10, figure_height=10, save_datasets=False, save_profile_data=True, save_motif_score_matrix=False,
-    save_figures=True, figure_formats=['png', 'svg'], figure_dpi=300, no_gpu=False, dataset=None
+    save_figures=True, figure_formats=['png', 'svg'], figure_dpi=300, no_gpu=False, dataset=None, dp_precision=None
 ):
-    """single.py:57-302.  `dataset` (an already loaded ScoredDataset) is an extension that lets the batch
+    """single.py:57-302.  dp_precision (extension): grid of the MOODS threshold DP, recorded in params.yaml.  `dataset` (an already loaded ScoredDataset) is an extension that lets the batch
     driver skip the per-task load_dataset of single.py:177."""
     if no_gpu:
         force_cpu_only()
@@ -106,6 +106,8 @@ def run_single(
         figure_height=figure_height, save_datasets=save_datasets, save_profile_data=save_profile_data,
         save_motif_score_matrix=save_motif_score_matrix, save_figures=save_figures, figure_formats=figure_formats,
         figure_dpi=figure_dpi)
+    from .motif_layers import DP_PRECISION
+    params['dp_precision'] = float(DP_PRECISION if dp_precision is None else dp_precision)
     filepaths = _task_filepaths(output_filepath, dataset_filepath, motif_matrix_filepath, figure_formats)
     os.makedirs(filepaths['output'], exist_ok=True)
     if dataset is None:
@@ -114,7 +116,7 @@ def run_single(
     (motif_score_matrix, positions_df, ranks_df, _processed, _smoothed) = dataset_and_motif_matrix_to_profile_data(
         dataset, motif_matrix, orientation=motif_orientation, motif_margin=motif_margin,
         motif_pseudocount=motif_pseudocount, motif_pvalue=motif_pvalue, bg=bg, center=center,
-        confidence_interval_pct=confidence_interval_pct)
+        confidence_interval_pct=confidence_interval_pct, dp_precision=dp_precision)
     if save_figures:
         _maybe_plot(filepaths, motif_score_matrix, positions_df, ranks_df, motif_matrix, params)
     else:

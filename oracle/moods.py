@@ -12,7 +12,7 @@ import numpy as np
 # p-value DP.  SURVEY.md section 8(c) fixes 1000.0 (PVAL_DP_MULTIPLIER); some
 # MOODS 1.9.4.x builds are believed to use DEFAULT_DP_PRECISION = 2000.0.  It
 # is a parameter everywhere so either can be selected; 1000.0 is the contract.
-DP_PRECISION = 1000.0
+DP_PRECISION = 2000.0
 
 
 def flat_bg(alphabet_size=4):

@@ -267,6 +267,26 @@ def test_run_batch_isolates_a_poisoned_motif(tmp_path):
         assert pa.equals(pb)
 
 
+def test_match_driven_sparse_profile_equals_the_entry_form():
+    """mepp_profile_matches (one gathered row of Y per match, window sums of the per-position products) against
+    mepp_profile_sparse (one per non-zero of the blurred matrix): same r within the float32 rounding of the blurred
+    values, for margins 0 .. 16, a peaked profile (planted motif) and a motif that never matches."""
+    from mepp_b200 import synth
+    cfg = synth.make_config("cfg1", n_seq=700, n_motifs=6, n_perm=60)
+    tasks = [(pwm, o) for _, pwm, o in cfg["tasks"]]
+    eng = _engine().stage(cfg["ascii"], cfg["scores"], cfg["perm_idx"], use_gc=True)
+    for margin in (0, 1, 2, 5, 16):
+        eng.sparse_matches = False
+        want = eng.profile(tasks, margin=margin, return_r=True)
+        eng.sparse_matches = True
+        got = eng.profile(tasks, margin=margin, return_r=True)
+        assert set(eng.last_paths) == {'sparse'}
+        scale = np.abs(want.r).max(axis=-1, keepdims=True)
+        assert (np.abs(got.r.astype(np.float64) - want.r) <= 2e-6 * np.abs(want.r) + 2e-6 * scale + 1e-12).all(), margin
+        assert np.array_equal(got.density, want.density)
+    eng.sparse_matches = False
+
+
 def test_motif_length_and_margin_extremes():
     """m = 1, 2, 3 and the maximum 32 at the maximum margin 16, on sequences shorter than the blur window
     would like (L = 40) and on an L that is not a multiple of anything (L = 203)."""
@@ -540,6 +560,33 @@ def test_device_thresholds_equal_host_thresholds():
         assert np.array_equal(thr, np.array([tb['thr'] for tb in ref]))
         assert np.array_equal(bias, np.array([tb['bias'] for tb in ref], dtype=np.float32))
         assert np.array_equal(qthr, np.stack([tb['qthr'] for tb in ref]))
+
+
+@pytest.mark.parametrize("grid", [1000.0, 2000.0])
+def test_device_thresholds_equal_the_oracle_on_both_dp_grids(grid):
+    """MOODS threshold_from_p on the 1/1000 grid (MOODS <= 1.9.2) and on the 1/2000 grid (MOODS >= 1.9.3, the
+    default): the device DP, the host C++ DP and the numpy oracle give the same threshold for EVERY motif of the three
+    shipped libraries in the orientations that have their own threshold ('+' and '-'), and a task run with
+    dp_precision=grid reports exactly that threshold."""
+    from mepp_b200 import synth, motif_layers
+    from oracle import moods
+    eng = _engine()
+    tasks, want = [], []
+    for lib in ("ohler", "homer_clustered", "homer"):
+        for pwm in synth.load_motif_library(lib).values():
+            W = moods.log_odds(pwm, [0.25] * 4, 1e-4)
+            for o, Wo in (('+', W), ('-', W[::-1, ::-1])):
+                tasks.append((pwm, o))
+                want.append(moods.threshold_from_p(Wo, [0.25] * 4, 1e-4, grid))
+    dt = eng.device_tables_for(tasks, dp_precision=grid)
+    host = motif_layers.scan_tables(tasks, dp_precision=grid)
+    assert np.array_equal(dt.dev['thr'].cpu().numpy(), np.array(want))
+    assert np.array_equal(np.array([tb['thr'] for tb in host]), np.array(want))
+    cfg = synth.make_config("cfg1", n_seq=64, n_motifs=3, n_perm=8)
+    sel = [(pwm, o) for _, pwm, o in cfg["tasks"]]
+    got = eng.stage(cfg["ascii"], cfg["scores"], cfg["perm_idx"]).profile(sel, margin=2, dp_precision=grid)
+    for (pwm, o), thr in zip(sel, got.thr):
+        assert thr == profile.motif_weights(pwm, o, precision=grid)[2]
 
 
 def test_tiled_operand_is_restored_even_when_the_match_list_overflows():

@@ -20,23 +20,38 @@ def codes_of(seq):
     return staging.ascii_to_codes(np.frombuffer(seq.encode(), dtype=np.uint8)[None, :])
 
 
-def test_kat1_uniform_pwm_never_matches():
+# The DP grid of MOODS' threshold_from_p: 1/1000 (PVAL_DP_MULTIPLIER of MOODS <= 1.9.2, the grid SURVEY.md 8c restates)
+# and 1/2000 (DEFAULT_DP_PRECISION of MOODS >= 1.9.3, what the reference's `MOODS-python>=1.9.4` pin most likely runs
+# and therefore the default here); every known answer below is derived by hand for both.
+GRIDS = [1000.0, 2000.0]
+
+
+def test_default_grid_is_the_one_of_the_pinned_moods():
+    from mepp_b200 import motif_layers
+    assert moods.DP_PRECISION == 2000.0 and motif_layers.DP_PRECISION == 2000.0
+
+
+@pytest.mark.parametrize("grid", GRIDS)
+def test_kat1_uniform_pwm_never_matches(grid):
     W = moods.log_odds(np.full((4, 8), 0.25), BG, 1e-4)
     assert np.allclose(W, 0.0, atol=1e-15)
-    assert moods.threshold_from_p(W, BG, 1e-4) == pytest.approx(0.001)
+    assert moods.threshold_from_p(W, BG, 1e-4, grid) == pytest.approx(1.0 / grid)
     codes = np.random.default_rng(0).integers(0, 4, (5, 50)).astype(np.int8)
-    X0 = profile.scan(codes, W.astype(np.float32), None, 0.001)
+    X0 = profile.scan(codes, W.astype(np.float32), None, 1.0 / grid)
     assert (X0 == 0).all()
 
 
-def test_kat2_consensus_threshold_and_position():
+@pytest.mark.parametrize("grid", GRIDS)
+def test_kat2_consensus_threshold_and_position(grid):
     pwm = consensus_pwm()
     W = moods.log_odds(pwm, BG, 1e-4)
     assert W[0, 0] == pytest.approx(np.log(0.999925 / 0.25) - 0.0, rel=1e-6)  # (1 + 2.5e-5)/1.0001 / .25
     assert W[1, 0] == pytest.approx(-9.2104, abs=1e-3)
-    thr = moods.threshold_from_p(W, BG, 1e-4)
-    assert thr == pytest.approx((7 * 1386 - 9210 + 1) / 1000)      # only exact consensus passes
-    assert thr == moods.threshold_bruteforce(W, BG, 1e-4)
+    thr = moods.threshold_from_p(W, BG, 1e-4, grid)
+    # integer scores: trunc(grid * 1.38622 + 0.5) = 1386 / 2772, trunc(grid * -9.2104 - 0.5) = -9210 / -18421
+    i_match, i_mis = {1000.0: (1386, -9210), 2000.0: (2772, -18421)}[grid]
+    assert thr == pytest.approx((7 * i_match + i_mis + 1) / grid)      # only exact consensus passes
+    assert thr == moods.threshold_bruteforce(W, BG, 1e-4, grid)
     seq = "T" * 10 + "ACGTACGT" + "T" * 12
     X0 = profile.scan(codes_of(seq), W.astype(np.float32), None, thr)
     nz = np.nonzero(X0[0])[0]
@@ -111,22 +126,24 @@ def test_kat7_percentiles_and_pvalues():
     assert list(cols.keys()) == profile.POSITIONS_COLUMNS[:15]
 
 
-def test_kat8_short_motif_threshold_above_max():
-    # a 5-mer's best score has probability 4^-5 > 1e-4 -> thr = max + 0.001 -> no matches (quirk vi)
+@pytest.mark.parametrize("grid", GRIDS)
+def test_kat8_short_motif_threshold_above_max(grid):
+    # a 5-mer's best score has probability 4^-5 > 1e-4 -> thr = max + one grid step -> no matches (quirk vi)
     pwm = consensus_pwm("ACGTA")
     W = moods.log_odds(pwm, BG, 1e-4)
-    thr = moods.threshold_from_p(W, BG, 1e-4)
-    imax = int(sum(np.trunc(1000 * W.max(axis=0) + 0.5)))
-    assert thr == pytest.approx((imax + 1) / 1000)
-    # whether anything can still match depends on the integer rounding of the column maxima:
-    # here 5 * 1.38622 = 6.9311 > 6.931, so only the exact consensus passes, by < 1e-3
+    thr = moods.threshold_from_p(W, BG, 1e-4, grid)
+    imax = int(sum(np.trunc(grid * W.max(axis=0) + 0.5)))
+    assert thr == pytest.approx((imax + 1) / grid)
+    # whether anything can still match depends on the integer rounding of the column maxima: 5 * 1.38622 = 6.9311;
+    # grid 1000: 5 * 1386 + 1 = 6931 -> thr 6.931 < 6.9311, the exact consensus still passes, by < 1e-3;
+    # grid 2000: 5 * 2772 + 1 = 13861 -> thr 6.9305, it passes by < 1e-3 as well
     X0 = profile.scan(codes_of("GG" + "ACGTA" + "GG"), W.astype(np.float32), None, thr)
     assert list(np.nonzero(X0[0])[0]) == [4] and 0 < X0[0, 4] < 1e-3
-    # the shipped 5-mer 'Tgif1,Tgif2 Homeobox' has max 5.679 < thr 5.680 -> no position can match
+    # the shipped 5-mer 'Tgif1,Tgif2 Homeobox' has max 5.679 < thr -> no position can match
     from mepp_b200 import synth
     tg = synth.load_motif_library('homer_clustered')['Tgif1,Tgif2 Homeobox']
     Wt = moods.log_odds(tg, BG, 1e-4)
-    assert Wt.shape[1] == 5 and moods.threshold_from_p(Wt, BG, 1e-4) > Wt.max(axis=0).sum()
+    assert Wt.shape[1] == 5 and moods.threshold_from_p(Wt, BG, 1e-4, grid) > Wt.max(axis=0).sum()
 
 
 def test_kat9_dp_equals_bruteforce_on_random_motifs():
@@ -138,12 +155,16 @@ def test_kat9_dp_equals_bruteforce_on_random_motifs():
             assert moods.threshold_from_p(W, BG, p) == moods.threshold_bruteforce(W, BG, p)
 
 
-def test_ohler_thresholds_frozen():
-    """Thresholds of the shipped ohler library under the restated MOODS spec."""
+@pytest.mark.parametrize("grid,table", [
+    (1000.0, [6.393, 7.225, 7.127, 7.522, 6.318, 6.166, 7.482, 6.636, 6.329, 5.063]),
+    (2000.0, [6.3905, 7.2255, 7.126, 7.5215, 6.319, 6.1655, 7.482, 6.6375, 6.3295, 5.062])])
+def test_ohler_thresholds_frozen(grid, table):
+    """Thresholds of the shipped ohler library under the restated MOODS spec, on both DP grids (the grid moves them by
+    up to 2.5e-3: integer rounding of every matrix entry, summed over the motif)."""
     from mepp_b200 import synth
     lib = synth.load_motif_library('ohler')
-    thr = [moods.threshold_from_p(moods.log_odds(v, BG, 1e-4), BG, 1e-4) for v in lib.values()]
-    assert thr == pytest.approx([6.393, 7.225, 7.127, 7.522, 6.318, 6.166, 7.482, 6.636, 6.329, 5.063])
+    thr = [moods.threshold_from_p(moods.log_odds(v, BG, 1e-4), BG, 1e-4, grid) for v in lib.values()]
+    assert thr == pytest.approx(table)
 
 
 def test_n_base_uses_four_quarter_adds():

@@ -1,78 +1,43 @@
-"""Text summary of an .ncu-rep (run here, no GPU needed): key raw metrics per kernel + hot SASS regions."""
+#!/usr/bin/env python
+"""Key metrics of .ncu-rep files (ncu -i ... --page raw --csv) as a short text summary: tools/ncu_summary.py a.ncu-rep ..."""
 import csv
 import io
 import subprocess
 import sys
 
-KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum ', 'dram__bytes_write.sum ', 'dram__bytes_read.sum [',
-        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__pipe_tensor_cycles_active',
-        'sm__inst_executed_pipe_tensor', 'sm__warps_active.avg.pct_of_peak_sustained_active',
-        'launch__registers_per_thread ', 'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic',
-        'launch__occupancy_limit', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'smsp__average_warps_issue_stalled', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
-        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
-        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum ', 'lts__t_bytes.sum ', 'smsp__inst_executed.sum ',
-        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
-        'sm__cycles_elapsed.max ']
-
-
-def run(args):
-    return subprocess.run(["ncu"] + args, capture_output=True, text=True).stdout
-
-
-def main(path):
-    raw = list(csv.reader(io.StringIO(run(["-i", path, "--page", "raw", "--csv"]))))
-    hdr, units = raw[0], raw[1]
-    for r in raw[2:]:
-        name = r[hdr.index('Kernel Name')]
-        print(f"=== {name}")
-        for i, h in enumerate(hdr):
-            hh = h + ' '
-            if any(k in hh or k in h + ' [' for k in KEYS):
-                if 'stalled' in h:
-                    try:
-                        if float(r[i]) < 0.2:
-                            continue
-                    except ValueError:
-                        continue
-                print(f"  {h} [{units[i]}] = {r[i]}")
-    src = list(csv.reader(io.StringIO(run(["-i", path, "--page", "source", "--csv"]))))
-    # the source page concatenates kernels: split on header rows
-    blocks, cur = [], None
-    for row in src:
-        if row and row[0] == 'Kernel Name':
-            cur = dict(name=row[1], rows=[])
-            blocks.append(cur)
-        elif cur is not None:
-            cur['rows'].append(row)
-    for b in blocks:
-        rows = b['rows']
-        if len(rows) < 3:
-            continue
-        hdr = rows[0]
-        data = [r for r in rows[1:] if len(r) == len(hdr)]
-        try:
-            ie, sm, so = hdr.index('Instructions Executed'), hdr.index('# Samples'), hdr.index('Source')
-        except ValueError:
-            continue
-        tot = sum(float(r[ie]) for r in data) or 1.0
-        ts = sum(float(r[sm]) for r in data) or 1.0
-        print(f"=== hot SASS regions of {b['name']}: {len(data)} SASS instructions, {tot / 1e9:.3f} G warp-instructions")
-        runs, c = [], None
-        for i, r in enumerate(data):
-            e = float(r[ie])
-            if c and abs(e - c['e']) <= 0.03 * max(e, c['e'], 1):
-                c['n'] += 1; c['sum'] += e; c['samples'] += float(r[sm]); c['end'] = i
-            else:
-                if c:
-                    runs.append(c)
-                c = dict(start=i, end=i, e=e, n=1, sum=e, samples=float(r[sm]))
-        runs.append(c)
-        for c in sorted([c for c in runs if c['sum'] / tot > 0.02 or c['samples'] / ts > 0.03], key=lambda c: c['start']):
-            print(f"  sass[{c['start']:5d}..{c['end']:5d}] n={c['n']:4d} exec/instr={c['e'] / 1e6:9.2f}M "
-                  f"instr share={100 * c['sum'] / tot:5.1f}% stall-sample share={100 * c['samples'] / ts:5.1f}%  "
-                  f"{data[c['start']][so].strip()[:48]}")
-
-
-if __name__ == "__main__":
-    main(sys.argv[1])
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
+        "lts__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed.sum", "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.sum", "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio"]
+for path in sys.argv[1:]:
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    if len(rows) < 3:
+        print(path, "no data"); continue
+    head, units = rows[0], rows[1]
+    for r in rows[2:]:
+        d = dict(zip(head, r))
+        print(f"== {path}: {d.get('Kernel Name', '?')[:90]}")
+        for k in KEYS:
+            if k in d:
+                print(f"   {k:90s} {d[k]:>16s} {units[head.index(k)]}")
+        extra = [k for k in head if ("tensor" in k or "tmem" in k.lower()) and k not in KEYS and d[k] not in ("", "0", "n/a")]
+        for k in extra[:12]:
+            print(f"   {k:90s} {d[k]:>16s} {units[head.index(k)]}")
