@@ -246,6 +246,12 @@ int mepp_x_planes_reset(void* x_planes_dev, const void* hits_dev, int64_t hits_c
  * work_dev: mepp_profile_sparse_work_bytes(m_rows, entry_cap) bytes, beginning with int32 offsets[m_rows + 2]
  * (CSR row offsets; offsets[m_rows] = number of non-zeros, offsets[m_rows + 1] = 1 if the list overflowed);
  * row_nnz_dev is consumed. */
+/* Column statistics of the exact float32 score operand (what the sparse profile path multiplies: mepp_build_y_rows):
+ * ysum_dev[2] = sum and sum of squares of yhat (float64; the same for every permuted column), col_syz_dev[c] =
+ * sum_n y_c[n] * zhat[n] (zeros when zhat_dev is NULL).  mepp_build_y computes the same from the fp16 hi + lo split the
+ * tiled operand of the tensor path holds. */
+int mepp_y_stats(const float* yhat_dev, const int32_t* perm_dev, const float* zhat_dev, int64_t N, int P,
+                 double* col_syz_dev, double* ysum_dev, void* stream);
 int64_t mepp_y_rows_ld(int C);
 int mepp_build_y_rows(const float* yhat_dev, const int32_t* perm_dev, int64_t N, int P, float* y_rows_dev,
                       void* stream);

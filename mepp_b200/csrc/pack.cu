@@ -166,8 +166,45 @@ __global__ void y_colstats_kernel(const uint32_t* __restrict__ ysplit, const int
   }
 }
 
-// Row-major float32 copy of Y for the sparse profile path: y_rows[n][c] = hi + lo of the same fp16 split the
-// tiled operand holds (exactly representable in float32), zero in the padding rows / columns.
+// Column statistics of the EXACT float32 operand (sparse profile path): sum and sum of squares of yhat in float64
+// (identical for every permuted column) ...
+__global__ void y_sum_kernel(const float* __restrict__ yhat, int64_t N, double* __restrict__ ysum) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double v = n < N ? (double)yhat[n] : 0.0;
+  double s = v, ss = v * v;
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (s != 0.0 || ss != 0.0)) {
+    atomicAdd(&ysum[0], s);
+    atomicAdd(&ysum[1], ss);
+  }
+}
+
+// ... and col_syz[c] = sum_n y_c[n] * zhat[n] in float64; one block per column.
+__global__ void y_colstats_exact_kernel(const float* __restrict__ yhat, const int32_t* __restrict__ perm,
+                                        const float* __restrict__ zhat, int64_t N, int C,
+                                        double* __restrict__ col_syz) {
+  const int c = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t n = threadIdx.x; n < N; n += blockDim.x) {
+    const int64_t src = c == 0 ? n : (int64_t)perm[(int64_t)(c - 1) * N + n];
+    acc += (double)yhat[src] * (double)zhat[n];
+  }
+  __shared__ double red[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) col_syz[c] = v;
+  }
+}
+
+// Row-major float32 copy of Y for the sparse profile path: y_rows[n][c] = the float32 score operand itself
+// (the reference's dataset holds float32 scores, utils.py:188-192), zero in the padding rows / columns.
 __global__ void y_rows_kernel(const float* __restrict__ yhat, const int32_t* __restrict__ perm, int64_t N,
                               int64_t n_pad, int C, int64_t ldY, float* __restrict__ out) {
   const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
@@ -176,9 +213,7 @@ __global__ void y_rows_kernel(const float* __restrict__ yhat, const int32_t* __r
   float v = 0.0f;
   if (c < C && n < N) {
     const int64_t src = c == 0 ? n : (int64_t)perm[(c - 1) * N + n];
-    __half h, l;
-    split_half(yhat[src], h, l);
-    v = __half2float(h) + __half2float(l);
+    v = yhat[src];
   }
   out[n * ldY + c] = v;
 }
@@ -198,6 +233,25 @@ int mepp_build_y_rows(const float* yhat_dev, const int32_t* perm_dev, int64_t N,
   MEPP_REQUIRE(n_pad < (1LL << 31) && (ldY + 255) / 256 <= 65535, "build_y_rows: shape too large");
   dim3 grid((unsigned)n_pad, (unsigned)((ldY + 255) / 256));
   y_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(yhat_dev, perm_dev, N, n_pad, C, ldY, y_rows_dev);
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mepp_y_stats(const float* yhat_dev, const int32_t* perm_dev, const float* zhat_dev, int64_t N, int P,
+                 double* col_syz_dev, double* ysum_dev, void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(yhat_dev && col_syz_dev && ysum_dev, "y_stats: null pointer");
+  MEPP_REQUIRE(N > 0 && P >= 0 && (P == 0 || perm_dev), "y_stats: bad arguments");
+  MEPP_REQUIRE(mepp_device_ok(), "y_stats: no sm_100 CUDA device (no CPU fallback)");
+  cudaStream_t st = as_stream(stream);
+  const int C = 1 + P;
+  MEPP_CUDA_CHECK(cudaMemsetAsync(ysum_dev, 0, 2 * sizeof(double), st));
+  y_sum_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(yhat_dev, N, ysum_dev);
+  if (zhat_dev) {
+    y_colstats_exact_kernel<<<(unsigned)C, 256, 0, st>>>(yhat_dev, perm_dev, zhat_dev, N, C, col_syz_dev);
+  } else {
+    MEPP_CUDA_CHECK(cudaMemsetAsync(col_syz_dev, 0, sizeof(double) * (size_t)C, st));
+  }
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

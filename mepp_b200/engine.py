@@ -303,6 +303,9 @@ class Engine:
             scale = 1.0 if amax == 0.0 or not math.isfinite(amax) else 2.0 ** (13 - math.floor(math.log2(amax)))
             yhat = (yc * scale).astype(np.float32)
             yhat_d = self._to_dev(yhat)
+            # the sparse path multiplies the float32 scores THEMSELVES (exact products, float64 sums: the raw-moment
+            # cancellation of core.py:182-185 is harmless there); the centred / scaled copy is for the tensor path
+            self._yraw_d = self._to_dev(s32)
             if isinstance(perm_idx, torch.Tensor) and perm_idx.is_cuda:
                 P, perm_d = int(perm_idx.shape[0]), perm_idx          # already on the device (stage_broadcast)
                 self._perm_ready = getattr(self, '_bcast_perm_ready', None)   # its broadcast may still be in flight
@@ -335,6 +338,7 @@ class Engine:
             # Y operands are built at first use (_ensure_y)
             self._yhat_d, self._perm_d, self._y_rows = yhat_d, perm_d, None
             self._y_planes = self._col_syz = self._ysum = None
+            self._col_syz_x = self._ysum_x = self._colconst_x = None      # statistics of the exact float32 operand
             self._zsum_host = None
             self._colconst_dev = None
             self.staged = True
@@ -458,12 +462,24 @@ class Engine:
         self._ensure_y()
         return self._ysum
 
+    def _ensure_y_exact(self):
+        """Column statistics of the exact float32 score operand (sparse path: mepp_y_stats), once per staged dataset."""
+        if self._ysum_x is None:
+            torch = self.torch
+            if self._perm_ready is not None:
+                torch.cuda.current_stream(self.device).wait_event(self._perm_ready)
+            self._col_syz_x = torch.empty(self.C, dtype=torch.float64, device=self.device)
+            self._ysum_x = torch.empty(2, dtype=torch.float64, device=self.device)
+            _lib.check(_lib.lib.mepp_y_stats(_ptr(self._yraw_d), _ptr(self._perm_d), _ptr(self.zhat), self.N, self.P,
+                                             _ptr(self._col_syz_x), _ptr(self._ysum_x), self._stream()), "y_stats")
+            self.launches += 2 if self.use_gc else 1
+
     def _yrows(self):
         if self._y_rows is None:
-            self._ensure_y()
+            self._ensure_y_exact()
             ldY = int(_lib.lib.mepp_y_rows_ld(self.C))
             self._y_rows = self.torch.empty((self.n_pad, ldY), dtype=self.torch.float32, device=self.device)
-            _lib.check(_lib.lib.mepp_build_y_rows(_ptr(self._yhat_d), _ptr(self._perm_d), self.N, self.P,
+            _lib.check(_lib.lib.mepp_build_y_rows(_ptr(self._yraw_d), _ptr(self._perm_d), self.N, self.P,
                                                   _ptr(self._y_rows), self._stream()), "build_y_rows")
             self.launches += 1
         return self._y_rows
@@ -582,8 +598,19 @@ class Engine:
         small = density * len(tables) * self.N * self.L <= SPARSE_SMALL_ENTRIES
         return 'sparse' if density <= SPARSE_DENSITY_MAX or small else 'tensor'
 
-    def _colconst(self):
-        """Per-dataset constants of the fused correlation epilogue (built once per stage())."""
+    def _colconst(self, sparse=False):
+        """Per-dataset constants of the fused correlation epilogue (built once per stage()): from the statistics of the
+        operand the path multiplies -- the exact float32 scores (sparse path) or their fp16 hi + lo split (tensor path)."""
+        if sparse:
+            if self._colconst_x is None:
+                self._ensure_y_exact()
+                cc = self.torch.empty(8 + 2 * self.C, dtype=self.torch.float64, device=self.device)
+                _lib.check(_lib.lib.mepp_col_constants_dev(_ptr(self._col_syz_x), _ptr(self._ysum_x), _ptr(self._zsum_dev),
+                                                           self.N, self.C, 1 if self.use_gc else 0, _ptr(cc),
+                                                           self._stream()), "col_constants")
+                self.launches += 1
+                self._colconst_x = cc
+            return self._colconst_x
         if self._colconst_dev is None:
             cc = self.torch.empty(8 + 2 * self.C, dtype=self.torch.float64, device=self.device)
             _lib.check(_lib.lib.mepp_col_constants_dev(_ptr(self.col_syz), _ptr(self.ysum), _ptr(self._zsum_dev), self.N,
@@ -914,7 +941,7 @@ class Engine:
         compute_stream = torch.cuda.current_stream(self.device)
         if overlap:
             self._yrows()
-            self._colconst()          # (built once, on the compute stream, before the chain is handed over)
+            self._colconst(sparse=True)   # (built once, on the compute stream, before the chain is handed over)
             if self._post_stream is None:
                 self._post_stream = torch.cuda.Stream(device=self.device, priority=-1)
             scanned = torch.cuda.Event()
@@ -932,7 +959,8 @@ class Engine:
                 # one gathered row of Y per MATCH (the blur commutes with the contraction), not per blurred non-zero
                 work = self._buf('match_work', int(_lib.lib.mepp_profile_matches_work_bytes(m_rows, cap)), torch.uint8)
                 _lib.check(_lib.lib.mepp_profile_matches(_ptr(hits_d), _ptr(hit_count), cap, _ptr(count), T, L, int(margin),
-                                                         _ptr(self._yrows()), _ptr(rowstats), _ptr(self._colconst()),
+                                                         _ptr(self._yrows()), _ptr(rowstats),
+                                                         _ptr(self._colconst(sparse=True)),
                                                          _ptr(r), self.ldS, C_, _ptr(work), st), "profile_matches")
                 self.launches += 3
                 nnz_d = work[m_rows * 4:m_rows * 4 + 4].view(torch.int32)     # offsets[m_rows] = matches of the group
@@ -940,7 +968,8 @@ class Engine:
             elif path == 'sparse':
                 work = self._buf('sparse_work', int(_lib.lib.mepp_profile_sparse_work_bytes(m_rows, entry_cap)), torch.uint8)
                 _lib.check(_lib.lib.mepp_profile_sparse(_ptr(entries), _ptr(entry_count), entry_cap, _ptr(row_nnz),
-                                                        _ptr(self._yrows()), _ptr(rowstats), _ptr(self._colconst()), _ptr(r),
+                                                        _ptr(self._yrows()), _ptr(rowstats),
+                                                        _ptr(self._colconst(sparse=True)), _ptr(r),
                                                         self.ldS, m_rows, C_, _ptr(work), st), "profile_sparse")
                 self.launches += 3
                 nnz_d = work[m_rows * 4:m_rows * 4 + 4].view(torch.int32)     # offsets[m_rows] = non-zeros of X
