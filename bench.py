@@ -132,6 +132,16 @@ def build_workload(workload, world, scaling="strong"):
     return cfg, tasks
 
 
+def perm_rows_for_cpu(cfg, max_bytes=4 << 30):
+    """Permutation rows for the CPU legs (oracle check, CPU port): the whole matrix, or -- when it only exists as a
+    PermutationSource (cfg 5) -- its first rows, as many as fit `max_bytes`.  Returns (rows, all_of_them)."""
+    perm = cfg["perm_idx"]
+    if not hasattr(perm, "rows"):
+        return perm, True
+    n = max(64, min(perm.shape[0], (max_bytes // (4 * perm.shape[1])) // 64 * 64))
+    return perm.rows(0, n), n >= perm.shape[0]
+
+
 def bench_config(args, cfg, n_tasks):
     """`config` of the JSON line: the same keys and values for both arms (the driver compares them)."""
     return dict(workload=args.workload, N=cfg["N"], L=cfg["L"], P=cfg["P"], margin=cfg["margin"], tasks_total=n_tasks,
@@ -147,7 +157,8 @@ def run_reference(args, rank, world):
     from oracle import baseline, staging
     cfg, tasks = build_workload(args.workload, world, args.scaling)
     codes = staging.ascii_to_codes(cfg["ascii"])
-    Y = staging.permuted_scores(cfg["scores"], cfg["perm_idx"])
+    perm_cpu, perm_all = perm_rows_for_cpu(cfg)
+    Y = staging.permuted_scores(cfg["scores"], perm_cpu)
     z = staging.gc_ratio_global(codes)
     cores = os.cpu_count() or 1
     # a step = a bounded sample of the workload: whole tasks until the step's share of ~2 minutes is spent (at least one)
@@ -162,7 +173,8 @@ def run_reference(args, rank, world):
         total_tasks += n_done
     value = cfg["N"] * cfg["L"] * total_tasks / total_t / 1e9
     sample = (f"{total_tasks} whole tasks of {args.workload} (first {n_done} motif x orientation tasks per step, "
-              f"N={cfg['N']} L={cfg['L']} P={cfg['P']}), float32 scan in C + BLAS sgemm profile + numpy stats")
+              f"N={cfg['N']} L={cfg['L']} P={Y.shape[1] - 1}{'' if perm_all else ' of ' + str(cfg['P'])}), "
+              f"float32 scan in C + BLAS sgemm profile + numpy stats")
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * total_t / max(1, args.steps), higher_is_better=True,
                 scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
@@ -186,9 +198,13 @@ def accuracy_block(eng, cfg, my_tasks, my_ids, n_check, margin):
     got = eng.profile(sel, margin=margin, return_hits=True, return_r=True)
     hits = got.hits.copy()
     codes = staging.ascii_to_codes(cfg["ascii"])
-    Y = staging.permuted_scores(cfg["scores"], cfg["perm_idx"])
+    perm_cpu, perm_all = perm_rows_for_cpu(cfg)
+    Y = staging.permuted_scores(cfg["scores"], perm_cpu)
     z = staging.gc_ratio_global(codes)
-    rep = checks.accuracy_report(codes, Y, z, sel, [my_ids[i] for i in pick], margin, hits, got.r, got.positions)
+    # (when only the first permutation rows are checked, the statistics over ALL permutations are not compared)
+    rep = checks.accuracy_report(codes, Y, z, sel, [my_ids[i] for i in pick], margin, hits, got.r[:, :, :Y.shape[1]],
+                                 got.positions if perm_all else None)
+    rep["permutation_columns_checked"] = int(Y.shape[1] - 1)
     rep["scan_form"] = getattr(eng, "last_scan", None)
     rep["profile_path"] = ",".join(sorted(set(eng.last_paths)))
     rep["seconds"] = round(time.perf_counter() - t0, 1)
@@ -341,7 +357,8 @@ def main():
     # pinned host inputs (the e2e path copies them every step)
     h_ascii = torch.from_numpy(cfg["ascii"]).pin_memory()
     h_scores = torch.from_numpy(cfg["scores"]).pin_memory()
-    h_perm = torch.from_numpy(cfg["perm_idx"]).pin_memory()
+    lazy_perm = hasattr(cfg["perm_idx"], "rows")      # cfg 5: the 40 GB index matrix is generated and staged in chunks
+    h_perm = cfg["perm_idx"] if lazy_perm else torch.from_numpy(cfg["perm_idx"]).pin_memory()
     # host -> device bytes of one end-to-end step on this rank (sharded upload + all-gather when world > 1)
     h2d_bytes = (-(-h_ascii.shape[0] // world) * h_ascii.shape[1] + 4 * h_scores.numel()
                  + 4 * -(-h_perm.shape[0] // world) * h_perm.shape[1] + len(my_tasks) * (32 * 4 * 2 * 4 + 12))
@@ -573,12 +590,12 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         from oracle import baseline, staging
         codes = staging.ascii_to_codes(cfg["ascii"])
-        Y = staging.permuted_scores(cfg["scores"], cfg["perm_idx"])
+        Y = staging.permuted_scores(cfg["scores"], perm_rows_for_cpu(cfg)[0])
         z = staging.gc_ratio_global(codes)
         cores = os.cpu_count() or 1
         t, n_done = baseline.time_sample(codes, Y, z, tasks, margin, threads=cores, budget_s=15.0)
         cpu_baseline = dict(value=N * L * n_done / t / 1e9, unit=UNIT, cores=cores, kind="port",
-                            sample=f"first {n_done} tasks of {args.workload} (N={N}, L={L}, P={P}) in {t:.1f} s; "
+                            sample=f"first {n_done} tasks of {args.workload} (N={N}, L={L}, P={Y.shape[1] - 1}) in {t:.1f} s; "
                                    f"float32 scan in C + BLAS sgemm profile + numpy statistics")
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 1),

@@ -252,6 +252,12 @@ int mepp_x_planes_reset(void* x_planes_dev, const void* hits_dev, int64_t hits_c
  * tiled operand of the tensor path holds. */
 int mepp_y_stats(const float* yhat_dev, const int32_t* perm_dev, const float* zhat_dev, int64_t N, int P,
                  double* col_syz_dev, double* ysum_dev, void* stream);
+/* Chunked form of mepp_build_y_rows + mepp_y_stats, for permutation matrices that are staged a few hundred rows at a
+ * time (cfg 5: 1e4 x 1e6 indices = 40 GB): columns col0 .. col0 + n_cols - 1 of y_rows / col_syz from perm_chunk_dev
+ * (n_cols x N; NULL with col0 = 0, n_cols = 1: column 0 = the true scores).  The call with col0 = 0 also clears y_rows
+ * and fills ysum, so it comes first; C = 1 + P of the whole operand. */
+int mepp_build_y_cols(const float* yhat_dev, const int32_t* perm_chunk_dev, const float* zhat_dev, int64_t N, int col0,
+                      int n_cols, int C, float* y_rows_dev, double* col_syz_dev, double* ysum_dev, void* stream);
 int64_t mepp_y_rows_ld(int C);
 int mepp_build_y_rows(const float* yhat_dev, const int32_t* perm_dev, int64_t N, int P, float* y_rows_dev,
                       void* stream);

@@ -218,9 +218,81 @@ __global__ void y_rows_kernel(const float* __restrict__ yhat, const int32_t* __r
   out[n * ldY + c] = v;
 }
 
+// Columns col0 .. col0 + n_cols - 1 of y_rows from a CHUNK of permutation rows (perm_chunk[j][n], j < n_cols; nullptr:
+// the identity, i.e. the true scores of column 0): a 32 x 32 transpose through shared memory, so that the index rows
+// are read and the operand rows written in full lines.
+__global__ void __launch_bounds__(256) y_rows_cols_kernel(const float* __restrict__ yhat, const int32_t* __restrict__ perm_chunk,
+                                                          int64_t N, int64_t n_pad, int col0, int n_cols, int64_t ldY,
+                                                          float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int64_t n0 = (int64_t)blockIdx.x * 32;
+  const int j0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+  for (int jj = ty; jj < 32; jj += 8) {
+    const int j = j0 + jj;
+    const int64_t n = n0 + tx;
+    float v = 0.0f;
+    if (j < n_cols && n < N) v = yhat[perm_chunk ? (int64_t)perm_chunk[(int64_t)j * N + n] : n];
+    tile[jj][tx] = v;
+  }
+  __syncthreads();
+  for (int nn = ty; nn < 32; nn += 8) {
+    const int64_t n = n0 + nn;
+    const int j = j0 + tx;
+    if (n < n_pad && j < n_cols) out[n * ldY + col0 + j] = tile[tx][nn];
+  }
+}
+
+// col_syz[col0 + j] for a chunk of permutation rows (see y_colstats_exact_kernel)
+__global__ void y_colstats_cols_kernel(const float* __restrict__ yhat, const int32_t* __restrict__ perm_chunk,
+                                       const float* __restrict__ zhat, int64_t N, int col0, double* __restrict__ col_syz) {
+  const int j = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t n = threadIdx.x; n < N; n += blockDim.x) {
+    const int64_t src = perm_chunk ? (int64_t)perm_chunk[(int64_t)j * N + n] : n;
+    acc += (double)yhat[src] * (double)zhat[n];
+  }
+  __shared__ double red[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) col_syz[col0 + j] = v;
+  }
+}
+
 }  // namespace mepp
 
 extern "C" {
+
+int mepp_build_y_cols(const float* yhat_dev, const int32_t* perm_chunk_dev, const float* zhat_dev, int64_t N, int col0,
+                      int n_cols, int C, float* y_rows_dev, double* col_syz_dev, double* ysum_dev, void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(yhat_dev && y_rows_dev && col_syz_dev && ysum_dev, "build_y_cols: null pointer");
+  MEPP_REQUIRE(N > 0 && C > 0 && col0 >= 0 && n_cols > 0 && col0 + n_cols <= C && (perm_chunk_dev || (col0 == 0 && n_cols == 1)),
+               "build_y_cols: bad arguments");
+  MEPP_REQUIRE(mepp_device_ok(), "build_y_cols: no sm_100 CUDA device (no CPU fallback)");
+  cudaStream_t st = as_stream(stream);
+  const int64_t ldY = mepp_y_rows_ld(C), n_pad = mepp_pad32(N);
+  MEPP_REQUIRE(n_pad / 32 < (1LL << 31) && (n_cols + 31) / 32 <= 65535, "build_y_cols: shape too large");
+  if (col0 == 0) {
+    // first call: zero the padding rows / columns, sum and sum of squares of the scores (the same for every column)
+    MEPP_CUDA_CHECK(cudaMemsetAsync(y_rows_dev, 0, sizeof(float) * (size_t)n_pad * (size_t)ldY, st));
+    MEPP_CUDA_CHECK(cudaMemsetAsync(ysum_dev, 0, 2 * sizeof(double), st));
+    y_sum_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(yhat_dev, N, ysum_dev);
+  }
+  dim3 grid((unsigned)(n_pad / 32), (unsigned)((n_cols + 31) / 32));
+  y_rows_cols_kernel<<<grid, 256, 0, st>>>(yhat_dev, perm_chunk_dev, N, n_pad, col0, n_cols, ldY, y_rows_dev);
+  if (zhat_dev) {
+    y_colstats_cols_kernel<<<(unsigned)n_cols, 256, 0, st>>>(yhat_dev, perm_chunk_dev, zhat_dev, N, col0, col_syz_dev);
+  } else {
+    MEPP_CUDA_CHECK(cudaMemsetAsync(col_syz_dev + col0, 0, sizeof(double) * (size_t)n_cols, st));
+  }
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 int mepp_build_y_rows(const float* yhat_dev, const int32_t* perm_dev, int64_t N, int P, float* y_rows_dev,
                       void* stream) {

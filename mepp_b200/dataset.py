@@ -17,7 +17,9 @@ class ScoredDataset:
         self.scores = np.ascontiguousarray(scores, dtype=np.float32)
         if self.scores.shape != (self.ascii.shape[0],):
             raise ValueError("scores must be (N,)")
-        self.perm_idx = None if perm_idx is None else np.ascontiguousarray(perm_idx, dtype=np.int32)
+        # (P, N) int32 indices, or a permutations.PermutationSource that generates them in row ranges
+        self.perm_idx = perm_idx if perm_idx is None or hasattr(perm_idx, 'rows') else \
+            np.ascontiguousarray(perm_idx, dtype=np.int32)
         self.has_gc = bool(has_gc)
         self.batch_size = batch_size
         self._engine = None

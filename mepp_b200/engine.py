@@ -178,7 +178,7 @@ class PendingProfile:
 
 
 class Engine:
-    def __init__(self, device=None, mem_budget_bytes=32 << 30, max_group=512):
+    def __init__(self, device=None, mem_budget_bytes=None, max_group=512):
         torch = _torch()
         if not torch.cuda.is_available():
             raise RuntimeError("mepp_b200: no CUDA device visible; the engine has no CPU fallback")
@@ -187,6 +187,11 @@ class Engine:
         with torch.cuda.device(self.device):
             if not _lib.device_ok():
                 raise RuntimeError("mepp_b200: device is not sm_100 (B200); kernels are built for sm_100a only")
+        if mem_budget_bytes is None:
+            # half of the device (90 GB on a B200): the staged dataset, the score operand (41 GB at cfg 5) and two
+            # staging slots of per-group buffers have to fit
+            with torch.cuda.device(self.device):
+                mem_budget_bytes = torch.cuda.mem_get_info()[1] // 2
         self.mem_budget = int(mem_budget_bytes)
         self.max_group = int(max_group)
         self.staged = False
@@ -306,7 +311,16 @@ class Engine:
             # the sparse path multiplies the float32 scores THEMSELVES (exact products, float64 sums: the raw-moment
             # cancellation of core.py:182-185 is harmless there); the centred / scaled copy is for the tensor path
             self._yraw_d = self._to_dev(s32)
-            if isinstance(perm_idx, torch.Tensor) and perm_idx.is_cuda:
+            self._perm_src = None
+            if perm_idx is not None and hasattr(perm_idx, 'rows'):
+                # a permutations.PermutationSource: the index matrix is generated, uploaded and consumed in row chunks
+                # when the score operand is built (_yrows); it never exists as a whole (cfg 5: 40 GB)
+                if tuple(perm_idx.shape) != (int(perm_idx.shape[0]), N):
+                    raise ValueError("perm_idx must have shape (P, N)")
+                P, perm_d = int(perm_idx.shape[0]), None
+                self._perm_src = perm_idx
+                self._perm_ready = None
+            elif isinstance(perm_idx, torch.Tensor) and perm_idx.is_cuda:
                 P, perm_d = int(perm_idx.shape[0]), perm_idx          # already on the device (stage_broadcast)
                 self._perm_ready = getattr(self, '_bcast_perm_ready', None)   # its broadcast may still be in flight
                 self._bcast_perm_ready = None
@@ -396,8 +410,8 @@ class Engine:
         The permutation indices travel on the side stream, behind the first scan."""
         torch = self.torch
         import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return self.stage(ascii_u8, scores, perm_idx, use_gc=use_gc)
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or hasattr(perm_idx, 'rows'):
+            return self.stage(ascii_u8, scores, perm_idx, use_gc=use_gc)     # (a PermutationSource is staged per rank)
         world, rank = dist.get_world_size(), dist.get_rank()
         as_t = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dt)
         with torch.cuda.device(self.device):
@@ -436,6 +450,13 @@ class Engine:
         """Tiled Y operand, column sums and sum of squares (mepp_build_y), once per staged dataset."""
         if self._ysum is None:
             torch = self.torch
+            if self._perm_src is not None and self._perm_d is None:
+                # the tensor path needs the whole index matrix on the device
+                nbytes = 4 * self.P * self.N
+                if nbytes > self.mem_budget // 4:
+                    raise RuntimeError("the tensor profile path needs the whole permutation index matrix on the device "
+                                       f"({nbytes >> 30} GB); use the sparse path or fewer permutations")
+                self._perm_d = self._to_dev(self._perm_src.materialize())
             if self._perm_ready is not None:
                 torch.cuda.current_stream(self.device).wait_event(self._perm_ready)
             self._y_planes = torch.empty(int(_lib.lib.mepp_y_planes_bytes(self.C, self.n_pad)), dtype=torch.uint8,
@@ -462,8 +483,49 @@ class Engine:
         self._ensure_y()
         return self._ysum
 
+    PERM_STAGE_ROWS = 256      # permutation rows per staged chunk of a PermutationSource (1 GB at N = 1e6)
+
+    def _build_y_chunked(self):
+        """Score operand of the sparse path and its column statistics from a PermutationSource: the host generates
+        chunk k + 1 (numpy shuffles on the host threads) while chunk k is uploaded from one of two pinned buffers and
+        scattered into its columns of y_rows (mepp_build_y_cols)."""
+        from concurrent.futures import ThreadPoolExecutor
+        torch = self.torch
+        src, N, P, C_ = self._perm_src, self.N, self.P, self.C
+        ldY = int(_lib.lib.mepp_y_rows_ld(C_))
+        self._y_rows = torch.empty((self.n_pad, ldY), dtype=torch.float32, device=self.device)
+        self._col_syz_x = torch.empty(C_, dtype=torch.float64, device=self.device)
+        self._ysum_x = torch.empty(2, dtype=torch.float64, device=self.device)
+        st = self._stream()
+        args = lambda perm, c0, nc: (_ptr(self._yraw_d), _ptr(perm), _ptr(self.zhat), N, c0, nc, C_, _ptr(self._y_rows),
+                                     _ptr(self._col_syz_x), _ptr(self._ysum_x), st)
+        _lib.check(_lib.lib.mepp_build_y_cols(*args(None, 0, 1)), "build_y_cols")           # column 0: the true scores
+        self.launches += 3
+        rows = self.PERM_STAGE_ROWS
+        pins = [torch.empty((rows, N), dtype=torch.int32, pin_memory=True) for _ in range(2)]
+        devs = [torch.empty((rows, N), dtype=torch.int32, device=self.device) for _ in range(2)]
+        used = [None, None]
+        bounds = [(p0, min(P, p0 + rows)) for p0 in range(0, P, rows)]
+        with ThreadPoolExecutor(max_workers=1, thread_name_prefix="mepp-perm") as ex:
+            gen = lambda k: src.rows(bounds[k][0], bounds[k][1], out=pins[k % 2].numpy()[:bounds[k][1] - bounds[k][0]])
+            fut = ex.submit(gen, 0) if bounds else None
+            for k, (p0, p1) in enumerate(bounds):
+                fut.result()
+                if k + 1 < len(bounds):
+                    if used[(k + 1) % 2] is not None:
+                        used[(k + 1) % 2].synchronize()      # the upload that read this pinned buffer is done
+                    fut = ex.submit(gen, k + 1)
+                devs[k % 2][:p1 - p0].copy_(pins[k % 2][:p1 - p0], non_blocking=True)
+                used[k % 2] = torch.cuda.Event()
+                used[k % 2].record(torch.cuda.current_stream(self.device))
+                _lib.check(_lib.lib.mepp_build_y_cols(*args(devs[k % 2], 1 + p0, p1 - p0)), "build_y_cols")
+                self.launches += 2
+        torch.cuda.current_stream(self.device).synchronize()      # the staging buffers are freed on return
+
     def _ensure_y_exact(self):
         """Column statistics of the exact float32 score operand (sparse path: mepp_y_stats), once per staged dataset."""
+        if self._ysum_x is None and self._perm_src is not None and self._perm_d is None:
+            self._build_y_chunked()
         if self._ysum_x is None:
             torch = self.torch
             if self._perm_ready is not None:
@@ -476,7 +538,8 @@ class Engine:
 
     def _yrows(self):
         if self._y_rows is None:
-            self._ensure_y_exact()
+            self._ensure_y_exact()         # (a PermutationSource builds the operand together with its statistics)
+        if self._y_rows is None:
             ldY = int(_lib.lib.mepp_y_rows_ld(self.C))
             self._y_rows = self.torch.empty((self.n_pad, ldY), dtype=self.torch.float32, device=self.device)
             _lib.check(_lib.lib.mepp_build_y_rows(_ptr(self._yraw_d), _ptr(self._perm_d), self.N, self.P,

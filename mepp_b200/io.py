@@ -113,7 +113,10 @@ def save_dataset(dataset, path, compression=None, element_spec_suffix='.element_
         return
     arrays = dict(ascii=dataset.ascii, scores=dataset.scores, has_gc=np.array(dataset.has_gc),
                   batch_size=np.array(dataset.batch_size if dataset.batch_size is not None else -1))
-    if dataset.perm_idx is not None:
+    if dataset.perm_idx is not None and hasattr(dataset.perm_idx, 'rows'):
+        # a PermutationSource is saved as its seed entropy: the indices are regenerated in chunks when staged
+        arrays['perm_source'] = np.array([str(dataset.perm_idx.entropy), str(dataset.perm_idx.P)])
+    elif dataset.perm_idx is not None:
         arrays['perm_idx'] = dataset.perm_idx
     saver = np.savez_compressed if compression else np.savez
     saver(os.path.join(normpath, 'dataset.npz'), **arrays)
@@ -124,5 +127,9 @@ def save_dataset(dataset, path, compression=None, element_spec_suffix='.element_
 def load_dataset(path, compression=None, element_spec_suffix='.element_spec.p'):
     with np.load(os.path.join(os.path.normpath(path), 'dataset.npz')) as z:
         bs = int(z['batch_size'])
-        return ScoredDataset(z['ascii'], z['scores'], z['perm_idx'] if 'perm_idx' in z else None,
+        perm = z['perm_idx'] if 'perm_idx' in z else None
+        if 'perm_source' in z:
+            from .permutations import PermutationSource
+            perm = PermutationSource(z['ascii'].shape[0], int(z['perm_source'][1]), seed=int(z['perm_source'][0]))
+        return ScoredDataset(z['ascii'], z['scores'], perm,
                              has_gc=bool(z['has_gc']), batch_size=None if bs < 0 else bs)

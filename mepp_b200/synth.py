@@ -45,13 +45,18 @@ def synth_sequences(N, L, seed, motifs=None, n_plant=8, n_rate=0.002, lower_rate
     return np.ascontiguousarray(seq), scores
 
 
-def synth_permutations(N, P, seed):
-    rng = np.random.Generator(np.random.PCG64(seed + 1))
-    out = np.empty((P, N), dtype=np.int32)
-    base = np.arange(N, dtype=np.int32)
-    for p in range(P):
-        out[p] = rng.permutation(base)
-    return out
+LAZY_PERM_BYTES = 8 << 30     # above this the index matrix stays a PermutationSource (cfg 5: 40 GB)
+
+
+def synth_permutations(N, P, seed, lazy=None):
+    """(P, N) int32 permutation indices from PCG64 streams seeded with seed + 1 (permutations.PermutationSource: chunked
+    streams, filled by the host threads).  Matrices above LAZY_PERM_BYTES are returned as the source itself: the engine
+    stages it in row chunks and the oracle asks for the rows it checks."""
+    from .permutations import PermutationSource
+    src = PermutationSource(N, P, seed + 1)
+    if lazy is None:
+        lazy = 4 * N * P > LAZY_PERM_BYTES
+    return src if lazy else src.materialize()
 
 
 def synth_motifs(n_motifs, seed, m_lo=6, m_hi=20):

@@ -110,7 +110,7 @@ def accuracy_report(codes, Y32, z32, tasks, task_ids, margin, gpu_hits, gpu_r, g
             rel = np.where(scale > 0, d / (np.abs(r64) + scale), 0.0)
         out['r_max_rel_err'] = max(out['r_max_rel_err'], float(rel.max()))
         out['r_within_1e5_gate'] &= bool((d <= 1e-5 * np.abs(r64) + 1e-5 * scale + 1e-12).all())
-        if P > 0:
+        if P > 0 and gpu_positions is not None:
             cols = profile.positional_r_columns(np.nan_to_num(r64.astype(np.float32), 0.0),
                                                 confidence_interval_pct=confidence_interval_pct)
             for name in ('permutation_full_positional_r_pval', 'permutation_semi_positional_r_pval',

@@ -267,6 +267,24 @@ def test_run_batch_isolates_a_poisoned_motif(tmp_path):
         assert pa.equals(pb)
 
 
+def test_chunked_permutation_staging_equals_the_whole_matrix():
+    """A PermutationSource staged in row chunks (Engine._build_y_chunked, how cfg 5's 40 GB index matrix reaches the
+    device) gives the same operand, statistics and outputs as the materialised (P, N) matrix -- to the last bit."""
+    from mepp_b200 import synth, permutations
+    cfg = synth.make_config("cfg1", n_seq=777, n_motifs=4, n_perm=8)
+    tasks = [(pwm, o) for _, pwm, o in cfg["tasks"]]
+    P = 200
+    src = permutations.PermutationSource(777, P, seed=5)
+    whole = _engine().stage(cfg["ascii"], cfg["scores"], src.materialize(), use_gc=True)
+    want = whole.profile(tasks, margin=2, return_r=True)
+    eng = _engine()
+    eng.PERM_STAGE_ROWS = 64                      # four chunks, the last one short
+    got = eng.stage(cfg["ascii"], cfg["scores"], src, use_gc=True).profile(tasks, margin=2, return_r=True)
+    assert torch.equal(eng._y_rows, whole._y_rows) and torch.equal(eng._col_syz_x, whole._col_syz_x)
+    assert got.r.shape[2] == 1 + P and np.allclose(got.r, want.r, rtol=1e-6, atol=1e-9)   # (float64 atomics: order may differ)
+    assert np.array_equal(got.density, want.density)
+
+
 def test_match_driven_sparse_profile_equals_the_entry_form():
     """mepp_profile_matches (one gathered row of Y per match, window sums of the per-position products) against
     mepp_profile_sparse (one per non-zero of the blurred matrix): same r within the float32 rounding of the blurred

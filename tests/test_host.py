@@ -507,3 +507,27 @@ def test_task_writer_pool_writes_the_reference_layout_and_isolates_failures(tmp_
         assert list(pos.columns) == list(jobs[i]['positions'])
         assert open(os.path.join(d, 'positions_df.tsv')).read() == pos.to_csv(sep='\t', index=False)
     assert not os.path.exists(os.path.join(jobs[1]['outdir'], 'positions_df.tsv'))
+
+
+def test_permutation_source_row_ranges_equal_the_full_matrix(tmp_path):
+    """permutations.PermutationSource: any row range equals the same rows of the whole (P, N) matrix whatever the
+    number of host threads (chunked random streams), every row is a permutation, and a dataset that holds a source
+    survives save_dataset / load_dataset as its seed."""
+    from mepp_b200 import permutations, io as mio
+    from mepp_b200.dataset import ScoredDataset
+    N, P = 1000, 300
+    full = permutations.make_permutation_indices(N, P, seed=11, threads=1)
+    assert full.shape == (P, N) and full.dtype == np.int32
+    assert (np.sort(full, axis=1) == np.arange(N)).all()
+    src = permutations.PermutationSource(N, P, seed=11)
+    assert np.array_equal(src.rows(0, P, threads=4), full)
+    assert np.array_equal(src.rows(128, 260, threads=3), full[128:260])
+    assert np.array_equal(src.rows(256, 999), full[256:])
+    with pytest.raises(ValueError):
+        src.rows(10, 20)
+    assert not np.array_equal(permutations.make_permutation_indices(N, P, seed=12), full)
+    ds = ScoredDataset(np.full((N, 8), ord('A'), dtype=np.uint8), np.arange(N, dtype=np.float32), perm_idx=src)
+    assert ds.num_permutations == P
+    mio.save_dataset(ds, str(tmp_path / 'ds'))
+    back = mio.load_dataset(str(tmp_path / 'ds'))
+    assert hasattr(back.perm_idx, 'rows') and np.array_equal(back.perm_idx.rows(64, 128), full[64:128])
