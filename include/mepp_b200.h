@@ -215,6 +215,7 @@ int mepp_scan_lean(const uint32_t* sym_T_dev, const float* zhat_dev,
  * onehot_dev: mepp_onehot_words(N, L) uint32.  units_host / mlen_host: host copies of the unit list (null = one unit per
  * task, like units_dev) and of the motif lengths of all T tasks (the N-tile plan is made on the host).
  * work_dev: mepp_scan_tc_work_bytes(N, L, units) bytes of scratch (weights, candidate lists).
+ * entries_dev may be NULL (match-driven profile, mepp_profile_matches: only the row sums are built from the buckets).
  * dbg_acc_dev (optional, int32 [128][dbg_ld]): raw accumulators of the first 128 windows, for bring-up tests. */
 int64_t mepp_onehot_words(int64_t N, int L);
 int mepp_pack_onehot(const uint8_t* ascii_dev, int64_t N, int L, uint32_t* onehot_dev, void* stream);
@@ -263,10 +264,12 @@ int mepp_build_y_rows(const float* yhat_dev, const int32_t* perm_dev, int64_t N,
                       void* stream);
 /* Match-driven form of the sparse profile (default): the blur commutes with the contraction, so r is built from ONE
  * gathered row of Y per match -- hits_dev / hit_count_dev / count_dev as mepp_scan leaves them, rowstats_dev the
- * float32-blur row sums -- instead of one per non-zero of the blurred matrix (2 margin + 1 times fewer bytes).  Same
- * outputs as mepp_profile_sparse up to the float32 rounding of the blurred value (<= 6e-8 relative per term).  A match
- * list longer than hits_cap leaves r untouched (the caller sees hit_count > hits_cap and redoes the group). */
-int64_t mepp_profile_matches_work_bytes(int64_t m_rows, int64_t hits_cap);
+ * float32-blur row sums -- instead of one per non-zero of the blurred matrix (2 margin + 1 times fewer bytes).  Two
+ * passes: per-position products S0 (float64, m_rows x mepp_y_rows_ld(C), inside work_dev), then their window sums
+ * and the correlation epilogue.  Same outputs as mepp_profile_sparse up to the float32 rounding of the blurred value
+ * (<= 6e-8 relative per term).  A match list longer than hits_cap leaves r untouched (the caller sees
+ * hit_count > hits_cap and redoes the group). */
+int64_t mepp_profile_matches_work_bytes(int64_t m_rows, int64_t hits_cap, int C);
 int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_count_dev, int64_t hits_cap,
                          const int32_t* count_dev, int T, int L, int margin, const float* y_rows_dev,
                          const double* rowstats_dev, const double* colconst_dev, float* r_dev, int64_t ldr, int C,

@@ -1096,8 +1096,10 @@ __global__ void __launch_bounds__(128) bucket_entries_kernel(const uint2* __rest
   const int total = __shfl_sync(full, pre, 31);
   if (total == 0) return;
   const int list = kb & (MEPP_ENTRY_LISTS - 1);
+  // entries == nullptr (match-driven profile, mepp_profile_matches): only the row sums are wanted
+  const bool emit_entries = entries != nullptr;
   unsigned long long slot = 0ull;
-  if (lane == 0) slot = atomicAdd(entry_count + list * 16, (unsigned long long)total);
+  if (emit_entries && lane == 0) slot = atomicAdd(entry_count + list * 16, (unsigned long long)total);
   slot = __shfl_sync(full, slot, 0) + (unsigned long long)(pre - cnt);
   uint4* dst = reinterpret_cast<uint4*>(entries + (int64_t)list * sub_cap);
   auto emit = [&](int idx, int r_lo, int r_hi, int sq) {
@@ -1109,9 +1111,11 @@ __global__ void __launch_bounds__(128) bucket_entries_kernel(const uint2* __rest
         acc = __fadd_rn(acc, val[j]);
       const float xb = k > 1 ? __fdiv_rn(acc, kf) : acc;
       const int r = t * L + p;
-      if ((int64_t)slot < sub_cap) dst[slot] = make_uint4((uint32_t)r, (uint32_t)ns, __float_as_uint(xb), 0u);
-      ++slot;
-      atomicAdd(row_nnz + r, 1);
+      if (emit_entries) {
+        if ((int64_t)slot < sub_cap) dst[slot] = make_uint4((uint32_t)r, (uint32_t)ns, __float_as_uint(xb), 0u);
+        ++slot;
+        atomicAdd(row_nnz + r, 1);
+      }
       const double v = (double)xb;
       double* rs = rowstats + (int64_t)r * 3;
       atomicAdd(rs + 0, v); atomicAdd(rs + 1, v * v); atomicAdd(rs + 2, v * z);
@@ -1407,14 +1411,15 @@ extern "C" int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_de
                             void* stream) {
   using namespace mepp;
   MEPP_REQUIRE(sym_T_dev && onehot_dev && lut_dev && bias_dev && mlen_dev && nfilt_dev && mlen_host && rowstats_dev &&
-               count_dev && density_dev && entries_dev && entry_count_dev && row_nnz_dev && buckets_dev &&
+               count_dev && density_dev && entry_count_dev && row_nnz_dev && buckets_dev &&
                bucket_count_dev && work_dev, "scan_tc: null pointer");
   MEPP_REQUIRE(N > 0 && L > 0 && T > 0 && L <= 65535, "scan_tc: bad sizes (L <= 65535)");
   MEPP_REQUIRE((units_dev == nullptr) == (units_host == nullptr), "scan_tc: the unit list is needed on both sides");
   MEPP_REQUIRE(units_dev == nullptr || (n_units > 0 && n_units <= T), "scan_tc: bad unit list");
   MEPP_REQUIRE((int64_t)T * L < (1LL << 31), "scan_tc: T * L must be below 2^31");
   MEPP_REQUIRE(margin >= 0 && margin <= MEPP_MAX_MARGIN, "scan_tc: margin must be in [0, 16]");
-  MEPP_REQUIRE(entry_cap >= MEPP_ENTRY_LISTS && entry_cap % MEPP_ENTRY_LISTS == 0, "scan_tc: bad entry capacity");
+  MEPP_REQUIRE(entries_dev == nullptr || (entry_cap >= MEPP_ENTRY_LISTS && entry_cap % MEPP_ENTRY_LISTS == 0),
+               "scan_tc: bad entry capacity");
   MEPP_REQUIRE(hits_dev == nullptr || hit_count_dev != nullptr, "scan_tc: hits need a hit counter");
   MEPP_REQUIRE(N * (int64_t)L / 4 < (1LL << 32), "scan_tc: N * L must be below 2^34");
   MEPP_REQUIRE(mepp_device_ok(), "scan_tc: no sm_100 CUDA device (no CPU fallback)");

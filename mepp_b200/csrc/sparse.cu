@@ -195,28 +195,27 @@ __global__ void __launch_bounds__(256, 3) profile_sparse_kernel(const __grid_con
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// Match-driven form (default).  The blur is linear and acts along the positions, the contraction along the sequences,
-// so they commute:   sum_n xbar[n, p] y[n, c]  =  (1 / k) sum_{|d| <= margin} ( sum_n x0[n, p + d] y[n, c] ).
+// Match-driven form.  The blur is linear and acts along the positions, the contraction along the sequences, so they
+// commute:   sum_n xbar[n, p] y[n, c]  =  (1 / k) sum_{|d| <= margin} ( sum_n x0[n, p + d] y[n, c] ).
 // Gathering one row of Y per MATCH instead of one per non-zero of the blurred matrix moves 2 margin + 1 = 5 times
-// fewer bytes -- and those bytes are what bounds the kernel (at cfg 3 Y is 410 MB and comes from HBM: 65 GB per step
-// for the entry form).  A warp owns 32 consecutive positions of one task and 256 columns: it walks the positions once,
-// S0[q] = sum over the matches at q of x0 * Y[seq] (float64, exact products), keeps the last k rows of S0 in a
-// shared-memory ring and a running window sum, and applies the correlation epilogue to sum / k.  The only difference
-// to the entry form is that xbar is not rounded to float32 before it multiplies y (<= 6e-8 relative per term; the row
-// statistics sum(xbar), sum(xbar^2), sum(xbar z) still come from the float32 blur, bucket_entries_kernel / the scan).
+// fewer bytes and converts 5 times fewer floats -- at cfg 3 Y is 410 MB and comes from HBM (65 GB per step for the
+// entry form).  Two passes, each with the simplest possible inner loop:
+//   match_gather_kernel: S0[row, :] = sum over the matches (n, x0) of row = task * L + position of x0 * Y[n, :]
+//                        (float64, exact products; the loop of profile_sparse_kernel without its epilogue; rows
+//                        without a match are neither computed nor written),
+//   match_blur_kernel:   window sums of S0 along the positions of a task (each S0 row is read once: a CTA walks a block
+//                        of positions with the last k rows in a shared-memory ring) and the correlation epilogue.
+// S0 costs 8 bytes per (row, column) written and read once (2 x 2.6 GB per cfg 3 step), against the 52 GB of gathers it
+// saves.  The only difference to the entry form is that xbar is not rounded to float32 before it multiplies y
+// (<= 6e-8 relative per term; the row statistics sum(xbar), sum(xbar^2), sum(xbar z) still come from the float32 blur).
 struct HitRec4 { int32_t task, seq, pos; float x0; };
-
-constexpr int kMCols = 256;      // columns of S per warp: lane holds slab * 256 + j * 128 + lane * 4 + {0..3}, j < 2
-constexpr int kMRows = 32;       // output positions per work item, at most
-constexpr int kMBlockRecs = 512; // matches per work item, about (a single position may hold more)
 
 // offsets[0 .. m_rows] = exclusive prefix sum of count; offsets[m_rows + 1] = 1 when the match list overflowed;
 // cursor[0 .. m_rows) = 0
 __global__ void __launch_bounds__(kScanThreads) match_offsets_kernel(const int32_t* __restrict__ count, int64_t m_rows,
                                                                      const unsigned long long* __restrict__ hit_count,
                                                                      int64_t hits_cap, int32_t* __restrict__ offsets,
-                                                                     int32_t* __restrict__ cursor, int L,
-                                                                     int32_t* __restrict__ blk_start) {
+                                                                     int32_t* __restrict__ cursor) {
   __shared__ int32_t s_warp[32];
   __shared__ int32_t s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -258,56 +257,6 @@ __global__ void __launch_bounds__(kScanThreads) match_offsets_kernel(const int32
     __syncthreads();
   }
   if (tid == 0) offsets[m_rows] = s_base;
-  __syncthreads();
-  // Work items of the gather kernel: blocks of consecutive positions of one task, at most kMRows positions and about
-  // kMBlockRecs matches each.  Real profiles are peaked (that is what MEPP looks for): a position under a peak holds
-  // 50 times the average number of matches, and equal-length blocks would leave one warp with most of a task's work.
-  // A row starts a block when it is a multiple of kMRows inside its task or when the running match count crosses a
-  // multiple of kMBlockRecs -- a local rule, compacted with one more scan.  blk_start[0] = number of blocks,
-  // blk_start[1 + b] = first row of block b, blk_start[1 + n] = m_rows.
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int64_t tile = 0; tile < m_rows; tile += 4 * kScanThreads) {
-    const int64_t i0 = tile + 4 * tid;
-    int32_t v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int64_t row = i0 + k;
-      int f = 0;
-      if (row < m_rows) {
-        const int pp = (int)(row % L);
-        f = (pp % kMRows) == 0 || (offsets[row] / kMBlockRecs) != (offsets[row - 1] / kMBlockRecs);   // (pp > 0 => row > 0)
-      }
-      v[k] = f;
-    }
-    const int32_t mine = v[0] + v[1] + v[2] + v[3];
-    int32_t inc = mine;
-    for (int o = 1; o < 32; o <<= 1) {
-      const int32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += u;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      int32_t w = s_warp[lane];
-      for (int o = 1; o < 32; o <<= 1) {
-        const int32_t u = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += u;
-      }
-      s_warp[lane] = w;
-    }
-    __syncthreads();
-    int32_t run = s_base + (warp ? s_warp[warp - 1] : 0) + inc - mine;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (v[k]) blk_start[1 + run] = (int32_t)(i0 + k);
-      run += v[k];
-    }
-    __syncthreads();
-    if (tid == kScanThreads - 1) s_base = run;
-    __syncthreads();
-  }
-  if (tid == 0) { blk_start[0] = s_base; blk_start[1 + s_base] = (int32_t)m_rows; }
 }
 
 // csr[offsets[row] + k] = (seq, x0) for the k-th match of row = task * L + pos that arrives
@@ -324,212 +273,171 @@ __global__ void match_fill_kernel(const HitRec4* __restrict__ hits, const unsign
   }
 }
 
-struct MatchArgs {
-  const uint2* csr; const int32_t* offsets; const int32_t* blk_start;
+struct GatherArgs {
+  const uint2* csr; const int32_t* offsets;
   const float* y_rows; int64_t ldY;
-  const double* rowstats; const double* colconst;
-  float* r; int64_t ldr;
-  int T, L, C, margin, n_slabs, warps;
+  double* S0;                      // [m_rows][ldY]
+  int64_t m_rows; int n_slabs;
 };
 
-constexpr int kMBatch = 4;       // records per cp.async group
-constexpr int kMBatches = 4;     // batches in the gather ring: three in flight while one is consumed
-constexpr int kMDepth = 16;      // slots of the gather ring (power of two >= kMBatch * kMBatches), kMCols * 4 bytes each
-constexpr bool kMF32 = false;    // true: sum up to kMFlush products in float32 before they move to the float64 accumulators
-constexpr int kMFlush = 8;       // (cheaper per element, but the result then depends on the order of the match list)
-constexpr int kMV = kMCols / 128;   // float4 pieces of a gathered row per lane
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+// One warp = one (row with matches, slab of 512 columns); four matches (16 x 512 B of Y) in flight per warp.
+__global__ void __launch_bounds__(256, 3) match_gather_kernel(const __grid_constant__ GatherArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_items = a.m_rows * a.n_slabs;
+  if (a.offsets[a.m_rows + 1] != 0) return;            // match list overflow: the caller redoes the group
+  const int64_t ld4 = a.ldY >> 2;
+  for (int64_t item = warp0; item < n_items; item += n_warps) {
+    const int64_t row = item / a.n_slabs;
+    const int slab = (int)(item - row * a.n_slabs);
+    const int beg = __ldg(a.offsets + row), end = __ldg(a.offsets + row + 1);
+    if (beg == end) continue;
+    const float4* yb = reinterpret_cast<const float4*>(a.y_rows) + (int64_t)slab * (kSlabCols / 4) + lane;
+    double acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+    auto rec = [&](int e) { return e < end ? __ldg(a.csr + e) : make_uint2(0u, 0u); };   // (row 0, x = 0) past the end
+    uint2 c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = rec(beg + k);
+#pragma unroll 1
+    for (int e = beg; e < end; e += 4) {
+      float4 v[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4* y = yb + (int64_t)c[k].x * ld4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[k][j] = __ldg(y + j * 32);
+      }
+      uint2 nx[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nx[k] = rec(e + 4 + k);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) fma4(acc, (double)__uint_as_float(c[k].y), v[k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c[k] = nx[k];
+    }
+    double2* dst = reinterpret_cast<double2*>(a.S0 + row * a.ldY + (int64_t)slab * kSlabCols + lane * 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dst[j * 64] = make_double2(acc[4 * j + 0], acc[4 * j + 1]);
+      dst[j * 64 + 1] = make_double2(acc[4 * j + 2], acc[4 * j + 3]);
+    }
+  }
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Work item = (block of positions of one task, slab of kMCols columns), one warp each.  The matches of the positions
-// [p0 - margin, p1 + margin) of a task are ONE contiguous run of the CSR (rows are positions), so the warp streams that
-// run through a ring of asynchronous copies (the latency of a Y row -- HBM at cfg 3 -- is paid once per ring, not once
-// per row) and finishes a position whenever the stream crosses a row boundary.
-// Arithmetic: exact float32 x float32 products accumulated in float64 (kMF32 = false), the window sums and the
-// correlation epilogue in float64.  The kernel is bound by instruction issue -- ~100 instructions per record and 128
-// columns, 20 of them the float -> double conversions (ncu: profiles/r02_profile_matches_ncu_summary.txt); summing a few
-// products in float32 first (kMF32) is cheaper per element but makes r depend on the order of the match list, which
-// the atomics of match_fill_kernel do not fix, so it stays off.
-__global__ void __launch_bounds__(128, 2) profile_matches_kernel(const __grid_constant__ MatchArgs a) {
-  extern __shared__ __align__(16) uint8_t s_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+struct BlurArgs {
+  const double* S0; int64_t ldS0; const int32_t* offsets;
+  const double* rowstats; const double* colconst;
+  float* r; int64_t ldr;
+  int T, L, C, margin, pb, n_pb, n_slabs;
+};
+
+constexpr int kBlurThreads = 128;                 // one thread = two adjacent columns
+constexpr int kBlurCols = 2 * kBlurThreads;       // columns of r per CTA
+constexpr int kBlurMaxPb = 128;                   // positions per CTA, at most
+
+// CTA = (task, block of `pb` positions, slab of 256 columns).  It walks the positions p0 - margin .. p1 + margin - 1
+// once: row q of S0 enters a ring of the last k rows (shared memory), and row p = q - margin of r is the sum of the
+// ring in position order, divided by k, through the correlation epilogue (core.py:182-193,255-265 in float64 +
+// np.nan_to_num, core.py:602).  Rows of S0 without a match were never written: they are known from the CSR offsets.
+__global__ void __launch_bounds__(kBlurThreads) match_blur_kernel(const __grid_constant__ BlurArgs a) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  __shared__ double s_rc[kBlurMaxPb][4];            // per row of the block: n / sqrt(ax ay) ..., see below
+  __shared__ uint8_t s_has[kBlurMaxPb + 2 * MEPP_MAX_MARGIN];
   if (a.offsets[(int64_t)a.T * a.L + 1] != 0) return;           // match list overflow: the caller redoes the group
-  if (warp >= a.warps) return;
+  const int tid = threadIdx.x;
   const int k = 2 * a.margin + 1;
-  // per warp: [k + 1][4 kMV][32] float64 (window ring + the running window sum)
-  const size_t per_warp = (size_t)(k + 1) * kMCols * 8;
-  double* ring = reinterpret_cast<double*>(s_raw + warp * per_warp) + lane;
-  double* runp = ring + (size_t)k * kMCols;
-  const int64_t n_items = (int64_t)a.blk_start[0] * a.n_slabs;
-  const int64_t w0 = (int64_t)blockIdx.x * a.warps + warp, n_warps = (int64_t)gridDim.x * a.warps;
+  double2* ring = reinterpret_cast<double2*>(s_dyn) + tid;      // ring[j * kBlurThreads]
+  int64_t b = blockIdx.x;
+  const int slab = (int)(b % a.n_slabs); b /= a.n_slabs;
+  const int pbi = (int)(b % a.n_pb);
+  const int t = (int)(b / a.n_pb);
+  const int p0 = pbi * a.pb, p1 = p0 + a.pb < a.L ? p0 + a.pb : a.L;
+  const int q0 = p0 - a.margin, q1 = p1 + a.margin;             // rows of S0 this CTA walks
   const double* cc = a.colconst;
   const double n = cc[0], sy = cc[1], ay = cc[2], sz = cc[3], az = cc[4];
   const bool use_z = cc[5] != 0.0;
-  const double inv_k = 1.0 / (double)k;
-  const unsigned full = 0xffffffffu;
-  for (int64_t item = w0; item < n_items; item += n_warps) {
-    // consecutive items = the slabs of one block of positions: the warps that gather the same rows of Y run together
-    const int slab = (int)(item % a.n_slabs);
-    const int64_t blk = item / a.n_slabs;
-    const int row0 = __ldg(a.blk_start + 1 + blk), row1 = __ldg(a.blk_start + 2 + blk);
-    const int t = row0 / a.L, p0 = row0 - t * a.L, p1 = p0 + (row1 - row0);
-    const int qa = p0 - a.margin > 0 ? p0 - a.margin : 0, qb = p1 + a.margin < a.L ? p1 + a.margin : a.L;
-    const float* yb = a.y_rows + (int64_t)slab * kMCols + lane * 4;
-    const int32_t* offs = a.offsets + (int64_t)t * a.L;
-    // Nothing in the loops below may wait for a dependent global load (a warp issues in order: one exposed L2 round
-    // trip per record or per position would serialise the whole stream).  The row boundaries of the item's positions
-    // are fetched once (lane i: boundary qa + i, + 32, + 64), the CSR records in coalesced chunks of 32 one chunk
-    // ahead, the row statistics one position ahead.
-    int32_t bnd[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int qq = qa + lane + 32 * j;
-      bnd[j] = __ldg(offs + (qq < qb ? qq : qb));
+  const int64_t row_t = (int64_t)t * a.L;
+  for (int i = tid; i < q1 - q0; i += kBlurThreads) {
+    const int q = q0 + i;
+    s_has[i] = (q >= 0 && q < a.L) ? (__ldg(a.offsets + row_t + q + 1) != __ldg(a.offsets + row_t + q)) : 0;
+  }
+  for (int i = tid; i < p1 - p0; i += kBlurThreads) {
+    const double* rs = a.rowstats + (row_t + p0 + i) * 3;
+    const double sx = rs[0], sxx = rs[1], sxz = rs[2];
+    const double ax = n * sxx - sx * sx;
+    double r_xz = 0.0, row_den = 1.0;
+    if (use_z) {
+      r_xz = (n * sxz - sx * sz) / sqrt(ax * az);
+      row_den = 1.0 / sqrt(1.0 - r_xz * r_xz);
     }
-    auto boundary = [&](int qq) {           // offs[qq] for qa <= qq <= qb (warp uniform)
-      const int i = qq - qa;
-      const int32_t b0 = __shfl_sync(full, bnd[0], i & 31), b1 = __shfl_sync(full, bnd[1], i & 31),
-                    b2 = __shfl_sync(full, bnd[2], i & 31);
-      return i < 32 ? b0 : i < 64 ? b1 : b2;
-    };
-    const int e_begin = boundary(qa), e_end = boundary(qb);
-    float part[4 * kMV];                    // float32 partial sums of the current position (at most kMFlush records)
-    double s0[4 * kMV];                     // float64 sums of the current position
+    s_rc[i][0] = 1.0 / sqrt(ax * ay); s_rc[i][1] = sx * sy; s_rc[i][2] = r_xz; s_rc[i][3] = row_den;
+  }
+  for (int j = 0; j < k; ++j) ring[j * kBlurThreads] = make_double2(0.0, 0.0);
+  __syncthreads();
+  const int c0 = slab * kBlurCols + 2 * tid;
+  const bool store = c0 < a.ldr;
+  double2 cz0 = make_double2(0.0, 1.0), cz1 = make_double2(0.0, 1.0);
+  if (use_z) {
+    if (c0 < a.C) cz0 = __ldg(reinterpret_cast<const double2*>(cc + 8 + 2 * c0));
+    if (c0 + 1 < a.C) cz1 = __ldg(reinterpret_cast<const double2*>(cc + 8 + 2 * (c0 + 1)));
+  }
+  const double inv_k = 1.0 / (double)k;
+  const double* src = a.S0 + row_t * a.ldS0 + c0;
+  int slot = 0;
+  int live_rows = 0;                      // rows with a match among the k rows of the ring
+  constexpr int kAhead = 8;               // rows requested before the first of them is used
+  for (int qb = q0; qb < q1; qb += kAhead) {
+    double2 v[kAhead];
 #pragma unroll
-    for (int j = 0; j < 4 * kMV; ++j) { part[j] = 0.0f; s0[j] = 0.0; }
-    for (int i = 0; i < (k + 1) * 4 * kMV; ++i) ring[i * 32] = 0.0;
-    __syncwarp();
-    int slot = 0, n_part = 0;
-    int q = p0 - a.margin;                 // the position whose matches are being summed (rows before 0 are empty)
-    int next_bnd = q >= 0 ? boundary(q + 1) : e_begin;        // first record that does NOT belong to position q
-    // record chunks: chunk c = records e_begin + 32 c + lane
-    auto load_chunk = [&](int c) {
-      const int e = e_begin + 32 * c + lane;
-      return e < e_end ? __ldg(a.csr + e) : make_uint2(0u, 0u);
-    };
-    uint2 ch_prev = make_uint2(0u, 0u), ch_cur = load_chunk(0), ch_next = load_chunk(1);
-    int ch_idx = 0;                        // chunk index of ch_cur = chunk of the issue pointer
-    // one batch = kMBatch records starting at e (e - e_begin is a multiple of kMBatch: a batch never straddles a chunk);
-    // the rows of Y go straight to registers, the next batch is requested before the current one is summed
-    auto load_batch = [&](int e, float4 (&v)[kMBatch][kMV]) {
-      if (e < e_end) {
-        const int i = e - e_begin;
-        if ((i >> 5) != ch_idx) { ch_prev = ch_cur; ch_cur = ch_next; ++ch_idx; ch_next = load_chunk(ch_idx + 1); }
+    for (int u = 0; u < kAhead; ++u) {
+      const int q = qb + u;
+      v[u] = make_double2(0.0, 0.0);
+      if (q < q1 && s_has[q - q0]) v[u] = __ldg(reinterpret_cast<const double2*>(src + (int64_t)q * a.ldS0));
+    }
 #pragma unroll
-        for (int u = 0; u < kMBatch; ++u) {
-          const uint32_t seq = __shfl_sync(full, ch_cur.x, (i + u) & 31);     // (padding records: row 0, x = 0)
-          const float4* src = reinterpret_cast<const float4*>(yb + (int64_t)seq * a.ldY);
-#pragma unroll
-          for (int j = 0; j < kMV; ++j) v[u][j] = __ldg(src + 32 * j);
-        }
-      }
-    };
-    auto flush_part = [&]() {
-#pragma unroll
-      for (int j = 0; j < 4 * kMV; ++j) { s0[j] += f2d(part[j]); part[j] = 0.0f; }
-      n_part = 0;
-    };
-    // row statistics of the next row to be written, fetched one position ahead
-    double st_sx = 0.0, st_sxx = 0.0, st_sxz = 0.0;
-    auto fetch_stats = [&](int p) {
-      if (p >= p0 && p < p1) {
-        const double* rsx = a.rowstats + ((int64_t)t * a.L + p) * 3;
-        st_sx = __ldg(rsx); st_sxx = __ldg(rsx + 1); st_sxz = __ldg(rsx + 2);
-      }
-    };
-    fetch_stats(p0);
-    // position q is complete: it enters the window, the oldest row leaves, and row q - margin can be written
-    auto finish_position = [&]() {
-      if (n_part) flush_part();
-      double* rs = ring + (size_t)slot * kMCols;
+    for (int u = 0; u < kAhead; ++u) {
+      const int q = qb + u;
+      if (q >= q1) break;
+      // row q enters, row q - k leaves
+      live_rows += (int)s_has[q - q0] - (q - k >= q0 ? (int)s_has[q - k - q0] : 0);
+      ring[slot * kBlurThreads] = v[u];
       if (++slot == k) slot = 0;
       const int p = q - a.margin;
-      ++q;
-      next_bnd = q < 0 ? e_begin : q < qb ? boundary(q + 1) : e_end;
-      const bool emit = p >= p0;
+      if (p < p0) continue;
+      float o0 = 0.0f, o1 = 0.0f;
       // core.py:79-91 zeroes the first / last `margin` rows of the blurred matrix
       const bool live = p >= a.margin && p < a.L - a.margin;
-      const int64_t row = (int64_t)t * a.L + p;
-      double inv_xy = 0.0, sxsy = 0.0, r_xz = 0.0, row_den = 1.0;
-      if (emit) {
-        const double sx = st_sx, sxx = st_sxx, sxz = st_sxz;
-        fetch_stats(p + 1);
-        const double ax = n * sxx - sx * sx;
-        inv_xy = 1.0 / sqrt(ax * ay);
-        sxsy = sx * sy;
-        if (use_z) {
-          r_xz = (n * sxz - sx * sz) / sqrt(ax * az);
-          row_den = 1.0 / sqrt(1.0 - r_xz * r_xz);
+      double w0 = 0.0, w1 = 0.0;
+      if (live && live_rows > 0) {
+        int j = slot;                                           // oldest row first: position order
+        for (int i = 0; i < k; ++i) {
+          const double2 x = ring[j * kBlurThreads];
+          w0 += x.x; w1 += x.y;
+          if (++j == k) j = 0;
         }
       }
-#pragma unroll
-      for (int j = 0; j < kMV; ++j) {
-        float o[4];
-        const int c0 = slab * kMCols + j * 128 + lane * 4;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = (4 * j + u) * 32;
-          const double old = rs[idx];
-          const double w = runp[idx] + (s0[4 * j + u] - old);       // the window sum after position q - 1 entered
-          rs[idx] = s0[4 * j + u];
-          runp[idx] = w;
-          s0[4 * j + u] = 0.0;
-          float out = 0.0f;
-          const int col = c0 + u;
-          if (emit && col < a.C) {
-            const double sxy = live ? w * inv_k : 0.0;
-            double rr = (n * sxy - sxsy) * inv_xy;
-            if (use_z) {
-              const double2 cz = __ldg(reinterpret_cast<const double2*>(cc + 8 + 2 * col));
-              rr = (rr - r_xz * cz.x) * row_den * cz.y;
-            }
-            out = (float)rr;
-            if (out != out) out = 0.0f;
-            else if (isinf(out)) out = out > 0 ? FLT_MAX : -FLT_MAX;
-          }
-          o[u] = out;
-        }
-        if (emit && c0 < a.ldr) *reinterpret_cast<float4*>(a.r + row * a.ldr + c0) = make_float4(o[0], o[1], o[2], o[3]);
+      const double inv_xy = s_rc[p - p0][0], sxsy = s_rc[p - p0][1];
+      double r0 = (n * (w0 * inv_k) - sxsy) * inv_xy, r1 = (n * (w1 * inv_k) - sxsy) * inv_xy;
+      if (use_z) {
+        const double r_xz = s_rc[p - p0][2], row_den = s_rc[p - p0][3];
+        r0 = (r0 - r_xz * cz0.x) * row_den * cz0.y;
+        r1 = (r1 - r_xz * cz1.x) * row_den * cz1.y;
       }
-    };
-    auto sum_batch = [&](int e, const float4 (&v)[kMBatch][kMV]) {
-      // the load pointer is less than 32 records ahead: the batch is in the current chunk or the previous one
-      const int i = e - e_begin;
-      const bool in_cur = (i >> 5) == ch_idx;
-#pragma unroll
-      for (int u = 0; u < kMBatch; ++u) {
-        const uint32_t xc = __shfl_sync(full, ch_cur.y, (i + u) & 31), xp = __shfl_sync(full, ch_prev.y, (i + u) & 31);
-        if (e + u < e_end) {
-          while (e + u >= next_bnd) finish_position();
-          const double xd = f2d(__uint_as_float(in_cur ? xc : xp));
-#pragma unroll
-          for (int j = 0; j < kMV; ++j) {
-            s0[4 * j + 0] = fma(xd, f2d(v[u][j].x), s0[4 * j + 0]);
-            s0[4 * j + 1] = fma(xd, f2d(v[u][j].y), s0[4 * j + 1]);
-            s0[4 * j + 2] = fma(xd, f2d(v[u][j].z), s0[4 * j + 2]);
-            s0[4 * j + 3] = fma(xd, f2d(v[u][j].w), s0[4 * j + 3]);
-          }
-        }
+      if (c0 < a.C) {
+        o0 = (float)r0;
+        if (o0 != o0) o0 = 0.0f;
+        else if (isinf(o0)) o0 = o0 > 0 ? FLT_MAX : -FLT_MAX;
       }
-    };
-    float4 va[kMBatch][kMV], vb[kMBatch][kMV];
-    load_batch(e_begin, va);
-#pragma unroll 1
-    for (int e = e_begin; e < e_end; e += 2 * kMBatch) {
-      load_batch(e + kMBatch, vb);
-      sum_batch(e, va);
-      if (e + kMBatch < e_end) {
-        load_batch(e + 2 * kMBatch, va);
-        sum_batch(e + kMBatch, vb);
+      if (c0 + 1 < a.C) {
+        o1 = (float)r1;
+        if (o1 != o1) o1 = 0.0f;
+        else if (isinf(o1)) o1 = o1 > 0 ? FLT_MAX : -FLT_MAX;
       }
+      if (store) *reinterpret_cast<float2*>(a.r + (row_t + p) * a.ldr + c0) = make_float2(o0, o1);
     }
-    while (q < p1 + a.margin) finish_position();
   }
 }
 
@@ -571,8 +479,9 @@ int mepp_profile_sparse(const void* entries_dev, const unsigned long long* entry
   return 0;
 }
 
-int64_t mepp_profile_matches_work_bytes(int64_t m_rows, int64_t hits_cap) {
-  return 2 * (((m_rows + 2) * 4 + 255) / 256 * 256) + (m_rows * 4 + 255) / 256 * 256 + hits_cap * 8;
+int64_t mepp_profile_matches_work_bytes(int64_t m_rows, int64_t hits_cap, int C) {
+  return ((m_rows + 2) * 4 + 255) / 256 * 256 + (m_rows * 4 + 255) / 256 * 256 + (hits_cap * 8 + 255) / 256 * 256 +
+         m_rows * mepp_y_rows_ld(C) * 8;
 }
 
 int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_count_dev, int64_t hits_cap,
@@ -593,28 +502,30 @@ int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_cou
   w += ((m_rows + 2) * 4 + 255) / 256 * 256;
   int32_t* cursor = reinterpret_cast<int32_t*>(w);
   w += (m_rows * 4 + 255) / 256 * 256;
-  int32_t* blk_start = reinterpret_cast<int32_t*>(w);
-  w += ((m_rows + 2) * 4 + 255) / 256 * 256;
   uint2* csr = reinterpret_cast<uint2*>(w);
-  match_offsets_kernel<<<1, kScanThreads, 0, st>>>(count_dev, m_rows, hit_count_dev, hits_cap, offsets, cursor, L,
-                                                   blk_start);
+  w += (hits_cap * 8 + 255) / 256 * 256;
+  double* S0 = reinterpret_cast<double*>(w);
+  match_offsets_kernel<<<1, kScanThreads, 0, st>>>(count_dev, m_rows, hit_count_dev, hits_cap, offsets, cursor);
   match_fill_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const HitRec4*>(hits_dev), hit_count_dev, L, m_rows, offsets,
                                              cursor, csr);
-  MatchArgs a;
-  a.csr = csr; a.offsets = offsets; a.blk_start = blk_start;
-  a.y_rows = y_rows_dev; a.ldY = mepp_y_rows_ld(C);
-  a.rowstats = rowstats_dev; a.colconst = colconst_dev; a.r = r_dev; a.ldr = ldr;
-  a.T = T; a.L = L; a.C = C; a.margin = margin; a.n_slabs = (int)(a.ldY / kMCols);
-  // per warp: window ring + running sum ((k + 1) rows x kMCols float64) and the gather ring; as many warps per CTA
-  // (<= 4) as fit ~106 KB, two CTAs per SM
-  const int k = 2 * margin + 1;
-  const size_t per_warp = (size_t)(k + 1) * kMCols * 8;
-  int warps = (int)(106 * 1024 / per_warp);
-  warps = warps > 4 ? 4 : warps < 1 ? 1 : warps;
-  a.warps = warps;
-  const size_t smem = (size_t)warps * per_warp;
-  MEPP_CUDA_CHECK(cudaFuncSetAttribute(profile_matches_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  profile_matches_kernel<<<148 * 2, 128, smem, st>>>(a);
+  GatherArgs g;
+  g.csr = csr; g.offsets = offsets; g.y_rows = y_rows_dev; g.ldY = mepp_y_rows_ld(C); g.S0 = S0;
+  g.m_rows = m_rows; g.n_slabs = (int)(g.ldY / kSlabCols);
+  match_gather_kernel<<<148 * 16, 256, 0, st>>>(g);
+  BlurArgs a;
+  a.S0 = S0; a.ldS0 = g.ldY; a.offsets = offsets; a.rowstats = rowstats_dev; a.colconst = colconst_dev;
+  a.r = r_dev; a.ldr = ldr; a.T = T; a.L = L; a.C = C; a.margin = margin;
+  // positions per CTA: long enough that the 2 * margin extra rows a block reads stay a small share, short enough for
+  // a few thousand CTAs
+  int pb = 8 * (2 * margin + 1);
+  pb = pb < 32 ? 32 : pb > kBlurMaxPb ? kBlurMaxPb : pb;
+  a.pb = pb; a.n_pb = (L + pb - 1) / pb;
+  a.n_slabs = (int)((ldr + kBlurCols - 1) / kBlurCols);
+  const size_t smem = (size_t)(2 * margin + 1) * kBlurThreads * sizeof(double2);
+  MEPP_CUDA_CHECK(cudaFuncSetAttribute(match_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n_ctas = (int64_t)T * a.n_pb * a.n_slabs;
+  MEPP_REQUIRE(n_ctas < ((int64_t)1 << 31), "profile_matches: too many blocks in one group");
+  match_blur_kernel<<<(unsigned)n_ctas, kBlurThreads, smem, st>>>(a);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -226,11 +226,11 @@ class Engine:
         # tensor-core first stage of the lean scan (mepp_scan_tc: tcgen05 int8 products over the one-hot stream)
         self.tc_scan = os.environ.get("MEPP_SCAN_TC", "1") != "0"
         self.bp_cost_ratio = float(os.environ.get("MEPP_BP_COST_RATIO", "1.0"))
-        # sparse profile from the match list (one row of Y per match; the blur commutes with the contraction) instead of
-        # the blurred entries (one per non-zero).  Built, exact to 1e-7, but slower on B200 (cfg 3: 24.3 vs 22.9 ms per
-        # step): both forms are bound by instruction issue, not bytes, and the per-position bookkeeping of the match
-        # form costs more than the conversions it saves.  Off by default.
-        self.sparse_matches = os.environ.get("MEPP_SPARSE_FORM", "entries") == "matches"
+        # sparse profile from the match list (one row of Y per match; the blur commutes with the contraction:
+        # mepp_profile_matches, per-position products S0 then their window sums) instead of the blurred entries (one
+        # gathered row per non-zero, 2 margin + 1 times as many: mepp_profile_sparse).  cfg 3: 9.0 -> 4.9 ms per step.
+        # MEPP_SPARSE_FORM=entries selects the entry form.
+        self.sparse_matches = os.environ.get("MEPP_SPARSE_FORM", "matches") == "matches"
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -970,8 +970,9 @@ class Engine:
                 _ptr(self.sym_T), _ptr(self.onehot), _ptr(self.zhat), N, L, T, int(margin), _ptr(lut_d), _ptr(bias_d),
                 _ptr(mlen_d), _ptr(nfilt_d), _ptr(units_d), units_h.ctypes.data if units_h is not None else None, n_units,
                 mlen_h.ctypes.data, _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap, _ptr(hit_count),
-                _ptr(entries), entry_cap, _ptr(entry_count), _ptr(row_nnz), _ptr(buckets), _ptr(bucket_count),
-                _ptr(tc_work), wbytes, _ptr(dbg), int(dbg.shape[1]) if dbg is not None else 0, st), "scan_tc")
+                None if use_matches else _ptr(entries), entry_cap, _ptr(entry_count), _ptr(row_nnz), _ptr(buckets),
+                _ptr(bucket_count), _ptr(tc_work), wbytes, _ptr(dbg), int(dbg.shape[1]) if dbg is not None else 0, st),
+                "scan_tc")
             self.launches += 4
             self.last_scan = 'tc'
         elif use_lean and path == 'sparse' and not bitpar_on and L <= 65535:
@@ -1020,7 +1021,7 @@ class Engine:
             r = self._buf('r', (m_rows, self.ldS), torch.float32)
             if path == 'sparse' and use_matches:
                 # one gathered row of Y per MATCH (the blur commutes with the contraction), not per blurred non-zero
-                work = self._buf('match_work', int(_lib.lib.mepp_profile_matches_work_bytes(m_rows, cap)), torch.uint8)
+                work = self._buf('match_work', int(_lib.lib.mepp_profile_matches_work_bytes(m_rows, cap, C_)), torch.uint8)
                 _lib.check(_lib.lib.mepp_profile_matches(_ptr(hits_d), _ptr(hit_count), cap, _ptr(count), T, L, int(margin),
                                                          _ptr(self._yrows()), _ptr(rowstats),
                                                          _ptr(self._colconst(sparse=True)),

@@ -453,10 +453,17 @@ def test_sparse_and_tensor_profile_paths_agree(monkeypatch):
         assert _r_close(sp.r[t], orc["r"], rel=2e-6, floor_frac=2e-6).all(), t    # float64 sums: tighter than the GEMM
     for col in ('positional_r', 'permutation_positional_r_lower', 'integral_r'):
         assert np.allclose(np.asarray(sp.positions[col]), np.asarray(tc.positions[col]), rtol=1e-4, atol=1e-7), col
-    # overflow -> fallback
+    # a match list that overflows (match-driven form, the default) -> the group is redone from the blurred entries
+    eng.profile_path = 'sparse'
+    assert eng.sparse_matches
+    eng.last_paths, eng.fallbacks = [], []
+    fm = eng.profile(tasks, margin=2, return_r=True, hits_cap=64)
+    assert eng.last_paths == ['sparse', 'sparse'] and eng.fallbacks == ['entries']
+    assert _r_close(fm.r, sp.r, rel=2e-6, floor_frac=2e-6).all()
+    # an entry list that overflows (entry form) -> the tensor-core path
     monkeypatch.setattr(engine_mod, 'SPARSE_ENTRY_DENSITY', 1e-9)
     monkeypatch.setattr(engine_mod, 'MIN_ENTRY_CAP', 16)
-    eng.profile_path = 'sparse'
+    eng.sparse_matches = False
     eng.last_paths = []
     fb = eng.profile(tasks, margin=2, return_r=True)
     assert eng.last_paths == ['sparse', 'tensor']

@@ -1,7 +1,9 @@
 #!/bin/bash
-W=${1:-cfg3}
-for M in 0 4 6 12 14 15; do
-  MEPP_TC_MODE=$M timeout 200 python bench.py --workload $W --steps 3 --warmup 3 --no-cpu-baseline --no-clocks > gpurun_out/mode$M.json 2>gpurun_out/mode$M.err
+# timing experiments of the tensor-core scan (MEPP_TC_MODE bits: 1 no TMEM reads / epilogue work, 2 no MMAs,
+# 4 TMEM reads but no sign tests, 8 no stream copies): tools/run_tc_modes.sh [workload] [modes...]
+W=${1:-cfg3}; shift
+for M in ${@:-0 1 2 4 5}; do
+  MEPP_TC_MODE=$M timeout 200 python bench.py --workload $W --steps 3 --warmup 3 --no-cpu-baseline --no-clocks --no-accuracy --no-fullrun > gpurun_out/mode$M.json 2>gpurun_out/mode$M.err
   python - gpurun_out/mode$M.json $M <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
