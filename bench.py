@@ -47,8 +47,9 @@ METRIC = "Gbp*motifs/s scanned+profiled"
 UNIT = "Gbp*motifs/s"
 
 
-SCAN_DRAM_BYTES_PER_LAUNCH = 16.0e6   # dram__bytes_read + write of one scan launch (82 tasks of cfg 2), ncu --set full:
-                                      # profiles/r01_final_kernels_ncu_summary.txt
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu --set full
+# capture of the same bench command (profiles/r02_kernels_ncu_summary.txt); null for workloads without a capture
+NCU_DRAM_BYTES_PER_LAUNCH = {("tc_scan_kernel", "cfg3"): None, ("scan_kernel", "cfg2"): 16.0e6}
 
 
 def clocks_mhz_hint(peaks):
@@ -309,6 +310,9 @@ def main():
                          "work of a strong-scaling run); the printed value is NOT a bench value")
     ap.add_argument("--no-accuracy", action="store_true", help="skip the full-size oracle check of a few tasks")
     ap.add_argument("--accuracy-tasks", type=int, default=4)
+    ap.add_argument("--no-tensor-leg", action="store_true",
+                    help="skip the extra tensor-path (tcgen05 profile GEMM) measurement on a slice of the task list")
+    ap.add_argument("--tensor-leg-tasks", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not run the nvidia-smi clock sampler")
     args = ap.parse_args()
@@ -453,15 +457,49 @@ def main():
     eng.profile(my_tasks, margin=margin, tables=dev_tables)
     sync_all()
     eng.timing = {}
+    _lib.check(_lib.lib.mepp_scan_tc_timing(1, None, None, None, None), "scan_tc_timing")   # events around tc_scan_kernel
     for _ in range(kernel_steps):
         eng.profile(my_tasks, margin=margin, tables=dev_tables)
     sync_all()
     stage_ms = eng.collect_timing()
+    tc_ms, tc_macs, tc_bytes, tc_n = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int(0)
+    _lib.check(_lib.lib.mepp_scan_tc_timing(0, C.byref(tc_ms), C.byref(tc_macs), C.byref(tc_bytes), C.byref(tc_n)),
+               "scan_tc_timing")
     eng.timing = None
     eng.overlap = overlap_was
     steps2 = (C.c_ulonglong * 2)()
     _lib.check(_lib.lib.mepp_gemm_counters(steps2, 0), "gemm_counters")
     issued_frac = (steps2[0] / steps2[1]) if steps2[1] else 1.0
+    # the tcgen05 profile GEMM (the path of a dense X: Engine.choose_path) on a slice of the same task list, so that its
+    # tensor-pipe figures are in every bench line although the default step takes the sparse path at p = 1e-4
+    tensor_leg = None
+    if not args.no_tensor_leg and all(p_ == "sparse" for p_ in eng.last_stats["paths"]):
+        sub = my_tasks[:min(len(my_tasks), args.tensor_leg_tasks)]
+        path_was, eng.profile_path, eng.overlap = eng.profile_path, "tensor", False
+        try:
+            eng.profile(sub, margin=margin)                      # warm-up: operand buffers
+            sync_all()
+            _lib.check(_lib.lib.mepp_gemm_counters(None, 1), "gemm_counters")
+            eng.timing = {}
+            for _ in range(2):
+                eng.profile(sub, margin=margin)
+            sync_all()
+            tl_ms = eng.collect_timing()
+            eng.timing = None
+            _lib.check(_lib.lib.mepp_gemm_counters(steps2, 0), "gemm_counters")
+            tl_frac = (steps2[0] / steps2[1]) if steps2[1] else 1.0
+            t_gemm = tl_ms.get("gemm", 0.0) * 1e-3 / 2
+            if t_gemm > 0:
+                alg = 2.0 * L * N * (1 + P) * len(sub)
+                ex = 3.0 * alg * tl_frac * (eng.ldS / float(1 + P))
+                tensor_leg = dict(tasks=len(sub), bound="tensor", achieved=ex / t_gemm / 1e12, unit="TFLOP/s",
+                                  peak=None, frac=None, algorithmic_tflops=alg / t_gemm / 1e12, issued_step_fraction=tl_frac,
+                                  split_products=3, ms=1e3 * t_gemm, paths=sorted(set(eng.last_stats["paths"])),
+                                  note="profile_gemm_kernel (tcgen05 kind::f16, fp16 hi/lo split, 3 products, fp32 TMEM "
+                                       "accumulators, correlation epilogue fused) on the first tasks of the list; executed = "
+                                       "issued MMAs only (all-zero K = 16 steps of X are skipped)")
+        finally:
+            eng.profile_path, eng.overlap, eng.timing = path_was, overlap_was, None
     dt_value = parallel.barrier_and_max(1e-3 * ev_a.elapsed_time(ev_b), device=dev if world > 1 else None)
 
     # (2) end to end from pinned host buffers (clock sampler halted: its NVML polling slows host-side CUDA calls)
@@ -524,12 +562,19 @@ def main():
         # reads 3 bits per base per scan unit (a '+/-' task and its '+' twin share one pass), writes 16 B per match and
         # 16 B per non-zero of X (sparse path) or 32 B per non-zero 8-sequence piece (tiled path, <= one per non-zero)
         lean = bool(getattr(eng, "lean", False)) and sparse       # matches also go to buckets (8 B each), read back once
+        tc = getattr(eng, "last_scan", None) == "tc"
         scan_bytes = (0.375 * N * L * st["units"] + (32.0 if lean else 16.0) * st["hits"]
                       + (16.0 if sparse else 32.0) * max(st["entries"], st["hits"]))
+        if tc:        # the first stage reads the flat one-hot stream (4 B per base) once per launch instead
+            scan_bytes += tc_bytes.value / steps - 0.375 * N * L * st["units"]
         a = scan_bytes / per("scan") / 1e9
         kernels["scan"] = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"],
-                               ms_per_step=1e3 * per("scan"), launches_per_step=groups * (2 if lean else 1),
-                               form="lean: matches only + entries built from per-(task, k-block) buckets" if lean
+                               ms_per_step=1e3 * per("scan"),
+                               launches_per_step=(tc_n.value // steps) * 3 + groups if tc else groups * (2 if lean else 1),
+                               form="tc: tcgen05 int8 first stage over the one-hot stream (tc_scan_kernel), exact float32 "
+                                    "evaluation of its candidates (tc_exact_kernel), row sums from per-(task, k-block) "
+                                    "buckets of matches (bucket_entries_kernel)" if tc else
+                                    "lean: matches only + entries built from per-(task, k-block) buckets" if lean
                                     else "full: blur and entries from staging rows inside the scan",
                                gwindows_per_s=N * L * n_local / per("scan") / 1e9,
                                # a scan that writes X once moves 4 B per bp*task; this one emits X as a list of
@@ -539,20 +584,53 @@ def main():
                                tap_adds_per_s=float(N) * L * sum(pwm.shape[1] * (1 if o in ('+', '-') else 2)
                                                                  for pwm, o in my_tasks) / per("scan"),
                                int_add_peak_per_s=148 * 128 * clocks_mhz_hint(peaks) * 1e6,
-                               limit="integer issue / shared-memory lookups of the pre-filter (ncu: issue slots ~47 % busy, "
+                               limit=("tensor pipe hand-overs of the first stage (tc_scan_kernel, see roofline) + atomics of "
+                                      "the match publication; X is written as a list of its matches, so almost no bytes move")
+                                     if tc else
+                                     "integer issue / shared-memory lookups of the pre-filter (ncu: issue slots ~47 % busy, "
                                      "DRAM < 1 %): X is written as a list of its non-zeros, so almost no bytes move")
+        if tc and tc_ms.value > 0:
+            t_tc = tc_ms.value * 1e-3 / steps                          # seconds of tc_scan_kernel per step (CUDA events)
+            tops = 2.0 * tc_macs.value / steps / t_tc / 1e12
+            i8_peak = 2.0 * peaks["tf_sustained"]
+            alg = 2.0 * float(N) * L * sum(pwm.shape[1] * (1 if o in ('+', '-') else 2) for pwm, o in my_tasks)
+            kernels["tc_scan_kernel"] = dict(
+                bound="tensor", achieved=tops, peak=i8_peak, unit="TOP/s", frac=tops / i8_peak,
+                ms_per_step=1e3 * t_tc, launches_per_step=tc_n.value // steps, ms_per_launch=tc_ms.value / max(1, tc_n.value),
+                peak_note="dense int8 = 2 x the measured sustained bf16 rate of MEASURED_PEAKS.json (kind::i8 issues K = 32 "
+                          "per instruction against 16 for bf16); burst: %.0f" % (2.0 * peaks["tf_burst"]),
+                issued_note="issued multiply-adds: 128 windows x N-tile columns x 32 channels per K-step, the padding of "
+                            "the K-steps (taps + 3 phases rounded up to 8 bases) and of the N-tiles included",
+                algorithmic_tops=alg / t_tc / 1e12,
+                algorithmic_note="SURVEY 8(d) compute-bound form: N * L * m * strands multiply-adds per task",
+                stream_gbs=tc_bytes.value / steps / t_tc / 1e9,
+                limit="accumulator hand-over between the MMA issuers and the epilogue warps (2 stages of 256 TMEM "
+                      "columns): DESIGN.md section 4")
     if stage_ms.get("gemm") and sparse:
         # HBM: Y rows once (L2-resident afterwards), CSR records, r written once; L2 -> SM: one Y row per non-zero
         ldY = -(-C_ // 512) * 512
-        hbm = 4.0 * eng.n_pad * ldY + 24.0 * st["entries"] + 4.0 * n_local * L * eng.ldS
-        l2 = 4.0 * ldY * st["entries"]
+        by_match = bool(getattr(eng, "sparse_matches", False))
+        y_bytes = 4.0 * eng.n_pad * ldY
+        gather = 4.0 * ldY * st["entries"]               # one float32 row of Y per record (match, or non-zero of X)
+        if by_match:
+            # Y rows gathered once per match (from HBM when Y exceeds the L2: cfg 3), S0 float64 written and read once,
+            # the match CSR, r written once
+            hbm = (gather if y_bytes > 100e6 else y_bytes) + 2 * 8.0 * n_local * L * ldY + 24.0 * st["entries"] \
+                  + 4.0 * n_local * L * eng.ldS
+        else:
+            hbm = y_bytes + 24.0 * st["entries"] + 4.0 * n_local * L * eng.ldS
         a = hbm / per("gemm") / 1e9
         kernels["profile_sparse"] = dict(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s",
                                          frac=a / peaks["hbm_gbs"], ms_per_step=1e3 * per("gemm"),
-                                         launches_per_step=3 * groups, l2_gather_gbs=l2 / per("gemm") / 1e9,
-                                         l2_cap_gbs=l2_cap_gbs, l2_frac=l2 / per("gemm") / 1e9 / l2_cap_gbs,
-                                         nonzeros_per_step=st["entries"],
-                                         limit="L2 -> SM gather of one float32 Y row (4 * ldY bytes) per non-zero of X")
+                                         launches_per_step=(4 if by_match else 3) * groups,
+                                         form="matches: S0 = one gathered row of Y per match (float64), window sums of S0 + "
+                                              "correlation epilogue" if by_match else
+                                              "entries: one gathered row of Y per non-zero of the blurred matrix",
+                                         gather_gbs=gather / per("gemm") / 1e9,
+                                         l2_cap_gbs=l2_cap_gbs, gather_frac_of_l2_cap=gather / per("gemm") / 1e9 / l2_cap_gbs,
+                                         records_per_step=st["entries"],
+                                         limit="gather of one float32 Y row (4 * ldY bytes) per record: HBM when Y (%.0f MB) "
+                                               "exceeds the L2, else L2 -> SM" % (y_bytes / 1e6))
     elif stage_ms.get("gemm"):
         # executed = issued MMAs only (all-zero K=16 steps of X are skipped); padded tile columns are counted as issued
         gemm_alg = 2.0 * L * N * C_ * n_local
@@ -573,14 +651,30 @@ def main():
     for k in ("correlation", "finalize"):
         if stage_ms.get(k):
             kernels[k] = dict(ms_per_step=1e3 * per(k))
-    dominant = "scan" if "scan" in kernels else next(iter(kernels))   # the longest single kernel of the step
-    dk = kernels.get(dominant, {})
-    roofline = dict(kernel=dominant + "_kernel", bound=dk.get("bound"), achieved=dk.get("achieved"), peak=dk.get("peak"),
-                    unit=dk.get("unit"), frac=dk.get("frac"), traffic=SCAN_DRAM_BYTES_PER_LAUNCH,
-                    peak_source=peaks["source"],
-                    note="achieved = algorithmic bytes (3 bits per base per scan unit read, 16 B per match and per non-zero of "
-                         "X written) / CUDA-event time of the launches; the kernel is bound by integer issue, not by HBM "
-                         "(DESIGN.md section 4); traffic = DRAM bytes of one launch from the committed ncu capture (full-form kernel)")
+    if tensor_leg is not None:
+        tensor_leg["peak"] = peaks["tf_sustained"]
+        tensor_leg["frac"] = tensor_leg["achieved"] / peaks["tf_sustained"]
+        tensor_leg["frac_of_burst"] = tensor_leg["achieved"] / peaks["tf_burst"]
+        kernels["profile_gemm"] = tensor_leg
+    # the dominant kernel of the step (the longest single kernel of the ncu launch list, profiles/)
+    if "tc_scan_kernel" in kernels:
+        dk = kernels["tc_scan_kernel"]
+        roofline = dict(kernel="tc_scan_kernel", bound="tensor", achieved=dk["achieved"], peak=dk["peak"], unit=dk["unit"],
+                        frac=dk["frac"], traffic=NCU_DRAM_BYTES_PER_LAUNCH.get(("tc_scan_kernel", args.workload)),
+                        peak_source=peaks["source"] + "; " + dk["peak_note"], ms_per_launch=dk["ms_per_launch"],
+                        algorithmic=dk["algorithmic_tops"], share_of_step=dk["ms_per_step"] / (1e3 * dt_value / args.steps),
+                        note="achieved = int8 multiply-adds issued by the launches x 2 / their CUDA-event time (events on the "
+                             "launching stream around every tc_scan_kernel launch of a serial pass, mepp_scan_tc_timing); "
+                             "algorithmic = 2 N L m strands per task / the same time; traffic = dram__bytes_read + write of "
+                             "one launch, ncu --set full of this command (profiles/r02_kernels_ncu_summary.txt)")
+    else:
+        dominant = "scan" if "scan" in kernels else next(iter(kernels))
+        dk = kernels.get(dominant, {})
+        roofline = dict(kernel=dominant + "_kernel", bound=dk.get("bound"), achieved=dk.get("achieved"), peak=dk.get("peak"),
+                        unit=dk.get("unit"), frac=dk.get("frac"),
+                        traffic=NCU_DRAM_BYTES_PER_LAUNCH.get((dominant + "_kernel", args.workload)),
+                        peak_source=peaks["source"],
+                        note="achieved = algorithmic bytes / CUDA-event time of the launches (DESIGN.md section 4)")
 
     accuracy = None
     if not args.no_accuracy:

@@ -230,6 +230,12 @@ int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_dev, const fl
                  void* buckets_dev, int32_t* bucket_count_dev, void* work_dev, int64_t work_bytes,
                  int32_t* dbg_acc_dev, int dbg_ld, void* stream);
 
+/* Measurement hook (bench.py's roofline block): while enabled, every tc_scan_kernel launch of mepp_scan_tc is bracketed
+ * by CUDA events on its stream.  A call returns what was gathered since the previous call -- summed kernel time (it
+ * waits for the recorded events), int8 multiply-adds issued (128 x columns x 32 per K-step and 512-base tile, padding
+ * included), bytes of the one-hot stream read, launches -- clears it and sets the new state.  Outputs may be NULL. */
+int mepp_scan_tc_timing(int enable, double* ms_out, double* macs_out, double* stream_bytes_out, int* launches_out);
+
 /* Restore the all-zero state of an A operand that mepp_scan(..., N, L, T, margin, ...) wrote, from the
  * match list of that call (every match dirties rows pos-margin..pos+margin of one 8-column group); a NULL
  * or overflowed list clears the whole operand instead.  Call after the operand's last consumer. */

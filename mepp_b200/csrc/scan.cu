@@ -34,6 +34,8 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "tcscan.cuh"
+#include <utility>
+#include <vector>
 
 namespace mepp {
 
@@ -1390,6 +1392,39 @@ __global__ void __launch_bounds__(128) tc_exact_kernel(const ScanArgs a, const u
 }
 }  // namespace mepp
 
+// Optional per-launch timing of tc_scan_kernel (bench.py's roofline block): CUDA events on the launching stream around
+// every launch while enabled, and the int8 multiply-adds the launches issued.
+namespace mepp {
+struct TcTiming {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  double macs = 0.0;          // issued int8 multiply-adds (128 x bn x 32 per K-step and M-tile, padding included)
+  double stream_bytes = 0.0;  // bytes of the one-hot stream the launches read
+};
+static TcTiming g_tc_timing;
+}  // namespace mepp
+
+extern "C" int mepp_scan_tc_timing(int enable, double* ms_out, double* macs_out, double* stream_bytes_out,
+                                   int* launches_out) {
+  using namespace mepp;
+  TcTiming& t = g_tc_timing;
+  double ms = 0.0;
+  for (auto& e : t.ev) {
+    MEPP_CUDA_CHECK(cudaEventSynchronize(e.second));
+    float x = 0.0f;
+    MEPP_CUDA_CHECK(cudaEventElapsedTime(&x, e.first, e.second));
+    ms += x;
+    cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+  }
+  if (ms_out) *ms_out = ms;
+  if (macs_out) *macs_out = t.macs;
+  if (stream_bytes_out) *stream_bytes_out = t.stream_bytes;
+  if (launches_out) *launches_out = (int)t.ev.size();
+  t.ev.clear(); t.macs = 0.0; t.stream_bytes = 0.0;
+  t.on = enable != 0;
+  return 0;
+}
+
 extern "C" int64_t mepp_scan_tc_work_bytes(int64_t N, int L, int n_units) {
   using namespace mepp;
   // weight operands of every launch (<= 8 columns x 160 channels per unit, plus tile padding), candidate lists, counters
@@ -1511,7 +1546,17 @@ extern "C" int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_de
     b_used += ((int64_t)ln.b_bytes + 1023) / 1024 * 1024;
     if (tc_build_weights(ln, lut_dev, bias_dev, mlen_dev, nfilt_dev, units_dev, u0, U, B_launch, st)) return 1;
     g.B = B_launch;
-    if (tc_scan_launch(ln, g, st)) return 1;
+    if (g_tc_timing.on) {
+      cudaEvent_t e0, e1;
+      MEPP_CUDA_CHECK(cudaEventCreate(&e0)); MEPP_CUDA_CHECK(cudaEventCreate(&e1));
+      MEPP_CUDA_CHECK(cudaEventRecord(e0, st));
+      if (tc_scan_launch(ln, g, st)) return 1;
+      MEPP_CUDA_CHECK(cudaEventRecord(e1, st));
+      g_tc_timing.ev.emplace_back(e0, e1);
+      for (int k = 0; k < ln.n_tiles; ++k)
+        g_tc_timing.macs += (double)g.n_mtiles * kTcRowsPerTile * ln.tiles[k].bn * 32.0 * ln.tiles[k].ksteps;
+      g_tc_timing.stream_bytes += (double)g.n_mtiles * 2048.0;
+    } else if (tc_scan_launch(ln, g, st)) return 1;
     int n_lists = grid;
     if ((int64_t)n_lists > g.n_mtiles) n_lists = (int)g.n_mtiles;
     tc_exact_kernel<<<(unsigned)(n_lists * kTcEpiWarps), 128, 0, st>>>(a, g.cand, g.cand_count, g.list_cap, u0, u - u0);

@@ -2,7 +2,7 @@
 # A/B of an environment switch on the cfg3 / cfg2 step: tools/run_s2_ab.sh VAR valueA valueB [workload]
 VAR=$1; A=$2; B=$3; W=${4:-cfg3}
 for V in $A $B $A $B; do
-env $VAR=$V timeout 600 python bench.py --workload $W --steps 30 --warmup 3 --no-cpu-baseline --no-accuracy --no-clocks --no-fullrun > gpurun_out/s2_ab_$V.json 2>gpurun_out/s2_ab_$V.err
+env $VAR=$V timeout 600 python bench.py --workload $W --steps 30 --warmup 3 --no-cpu-baseline --no-accuracy --no-clocks --no-fullrun --no-tensor-leg > gpurun_out/s2_ab_$V.json 2>gpurun_out/s2_ab_$V.err
 python - gpurun_out/s2_ab_$V.json $VAR=$V <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])

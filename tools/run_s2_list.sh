@@ -1,7 +1,7 @@
 #!/bin/bash
 # per-kernel device time of a step (ncu launch list): tools/run_s2_list.sh <tag> [workload]
 TAG=${1:-r02l}; W=${2:-cfg3}
-ARGS="--workload $W --steps 2 --warmup 1 --no-cpu-baseline --no-clocks --no-accuracy --no-fullrun"
+ARGS="--workload $W --steps 2 --warmup 1 --no-cpu-baseline --no-clocks --no-accuracy --no-fullrun --no-tensor-leg"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${TAG}_launches.csv \
   python bench.py $ARGS > gpurun_out/${TAG}_ncu_list.log 2>&1
 python - gpurun_out/${TAG}_launches.csv <<'PY'

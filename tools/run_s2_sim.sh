@@ -1,7 +1,7 @@
 #!/bin/bash
 # per-rank load of an N-GPU strong-scaling run on one GPU, with the host phases of a profile() call
 for SW in "$@"; do
-timeout 600 python bench.py --steps 20 --warmup 3 --simulate-world $SW --no-cpu-baseline --no-accuracy --no-clocks > gpurun_out/s2_sim$SW.json 2>gpurun_out/s2_sim$SW.err
+timeout 600 python bench.py --steps 20 --warmup 3 --simulate-world $SW --no-cpu-baseline --no-accuracy --no-clocks --no-tensor-leg > gpurun_out/s2_sim$SW.json 2>gpurun_out/s2_sim$SW.err
 python - gpurun_out/s2_sim$SW.json $SW <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])

@@ -3,7 +3,7 @@
 # 4 TMEM reads but no sign tests, 8 no stream copies): tools/run_tc_modes.sh [workload] [modes...]
 W=${1:-cfg3}; shift
 for M in ${@:-0 1 2 4 5}; do
-  MEPP_TC_MODE=$M timeout 200 python bench.py --workload $W --steps 3 --warmup 3 --no-cpu-baseline --no-clocks --no-accuracy --no-fullrun > gpurun_out/mode$M.json 2>gpurun_out/mode$M.err
+  MEPP_TC_MODE=$M timeout 200 python bench.py --workload $W --steps 3 --warmup 3 --no-cpu-baseline --no-clocks --no-accuracy --no-fullrun --no-tensor-leg > gpurun_out/mode$M.json 2>gpurun_out/mode$M.err
   python - gpurun_out/mode$M.json $M <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
