@@ -1508,7 +1508,7 @@ extern "C" int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_de
   // (MEPP_TC_TILES_PER_LAUNCH = 1: one N-tile per launch, measured slower -- the stream is scanned once per launch.)
   static const int tiles_per_launch = [] { const char* e = getenv("MEPP_TC_TILES_PER_LAUNCH"); int v = e ? atoi(e) : kTcMaxTiles;
                                            return v < 1 ? 1 : v > kTcMaxTiles ? kTcMaxTiles : v; }();
-  const int n_ntiles = (U + kTcUnitsPerTile - 1) / kTcUnitsPerTile;
+  const int n_ntiles = (U + tc_units_per_tile() - 1) / tc_units_per_tile();
   const int units_per_tile = ((U + n_ntiles - 1) / n_ntiles + 3) / 4 * 4;
   int u0 = 0;
   int64_t b_used = 0;

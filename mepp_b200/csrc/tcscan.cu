@@ -305,6 +305,223 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
   }
 }
 
+// ---- four-stage form ------------------------------------------------------------------------------------------------
+// The two-stage kernel above is bound by its hand-overs, not by the tensor pipe (17 % active, ncu): an accumulator stage
+// goes issuer -> commit -> epilogue wake-up -> TMEM reads -> arrive -> issuer wake-up (~700-900 cycles, cycle stamps of
+// tools/gpu_tc_clk.py) for ~350 cycles of products, and with two stages only one other N-tile can cover that.  Here
+// an N-tile is at most 128 columns (16 scan units) and TMEM holds FOUR accumulator stages of 128 columns; N-tile number
+// s (running over the whole launch) uses stage s % 4, is issued by issuer s % 2 and drained by epilogue group s % 4 --
+// every group owns one stage, so no barrier is shared between groups and three other N-tiles are in flight behind
+// every hand-over.  (At N = 128 an MMA reads as many operand bytes per cycle as the shared memory delivers, 8 KB in
+// 64 cycles: the narrower tile costs no tensor time.)
+constexpr int kTc4Stages = 4;
+constexpr int kTc4Cols = 128;
+
+template <bool PACK, int ISS>
+__global__ void __launch_bounds__(32 * (1 + ISS + kTcEpiWarps), 1) tc_scan4_kernel(const __grid_constant__ TcLaunch ln,
+                                                                 const __grid_constant__ TcScanArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b_pad = (ln.b_bytes + 1023u) & ~1023u;
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + b_pad;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(sA + kTcStages * kTcStageBytes);   // [kTcStages]
+  uint64_t* aempty = afull + kTcStages;                                            // [kTcStages]
+  uint64_t* tfull = aempty + kTcStages;                                            // [kTc4Stages]
+  uint64_t* tempty = tfull + kTc4Stages;                                           // [kTc4Stages]
+  uint64_t* bfull = tempty + kTc4Stages;                                           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  __shared__ uint4 s_nt[kTcMaxTiles];
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(smem_u32(&afull[s]), 1); mbar_init(smem_u32(&aempty[s]), ISS); }
+    for (int s = 0; s < kTc4Stages; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), 4); }
+    mbar_init(smem_u32(bfull), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(kTc4Stages * kTc4Cols)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 1 + ISS && lane < ln.n_tiles) {
+    const TcTile tl = ln.tiles[lane];
+    const uint32_t bn = tl.bn;
+    const uint32_t idesc = (2u << 4) | (1u << 10) | ((bn >> 3) << 17) | ((uint32_t)(kTcRowsPerTile >> 4) << 24);
+    s_nt[lane] = make_uint4((((smem_u32(sB) + tl.b_off) & 0x3FFFFu) >> 4) | (bn << 16), idesc, tl.ksteps, 2u * bn);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t a_bytes = 2048u + 32u * (uint32_t)ln.ks_max;
+  const int n_tiles = ln.n_tiles;
+  const uint32_t park_ns = (uint32_t)g.mode >> 8;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      const uint32_t bb = smem_u32(bfull);
+      mbar_expect_tx(bb, ln.b_bytes);
+      for (uint32_t off = 0; off < ln.b_bytes; off += 32768u) {
+        const uint32_t n = ln.b_bytes - off < 32768u ? ln.b_bytes - off : 32768u;
+        bulk_g2s(smem_u32(sB + off), g.B + off, n, bb);
+      }
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < g.n_mtiles; tile += gridDim.x) {
+        mbar_wait_parked(smem_u32(&aempty[stage]), phase ^ 1u, park_ns);
+        const uint32_t fb = smem_u32(&afull[stage]);
+        mbar_expect_tx(fb, a_bytes);
+        bulk_g2s(smem_u32(sA + stage * kTcStageBytes), g.onehot + tile * 2048, a_bytes, fb);
+        if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp <= ISS) {
+    // ------------------------------------------------------------ MMA issuers (warps 1 .. ISS): N-tiles s % ISS == me
+    const uint32_t me = (uint32_t)(warp - 1);
+    const uint32_t kDescHi = 8u | (1u << 14);
+    mbar_wait_parked(smem_u32(bfull), 0u, park_ns);
+    tc_fence_after();
+    const bool issuer = lane == 0;
+    const uint32_t a_lo_base = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+    uint32_t stage = 0, phase = 0, seq = 0, uses = 0;      // uses: N-tiles this issuer has issued (4 / ISS per stage round)
+    for (int64_t tile = blockIdx.x; tile < g.n_mtiles; tile += gridDim.x) {
+      mbar_wait_parked(smem_u32(&afull[stage]), phase, park_ns);
+      tc_fence_after();
+      const uint32_t a_lo = a_lo_base + stage * (uint32_t)(kTcStageBytes / 16);
+      for (int nt = 0; nt < n_tiles; ++nt, ++seq) {
+        if ((seq & (uint32_t)(ISS - 1)) != me) continue;
+        const uint32_t st = seq & 3u;                        // ISS = 2: me or me + 2, alternating; ISS = 4: me
+        const uint4 c = s_nt[nt];
+        mbar_wait(smem_u32(&tempty[st]), ((uses / (4 / ISS)) & 1u) ^ 1u);
+        ++uses;
+        tc_fence_after();
+        if (g.dbg_clk && blockIdx.x == 0 && issuer && seq < 256) g.dbg_clk[seq] = clock64();
+        if (issuer) {
+          const uint32_t d_tmem = tmem_base + st * kTc4Cols;
+#pragma unroll
+          for (uint32_t ks = 0; ks < 5; ++ks)
+            if (ks < c.z)
+              tc_mma_i8(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + 2u * ks), ((uint64_t)kDescHi << 32) | (c.x + ks * c.w),
+                        c.y, ks > 0 ? 1u : 0u);
+          tc_commit(smem_u32(&tfull[st]));
+          if (g.dbg_clk && blockIdx.x == 0 && seq < 256) g.dbg_clk[256 + seq] = clock64();
+        }
+        __syncwarp();
+      }
+      if (issuer) tc_commit(smem_u32(&aempty[stage]));     // the stream tile is free once both issuers' MMAs retired
+      __syncwarp();
+      if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 3..18): group = stage
+    const unsigned full = 0xffffffffu;
+    const int ew = warp - (1 + ISS), q = warp & 3, gidx = ew >> 2;
+    uint32_t my_count = 0, seq = 0, seen = 0;
+    const int64_t list = (int64_t)blockIdx.x * kTcEpiWarps + ew;
+    uint2* const my_list = g.cand + list * (int64_t)g.list_cap;
+    const uint32_t tfull_me = smem_u32(&tfull[gidx]), tempty_me = smem_u32(&tempty[gidx]);
+    const uint32_t t_me = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)gidx * kTc4Cols;
+    for (int64_t tile = blockIdx.x; tile < g.n_mtiles; tile += gridDim.x) {
+      const uint32_t row = (uint32_t)(tile * kTcRowsPerTile) + (uint32_t)(q * 32 + lane);
+      int dbg_col = 0;
+      for (int nt = 0; nt < n_tiles; ++nt, ++seq) {
+        const int bn = (int)(s_nt[nt].w >> 1);
+        if ((int)(seq & 3u) != gidx) { dbg_col += bn; continue; }
+        const int nc = bn >> 5;                                   // 32-column chunks of this N-tile (<= 4)
+        mbar_wait_parked(tfull_me, seen & 1u, park_ns);
+        ++seen;
+        tc_fence_after();
+        const bool stamp = g.dbg_clk && blockIdx.x == 0 && lane == 0 && q == 0 && seq < 256;
+        if (stamp) g.dbg_clk[512 + seq] = clock64();
+        uint32_t v[4][PACK ? 16 : 32];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < nc && !(g.mode & 1)) {
+            if constexpr (PACK) tmem_ld16p_nowait(t_me + (uint32_t)(k * 32), v[k]);
+            else tmem_ld32_nowait(t_me + (uint32_t)(k * 32), v[k]);
+          }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_me);
+        if (stamp) g.dbg_clk[768 + seq] = clock64();
+        if (!(g.mode & 5)) {
+          if (g.dbg_acc != nullptr && tile == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k >= nc) break;
+              int32_t* d = g.dbg_acc + (int64_t)(q * 32 + lane) * g.dbg_ld + dbg_col + k * 32;
+              if constexpr (PACK) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { d[2 * j] = (int32_t)(int16_t)(v[k][j] & 0xffffu); d[2 * j + 1] = (int32_t)(int16_t)(v[k][j] >> 16); }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) d[j] = (int32_t)v[k][j];
+              }
+            }
+          }
+          constexpr int NV = PACK ? 16 : 32;
+          uint32_t hasm = 0u;                      // bit k: some accumulator of this row in chunk k is non-negative
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k >= nc) break;
+            uint32_t t = v[k][0];
+#pragma unroll
+            for (int j = 1; j < NV; ++j) t &= v[k][j];
+            const bool has = PACK ? (t & 0x80008000u) != 0x80008000u : (int32_t)t >= 0;
+            hasm |= has ? 1u << k : 0u;
+          }
+          if (__any_sync(full, hasm != 0u)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k >= nc) break;
+              unsigned bal = __ballot_sync(full, (hasm >> k) & 1u);      // lanes (rows) with a candidate in chunk k
+              if (bal == 0u) continue;
+              uint32_t cm = 0u;                    // bit p: (unit p / 4 of the chunk, phase p % 4) passes on a strand
+              if ((hasm >> k) & 1u) {
+#pragma unroll
+                for (int p = 0; p < 16; ++p) {
+                  bool pass;
+                  if constexpr (PACK) pass = (v[k][p] & 0x80008000u) != 0x80008000u;
+                  else pass = (int32_t)(v[k][2 * p] & v[k][2 * p + 1]) >= 0;
+                  if (pass) cm |= 1u << p;
+                }
+              }
+              const uint32_t ubase = ((uint32_t)ln.tiles[nt].unit0 + (uint32_t)k * 4u) << 2;
+              while (bal != 0u) {
+                const int src = __ffs((int)bal) - 1;
+                bal &= bal - 1u;
+                const int n = __popc(__shfl_sync(full, cm, src));
+                if (lane == src) {
+                  uint32_t slot = my_count;
+                  while (cm != 0u) {
+                    const int p = __ffs((int)cm) - 1;
+                    cm &= cm - 1u;
+                    if (slot < g.list_cap) my_list[slot] = make_uint2(row, ubase + (uint32_t)p);
+                    ++slot;
+                  }
+                }
+                my_count += (uint32_t)n;
+              }
+            }
+          }
+        }
+        if (stamp) g.dbg_clk[1024 + seq] = clock64();
+        dbg_col += bn;
+      }
+    }
+    if (lane == 0) g.cand_count[list] = my_count;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(kTc4Stages * kTc4Cols)) : "memory");
+  }
+}
+
 // One CTA per (N-tile, unit slot): the 8 columns (4 phases x 2 filters) of one scan unit, or never-passing columns for
 // the padding slots of the tile.
 __global__ void __launch_bounds__(128) tc_weights_kernel(const __grid_constant__ TcLaunch ln, const float* __restrict__ lut,
@@ -367,6 +584,13 @@ __global__ void __launch_bounds__(128) tc_weights_kernel(const __grid_constant__
   }
 }
 
+// Scan units per N-tile: 16 (128 columns, four accumulator stages: tc_scan4_kernel, the default) or 32 (256 columns, two
+// stages: tc_scan_kernel; MEPP_TC_STAGES=2).
+int tc_units_per_tile() {
+  static const int v = [] { const char* e = getenv("MEPP_TC_STAGES"); return (e && atoi(e) == 2) ? 32 : 16; }();
+  return v;
+}
+
 int tc_scan_grid() {
   static int sms = 0;
   if (sms == 0) {
@@ -394,6 +618,20 @@ int tc_scan_launch(const TcLaunch& ln, const TcScanArgs& a, cudaStream_t st) {
   static const bool pack = [] { const char* e = getenv("MEPP_TC_PACK"); return e ? atoi(e) != 0 : true; }();
   int grid = tc_scan_grid();
   if ((int64_t)grid > a.n_mtiles) grid = (int)a.n_mtiles;
+  if (tc_units_per_tile() == 16) {
+    for (int k = 0; k < ln.n_tiles; ++k)
+      MEPP_REQUIRE(ln.tiles[k].bn <= kTc4Cols, "scan_tc: N-tile wider than an accumulator stage of the four-stage form");
+    static const int issuers = [] { const char* e = getenv("MEPP_TC_ISSUERS"); return (e && atoi(e) == 4) ? 4 : 2; }();
+    auto launch = [&](auto kern, int iss) {
+      MEPP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, 32 * (1 + iss + kTcEpiWarps), smem, st>>>(ln, a);
+      return 0;
+    };
+    if (issuers == 4) { if (pack ? launch(tc_scan4_kernel<true, 4>, 4) : launch(tc_scan4_kernel<false, 4>, 4)) return 1; }
+    else { if (pack ? launch(tc_scan4_kernel<true, 2>, 2) : launch(tc_scan4_kernel<false, 2>, 2)) return 1; }
+    MEPP_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   if (pack) {
     MEPP_CUDA_CHECK(cudaFuncSetAttribute(tc_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_scan_kernel<true><<<grid, kTcThreads, smem, st>>>(ln, a);

@@ -39,6 +39,7 @@ struct TcScanArgs {
 };
 
 int tc_scan_grid();   // CTAs of a launch (one per SM)
+int tc_units_per_tile();   // 16 (four accumulator stages of 128 columns, default) or 32 (two of 256)
 
 // Fills the int8 weight operand of one launch from the float32 weights and biases of its units (device side: the
 // thresholds may have been computed on the GPU).
