@@ -314,11 +314,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan_kernel(const __grid_con
 // every group owns one stage, so no barrier is shared between groups and three other N-tiles are in flight behind
 // every hand-over.  (At N = 128 an MMA reads as many operand bytes per cycle as the shared memory delivers, 8 KB in
 // 64 cycles: the narrower tile costs no tensor time.)
+// What is left (cycle stamps, profiles/r02_tc_scan_stamps.log): one thread gets a tcgen05.mma of this size accepted only
+// every ~100 cycles (64 cycles of products), and an issuer spends ~400 more cycles per N-tile between its batches
+// (try_wait ~90 even when the phase is complete, fences, commit), so two issuers keep the pipe ~35 % busy.  Tried and
+// dropped, all measured on cfg 3 (6.1 ms per step for this kernel): one issuer per stage (21 warps leave 80 registers
+// per thread, the epilogue spills: 7.1 ms); the first warp of every epilogue group issuing the group's next N-tile before
+// its sign tests (no issuer warps; the four groups fall into lock step and the issuing warp's chain load -> issue ->
+// test is the critical path: 6.9 ms); three issuers over four stages (a stage would change issuers, and a parity wait
+// cannot tell phase k + 1 of its barrier from phase k - 1: races).
 constexpr int kTc4Stages = 4;
 constexpr int kTc4Cols = 128;
 
-template <bool PACK, int ISS>
-__global__ void __launch_bounds__(32 * (1 + ISS + kTcEpiWarps), 1) tc_scan4_kernel(const __grid_constant__ TcLaunch ln,
+template <bool PACK>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_scan4_kernel(const __grid_constant__ TcLaunch ln,
                                                                  const __grid_constant__ TcScanArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__(32 * (1 + ISS + kTcEpiWarps), 1) tc_scan4_kern
   __shared__ uint4 s_nt[kTcMaxTiles];
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcStages; ++s) { mbar_init(smem_u32(&afull[s]), 1); mbar_init(smem_u32(&aempty[s]), ISS); }
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(smem_u32(&afull[s]), 1); mbar_init(smem_u32(&aempty[s]), kTcIssuers); }
     for (int s = 0; s < kTc4Stages; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), 4); }
     mbar_init(smem_u32(bfull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(32 * (1 + ISS + kTcEpiWarps), 1) tc_scan4_kern
                  ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(kTc4Stages * kTc4Cols)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp == 1 + ISS && lane < ln.n_tiles) {
+  if (warp == 1 + kTcIssuers && lane < ln.n_tiles) {
     const TcTile tl = ln.tiles[lane];
     const uint32_t bn = tl.bn;
     const uint32_t idesc = (2u << 4) | (1u << 10) | ((bn >> 3) << 17) | ((uint32_t)(kTcRowsPerTile >> 4) << 24);
@@ -377,34 +385,40 @@ __global__ void __launch_bounds__(32 * (1 + ISS + kTcEpiWarps), 1) tc_scan4_kern
         if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp <= ISS) {
-    // ------------------------------------------------------------ MMA issuers (warps 1 .. ISS): N-tiles s % ISS == me
+  } else if (warp <= kTcIssuers) {
+    // ------------------------------------------------------------ MMA issuers (warps 1, 2): N-tiles s % 2 == me, i.e.
+    // issuer me owns the stages me and me + 2 (a stage must stay with ONE issuer: a parity wait only tells adjacent
+    // phases of a barrier apart, so the uses of a stage have to be issued in order by one thread)
     const uint32_t me = (uint32_t)(warp - 1);
     const uint32_t kDescHi = 8u | (1u << 14);
     mbar_wait_parked(smem_u32(bfull), 0u, park_ns);
     tc_fence_after();
     const bool issuer = lane == 0;
     const uint32_t a_lo_base = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
-    uint32_t stage = 0, phase = 0, seq = 0, uses = 0;      // uses: N-tiles this issuer has issued (4 / ISS per stage round)
+    uint32_t stage = 0, phase = 0, seq = 0;
     for (int64_t tile = blockIdx.x; tile < g.n_mtiles; tile += gridDim.x) {
+      if (g.dbg_clk && blockIdx.x == 0 && issuer && seq < 256) g.dbg_clk[9 * 256 + seq] = clock64();   // loop top
       mbar_wait_parked(smem_u32(&afull[stage]), phase, park_ns);
       tc_fence_after();
+      if (g.dbg_clk && blockIdx.x == 0 && issuer && seq < 256) g.dbg_clk[5 * 256 + seq] = clock64();   // stream tile there
       const uint32_t a_lo = a_lo_base + stage * (uint32_t)(kTcStageBytes / 16);
       for (int nt = 0; nt < n_tiles; ++nt, ++seq) {
-        if ((seq & (uint32_t)(ISS - 1)) != me) continue;
-        const uint32_t st = seq & 3u;                        // ISS = 2: me or me + 2, alternating; ISS = 4: me
+        if ((seq & 1u) != me) continue;
+        const uint32_t st = seq & 3u;                        // N-tile seq is use number seq >> 2 of stage seq & 3
         const uint4 c = s_nt[nt];
-        mbar_wait(smem_u32(&tempty[st]), ((uses / (4 / ISS)) & 1u) ^ 1u);
-        ++uses;
+        mbar_wait(smem_u32(&tempty[st]), ((seq >> 2) & 1u) ^ 1u);
         tc_fence_after();
         if (g.dbg_clk && blockIdx.x == 0 && issuer && seq < 256) g.dbg_clk[seq] = clock64();
         if (issuer) {
           const uint32_t d_tmem = tmem_base + st * kTc4Cols;
 #pragma unroll
           for (uint32_t ks = 0; ks < 5; ++ks)
-            if (ks < c.z)
+            if (ks < c.z) {
               tc_mma_i8(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + 2u * ks), ((uint64_t)kDescHi << 32) | (c.x + ks * c.w),
                         c.y, ks > 0 ? 1u : 0u);
+              if (ks == 0 && g.dbg_clk && blockIdx.x == 0 && seq < 256) g.dbg_clk[6 * 256 + seq] = clock64();   // first MMA issued
+            }
+          if (g.dbg_clk && blockIdx.x == 0 && seq < 256) g.dbg_clk[7 * 256 + seq] = clock64();     // last MMA issued
           tc_commit(smem_u32(&tfull[st]));
           if (g.dbg_clk && blockIdx.x == 0 && seq < 256) g.dbg_clk[256 + seq] = clock64();
         }
@@ -417,7 +431,7 @@ __global__ void __launch_bounds__(32 * (1 + ISS + kTcEpiWarps), 1) tc_scan4_kern
   } else {
     // ------------------------------------------------------------ epilogue (warps 3..18): group = stage
     const unsigned full = 0xffffffffu;
-    const int ew = warp - (1 + ISS), q = warp & 3, gidx = ew >> 2;
+    const int ew = warp - (1 + kTcIssuers), q = warp & 3, gidx = ew >> 2;
     uint32_t my_count = 0, seq = 0, seen = 0;
     const int64_t list = (int64_t)blockIdx.x * kTcEpiWarps + ew;
     uint2* const my_list = g.cand + list * (int64_t)g.list_cap;
@@ -621,14 +635,13 @@ int tc_scan_launch(const TcLaunch& ln, const TcScanArgs& a, cudaStream_t st) {
   if (tc_units_per_tile() == 16) {
     for (int k = 0; k < ln.n_tiles; ++k)
       MEPP_REQUIRE(ln.tiles[k].bn <= kTc4Cols, "scan_tc: N-tile wider than an accumulator stage of the four-stage form");
-    static const int issuers = [] { const char* e = getenv("MEPP_TC_ISSUERS"); return (e && atoi(e) == 4) ? 4 : 2; }();
-    auto launch = [&](auto kern, int iss) {
-      MEPP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<grid, 32 * (1 + iss + kTcEpiWarps), smem, st>>>(ln, a);
-      return 0;
-    };
-    if (issuers == 4) { if (pack ? launch(tc_scan4_kernel<true, 4>, 4) : launch(tc_scan4_kernel<false, 4>, 4)) return 1; }
-    else { if (pack ? launch(tc_scan4_kernel<true, 2>, 2) : launch(tc_scan4_kernel<false, 2>, 2)) return 1; }
+    if (pack) {
+      MEPP_CUDA_CHECK(cudaFuncSetAttribute(tc_scan4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc_scan4_kernel<true><<<grid, kTcThreads, smem, st>>>(ln, a);
+    } else {
+      MEPP_CUDA_CHECK(cudaFuncSetAttribute(tc_scan4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc_scan4_kernel<false><<<grid, kTcThreads, smem, st>>>(ln, a);
+    }
     MEPP_CUDA_CHECK(cudaGetLastError());
     return 0;
   }

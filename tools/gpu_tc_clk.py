@@ -11,7 +11,7 @@ tasks = [(pwm, o) for _, pwm, o in cfg["tasks"]]
 eng = Engine()
 eng.stage(cfg["ascii"], cfg["scores"], cfg["perm_idx"], use_gc=True)
 tables = motif_layers.scan_tables(tasks)
-clk = torch.zeros((5, 256), dtype=torch.int64, device='cuda')
+clk = torch.zeros((10, 256), dtype=torch.int64, device='cuda')
 
 
 class Dbg:      # quacks like the accumulator dump: shape[1] < 0 selects the stamp mode of mepp_scan_tc
@@ -25,11 +25,12 @@ eng.profile(tasks, margin=2, tables=tables)
 torch.cuda.synchronize()
 c = clk.cpu().numpy()
 t0 = c[0][0]
-names = ["mma: tempty ok", "mma: committed", "epi: tfull ok", "epi: released", "epi: tested"]
+names = ["mma: tempty ok", "mma: committed", "epi: tfull ok", "epi: released", "epi: tested", "mma: tile there", "mma: 1st issued",
+         "mma: all issued", "-", "mma: loop top"]
 n = int(os.environ.get("CLK_N", "40"))
-print("n-tile " + " ".join(f"{x:>16s}" for x in names))
+print("n-tile " + " ".join(f"{names[k]:>16s}" for k in (9, 5, 0, 6, 7, 1, 2, 3, 4)))
 for i in range(n):
-    print(f"{i:6d} " + " ".join(f"{int(c[k][i] - t0):16d}" for k in range(5)))
+    print(f"{i:6d} " + " ".join(f"{int(c[k][i] - t0) if c[k][i] else 0:16d}" for k in (9, 5, 0, 6, 7, 1, 2, 3, 4)))
 d = np.diff(c[1][8:200])
 print("steady-state cycles per N-tile (mma commit to commit): median", np.median(d), "mean", d.mean())
 print("commit -> epilogue sees tfull: median", np.median(c[2][8:200] - c[1][8:200]))
