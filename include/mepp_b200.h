@@ -272,8 +272,9 @@ int mepp_build_y_rows(const float* yhat_dev, const int32_t* perm_dev, int64_t N,
  * gathered row of Y per match -- hits_dev / hit_count_dev / count_dev as mepp_scan leaves them, rowstats_dev the
  * float32-blur row sums -- instead of one per non-zero of the blurred matrix (2 margin + 1 times fewer bytes).  Two
  * passes: per-position products S0 (float64, m_rows x mepp_y_rows_ld(C), inside work_dev), then their window sums
- * and the correlation epilogue.  Same outputs as mepp_profile_sparse up to the float32 rounding of the blurred value
- * (<= 6e-8 relative per term).  A match list longer than hits_cap leaves r untouched (the caller sees
+ * and the correlation epilogue.  A match enters as float32(x0 / k), the blurred value of a window it is alone in, so the
+ * products are the ones mepp_profile_sparse sums; only windows holding two matches of one sequence differ (by the
+ * rounding of one float32 addition).  A match list longer than hits_cap leaves r untouched (the caller sees
  * hit_count > hits_cap and redoes the group). */
 int64_t mepp_profile_matches_work_bytes(int64_t m_rows, int64_t hits_cap, int C);
 int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_count_dev, int64_t hits_cap,

@@ -200,14 +200,15 @@ __global__ void __launch_bounds__(256, 3) profile_sparse_kernel(const __grid_con
 // Gathering one row of Y per MATCH instead of one per non-zero of the blurred matrix moves 2 margin + 1 = 5 times
 // fewer bytes and converts 5 times fewer floats -- at cfg 3 Y is 410 MB and comes from HBM (65 GB per step for the
 // entry form).  Two passes, each with the simplest possible inner loop:
-//   match_gather_kernel: S0[row, :] = sum over the matches (n, x0) of row = task * L + position of x0 * Y[n, :]
+//   match_gather_kernel: S0[row, :] = sum over the matches (n, x0) of row = task * L + position of (x0 / k) * Y[n, :]
 //                        (float64, exact products; the loop of profile_sparse_kernel without its epilogue; rows
 //                        without a match are neither computed nor written),
 //   match_blur_kernel:   window sums of S0 along the positions of a task (each S0 row is read once: a CTA walks a block
 //                        of positions with the last k rows in a shared-memory ring) and the correlation epilogue.
 // S0 costs 8 bytes per (row, column) written and read once (2 x 2.6 GB per cfg 3 step), against the 52 GB of gathers it
-// saves.  The only difference to the entry form is that xbar is not rounded to float32 before it multiplies y
-// (<= 6e-8 relative per term; the row statistics sum(xbar), sum(xbar^2), sum(xbar z) still come from the float32 blur).
+// saves.  x0 / k is rounded to float32 like the blurred value it stands for (match_fill_kernel), so the only difference
+// to the entry form are the windows that hold two matches of one sequence (the row statistics sum(xbar), sum(xbar^2),
+// sum(xbar z) always come from the float32 blur).
 struct HitRec4 { int32_t task, seq, pos; float x0; };
 
 // offsets[0 .. m_rows] = exclusive prefix sum of count; offsets[m_rows + 1] = 1 when the match list overflowed;
@@ -259,17 +260,21 @@ __global__ void __launch_bounds__(kScanThreads) match_offsets_kernel(const int32
   if (tid == 0) offsets[m_rows] = s_base;
 }
 
-// csr[offsets[row] + k] = (seq, x0) for the k-th match of row = task * L + pos that arrives
+// csr[offsets[row] + j] = (seq, x0 / k in float32) for the j-th match of row = task * L + pos that arrives.  x0 / k
+// rounded to float32 IS the blurred value of every row of the window of a match that is alone in it (the float32 sum of
+// the window is x0 itself), so the products below are the very numbers the entry form multiplies; only windows that
+// hold two matches of one sequence differ, by the rounding of one float32 addition.
 __global__ void match_fill_kernel(const HitRec4* __restrict__ hits, const unsigned long long* __restrict__ hit_count, int L,
                                   int64_t m_rows, const int32_t* __restrict__ offsets, int32_t* __restrict__ cursor,
-                                  uint2* __restrict__ csr) {
+                                  float kf, uint2* __restrict__ csr) {
   if (offsets[m_rows + 1] != 0) return;
   const int64_t n = (int64_t)*hit_count;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(hits + i));
     const int64_t row = (int64_t)(int)raw.x * L + (int)raw.z;
-    const int k = atomicAdd(cursor + row, 1);
-    csr[offsets[row] + k] = make_uint2(raw.y, raw.w);
+    const int j = atomicAdd(cursor + row, 1);
+    const float x0 = __uint_as_float(raw.w);
+    csr[offsets[row] + j] = make_uint2(raw.y, __float_as_uint(kf > 1.0f ? __fdiv_rn(x0, kf) : x0));
   }
 }
 
@@ -384,7 +389,6 @@ __global__ void __launch_bounds__(kBlurThreads) match_blur_kernel(const __grid_c
     if (c0 < a.C) cz0 = __ldg(reinterpret_cast<const double2*>(cc + 8 + 2 * c0));
     if (c0 + 1 < a.C) cz1 = __ldg(reinterpret_cast<const double2*>(cc + 8 + 2 * (c0 + 1)));
   }
-  const double inv_k = 1.0 / (double)k;
   const double* src = a.S0 + row_t * a.ldS0 + c0;
   int slot = 0;
   int live_rows = 0;                      // rows with a match among the k rows of the ring
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(kBlurThreads) match_blur_kernel(const __grid_c
         }
       }
       const double inv_xy = s_rc[p - p0][0], sxsy = s_rc[p - p0][1];
-      double r0 = (n * (w0 * inv_k) - sxsy) * inv_xy, r1 = (n * (w1 * inv_k) - sxsy) * inv_xy;
+      double r0 = (n * w0 - sxsy) * inv_xy, r1 = (n * w1 - sxsy) * inv_xy;
       if (use_z) {
         const double r_xz = s_rc[p - p0][2], row_den = s_rc[p - p0][3];
         r0 = (r0 - r_xz * cz0.x) * row_den * cz0.y;
@@ -507,7 +511,7 @@ int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_cou
   double* S0 = reinterpret_cast<double*>(w);
   match_offsets_kernel<<<1, kScanThreads, 0, st>>>(count_dev, m_rows, hit_count_dev, hits_cap, offsets, cursor);
   match_fill_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const HitRec4*>(hits_dev), hit_count_dev, L, m_rows, offsets,
-                                             cursor, csr);
+                                             cursor, (float)(2 * margin + 1), csr);
   GatherArgs g;
   g.csr = csr; g.offsets = offsets; g.y_rows = y_rows_dev; g.ldY = mepp_y_rows_ld(C); g.S0 = S0;
   g.m_rows = m_rows; g.n_slabs = (int)(g.ldY / kSlabCols);
