@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU tests, then cfg5 at full size (1e6 x 200 bp, P = 1e4: the permutation index matrix is staged in chunks)
 SECONDS=0
-timeout 1500 python bench.py --workload cfg5 --steps ${1:-3} --warmup 3 --no-cpu-baseline --no-fullrun --no-clocks > gpurun_out/s2_cfg5.json 2>gpurun_out/s2_cfg5.err; echo rc=$?
+timeout 1500 python bench.py --workload cfg5 --steps ${1:-3} --warmup 3 --no-cpu-baseline --no-fullrun --no-clocks --no-tensor-leg > gpurun_out/s2_cfg5.json 2>gpurun_out/s2_cfg5.err; echo rc=$?
 grep -v "^\s" gpurun_out/s2_cfg5.err | tail -5
 python - gpurun_out/s2_cfg5.json <<'PY'
 import json, sys
