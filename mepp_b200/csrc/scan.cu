@@ -1379,7 +1379,12 @@ __global__ void __launch_bounds__(128) tc_exact_kernel(const ScanArgs a, const u
       atomicAdd(&a.count[(int64_t)tt * a.L + p], 1);
       atomicAdd(&a.density[(int64_t)tt * a.n_pad + seq], 1);
       if (a.hit_count) {
-        const unsigned long long hs = atomicAdd(a.hit_count, 1ull);
+        // one reservation per group of lanes that publish together: every match of a launch goes through this ONE counter
+        const unsigned act = __activemask();
+        const int leader = __ffs((int)act) - 1, rank = __popc(act & ((1u << (threadIdx.x & 31)) - 1u));
+        unsigned long long base = 0ull;
+        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(a.hit_count, (unsigned long long)__popc(act));
+        const unsigned long long hs = __shfl_sync(act, base, leader) + (unsigned long long)rank;
         if (a.hits && (int64_t)hs < a.hits_cap) {
           HitRec h; h.task = tt; h.seq = (int32_t)seq; h.pos = p; h.x0 = x0;
           a.hits[hs] = h;

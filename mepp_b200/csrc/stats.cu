@@ -394,29 +394,47 @@ __global__ void radix_pick_kernel(const uint32_t* __restrict__ hist, int hists_p
 // Per task: sorted thresholds |r[l,0]| (ascending) for the pooled p-values, and a table that narrows the search
 // among them: the bit patterns of non-negative floats are ordered like the floats, so bin(a) = (bits(a) - bits(t_min))
 // >> shift is monotone; tab[b] = index of the first threshold whose bin is >= b (kNarrowBins + 1 entries, shift
-// chosen so that t_max lands in the last bin).  thr_par[t] = {bits(t_min), shift}.
-constexpr int kNarrowBins = 4096;
+// chosen so that t_max lands in the last bin).  t_min is the smallest NON-ZERO threshold: the rows the blur zeroes
+// (and motifs without a match) have r = 0 exactly, and a table that started at bit pattern 0 would spend its bins on
+// 127 empty octaves (the search among the thresholds of a bin was 37 % of the pooled pass's instructions with 4096
+// bins from zero; with 16384 from t_min most bins hold no threshold and the rest one).
+// thr_par[t] = {bits(t_min), shift, number of zero thresholds, -}.
+constexpr int kNarrowBins = 16384;
 __global__ void thresholds_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, int L_pow2,
                                   float* __restrict__ ts_sorted, uint16_t* __restrict__ tab, uint32_t* __restrict__ thr_par) {
   extern __shared__ uint32_t s_keys[];
+  __shared__ int s_zero;
   const int t = blockIdx.x;
+  if (threadIdx.x == 0) s_zero = 0;
   for (int i = threadIdx.x; i < L_pow2; i += blockDim.x)
     s_keys[i] = i < L ? __float_as_uint(fabsf(r[((int64_t)t * L + i) * ldr])) : 0xffffffffu;
   __syncthreads();
   bitonic_sort_keys(s_keys, L_pow2);
-  for (int i = threadIdx.x; i < L; i += blockDim.x) ts_sorted[(int64_t)t * L + i] = __uint_as_float(s_keys[i]);
-  const uint32_t kmin = s_keys[0], kmax = s_keys[L - 1];
+  int nz = 0;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    ts_sorted[(int64_t)t * L + i] = __uint_as_float(s_keys[i]);
+    nz += s_keys[i] == 0u;
+  }
+  if (nz) atomicAdd(&s_zero, nz);
+  __syncthreads();
+  const int j0 = s_zero;                                   // thresholds [0, j0) are zero: every |v| reaches them
+  uint16_t* tb = tab + (int64_t)t * (kNarrowBins + 2);
+  if (j0 >= L) {                                           // all zero
+    for (int b = threadIdx.x; b <= kNarrowBins; b += blockDim.x) tb[b] = (uint16_t)L;
+    if (threadIdx.x == 0) { thr_par[4 * t] = 0xffffffffu; thr_par[4 * t + 1] = 0u; thr_par[4 * t + 2] = (uint32_t)L; }
+    return;
+  }
+  const uint32_t kmin = s_keys[j0], kmax = s_keys[L - 1];
   int shift = 0;
   while (((kmax - kmin) >> shift) >= (uint32_t)kNarrowBins) ++shift;
-  uint16_t* tb = tab + (int64_t)t * (kNarrowBins + 2);
-  for (int j = threadIdx.x; j < L; j += blockDim.x) {
+  for (int j = j0 + threadIdx.x; j < L; j += blockDim.x) {
     const int bj = (int)((s_keys[j] - kmin) >> shift);
-    const int bp = j == 0 ? -1 : (int)((s_keys[j - 1] - kmin) >> shift);
+    const int bp = j == j0 ? -1 : (int)((s_keys[j - 1] - kmin) >> shift);
     for (int b = bp + 1; b <= bj; ++b) tb[b] = (uint16_t)j;      // first threshold with bin >= b
   }
   const int b_last = (int)((kmax - kmin) >> shift);
   for (int b = b_last + 1 + threadIdx.x; b <= kNarrowBins; b += blockDim.x) tb[b] = (uint16_t)L;
-  if (threadIdx.x == 0) { thr_par[2 * t] = kmin; thr_par[2 * t + 1] = (uint32_t)shift; }
+  if (threadIdx.x == 0) { thr_par[4 * t] = kmin; thr_par[4 * t + 1] = (uint32_t)shift; thr_par[4 * t + 2] = (uint32_t)j0; }
 }
 
 // One pass over the permuted values of a task for two things: (1) the histogram of the pooled |r_perm| values
@@ -442,7 +460,8 @@ __global__ void __launch_bounds__(256) pooled_pass_kernel(const float* __restric
   for (int i = threadIdx.x; i <= L; i += blockDim.x) s_hist[i] = 0;
   for (int i = threadIdx.x; i < 4 * kRadixBins; i += blockDim.x) s_h2[i] = 0u;
   for (int i = threadIdx.x; i < kNarrowBins + 2; i += blockDim.x) s_tab[i] = tab[(int64_t)t * (kNarrowBins + 2) + i];
-  const uint32_t kmin = thr_par[2 * t], shift = thr_par[2 * t + 1];
+  const uint32_t kmin = thr_par[4 * t], shift = thr_par[4 * t + 1];
+  const int n_zero = (int)thr_par[4 * t + 2];
   const RadixState st = state[t];
   const uint32_t p0 = st.prefix[0] >> 21, p1 = st.prefix[1] >> 21, p2 = st.prefix[2] >> 21, p3 = st.prefix[3] >> 21;
   __syncthreads();
@@ -459,7 +478,7 @@ __global__ void __launch_bounds__(256) pooled_pass_kernel(const float* __restric
         if (j < nr) {
           const float a = fabsf(v[j]);
           const uint32_t ab = __float_as_uint(a);
-          int lo = 0, hi = 0;                           // below every threshold: none is <= a
+          int lo = n_zero, hi = n_zero;                 // below every non-zero threshold: only the zero ones are <= a
           if (ab >= kmin) {
             const uint32_t b = min((ab - kmin) >> shift, (uint32_t)kNarrowBins);
             lo = s_tab[b];
@@ -667,7 +686,7 @@ int64_t mepp_perm_stats_work_bytes(int T, int L, int C) {
   const int64_t h1 = up256((int64_t)T * mepp::kRadixBins * 4);      // radix select: first digit
   const int64_t h23 = up256((int64_t)T * 4 * mepp::kRadixBins * 4); // second / third digit, four targets
   const int64_t state = up256((int64_t)T * sizeof(mepp::RadixState));
-  const int64_t tab = up256((int64_t)T * (mepp::kNarrowBins + 2) * 2) + up256((int64_t)T * 8);   // narrowing table + parameters
+  const int64_t tab = up256((int64_t)T * (mepp::kNarrowBins + 2) * 2) + up256((int64_t)T * 16);   // narrowing table + parameters
   const int64_t part = up256((int64_t)T * mepp::kIntChunks * C * 8);   // row-chunk partial sums of the integrals
   return ts + hist + h1 + 2 * h23 + state + tab + part;
 }
@@ -701,7 +720,7 @@ int mepp_perm_stats(const float* r_dev, int64_t ldr, int T, int L, int C, int k_
   const int64_t state_b = up256((int64_t)T * sizeof(RadixState)), tab_b = up256((int64_t)T * (kNarrowBins + 2) * 2);
   uint16_t* tab = reinterpret_cast<uint16_t*>(w + ts_b + hist_b + h1_b + 2 * h23_b + state_b);
   uint32_t* thr_par = reinterpret_cast<uint32_t*>(w + ts_b + hist_b + h1_b + 2 * h23_b + state_b + tab_b);
-  double* partial = reinterpret_cast<double*>(w + ts_b + hist_b + h1_b + 2 * h23_b + state_b + tab_b + up256((int64_t)T * 8));
+  double* partial = reinterpret_cast<double*>(w + ts_b + hist_b + h1_b + 2 * h23_b + state_b + tab_b + up256((int64_t)T * 16));
   MEPP_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)(hist_b + h1_b + 2 * h23_b), st));
 
   // rows per CTA: enough CTAs to fill the machine, few enough that the per-task histogram flushes stay cheap

@@ -6,6 +6,6 @@ env $VAR=$V timeout 600 python bench.py --workload $W --steps 30 --warmup 3 --no
 python - gpurun_out/s2_ab_$V.json $VAR=$V <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print(sys.argv[2], "ms", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["ms_per_step"], 2), {k: round(v.get("ms_per_step"), 3) for k, v in d["kernels"].items()})
+print(sys.argv[2], "ms", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["ms_per_step"], 2), {k: round(v.get("ms_per_step") or v.get("ms") or 0, 3) for k, v in d["kernels"].items()})
 PY
 done

@@ -5,6 +5,6 @@ timeout 600 python bench.py --steps 20 --warmup 3 --simulate-world $SW --no-cpu-
 python - gpurun_out/s2_sim$SW.json $SW <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print("sim", sys.argv[2], "ms", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["ms_per_step"], 2), {k: round(v.get("ms_per_step"), 3) for k, v in d["kernels"].items()}, d["details"]["host_ms_per_step"], "launches", d["gpu_launches"])
+print("sim", sys.argv[2], "ms", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["ms_per_step"], 2), {k: round(v.get("ms_per_step") or v.get("ms") or 0, 3) for k, v in d["kernels"].items()}, d["details"]["host_ms_per_step"], "launches", d["gpu_launches"])
 PY
 done

@@ -11,7 +11,7 @@ timeout 300 python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline
 python - gpurun_out/tc_ab_$W.json <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print(d["config"]["workload"], d["value"], d["ms_per_step"], "e2e", d["e2e"]["ms_per_step"], {k: round(v.get("ms_per_step"), 3) for k, v in d["kernels"].items()})
+print(d["config"]["workload"], d["value"], d["ms_per_step"], "e2e", d["e2e"]["ms_per_step"], {k: round(v.get("ms_per_step") or v.get("ms") or 0, 3) for k, v in d["kernels"].items()})
 PY
 done
 timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
