@@ -49,7 +49,7 @@ UNIT = "Gbp*motifs/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu --set full
 # capture of the same bench command (profiles/r02_kernels_ncu_summary.txt); null for workloads without a capture
-NCU_DRAM_BYTES_PER_LAUNCH = {("tc_scan_kernel", "cfg3"): None, ("scan_kernel", "cfg2"): 16.0e6}
+NCU_DRAM_BYTES_PER_LAUNCH = {("tc_scan4_kernel", "cfg3"): 413.4e6, ("scan_kernel", "cfg2"): 16.0e6}
 
 
 def clocks_mhz_hint(peaks):
@@ -604,8 +604,11 @@ def main():
                 algorithmic_tops=alg / t_tc / 1e12,
                 algorithmic_note="SURVEY 8(d) compute-bound form: N * L * m * strands multiply-adds per task",
                 stream_gbs=tc_bytes.value / steps / t_tc / 1e9,
-                limit="accumulator hand-over between the MMA issuers and the epilogue warps (2 stages of 256 TMEM "
-                      "columns): DESIGN.md section 4")
+                ncu="profiles/r02_kernels_ncu_summary.txt (cfg3): tensor pipe 20 % active, issue slots 53 % busy, DRAM 413 MB "
+                    "per launch (the one-hot stream, read once)",
+                limit="issue rate of the small MMAs (one thread gets a 128 x 128 x 32 product accepted every ~100 cycles) "
+                      "and the ~400 cycles an issuer spends between its batches (four accumulator stages of 128 TMEM "
+                      "columns, two issuers): DESIGN.md section 4")
     if stage_ms.get("gemm") and sparse:
         # HBM: Y rows once (L2-resident afterwards), CSR records, r written once; L2 -> SM: one Y row per non-zero
         ldY = -(-C_ // 512) * 512
@@ -659,12 +662,12 @@ def main():
     # the dominant kernel of the step (the longest single kernel of the ncu launch list, profiles/)
     if "tc_scan_kernel" in kernels:
         dk = kernels["tc_scan_kernel"]
-        roofline = dict(kernel="tc_scan_kernel", bound="tensor", achieved=dk["achieved"], peak=dk["peak"], unit=dk["unit"],
-                        frac=dk["frac"], traffic=NCU_DRAM_BYTES_PER_LAUNCH.get(("tc_scan_kernel", args.workload)),
+        roofline = dict(kernel="tc_scan4_kernel", bound="tensor", achieved=dk["achieved"], peak=dk["peak"], unit=dk["unit"],
+                        frac=dk["frac"], traffic=NCU_DRAM_BYTES_PER_LAUNCH.get(("tc_scan4_kernel", args.workload)),
                         peak_source=peaks["source"] + "; " + dk["peak_note"], ms_per_launch=dk["ms_per_launch"],
                         algorithmic=dk["algorithmic_tops"], share_of_step=dk["ms_per_step"] / (1e3 * dt_value / args.steps),
                         note="achieved = int8 multiply-adds issued by the launches x 2 / their CUDA-event time (events on the "
-                             "launching stream around every tc_scan_kernel launch of a serial pass, mepp_scan_tc_timing); "
+                             "launching stream around every tc_scan4_kernel launch of a serial pass, mepp_scan_tc_timing); "
                              "algorithmic = 2 N L m strands per task / the same time; traffic = dram__bytes_read + write of "
                              "one launch, ncu --set full of this command (profiles/r02_kernels_ncu_summary.txt)")
     else:

@@ -734,8 +734,10 @@ class Engine:
         G = self.group_size()
         if T_all > 96:
             # several groups so that the host finalisation of one group overlaps the kernels of the next and the
-            # exposed finalisation of the last group stays small (4 measured best on cfg 2)
-            n_groups = int(os.environ.get("MEPP_GROUPS", "4"))
+            # exposed finalisation of the last group stays small (4 measured best on cfg 2) -- but no group below ~80
+            # tasks: the tensor-core scan pays per N-tile of 16 scan units (32 tasks of a '+', '+/-' list), and 41
+            # units fill three tiles where 21 units still need two (the per-rank share of a sharded task list)
+            n_groups = int(os.environ.get("MEPP_GROUPS", "0")) or min(4, max(1, round(T_all / 81.0)))
             G = min(G, max(32, -(-T_all // n_groups)))
         G += G & 1 if G < T_all else 0      # even: the ('+', '+/-') pair of a motif stays in one group
         groups = [(g0, min(g0 + G, T_all)) for g0 in range(0, T_all, G)]
