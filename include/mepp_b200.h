@@ -274,11 +274,12 @@ int mepp_build_y_rows(const float* yhat_dev, const int32_t* perm_dev, int64_t N,
  * passes: per-position products S0 (float64, m_rows x mepp_y_rows_ld(C), inside work_dev), then their window sums
  * and the correlation epilogue.  A match enters as float32(x0 / k), the blurred value of a window it is alone in, so the
  * products are the ones mepp_profile_sparse sums; only windows holding two matches of one sequence differ (by the
- * rounding of one float32 addition).  A match list longer than hits_cap leaves r untouched (the caller sees
+ * rounding of one float32 addition).  n_pad_rows = rows of y_rows_dev (mepp_pad32(N)): an operand beyond the L2 is
+ * gathered in 128-column slabs, slab by slab.  A match list longer than hits_cap leaves r untouched (the caller sees
  * hit_count > hits_cap and redoes the group). */
 int64_t mepp_profile_matches_work_bytes(int64_t m_rows, int64_t hits_cap, int C);
 int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_count_dev, int64_t hits_cap,
-                         const int32_t* count_dev, int T, int L, int margin, const float* y_rows_dev,
+                         const int32_t* count_dev, int T, int L, int margin, const float* y_rows_dev, int64_t n_pad_rows,
                          const double* rowstats_dev, const double* colconst_dev, float* r_dev, int64_t ldr, int C,
                          void* work_dev, void* stream);
 int64_t mepp_profile_sparse_work_bytes(int64_t m_rows, int64_t entry_cap);

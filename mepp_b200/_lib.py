@@ -67,7 +67,7 @@ SIGNATURES = {
     "mepp_y_rows_ld": (_i64, [_i32]),
     "mepp_build_y_rows": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "mepp_profile_matches_work_bytes": (_i64, [_i64, _i64, _i32]),
-    "mepp_profile_matches": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "mepp_profile_matches": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "mepp_profile_sparse_work_bytes": (_i64, [_i64, _i64]),
     "mepp_profile_sparse": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     "mepp_finalize_out_bytes": (_i64, [_i32, _i32]),

@@ -11,6 +11,7 @@
 // N = 20 000, P = 1000) stays L2-resident; the kernel is bound by L2 -> SM bandwidth (4 KB per non-zero).
 #include "common.cuh"
 #include <cfloat>
+#include <stdlib.h>
 
 namespace mepp {
 
@@ -285,7 +286,11 @@ struct GatherArgs {
   int64_t m_rows; int n_slabs;
 };
 
-// One warp = one (row with matches, slab of 512 columns); four matches (16 x 512 B of Y) in flight per warp.
+// One warp = one (row with matches, slab of 128 * J columns); four matches in flight per warp.  Items run slab-major: all
+// warps work on the same slab of Y at about the same time.  J = 4 (512 columns) when Y fits the L2 anyway; J = 1 when it
+// does not (cfg 3: 410 MB): a 128-column slab of Y is N * 512 bytes (51 MB), stays L2-resident while the rows of the
+// group pass over it, and the gather then reads HBM once per slab instead of once per match.
+template <int J>
 __global__ void __launch_bounds__(256, 3) match_gather_kernel(const __grid_constant__ GatherArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -294,40 +299,49 @@ __global__ void __launch_bounds__(256, 3) match_gather_kernel(const __grid_const
   if (a.offsets[a.m_rows + 1] != 0) return;            // match list overflow: the caller redoes the group
   const int64_t ld4 = a.ldY >> 2;
   for (int64_t item = warp0; item < n_items; item += n_warps) {
-    const int64_t row = item / a.n_slabs;
-    const int slab = (int)(item - row * a.n_slabs);
+    const int slab = (int)(item / a.m_rows);
+    const int64_t row = item - (int64_t)slab * a.m_rows;
     const int beg = __ldg(a.offsets + row), end = __ldg(a.offsets + row + 1);
     if (beg == end) continue;
-    const float4* yb = reinterpret_cast<const float4*>(a.y_rows) + (int64_t)slab * (kSlabCols / 4) + lane;
-    double acc[16];
+    const float4* yb = reinterpret_cast<const float4*>(a.y_rows) + (int64_t)slab * (32 * J) + lane;
+    double acc[4 * J];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+    for (int j = 0; j < 4 * J; ++j) acc[j] = 0.0;
     auto rec = [&](int e) { return e < end ? __ldg(a.csr + e) : make_uint2(0u, 0u); };   // (row 0, x = 0) past the end
     uint2 c[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) c[k] = rec(beg + k);
 #pragma unroll 1
     for (int e = beg; e < end; e += 4) {
-      float4 v[4][4];
+      float4 v[4][J];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float4* y = yb + (int64_t)c[k].x * ld4;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[k][j] = __ldg(y + j * 32);
+        for (int j = 0; j < J; ++j) v[k][j] = __ldg(y + j * 32);
       }
       uint2 nx[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) nx[k] = rec(e + 4 + k);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) fma4(acc, (double)__uint_as_float(c[k].y), v[k]);
+      for (int k = 0; k < 4; ++k) {
+        const double x = (double)__uint_as_float(c[k].y);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          acc[4 * j + 0] = fma(x, f2d(v[k][j].x), acc[4 * j + 0]);
+          acc[4 * j + 1] = fma(x, f2d(v[k][j].y), acc[4 * j + 1]);
+          acc[4 * j + 2] = fma(x, f2d(v[k][j].z), acc[4 * j + 2]);
+          acc[4 * j + 3] = fma(x, f2d(v[k][j].w), acc[4 * j + 3]);
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) c[k] = nx[k];
     }
-    double2* dst = reinterpret_cast<double2*>(a.S0 + row * a.ldY + (int64_t)slab * kSlabCols + lane * 4);
+    double2* dst = reinterpret_cast<double2*>(a.S0 + row * a.ldY + (int64_t)slab * (128 * J) + lane * 4);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      dst[j * 64] = make_double2(acc[4 * j + 0], acc[4 * j + 1]);
-      dst[j * 64 + 1] = make_double2(acc[4 * j + 2], acc[4 * j + 3]);
+    for (int j = 0; j < J; ++j) {                       // streaming stores: S0 must not evict the slab of Y from the L2
+      __stcs(dst + j * 64, make_double2(acc[4 * j + 0], acc[4 * j + 1]));
+      __stcs(dst + j * 64 + 1, make_double2(acc[4 * j + 2], acc[4 * j + 3]));
     }
   }
 }
@@ -489,7 +503,7 @@ int64_t mepp_profile_matches_work_bytes(int64_t m_rows, int64_t hits_cap, int C)
 }
 
 int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_count_dev, int64_t hits_cap,
-                         const int32_t* count_dev, int T, int L, int margin, const float* y_rows_dev,
+                         const int32_t* count_dev, int T, int L, int margin, const float* y_rows_dev, int64_t n_pad_rows,
                          const double* rowstats_dev, const double* colconst_dev, float* r_dev, int64_t ldr, int C,
                          void* work_dev, void* stream) {
   using namespace mepp;
@@ -514,8 +528,17 @@ int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_cou
                                              cursor, (float)(2 * margin + 1), csr);
   GatherArgs g;
   g.csr = csr; g.offsets = offsets; g.y_rows = y_rows_dev; g.ldY = mepp_y_rows_ld(C); g.S0 = S0;
-  g.m_rows = m_rows; g.n_slabs = (int)(g.ldY / kSlabCols);
-  match_gather_kernel<<<148 * 16, 256, 0, st>>>(g);
+  g.m_rows = m_rows;
+  // narrow slabs when the operand does not fit the L2 (MEPP_GATHER_SLAB = 128 / 512 overrides)
+  static const int slab_env = [] { const char* e = getenv("MEPP_GATHER_SLAB"); return e ? atoi(e) : 0; }();
+  const bool narrow = slab_env == 128 || (slab_env != 512 && 4.0 * (double)n_pad_rows * (double)g.ldY > 96e6);
+  if (narrow) {
+    g.n_slabs = (int)(g.ldY / 128);
+    match_gather_kernel<1><<<148 * 16, 256, 0, st>>>(g);
+  } else {
+    g.n_slabs = (int)(g.ldY / kSlabCols);
+    match_gather_kernel<4><<<148 * 16, 256, 0, st>>>(g);
+  }
   BlurArgs a;
   a.S0 = S0; a.ldS0 = g.ldY; a.offsets = offsets; a.rowstats = rowstats_dev; a.colconst = colconst_dev;
   a.r = r_dev; a.ldr = ldr; a.T = T; a.L = L; a.C = C; a.margin = margin;

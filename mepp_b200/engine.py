@@ -216,7 +216,13 @@ class Engine:
         self._post_stream = None
         self._post_done = {}
         self._carry = None          # the in-flight last group of a profile_async() call
-        self._slot = 0              # staging slot of the next task group (two slots, alternating over ALL launches)
+        self._slot = 0              # staging slot of the next task group (round robin over ALL launches)
+        # staging slots = task groups that may be on the GPU at once (their scan outputs and result copies are per
+        # slot).  With four, every scan of a four-group call is enqueued before the host first waits for a result: in an
+        # end-to-end step the scans then run under the upload of the permutation indices, which only the profile
+        # chains need.
+        self.n_slots = max(2, int(os.environ.get("MEPP_SLOTS", "4")))
+        self._table_cache = {}      # task-list key -> DeviceTables (device_tables_for)
         # bit-parallel first stage of the scan for the units whose expected survivor rate allows it
         # (mepp_scan_bitpar); a unit takes it when its modelled cost is below MEPP_BP_COST_RATIO x the pair tables'
         self.bitpar = os.environ.get("MEPP_SCAN_BITPAR", "0") != "0"
@@ -562,6 +568,12 @@ class Engine:
         everything that does not need the threshold, one launch of the threshold DP over the distinct
         (motif, filter-0 orientation) units, one for the threshold-dependent table entries."""
         torch = self.torch
+        # the tables depend on the task list alone (motif matrices, orientations, threshold parameters): a list that
+        # comes again -- every step of a stream of datasets profiled against the same motifs -- reuses them
+        key = self._table_key(tasks, table_kw)
+        hit = self._table_cache.get(key)
+        if hit is not None:
+            return hit
         host = motif_layers.prepare_tables(tasks, **table_kw)
         T = len(tasks)
         rows = host['unit_rows']
@@ -610,7 +622,29 @@ class Engine:
         # (kept alive with the tables: the kernels above read them asynchronously)
         dev['_keep'] = (smat_d, umlen_d, par_d, off_d, uot_d, qpar_d, thr_unit)
         self.launches += 2
-        return DeviceTables(dev, host, 0, T)
+        out = DeviceTables(dev, host, 0, T)
+        if len(self._table_cache) >= 4:
+            self._table_cache.pop(next(iter(self._table_cache)))
+        self._table_cache[key] = out
+        return out
+
+    @staticmethod
+    def _table_key(tasks, table_kw):
+        """Content key of a task list: the bytes of every distinct matrix object, the orientations, the parameters."""
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        seen = {}
+        for pwm, orient in tasks:
+            d = seen.get(id(pwm))
+            if d is None:
+                a = np.ascontiguousarray(pwm, dtype=np.float64)
+                d = seen[id(pwm)] = hashlib.blake2b(a.tobytes(), digest_size=16).digest() + bytes([a.shape[-1] & 255])
+            h.update(d)
+            h.update(str(orient).encode())
+        bg = table_kw.get('bg')
+        kw = tuple(sorted((k, (tuple(np.asarray(v, dtype=np.float64).ravel()) if k == 'bg' and v is not None else v))
+                          for k, v in table_kw.items()))
+        return h.digest(), len(tasks), kw
 
     def upload_tables(self, tables):
         """Host scan tables (motif_layers.scan_tables) -> DeviceTables resident in HBM, so that repeated profile()
@@ -696,7 +730,7 @@ class Engine:
         """Tasks per group that fit the memory budget with the larger of the two profile paths (the tiled X operand)."""
         per_task = (self.L * self.n_pad * 4            # X planes (fp16 hi + lo; the sparse path needs ~1 % of this)
                     + self.L * self.ldS * 4            # r
-                    + 2 * (self.n_pad * 4 + self.L * 80))   # densities and finalised columns, two staging slots
+                    + self.n_slots * (self.n_pad * 4 + self.L * 80))   # densities and finalised columns per staging slot
         g = max(1, min(self.max_group, self.mem_budget // max(per_task, 1)))
         return int(g)
 
@@ -752,7 +786,8 @@ class Engine:
         with torch.cuda.device(self.device):
             # the last group of the PREVIOUS call may still be in flight (profile_async): it is collected, like any
             # group, right after the next group has been enqueued, so the GPU never waits for the host side of a call
-            pending, self._carry = self._carry, None
+            inflight = [self._carry] if self._carry is not None else []
+            self._carry = None
             # host threshold DP: every group's tables are submitted to the host thread pool now and collected when
             # the group is launched, so the DP of the later groups runs while the earlier ones are on the GPU
             dtab = futures = None
@@ -767,20 +802,26 @@ class Engine:
                 gt = dtab.slice(g0, g1) if dtab is not None else tables[g0:g1] if tables is not None else futures[gi]()
                 if dtab is None:
                     call.all_tables.extend(gt)
-                slot, self._slot = self._slot, self._slot ^ 1
+                # round-robin slots: the group that used this slot n_slots launches ago has to be collected first
+                while len(inflight) > self.n_slots - 1:
+                    self._collect(inflight.pop(0))
+                slot, self._slot = self._slot, (self._slot + 1) % self.n_slots
                 nxt = self._launch_group(gt, margin, return_hits, return_r, hits_cap, confidence_interval_pct, slot)
                 nxt['t0'] = g0
                 nxt['call'] = call
                 call.units += self.last_units
                 call.paths.append(nxt['path'])
-                if pending is not None:
-                    self._collect(pending)
-                pending = nxt
+                inflight.append(nxt)
+                # results that are already on the host are handed over at once (on_group: the file writers)
+                while len(inflight) > 1 and inflight[0]['done'].query():
+                    self._collect(inflight.pop(0))
                 if return_hits or return_r:
                     # the match list / r buffers are reused by the next group: no overlap in this mode
-                    self._collect(pending)
-                    pending = None
-            self._carry = pending
+                    while inflight:
+                        self._collect(inflight.pop(0))
+            while len(inflight) > 1:
+                self._collect(inflight.pop(0))
+            self._carry = inflight[0] if inflight else None
         if self.host_timing is not None:
             self.host_timing['enqueue_ms'] = self.host_timing.get('enqueue_ms', 0.0) + 1e3 * (_time.perf_counter() - t_begin)
         return call
@@ -941,7 +982,10 @@ class Engine:
         else:
             dens = max(SPARSE_ENTRY_DENSITY, 2.0 * getattr(self, '_density_est', 0.0))
             entry_cap = -(-max(MIN_ENTRY_CAP, int(T * N * L * dens)) // _lib.ENTRY_LISTS) * _lib.ENTRY_LISTS
-            entries = self._buf(f'entries{slot}', entry_cap * 16, torch.uint8)
+            # (the match-driven profile behind the tensor-core scan never reads the entry list: not allocated then)
+            tc_matches = (use_matches and use_lean and self.tc_scan and getattr(self, 'onehot', None) is not None
+                          and not (self.bitpar and self.planes_T is not None))
+            entries = None if tc_matches else self._buf(f'entries{slot}', entry_cap * 16, torch.uint8)
             entry_count = self._buf(f'entry_count{slot}', (16 * _lib.ENTRY_LISTS,), torch.int64)
             row_nnz = self._buf(f'row_nnz{slot}', (m_rows + 1,), torch.int32)
         rowstats = self._buf(f'rowstats{slot}', (m_rows, 3), torch.float64)
@@ -972,7 +1016,7 @@ class Engine:
                 _ptr(self.sym_T), _ptr(self.onehot), _ptr(self.zhat), N, L, T, int(margin), _ptr(lut_d), _ptr(bias_d),
                 _ptr(mlen_d), _ptr(nfilt_d), _ptr(units_d), units_h.ctypes.data if units_h is not None else None, n_units,
                 mlen_h.ctypes.data, _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits_d), cap, _ptr(hit_count),
-                None if use_matches else _ptr(entries), entry_cap, _ptr(entry_count), _ptr(row_nnz), _ptr(buckets),
+                _ptr(entries), entry_cap, _ptr(entry_count), _ptr(row_nnz), _ptr(buckets),
                 _ptr(bucket_count), _ptr(tc_work), wbytes, _ptr(dbg), int(dbg.shape[1]) if dbg is not None else 0, st),
                 "scan_tc")
             self.launches += 4
@@ -1006,8 +1050,8 @@ class Engine:
         overlap = (self.overlap and path == 'sparse' and self.fuse_correlation and not return_hits and not return_r)
         compute_stream = torch.cuda.current_stream(self.device)
         if overlap:
-            self._yrows()
-            self._colconst(sparse=True)   # (built once, on the compute stream, before the chain is handed over)
+            # (the score operand and its constants are built by the first chain, on the chain's stream: they wait for the
+            # upload of the permutation indices, which must not hold up the scans of the later groups)
             if self._post_stream is None:
                 self._post_stream = torch.cuda.Stream(device=self.device, priority=-1)
             scanned = torch.cuda.Event()
@@ -1025,7 +1069,7 @@ class Engine:
                 # one gathered row of Y per MATCH (the blur commutes with the contraction), not per blurred non-zero
                 work = self._buf('match_work', int(_lib.lib.mepp_profile_matches_work_bytes(m_rows, cap, C_)), torch.uint8)
                 _lib.check(_lib.lib.mepp_profile_matches(_ptr(hits_d), _ptr(hit_count), cap, _ptr(count), T, L, int(margin),
-                                                         _ptr(self._yrows()), _ptr(rowstats),
+                                                         _ptr(self._yrows()), self.n_pad, _ptr(rowstats),
                                                          _ptr(self._colconst(sparse=True)),
                                                          _ptr(r), self.ldS, C_, _ptr(work), st), "profile_matches")
                 self.launches += 3
