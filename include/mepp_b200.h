@@ -230,6 +230,16 @@ int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_dev, const fl
                  void* buckets_dev, int32_t* bucket_count_dev, void* work_dev, int64_t work_bytes,
                  int32_t* dbg_acc_dev, int dbg_ld, void* stream);
 
+/* ------------------------------------------------------------------ heat-map reduction
+ * Replaces mepp/plot.py:57-66 (clip at mean + sigma * std of the non-zero scores) and plot.py:32-55,106-145 (block
+ * maximum down to the figure's pixel grid) on the dense (N, L) score matrix that core.py:568-573 returns: computed
+ * from the match list {task, seq, pos, x0} (hits_dev / hit_count_dev as mepp_scan leaves them), the dense matrix never
+ * exists.  out_dev: float [T][H][W], H = ceil(N / block_rows), W = ceil(L / block_cols) (the blocks of
+ * get_aspect_tensor, plot.py:32-40); sigma < 0: no clip.  work_dev: mepp_heatmap_work_bytes(T) bytes. */
+int64_t mepp_heatmap_work_bytes(int T);
+int mepp_heatmap(const void* hits_dev, const unsigned long long* hit_count_dev, int64_t hits_cap, int T, int64_t N, int L,
+                 int block_rows, int block_cols, float sigma, float* out_dev, void* work_dev, void* stream);
+
 /* Measurement hook (bench.py's roofline block): while enabled, every tc_scan_kernel launch of mepp_scan_tc is bracketed
  * by CUDA events on its stream.  A call returns what was gathered since the previous call -- summed kernel time (it
  * waits for the recorded events), int8 multiply-adds issued (128 x columns x 32 per K-step and 512-base tile, padding

@@ -62,6 +62,8 @@ SIGNATURES = {
     "mepp_scan_tc": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
                             _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp]),
     "mepp_scan_tc_timing": (_i32, [_i32, _pd, _pd, _pd, _pi]),
+    "mepp_heatmap_work_bytes": (_i64, [_i32]),
+    "mepp_heatmap": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _i32, _i32, C.c_float, _vp, _vp, _vp]),
     "mepp_y_stats": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "mepp_build_y_cols": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "mepp_y_rows_ld": (_i64, [_i32]),

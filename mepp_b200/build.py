@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmepp_b200.so")
-SOURCES = ["host.cu", "pack.cu", "scan.cu", "tcscan.cu", "gemm.cu", "sparse.cu", "stats.cu", "finalize.cu", "tables.cu", "writer.cu"]
+SOURCES = ["host.cu", "pack.cu", "scan.cu", "tcscan.cu", "gemm.cu", "sparse.cu", "stats.cu", "finalize.cu", "tables.cu", "writer.cu", "heatmap.cu"]
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
               "-lineinfo", "-O3", "-std=c++17"]
 

@@ -35,7 +35,8 @@ def _ptr(t):
 class ProfileBatch:
     """Results of a group of tasks: {column: (T, L)} positions, (T, N) density, thresholds, optional hits / r."""
 
-    def __init__(self, task_ids, positions, density, scores, thr, hit_counts=None, hits=None, r=None, n_seq=0):
+    def __init__(self, task_ids, positions, density, scores, thr, hit_counts=None, hits=None, r=None, n_seq=0,
+                 heatmaps=None, heatmap_spec=None):
         self.task_ids = task_ids
         self.positions = positions
         self.density = density
@@ -45,6 +46,10 @@ class ProfileBatch:
         self.hits = hits
         self.r = r
         self.n_seq = n_seq
+        # (T, H, W) float32 block maxima built on the device (profile(..., heatmap=(pixel_width, pixel_height, sigma)))
+        # and the request they answer
+        self.heatmaps = heatmaps
+        self.heatmap_spec = heatmap_spec
 
     def __len__(self):
         return len(self.task_ids)
@@ -63,8 +68,10 @@ class ProfileBatch:
         """Clipped block-max of task i's score matrix on a pixel grid (plot.py:32-66, 106-145) from the match
         list, without materialising the (N, L) matrix."""
         from . import heatmap as _hm
+        if self.heatmaps is not None and self.heatmap_spec == (pixel_width, pixel_height, sigma):
+            return self.heatmaps[i]                     # reduced on the device (mepp_heatmap)
         if self.hits is None:
-            raise RuntimeError("profile() was called without return_hits=True")
+            raise RuntimeError("profile() was called without return_hits=True or heatmap=(width, height, sigma)")
         h = self.hits[self.hits['task'] == i]
         return _hm.compress_hits_to_pixels(h['seq'], h['pos'], h['x0'], (self.n_seq, L), pixel_width, pixel_height,
                                            sigma)
@@ -171,6 +178,7 @@ class PendingProfile:
         self.return_hits, self.return_r, self.on_group, self.n_groups = return_hits, return_r, on_group, n_groups
         self.outs, self.paths, self.all_tables = [], [], []
         self.units = 0
+        self.heatmap = None
         self.dtab = self.store = self.density_all = self.pos_view = self.batch = None
 
     def result(self):
@@ -737,14 +745,16 @@ class Engine:
     # ------------------------------------------------------------------ tasks
     def profile_async(self, tasks, margin=0, confidence_interval_pct=95, center=None, return_hits=False,
                       return_r=False, hits_cap=None, tables=None, honour_flags=False, pseudocount=1e-4, pvalue=1e-4,
-                      bg=None, on_group=None, dp_precision=None):
+                      bg=None, on_group=None, dp_precision=None, heatmap=None):
         """Enqueue (motif_matrix (4, m), orientation) tasks; returns a PendingProfile whose result() is the
         ProfileBatch.  The last task group of the call stays in flight: its device -> host copies and the host side of
         its results overlap whatever the caller enqueues next (the next profile_async call of a stream of task lists),
         and are completed by result() at the latest.  At most one call is left in flight.  on_group(t0, t1, positions,
         density), if given, is called as soon as the results of tasks t0 .. t1-1 are in the host tables (rows t0 .. t1-1
         of the {column: (T, L)} positions and of the (T, N) density are final): the caller can serialise them while
-        the later groups are still on the GPU."""
+        the later groups are still on the GPU.  heatmap = (pixel_width, pixel_height, sigma): the clipped block maxima
+        of every task's score matrix on that pixel grid (plot.py:32-66,106-145), reduced on the device from the match
+        list (ProfileBatch.heatmaps / .heatmap(i, ...)); sigma None: no clip."""
         if not self.staged:
             raise RuntimeError("Engine.stage() must be called first")
         if not 0 <= int(margin) <= _lib.MAX_MARGIN:
@@ -777,6 +787,8 @@ class Engine:
         groups = [(g0, min(g0 + G, T_all)) for g0 in range(0, T_all, G)]
         call = PendingProfile(self, T_all, center, margin, confidence_interval_pct, return_hits, return_r, on_group,
                               len(groups))
+        if heatmap is not None:
+            call.heatmap = (heatmap[0], heatmap[1], heatmap[2] if len(heatmap) > 2 else 1.0)
         call.store = stats_host.alloc_positions(T_all, L, self.P)
         # matches per (task, sequence): <= L, so two bytes do whenever L <= 65535 (half the result bytes of a step)
         call.density_all = np.empty((T_all, N), dtype=np.uint16 if L <= 65535 else np.int32)
@@ -806,7 +818,8 @@ class Engine:
                 while len(inflight) > self.n_slots - 1:
                     self._collect(inflight.pop(0))
                 slot, self._slot = self._slot, (self._slot + 1) % self.n_slots
-                nxt = self._launch_group(gt, margin, return_hits, return_r, hits_cap, confidence_interval_pct, slot)
+                nxt = self._launch_group(gt, margin, return_hits, return_r, hits_cap, confidence_interval_pct, slot,
+                                         heatmap=call.heatmap)
                 nxt['t0'] = g0
                 nxt['call'] = call
                 call.units += self.last_units
@@ -892,8 +905,10 @@ class Engine:
             thr = thr_all[dtab.g0:dtab.g1]
         else:
             thr = np.array([tb['thr'] for tb in call.all_tables])
+        heat = np.concatenate([o['heatmap'] for o in outs], axis=0) if call.heatmap is not None else None
         call.batch = ProfileBatch(list(range(call.T_all)), positions, call.density_all, self.scores, thr,
-                                  hit_counts=cat('hit_count'), hits=hits, r=r, n_seq=self.N)
+                                  hit_counts=cat('hit_count'), hits=hits, r=r, n_seq=self.N, heatmaps=heat,
+                                  heatmap_spec=call.heatmap)
         call.store = call.pos_view = call.on_group = None
         return call.batch
 
@@ -937,7 +952,7 @@ class Engine:
         return cur[:need].view(tuple(int(x) for x in shape))
 
     def _launch_group(self, tables, margin, return_hits, return_r, hits_cap, ci, slot, path=None, lean=None,
-                      matches=None):
+                      matches=None, heatmap=None):
         """Enqueue every kernel of one task group plus the D2H copies of its results (no host sync)."""
         torch = self.torch
         T = len(tables)
@@ -1146,6 +1161,18 @@ class Engine:
             else:
                 dev['density'] = density
             dev['hit_count'] = hit_count
+            if heatmap is not None:
+                # block maxima of the clipped score matrix on the figure's pixel grid, from the match list of the group
+                from . import heatmap as _hm
+                bh, bw = _hm.get_aspect_tensor((N, L), heatmap[0], heatmap[1])
+                H, W = -(-N // bh), -(-L // bw)
+                heat = self._buf(f'heat{slot}', (T, H, W), torch.float32)
+                hwork = self._buf('heat_work', int(_lib.lib.mepp_heatmap_work_bytes(T)), torch.uint8)
+                sig = -1.0 if heatmap[2] is None else float(heatmap[2])
+                _lib.check(_lib.lib.mepp_heatmap(_ptr(hits_d), _ptr(hit_count), cap, T, N, L, bh, bw, sig, _ptr(heat),
+                                                 _ptr(hwork), st), "heatmap")
+                self.launches += 3
+                dev['heatmap'] = heat
             if path == 'sparse':
                 dev['entry_count'] = entry_count
                 dev['nnz'] = nnz_d
@@ -1169,6 +1196,7 @@ class Engine:
             return dict(host=host, done=done, T=T, hits_d=hits_d, cap=cap, return_hits=return_hits, path=path,
                         use_matches=use_matches,
                         entry_cap=entry_cap, slot=slot, tables=tables, return_r=return_r, hits_cap=hits_cap,
+                        heatmap=heatmap,
                         dev=dev, chain_done=ready)    # (keeps the copied tensors alive until the side stream is done with them)
 
         if not overlap:
@@ -1199,7 +1227,7 @@ class Engine:
                 redo = self._launch_group(pend['tables'], margin, pend['return_hits'], pend['return_r'], pend['hits_cap'],
                                           ci, pend['slot'], path='tensor' if list_full else 'sparse',
                                           lean=False if lean_full or list_full else None,
-                                          matches=False if hits_full else None)
+                                          matches=False if hits_full else None, heatmap=pend.get('heatmap'))
                 redo['t0'] = t0
                 redo['call'] = pend.get('call')
                 if redo['call'] is not None:
@@ -1230,4 +1258,8 @@ class Engine:
             out['hits'] = pend['hits_d'][:nh * 16].cpu().numpy().view(HIT_DTYPE).copy()
         if 'r' in h:
             out['r'] = h['r'].copy()
+        if 'heatmap' in h:
+            if nh > pend['cap']:
+                raise RuntimeError(f"match list overflow: {nh} matches > capacity {pend['cap']}; pass hits_cap")
+            out['heatmap'] = h['heatmap'].copy()
         return out

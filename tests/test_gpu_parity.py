@@ -370,6 +370,34 @@ def test_heatmap_from_hits_equals_dense_block_max(cfg1):
 
 
 
+def test_device_heatmap_equals_dense_block_max(cfg1):
+    """mepp_heatmap (clip at mean + sigma * std of the non-zero scores, block maximum down to the pixel
+    grid, on the device from the match list) against the dense restatement of plot.py:32-66,106-145.  Unclipped pixels
+    are bit-equal; clipped ones equal the limit, which the device computes in float64 and numpy in float32."""
+    from mepp_b200 import heatmap
+    eng = _engine().stage(cfg1["ascii"], cfg1["scores"], cfg1["perm_idx"])
+    tasks = [(pwm, o) for _, pwm, o in cfg1["tasks"]][:6]
+    ref = eng.profile(tasks, margin=cfg1["margin"], return_hits=True)
+    N, L = cfg1["N"], cfg1["L"]
+    for pw, ph, sigma in ((100, 50, 1.0), (201, 1000, 1.0), (7, 13, 2.5), (64, 64, None)):
+        got = eng.profile(tasks, margin=cfg1["margin"], heatmap=(pw, ph, sigma))
+        assert got.heatmaps is not None and got.heatmaps.dtype == np.float32
+        assert np.array_equal(np.asarray(got.positions["positional_r"]), np.asarray(ref.positions["positional_r"]))
+        for t in range(len(tasks)):
+            X0 = ref.motif_score_matrix(t, L)
+            want = heatmap.compress_dense_to_pixels(X0, pw, ph, sigma)
+            a = got.heatmap(t, L, pw, ph, sigma)
+            assert a.shape == want.shape, (pw, ph, t)
+            lim = heatmap.clip_limit(X0[X0 != 0], sigma)
+            if lim is None:
+                assert np.array_equal(a, want)
+            else:
+                below = want < np.float32(lim) * (1 - 1e-6)
+                assert np.array_equal(a[below], want[below]), (pw, ph, t)
+                assert np.allclose(a[~below], want[~below], rtol=2e-6, atol=0), (pw, ph, t)
+            assert (a > 0).sum() == (want > 0).sum()
+
+
 def test_shared_scan_units_equal_separate_scans():
     """'+' tasks ride on the '+/-' pass of the same motif (engine.scan_units); out-of-order pairs, unpaired
     tasks and '-' tasks in the same call; results equal the one-scan-per-task path and the oracle."""
