@@ -66,8 +66,14 @@ struct ScanArgs {
   // lean mode (optional, sparse path): the scan only finds and publishes matches; they also go to fixed-capacity
   // buckets per (task, k-block), from which bucket_entries_kernel builds the blurred entries and the row sums
   int lean; uint2* buckets; int32_t* bucket_count;
+  // overflow of the buckets (optional, tensor-core scan): matches beyond a bucket's capacity go to ONE list
+  // {bucket, key, x0}; bucket_entries_kernel lists the buckets that overflowed and bucket_overflow_kernel redoes those
+  // from both places.  ovf_count[0] = records, [1] = overflowed buckets.
+  uint4* ovf; uint32_t* ovf_count; uint32_t ovf_cap; int32_t* ovf_bkts; uint32_t ovf_bkt_cap;
 };
-constexpr int kBucketCap = 64;   // matches per (task, k-block) bucket; an overflow sends the group through the full scan
+constexpr int kBucketCap = 64;   // matches per (task, k-block) bucket; more go to the overflow list (tensor-core scan) or
+                                 // send the group through the full scan (CUDA-core lean scan)
+constexpr int kOvfMax = 4096;    // matches of one overflowed bucket that bucket_overflow_kernel sorts in shared memory
 
 // Per-warp (= per unit) state shared by the helper routines below.  The helpers are deliberately NOT
 // inlined and NOT templated on the task: one small instruction stream for every task keeps the kernel
@@ -1037,7 +1043,10 @@ __global__ void __launch_bounds__(128) bucket_entries_kernel(const uint2* __rest
                                                              int64_t KB, int L, int margin, int64_t N,
                                                              const float* __restrict__ zhat, XEntry* __restrict__ entries,
                                                              int64_t sub_cap, unsigned long long* __restrict__ entry_count,
-                                                             int32_t* __restrict__ row_nnz, double* __restrict__ rowstats) {
+                                                             int32_t* __restrict__ row_nnz, double* __restrict__ rowstats,
+                                                             int32_t* __restrict__ ovf_bkts = nullptr,
+                                                             uint32_t* __restrict__ ovf_count = nullptr,
+                                                             uint32_t ovf_bkt_cap = 0) {
   __shared__ uint32_t s_key[4][2][kBucketCap];
   __shared__ float s_val[4][2][kBucketCap];
   const unsigned full = 0xffffffffu;
@@ -1047,7 +1056,12 @@ __global__ void __launch_bounds__(128) bucket_entries_kernel(const uint2* __rest
   const int n = bucket_count[bkt];
   if (n == 0) return;
   if (n > kBucketCap) {
-    if (lane == 0) atomicAdd(entry_count + 1, 1ull);        // word 1 of the counter block: "a bucket overflowed"
+    if (lane == 0) {
+      // listed for bucket_overflow_kernel, or (no list, list full) word 1 of the counter block: "a bucket overflowed"
+      const uint32_t i = ovf_bkts ? atomicAdd(ovf_count + 1, 1u) : 0xffffffffu;
+      if (i < ovf_bkt_cap) ovf_bkts[i] = (int32_t)bkt;
+      else atomicAdd(entry_count + 1, 1ull);
+    }
     return;
   }
   const int t = (int)(bkt / KB), kb = (int)(bkt % KB);
@@ -1129,6 +1143,110 @@ __global__ void __launch_bounds__(128) bucket_entries_kernel(const uint2* __rest
 }  // namespace mepp
 
 namespace mepp {
+// The buckets that overflowed (a run of matches inside 32 sequences: low-complexity repeats, a strongly enriched motif
+// in neighbouring sequences): one CTA per listed bucket collects its matches from the bucket (the first kBucketCap) and
+// from the overflow list, sorts them by (sequence, position) in shared memory and emits exactly what
+// bucket_entries_kernel emits.  More than kOvfMax matches in one bucket, or an overflow list that itself overflowed,
+// raise the group-wide flag (entry_count[1]) and the caller redoes the group with the full-form scan.
+__global__ void __launch_bounds__(256) bucket_overflow_kernel(const uint2* __restrict__ buckets,
+                                                              const int32_t* __restrict__ bucket_count, int64_t KB, int L,
+                                                              int margin, int64_t N, const float* __restrict__ zhat,
+                                                              XEntry* __restrict__ entries, int64_t sub_cap,
+                                                              unsigned long long* __restrict__ entry_count,
+                                                              int32_t* __restrict__ row_nnz, double* __restrict__ rowstats,
+                                                              const uint4* __restrict__ ovf,
+                                                              const uint32_t* __restrict__ ovf_count, uint32_t ovf_cap,
+                                                              const int32_t* __restrict__ ovf_bkts, uint32_t ovf_bkt_cap) {
+  __shared__ uint32_t s_key[kOvfMax];
+  __shared__ float s_val[kOvfMax];
+  __shared__ int s_n;
+  const uint32_t n_rec = ovf_count[0];
+  uint32_t n_b = ovf_count[1];
+  if (n_b == 0) return;
+  if (n_rec > ovf_cap) {                                     // records were dropped: nothing here can be trusted
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(entry_count + 1, 1ull);
+    return;
+  }
+  if (n_b > ovf_bkt_cap) n_b = ovf_bkt_cap;                  // (the unlisted ones raised the flag themselves)
+  const int tid = threadIdx.x;
+  const int mg = margin, k = 2 * margin + 1;
+  const float kf = (float)k;
+  for (uint32_t b = blockIdx.x; b < n_b; b += gridDim.x) {
+    const int64_t bkt = ovf_bkts[b];
+    const int t = (int)(bkt / KB), kb = (int)(bkt % KB);
+    __syncthreads();
+    if (tid == 0) s_n = kBucketCap;
+    for (int i = tid; i < kBucketCap; i += blockDim.x) {
+      const uint2 r = buckets[bkt * kBucketCap + i];
+      s_key[i] = r.x; s_val[i] = __uint_as_float(r.y);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n_rec; i += blockDim.x) {
+      const uint4 r = __ldg(ovf + i);
+      if ((int64_t)r.x == bkt) {
+        const int j = atomicAdd(&s_n, 1);
+        if (j < kOvfMax) { s_key[j] = r.y; s_val[j] = __uint_as_float(r.z); }
+      }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n > kOvfMax || n != bucket_count[bkt]) {             // too long a run for this kernel (or an inconsistent list)
+      if (tid == 0) atomicAdd(entry_count + 1, 1ull);
+      continue;
+    }
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int i = n + tid; i < n2; i += blockDim.x) { s_key[i] = 0xffffffffu; s_val[i] = 0.0f; }
+    __syncthreads();
+    for (int kk = 2; kk <= n2; kk <<= 1)                     // bitonic sort of (key, value) pairs, ascending keys
+      for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+        for (int i = tid; i < n2; i += blockDim.x) {
+          const int p = i ^ jj;
+          if (p > i) {
+            const bool up = (i & kk) == 0;
+            const uint32_t a0 = s_key[i], a1 = s_key[p];
+            if ((a0 > a1) == up) {
+              s_key[i] = a1; s_key[p] = a0;
+              const float v = s_val[i]; s_val[i] = s_val[p]; s_val[p] = v;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    const int list = kb & (MEPP_ENTRY_LISTS - 1);
+    uint4* dst = entries ? reinterpret_cast<uint4*>(entries + (int64_t)list * sub_cap) : nullptr;
+    for (int idx = tid; idx < n; idx += blockDim.x) {
+      // rows owned by match idx: its window, minus the rows an earlier match of the same sequence owns
+      const int sq = (int)(s_key[idx] >> 16), pos = (int)(s_key[idx] & 0xffffu);
+      int r_lo = max(pos - mg, mg);
+      const int r_hi = min(pos + mg, L - 1 - mg);
+      if (idx > 0 && (int)(s_key[idx - 1] >> 16) == sq) r_lo = max(r_lo, (int)(s_key[idx - 1] & 0xffffu) + mg + 1);
+      const int cnt = r_hi - r_lo + 1;
+      if (cnt <= 0) continue;
+      unsigned long long slot = dst ? atomicAdd(entry_count + list * 16, (unsigned long long)cnt) : 0ull;
+      const int64_t ns = (int64_t)kb * 32 + sq;
+      const double z = (zhat && ns < N) ? (double)__ldg(zhat + ns) : 0.0;
+      for (int p = r_lo; p <= r_hi; ++p) {
+        float acc = 0.0f;
+        for (int j = idx; j < n && (int)(s_key[j] >> 16) == sq && (int)(s_key[j] & 0xffffu) <= p + mg; ++j)
+          acc = __fadd_rn(acc, s_val[j]);
+        const float xb = k > 1 ? __fdiv_rn(acc, kf) : acc;
+        const int r = t * L + p;
+        if (dst) {
+          if ((int64_t)slot < sub_cap) dst[slot] = make_uint4((uint32_t)r, (uint32_t)ns, __float_as_uint(xb), 0u);
+          ++slot;
+          atomicAdd(row_nnz + r, 1);
+        }
+        const double v = (double)xb;
+        double* rs = rowstats + (int64_t)r * 3;
+        atomicAdd(rs + 0, v); atomicAdd(rs + 1, v * v); atomicAdd(rs + 2, v * z);
+      }
+    }
+  }
+}
+}  // namespace mepp
+
+namespace mepp {
 static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
                      int64_t N, int L, int T, int margin, const float* lut_dev, const float* bias_dev,
                      const int32_t* mlen_dev, const int32_t* nfilt_dev, const uint32_t* qtab_dev,
@@ -1176,6 +1294,7 @@ static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
   MEPP_REQUIRE(!lean || (bucket_count_dev && entries_dev && !x_planes_dev && !bitpar && L <= 65535),
                "scan_lean: needs the bucket counters and the entry list, no tiled operand, no bit planes, L <= 65535");
   a.lean = lean ? 1 : 0; a.buckets = reinterpret_cast<uint2*>(buckets_dev); a.bucket_count = bucket_count_dev;
+  a.ovf = nullptr; a.ovf_count = nullptr; a.ovf_cap = 0; a.ovf_bkts = nullptr; a.ovf_bkt_cap = 0;
   const int nbuf = 32 + 2 * margin;
   auto smem_bytes = [&](bool bp) {
     return (lean ? 0 : sizeof(float) * kScanWarps * ((units_dev || bitpar) ? 2 : 1) * nbuf * kRowStride) +
@@ -1375,7 +1494,13 @@ __global__ void __launch_bounds__(128) tc_exact_kernel(const ScanArgs a, const u
     auto publish = [&](int tt, float x0) {
       const int64_t bkt = (int64_t)tt * a.KB + kb;
       const int slot = atomicAdd(&a.bucket_count[bkt], 1);
-      if (slot < kBucketCap) a.buckets[bkt * kBucketCap + slot] = make_uint2(((uint32_t)s << 16) | (uint32_t)p, __float_as_uint(x0));
+      const uint32_t key = ((uint32_t)s << 16) | (uint32_t)p;
+      if (slot < kBucketCap) {
+        a.buckets[bkt * kBucketCap + slot] = make_uint2(key, __float_as_uint(x0));
+      } else if (a.ovf) {
+        const uint32_t o = atomicAdd(a.ovf_count, 1u);
+        if (o < a.ovf_cap) a.ovf[o] = make_uint4((uint32_t)bkt, key, __float_as_uint(x0), 0u);
+      }
       atomicAdd(&a.count[(int64_t)tt * a.L + p], 1);
       atomicAdd(&a.density[(int64_t)tt * a.n_pad + seq], 1);
       if (a.hit_count) {
@@ -1430,6 +1555,12 @@ extern "C" int mepp_scan_tc_timing(int enable, double* ms_out, double* macs_out,
   return 0;
 }
 
+namespace mepp {
+// bucket overflow (ScanArgs::ovf): counters, the list of overflowed buckets, the records; behind the candidate lists
+constexpr uint32_t kTcOvfRecs = 1u << 20, kTcOvfBkts = 1u << 16;
+constexpr int64_t kTcOvfBytes = 256 + (int64_t)kTcOvfBkts * 4 + (int64_t)kTcOvfRecs * 16;
+}  // namespace mepp
+
 extern "C" int64_t mepp_scan_tc_work_bytes(int64_t N, int L, int n_units) {
   using namespace mepp;
   // weight operands of every launch (<= 8 columns x 160 channels per unit, plus tile padding), candidate lists, counters
@@ -1437,7 +1568,7 @@ extern "C" int64_t mepp_scan_tc_work_bytes(int64_t N, int L, int n_units) {
   const double expect = (double)N * (double)L * (double)(n_units < 256 ? n_units : 256) * 4e-3 / (148.0 * kTcEpiWarps);
   int64_t cap = (int64_t)expect + 2048;
   if (cap > (1 << 22)) cap = 1 << 22;
-  return 1024 + (int64_t)(n_units + n_units / 8 + 64) * 8 * 160 + lists * 16 + lists * cap * 8 + 1024;
+  return 1024 + (int64_t)(n_units + n_units / 8 + 64) * 8 * 160 + lists * 16 + lists * cap * 8 + 1024 + kTcOvfBytes;
 }
 
 extern "C" int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_dev, const float* zhat_dev,
@@ -1478,6 +1609,13 @@ extern "C" int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_de
   a.entry_count = entry_count_dev; a.row_nnz = row_nnz_dev;
   a.planes_T = nullptr; a.bp = nullptr; a.unit_count = nullptr;
   a.lean = 1; a.buckets = reinterpret_cast<uint2*>(buckets_dev); a.bucket_count = bucket_count_dev;
+  {
+    uint8_t* ob = reinterpret_cast<uint8_t*>(work_dev) + ((work_bytes - kTcOvfBytes) & ~(int64_t)255);
+    a.ovf_count = reinterpret_cast<uint32_t*>(ob);
+    a.ovf_bkts = reinterpret_cast<int32_t*>(ob + 256); a.ovf_bkt_cap = kTcOvfBkts;
+    a.ovf = reinterpret_cast<uint4*>(ob + 256 + (size_t)kTcOvfBkts * 4); a.ovf_cap = kTcOvfRecs;
+    MEPP_CUDA_CHECK(cudaMemsetAsync(a.ovf_count, 0, 8, st));
+  }
   MEPP_CUDA_CHECK(cudaMemsetAsync(rowstats_dev, 0, sizeof(double) * 3 * (size_t)T * L, st));
   MEPP_CUDA_CHECK(cudaMemsetAsync(count_dev, 0, sizeof(int32_t) * (size_t)T * L, st));
   MEPP_CUDA_CHECK(cudaMemsetAsync(density_dev, 0, sizeof(int32_t) * (size_t)T * a.n_pad, st));
@@ -1494,7 +1632,9 @@ extern "C" int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_de
   const int64_t b_region = ((int64_t)(U + U / 8 + 64) * 8 * 160 + 1023) / 1024 * 1024;
   uint32_t* counts_dev = reinterpret_cast<uint32_t*>(wk + b_region);
   uint2* cand_dev = reinterpret_cast<uint2*>(wk + b_region + ((lists * 4 + 1023) / 1024 * 1024));
-  const int64_t cand_bytes = work_bytes - (reinterpret_cast<uint8_t*>(cand_dev) - reinterpret_cast<uint8_t*>(work_dev));
+  // (the last kTcOvfBytes of the work buffer hold the bucket-overflow lists)
+  uint8_t* ovf_base = reinterpret_cast<uint8_t*>(work_dev) + ((work_bytes - kTcOvfBytes) & ~(int64_t)255);
+  const int64_t cand_bytes = ovf_base - reinterpret_cast<uint8_t*>(cand_dev);
   int64_t cap64 = cand_bytes / (lists * 8);
   MEPP_REQUIRE(cap64 >= 256, "scan_tc: work buffer too small for the candidate lists");
   if (cap64 > (1 << 22)) cap64 = 1 << 22;
@@ -1571,7 +1711,11 @@ extern "C" int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_de
   const int64_t n_buckets = (int64_t)T * a.KB;
   bucket_entries_kernel<<<(unsigned)((n_buckets + 3) / 4), 128, 0, st>>>(
       a.buckets, bucket_count_dev, n_buckets, a.KB, L, margin, N, zhat_dev, a.entries, a.sub_cap, entry_count_dev,
-      row_nnz_dev, rowstats_dev);
+      row_nnz_dev, rowstats_dev, a.ovf_bkts, a.ovf_count, a.ovf_bkt_cap);
+  // the buckets that overflowed, one by one (returns at once when there is none)
+  bucket_overflow_kernel<<<74, 256, 0, st>>>(a.buckets, bucket_count_dev, a.KB, L, margin, N, zhat_dev, a.entries, a.sub_cap,
+                                             entry_count_dev, row_nnz_dev, rowstats_dev, a.ovf, a.ovf_count, a.ovf_cap,
+                                             a.ovf_bkts, a.ovf_bkt_cap);
   MEPP_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
