@@ -291,7 +291,7 @@ struct GatherArgs {
 // does not (cfg 3: 410 MB): a 128-column slab of Y is N * 512 bytes (51 MB), stays L2-resident while the rows of the
 // group pass over it, and the gather then reads HBM once per slab instead of once per match.
 template <int J>
-__global__ void __launch_bounds__(256, 3) match_gather_kernel(const __grid_constant__ GatherArgs a) {
+__global__ void __launch_bounds__(256, J == 1 ? 4 : 3) match_gather_kernel(const __grid_constant__ GatherArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -532,12 +532,17 @@ int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_cou
   // narrow slabs when the operand does not fit the L2 (MEPP_GATHER_SLAB = 128 / 512 overrides)
   static const int slab_env = [] { const char* e = getenv("MEPP_GATHER_SLAB"); return e ? atoi(e) : 0; }();
   const bool narrow = slab_env == 128 || (slab_env != 512 && 4.0 * (double)n_pad_rows * (double)g.ldY > 96e6);
+  // (grids: measured.  The narrow form reads 2.5 GB of HBM per cfg 3 launch for the 0.4 GB of Y -- its later waves of
+  // CTAs start again at slab 0 -- but a grid of exactly the resident CTAs, one sweep, was no faster (4.46 vs 4.37 ms
+  // per step: the rows are too uneven for a static deal over 4.7 k warps); the wide form gained 3 % from it.)
+  static const int sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+                              return n > 0 ? n : 148; }();
   if (narrow) {
     g.n_slabs = (int)(g.ldY / 128);
-    match_gather_kernel<1><<<148 * 16, 256, 0, st>>>(g);
+    match_gather_kernel<1><<<sms * 16, 256, 0, st>>>(g);
   } else {
     g.n_slabs = (int)(g.ldY / kSlabCols);
-    match_gather_kernel<4><<<148 * 16, 256, 0, st>>>(g);
+    match_gather_kernel<4><<<sms * 3, 256, 0, st>>>(g);
   }
   BlurArgs a;
   a.S0 = S0; a.ldS0 = g.ldY; a.offsets = offsets; a.rowstats = rowstats_dev; a.colconst = colconst_dev;
