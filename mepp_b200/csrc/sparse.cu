@@ -534,7 +534,8 @@ int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_cou
   const bool narrow = slab_env == 128 || (slab_env != 512 && 4.0 * (double)n_pad_rows * (double)g.ldY > 96e6);
   // (grids: measured.  The narrow form reads 2.5 GB of HBM per cfg 3 launch for the 0.4 GB of Y -- its later waves of
   // CTAs start again at slab 0 -- but a grid of exactly the resident CTAs, one sweep, was no faster (4.46 vs 4.37 ms
-  // per step: the rows are too uneven for a static deal over 4.7 k warps); the wide form gained 3 % from it.)
+  // per step: the rows are too uneven for a static deal over 4.7 k warps); the wide form gained 3 % from it.  A dynamic
+  // deal -- warps taking 16 consecutive rows at a time from one counter, slab-major -- was much slower (7.5 ms).)
   static const int sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
                               return n > 0 ? n : 148; }();
   if (narrow) {
