@@ -143,7 +143,11 @@ int mepp_build_y(const float* yhat_dev, const int32_t* perm_dev, const float* zh
  *   count_dev     int32 [T*L]  : #sequences with an unsmoothed match at each position; zeroed by the call
  *   density_dev   int32 [T][n_pad]: #matches per sequence
  *   hits_dev      optional: {int32 task, int32 seq, int32 pos, float x0} records, capacity hits_cap,
- *                 hit_count_dev int64[1] total number of matches (may exceed cap); NULL to skip */
+ *                 hit_count_dev int64[1] total number of matches (may exceed cap); NULL to skip
+ *   xscale_dev    optional float [T]: per-task power-of-two scale of the fp16 hi + lo pieces of x_planes_dev
+ *                 (mepp_x_scales; pass the same array to mepp_profile_corr_gemm); NULL: MEPP_X_SCALE for every task */
+int mepp_x_scales(const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev, const int32_t* nfilt_dev, int T,
+                  float* xscale_dev, void* stream);
 int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
               int64_t N, int L, int T, int margin,
               const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev, const int32_t* nfilt_dev,
@@ -152,7 +156,7 @@ int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
               void* x_planes_dev, double* rowstats_dev, int32_t* count_dev, int32_t* density_dev,
               void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
               void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
-              void* stream);
+              const float* xscale_dev, void* stream);
 
 /* ---- bit-parallel first stage of the scan (same reference code as mepp_scan: motif_layers.py:80-165) ----
  * Matches are rare, so most windows can be discarded by counting "bad" letters: with a cut d0 on the per-tap
@@ -183,7 +187,8 @@ int mepp_scan_bitpar(const uint32_t* sym_T_dev, const float* zhat_dev,
                      void* x_planes_dev, double* rowstats_dev, int32_t* count_dev, int32_t* density_dev,
                      void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
                      void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev, int32_t* row_nnz_dev,
-                     const uint32_t* planes_T_dev, const uint32_t* bp_dev, int32_t* bp_scratch_dev, void* stream);
+                     const uint32_t* planes_T_dev, const uint32_t* bp_dev, int32_t* bp_scratch_dev,
+                     const float* xscale_dev, void* stream);
 
 /* ---- lean scan for the sparse path (optional, MEPP_SCAN_LEAN=1; same reference code as mepp_scan) ----
  * The scan only finds and publishes matches (count, density, match list) and drops them into fixed-capacity buckets
@@ -327,9 +332,10 @@ int mepp_col_constants(const double* col_syz_dev, const double* ysum_dev, const 
 /* Same, with {sum zhat, sum zhat^2} read from device memory (no host synchronisation). */
 int mepp_col_constants_dev(const double* col_syz_dev, const double* ysum_dev, const double* zsum_dev, int64_t N, int C,
                            int use_z, double* colconst_dev, void* stream);
+/* xscale_dev / L: the per-task scales the scan wrote x_planes_dev with (float [m_rows / L]) or NULL. */
 int mepp_profile_corr_gemm(const void* x_planes_dev, const void* y_planes_dev, const double* rowstats_dev,
                            const double* colconst_dev, float* r_dev, int64_t m_rows, int C, int64_t n_pad,
-                           void* stream);
+                           const float* xscale_dev, int L, void* stream);
 
 /* ------------------------------------------------------------------ K3: permutation statistics
  * core.py:269-376 for T tasks of L positions and C = 1+P columns (r_dev: float [T*L][ldr]).

@@ -46,13 +46,14 @@ SIGNATURES = {
     "mepp_y_planes_bytes": (_i64, [_i32, _i64]),
     "mepp_pack_dna": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "mepp_build_y": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "mepp_x_scales": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "mepp_scan": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
-                         _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
+                         _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mepp_plane_words": (_i64, [_i32]),
     "mepp_pack_planes": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "mepp_scan_bitpar_tables": (_i32, [_vp, _vp, _vp, _vp, _i32, _f64, _vp, _vp]),
     "mepp_scan_bitpar": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
-                                _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mepp_scan_lean_bucket_bytes": (_i64, [_i32, _i64]),
     "mepp_scan_lean": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                               _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
@@ -84,7 +85,7 @@ SIGNATURES = {
     "mepp_correlation": (_i32, [_vp, _i64, _vp, _vp, _vp, _pd, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),
     "mepp_col_constants": (_i32, [_vp, _vp, _pd, _i64, _i32, _i32, _vp, _vp]),
     "mepp_col_constants_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
-    "mepp_profile_corr_gemm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _vp]),
+    "mepp_profile_corr_gemm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp]),
     "mepp_perm_stats_work_bytes": (_i64, [_i32, _i32, _i32]),
     "mepp_perm_stats": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i64, _i64,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

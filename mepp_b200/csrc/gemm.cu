@@ -48,6 +48,7 @@ struct GemmArgs {
   // fused correlation epilogue (stats.cu: col_constants_kernel): when colconst != nullptr the epilogue writes
   // r = nan_to_num(partial correlation) into S (as float [m_rows][ldS]) instead of the raw sums
   const double* rowstats; const double* colconst; int C;
+  const float* xscale; int L;   // per-task scale of the A operand (row / L = task); null: MEPP_X_SCALE
 };
 
 // Does k-block kb of the current item have to be loaded and multiplied?  Yes if one of its two K=16
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const Gem
             row_den = 1.0 / sqrt(1.0 - r_xz * r_xz);
           }
           const int col0 = (int)(nt * (int64_t)BN) + h * 128;
+          const double inv_xs = g.xscale ? 1.0 / (double)__ldg(g.xscale + row / g.L) : 1.0 / (double)MEPP_X_SCALE;
 #pragma unroll
           for (int c0 = 0; c0 < 128; c0 += 4) {
             if (h * 128 + c0 < BN) {
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) profile_gemm_kernel(const Gem
                 const int c = col0 + c0 + j;
                 float out = 0.0f;
                 if (c < g.C) {
-                  const double sxy = (double)sum[c0 + j] * (1.0 / (double)MEPP_X_SCALE);
+                  const double sxy = (double)sum[c0 + j] * inv_xs;
                   double r = (n * sxy - sxsy) * inv_xy;
                   if (use_z) r = (r - r_xz * __ldg(cc + 8 + 2 * c)) * row_den * __ldg(cc + 9 + 2 * c);
                   out = (float)r;
@@ -551,7 +553,7 @@ __global__ void gemm_check_kernel(const uint8_t* __restrict__ A, const uint8_t* 
 
 static int launch_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float* out_dev, int64_t m_rows,
                                int C, int64_t n_pad, const double* rowstats_dev, const double* colconst_dev,
-                               void* stream) {
+                               const float* xscale_dev, int L, void* stream) {
   using namespace mepp;
   MEPP_REQUIRE(x_planes_dev && y_planes_dev && out_dev, "profile_gemm: null pointer");
   MEPP_REQUIRE(m_rows > 0 && C > 0 && n_pad > 0 && n_pad % kBlockK == 0, "profile_gemm: bad shape");
@@ -566,6 +568,7 @@ static int launch_profile_gemm(const void* x_planes_dev, const void* y_planes_de
   g.ldS = (int64_t)g.n_tiles_n * g.BN;
   g.n_tiles_m = (int)((m_rows + kBlockM - 1) / kBlockM);
   g.rowstats = rowstats_dev; g.colconst = colconst_dev; g.C = C;
+  g.xscale = xscale_dev; g.L = L > 0 ? L : 1;
   const char* var = getenv("MEPP_GEMM_DESC_VARIANT");
   g.variant = var ? atoi(var) : 0;
   g.FW = (int)flag_words(g.KB);
@@ -603,14 +606,17 @@ extern "C" {
 
 int mepp_profile_gemm(const void* x_planes_dev, const void* y_planes_dev, float* S_dev, int64_t m_rows,
                       int C, int64_t n_pad, void* stream) {
-  return launch_profile_gemm(x_planes_dev, y_planes_dev, S_dev, m_rows, C, n_pad, nullptr, nullptr, stream);
+  return launch_profile_gemm(x_planes_dev, y_planes_dev, S_dev, m_rows, C, n_pad, nullptr, nullptr, nullptr, 0, stream);
 }
 
 int mepp_profile_corr_gemm(const void* x_planes_dev, const void* y_planes_dev, const double* rowstats_dev,
                            const double* colconst_dev, float* r_dev, int64_t m_rows, int C, int64_t n_pad,
-                           void* stream) {
+                           const float* xscale_dev, int L, void* stream) {
   if (!rowstats_dev || !colconst_dev) return mepp::fail("mepp_b200: profile_corr_gemm: null pointer");
-  return launch_profile_gemm(x_planes_dev, y_planes_dev, r_dev, m_rows, C, n_pad, rowstats_dev, colconst_dev, stream);
+  if (xscale_dev && (L <= 0 || m_rows % L != 0))
+    return mepp::fail("mepp_b200: profile_corr_gemm: per-task scales need L with m_rows = T * L");
+  return launch_profile_gemm(x_planes_dev, y_planes_dev, r_dev, m_rows, C, n_pad, rowstats_dev, colconst_dev, xscale_dev, L,
+                             stream);
 }
 
 int mepp_gemm_counters(unsigned long long* out2, int reset) {

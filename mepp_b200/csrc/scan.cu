@@ -70,6 +70,8 @@ struct ScanArgs {
   // {bucket, key, x0}; bucket_entries_kernel lists the buckets that overflowed and bucket_overflow_kernel redoes those
   // from both places.  ovf_count[0] = records, [1] = overflowed buckets.
   uint4* ovf; uint32_t* ovf_count; uint32_t ovf_cap; int32_t* ovf_bkts; uint32_t ovf_bkt_cap;
+  // tiled operand (optional): per-task power-of-two scale of the fp16 hi + lo pieces (mepp_x_scales); null = MEPP_X_SCALE
+  const float* xscale;
 };
 constexpr int kBucketCap = 64;   // matches per (task, k-block) bucket; more go to the overflow list (tensor-core scan) or
                                  // send the group through the full scan (CUDA-core lean scan)
@@ -277,11 +279,12 @@ __device__ __noinline__ void store_chunk(const ScanArgs& a, const TaskCtx& c, in
     }
     if (nz && a.x_planes) {
       uint32_t h[4], l[4];
+      const float xs = a.xscale ? __ldg(a.xscale + t) : (float)MEPP_X_SCALE;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         __half h0, l0, h1, l1;
-        split_half(xb[2 * q] * MEPP_X_SCALE, h0, l0);
-        split_half(xb[2 * q + 1] * MEPP_X_SCALE, h1, l1);
+        split_half(xb[2 * q] * xs, h0, l0);
+        split_half(xb[2 * q + 1] * xs, h1, l1);
         h[q] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
         l[q] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
       }
@@ -1255,7 +1258,7 @@ static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
                      int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
                      void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev,
                      int32_t* row_nnz_dev, const uint32_t* planes_T_dev, const uint32_t* bp_dev, int32_t* bp_scratch_dev,
-                     void* buckets_dev, int32_t* bucket_count_dev, void* stream) {
+                     void* buckets_dev, int32_t* bucket_count_dev, const float* xscale_dev, void* stream) {
   MEPP_REQUIRE(sym_T_dev && lut_dev && bias_dev && mlen_dev && nfilt_dev && qtab_dev && qthr_dev &&
                rowstats_dev && count_dev && density_dev, "scan: null pointer");
   MEPP_REQUIRE(x_planes_dev || entries_dev, "scan: neither the tiled operand nor the entry list was requested");
@@ -1295,6 +1298,7 @@ static int scan_impl(const uint32_t* sym_T_dev, const float* zhat_dev,
                "scan_lean: needs the bucket counters and the entry list, no tiled operand, no bit planes, L <= 65535");
   a.lean = lean ? 1 : 0; a.buckets = reinterpret_cast<uint2*>(buckets_dev); a.bucket_count = bucket_count_dev;
   a.ovf = nullptr; a.ovf_count = nullptr; a.ovf_cap = 0; a.ovf_bkts = nullptr; a.ovf_bkt_cap = 0;
+  a.xscale = xscale_dev;
   const int nbuf = 32 + 2 * margin;
   auto smem_bytes = [&](bool bp) {
     return (lean ? 0 : sizeof(float) * kScanWarps * ((units_dev || bitpar) ? 2 : 1) * nbuf * kRowStride) +
@@ -1372,11 +1376,11 @@ extern "C" int mepp_scan(const uint32_t* sym_T_dev, const float* zhat_dev,
                          void* x_planes_dev, double* rowstats_dev, int32_t* count_dev,
                          int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
                          void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev,
-                         int32_t* row_nnz_dev, void* stream) {
+                         int32_t* row_nnz_dev, const float* xscale_dev, void* stream) {
   return mepp::scan_impl(sym_T_dev, zhat_dev, N, L, T, margin, lut_dev, bias_dev, mlen_dev, nfilt_dev, qtab_dev, qthr_dev,
                          units_dev, n_units, max_motif_len, x_planes_dev, rowstats_dev, count_dev, density_dev, hits_dev,
                          hits_cap, hit_count_dev, entries_dev, entry_cap, entry_count_dev, row_nnz_dev, nullptr, nullptr,
-                         nullptr, nullptr, nullptr, stream);
+                         nullptr, nullptr, nullptr, xscale_dev, stream);
 }
 
 extern "C" int mepp_scan_bitpar(const uint32_t* sym_T_dev, const float* zhat_dev,
@@ -1387,12 +1391,12 @@ extern "C" int mepp_scan_bitpar(const uint32_t* sym_T_dev, const float* zhat_dev
                                 int32_t* density_dev, void* hits_dev, int64_t hits_cap, unsigned long long* hit_count_dev,
                                 void* entries_dev, int64_t entry_cap, unsigned long long* entry_count_dev,
                                 int32_t* row_nnz_dev, const uint32_t* planes_T_dev, const uint32_t* bp_dev,
-                                int32_t* bp_scratch_dev, void* stream) {
+                                int32_t* bp_scratch_dev, const float* xscale_dev, void* stream) {
   MEPP_REQUIRE(planes_T_dev && bp_dev && bp_scratch_dev, "scan_bitpar: null pointer");
   return mepp::scan_impl(sym_T_dev, zhat_dev, N, L, T, margin, lut_dev, bias_dev, mlen_dev, nfilt_dev, qtab_dev, qthr_dev,
                          units_dev, n_units, max_motif_len, x_planes_dev, rowstats_dev, count_dev, density_dev, hits_dev,
                          hits_cap, hit_count_dev, entries_dev, entry_cap, entry_count_dev, row_nnz_dev, planes_T_dev,
-                         bp_dev, bp_scratch_dev, nullptr, nullptr, stream);
+                         bp_dev, bp_scratch_dev, nullptr, nullptr, xscale_dev, stream);
 }
 
 extern "C" int64_t mepp_scan_lean_bucket_bytes(int T, int64_t N) {
@@ -1411,7 +1415,7 @@ extern "C" int mepp_scan_lean(const uint32_t* sym_T_dev, const float* zhat_dev,
   return mepp::scan_impl(sym_T_dev, zhat_dev, N, L, T, margin, lut_dev, bias_dev, mlen_dev, nfilt_dev, qtab_dev, qthr_dev,
                          units_dev, n_units, max_motif_len, nullptr, rowstats_dev, count_dev, density_dev, hits_dev,
                          hits_cap, hit_count_dev, entries_dev, entry_cap, entry_count_dev, row_nnz_dev, nullptr, nullptr,
-                         nullptr, buckets_dev, bucket_count_dev, stream);
+                         nullptr, buckets_dev, bucket_count_dev, nullptr, stream);
 }
 
 extern "C" int mepp_scan_bitpar_tables(const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev,
@@ -1522,6 +1526,52 @@ __global__ void __launch_bounds__(128) tc_exact_kernel(const ScanArgs a, const u
 }
 }  // namespace mepp
 
+// Per-task power-of-two scale of the tiled operand: the largest s = 2^k with s * (largest possible score - threshold)
+// <= 16384, never below MEPP_X_SCALE.  The fp16 hi + lo pair carries ~22 bits only while lo is a normal fp16 number, i.e.
+// for s * xbar >~ 0.13: with the one global scale of 256, rows whose non-zeros are all below 5e-4 lost relative precision
+// (3e-5 in r, found by tools/gpu_fuzz.py); a task whose scores can only be small now gets a correspondingly larger scale.
+namespace mepp {
+__global__ void x_scales_kernel(const float* __restrict__ lut, const float* __restrict__ bias,
+                                const int32_t* __restrict__ mlen, const int32_t* __restrict__ nfilt, int T,
+                                float* __restrict__ xscale) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float* l = lut + (size_t)t * (MEPP_MAX_MOTIF_LEN * 8);
+  const int m = mlen[t], nf = nfilt[t];
+  double best = 0.0;
+  for (int f = 0; f < nf; ++f) {
+    double sm = 0.0;
+    for (int j = 0; j < m; ++j) {
+      double mx = -1e300;
+      for (int c = 0; c < 4; ++c) mx = fmax(mx, (double)l[(j * 4 + c) * 2 + f]);
+      sm += mx;
+    }
+    best = fmax(best, sm + (double)bias[t]);             // bias = float32(-threshold)
+  }
+  float s = (float)MEPP_X_SCALE;
+  if (best > 0.0) {
+    const double want = 16384.0 / (best * 1.001 + 1e-6);
+    int e = 0;
+    frexp(want, &e);                                     // want = f * 2^e, 0.5 <= f < 1: 2^(e-1) <= want
+    double p2 = ldexp(1.0, e - 1);
+    if (p2 > 16777216.0) p2 = 16777216.0;
+    if (p2 > (double)MEPP_X_SCALE) s = (float)p2;
+  }
+  xscale[t] = s;
+}
+}  // namespace mepp
+
+extern "C" int mepp_x_scales(const float* lut_dev, const float* bias_dev, const int32_t* mlen_dev, const int32_t* nfilt_dev,
+                             int T, float* xscale_dev, void* stream) {
+  using namespace mepp;
+  MEPP_REQUIRE(lut_dev && bias_dev && mlen_dev && nfilt_dev && xscale_dev && T > 0, "x_scales: bad arguments");
+  MEPP_REQUIRE(mepp_device_ok(), "x_scales: no sm_100 CUDA device (no CPU fallback)");
+  x_scales_kernel<<<(unsigned)((T + 127) / 128), 128, 0, as_stream(stream)>>>(lut_dev, bias_dev, mlen_dev, nfilt_dev, T,
+                                                                            xscale_dev);
+  MEPP_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // Optional per-launch timing of tc_scan_kernel (bench.py's roofline block): CUDA events on the launching stream around
 // every launch while enabled, and the int8 multiply-adds the launches issued.
 namespace mepp {
@@ -1609,6 +1659,7 @@ extern "C" int mepp_scan_tc(const uint32_t* sym_T_dev, const uint32_t* onehot_de
   a.entry_count = entry_count_dev; a.row_nnz = row_nnz_dev;
   a.planes_T = nullptr; a.bp = nullptr; a.unit_count = nullptr;
   a.lean = 1; a.buckets = reinterpret_cast<uint2*>(buckets_dev); a.bucket_count = bucket_count_dev;
+  a.xscale = nullptr;
   {
     uint8_t* ob = reinterpret_cast<uint8_t*>(work_dev) + ((work_bytes - kTcOvfBytes) & ~(int64_t)255);
     a.ovf_count = reinterpret_cast<uint32_t*>(ob);

@@ -1013,6 +1013,13 @@ class Engine:
         cap = int(hits_cap) if hits_cap else max(1 << 20, int(T * N * L * 2e-3))
         hits_d = self._buf(f'hits{slot}', cap * 16, torch.uint8)
         ev = self._mark(None, None)
+        # tiled operand: per-task power-of-two scale of the fp16 hi + lo pieces (mepp_x_scales), undone by the GEMM epilogue
+        xscale = None
+        if path == 'tensor' and self.fuse_correlation:
+            xscale = self._buf(f'xscale{slot}', (T,), torch.float32)
+            _lib.check(_lib.lib.mepp_x_scales(_ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), T, _ptr(xscale), st),
+                       "x_scales")
+            self.launches += 1
         scan_args = (_ptr(self.sym_T), _ptr(self.zhat), N, L, T, int(margin),
                      _ptr(lut_d), _ptr(bias_d), _ptr(mlen_d), _ptr(nfilt_d), _ptr(qtab_d), _ptr(qthr_d),
                      _ptr(units_d), n_units, int(mlen.max()), _ptr(x_planes), _ptr(rowstats), _ptr(count),
@@ -1046,12 +1053,12 @@ class Engine:
         elif bitpar_on:
             # units split by class on the device; the bit-parallel units and the pair-table units run as two launches
             bp_scratch = self._buf(f'bp_scratch{slot}', (4 * self.last_units + 2,), torch.int32)
-            _lib.check(_lib.lib.mepp_scan_bitpar(*scan_args, _ptr(self.planes_T), _ptr(bp_d), _ptr(bp_scratch), st),
-                       "scan_bitpar")
+            _lib.check(_lib.lib.mepp_scan_bitpar(*scan_args, _ptr(self.planes_T), _ptr(bp_d), _ptr(bp_scratch), _ptr(xscale),
+                                                 st), "scan_bitpar")
             self.launches += 3
             self.last_bp = (bp_d, bp_scratch, self.last_units)
         else:
-            _lib.check(_lib.lib.mepp_scan(*scan_args, st), "scan")
+            _lib.check(_lib.lib.mepp_scan(*scan_args, _ptr(xscale), st), "scan")
             self.launches += 1
             self.last_scan = 'full'
         if path == 'tensor':
@@ -1101,8 +1108,8 @@ class Engine:
                 ev = self._mark(ev, 'gemm')
             elif self.fuse_correlation:
                 _lib.check(_lib.lib.mepp_profile_corr_gemm(_ptr(x_planes), _ptr(self.y_planes), _ptr(rowstats),
-                                                           _ptr(self._colconst()), _ptr(r), m_rows, C_, self.n_pad, st),
-                           "profile_corr_gemm")
+                                                           _ptr(self._colconst()), _ptr(r), m_rows, C_, self.n_pad,
+                                                           _ptr(xscale), L, st), "profile_corr_gemm")
                 self.launches += 2
                 ev = self._mark(ev, 'gemm')
             else:

@@ -370,6 +370,41 @@ def test_heatmap_from_hits_equals_dense_block_max(cfg1):
 
 
 
+def test_tensor_path_keeps_rows_of_tiny_scores_within_the_gate():
+    """Regression for the precision hole of the tiled operand: with ONE global scale (256) the fp16 hi + lo pieces lost
+    relative precision on rows whose non-zeros are all tiny (scores barely above the threshold, large margins, few
+    sequences: 3e-5 relative in r, found by tools/gpu_fuzz.py).  With the per-task power-of-two scale (mepp_x_scales)
+    the randomised small cases stay inside the 1e-5 gate on the tensor path."""
+    from mepp_b200 import synth
+    rng = np.random.default_rng(20240)
+    eng = _engine()
+    eng.profile_path = 'tensor'
+    worst = 0.0
+    for case in range(40):
+        N = int(rng.integers(60, 300)); L = int(rng.integers(60, 300)); P = int(rng.choice([7, 33, 100]))
+        margin = int(rng.choice([2, 5, 16, 16]))
+        ascii_u8, scores = synth.synth_sequences(N, L, seed=int(rng.integers(1 << 30)), n_rate=0.01)
+        perm = synth.synth_permutations(N, P, seed=int(rng.integers(1 << 30)))
+        tasks = []
+        for m in (int(rng.integers(4, 20)) for _ in range(3)):
+            pwm = rng.dirichlet(np.full(4, float(rng.choice([0.05, 0.3, 1.0]))), size=m).T
+            tasks.append((pwm, str(rng.choice(['+', '-', '+/-']))))
+        eng.stage(ascii_u8, scores, perm, use_gc=True)
+        b = eng.profile(tasks, margin=margin, return_r=True)
+        assert set(eng.last_paths) == {'tensor'}
+        codes = staging.ascii_to_codes(ascii_u8)
+        Y = staging.permuted_scores(scores, perm)
+        z = staging.gc_ratio_global(codes)
+        for t, (pwm, o) in enumerate(tasks):
+            orc = profile.profile_task(codes, Y, z, pwm, o, margin=margin)
+            d = np.abs(b.r[t].astype(np.float64) - orc["r"].astype(np.float64))
+            scale = np.abs(orc["r"]).max(axis=-1, keepdims=True)
+            bound = 1e-5 * np.abs(orc["r"]) + 1e-5 * scale + 1e-12
+            worst = max(worst, float((d / bound).max()))
+            assert (d <= bound).all(), (case, t, N, L, margin, float((d / bound).max()))
+    assert worst > 0.0
+
+
 def test_device_heatmap_equals_dense_block_max(cfg1):
     """mepp_heatmap (clip at mean + sigma * std of the non-zero scores, block maximum down to the pixel
     grid, on the device from the match list) against the dense restatement of plot.py:32-66,106-145.  Unclipped pixels

@@ -36,7 +36,7 @@ st = eng._stream()
 def scan():
     _lib.check(_lib.lib.mepp_scan(_ptr(eng.sym_T), _ptr(eng.zhat), N, L, T, cfg["margin"], _ptr(lut), _ptr(bias), _ptr(mlen),
                                   _ptr(nfilt), _ptr(qtab), _ptr(qthr), _ptr(units), len(units_h), int(mlen_h.max()),
-                                  _ptr(x), _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits), cap, _ptr(hit_count), None, 0, None, None, st), "scan")
+                                  _ptr(x), _ptr(rowstats), _ptr(count), _ptr(density), _ptr(hits), cap, _ptr(hit_count), None, 0, None, None, None, st), "scan")
 
 def reset():
     _lib.check(_lib.lib.mepp_x_planes_reset(_ptr(x), _ptr(hits), cap, _ptr(hit_count), N, L, T, cfg["margin"], st), "reset")
