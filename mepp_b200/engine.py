@@ -97,7 +97,8 @@ def _copy_pool(n):
     return _COPY_POOLS[n]
 
 
-SPARSE_DENSITY_MAX = 5e-3     # expected non-zero fraction of X up to which the sparse profile path is used
+SPARSE_DENSITY_MAX = 5e-3     # expected non-zero fraction of X up to which the sparse profile path is used (entry form)
+SPARSE_MATCH_DENSITY_MAX = 1.5e-3   # expected matches per window up to which it is used (match-driven form)
 SPARSE_ENTRY_DENSITY = 8e-3   # capacity of the entry list as a fraction of T * N * L
 SPARSE_SMALL_ENTRIES = 4e6    # expected non-zeros per group below which the sparse path is used whatever the density
 MIN_ENTRY_CAP = 1 << 20
@@ -682,10 +683,10 @@ class Engine:
         return DeviceTables(dev, host, 0, T)
 
     def choose_path(self, tables, margin):
-        """'sparse' (gather of Y rows per non-zero of X) or 'tensor' (tcgen05 GEMM over the tiled operand).
-        The sparse path costs ~4 (1 + P) bytes of L2 traffic per non-zero, the GEMM the same whatever X holds:
-        with the reference's p = 1e-4 threshold X is ~1e-3 dense and the sparse path wins by ~4x; the
-        break-even is near 5e-3."""
+        """'sparse' (gather of Y rows per match, or per non-zero of X in the entry form) or 'tensor' (tcgen05 GEMM over
+        the tiled operand).  The sparse path costs ~4 (1 + P) bytes of traffic per record, the GEMM the same whatever
+        X holds: with the reference's p = 1e-4 threshold the sparse path wins by far; a dense X (large --motifpvalue
+        with the flags honoured) goes to the tensor cores."""
         self._density_est = 0.0
         if self.profile_path in ('sparse', 'tensor'):
             return self.profile_path
@@ -698,9 +699,14 @@ class Engine:
             pv = max((tb.get('pvalue', 1e-4) * tb['n_filters'] for tb in tables), default=1e-4)
         density = pv * (2 * int(margin) + 1)
         self._density_est = density
-        # small problems always take the sparse path (it is exact in x and its cost is negligible there); the tiled
-        # fp16 operands lose precision on rows of tiny scores, which only average out over many sequences
+        # small problems always take the sparse path (it is exact in x and its cost is negligible there)
         small = density * len(tables) * self.N * self.L <= SPARSE_SMALL_ENTRIES
+        if self.sparse_matches:
+            # the match-driven form gathers one row of Y per MATCH, whatever the margin: measured on a cfg 2-sized
+            # dataset (tools/gpu_dense_check.py) it is 3x faster than the GEMM at 1.6e-3 matches per window (p = 1e-3,
+            # two strands, margin 5: 26 vs 84 us per task) and breaks even near 7e-3; the limit is set where the buckets
+            # of the match publication (64 per task and 32 sequences) start to overflow as a rule
+            return 'sparse' if pv <= SPARSE_MATCH_DENSITY_MAX or small else 'tensor'
         return 'sparse' if density <= SPARSE_DENSITY_MAX or small else 'tensor'
 
     def _colconst(self, sparse=False):
