@@ -536,6 +536,211 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan4_kernel(const __grid_co
   }
 }
 
+// ---- four-stage form with one issuer per stage ------------------------------------------------------------------------
+// The issuing thread of tc_scan4_kernel is a chain of long-latency instructions (try_wait ~90 cycles, every tcgen05.mma
+// ~100, commit ~60, ...: ~1200 cycles per N-tile of its own, profiles/r02_tc_scan_stamps.log), so two issuers keep the
+// tensor pipe 20 % busy.  Here stage = issuer = epilogue group: N-tile number s of the CTA's running sequence belongs to
+// issuer s % 4, which owns accumulator stage s % 4 and hands it to epilogue group s % 4 -- four independent
+// (issuer, stage, group) pipelines that share only the stream ring and the tensor pipe, each with one private pair of
+// barriers in strict alternation.  An issuer only waits for / releases the stream tiles it has an N-tile of.
+// The first attempt at this (21 warps under one register cap of 80) spilled in the epilogue; here the warps sit on
+// warpgroup boundaries and trade registers with setmaxnreg: warps 0-3 issuers, warp 4 producer (5-7 idle), both
+// warpgroups at 40 registers, warps 8-23 epilogue at 96.  No debug stamps: the production loop carries no extra loads.
+constexpr int kTc4iThreads = 32 * (8 + kTcEpiWarps);
+constexpr int kTcDefaultIssuers = 2;      // (4 once measured faster: MEPP_TC_ISSUERS)
+
+template <bool PACK>
+__global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid_constant__ TcLaunch ln,
+                                                                   const __grid_constant__ TcScanArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b_pad = (ln.b_bytes + 1023u) & ~1023u;
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + b_pad;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(sA + kTcStages * kTcStageBytes);   // [kTcStages]
+  uint64_t* aempty = afull + kTcStages;                                            // [kTcStages]
+  uint64_t* tfull = aempty + kTcStages;                                            // [kTc4Stages]
+  uint64_t* tempty = tfull + kTc4Stages;                                           // [kTc4Stages]
+  uint64_t* bfull = tempty + kTc4Stages;                                           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  __shared__ uint4 s_nt[kTcMaxTiles];
+  const int n_tiles = ln.n_tiles;
+  // issuers with an N-tile of any one stream tile: consecutive N-tile numbers go to different issuers
+  const uint32_t n_release = n_tiles < kTc4Stages ? (uint32_t)n_tiles : (uint32_t)kTc4Stages;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(smem_u32(&afull[s]), 1); mbar_init(smem_u32(&aempty[s]), n_release); }
+    for (int s = 0; s < kTc4Stages; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), 4); }
+    mbar_init(smem_u32(bfull), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(kTc4Stages * kTc4Cols)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 5 && lane < n_tiles) {
+    const TcTile tl = ln.tiles[lane];
+    const uint32_t bn = tl.bn;
+    const uint32_t idesc = (2u << 4) | (1u << 10) | ((bn >> 3) << 17) | ((uint32_t)(kTcRowsPerTile >> 4) << 24);
+    s_nt[lane] = make_uint4((((smem_u32(sB) + tl.b_off) & 0x3FFFFu) >> 4) | (bn << 16), idesc, tl.ksteps, 2u * bn);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t a_bytes = 2048u + 32u * (uint32_t)ln.ks_max;
+  const uint32_t park_ns = (uint32_t)g.mode >> 8;
+  // stream tiles of this CTA: blockIdx.x, + gridDim.x, ...; its N-tiles are numbered mt * n_tiles + nt
+  const uint32_t my_mtiles = (uint32_t)((g.n_mtiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+  if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    if (warp == 4) {
+      // ---------------------------------------------------------- producer
+      if (lane == 0) {
+        const uint32_t bb = smem_u32(bfull);
+        mbar_expect_tx(bb, ln.b_bytes);
+        for (uint32_t off = 0; off < ln.b_bytes; off += 32768u) {
+          const uint32_t n = ln.b_bytes - off < 32768u ? ln.b_bytes - off : 32768u;
+          bulk_g2s(smem_u32(sB + off), g.B + off, n, bb);
+        }
+        uint32_t stage = 0, phase = 0;
+        for (int64_t tile = blockIdx.x; tile < g.n_mtiles; tile += gridDim.x) {
+          mbar_wait_parked(smem_u32(&aempty[stage]), phase ^ 1u, park_ns);
+          const uint32_t fb = smem_u32(&afull[stage]);
+          mbar_expect_tx(fb, a_bytes);
+          bulk_g2s(smem_u32(sA + stage * kTcStageBytes), g.onehot + tile * 2048, a_bytes, fb);
+          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp < kTc4Stages) {
+      // ---------------------------------------------------------- MMA issuer of stage `me` (N-tiles me, me + 4, ...)
+      const uint32_t me = (uint32_t)warp;
+      const uint32_t kDescHi = 8u | (1u << 14);
+      mbar_wait_parked(smem_u32(bfull), 0u, park_ns);
+      tc_fence_after();
+      const bool issuer = lane == 0;
+      const uint32_t a_lo_base = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t tfull_me = smem_u32(&tfull[me]), tempty_me = smem_u32(&tempty[me]);
+      const uint32_t d_tmem = tmem_base + me * kTc4Cols;
+      uint32_t mt = 0, nt = me, use = 0, mt_ready = 0xffffffffu;
+      while (nt >= (uint32_t)n_tiles) { nt -= (uint32_t)n_tiles; ++mt; }
+      while (mt < my_mtiles) {
+        const uint32_t stage = mt % (uint32_t)kTcStages;
+        if (mt != mt_ready) {
+          mbar_wait_parked(smem_u32(&afull[stage]), (mt / (uint32_t)kTcStages) & 1u, park_ns);
+          mt_ready = mt;
+        }
+        const uint4 c = s_nt[nt];
+        mbar_wait(tempty_me, (use & 1u) ^ 1u);
+        ++use;
+        tc_fence_after();
+        // this issuer's next N-tile: in another stream tile -> this one is released behind the products
+        uint32_t mt2 = mt, nt2 = nt + (uint32_t)kTc4Stages;
+        while (nt2 >= (uint32_t)n_tiles) { nt2 -= (uint32_t)n_tiles; ++mt2; }
+        if (issuer) {
+          const uint32_t a_lo = a_lo_base + stage * (uint32_t)(kTcStageBytes / 16);
+#pragma unroll
+          for (uint32_t ks = 0; ks < 5; ++ks)
+            if (ks < c.z)
+              tc_mma_i8(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + 2u * ks), ((uint64_t)kDescHi << 32) | (c.x + ks * c.w),
+                        c.y, ks > 0 ? 1u : 0u);
+          tc_commit(tfull_me);
+          if (mt2 != mt) tc_commit(smem_u32(&aempty[stage]));
+        }
+        __syncwarp();
+        mt = mt2; nt = nt2;
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;" ::: "memory");
+    // ------------------------------------------------------------ epilogue (warps 8..23): group = stage
+    const unsigned full = 0xffffffffu;
+    const int ew = warp - 8, q = warp & 3, gidx = ew >> 2;
+    uint32_t my_count = 0, use = 0;
+    const int64_t list = (int64_t)blockIdx.x * kTcEpiWarps + ew;
+    uint2* const my_list = g.cand + list * (int64_t)g.list_cap;
+    const uint32_t tfull_me = smem_u32(&tfull[gidx]), tempty_me = smem_u32(&tempty[gidx]);
+    const uint32_t t_me = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)gidx * kTc4Cols;
+    uint32_t mt = 0, nt = (uint32_t)gidx;
+    while (nt >= (uint32_t)n_tiles) { nt -= (uint32_t)n_tiles; ++mt; }
+    while (mt < my_mtiles) {
+      const uint32_t row = (uint32_t)(((int64_t)blockIdx.x + (int64_t)mt * gridDim.x) * kTcRowsPerTile) + (uint32_t)(q * 32 + lane);
+      const int nc = (int)(s_nt[nt].w >> 6);                      // 32-column chunks of this N-tile (<= 4)
+      mbar_wait_parked(tfull_me, use & 1u, park_ns);
+      ++use;
+      tc_fence_after();
+      uint32_t v[4][PACK ? 16 : 32];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < nc) {
+          if constexpr (PACK) tmem_ld16p_nowait(t_me + (uint32_t)(k * 32), v[k]);
+          else tmem_ld32_nowait(t_me + (uint32_t)(k * 32), v[k]);
+        }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_me);
+      constexpr int NV = PACK ? 16 : 32;
+      uint32_t hasm = 0u;                      // bit k: some accumulator of this row in chunk k is non-negative
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k >= nc) break;
+        uint32_t t = v[k][0];
+#pragma unroll
+        for (int j = 1; j < NV; ++j) t &= v[k][j];
+        const bool has = PACK ? (t & 0x80008000u) != 0x80008000u : (int32_t)t >= 0;
+        hasm |= has ? 1u << k : 0u;
+      }
+      if (__any_sync(full, hasm != 0u)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k >= nc) break;
+          unsigned bal = __ballot_sync(full, (hasm >> k) & 1u);      // lanes (rows) with a candidate in chunk k
+          if (bal == 0u) continue;
+          uint32_t cm = 0u;                    // bit p: (unit p / 4 of the chunk, phase p % 4) passes on a strand
+          if ((hasm >> k) & 1u) {
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+              bool pass;
+              if constexpr (PACK) pass = (v[k][p] & 0x80008000u) != 0x80008000u;
+              else pass = (int32_t)(v[k][2 * p] & v[k][2 * p + 1]) >= 0;
+              if (pass) cm |= 1u << p;
+            }
+          }
+          const uint32_t ubase = ((uint32_t)ln.tiles[nt].unit0 + (uint32_t)k * 4u) << 2;
+          while (bal != 0u) {
+            const int src = __ffs((int)bal) - 1;
+            bal &= bal - 1u;
+            const int n = __popc(__shfl_sync(full, cm, src));
+            if (lane == src) {
+              uint32_t slot = my_count;
+              while (cm != 0u) {
+                const int p = __ffs((int)cm) - 1;
+                cm &= cm - 1u;
+                if (slot < g.list_cap) my_list[slot] = make_uint2(row, ubase + (uint32_t)p);
+                ++slot;
+              }
+            }
+            my_count += (uint32_t)n;
+          }
+        }
+      }
+      nt += (uint32_t)kTc4Stages;
+      while (nt >= (uint32_t)n_tiles) { nt -= (uint32_t)n_tiles; ++mt; }
+    }
+    if (lane == 0) g.cand_count[list] = my_count;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(kTc4Stages * kTc4Cols)) : "memory");
+  }
+}
+
 // One CTA per (N-tile, unit slot): the 8 columns (4 phases x 2 filters) of one scan unit, or never-passing columns for
 // the padding slots of the tile.
 __global__ void __launch_bounds__(128) tc_weights_kernel(const __grid_constant__ TcLaunch ln, const float* __restrict__ lut,
@@ -635,7 +840,12 @@ int tc_scan_launch(const TcLaunch& ln, const TcScanArgs& a, cudaStream_t st) {
   if (tc_units_per_tile() == 16) {
     for (int k = 0; k < ln.n_tiles; ++k)
       MEPP_REQUIRE(ln.tiles[k].bn <= kTc4Cols, "scan_tc: N-tile wider than an accumulator stage of the four-stage form");
-    if (pack) {
+    // MEPP_TC_ISSUERS=4: one issuer per accumulator stage (tc_scan4i_kernel); 2: two issuers (tc_scan4_kernel)
+    static const int issuers = [] { const char* e = getenv("MEPP_TC_ISSUERS"); return e ? atoi(e) : kTcDefaultIssuers; }();
+    if (issuers == 4 && pack && a.dbg_acc == nullptr && a.dbg_clk == nullptr && (a.mode & 255) == 0) {
+      MEPP_CUDA_CHECK(cudaFuncSetAttribute(tc_scan4i_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc_scan4i_kernel<true><<<grid, kTc4iThreads, smem, st>>>(ln, a);
+    } else if (pack) {
       MEPP_CUDA_CHECK(cudaFuncSetAttribute(tc_scan4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       tc_scan4_kernel<true><<<grid, kTcThreads, smem, st>>>(ln, a);
     } else {
