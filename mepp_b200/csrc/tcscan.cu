@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan4_kernel(const __grid_co
 constexpr int kTc4iThreads = 32 * (8 + kTcEpiWarps);
 constexpr int kTcDefaultIssuers = 2;      // (4 once measured faster: MEPP_TC_ISSUERS)
 
-template <bool PACK>
+template <bool PACK, int MODE>      // MODE (timing experiments, MEPP_TC_MODE): 1 no TMEM reads / tests, 2 no products
 __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid_constant__ TcLaunch ln,
                                                                    const __grid_constant__ TcScanArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -564,6 +564,7 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
   uint64_t* bfull = tempty + kTc4Stages;                                           // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
   __shared__ uint4 s_nt[kTcMaxTiles];
+  __shared__ uint32_t s_cnt[kTcEpiWarps];      // candidates of every epilogue warp's list so far
   const int n_tiles = ln.n_tiles;
   // issuers with an N-tile of any one stream tile: consecutive N-tile numbers go to different issuers
   const uint32_t n_release = n_tiles < kTc4Stages ? (uint32_t)n_tiles : (uint32_t)kTc4Stages;
@@ -580,6 +581,7 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
                  ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(kTc4Stages * kTc4Cols)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp == 6 && lane < kTcEpiWarps) s_cnt[lane] = 0u;
   if (warp == 5 && lane < n_tiles) {
     const TcTile tl = ln.tiles[lane];
     const uint32_t bn = tl.bn;
@@ -644,7 +646,7 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
           const uint32_t a_lo = a_lo_base + stage * (uint32_t)(kTcStageBytes / 16);
 #pragma unroll
           for (uint32_t ks = 0; ks < 5; ++ks)
-            if (ks < c.z)
+            if (ks < c.z && !(MODE & 2))
               tc_mma_i8(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + 2u * ks), ((uint64_t)kDescHi << 32) | (c.x + ks * c.w),
                         c.y, ks > 0 ? 1u : 0u);
           tc_commit(tfull_me);
@@ -659,7 +661,7 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
     // ------------------------------------------------------------ epilogue (warps 8..23): group = stage
     const unsigned full = 0xffffffffu;
     const int ew = warp - 8, q = warp & 3, gidx = ew >> 2;
-    uint32_t my_count = 0, use = 0;
+    uint32_t use = 0;
     const int64_t list = (int64_t)blockIdx.x * kTcEpiWarps + ew;
     uint2* const my_list = g.cand + list * (int64_t)g.list_cap;
     const uint32_t tfull_me = smem_u32(&tfull[gidx]), tempty_me = smem_u32(&tempty[gidx]);
@@ -675,7 +677,7 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
       uint32_t v[4][PACK ? 16 : 32];
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (k < nc) {
+        if (k < nc && !(MODE & 1) && !((MODE & 8) && k >= 2)) {
           if constexpr (PACK) tmem_ld16p_nowait(t_me + (uint32_t)(k * 32), v[k]);
           else tmem_ld32_nowait(t_me + (uint32_t)(k * 32), v[k]);
         }
@@ -687,51 +689,44 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
       uint32_t hasm = 0u;                      // bit k: some accumulator of this row in chunk k is non-negative
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (k >= nc) break;
+        if (k >= nc || (MODE & 5) || ((MODE & 8) && k >= 2)) break;
         uint32_t t = v[k][0];
 #pragma unroll
         for (int j = 1; j < NV; ++j) t &= v[k][j];
         const bool has = PACK ? (t & 0x80008000u) != 0x80008000u : (int32_t)t >= 0;
         hasm |= has ? 1u << k : 0u;
       }
-      if (__any_sync(full, hasm != 0u)) {
+      // ~70 % of the (warp, N-tile) items hold a candidate somewhere, so this is the COMMON path: only the lanes (rows)
+      // with a candidate enter it, there is no warp-wide vote / shuffle in it, and a lane reserves its slots of the
+      // warp's list with one shared-memory atomic per chunk
+      if (hasm != 0u) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (k >= nc) break;
-          unsigned bal = __ballot_sync(full, (hasm >> k) & 1u);      // lanes (rows) with a candidate in chunk k
-          if (bal == 0u) continue;
+          if (!((hasm >> k) & 1u)) continue;
           uint32_t cm = 0u;                    // bit p: (unit p / 4 of the chunk, phase p % 4) passes on a strand
-          if ((hasm >> k) & 1u) {
 #pragma unroll
-            for (int p = 0; p < 16; ++p) {
-              bool pass;
-              if constexpr (PACK) pass = (v[k][p] & 0x80008000u) != 0x80008000u;
-              else pass = (int32_t)(v[k][2 * p] & v[k][2 * p + 1]) >= 0;
-              if (pass) cm |= 1u << p;
-            }
+          for (int p = 0; p < 16; ++p) {
+            bool pass;
+            if constexpr (PACK) pass = (v[k][p] & 0x80008000u) != 0x80008000u;
+            else pass = (int32_t)(v[k][2 * p] & v[k][2 * p + 1]) >= 0;
+            if (pass) cm |= 1u << p;
           }
           const uint32_t ubase = ((uint32_t)ln.tiles[nt].unit0 + (uint32_t)k * 4u) << 2;
-          while (bal != 0u) {
-            const int src = __ffs((int)bal) - 1;
-            bal &= bal - 1u;
-            const int n = __popc(__shfl_sync(full, cm, src));
-            if (lane == src) {
-              uint32_t slot = my_count;
-              while (cm != 0u) {
-                const int p = __ffs((int)cm) - 1;
-                cm &= cm - 1u;
-                if (slot < g.list_cap) my_list[slot] = make_uint2(row, ubase + (uint32_t)p);
-                ++slot;
-              }
-            }
-            my_count += (uint32_t)n;
+          uint32_t slot = atomicAdd(&s_cnt[ew], (uint32_t)__popc(cm));
+          while (cm != 0u) {
+            const int p = __ffs((int)cm) - 1;
+            cm &= cm - 1u;
+            if (slot < g.list_cap) my_list[slot] = make_uint2(row, ubase + (uint32_t)p);
+            ++slot;
           }
         }
       }
       nt += (uint32_t)kTc4Stages;
       while (nt >= (uint32_t)n_tiles) { nt -= (uint32_t)n_tiles; ++mt; }
     }
-    if (lane == 0) g.cand_count[list] = my_count;
+    __syncwarp();
+    if (lane == 0) g.cand_count[list] = s_cnt[ew];
   }
   tc_fence_before();
   __syncthreads();
@@ -842,9 +837,14 @@ int tc_scan_launch(const TcLaunch& ln, const TcScanArgs& a, cudaStream_t st) {
       MEPP_REQUIRE(ln.tiles[k].bn <= kTc4Cols, "scan_tc: N-tile wider than an accumulator stage of the four-stage form");
     // MEPP_TC_ISSUERS=4: one issuer per accumulator stage (tc_scan4i_kernel); 2: two issuers (tc_scan4_kernel)
     static const int issuers = [] { const char* e = getenv("MEPP_TC_ISSUERS"); return e ? atoi(e) : kTcDefaultIssuers; }();
-    if (issuers == 4 && pack && a.dbg_acc == nullptr && a.dbg_clk == nullptr && (a.mode & 255) == 0) {
-      MEPP_CUDA_CHECK(cudaFuncSetAttribute(tc_scan4i_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      tc_scan4i_kernel<true><<<grid, kTc4iThreads, smem, st>>>(ln, a);
+    if (issuers == 4 && pack && a.dbg_acc == nullptr && a.dbg_clk == nullptr && (a.mode & 255) <= 15) {
+      // (modes: 1 no TMEM reads / tests, 2 no products, 4 reads but no tests, 8 half of the reads)
+      const int md = a.mode & 15;
+      auto fn = md == 0 ? tc_scan4i_kernel<true, 0> : md == 1 ? tc_scan4i_kernel<true, 1> : md == 2 ? tc_scan4i_kernel<true, 2>
+              : md == 3 ? tc_scan4i_kernel<true, 3> : md == 4 ? tc_scan4i_kernel<true, 4> : md == 8 ? tc_scan4i_kernel<true, 8>
+              : tc_scan4i_kernel<true, 12>;
+      MEPP_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      fn<<<grid, kTc4iThreads, smem, st>>>(ln, a);
     } else if (pack) {
       MEPP_CUDA_CHECK(cudaFuncSetAttribute(tc_scan4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       tc_scan4_kernel<true><<<grid, kTcThreads, smem, st>>>(ln, a);
