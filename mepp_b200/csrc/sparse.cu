@@ -535,7 +535,9 @@ int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_cou
   // (grids: measured.  The narrow form reads 2.5 GB of HBM per cfg 3 launch for the 0.4 GB of Y -- its later waves of
   // CTAs start again at slab 0 -- but a grid of exactly the resident CTAs, one sweep, was no faster (4.46 vs 4.37 ms
   // per step: the rows are too uneven for a static deal over 4.7 k warps); the wide form gained 3 % from it.  A dynamic
-  // deal -- warps taking 16 consecutive rows at a time from one counter, slab-major -- was much slower (7.5 ms).)
+  // deal -- warps taking 16 consecutive rows at a time from one counter, slab-major -- was much slower (7.5 ms), and so
+  // was one launch per slab (every wave of a launch on the same 51 MB of Y: 5.4 vs 4.4 ms -- eight short launches with
+  // their tails cost more than the re-reads).)
   static const int sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
                               return n > 0 ? n : 148; }();
   if (narrow) {

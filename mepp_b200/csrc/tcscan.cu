@@ -547,9 +547,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_scan4_kernel(const __grid_co
 // warpgroup boundaries and trade registers with setmaxnreg: warps 0-3 issuers, warp 4 producer (5-7 idle), both
 // warpgroups at 40 registers, warps 8-23 epilogue at 96.  No debug stamps: the production loop carries no extra loads.
 constexpr int kTc4iThreads = 32 * (8 + kTcEpiWarps);
-constexpr int kTcDefaultIssuers = 2;      // (4 once measured faster: MEPP_TC_ISSUERS)
+constexpr int kTcDefaultIssuers = 4;      // one issuer per accumulator stage (MEPP_TC_ISSUERS=2: tc_scan4_kernel)
+constexpr int kTcDefaultSplit = 1;
+int tc_issuers();
+int tc_split();
 
-template <bool PACK, int MODE>      // MODE (timing experiments, MEPP_TC_MODE): 1 no TMEM reads / tests, 2 no products
+// SPLIT = 2: every (issuer, epilogue group) pipeline owns TWO half-stages of 64 columns and alternates between them
+// (N-tiles of <= 64 columns = 8 scan units), so the issuer fills one half while the group drains the other: the time per
+// item is the larger of the two sides instead of their sum.
+template <bool PACK, int MODE, int SPLIT>      // MODE (timing experiments, MEPP_TC_MODE): 1 no TMEM reads / tests, 2 no products
 __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid_constant__ TcLaunch ln,
                                                                    const __grid_constant__ TcScanArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -559,9 +565,11 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
   uint8_t* sA = smem + b_pad;
   uint64_t* afull = reinterpret_cast<uint64_t*>(sA + kTcStages * kTcStageBytes);   // [kTcStages]
   uint64_t* aempty = afull + kTcStages;                                            // [kTcStages]
-  uint64_t* tfull = aempty + kTcStages;                                            // [kTc4Stages]
-  uint64_t* tempty = tfull + kTc4Stages;                                           // [kTc4Stages]
-  uint64_t* bfull = tempty + kTc4Stages;                                           // [1]
+  constexpr int kAcc = kTc4Stages * SPLIT;          // accumulator (half-)stages
+  constexpr uint32_t kCols = (uint32_t)(kTc4Cols / SPLIT);
+  uint64_t* tfull = aempty + kTcStages;                                            // [kAcc]
+  uint64_t* tempty = tfull + kAcc;                                                 // [kAcc]
+  uint64_t* bfull = tempty + kAcc;                                                 // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
   __shared__ uint4 s_nt[kTcMaxTiles];
   __shared__ uint32_t s_cnt[kTcEpiWarps];      // candidates of every epilogue warp's list so far
@@ -571,7 +579,7 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) { mbar_init(smem_u32(&afull[s]), 1); mbar_init(smem_u32(&aempty[s]), n_release); }
-    for (int s = 0; s < kTc4Stages; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), 4); }
+    for (int s = 0; s < kAcc; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), 4); }
     mbar_init(smem_u32(bfull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -586,7 +594,8 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
     const TcTile tl = ln.tiles[lane];
     const uint32_t bn = tl.bn;
     const uint32_t idesc = (2u << 4) | (1u << 10) | ((bn >> 3) << 17) | ((uint32_t)(kTcRowsPerTile >> 4) << 24);
-    s_nt[lane] = make_uint4((((smem_u32(sB) + tl.b_off) & 0x3FFFFu) >> 4) | (bn << 16), idesc, tl.ksteps, 2u * bn);
+    s_nt[lane] = make_uint4((((smem_u32(sB) + tl.b_off) & 0x3FFFFu) >> 4) | (bn << 16), idesc,
+                            (uint32_t)tl.ksteps | ((uint32_t)tl.unit0 << 16), 2u * bn);
   }
   tc_fence_before();
   __syncthreads();
@@ -619,37 +628,51 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
       }
     } else if (warp < kTc4Stages) {
       // ---------------------------------------------------------- MMA issuer of stage `me` (N-tiles me, me + 4, ...)
-      const uint32_t me = (uint32_t)warp;
+      // The issuing thread's time is instruction latency (ncu source page: ~190 dependent instructions per N-tile at ~7
+      // cycles each), so everything it touches is kept warp-uniform for the compiler -- the warp index comes from a
+      // broadcast, the N-tile's constants from the kernel parameters (constant bank) instead of shared memory, the
+      // K-step loop runs `ksteps` times instead of five predicated bodies -- and the descriptors advance by one add.
+      const uint32_t me = __shfl_sync(0xffffffffu, (uint32_t)warp, 0);
       const uint32_t kDescHi = 8u | (1u << 14);
       mbar_wait_parked(smem_u32(bfull), 0u, park_ns);
       tc_fence_after();
-      const bool issuer = lane == 0;
+      const bool issuer = elect_one();
       const uint32_t a_lo_base = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
-      const uint32_t tfull_me = smem_u32(&tfull[me]), tempty_me = smem_u32(&tempty[me]);
-      const uint32_t d_tmem = tmem_base + me * kTc4Cols;
+      const uint32_t b_lo_base = smem_u32(sB);
+      const uint32_t tfull_me = smem_u32(&tfull[me * SPLIT]), tempty_me = smem_u32(&tempty[me * SPLIT]);
+      const uint32_t d_tmem_me = tmem_base + me * kTc4Cols;
+      const uint32_t nt_n = (uint32_t)n_tiles;
       uint32_t mt = 0, nt = me, use = 0, mt_ready = 0xffffffffu;
-      while (nt >= (uint32_t)n_tiles) { nt -= (uint32_t)n_tiles; ++mt; }
+      while (nt >= nt_n) { nt -= nt_n; ++mt; }
       while (mt < my_mtiles) {
         const uint32_t stage = mt % (uint32_t)kTcStages;
         if (mt != mt_ready) {
           mbar_wait_parked(smem_u32(&afull[stage]), (mt / (uint32_t)kTcStages) & 1u, park_ns);
           mt_ready = mt;
         }
-        const uint4 c = s_nt[nt];
-        mbar_wait(tempty_me, (use & 1u) ^ 1u);
+        const TcTile tl = ln.tiles[nt];
+        const uint32_t bn = tl.bn, ksteps = tl.ksteps;
+        const uint32_t idesc = (2u << 4) | (1u << 10) | ((bn >> 3) << 17) | ((uint32_t)(kTcRowsPerTile >> 4) << 24);
+        uint32_t b_lo = (((b_lo_base + tl.b_off) & 0x3FFFFu) >> 4) | (bn << 16);
+        uint32_t a_lo = a_lo_base + stage * (uint32_t)(kTcStageBytes / 16);
+        // item `use` of this pipeline: half-stage use % SPLIT, its use number use / SPLIT
+        const uint32_t hs = SPLIT == 2 ? (use & 1u) : 0u;
+        mbar_wait(tempty_me + 8u * hs, ((use / (uint32_t)SPLIT) & 1u) ^ 1u);
+        const uint32_t d_tmem = d_tmem_me + hs * kCols;
         ++use;
         tc_fence_after();
         // this issuer's next N-tile: in another stream tile -> this one is released behind the products
         uint32_t mt2 = mt, nt2 = nt + (uint32_t)kTc4Stages;
-        while (nt2 >= (uint32_t)n_tiles) { nt2 -= (uint32_t)n_tiles; ++mt2; }
+        while (nt2 >= nt_n) { nt2 -= nt_n; ++mt2; }
         if (issuer) {
-          const uint32_t a_lo = a_lo_base + stage * (uint32_t)(kTcStageBytes / 16);
-#pragma unroll
-          for (uint32_t ks = 0; ks < 5; ++ks)
-            if (ks < c.z && !(MODE & 2))
-              tc_mma_i8(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + 2u * ks), ((uint64_t)kDescHi << 32) | (c.x + ks * c.w),
-                        c.y, ks > 0 ? 1u : 0u);
-          tc_commit(tfull_me);
+          if (!(MODE & 2)) {
+            tc_mma_i8(d_tmem, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, 0u);
+            for (uint32_t ks = 1; ks < ksteps; ++ks) {
+              a_lo += 2u; b_lo += 2u * bn;
+              tc_mma_i8(d_tmem, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, 1u);
+            }
+          }
+          tc_commit(tfull_me + 8u * hs);
           if (mt2 != mt) tc_commit(smem_u32(&aempty[stage]));
         }
         __syncwarp();
@@ -659,24 +682,27 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 96;" ::: "memory");
     // ------------------------------------------------------------ epilogue (warps 8..23): group = stage
-    const unsigned full = 0xffffffffu;
     const int ew = warp - 8, q = warp & 3, gidx = ew >> 2;
     uint32_t use = 0;
     const int64_t list = (int64_t)blockIdx.x * kTcEpiWarps + ew;
     uint2* const my_list = g.cand + list * (int64_t)g.list_cap;
-    const uint32_t tfull_me = smem_u32(&tfull[gidx]), tempty_me = smem_u32(&tempty[gidx]);
-    const uint32_t t_me = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)gidx * kTc4Cols;
+    const uint32_t tfull_me = smem_u32(&tfull[gidx * SPLIT]), tempty_me = smem_u32(&tempty[gidx * SPLIT]);
+    const uint32_t t_grp = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)gidx * kTc4Cols;
     uint32_t mt = 0, nt = (uint32_t)gidx;
     while (nt >= (uint32_t)n_tiles) { nt -= (uint32_t)n_tiles; ++mt; }
     while (mt < my_mtiles) {
       const uint32_t row = (uint32_t)(((int64_t)blockIdx.x + (int64_t)mt * gridDim.x) * kTcRowsPerTile) + (uint32_t)(q * 32 + lane);
-      const int nc = (int)(s_nt[nt].w >> 6);                      // 32-column chunks of this N-tile (<= 4)
-      mbar_wait_parked(tfull_me, use & 1u, park_ns);
+      const uint4 cst = s_nt[nt];
+      const int nc = (int)(cst.w >> 6);                           // 32-column chunks of this N-tile (<= 4)
+      const uint32_t hs = SPLIT == 2 ? (use & 1u) : 0u;
+      mbar_wait_parked(tfull_me + 8u * hs, (use / (uint32_t)SPLIT) & 1u, park_ns);
+      const uint32_t t_me = t_grp + hs * kCols;
       ++use;
       tc_fence_after();
-      uint32_t v[4][PACK ? 16 : 32];
+      constexpr int kChunksMax = 4 / SPLIT;
+      uint32_t v[kChunksMax][PACK ? 16 : 32];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < kChunksMax; ++k)
         if (k < nc && !(MODE & 1) && !((MODE & 8) && k >= 2)) {
           if constexpr (PACK) tmem_ld16p_nowait(t_me + (uint32_t)(k * 32), v[k]);
           else tmem_ld32_nowait(t_me + (uint32_t)(k * 32), v[k]);
@@ -684,24 +710,37 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_me);
+      if (lane == 0) mbar_arrive(tempty_me + 8u * hs);
       constexpr int NV = PACK ? 16 : 32;
       uint32_t hasm = 0u;                      // bit k: some accumulator of this row in chunk k is non-negative
+      if (!(MODE & 5)) {
+        if (nc == kChunksMax) {                // full N-tile: straight-line code, the chunks' AND trees interleave
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k >= nc || (MODE & 5) || ((MODE & 8) && k >= 2)) break;
-        uint32_t t = v[k][0];
+          for (int k = 0; k < kChunksMax; ++k) {
+            uint32_t t = v[k][0];
 #pragma unroll
-        for (int j = 1; j < NV; ++j) t &= v[k][j];
-        const bool has = PACK ? (t & 0x80008000u) != 0x80008000u : (int32_t)t >= 0;
-        hasm |= has ? 1u << k : 0u;
+            for (int j = 1; j < NV; ++j) t &= v[k][j];
+            const bool has = PACK ? (t & 0x80008000u) != 0x80008000u : (int32_t)t >= 0;
+            hasm |= has ? 1u << k : 0u;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kChunksMax; ++k) {
+            if (k >= nc || ((MODE & 8) && k >= 2)) break;
+            uint32_t t = v[k][0];
+#pragma unroll
+            for (int j = 1; j < NV; ++j) t &= v[k][j];
+            const bool has = PACK ? (t & 0x80008000u) != 0x80008000u : (int32_t)t >= 0;
+            hasm |= has ? 1u << k : 0u;
+          }
+        }
       }
       // ~70 % of the (warp, N-tile) items hold a candidate somewhere, so this is the COMMON path: only the lanes (rows)
       // with a candidate enter it, there is no warp-wide vote / shuffle in it, and a lane reserves its slots of the
       // warp's list with one shared-memory atomic per chunk
       if (hasm != 0u) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kChunksMax; ++k) {
           if (k >= nc) break;
           if (!((hasm >> k) & 1u)) continue;
           uint32_t cm = 0u;                    // bit p: (unit p / 4 of the chunk, phase p % 4) passes on a strand
@@ -712,7 +751,7 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
             else pass = (int32_t)(v[k][2 * p] & v[k][2 * p + 1]) >= 0;
             if (pass) cm |= 1u << p;
           }
-          const uint32_t ubase = ((uint32_t)ln.tiles[nt].unit0 + (uint32_t)k * 4u) << 2;
+          const uint32_t ubase = ((cst.z >> 16) + (uint32_t)k * 4u) << 2;
           uint32_t slot = atomicAdd(&s_cnt[ew], (uint32_t)__popc(cm));
           while (cm != 0u) {
             const int p = __ffs((int)cm) - 1;
@@ -800,8 +839,17 @@ __global__ void __launch_bounds__(128) tc_weights_kernel(const __grid_constant__
 
 // Scan units per N-tile: 16 (128 columns, four accumulator stages: tc_scan4_kernel, the default) or 32 (256 columns, two
 // stages: tc_scan_kernel; MEPP_TC_STAGES=2).
+int tc_issuers() {
+  static const int v = [] { const char* e = getenv("MEPP_TC_ISSUERS"); return e ? atoi(e) : kTcDefaultIssuers; }();
+  return v;
+}
+// 2: half-stages of 64 columns, two per (issuer, group) pipeline (tc_scan4i_kernel<.., 2>; MEPP_TC_SPLIT)
+int tc_split() {
+  static const int v = [] { const char* e = getenv("MEPP_TC_SPLIT"); return (e ? atoi(e) : kTcDefaultSplit) == 2 && tc_issuers() == 4 ? 2 : 1; }();
+  return v;
+}
 int tc_units_per_tile() {
-  static const int v = [] { const char* e = getenv("MEPP_TC_STAGES"); return (e && atoi(e) == 2) ? 32 : 16; }();
+  static const int v = [] { const char* e = getenv("MEPP_TC_STAGES"); return (e && atoi(e) == 2) ? 32 : tc_split() == 2 ? 8 : 16; }();
   return v;
 }
 
@@ -832,17 +880,19 @@ int tc_scan_launch(const TcLaunch& ln, const TcScanArgs& a, cudaStream_t st) {
   static const bool pack = [] { const char* e = getenv("MEPP_TC_PACK"); return e ? atoi(e) != 0 : true; }();
   int grid = tc_scan_grid();
   if ((int64_t)grid > a.n_mtiles) grid = (int)a.n_mtiles;
-  if (tc_units_per_tile() == 16) {
+  if (tc_units_per_tile() <= 16) {
     for (int k = 0; k < ln.n_tiles; ++k)
-      MEPP_REQUIRE(ln.tiles[k].bn <= kTc4Cols, "scan_tc: N-tile wider than an accumulator stage of the four-stage form");
+      MEPP_REQUIRE(ln.tiles[k].bn <= kTc4Cols / tc_split(), "scan_tc: N-tile wider than an accumulator stage of the four-stage form");
     // MEPP_TC_ISSUERS=4: one issuer per accumulator stage (tc_scan4i_kernel); 2: two issuers (tc_scan4_kernel)
-    static const int issuers = [] { const char* e = getenv("MEPP_TC_ISSUERS"); return e ? atoi(e) : kTcDefaultIssuers; }();
+    const int issuers = tc_issuers();
     if (issuers == 4 && pack && a.dbg_acc == nullptr && a.dbg_clk == nullptr && (a.mode & 255) <= 15) {
       // (modes: 1 no TMEM reads / tests, 2 no products, 4 reads but no tests, 8 half of the reads)
       const int md = a.mode & 15;
-      auto fn = md == 0 ? tc_scan4i_kernel<true, 0> : md == 1 ? tc_scan4i_kernel<true, 1> : md == 2 ? tc_scan4i_kernel<true, 2>
-              : md == 3 ? tc_scan4i_kernel<true, 3> : md == 4 ? tc_scan4i_kernel<true, 4> : md == 8 ? tc_scan4i_kernel<true, 8>
-              : tc_scan4i_kernel<true, 12>;
+      void (*fn)(const TcLaunch, const TcScanArgs);
+      if (tc_split() == 2) fn = md == 0 ? tc_scan4i_kernel<true, 0, 2> : md == 1 ? tc_scan4i_kernel<true, 1, 2> : md == 4 ? tc_scan4i_kernel<true, 4, 2> : tc_scan4i_kernel<true, 3, 2>;
+      else fn = md == 0 ? tc_scan4i_kernel<true, 0, 1> : md == 1 ? tc_scan4i_kernel<true, 1, 1> : md == 2 ? tc_scan4i_kernel<true, 2, 1>
+              : md == 3 ? tc_scan4i_kernel<true, 3, 1> : md == 4 ? tc_scan4i_kernel<true, 4, 1> : md == 8 ? tc_scan4i_kernel<true, 8, 1>
+              : tc_scan4i_kernel<true, 12, 1>;
       MEPP_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       fn<<<grid, kTc4iThreads, smem, st>>>(ln, a);
     } else if (pack) {

@@ -4,7 +4,7 @@
 
 namespace mepp {
 
-constexpr int kTcMaxTiles = 8;            // N-tiles (of <= 32 scan units = 256 columns) per launch
+constexpr int kTcMaxTiles = 16;           // N-tiles (of 8, 16 or 32 scan units = 64, 128 or 256 columns) per launch
 constexpr int kTcUnitsPerTile = 32;
 constexpr int kTcRowsPerTile = 128;       // windows (at a stride of four bases) per M-tile
 constexpr int kTcBasesPerTile = 4 * kTcRowsPerTile;
