@@ -62,6 +62,12 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// atomicAdd on a shared-memory word given by its shared::cta address; returns the old value.
+__device__ __forceinline__ uint32_t atoms_add(uint32_t saddr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {

@@ -682,16 +682,24 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 96;" ::: "memory");
     // ------------------------------------------------------------ epilogue (warps 8..23): group = stage
+    // The epilogue warps are bound by the LENGTH of their instruction stream (ncu source page: ~210 instructions per item
+    // at ~7 cycles each, 82 % of the time busy), and the compiler likes to rematerialise everything that derives from
+    // the thread index (S2R + address arithmetic in front of every tcgen05.ld / arrive): the loop invariants are pinned
+    // in registers (an empty asm the compiler cannot see through), the row number advances by addition.
     const int ew = warp - 8, q = warp & 3, gidx = ew >> 2;
     uint32_t use = 0;
     const int64_t list = (int64_t)blockIdx.x * kTcEpiWarps + ew;
-    uint2* const my_list = g.cand + list * (int64_t)g.list_cap;
-    const uint32_t tfull_me = smem_u32(&tfull[gidx * SPLIT]), tempty_me = smem_u32(&tempty[gidx * SPLIT]);
-    const uint32_t t_grp = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)gidx * kTc4Cols;
+    uint2* my_list = g.cand + list * (int64_t)g.list_cap;
+    uint32_t tfull_me = smem_u32(&tfull[gidx * SPLIT]), tempty_me = smem_u32(&tempty[gidx * SPLIT]);
+    uint32_t t_grp = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)gidx * kTc4Cols;
+    uint32_t cnt_me = smem_u32(&s_cnt[ew]);
+    uint32_t lane0 = lane == 0 ? 1u : 0u;
+    const uint32_t nt_n = (uint32_t)n_tiles, row_step = gridDim.x * (uint32_t)kTcRowsPerTile, list_cap = g.list_cap;
+    uint32_t row = blockIdx.x * (uint32_t)kTcRowsPerTile + (uint32_t)(q * 32 + lane);
+    asm volatile("" : "+r"(tfull_me), "+r"(tempty_me), "+r"(t_grp), "+r"(cnt_me), "+r"(lane0), "+r"(row), "+l"(my_list));
     uint32_t mt = 0, nt = (uint32_t)gidx;
-    while (nt >= (uint32_t)n_tiles) { nt -= (uint32_t)n_tiles; ++mt; }
+    while (nt >= nt_n) { nt -= nt_n; ++mt; row += row_step; }
     while (mt < my_mtiles) {
-      const uint32_t row = (uint32_t)(((int64_t)blockIdx.x + (int64_t)mt * gridDim.x) * kTcRowsPerTile) + (uint32_t)(q * 32 + lane);
       const uint4 cst = s_nt[nt];
       const int nc = (int)(cst.w >> 6);                           // 32-column chunks of this N-tile (<= 4)
       const uint32_t hs = SPLIT == 2 ? (use & 1u) : 0u;
@@ -701,16 +709,24 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
       tc_fence_after();
       constexpr int kChunksMax = 4 / SPLIT;
       uint32_t v[kChunksMax][PACK ? 16 : 32];
+      if (nc == kChunksMax && !(MODE & 9)) {          // full N-tile: the loads back to back
 #pragma unroll
-      for (int k = 0; k < kChunksMax; ++k)
-        if (k < nc && !(MODE & 1) && !((MODE & 8) && k >= 2)) {
+        for (int k = 0; k < kChunksMax; ++k) {
           if constexpr (PACK) tmem_ld16p_nowait(t_me + (uint32_t)(k * 32), v[k]);
           else tmem_ld32_nowait(t_me + (uint32_t)(k * 32), v[k]);
         }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kChunksMax; ++k)
+          if (k < nc && !(MODE & 1) && !((MODE & 8) && k >= 2)) {
+            if constexpr (PACK) tmem_ld16p_nowait(t_me + (uint32_t)(k * 32), v[k]);
+            else tmem_ld32_nowait(t_me + (uint32_t)(k * 32), v[k]);
+          }
+      }
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_me + 8u * hs);
+      if (lane0) mbar_arrive(tempty_me + 8u * hs);
       constexpr int NV = PACK ? 16 : 32;
       uint32_t hasm = 0u;                      // bit k: some accumulator of this row in chunk k is non-negative
       if (!(MODE & 5)) {
@@ -752,17 +768,17 @@ __global__ void __launch_bounds__(kTc4iThreads, 1) tc_scan4i_kernel(const __grid
             if (pass) cm |= 1u << p;
           }
           const uint32_t ubase = ((cst.z >> 16) + (uint32_t)k * 4u) << 2;
-          uint32_t slot = atomicAdd(&s_cnt[ew], (uint32_t)__popc(cm));
+          uint32_t slot = atoms_add(cnt_me, (uint32_t)__popc(cm));
           while (cm != 0u) {
             const int p = __ffs((int)cm) - 1;
             cm &= cm - 1u;
-            if (slot < g.list_cap) my_list[slot] = make_uint2(row, ubase + (uint32_t)p);
+            if (slot < list_cap) my_list[slot] = make_uint2(row, ubase + (uint32_t)p);
             ++slot;
           }
         }
       }
       nt += (uint32_t)kTc4Stages;
-      while (nt >= (uint32_t)n_tiles) { nt -= (uint32_t)n_tiles; ++mt; }
+      while (nt >= nt_n) { nt -= nt_n; ++mt; row += row_step; }
     }
     __syncwarp();
     if (lane == 0) g.cand_count[list] = s_cnt[ew];
