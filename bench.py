@@ -49,7 +49,9 @@ UNIT = "Gbp*motifs/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu --set full
 # capture of the same bench command (profiles/r02_kernels_ncu_summary.txt); null for workloads without a capture
-NCU_DRAM_BYTES_PER_LAUNCH = {("tc_scan4_kernel", "cfg3"): 413.4e6, ("scan_kernel", "cfg2"): 16.0e6}
+# (tc_scan4i_kernel: profiles/r02_tc4i_ncu_summary.txt; tc_scan4_kernel, MEPP_TC_ISSUERS=2: profiles/r02_kernels_ncu_summary.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = {("tc_scan4i_kernel", "cfg3"): 409.3e6, ("tc_scan4_kernel", "cfg3"): 413.4e6, ("scan_kernel", "cfg2"): 16.0e6}
+TC_KERNEL = "tc_scan4_kernel" if os.environ.get("MEPP_TC_ISSUERS", "4") == "2" else "tc_scan4i_kernel"
 
 
 def clocks_mhz_hint(peaks):
@@ -604,11 +606,15 @@ def main():
                 algorithmic_tops=alg / t_tc / 1e12,
                 algorithmic_note="SURVEY 8(d) compute-bound form: N * L * m * strands multiply-adds per task",
                 stream_gbs=tc_bytes.value / steps / t_tc / 1e9,
-                ncu="profiles/r02_kernels_ncu_summary.txt (cfg3): tensor pipe 20 % active, issue slots 53 % busy, DRAM 413 MB "
-                    "per launch (the one-hot stream, read once)",
-                limit="issue rate of the small MMAs (one thread gets a 128 x 128 x 32 product accepted every ~100 cycles) "
-                      "and the ~400 cycles an issuer spends between its batches (four accumulator stages of 128 TMEM "
-                      "columns, two issuers): DESIGN.md section 4")
+                kernel=TC_KERNEL,
+                ncu=("profiles/r02_tc4i_ncu_summary.txt (cfg3, tc_scan4i_kernel): tensor pipe ~45 % active, DRAM 409 MB per "
+                     "launch (the one-hot stream, read once)" if TC_KERNEL == "tc_scan4i_kernel" else
+                     "profiles/r02_kernels_ncu_summary.txt (cfg3, tc_scan4_kernel): tensor pipe 20 % active, issue slots 53 % "
+                     "busy, DRAM 413 MB per launch (the one-hot stream, read once)"),
+                limit="the length of the hand-over chain of an accumulator stage (issuer wake-up, tcgen05.mma issue, "
+                      "completion, epilogue wake-up, TMEM reads, release: four stages of 128 TMEM columns, one issuer and "
+                      "one epilogue group per stage) and the instruction stream of the epilogue warps; floors: TMEM reads "
+                      "at 256 B/clk/SM ~2.1 ms per cfg3 step, products ~1.2 ms: DESIGN.md section 4")
     if stage_ms.get("gemm") and sparse:
         # HBM: Y rows once (L2-resident afterwards), CSR records, r written once; L2 -> SM: one Y row per non-zero
         ldY = -(-C_ // 512) * 512
@@ -662,14 +668,14 @@ def main():
     # the dominant kernel of the step (the longest single kernel of the ncu launch list, profiles/)
     if "tc_scan_kernel" in kernels:
         dk = kernels["tc_scan_kernel"]
-        roofline = dict(kernel="tc_scan4_kernel", bound="tensor", achieved=dk["achieved"], peak=dk["peak"], unit=dk["unit"],
-                        frac=dk["frac"], traffic=NCU_DRAM_BYTES_PER_LAUNCH.get(("tc_scan4_kernel", args.workload)),
+        roofline = dict(kernel=TC_KERNEL, bound="tensor", achieved=dk["achieved"], peak=dk["peak"], unit=dk["unit"],
+                        frac=dk["frac"], traffic=NCU_DRAM_BYTES_PER_LAUNCH.get((TC_KERNEL, args.workload)),
                         peak_source=peaks["source"] + "; " + dk["peak_note"], ms_per_launch=dk["ms_per_launch"],
                         algorithmic=dk["algorithmic_tops"], share_of_step=dk["ms_per_step"] / (1e3 * dt_value / args.steps),
                         note="achieved = int8 multiply-adds issued by the launches x 2 / their CUDA-event time (events on the "
-                             "launching stream around every tc_scan4_kernel launch of a serial pass, mepp_scan_tc_timing); "
+                             "launching stream around every " + TC_KERNEL + " launch of a serial pass, mepp_scan_tc_timing); "
                              "algorithmic = 2 N L m strands per task / the same time; traffic = dram__bytes_read + write of "
-                             "one launch, ncu --set full of this command (profiles/r02_kernels_ncu_summary.txt)")
+                             "one launch, ncu --set full of this command (profiles/r02_tc4i_ncu_summary.txt)")
     else:
         dominant = "scan" if "scan" in kernels else next(iter(kernels))
         dk = kernels.get(dominant, {})

@@ -1105,21 +1105,23 @@ __global__ void __launch_bounds__(128) bucket_entries_kernel(const uint2* __rest
   owned(i, lo, hi, seq);
   owned(i2, lo2, hi2, seq2);
   cnt = max(hi - lo + 1, 0) + max(hi2 - lo2 + 1, 0);
-  // one slot reservation per warp in the k-block's sub-list
-  int pre = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(full, pre, o);
-    if (lane >= o) pre += v;
-  }
-  const int total = __shfl_sync(full, pre, 31);
-  if (total == 0) return;
-  const int list = kb & (MEPP_ENTRY_LISTS - 1);
   // entries == nullptr (match-driven profile, mepp_profile_matches): only the row sums are wanted
   const bool emit_entries = entries != nullptr;
+  const int list = kb & (MEPP_ENTRY_LISTS - 1);
   unsigned long long slot = 0ull;
-  if (emit_entries && lane == 0) slot = atomicAdd(entry_count + list * 16, (unsigned long long)total);
-  slot = __shfl_sync(full, slot, 0) + (unsigned long long)(pre - cnt);
+  if (emit_entries) {
+    // one slot reservation per warp in the k-block's sub-list
+    int pre = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(full, pre, o);
+      if (lane >= o) pre += v;
+    }
+    const int total = __shfl_sync(full, pre, 31);
+    if (total == 0) return;
+    if (lane == 0) slot = atomicAdd(entry_count + list * 16, (unsigned long long)total);
+    slot = __shfl_sync(full, slot, 0) + (unsigned long long)(pre - cnt);
+  }
   uint4* dst = reinterpret_cast<uint4*>(entries + (int64_t)list * sub_cap);
   auto emit = [&](int idx, int r_lo, int r_hi, int sq) {
     const int64_t ns = (int64_t)kb * 32 + sq;

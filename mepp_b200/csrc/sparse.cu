@@ -279,6 +279,7 @@ __global__ void match_fill_kernel(const HitRec4* __restrict__ hits, const unsign
   }
 }
 
+constexpr int kGatherMixDefault = 2;
 struct GatherArgs {
   const uint2* csr; const int32_t* offsets;
   const float* y_rows; int64_t ldY;
@@ -290,7 +291,9 @@ struct GatherArgs {
 // warps work on the same slab of Y at about the same time.  J = 4 (512 columns) when Y fits the L2 anyway; J = 1 when it
 // does not (cfg 3: 410 MB): a 128-column slab of Y is N * 512 bytes (51 MB), stays L2-resident while the rows of the
 // group pass over it, and the gather then reads HBM once per slab instead of once per match.
-template <int J>
+// MIX: two of the four conversions of a float4 go through the F2F pipe, two through the integer pipe (f2d): the two
+// pipes work side by side (MEPP_GATHER_MIX).
+template <int J, int MIX>      // MIX = conversions per float4 that take the F2F pipe (0 .. 4)
 __global__ void __launch_bounds__(256, J == 1 ? 4 : 3) match_gather_kernel(const __grid_constant__ GatherArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -328,10 +331,10 @@ __global__ void __launch_bounds__(256, J == 1 ? 4 : 3) match_gather_kernel(const
         const double x = (double)__uint_as_float(c[k].y);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-          acc[4 * j + 0] = fma(x, f2d(v[k][j].x), acc[4 * j + 0]);
-          acc[4 * j + 1] = fma(x, f2d(v[k][j].y), acc[4 * j + 1]);
-          acc[4 * j + 2] = fma(x, f2d(v[k][j].z), acc[4 * j + 2]);
-          acc[4 * j + 3] = fma(x, f2d(v[k][j].w), acc[4 * j + 3]);
+          acc[4 * j + 0] = fma(x, MIX >= 4 ? (double)v[k][j].x : f2d(v[k][j].x), acc[4 * j + 0]);
+          acc[4 * j + 1] = fma(x, MIX >= 3 ? (double)v[k][j].y : f2d(v[k][j].y), acc[4 * j + 1]);
+          acc[4 * j + 2] = fma(x, MIX >= 2 ? (double)v[k][j].z : f2d(v[k][j].z), acc[4 * j + 2]);
+          acc[4 * j + 3] = fma(x, MIX >= 1 ? (double)v[k][j].w : f2d(v[k][j].w), acc[4 * j + 3]);
         }
       }
 #pragma unroll
@@ -540,12 +543,19 @@ int mepp_profile_matches(const void* hits_dev, const unsigned long long* hit_cou
   // their tails cost more than the re-reads).)
   static const int sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
                               return n > 0 ? n : 148; }();
+  static const int mix = [] { const char* e = getenv("MEPP_GATHER_MIX"); return e ? atoi(e) : kGatherMixDefault; }();
   if (narrow) {
     g.n_slabs = (int)(g.ldY / 128);
-    match_gather_kernel<1><<<sms * 16, 256, 0, st>>>(g);
+    if (mix == 1) match_gather_kernel<1, 1><<<sms * 16, 256, 0, st>>>(g);
+    else if (mix == 2) match_gather_kernel<1, 2><<<sms * 16, 256, 0, st>>>(g);
+    else if (mix == 3) match_gather_kernel<1, 3><<<sms * 16, 256, 0, st>>>(g);
+    else match_gather_kernel<1, 0><<<sms * 16, 256, 0, st>>>(g);
   } else {
     g.n_slabs = (int)(g.ldY / kSlabCols);
-    match_gather_kernel<4><<<sms * 3, 256, 0, st>>>(g);
+    if (mix == 1) match_gather_kernel<4, 1><<<sms * 3, 256, 0, st>>>(g);
+    else if (mix == 2) match_gather_kernel<4, 2><<<sms * 3, 256, 0, st>>>(g);
+    else if (mix == 3) match_gather_kernel<4, 3><<<sms * 3, 256, 0, st>>>(g);
+    else match_gather_kernel<4, 0><<<sms * 3, 256, 0, st>>>(g);
   }
   BlurArgs a;
   a.S0 = S0; a.ldS0 = g.ldY; a.offsets = offsets; a.rowstats = rowstats_dev; a.colconst = colconst_dev;
