@@ -399,7 +399,7 @@ __global__ void radix_pick_kernel(const uint32_t* __restrict__ hist, int hists_p
 // 127 empty octaves (the search among the thresholds of a bin was 37 % of the pooled pass's instructions with 4096
 // bins from zero; with 16384 from t_min most bins hold no threshold and the rest one).
 // thr_par[t] = {bits(t_min), shift, number of zero thresholds, -}.
-constexpr int kNarrowBins = 16384;
+constexpr int kNarrowBins = 4096;    // (16384 measured too: see below)
 __global__ void thresholds_kernel(const float* __restrict__ r, int64_t ldr, int L, int C, int L_pow2,
                                   float* __restrict__ ts_sorted, uint16_t* __restrict__ tab, uint32_t* __restrict__ thr_par) {
   extern __shared__ uint32_t s_keys[];
