@@ -607,8 +607,8 @@ def main():
                 algorithmic_note="SURVEY 8(d) compute-bound form: N * L * m * strands multiply-adds per task",
                 stream_gbs=tc_bytes.value / steps / t_tc / 1e9,
                 kernel=TC_KERNEL,
-                ncu=("profiles/r02_tc4i_ncu_summary.txt (cfg3, tc_scan4i_kernel): tensor pipe ~45 % active, DRAM 409 MB per "
-                     "launch (the one-hot stream, read once)" if TC_KERNEL == "tc_scan4i_kernel" else
+                ncu=("profiles/r02_tc4i_ncu_summary.txt (cfg3, tc_scan4i_kernel): tensor pipe 44 % active, TMEM port 58 % busy, issue "
+                     "slots 56 % busy, DRAM 409 MB per launch (the one-hot stream, read once)" if TC_KERNEL == "tc_scan4i_kernel" else
                      "profiles/r02_kernels_ncu_summary.txt (cfg3, tc_scan4_kernel): tensor pipe 20 % active, issue slots 53 % "
                      "busy, DRAM 413 MB per launch (the one-hot stream, read once)"),
                 limit="the length of the hand-over chain of an accumulator stage (issuer wake-up, tcgen05.mma issue, "
