@@ -404,6 +404,13 @@ def test_tc_scan_pipeline_protocol_has_no_deadlock():
     for bns in cases:
         for seed in range(2):
             assert sim.run(40, bns, seed=seed), (bns, seed)
+    # tc_scan4i_kernel (one issuer per accumulator stage; an issuer releases only the stream tiles it has an N-tile of, so
+    # the ring's "empty" barriers count min(n_tiles, 4) arrivals), whole stages and the half-stage form
+    for n_tiles in range(1, 17):
+        for split in (1, 2):
+            assert sim.run4i(40, n_tiles, split=split, seed=n_tiles), (n_tiles, split)
+    # the simulation has teeth: with four expected releases per stream tile three N-tiles per tile starve the producer
+    assert not sim.run4i(40, 3, n_release=4, max_steps=200_000)
 
 
 def test_native_tsv_writer_is_byte_identical_to_pandas(tmp_path):

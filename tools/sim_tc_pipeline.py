@@ -68,6 +68,69 @@ def run(n_mtiles, bns, stages=16, seed=0, async_delay=True):
         except StopIteration: alive.remove(p)
     while pending: pending.pop(0).arrive()
     return True
+
+def run4i(n_mtiles, n_tiles, split=1, stages=16, seed=0, n_release=None, max_steps=5_000_000):
+    """The protocol of tc_scan4i_kernel: stage = issuer = epilogue group; N-tile number s = mt * n_tiles + nt of the CTA's
+    running sequence belongs to pipeline s % 4; an issuer only waits for / releases (tcgen05.commit on aempty) the stream
+    tiles it has an N-tile of, so aempty counts min(n_tiles, 4) arrivals; split = 2: two half-stages per pipeline, used in
+    turn.  Returns False on a deadlock; asserts on an arrival that would complete a phase twice."""
+    rnd = random.Random(seed)
+    n_release = min(n_tiles, 4) if n_release is None else n_release
+    afull = [MBar(1, f'afull{i}') for i in range(stages)]; aempty = [MBar(n_release, f'aempty{i}') for i in range(stages)]
+    tfull = [[MBar(1, f'tfull{i}.{h}') for h in range(split)] for i in range(4)]
+    tempty = [[MBar(4, f'tempty{i}.{h}') for h in range(split)] for i in range(4)]
+    pending = []
+    done_items = [0] * 4
+    def items(me):
+        mt, nt = 0, me
+        while nt >= n_tiles: nt -= n_tiles; mt += 1
+        while mt < n_mtiles:
+            mt2, nt2 = mt, nt + 4
+            while nt2 >= n_tiles: nt2 -= n_tiles; mt2 += 1
+            yield mt, nt, mt2
+            mt, nt = mt2, nt2
+    def producer():
+        stage = 0; phase = 0
+        for t in range(n_mtiles):
+            while not aempty[stage].done(phase ^ 1): yield
+            pending.append(afull[stage])
+            stage += 1
+            if stage == stages: stage = 0; phase ^= 1
+    def issuer(me):
+        use = 0; ready = -1
+        for mt, nt, mt2 in items(me):
+            stage = mt % stages
+            if mt != ready:
+                while not afull[stage].done((mt // stages) & 1): yield
+                ready = mt
+            hs = use % split
+            while not tempty[me][hs].done(((use // split) & 1) ^ 1): yield
+            use += 1
+            pending.append(tfull[me][hs])
+            if mt2 != mt: pending.append(aempty[stage])
+            yield
+    def epi(g, w):
+        use = 0
+        for mt, nt, mt2 in items(g):
+            hs = use % split
+            while not tfull[g][hs].done((use // split) & 1): yield
+            use += 1
+            yield
+            tempty[g][hs].arrive()
+            if w == 0: done_items[g] += 1
+            yield
+    procs = [producer()] + [issuer(i) for i in range(4)] + [epi(g, w) for g in range(4) for w in range(4)]
+    alive = list(procs); steps = 0
+    while alive:
+        steps += 1
+        if steps > max_steps: return False
+        if pending and rnd.random() < 0.5:
+            pending.pop(rnd.randrange(len(pending))).arrive(); continue
+        p = rnd.choice(alive)
+        try: next(p)
+        except StopIteration: alive.remove(p)
+    while pending: pending.pop(0).arrive()
+    return sum(done_items) == n_mtiles * n_tiles
 if __name__ == "__main__":
     rnd = random.Random(5)
     cases = [[256, 96], [64], [256], [256, 256, 128], [96, 64, 32], [256] * 8, [160, 256, 32, 224, 128]]
@@ -78,3 +141,5 @@ if __name__ == "__main__":
             if not run(60, bns, seed=seed):
                 print("FAILED", bns, seed); bad += 1
     print("cases", len(cases), "failures", bad)
+    bad4 = sum(not run4i(50, nt, split=sp, seed=sd) for nt in range(1, 17) for sp in (1, 2) for sd in range(2))
+    print("tc_scan4i protocol: failures", bad4)
