@@ -71,14 +71,14 @@ def synth_motifs(n_motifs, seed, m_lo=6, m_hi=20):
 
 
 def load_motif_library(name, fixtures=None):
-    """Motif library from tests/golden/motif_libraries.npz (made from the reference's data/ files by
-    tests/golden/make_motif_fixtures.py).  name in {'ohler', 'homer_clustered', 'homer'}.
+    """Motif library from mepp_b200/data/motif_libraries.npz: the libraries the reference ships in its data/ directory,
+    packaged with this path (made from those files by tests/golden/make_motif_fixtures.py).
+    name in {'ohler', 'homer_clustered', 'homer'}.
     Returns {key: (4, m) float64} with the reference's rule that a later duplicate key overwrites an
     earlier one (mepp/io.py:27-38) -- 164 headers -> 162 keys for 'homer_clustered'."""
     import os
     if fixtures is None:
-        fixtures = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden",
-                                "motif_libraries.npz")
+        fixtures = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "motif_libraries.npz")
     with np.load(fixtures) as z:
         keys, lens, flat = z[f"{name}__keys"], z[f"{name}__lens"], z[f"{name}__flat"]
     out, off = {}, 0

@@ -1,4 +1,5 @@
-"""Generates tests/golden/motif_libraries.npz from the reference's motif libraries.
+"""Generates mepp_b200/data/motif_libraries.npz (package data: bench / tests / synthetic workloads read the shipped
+libraries from there, not from tests/) from the reference's motif libraries.
 
 Run in the build container (needs /root/reference); the GPU box only has the committed
 .npz.  Stores, per library, the headers in FILE ORDER (duplicates kept, so the reference's
@@ -44,4 +45,4 @@ for lib, fn in LIBS.items():
     out[f"{lib}__lens"] = np.array([p.shape[1] for p in pw], dtype=np.int32)
     out[f"{lib}__flat"] = np.concatenate([p.ravel() for p in pw])
     print(lib, len(keys), "headers,", len(set(keys)), "unique keys")
-np.savez_compressed(os.path.join(os.path.dirname(__file__), "motif_libraries.npz"), **out)
+np.savez_compressed(os.path.join(os.path.dirname(__file__), "..", "..", "mepp_b200", "data", "motif_libraries.npz"), **out)
