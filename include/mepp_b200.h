@@ -221,7 +221,8 @@ int mepp_scan_lean(const uint32_t* sym_T_dev, const float* zhat_dev,
  * task, like units_dev) and of the motif lengths of all T tasks (the N-tile plan is made on the host).
  * work_dev: mepp_scan_tc_work_bytes(N, L, units) bytes of scratch (weights, candidate lists).
  * entries_dev may be NULL (match-driven profile, mepp_profile_matches: only the row sums are built from the buckets).
- * dbg_acc_dev (optional, int32 [128][dbg_ld]): raw accumulators of the first 128 windows, for bring-up tests. */
+ * dbg_acc_dev (optional, int32 [128][dbg_ld]): raw accumulators of the first 128 windows, for bring-up tests (such calls
+ * run the two-issuer kernel tc_scan4_kernel, which carries the dump; the default is tc_scan4i_kernel). */
 int64_t mepp_onehot_words(int64_t N, int L);
 int mepp_pack_onehot(const uint8_t* ascii_dev, int64_t N, int L, uint32_t* onehot_dev, void* stream);
 int64_t mepp_scan_tc_work_bytes(int64_t N, int L, int n_units);
@@ -245,7 +246,7 @@ int64_t mepp_heatmap_work_bytes(int T);
 int mepp_heatmap(const void* hits_dev, const unsigned long long* hit_count_dev, int64_t hits_cap, int T, int64_t N, int L,
                  int block_rows, int block_cols, float sigma, float* out_dev, void* work_dev, void* stream);
 
-/* Measurement hook (bench.py's roofline block): while enabled, every tc_scan_kernel launch of mepp_scan_tc is bracketed
+/* Measurement hook (bench.py's roofline block): while enabled, every tensor-core scan launch of mepp_scan_tc is bracketed
  * by CUDA events on its stream.  A call returns what was gathered since the previous call -- summed kernel time (it
  * waits for the recorded events), int8 multiply-adds issued (128 x columns x 32 per K-step and 512-base tile, padding
  * included), bytes of the one-hot stream read, launches -- clears it and sets the new state.  Outputs may be NULL. */

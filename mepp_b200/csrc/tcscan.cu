@@ -20,10 +20,12 @@
 // Survivors (~3e-4 of the windows) are appended to per-warp candidate lists; scan.cu evaluates them in the
 // canonical float32 order, so every reported score still comes from the exact path.
 //
-// Structure: persistent CTAs (one per SM), warp 0 = producer (cp.async.bulk of the weights once, then a 16-stage
-// ring of 2 KB stream tiles), warp 1 = TMEM allocator + MMA issuer, warps 2-17 = epilogue in four independent groups
-// (tcgen05.ld.pack::16b of a 4 x 128-column accumulator ring, AND-reduction of the sign bits, candidate compaction):
-// a barrier hand-over costs ~250 cycles whatever the work, so four N-tiles are in flight.
+// Structure: persistent CTAs (one per SM); a producer thread streams 2 KB tiles of F through a 16-stage cp.async.bulk
+// ring (the weights of the launch are loaded once), issuer threads feed the tensor pipe, epilogue warps read the signs
+// back (tcgen05.ld.pack::16b, AND trees, candidate lists).  Three kernels, newest last -- all give identical candidates:
+//   tc_scan_kernel    two accumulator stages of 256 columns, two issuers                      (MEPP_TC_STAGES=2)
+//   tc_scan4_kernel   four stages of 128 columns, two issuers, four epilogue groups           (MEPP_TC_ISSUERS=2)
+//   tc_scan4i_kernel  four stages, stage = issuer = epilogue group, uniform-datapath issue    (the default)
 #include "tcscan.cuh"
 #include "tcgen05.cuh"
 #include <stdlib.h>
