@@ -10,6 +10,9 @@ import pandas as pd
 from .dataset import ScoredDataset
 from .onehot_dna import get_degenerate_pct, seqs_to_ascii
 
+# byte -> 1 for every character that is not an upper-case A, C, G, T (onehot_dna.py:41-53)
+_NOT_ACGT_TABLE = bytes(0 if chr(b) in 'ACGT' else 1 for b in range(256))
+
 
 def force_cpu_only():
     """utils.py:32-38 switched TensorFlow to the CPU.  This engine has no CPU path."""
@@ -40,11 +43,14 @@ def filter_scored_fasta_df(scored_fasta_df, degenerate_pct_thresh=100, sequence_
     if sequence_length is not None and seqs:
         # all rows have one length now: the share of characters outside ACGT (upper case; onehot_dna.py:41-53) of every
         # sequence from one byte matrix instead of one Python call per sequence
-        try:
-            from .onehot_dna import _IS_ACGT
-            a = seqs_to_ascii(seqs, int(sequence_length))
-            df['degenerate_pct'] = 100.0 * (~_IS_ACGT[a]).sum(axis=1) / float(sequence_length)
-        except ValueError:                      # (rows of unequal byte length: per-sequence path)
+        # (one bytes.translate over the joined sequences marks the characters outside ACGT; summing the flags of a row
+        # counts them -- no index lookup per base)
+        L_ = int(sequence_length)
+        buf = ''.join(seqs).encode('latin-1', 'replace')
+        if len(buf) == len(seqs) * L_:
+            flags = np.frombuffer(buf.translate(_NOT_ACGT_TABLE), dtype=np.uint8).reshape(len(seqs), L_)
+            df['degenerate_pct'] = 100.0 * flags.sum(axis=1, dtype=np.int64) / float(sequence_length)
+        else:                                   # (rows of unequal byte length: per-sequence path)
             df['degenerate_pct'] = df['sequence'].map(get_degenerate_pct)
     else:
         df['degenerate_pct'] = df['sequence'].map(get_degenerate_pct)
