@@ -26,9 +26,11 @@ def manage_gpu_memory(device_index=None):
 
 def scored_fasta_dicts_to_df(sequence_dict, score_dict, description_dict):
     """utils.py:53-75 (a sequence without a score raises KeyError, like the reference)."""
-    return pd.DataFrame(
-        data=[(sid, seq, score_dict[sid], description_dict[sid]) for sid, seq in sequence_dict.items()],
-        columns=['sequence_id', 'sequence', 'score', 'description'])
+    ids = list(sequence_dict.keys())       # (column lists: pandas does not have to transpose 100 000 row tuples)
+    return pd.DataFrame({'sequence_id': ids, 'sequence': list(sequence_dict.values()),
+                         'score': [score_dict[sid] for sid in ids],
+                         'description': [description_dict[sid] for sid in ids]},
+                        columns=['sequence_id', 'sequence', 'score', 'description'])
 
 
 def filter_scored_fasta_df(scored_fasta_df, degenerate_pct_thresh=100, sequence_length='max'):
