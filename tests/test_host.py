@@ -171,6 +171,28 @@ def test_filter_order_dataset_roundtrip(tmp_path):
     assert np.array_equal(ds2.ascii, ds.ascii) and np.array_equal(ds2.perm_idx, ds.perm_idx) and ds2.has_gc
 
 
+def test_vectorised_degenerate_filter_equals_the_per_sequence_rule():
+    """filter_scored_fasta_df counts the characters outside upper-case ACGT of all sequences at once (one translate over
+    the joined bytes); it has to give exactly what onehot_dna.get_degenerate_pct -- the reference's per-sequence rule,
+    onehot_dna.py:41-53 -- gives, for lower case, N, IUPAC codes, digits and characters outside latin-1 alike."""
+    import pandas as pd
+    from mepp_b200 import utils, onehot_dna
+    rng = np.random.default_rng(3)
+    letters = list("ACGTacgtNnRYKM-*0 ") + ["\u00e9", "\u4e2d"]
+    seqs = ["".join(rng.choice(letters, size=40, p=None)) for _ in range(200)]
+    seqs[0] = "ACGT" * 10
+    df = pd.DataFrame({'sequence_id': [f"s{i}" for i in range(len(seqs))], 'sequence': seqs,
+                       'score': rng.normal(size=len(seqs)), 'description': [("s", "0")] * len(seqs)})
+    out = utils.filter_scored_fasta_df(df, degenerate_pct_thresh=100)
+    assert len(out) == len(seqs)
+    want = np.array([onehot_dna.get_degenerate_pct(s) for s in out['sequence']])
+    assert np.array_equal(out['degenerate_pct'].to_numpy(), want)
+    assert want[0] == 0.0 and want.max() > 50.0
+    for thr in (0, 25.0, 60.0):
+        kept = utils.filter_scored_fasta_df(df, degenerate_pct_thresh=thr)
+        assert list(kept['sequence']) == [s for s in seqs if onehot_dna.get_degenerate_pct(s) <= thr]
+
+
 def test_synthetic_generator_is_deterministic_and_shaped():
     from mepp_b200 import synth
     a = synth.make_config("cfg1", n_motifs=2)
